@@ -1,0 +1,18 @@
+# Builds the C-ABI shared library for sm_100a (no torch dependency).
+NVCC ?= nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
+SRC := distbo_b200/csrc/chol.cu distbo_b200/csrc/gram.cu distbo_b200/csrc/score.cu distbo_b200/csrc/embed.cu
+OBJ := $(SRC:.cu=.o)
+LIB := distbo_b200/libdistbo_b200.so
+
+all: $(LIB)
+
+%.o: %.cu distbo_b200/csrc/common.cuh distbo_b200/csrc/gemm_core.cuh include/distbo_b200.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+
+clean:
+	rm -f $(OBJ) $(LIB)

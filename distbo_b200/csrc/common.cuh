@@ -1,0 +1,60 @@
+// Shared device helpers for the distbo_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DISTBO_OK 0
+#define DISTBO_EARG (-1)
+#define DISTBO_ECUDA (-2)
+
+#define DB_CHECK_LAUNCH()                                                  \
+  do {                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                  \
+    if (e__ != cudaSuccess) return DISTBO_ECUDA;                           \
+  } while (0)
+
+#define DB_CUDA(x)                                                         \
+  do {                                                                     \
+    cudaError_t e__ = (x);                                                 \
+    if (e__ != cudaSuccess) return DISTBO_ECUDA;                           \
+  } while (0)
+
+namespace db {
+
+constexpr double kSqrt3 = 1.7320508075688772935;
+constexpr double kDistClamp = 1e-32;  // reference train/kernels.py:25
+constexpr double kVarClamp = 1e-32;   // reference train/gp_regressor.py:197
+
+// FP64 tensor-core MMA, D(8x8) += A(8x4) * B(4x8).  SASS: DMMA.8x8x4.
+// lane l holds a = A[l>>2][l&3], b = B[l&3][l>>2], c0/c1 = C[l>>2][2*(l&3)+{0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// Matern-3/2 from a squared distance, reference train/kernels.py:25-27.
+__device__ __forceinline__ double matern32_from_d2(double d2) {
+  double r = sqrt(fmax(d2, kDistClamp));
+  double v = kSqrt3 * r;
+  return (1.0 + v) * exp(-v);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace db

@@ -1,0 +1,165 @@
+// FP64 tensor-core (DMMA.8x8x4) tile GEMM core shared by the Cholesky / inverse / scoring stages.
+//
+// One CTA (256 threads, 8 warps as 2x4, warp tile 64x32) produces one 128x128 output tile
+//     C[m0:m0+128, n0:n0+128] = alpha * sum_{k in [k_lo,k_hi)} opA(m,k) * opB(k,n) + beta * Cin
+// from a tile descriptor (m0, n0, k_lo, k_hi) in GLOBAL matrix coordinates.  Operands are staged
+// global -> shared with a 4-stage cp.async (LDGSTS) pipeline; shared rows are padded (+4 doubles)
+// so that every m8n8k4 fragment load is bank-conflict free.  All dimensions are multiples of the
+// tile (the host pads every matrix to a multiple of 128 with an identity block), so the hot loop
+// has no bounds checks.  Triangular structure (SYRK lower tiles, TRMM/TRTRI/LAUUM k-ranges) is
+// expressed purely through the host-generated tile list.
+#pragma once
+#include "common.cuh"
+
+namespace db {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int STAGES = 4;
+constexpr int LDK = BK + 4;             // k-contiguous tile: [128][20]
+constexpr int LDX = BM + 4;             // row-contiguous tile: [16][132]
+constexpr int STAGE_ELEMS = BM * LDK;   // 2560 doubles (>= BK*LDX = 2112)
+constexpr int GEMM_SMEM_BYTES = STAGES * 2 * STAGE_ELEMS * (int)sizeof(double);  // 163840
+
+// Operand layouts in global memory (both row-major matrices with leading dimension ld):
+//   KMAJOR: element (x, k) at g[x*ld + k]   (x = m for A, n for B)  -> "A" / "B^T" style
+//   XMAJOR: element (x, k) at g[k*ld + x]                           -> "A^T" / "B" style
+enum { KMAJOR = 0, XMAJOR = 1 };
+
+template <int LAY>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int ld, int x0,
+                                          int k0, int tid) {
+  if (LAY == KMAJOR) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = tid + i * GEMM_THREADS;
+      int row = c >> 3, kc = c & 7;
+      cp_async16(s + row * LDK + kc * 2, g + (size_t)(x0 + row) * ld + k0 + kc * 2);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = tid + i * GEMM_THREADS;
+      int kr = c >> 6, xc = c & 63;
+      cp_async16(s + kr * LDX + xc * 2, g + (size_t)(k0 + kr) * ld + x0 + xc * 2);
+    }
+  }
+}
+
+template <int LAY>
+__device__ __forceinline__ double frag_ld(const double* s, int x, int k) {
+  return LAY == KMAJOR ? s[x * LDK + k] : s[k * LDX + x];
+}
+
+// acc[mi][ni][0..1]: warp tile 64x32 as 8x4 m8n8 sub-tiles.
+template <int ALAY, int BLAY>
+__device__ __forceinline__ void gemm_mainloop(double (&acc)[8][4][2], const double* __restrict__ A,
+                                              int lda, const double* __restrict__ B, int ldb, int m0,
+                                              int n0, int k_lo, int k_hi, double* smem) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lk = lane & 3;
+  double* sA = smem;
+  double* sB = smem + STAGES * STAGE_ELEMS;
+  const int nk = (k_hi - k_lo) / BK;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) {
+      load_tile<ALAY>(sA + s * STAGE_ELEMS, A, lda, m0, k_lo + s * BK, tid);
+      load_tile<BLAY>(sB + s * STAGE_ELEMS, B, ldb, n0, k_lo + s * BK, tid);
+    }
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int kn = kt + STAGES - 1;
+      if (kn < nk) {
+        int s = kn & (STAGES - 1);
+        load_tile<ALAY>(sA + s * STAGE_ELEMS, A, lda, m0, k_lo + kn * BK, tid);
+        load_tile<BLAY>(sB + s * STAGE_ELEMS, B, ldb, n0, k_lo + kn * BK, tid);
+      }
+      cp_async_commit();
+    }
+    const double* a = sA + (kt & (STAGES - 1)) * STAGE_ELEMS;
+    const double* b = sB + (kt & (STAGES - 1)) * STAGE_ELEMS;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi) af[mi] = frag_ld<ALAY>(a, wm * 64 + mi * 8 + lr, k4 * 4 + lk);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) bf[ni] = frag_ld<BLAY>(b, wn * 32 + ni * 8 + lr, k4 * 4 + lk);
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // all warps done with smem: safe to reuse it / to overwrite an in-place operand
+}
+
+struct GemmArgs {
+  const double* A;
+  const double* B;
+  double* C;
+  const double* Cin;  // may alias C; ignored when beta == 0
+  int lda, ldb, ldc, ldcin;
+  double alpha, beta;
+  const int4* tiles;  // (m0, n0, k_lo, k_hi)
+};
+
+template <int ALAY, int BLAY>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tiles_kernel(GemmArgs p) {
+  extern __shared__ __align__(16) double smem[];
+  const int4 t = p.tiles[blockIdx.x];
+  double acc[8][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+  gemm_mainloop<ALAY, BLAY>(acc, p.A, p.lda, p.B, p.ldb, t.x, t.y, t.z, t.w, smem);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lk = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi) {
+    const int row = t.x + wm * 64 + mi * 8 + lr;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int col = t.y + wn * 32 + ni * 8 + lk * 2;
+      double2 v;
+      v.x = p.alpha * acc[mi][ni][0];
+      v.y = p.alpha * acc[mi][ni][1];
+      if (p.beta != 0.0) {
+        const double2 c = *reinterpret_cast<const double2*>(p.Cin + (size_t)row * p.ldcin + col);
+        v.x += p.beta * c.x;
+        v.y += p.beta * c.y;
+      }
+      *reinterpret_cast<double2*>(p.C + (size_t)row * p.ldc + col) = v;
+    }
+  }
+}
+
+template <int ALAY, int BLAY>
+inline cudaError_t launch_gemm_tiles(const GemmArgs& p, int ntiles, cudaStream_t st) {
+  if (ntiles <= 0) return cudaSuccess;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tiles_kernel<ALAY, BLAY>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  gemm_tiles_kernel<ALAY, BLAY><<<ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace db

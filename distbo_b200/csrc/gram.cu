@@ -1,0 +1,446 @@
+// K2: Matern-3/2 product Gram over (theta, dataset embedding), its hyper-parameter gradient
+// contraction, the task-level (T x T) embedding Gram and its backward, and the TF-style Adam step.
+// Reference: train/kernels.py:19-28,58-88; train/log_gaus_likelihood.py:86-122; train/train.py:31-40.
+#include "../../include/distbo_b200.h"
+#include "common.cuh"
+
+namespace db {
+
+constexpr int DMAX = 16;  // max hyper-parameter dimension handled in registers
+
+// ------------------------------------------------------------------ theta / bandwidth scaling
+__global__ void scale_theta_kernel(const double* __restrict__ theta, int N, int d,
+                                   const double* __restrict__ log_bw, double* __restrict__ theta_s,
+                                   double* __restrict__ sqnorm, int n_rows_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows_out) return;
+  double s = 0.0;
+  for (int k = 0; k < d; ++k) {
+    double v = 0.0;
+    if (i < N) v = theta[(size_t)i * d + k] / exp(log_bw[k]);  // tf.divide(X, stddev), kernels.py:20
+    theta_s[(size_t)i * d + k] = v;
+    s += v * v;
+  }
+  sqnorm[i] = s;
+}
+
+// ------------------------------------------------------------------ task-level Gram  KE [T,T]
+// one warp per (t,t') pair, expanded-distance form as kernels.py:22-25
+__global__ void __launch_bounds__(256) task_gram_kernel(const double* __restrict__ E, int lde, int T,
+                                                        int P, const double* __restrict__ log_bw_embed,
+                                                        double* __restrict__ KE) {
+  const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pair >= T * T) return;
+  const int t = pair / T, u = pair % T;
+  double xy = 0.0, xx = 0.0, yy = 0.0;
+  for (int c = lane; c < P; c += 32) {
+    const double s = exp(log_bw_embed[c]);
+    const double a = E[(size_t)t * lde + c] / s, b = E[(size_t)u * lde + c] / s;
+    xy += a * b;
+    xx += a * a;
+    yy += b * b;
+  }
+  xy = warp_sum(xy);
+  xx = warp_sum(xx);
+  yy = warp_sum(yy);
+  if (lane == 0) KE[pair] = matern32_from_d2(-2.0 * xy + xx + yy);
+}
+
+// ------------------------------------------------------------------ N x N Gram, lower 128-tiles
+constexpr int GT = 128;  // tile edge
+__global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ theta_s,
+                                                   const double* __restrict__ sqnorm, int N, int n_pad,
+                                                   int d, const int32_t* __restrict__ task_id,
+                                                   const double* __restrict__ KE, int T,
+                                                   const double* __restrict__ log_scale,
+                                                   const double* __restrict__ log_sigma, double jitter,
+                                                   double* __restrict__ K) {
+  extern __shared__ __align__(16) double sm[];
+  // lower-triangular tile index -> (bi, bj), bj <= bi
+  int bi = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) ++bi;
+  while (bi * (bi + 1) / 2 > (int)blockIdx.x) --bi;
+  const int bj = blockIdx.x - bi * (bi + 1) / 2;
+  double* sI = sm;                 // [GT][d]   rows of the i block
+  double* sJt = sm + GT * d;       // [d][GT]   transposed rows of the j block
+  double* sqI = sJt + GT * d;      // [GT]
+  double* sqJ = sqI + GT;          // [GT]
+  int* tI = (int*)(sqJ + GT);      // [GT]
+  int* tJ = tI + GT;               // [GT]
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < GT * d; idx += 256) {
+    const int r = idx / d, k = idx % d;
+    sI[idx] = theta_s[(size_t)(bi * GT + r) * d + k];
+    sJt[k * GT + r] = theta_s[(size_t)(bj * GT + r) * d + k];
+  }
+  for (int r = tid; r < GT; r += 256) {
+    const int gi = bi * GT + r, gj = bj * GT + r;
+    sqI[r] = sqnorm[gi];
+    sqJ[r] = sqnorm[gj];
+    tI[r] = (gi < N && task_id) ? task_id[gi] : 0;
+    tJ[r] = (gj < N && task_id) ? task_id[gj] : 0;
+  }
+  __syncthreads();
+  const double scale = exp(*log_scale);
+  const double diag_add = exp(2.0 * (*log_sigma)) + jitter;
+  const int cg = (tid & 31) * 4;  // 4 consecutive columns per thread: a warp writes one 1 KB row
+  const int w = tid >> 5;
+  for (int r = w; r < GT; r += 8) {
+    const int gi = bi * GT + r;
+    double dot[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < d; ++k) {
+      const double xi = sI[r * d + k];
+      const double4 yj = *reinterpret_cast<const double4*>(sJt + k * GT + cg);
+      dot[0] += xi * yj.x;
+      dot[1] += xi * yj.y;
+      dot[2] += xi * yj.z;
+      dot[3] += xi * yj.w;
+    }
+    double out[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = cg + q, gj = bj * GT + c;
+      double v;
+      if (gi < N && gj < N) {
+        const double d2 = -2.0 * dot[q] + sqI[r] + sqJ[c];
+        v = scale * matern32_from_d2(d2);
+        if (KE) v *= KE[(size_t)tI[r] * T + tJ[c]];
+        if (gi == gj) v += diag_add;
+      } else {
+        v = (gi == gj) ? 1.0 : 0.0;
+      }
+      out[q] = v;
+    }
+    double* dst = K + (size_t)gi * n_pad + bj * GT + cg;
+    *reinterpret_cast<double2*>(dst) = make_double2(out[0], out[1]);
+    *reinterpret_cast<double2*>(dst + 2) = make_double2(out[2], out[3]);
+  }
+}
+
+// ------------------------------------------------------------------ gradient contraction (K2g)
+// One warp per row i (longest rows first).  With g_ij = Kinv_ij - alpha_i alpha_j (= 2 G_ij) and
+// weight 1 for j < i, 1/2 for j == i, the symmetric sums over all (i,j) are recovered.
+//   rowH [n_pad][T]   : R[i][t'] = sum_{j in t', j<=i} w g_ij scale ktheta_ij
+//   rowbw[n_pad][d]   : sum_j w g_ij scale KE_ij 3 exp(-v) delta_k^2
+//   rowsc[n_pad][3]   : {alpha_i, Kinv_ii, alpha_i^2}
+template <int D>
+__global__ void __launch_bounds__(256) gram_grad_rows_kernel(
+    const double* __restrict__ Kinv, const double* __restrict__ alpha, const double* __restrict__ theta_s,
+    const double* __restrict__ sqnorm, int N, int n_pad, int d, const int32_t* __restrict__ task_id,
+    const int32_t* __restrict__ task_off, const double* __restrict__ KE, int T,
+    const double* __restrict__ log_scale, double* __restrict__ rowH, double* __restrict__ rowbw,
+    double* __restrict__ rowsc) {
+  const int wglobal = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wglobal >= N) return;
+  const int i = N - 1 - wglobal;
+  const double scale = exp(*log_scale);
+  const int ti = task_id ? task_id[i] : 0;
+  const double ai = alpha[i], sqi = sqnorm[i];
+  double xi[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) xi[k] = (k < d) ? theta_s[(size_t)i * d + k] : 0.0;
+  double gbw[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) gbw[k] = 0.0;
+  const double* krow = Kinv + (size_t)i * n_pad;
+
+  for (int tp = 0; tp < T; ++tp) {
+    double h = 0.0;
+    if (tp <= ti) {
+      const int j0 = task_off ? task_off[tp] : 0;
+      const int j1 = min(task_off ? task_off[tp + 1] : N, i + 1);
+      const double ke = KE ? KE[(size_t)ti * T + tp] : 1.0;
+      for (int j = j0 + lane; j < j1; j += 32) {
+        double g = krow[j] - ai * alpha[j];
+        if (j == i) g *= 0.5;
+        double dot = 0.0;
+        double dl[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double xj = (k < d) ? theta_s[(size_t)j * d + k] : 0.0;
+          dot += xi[k] * xj;
+          dl[k] = xi[k] - xj;
+        }
+        const double d2 = -2.0 * dot + sqi + sqnorm[j];
+        const double r = sqrt(fmax(d2, kDistClamp));
+        const double v = kSqrt3 * r;
+        const double e = exp(-v);
+        h += g * (scale * ((1.0 + v) * e));
+        if (d2 > kDistClamp) {  // tf.maximum routes the gradient to the constant when clamped
+          const double f = g * scale * ke * 3.0 * e;
+#pragma unroll
+          for (int k = 0; k < D; ++k) gbw[k] += f * dl[k] * dl[k];
+        }
+      }
+      h = warp_sum(h);
+    }
+    if (lane == 0) rowH[(size_t)i * T + tp] = h;
+  }
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double s = warp_sum(gbw[k]);
+    if (lane == 0 && k < d) rowbw[(size_t)i * d + k] = s;
+  }
+  if (lane == 0) {
+    rowsc[(size_t)i * 3 + 0] = ai;
+    rowsc[(size_t)i * 3 + 1] = krow[i];
+    rowsc[(size_t)i * 3 + 2] = ai * ai;
+  }
+}
+
+// fixed-order column sums of a [rows x cols] row-major matrix over row range, one CTA per column
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q];
+  }
+  __syncthreads();
+  return s;  // valid in thread 0
+}
+
+// grid: T*T blocks (t,t') -> Hsym[t][t'] = sum_{i in t} rowH[i][t'] (t >= t'), then symmetrise later
+__global__ void __launch_bounds__(256) gram_grad_reduceH_kernel(const double* __restrict__ rowH, int T,
+                                                                const int32_t* __restrict__ task_off,
+                                                                int N, double* __restrict__ Hsym) {
+  __shared__ double red[8];
+  const int t = blockIdx.x / T, u = blockIdx.x % T;
+  double acc = 0.0;
+  if (u <= t) {
+    const int i0 = task_off ? task_off[t] : 0, i1 = task_off ? task_off[t + 1] : N;
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) acc += rowH[(size_t)i * T + u];
+  }
+  const double s = block_sum_256(acc, red);
+  if (threadIdx.x == 0) Hsym[(size_t)t * T + u] = s;
+}
+
+// single block: finishes everything. H (full, symmetric) from Hsym; g_log_bw; scalars.
+__global__ void __launch_bounds__(256) gram_grad_finish_kernel(
+    const double* __restrict__ Hsym, const double* __restrict__ rowbw, const double* __restrict__ rowsc,
+    const double* __restrict__ KE, int T, int N, int d, const double* __restrict__ log_sigma,
+    double* __restrict__ H, double* __restrict__ g_log_bw, double* __restrict__ g_scalars) {
+  __shared__ double red[8];
+  // H[t][t] = Hsym[t][t]; H[t][u] = H[u][t] = 0.5 Hsym[max][min]
+  double gs = 0.0;
+  for (int idx = threadIdx.x; idx < T * T; idx += 256) {
+    const int t = idx / T, u = idx % T;
+    const int a = max(t, u), b = min(t, u);
+    const double h = (t == u) ? Hsym[(size_t)t * T + t] : 0.5 * Hsym[(size_t)a * T + b];
+    H[idx] = h;
+    gs += h * (KE ? KE[idx] : 1.0);
+  }
+  gs = block_sum_256(gs, red);
+  if (threadIdx.x == 0) g_scalars[0] = gs;  // d/dlog_scale = sum_ij G_ij K_ij
+  for (int k = 0; k < d; ++k) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < N; i += 256) a += rowbw[(size_t)i * d + k];
+    a = block_sum_256(a, red);
+    if (threadIdx.x == 0) g_log_bw[k] = a;
+  }
+  double sa = 0.0, tr = 0.0, aa = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) {
+    sa += rowsc[(size_t)i * 3 + 0];
+    tr += rowsc[(size_t)i * 3 + 1];
+    aa += rowsc[(size_t)i * 3 + 2];
+  }
+  sa = block_sum_256(sa, red);
+  tr = block_sum_256(tr, red);
+  aa = block_sum_256(aa, red);
+  if (threadIdx.x == 0) {
+    g_scalars[1] = -sa;                                       // d/dmean
+    g_scalars[2] = exp(2.0 * (*log_sigma)) * (tr - aa);       // d/dlog_sigma = 2 sigma^2 tr(G)
+  }
+}
+
+// ------------------------------------------------------------------ task Gram backward
+// One thread per embedding column c.  ev[t][u] = exp(-v) (0 where the distance was clamped).
+__global__ void __launch_bounds__(256) task_gram_bwd_kernel(const double* __restrict__ E, int lde, int T,
+                                                            int P, const double* __restrict__ log_bw_embed,
+                                                            const double* __restrict__ H,
+                                                            double* __restrict__ g_log_bw_embed,
+                                                            double* __restrict__ dE) {
+  extern __shared__ __align__(16) double ev[];  // [T*T]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int pair = warp; pair < T * T; pair += 8) {
+    const int t = pair / T, u = pair % T;
+    double xy = 0.0, xx = 0.0, yy = 0.0;
+    for (int c = lane; c < P; c += 32) {
+      const double s = exp(log_bw_embed[c]);
+      const double a = E[(size_t)t * lde + c] / s, b = E[(size_t)u * lde + c] / s;
+      xy += a * b;
+      xx += a * a;
+      yy += b * b;
+    }
+    xy = warp_sum(xy);
+    xx = warp_sum(xx);
+    yy = warp_sum(yy);
+    if (lane == 0) {
+      const double d2 = -2.0 * xy + xx + yy;
+      ev[pair] = (d2 > kDistClamp) ? exp(-kSqrt3 * sqrt(d2)) : 0.0;
+    }
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= P) return;
+  const double s = exp(log_bw_embed[c]);
+  const double inv_s2 = 1.0 / (s * s);
+  double gbw = 0.0;
+  for (int t = 0; t < T; ++t) {
+    const double et = E[(size_t)t * lde + c];
+    double de = 0.0;
+    for (int u = 0; u < T; ++u) {
+      const double diff = et - E[(size_t)u * lde + c];
+      const double h = H[(size_t)t * T + u], e = ev[t * T + u];
+      // dK/dd2 = -1.5 e ; dd2/dE_tc = 2 diff / s^2 for the pair (t,u) and the same again for (u,t)
+      de += (h + H[(size_t)u * T + t]) * (-1.5 * e) * 2.0 * diff * inv_s2;
+      // dd2/dlog s_c = -2 diff^2 / s^2
+      gbw += h * 3.0 * e * diff * diff * inv_s2;
+    }
+    dE[(size_t)t * lde + c] = de;
+  }
+  g_log_bw_embed[c] = gbw;
+}
+
+// ------------------------------------------------------------------ Adam (TF 1.7 form)
+__global__ void __launch_bounds__(1024) adam_kernel(double* __restrict__ params,
+                                                    const double* __restrict__ grads,
+                                                    double* __restrict__ m, double* __restrict__ v,
+                                                    long long n, double lr_t, double b1, double b2,
+                                                    double eps, double clip_norm) {
+  __shared__ double red[32];
+  __shared__ double gscale;
+  if (clip_norm > 0.0) {
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) s += grads[i] * grads[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      s = warp_sum(red[threadIdx.x]);
+      if (threadIdx.x == 0) {
+        const double gn = sqrt(s);
+        gscale = clip_norm / fmax(gn, clip_norm);  // tf.clip_by_global_norm
+      }
+    }
+    __syncthreads();
+  } else if (threadIdx.x == 0) {
+    gscale = 1.0;
+  }
+  __syncthreads();
+  const double gsc = gscale;
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const double g = grads[i] * gsc;
+    const double mi = b1 * m[i] + (1.0 - b1) * g;
+    const double vi = b2 * v[i] + (1.0 - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    params[i] -= lr_t * mi / (sqrt(vi) + eps);
+  }
+}
+
+}  // namespace db
+
+using namespace db;
+
+extern "C" int distbo_scale_theta_f64(const double* theta, int N, int d, const double* log_bw,
+                                      double* theta_s, double* sqnorm, int n_rows_out, void* stream) {
+  if (!theta || !log_bw || !theta_s || !sqnorm || N <= 0 || d <= 0 || n_rows_out < N) return DISTBO_EARG;
+  scale_theta_kernel<<<(n_rows_out + 255) / 256, 256, 0, (cudaStream_t)stream>>>(theta, N, d, log_bw, theta_s,
+                                                                                 sqnorm, n_rows_out);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
+extern "C" int distbo_task_gram_f64(const double* E, int lde, int T, int P, const double* log_bw_embed,
+                                    double* KE, void* stream) {
+  if (!E || !log_bw_embed || !KE || T <= 0 || P <= 0 || lde < P) return DISTBO_EARG;
+  task_gram_kernel<<<(T * T + 7) / 8, 256, 0, (cudaStream_t)stream>>>(E, lde, T, P, log_bw_embed, KE);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
+extern "C" int distbo_gram_f64(const double* theta_s, const double* sqnorm, int N, int n_pad, int d,
+                               const int32_t* task_id, const double* KE, int T, const double* log_scale,
+                               const double* log_sigma, double jitter, double* K, void* stream) {
+  if (!theta_s || !sqnorm || !log_scale || !log_sigma || !K || N <= 0 || n_pad < N || n_pad % 128 || d <= 0 ||
+      d > 64)
+    return DISTBO_EARG;
+  if (KE && (!task_id || T <= 0)) return DISTBO_EARG;
+  const int nb = n_pad / GT;
+  const int smem = (2 * GT * d + 2 * GT) * (int)sizeof(double) + 2 * GT * (int)sizeof(int);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    configured = true;
+  }
+  gram_kernel<<<nb * (nb + 1) / 2, 256, smem, (cudaStream_t)stream>>>(theta_s, sqnorm, N, n_pad, d, task_id, KE, T,
+                                                                     log_scale, log_sigma, jitter, K);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
+extern "C" int distbo_gram_grad_f64(const double* Kinv, const double* alpha, const double* theta_s,
+                                    const double* sqnorm, int N, int n_pad, int d, const int32_t* task_id,
+                                    const int32_t* task_off, const double* KE, int T, const double* log_scale,
+                                    const double* log_sigma, double* g_log_bw, double* g_scalars, double* H,
+                                    double* workspace, void* stream) {
+  if (!Kinv || !alpha || !theta_s || !sqnorm || !log_scale || !log_sigma || !g_log_bw || !g_scalars || !H ||
+      !workspace || N <= 0 || n_pad < N || d <= 0 || d > DMAX || T <= 0)
+    return DISTBO_EARG;
+  if (T > 1 && (!task_id || !task_off)) return DISTBO_EARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* rowH = workspace;                          // [n_pad][T]
+  double* rowbw = rowH + (size_t)n_pad * T;          // [n_pad][d]
+  double* rowsc = rowbw + (size_t)n_pad * d;         // [n_pad][3]
+  double* Hsym = rowsc + (size_t)n_pad * 3;          // [T*T] (fits: workspace has n_pad*(T+d+4))
+  if ((size_t)T * T > (size_t)n_pad) return DISTBO_EARG;
+  const int grid = (N + 7) / 8;
+  if (d <= 4)
+    gram_grad_rows_kernel<4><<<grid, 256, 0, st>>>(Kinv, alpha, theta_s, sqnorm, N, n_pad, d, task_id, task_off, KE,
+                                                   T, log_scale, rowH, rowbw, rowsc);
+  else if (d <= 8)
+    gram_grad_rows_kernel<8><<<grid, 256, 0, st>>>(Kinv, alpha, theta_s, sqnorm, N, n_pad, d, task_id, task_off, KE,
+                                                   T, log_scale, rowH, rowbw, rowsc);
+  else
+    gram_grad_rows_kernel<DMAX><<<grid, 256, 0, st>>>(Kinv, alpha, theta_s, sqnorm, N, n_pad, d, task_id, task_off,
+                                                      KE, T, log_scale, rowH, rowbw, rowsc);
+  DB_CHECK_LAUNCH();
+  gram_grad_reduceH_kernel<<<T * T, 256, 0, st>>>(rowH, T, task_off, N, Hsym);
+  DB_CHECK_LAUNCH();
+  gram_grad_finish_kernel<<<1, 256, 0, st>>>(Hsym, rowbw, rowsc, KE, T, N, d, log_sigma, H, g_log_bw, g_scalars);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
+extern "C" int distbo_task_gram_bwd_f64(const double* E, int lde, int T, int P, const double* log_bw_embed,
+                                        const double* H, double* g_log_bw_embed, double* dE, void* stream) {
+  if (!E || !log_bw_embed || !H || !g_log_bw_embed || !dE || T <= 0 || P <= 0 || lde < P) return DISTBO_EARG;
+  const int smem = T * T * (int)sizeof(double);
+  if (smem > 200 * 1024) return DISTBO_EARG;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(task_gram_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  task_gram_bwd_kernel<<<(P + 255) / 256, 256, smem, (cudaStream_t)stream>>>(E, lde, T, P, log_bw_embed, H,
+                                                                            g_log_bw_embed, dE);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
+extern "C" int distbo_adam_f64(double* params, const double* grads, double* m, double* v, int64_t n, double lr,
+                               double beta1, double beta2, double eps, int64_t step, double clip_norm,
+                               double* scratch, void* stream) {
+  (void)scratch;
+  if (!params || !grads || !m || !v || n <= 0 || step <= 0) return DISTBO_EARG;
+  const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)step)) / (1.0 - pow(beta1, (double)step));
+  adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grads, m, v, (long long)n, lr_t, beta1, beta2, eps,
+                                                    clip_norm);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}

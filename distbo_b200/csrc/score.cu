@@ -1,0 +1,262 @@
+// K4: posterior mean/variance + acquisition + argmax over a large candidate set.
+//   k_* = scale * matern32(theta, theta_c) * kvec ; A = L^-1 k_* = W k_* ; V = W (y - m)
+//   mean = A^T V + m ; var = scale - colsum(A^2) ; std = sqrt(max(var, 1e-32))
+// Reference: train/log_gaus_likelihood.py:128-218, train/gp_regressor.py:197,
+//            bayes_opt/helpers.py:51-68,151-171.
+//
+// Per chunk of candidates (one 128-candidate tile per SM):
+//   kst_kernel     : materialise k_* candidate-major, Kst[c][i] (i contiguous), zero on pad rows;
+//   score_kernel   : persistent CTA per candidate tile; loops over the 128-row blocks of W, runs the
+//                    DMMA main loop for k <= row block (W is lower triangular), and folds each
+//                    accumulator tile into column sums of A^2 and A*V - A is never written;
+//                    then the acquisition epilogue and a per-CTA (max value, lowest index);
+//   merge_kernel   : deterministic (max value, min index) merge into the running best.
+#include "../../include/distbo_b200.h"
+#include "gemm_core.cuh"
+
+namespace db {
+
+constexpr int SCORE_DMAX = 16;
+constexpr int KST_CAND = 8;  // candidates per CTA in kst_kernel
+
+__global__ void __launch_bounds__(256) kst_kernel(const double* __restrict__ theta_s,
+                                                  const double* __restrict__ sqnorm, int N, int n_pad, int d,
+                                                  const double* __restrict__ log_bw,
+                                                  const double* __restrict__ kvec,
+                                                  const double* __restrict__ log_scale,
+                                                  const double* __restrict__ theta_c, long long c_begin,
+                                                  long long M, double* __restrict__ Kst) {
+  __shared__ double ys[KST_CAND][SCORE_DMAX];
+  __shared__ double ysq[KST_CAND];
+  const int tid = threadIdx.x;
+  const long long cl0 = (long long)blockIdx.x * KST_CAND;  // local candidate row in the chunk
+  if (tid < KST_CAND * SCORE_DMAX) {
+    const int q = tid / SCORE_DMAX, k = tid % SCORE_DMAX;
+    const long long c = c_begin + cl0 + q;
+    double v = 0.0;
+    if (k < d && c < M) v = theta_c[c * d + k] / exp(log_bw[k]);
+    ys[q][k] = v;
+  }
+  __syncthreads();
+  if (tid < KST_CAND) {
+    double s = 0.0;
+    for (int k = 0; k < d; ++k) s += ys[tid][k] * ys[tid][k];
+    ysq[tid] = s;
+  }
+  __syncthreads();
+  const double scale = exp(*log_scale);
+  for (int i = tid; i < n_pad; i += 256) {
+    double xi[SCORE_DMAX];
+#pragma unroll
+    for (int k = 0; k < SCORE_DMAX; ++k) xi[k] = (k < d) ? theta_s[(size_t)i * d + k] : 0.0;
+    const double sqi = sqnorm[i];
+    const double kv = (i < N) ? kvec[i] : 0.0;
+#pragma unroll
+    for (int q = 0; q < KST_CAND; ++q) {
+      double dot = 0.0;
+#pragma unroll
+      for (int k = 0; k < SCORE_DMAX; ++k) dot += xi[k] * ys[q][k];
+      const double d2 = -2.0 * dot + sqi + ysq[q];
+      double v = (scale * matern32_from_d2(d2)) * kv;
+      if (i >= N || c_begin + cl0 + q >= M) v = 0.0;
+      Kst[(size_t)(cl0 + q) * n_pad + i] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ double acquisition(int kind, double mean, double std, double y_max, double xi,
+                                              double kappa) {
+  if (kind == DISTBO_ACQ_EI) {
+    const double imp = mean - y_max - xi;
+    const double z = imp / std;
+    const double cdf = 0.5 * erfc(-z * 0.70710678118654752440);
+    const double pdf = exp(-z * z / 2.0) / 2.5066282746310005024;
+    return imp * cdf + std * pdf;
+  }
+  if (kind == DISTBO_ACQ_UCB) return mean + kappa * std;
+  return mean - kappa * std;
+}
+
+struct ScoreArgs {
+  const double* W;
+  const double* V;
+  const double* Kst;
+  int n_pad;
+  const double* log_scale;
+  const double* mean_param;
+  long long c_begin, M, index_offset;
+  int acq_kind;
+  double y_max, xi, kappa;
+  double* out_mean;
+  double* out_std;
+  double* out_acq;
+  double* block_best_val;
+  long long* block_best_idx;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) score_kernel(ScoreArgs p) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double red2[2][128], redv[2][128];
+  __shared__ double bval[128];
+  __shared__ long long bidx[128];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int n0 = blockIdx.x * BN;  // candidate tile (local rows of Kst)
+  const int nb = p.n_pad / BM;
+
+  double s2[4][2], sv[4][2];
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni) s2[ni][0] = s2[ni][1] = sv[ni][0] = sv[ni][1] = 0.0;
+
+  for (int ib = 0; ib < nb; ++ib) {
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    gemm_mainloop<KMAJOR, KMAJOR>(acc, p.W, p.n_pad, p.Kst, p.n_pad, ib * BM, n0, 0, (ib + 1) * BM, smem);
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      const double v = p.V[ib * BM + wm * 64 + mi * 8 + lr];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        s2[ni][0] += acc[mi][ni][0] * acc[mi][ni][0];
+        s2[ni][1] += acc[mi][ni][1] * acc[mi][ni][1];
+        sv[ni][0] += acc[mi][ni][0] * v;
+        sv[ni][1] += acc[mi][ni][1] * v;
+      }
+    }
+  }
+  // reduce over the 8 row-lanes that share a column (lane bits 2..4), then over the two M-warps
+#pragma unroll
+  for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double a = s2[ni][e], b = sv[ni][e];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lr == 0) {
+        const int col = wn * 32 + ni * 8 + lk * 2 + e;
+        red2[wm][col] = a;
+        redv[wm][col] = b;
+      }
+    }
+  __syncthreads();
+  if (tid < 128) {
+    const long long c = p.c_begin + n0 + tid;
+    double val = -INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    if (c < p.M) {
+      const double sumsq = red2[0][tid] + red2[1][tid];
+      const double dot = redv[0][tid] + redv[1][tid];
+      const double scale = exp(*p.log_scale);
+      const double mean = dot + *p.mean_param;
+      const double var = scale - sumsq;
+      const double std = sqrt(fmax(var, kVarClamp));
+      const double a = acquisition(p.acq_kind, mean, std, p.y_max, p.xi, p.kappa);
+      if (p.out_mean) p.out_mean[c] = mean;
+      if (p.out_std) p.out_std[c] = std;
+      if (p.out_acq) p.out_acq[c] = a;
+      val = a;
+      idx = p.index_offset + c;
+    }
+    bval[tid] = val;
+    bidx[tid] = idx;
+  }
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (tid < s) {
+      const double v2 = bval[tid + s];
+      const long long i2 = bidx[tid + s];
+      if (v2 > bval[tid] || (v2 == bval[tid] && i2 < bidx[tid])) {
+        bval[tid] = v2;
+        bidx[tid] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    p.block_best_val[blockIdx.x] = bval[0];
+    p.block_best_idx[blockIdx.x] = bidx[0];
+  }
+}
+
+// running (max value, min index) over the chunk's CTAs; `first` resets the running best
+__global__ void merge_best_kernel(const double* __restrict__ bv, const long long* __restrict__ bi, int nblocks,
+                                  int first, double* best_val, long long* best_idx) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double v = first ? -INFINITY : *best_val;
+  long long i = first ? 0x7fffffffffffffffLL : *best_idx;
+  for (int b = 0; b < nblocks; ++b)
+    if (bv[b] > v || (bv[b] == v && bi[b] < i)) {
+      v = bv[b];
+      i = bi[b];
+    }
+  *best_val = v;
+  *best_idx = i;
+}
+
+static int g_score_chunk = 0;
+
+}  // namespace db
+
+using namespace db;
+
+extern "C" int distbo_score_chunk(void) {
+  if (g_score_chunk == 0) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) sms = prop.multiProcessorCount;
+    }
+    g_score_chunk = sms * BN;  // one 128-candidate tile per SM: a single, perfectly balanced wave
+  }
+  return g_score_chunk;
+}
+
+extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_pad, const double* theta_s,
+                                const double* sqnorm, int d, const double* log_bw, const double* kvec,
+                                const double* log_scale, const double* mean_param, const double* theta_c,
+                                int64_t M, int acq_kind, double y_max, double xi, double kappa, double* Kst,
+                                double* out_mean, double* out_std, double* out_acq, double* block_best_val,
+                                int64_t* block_best_idx, double* best_val, int64_t* best_idx,
+                                int64_t index_offset, void* stream) {
+  if (!W || !V || !theta_s || !sqnorm || !log_bw || !kvec || !log_scale || !mean_param || !theta_c || !Kst ||
+      !block_best_val || !block_best_idx || !best_val || !best_idx)
+    return DISTBO_EARG;
+  if (N <= 0 || n_pad < N || n_pad % 128 || d <= 0 || d > SCORE_DMAX || M <= 0) return DISTBO_EARG;
+  if (acq_kind < 0 || acq_kind > 2) return DISTBO_EARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = distbo_score_chunk();
+  static bool configured = false;
+  if (!configured) {
+    DB_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    configured = true;
+  }
+  int first = 1;
+  for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+    const int64_t mc = (M - c0 < chunk) ? (M - c0) : chunk;
+    const int tiles = (int)((mc + BN - 1) / BN);
+    kst_kernel<<<tiles * BN / KST_CAND, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale,
+                                                     theta_c, (long long)c0, (long long)M, Kst);
+    DB_CHECK_LAUNCH();
+    ScoreArgs a;
+    a.W = W; a.V = V; a.Kst = Kst; a.n_pad = n_pad;
+    a.log_scale = log_scale; a.mean_param = mean_param;
+    a.c_begin = c0; a.M = M; a.index_offset = index_offset;
+    a.acq_kind = acq_kind; a.y_max = y_max; a.xi = xi; a.kappa = kappa;
+    a.out_mean = out_mean; a.out_std = out_std; a.out_acq = out_acq;
+    a.block_best_val = block_best_val; a.block_best_idx = (long long*)block_best_idx;
+    score_kernel<<<tiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
+    DB_CHECK_LAUNCH();
+    merge_best_kernel<<<1, 32, 0, st>>>(block_best_val, (const long long*)block_best_idx, tiles, first, best_val,
+                                        (long long*)best_idx);
+    DB_CHECK_LAUNCH();
+    first = 0;
+  }
+  return DISTBO_OK;
+}

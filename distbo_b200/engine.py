@@ -1,0 +1,337 @@
+"""Device-side engine of the joint GP over (theta, dataset embedding).
+
+Thin host layer over the C-ABI library: owns the HBM-resident state of one surrogate (padded
+N x N matrices, vectors, hyper-parameters, Adam slots) as torch CUDA tensors and sequences the
+kernels on torch's current stream.  PyTorch is used for device memory and streams only - every
+arithmetic step on the hot path is a kernel of libdistbo_b200.so.
+
+Layout in HBM (row-major, fp64 unless noted; n_pad = roundup(N, 128)):
+  K/L   [n_pad, n_pad]  Gram -> Cholesky factor in place (lower 128-tiles valid; pad = identity)
+  W     [n_pad, n_pad]  L^-1 (lower)
+  T     [n_pad, n_pad]  TRTRI temp, reused as Kinv = W^T W (lower tiles)
+  theta_s [n_pad, d], sqnorm [n_pad], V, alpha [n_pad], task_id int32 [N], task_off int32 [T+1]
+  E     [T(+1), P]      dataset embeddings (last row = target at predict time), KE [T,T]
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+JITTER = 0.000001  # reference train/log_gaus_likelihood.py:122,210
+ACQ = {"ei": 0, "ucb": 1, "lcb": 2}
+
+
+def round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+def _stream():
+    return _lib.C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Plans:
+    """One fit plan per (device, n_pad)."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, n_pad):
+        key = (torch.cuda.current_device(), n_pad)
+        if key not in cls._cache:
+            lib = _lib.load()
+            h = _lib.C.c_void_p()
+            _lib.check(lib.distbo_plan_create(n_pad, _lib.C.byref(h)), "distbo_plan_create")
+            cls._cache[key] = h
+        return cls._cache[key]
+
+
+class NetSpec:
+    """Shapes of the embedding nets (reference train/gp_utils.py:13-26, two-layer form)."""
+
+    def __init__(self, dx, dy, hx, p, hy=0, q=0, y_mode=0):
+        self.dx, self.dy, self.hx, self.p, self.hy, self.q, self.y_mode = dx, dy, hx, p, hy, q, y_mode
+
+    @property
+    def pooled_width(self):
+        if self.y_mode == 0:
+            return self.p
+        if self.y_mode == 1:
+            return self.p * self.q
+        return self.p * self.dy + self.dy
+
+
+class ParamStore:
+    """Flat fp64 parameter vector on the device with named views, plus gradient and Adam slots."""
+
+    def __init__(self, shapes, device):
+        self.shapes = dict(shapes)
+        self.offsets = {}
+        off = 0
+        for k, shp in shapes.items():
+            n = int(np.prod(shp)) if len(shp) else 1
+            self.offsets[k] = (off, n)
+            off += n
+        self.n = off
+        self.flat = torch.zeros(off, dtype=torch.float64, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float64, device=device)
+        self.m = torch.zeros(off, dtype=torch.float64, device=device)
+        self.v = torch.zeros(off, dtype=torch.float64, device=device)
+        self.step = 0
+
+    def view(self, name, buf=None):
+        off, n = self.offsets[name]
+        buf = self.flat if buf is None else buf
+        return buf[off:off + n].view(*self.shapes[name]) if len(self.shapes[name]) else buf[off:off + 1]
+
+    def gview(self, name):
+        return self.view(name, self.grad)
+
+    def set(self, name, value):
+        v = torch.as_tensor(np.asarray(value, dtype=np.float64)).reshape(-1)
+        off, n = self.offsets[name]
+        assert v.numel() == n, (name, v.numel(), n)
+        self.flat[off:off + n].copy_(v)
+
+    def get(self, name):
+        off, n = self.offsets[name]
+        return self.flat[off:off + n].cpu().numpy().reshape(self.shapes[name])
+
+    def get_grad(self, name):
+        off, n = self.offsets[name]
+        return self.grad[off:off + n].cpu().numpy().reshape(self.shapes[name])
+
+    def has(self, name):
+        return name in self.offsets
+
+
+class GPEngine:
+    def __init__(self, d_theta, n_embed=0, net=None, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.DistboError("distbo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.d = int(d_theta)
+        self.P = int(n_embed)            # embedding width incl. size-ratio column (0: kernel 'params')
+        self.net = net
+        shapes = {}
+        if net is not None:
+            shapes["weights_x_1"] = (net.dx, net.hx)
+            shapes["bias_x_1"] = (net.hx,)
+            shapes["weights_x_2"] = (net.hx, net.p)
+            if net.y_mode == 1:
+                shapes["weights_y_1"] = (net.dy, net.hy)
+                shapes["bias_y_1"] = (net.hy,)
+                shapes["weights_y_2"] = (net.hy, net.q)
+        if self.P > 0:
+            shapes["log_bw_embed"] = (self.P,)
+        shapes["log_bw"] = (self.d,)
+        shapes["log_scale"] = (1,)
+        shapes["mean"] = (1,)
+        shapes["log_sigma"] = ()
+        self.params = ParamStore(shapes, self.dev)
+        self.N = 0
+        self.n_pad = 0
+        self.info = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.nll = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.best_val = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.best_idx = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._score_ws = None
+        self._emb_ws = None
+        self.E = None
+        self.KE = None
+        self.T = 1
+
+    # ------------------------------------------------------------------ buffers
+    def _f64(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float64, device=self.dev)
+
+    def set_observations(self, theta, y, sizes=None):
+        """theta [N,d] (already StandardScaler-transformed), y [N]; sizes = observations per task."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        N = theta.shape[0]
+        assert theta.shape[1] == self.d and y.shape[0] == N
+        n_pad = round_up(N, 128)
+        if n_pad != self.n_pad:
+            self.n_pad = n_pad
+            self.K = self._f64(n_pad, n_pad)
+            self.W = self._f64(n_pad, n_pad)
+            self.Tm = self._f64(n_pad, n_pad)
+            self.theta_s = self._f64(n_pad, self.d)
+            self.sqnorm = self._f64(n_pad)
+            self.V = self._f64(n_pad)
+            self.alpha = self._f64(n_pad)
+            self.kvec = self._f64(n_pad)
+            self.plan = Plans.get(n_pad)
+        self.N = N
+        self.theta = torch.from_numpy(theta).to(self.dev)
+        self.y = torch.from_numpy(y).to(self.dev)
+        if sizes is None:
+            sizes = [N]
+        sizes = np.asarray(sizes, dtype=np.int64).reshape(-1)
+        assert sizes.sum() == N
+        self.T = len(sizes)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        self.task_off = torch.from_numpy(off).to(self.dev)
+        self.task_id = torch.from_numpy(np.repeat(np.arange(self.T), sizes).astype(np.int32)).to(self.dev)
+        self.gws = self._f64(n_pad * (self.T + self.d + 4))
+        self.H = self._f64(self.T, self.T)
+        self.gscal = self._f64(3)
+        self.W_valid = False
+
+    # ------------------------------------------------------------------ embedding
+    def embed(self, X, Y, seg_off, out=None, n_rows=None, dtype=torch.float64):
+        """K1 forward: X [S,dx], Y [S,dy] device tensors, seg_off int32 [T+1] -> E rows [T, P]."""
+        net = self.net
+        Tn = seg_off.numel() - 1
+        if out is None:
+            out = torch.zeros(Tn, max(self.P, net.pooled_width), dtype=dtype, device=self.dev)
+        p = self.params
+        if dtype == torch.float64:
+            fn = self.lib.distbo_embed_fwd_f64
+            cast = lambda t: t
+        else:
+            fn = self.lib.distbo_embed_fwd_f32
+            cast = lambda t: t.float().contiguous()
+        w = lambda name: cast(p.view(name)) if p.has(name) else None
+        wx1, bx1, wx2 = w("weights_x_1"), w("bias_x_1"), w("weights_x_2")
+        wy1, by1, wy2 = w("weights_y_1"), w("bias_y_1"), w("weights_y_2")
+        rc = fn(_lib.ptr(X), _lib.ptr(Y), _lib.ptr(seg_off), Tn, net.dx, net.dy,
+                _lib.ptr(wx1), _lib.ptr(bx1), _lib.ptr(wx2), net.hx, net.p,
+                _lib.ptr(wy1), _lib.ptr(by1), _lib.ptr(wy2), net.hy, net.q,
+                net.y_mode, _lib.ptr(out), out.stride(0), _stream())
+        _lib.check(rc, "distbo_embed_fwd")
+        return out
+
+    def embed_backward(self, X, Y, seg_off, dE):
+        """K1 backward into the gradient slots of the net weights."""
+        net, p = self.net, self.params
+        need = self.lib.distbo_embed_bwd_workspace(int(X.shape[0]), net.dx, net.dy, net.hx, net.p, net.hy, net.q)
+        if self._emb_ws is None or self._emb_ws.numel() < need:
+            self._emb_ws = self._f64(need)
+        g = lambda name: _lib.ptr(p.gview(name)) if p.has(name) else None
+        w = lambda name: _lib.ptr(p.view(name)) if p.has(name) else None
+        Tn = seg_off.numel() - 1
+        rc = self.lib.distbo_embed_bwd_f64(
+            _lib.ptr(X), _lib.ptr(Y), _lib.ptr(seg_off), Tn, net.dx, net.dy,
+            w("weights_x_1"), w("bias_x_1"), w("weights_x_2"), net.hx, net.p,
+            w("weights_y_1"), w("bias_y_1"), w("weights_y_2"), net.hy, net.q, net.y_mode,
+            _lib.ptr(dE), dE.stride(0),
+            g("weights_x_1"), g("bias_x_1"), g("weights_x_2"),
+            g("weights_y_1"), g("bias_y_1"), g("weights_y_2"),
+            _lib.ptr(self._emb_ws), self._emb_ws.numel(), _stream())
+        _lib.check(rc, "distbo_embed_bwd_f64")
+
+    # ------------------------------------------------------------------ Gram and fit
+    def task_gram(self, E, Tn):
+        """KE [Tn,Tn] over the first Tn rows of E (width P)."""
+        KE = self._f64(Tn, Tn)
+        rc = self.lib.distbo_task_gram_f64(_lib.ptr(E), E.stride(0), Tn, self.P,
+                                           _lib.ptr(self.params.view("log_bw_embed")), _lib.ptr(KE), _stream())
+        _lib.check(rc, "distbo_task_gram_f64")
+        return KE
+
+    def build_gram(self, KE=None):
+        p = self.params
+        rc = self.lib.distbo_scale_theta_f64(_lib.ptr(self.theta), self.N, self.d, _lib.ptr(p.view("log_bw")),
+                                             _lib.ptr(self.theta_s), _lib.ptr(self.sqnorm), self.n_pad, _stream())
+        _lib.check(rc, "distbo_scale_theta_f64")
+        rc = self.lib.distbo_gram_f64(_lib.ptr(self.theta_s), _lib.ptr(self.sqnorm), self.N, self.n_pad, self.d,
+                                      _lib.ptr(self.task_id), _lib.ptr(KE), self.T if KE is not None else 1,
+                                      _lib.ptr(p.view("log_scale")), _lib.ptr(p.view("log_sigma")), JITTER,
+                                      _lib.ptr(self.K), _stream())
+        _lib.check(rc, "distbo_gram_f64")
+        self.KE = KE
+
+    def factorize(self, need_inverse=True, need_kinv=False):
+        """K (in self.K) -> L in place; W = L^-1; optionally Kinv = W^T W (into self.Tm)."""
+        st = _stream()
+        _lib.check(self.lib.distbo_potrf_f64(self.plan, _lib.ptr(self.K), _lib.ptr(self.W), _lib.ptr(self.info), st),
+                   "distbo_potrf_f64")
+        if need_inverse or need_kinv:
+            _lib.check(self.lib.distbo_trtri_f64(self.plan, _lib.ptr(self.K), _lib.ptr(self.W), _lib.ptr(self.Tm), st),
+                       "distbo_trtri_f64")
+            self.W_valid = True
+        if need_kinv:
+            _lib.check(self.lib.distbo_lauum_f64(self.plan, _lib.ptr(self.W), _lib.ptr(self.Tm), st),
+                       "distbo_lauum_f64")
+
+    def likelihood(self):
+        rc = self.lib.distbo_nll_f64(_lib.ptr(self.K), _lib.ptr(self.W), self.N, self.n_pad, _lib.ptr(self.y),
+                                     _lib.ptr(self.params.view("mean")), _lib.ptr(self.V), _lib.ptr(self.alpha),
+                                     _lib.ptr(self.nll), _stream())
+        _lib.check(rc, "distbo_nll_f64")
+
+    def gram_gradient(self):
+        """Fills the gradient slots of log_bw, log_scale, mean, log_sigma and self.H = dNLL/dKE."""
+        p = self.params
+        multi = self.KE is not None
+        rc = self.lib.distbo_gram_grad_f64(
+            _lib.ptr(self.Tm), _lib.ptr(self.alpha), _lib.ptr(self.theta_s), _lib.ptr(self.sqnorm), self.N,
+            self.n_pad, self.d, _lib.ptr(self.task_id) if multi else None,
+            _lib.ptr(self.task_off) if multi else None, _lib.ptr(self.KE) if multi else None,
+            self.T if multi else 1, _lib.ptr(p.view("log_scale")), _lib.ptr(p.view("log_sigma")),
+            _lib.ptr(p.gview("log_bw")), _lib.ptr(self.gscal), _lib.ptr(self.H), _lib.ptr(self.gws), _stream())
+        _lib.check(rc, "distbo_gram_grad_f64")
+        p.gview("log_scale").copy_(self.gscal[0:1])
+        p.gview("mean").copy_(self.gscal[1:2])
+        p.gview("log_sigma").copy_(self.gscal[2:3])
+
+    def task_gram_backward(self, E, Tn):
+        dE = self._f64(Tn, E.shape[1])
+        rc = self.lib.distbo_task_gram_bwd_f64(_lib.ptr(E), E.stride(0), Tn, self.P,
+                                               _lib.ptr(self.params.view("log_bw_embed")), _lib.ptr(self.H),
+                                               _lib.ptr(self.params.gview("log_bw_embed")), _lib.ptr(dE), _stream())
+        _lib.check(rc, "distbo_task_gram_bwd_f64")
+        return dE
+
+    def adam_step(self, lr, clip_norm=0.0):
+        p = self.params
+        p.step += 1
+        rc = self.lib.distbo_adam_f64(_lib.ptr(p.flat), _lib.ptr(p.grad), _lib.ptr(p.m), _lib.ptr(p.v), p.n,
+                                      float(lr), 0.9, 0.999, 1e-8, p.step, float(clip_norm), None, _stream())
+        _lib.check(rc, "distbo_adam_f64")
+
+    def read_loss(self):
+        """One device->host sync: (nll, info).  Raises on a failed Cholesky like TF's
+        InvalidArgumentError."""
+        out = torch.stack([self.nll[0], self.info[0].double()]).cpu().numpy()
+        if int(out[1]) != 0:
+            raise _lib.DistboError("Cholesky decomposition was not successful: non-positive pivot at row %d "
+                                   "(matrix not positive definite)" % int(out[1]))
+        return float(out[0])
+
+    # ------------------------------------------------------------------ scoring
+    def score(self, theta_c, acq="ei", y_max=0.0, xi=0.0, kappa=1.0, want_arrays=True, index_offset=0,
+              kvec=None):
+        """K4 on candidates theta_c [M,d] (device or host array, already scaler-transformed).
+        Returns dict(best_val, best_idx, mean, std, acq) - arrays only when want_arrays."""
+        assert self.W_valid, "factorize(need_inverse=True) first"
+        if not torch.is_tensor(theta_c):
+            theta_c = torch.from_numpy(np.ascontiguousarray(theta_c, dtype=np.float64)).to(self.dev)
+        M = int(theta_c.shape[0])
+        chunk = self.lib.distbo_score_chunk()
+        if self._score_ws is None or self._score_ws[0].numel() < chunk * self.n_pad:
+            self._score_ws = (torch.empty(chunk * self.n_pad, dtype=torch.float64, device=self.dev),
+                              torch.empty(chunk // 128, dtype=torch.float64, device=self.dev),
+                              torch.empty(chunk // 128, dtype=torch.int64, device=self.dev))
+        kst, bbv, bbi = self._score_ws
+        if kvec is None:
+            kvec = self.kvec
+        mean = std = acqv = None
+        if want_arrays:
+            mean = torch.empty(M, dtype=torch.float64, device=self.dev)
+            std = torch.empty(M, dtype=torch.float64, device=self.dev)
+            acqv = torch.empty(M, dtype=torch.float64, device=self.dev)
+        p = self.params
+        rc = self.lib.distbo_score_f64(
+            _lib.ptr(self.W), _lib.ptr(self.V), self.N, self.n_pad, _lib.ptr(self.theta_s), _lib.ptr(self.sqnorm),
+            self.d, _lib.ptr(p.view("log_bw")), _lib.ptr(kvec), _lib.ptr(p.view("log_scale")),
+            _lib.ptr(p.view("mean")), _lib.ptr(theta_c), M, ACQ[acq], float(y_max), float(xi), float(kappa),
+            _lib.ptr(kst), _lib.ptr(mean), _lib.ptr(std), _lib.ptr(acqv), _lib.ptr(bbv), _lib.ptr(bbi),
+            _lib.ptr(self.best_val), _lib.ptr(self.best_idx), int(index_offset), _stream())
+        _lib.check(rc, "distbo_score_f64")
+        return {"best_val": self.best_val, "best_idx": self.best_idx, "mean": mean, "std": std, "acq": acqv}

@@ -1,0 +1,132 @@
+/* distbo_b200 - C ABI of the B200-native (sm_100a) distBO joint-GP hot path.
+ *
+ * Drop-in boundary.  The reference (hcllaw/distBO) has no FFI: its hot path
+ * is a TensorFlow-1.7 graph evaluated by sess.run.  Each entry point below replaces the TF ops
+ * cited next to it (paths relative to the reference repository).  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers unless a name ends in _host; matrices are row-major;
+ *  - dense N x N matrices are padded to n_pad = roundup(N,128) with leading dimension n_pad, the
+ *    pad block being the identity (K, L, W=L^-1) or zero (everything else);
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and
+ *    never synchronises the device (distbo_plan_create / destroy excepted);
+ *  - return value: 0 ok, <0 bad argument (-1) or CUDA error (-2).  A failed Cholesky is reported
+ *    asynchronously through the device int `info` (LAPACK style: 1-based index of the first
+ *    non-positive pivot, 0 = success); the caller reads it back with the loss.
+ *  - not re-entrant per plan; one plan per (device, n_pad).
+ */
+#ifndef DISTBO_B200_H
+#define DISTBO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DISTBO_ACQ_EI 0  /* bayes_opt/helpers.py:165-171 */
+#define DISTBO_ACQ_UCB 1 /* bayes_opt/helpers.py:151-156 */
+#define DISTBO_ACQ_LCB 2 /* bayes_opt/helpers.py:158-163 */
+
+/* Library / build identification: returns the compiled arch as an int (1000 for sm_100a). */
+int distbo_version(void);
+
+/* ---- K1: dataset embedding  (train/distbo_net.py:7-48, train/base.py:9-43) ----------------------
+ * Fused tanh-MLP feature map phi_x (and phi_y), per-sample outer product phi_x (x) phi_y, and
+ * per-dataset mean over contiguous row segments seg_off[t]..seg_off[t+1].
+ *   X [S,dx], Y [S,dy] row-major; nets: W1 [d_in,h], b1 [h], W2 [h,p] (no bias on the last layer).
+ *   y_mode 0: embed_op 'none'  -> out cols = p                      (phi_x only)
+ *          1: 'joint' regression -> p*q  (index i*q+j), y-net (W1y,b1y,W2y) applied to Y
+ *          2: classification     -> p*dy + dy  (outer product with one-hot Y, then class ratios)
+ *   E [T, lde]: columns [0,P') written, the caller owns any extra columns (size-ratio column).
+ * _f32 / _f64 select the arithmetic type of samples, weights and output. */
+int distbo_embed_fwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int dx, int dy,
+                         const double* W1x, const double* b1x, const double* W2x, int hx, int p,
+                         const double* W1y, const double* b1y, const double* W2y, int hy, int q,
+                         int y_mode, double* E, int lde, void* stream);
+int distbo_embed_fwd_f32(const float* X, const float* Y, const int32_t* seg_off, int T, int dx, int dy,
+                         const float* W1x, const float* b1x, const float* W2x, int hx, int p,
+                         const float* W1y, const float* b1y, const float* W2y, int hy, int q,
+                         int y_mode, float* E, int lde, void* stream);
+/* Backward of the above (replaces TF autodiff through distbo_net, train/train.py:31-40):
+ * dE [T,lde] -> gradients of the net weights (same shapes as the weights; overwritten). */
+int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int dx, int dy,
+                         const double* W1x, const double* b1x, const double* W2x, int hx, int p,
+                         const double* W1y, const double* b1y, const double* W2y, int hy, int q,
+                         int y_mode, const double* dE, int lde,
+                         double* gW1x, double* gb1x, double* gW2x,
+                         double* gW1y, double* gb1y, double* gW2y,
+                         double* workspace, int64_t workspace_elems, void* stream);
+/* workspace size (in doubles) distbo_embed_bwd_f64 needs for S samples */
+int64_t distbo_embed_bwd_workspace(int64_t S, int dx, int dy, int hx, int p, int hy, int q);
+
+/* ---- K2: Matern-3/2 product Gram  (train/kernels.py:19-28,58-88; log_gaus_likelihood.py:86-122) --
+ * Task-level Gram KE[t,t'] = matern32(E[t]/exp(log_bw_embed), E[t']/exp(log_bw_embed)), [T,T]. */
+int distbo_task_gram_f64(const double* E, int lde, int T, int P, const double* log_bw_embed,
+                         double* KE, void* stream);
+/* theta_s[i,k] = theta[i,k] / exp(log_bw[k]) and its row norms; pad rows (i >= N) are zero. */
+int distbo_scale_theta_f64(const double* theta, int N, int d, const double* log_bw, double* theta_s,
+                           double* sqnorm, int n_rows_out, void* stream);
+/* K[i,j] = exp(log_scale) * matern32(theta_i, theta_j) * KE[task_id[i], task_id[j]]
+ *          + (exp(2 log_sigma) + jitter) * [i == j]           for i,j < N (lower 128-tiles only),
+ * identity on the pad block.  KE may be NULL (kernel 'params': factor 1). */
+int distbo_gram_f64(const double* theta_s, const double* sqnorm, int N, int n_pad, int d,
+                    const int32_t* task_id, const double* KE, int T, const double* log_scale,
+                    const double* log_sigma, double jitter, double* K, void* stream);
+
+/* ---- K3: GP fit  (tf.cholesky log_gaus_likelihood.py:123,211; gp_utils.py:118-147) ---------------
+ * A plan caches the tile lists / streams / events for one padded size. */
+int distbo_plan_create(int n_pad, void** plan_out);
+int distbo_plan_destroy(void* plan);
+/* A (n_pad x n_pad, lower tiles valid) is overwritten by its lower Cholesky factor L (upper part of
+ * the diagonal blocks zeroed); the 128x128 diagonal blocks of W receive inv(L_kk). */
+int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info, void* stream);
+/* W <- L^-1 (lower), given L and the diagonal blocks left in W by distbo_potrf_f64. T: n_pad^2 temp. */
+int distbo_trtri_f64(void* plan, const double* L, double* W, double* T, void* stream);
+/* Kinv (lower 128-tiles) <- W^T W. */
+int distbo_lauum_f64(void* plan, const double* W, double* Kinv, void* stream);
+/* V = W (y - mean), alpha = W^T V, nll = 0.5|V|^2 + 0.5 N log(2 pi) + sum log L_ii.
+ * y [N]; V, alpha [n_pad]; mean, nll device scalars. */
+int distbo_nll_f64(const double* L, const double* W, int N, int n_pad, const double* y,
+                   const double* mean, double* V, double* alpha, double* nll, void* stream);
+/* Closed-form gradient contraction with G = 0.5 (Kinv - alpha alpha^T), replacing TF autodiff
+ * through the Cholesky (train/train.py:33-40):
+ *   g_log_bw [d], g_scalars = {d/dlog_scale, d/dmean, d/dlog_sigma}, H [T,T] = dNLL/dKE (full).
+ * workspace: n_pad * (T + d + 4) doubles. */
+int distbo_gram_grad_f64(const double* Kinv, const double* alpha, const double* theta_s,
+                         const double* sqnorm, int N, int n_pad, int d, const int32_t* task_id,
+                         const int32_t* task_off, const double* KE, int T, const double* log_scale,
+                         const double* log_sigma, double* g_log_bw, double* g_scalars, double* H,
+                         double* workspace, void* stream);
+/* Backward of distbo_task_gram_f64: H [T,T] -> g_log_bw_embed [P], dE [T,lde] (cols < P). */
+int distbo_task_gram_bwd_f64(const double* E, int lde, int T, int P, const double* log_bw_embed,
+                             const double* H, double* g_log_bw_embed, double* dE, void* stream);
+/* TF-1.7 Adam update on a flat parameter vector (train/gp_regressor.py:141; epsilon-hat form).
+ * clip_norm <= 0 disables tf.clip_by_global_norm (train/train.py:33-35). step is 1-based. */
+int distbo_adam_f64(double* params, const double* grads, double* m, double* v, int64_t n, double lr,
+                    double beta1, double beta2, double eps, int64_t step, double clip_norm,
+                    double* scratch, void* stream);
+
+/* ---- K4: posterior + acquisition + argmax  (log_gaus_likelihood.py:128-218; gp_regressor.py:197;
+ *      bayes_opt/helpers.py:51-68,151-171) ---------------------------------------------------------
+ * For candidates theta_c [M,d] (already scaled by the frozen StandardScaler; NOT yet divided by the
+ * bandwidths): k_* = scale * matern32(theta, theta_c) * kvec, A = W k_*, mean = A^T V + m,
+ * var = scale - |A|^2, std = sqrt(max(var,1e-32)), acq in {EI, UCB, LCB}.
+ * kvec [n_pad] = KE[task(i), target] (1 for kernel 'params'; 0 on pad rows).
+ * Outputs (any may be NULL): mean [M], std [M], acq [M]; best_val[1], best_idx[1] (int64; first
+ * index of the maximum, as numpy argmax).  Kst: workspace of chunk*n_pad doubles with
+ * chunk = distbo_score_chunk(); partial workspace of distbo_score_chunk()/128*2 pairs. */
+int distbo_score_chunk(void);
+int distbo_score_f64(const double* W, const double* V, int N, int n_pad, const double* theta_s,
+                     const double* sqnorm, int d, const double* log_bw, const double* kvec,
+                     const double* log_scale, const double* mean_param, const double* theta_c,
+                     int64_t M, int acq_kind, double y_max, double xi, double kappa, double* Kst,
+                     double* out_mean, double* out_std, double* out_acq, double* block_best_val,
+                     int64_t* block_best_idx, double* best_val, int64_t* best_idx,
+                     int64_t index_offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISTBO_B200_H */

@@ -1,0 +1,277 @@
+"""GPU parity tests: every kernel of libdistbo_b200.so against the CPU oracle on the same seeded
+inputs (called through the C ABI via distbo_b200.engine).  Tolerances are the north_star's:
+fp64 GP quantities 1e-8 relative, fp32 embeddings 1e-5 relative."""
+import math
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import gp_oracle as O  # noqa: E402
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def make_problem(N, d, sizes=None, P=0, var=1e-2, seed=0):
+    rs = np.random.RandomState(seed)
+    theta = rs.randn(N, d)
+    y = rs.randn(N)
+    E = rs.randn(len(sizes), P) * 0.3 if P else None
+    return rs, theta, y, E
+
+
+def setup_engine(eng, theta, y, sizes=None, E=None, var=1e-2, log_bw=None, log_scale=0.3, mean=0.2,
+                 log_bw_embed=None):
+    N, d = theta.shape
+    P = 0 if E is None else E.shape[1]
+    e = eng.GPEngine(d, n_embed=P)
+    e.params.set("log_sigma", 0.5 * math.log(var))
+    e.params.set("log_scale", [log_scale])
+    e.params.set("mean", [mean])
+    if log_bw is not None:
+        e.params.set("log_bw", log_bw)
+    if P and log_bw_embed is not None:
+        e.params.set("log_bw_embed", log_bw_embed)
+    e.set_observations(theta, y, sizes)
+    KE = None
+    if P:
+        e.E = torch.from_numpy(E).to(e.dev)
+        KE = e.task_gram(e.E, len(sizes))
+    e.build_gram(KE)
+    return e
+
+
+def oracle_params(e):
+    p = {k: e.params.get(k) for k in e.params.offsets}
+    return p
+
+
+def oracle_K(p, theta, sizes=None, E=None):
+    k = O.matern32_kernel(O.NP, theta, theta, np.exp(p["log_bw"]))
+    if E is not None:
+        emb = np.repeat(E, sizes, axis=0)
+        k = k * O.matern32_kernel(O.NP, emb, emb, np.exp(p["log_bw_embed"]))
+    k = np.exp(p["log_scale"]) * k
+    ks = k + (np.exp(2.0 * p["log_sigma"]) + O.JITTER) * np.eye(len(theta))
+    return k, ks
+
+
+@pytest.mark.parametrize("N,d,sizes,P", [(200, 3, None, 0), (300, 2, [100, 50, 150], 5), (465, 1, [31] * 15, 10)])
+def test_gram(cuda_engine_mod, N, d, sizes, P):
+    rs, theta, y, E = make_problem(N, d, sizes, P)
+    lbw = rs.randn(d) * 0.3
+    lbe = rs.randn(P) * 0.3 if P else None
+    e = setup_engine(cuda_engine_mod, theta, y, sizes, E, log_bw=lbw, log_bw_embed=lbe)
+    p = oracle_params(e)
+    _, ks = oracle_K(p, theta, sizes, E)
+    K = e.K.cpu().numpy()
+    got = np.tril(K[:N, :N])
+    assert rel(got, np.tril(ks)) < 1e-13
+    # pad block is the identity
+    if e.n_pad > N:
+        assert np.array_equal(np.tril(K[N:, N:]), np.eye(e.n_pad - N))
+        assert not K[N:, :N].any()
+    if P:
+        emb_k = O.matern32_kernel(O.NP, E, E, np.exp(p["log_bw_embed"]))
+        assert rel(e.KE.cpu().numpy(), emb_k) < 1e-13
+
+
+@pytest.mark.parametrize("N", [100, 384, 700, 1300])
+def test_cholesky_inverse(cuda_engine_mod, N):
+    rs, theta, y, _ = make_problem(N, 4, seed=N)
+    e = setup_engine(cuda_engine_mod, theta, y)
+    p = oracle_params(e)
+    _, ks = oracle_K(p, theta)
+    e.factorize(need_inverse=True, need_kinv=True)
+    e.likelihood()
+    nll = e.read_loss()
+    Lref = scipy.linalg.cholesky(ks, lower=True)
+    L = np.tril(e.K.cpu().numpy())[:N, :N]
+    assert rel(L, Lref) < 1e-10
+    W = np.tril(e.W.cpu().numpy())[:N, :N]
+    Wref = scipy.linalg.solve_triangular(Lref, np.eye(N), lower=True)
+    assert rel(W, Wref) < 1e-9
+    Kinv = np.tril(e.Tm.cpu().numpy())[:N, :N]
+    assert rel(Kinv, np.tril(np.linalg.inv(ks))) < 1e-8
+    b = O.TrainBatch(h_params=theta, obs=y[:, None])
+    ref = float(O.neg_log_marg_likhd(O.NP, p, "params", b))
+    assert abs(nll - ref) <= 1e-10 * abs(ref)
+    V = e.V.cpu().numpy()[:N]
+    Vref = scipy.linalg.solve_triangular(Lref, y - p["mean"][0], lower=True)
+    assert rel(V, Vref) < 1e-9
+    alpha = e.alpha.cpu().numpy()[:N]
+    assert rel(alpha, scipy.linalg.solve_triangular(Lref.T, Vref, lower=False)) < 1e-8
+    if e.n_pad > N:
+        assert not e.V.cpu().numpy()[N:].any() and not e.alpha.cpu().numpy()[N:].any()
+
+
+def test_cholesky_not_pd_raises(cuda_engine_mod):
+    rs, theta, y, _ = make_problem(150, 2)
+    e = setup_engine(cuda_engine_mod, theta, y)
+    e.K[10, 10] = -1.0
+    e.factorize(need_inverse=False)
+    e.likelihood()
+    with pytest.raises(RuntimeError, match="not successful"):
+        e.read_loss()
+
+
+@pytest.mark.parametrize("N,d,sizes,P", [(200, 3, None, 0), (300, 2, [100, 50, 150], 5), (450, 1, [30] * 15, 10)])
+def test_gram_gradient(cuda_engine_mod, N, d, sizes, P):
+    rs, theta, y, E = make_problem(N, d, sizes, P, seed=3)
+    lbw = rs.randn(d) * 0.3
+    lbe = rs.randn(P) * 0.3 if P else None
+    e = setup_engine(cuda_engine_mod, theta, y, sizes, E, log_bw=lbw, log_bw_embed=lbe)
+    e.factorize(need_inverse=True, need_kinv=True)
+    e.likelihood()
+    e.gram_gradient()
+    p = oracle_params(e)
+    if P:
+        dE = e.task_gram_backward(e.E, len(sizes)).cpu().numpy()
+    # autograd reference (torch CPU fp64), embeddings as a leaf
+    tp = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=True) for k, v in p.items()}
+    B = O.TH()
+    th = torch.from_numpy(theta)
+    k = O.matern32_kernel(B, th, th, torch.exp(tp["log_bw"]))
+    if P:
+        Et = torch.tensor(E, requires_grad=True)
+        emb = B.repeat_rows(Et, sizes)
+        k = k * O.matern32_kernel(B, emb, emb, torch.exp(tp["log_bw_embed"]))
+    k = torch.exp(tp["log_scale"]) * k
+    ks = k + (torch.exp(2.0 * tp["log_sigma"]) + O.JITTER) * torch.eye(N, dtype=torch.float64)
+    L = torch.linalg.cholesky(ks)
+    mean = tp["mean"] * torch.ones(N, 1, dtype=torch.float64)
+    loss = -O.multivariate_normal_logpdf(B, torch.from_numpy(y[:, None]), mean, L).reshape(())
+    loss.backward()
+    for name in ["log_bw", "log_scale", "mean", "log_sigma"] + (["log_bw_embed"] if P else []):
+        got = e.params.get_grad(name)
+        want = tp[name].grad.numpy().reshape(got.shape)
+        assert rel(got, want) < 1e-8, name
+    if P:
+        assert rel(dE[:, :P], Et.grad.numpy()) < 1e-8
+
+
+@pytest.mark.parametrize("N,d,M,acq", [(200, 3, 1000, "ei"), (300, 8, 5000, "ucb"), (520, 2, 300, "lcb"),
+                                       (200, 1, 20000, "ei")])
+def test_score(cuda_engine_mod, N, d, M, acq):
+    rs, theta, y, _ = make_problem(N, d, seed=7 + N)
+    e = setup_engine(cuda_engine_mod, theta, y)
+    e.factorize(need_inverse=True)
+    e.likelihood()
+    e.read_loss()
+    kv = rs.rand(N) * 0.5 + 0.5
+    e.kvec.zero_()
+    e.kvec[:N] = torch.from_numpy(kv).to(e.dev)
+    cand = rs.randn(M, d) * 1.5
+    y_max, xi, kappa = float(np.max(y)), 0.01, 2.58
+    out = e.score(cand, acq=acq, y_max=y_max, xi=xi, kappa=kappa)
+    p = oracle_params(e)
+    b = O.TrainBatch(h_params=theta, obs=y[:, None])
+    # kernel 'dist' form with every column of k_dist_pred equal to kvec and k_dist = 1
+    mean, var = O.predict(O.NP, p, "dist", b, cand, k_dist=np.ones((N, N)), k_dist_pred=kv[:, None])
+    std = O.std_from_var(var)
+    a = O.acquisition(acq, mean, std, y_max=y_max, xi=xi, kappa=kappa)
+    scale = float(np.exp(p["log_scale"][0]))
+    assert rel(out["mean"].cpu().numpy(), mean[:, 0]) < 1e-9
+    assert np.max(np.abs(out["std"].cpu().numpy() ** 2 - std[:, 0] ** 2)) < 1e-9 * scale
+    assert np.max(np.abs(out["acq"].cpu().numpy() - a)) < 1e-9 * max(1.0, np.max(np.abs(a)))
+    assert int(out["best_idx"].item()) == int(np.argmax(a))
+    assert float(out["best_val"].item()) == pytest.approx(float(np.max(a)), rel=1e-9, abs=1e-12)
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 1e-5)])
+@pytest.mark.parametrize("mode", ["none", "joint", "class"])
+def test_embed_forward(cuda_engine_mod, dtype, tol, mode):
+    eng = cuda_engine_mod
+    rs = np.random.RandomState(11)
+    sizes = [300, 17, 1000, 129, 1]
+    S = sum(sizes)
+    if mode == "class":
+        dx, dy, y_mode, model_type, embed_op = 16, 2, 2, "classification", "joint"
+        X = (rs.rand(S, dx) < 0.3).astype(np.float64)
+        lab = (rs.rand(S) < 0.3).astype(int)
+        Y = np.eye(2)[lab]
+    else:
+        dx, dy, model_type = 7, 1, "regression"
+        y_mode, embed_op = (0, "none") if mode == "none" else (1, "joint")
+        X = rs.randn(S, dx)
+        Y = rs.rand(S, dy)
+    net = eng.NetSpec(dx, dy, 20, 10, 20 if y_mode == 1 else 0, 10 if y_mode == 1 else 0, y_mode)
+    e = eng.GPEngine(2, n_embed=net.pooled_width, net=net)
+    p = O.build_params(2, "dist", in_dim_x=dx, in_dim_y=dy, weight_dim_x=[20, 10], weight_dim_y=[20, 10],
+                       model_type=model_type, embed_op=embed_op, seed=5)
+    p["bias_x_1"] = rs.randn(20) * 0.1
+    if "bias_y_1" in p:
+        p["bias_y_1"] = rs.randn(20) * 0.1
+    for k, v in p.items():
+        if e.params.has(k) and k.startswith(("weights", "bias")):
+            e.params.set(k, v)
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    Xd = torch.from_numpy(X).to(e.dev).to(tdt)
+    Yd = torch.from_numpy(Y).to(e.dev).to(tdt)
+    off = torch.from_numpy(np.r_[0, np.cumsum(sizes)].astype(np.int32)).to(e.dev)
+    Eg = e.embed(Xd, Yd, off, dtype=tdt).double().cpu().numpy()
+    want = O.distbo_net(O.NP, X, Y, sizes, p, embed_op=embed_op, model_type=model_type)
+    assert Eg.shape[1] >= want.shape[1]
+    assert rel(Eg[:, :want.shape[1]], want) < tol
+
+
+@pytest.mark.parametrize("mode", ["none", "joint", "class"])
+def test_embed_backward(cuda_engine_mod, mode):
+    eng = cuda_engine_mod
+    rs = np.random.RandomState(12)
+    sizes = [200, 130, 77, 1]
+    S = sum(sizes)
+    if mode == "class":
+        dx, dy, y_mode, model_type, embed_op = 16, 2, 2, "classification", "joint"
+        X = (rs.rand(S, dx) < 0.3).astype(np.float64)
+        Y = np.eye(2)[(rs.rand(S) < 0.3).astype(int)]
+    else:
+        dx, dy, model_type = 40, 1, "regression"
+        y_mode, embed_op = (0, "none") if mode == "none" else (1, "joint")
+        X = rs.randn(S, dx)
+        Y = rs.rand(S, dy)
+    net = eng.NetSpec(dx, dy, 20, 10, 20 if y_mode == 1 else 0, 10 if y_mode == 1 else 0, y_mode)
+    e = eng.GPEngine(2, n_embed=net.pooled_width, net=net)
+    p = O.build_params(2, "dist", in_dim_x=dx, in_dim_y=dy, weight_dim_x=[20, 10], weight_dim_y=[20, 10],
+                       model_type=model_type, embed_op=embed_op, seed=6)
+    p["bias_x_1"] = rs.randn(20) * 0.1
+    for k, v in p.items():
+        if e.params.has(k) and k.startswith(("weights", "bias")):
+            e.params.set(k, v)
+    Xd = torch.from_numpy(X).to(e.dev)
+    Yd = torch.from_numpy(Y).to(e.dev)
+    off = torch.from_numpy(np.r_[0, np.cumsum(sizes)].astype(np.int32)).to(e.dev)
+    Pw = net.pooled_width
+    dE = rs.randn(len(sizes), Pw)
+    e.embed_backward(Xd, Yd, off, torch.from_numpy(dE).to(e.dev))
+    tp = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=True) for k, v in p.items()}
+    out = O.distbo_net(O.TH(), torch.from_numpy(X), torch.from_numpy(Y), sizes, tp, embed_op=embed_op,
+                       model_type=model_type)
+    (out * torch.from_numpy(dE)).sum().backward()
+    for name in e.params.offsets:
+        if name.startswith(("weights", "bias")):
+            assert rel(e.params.get_grad(name), tp[name].grad.numpy()) < 1e-10, name
+
+
+def test_adam_matches_tf_form(cuda_engine_mod):
+    eng = cuda_engine_mod
+    e = eng.GPEngine(3)
+    rs = np.random.RandomState(0)
+    x0 = rs.randn(e.params.n)
+    e.params.flat.copy_(torch.from_numpy(x0))
+    adam = O.TFAdam(0.005)
+    ref = {"x": x0.copy()}
+    for step in range(5):
+        g = rs.randn(e.params.n) * 10
+        e.params.grad.copy_(torch.from_numpy(g))
+        e.adam_step(0.005, clip_norm=5.0 if step % 2 else 0.0)
+        ref = adam.step(ref, {"x": g}, clip_norm=5.0 if step % 2 else None)
+        assert rel(e.params.flat.cpu().numpy(), ref["x"]) < 1e-14
