@@ -15,91 +15,9 @@
 
 #include "../../include/distbo_b200.h"
 #include "gemm_core.cuh"
+#include "potf2.cuh"
 
 namespace db {
-
-// ------------------------------------------------------------------ diagonal block: potf2 + inverse
-constexpr int PB = 128;
-constexpr int PLD = 129;
-constexpr int POTF2_THREADS = 256;
-constexpr int POTF2_SMEM = (PB * PLD + 2 * PB) * (int)sizeof(double);
-
-__global__ void __launch_bounds__(POTF2_THREADS, 1)
-potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int blk, int32_t* info) {
-  extern __shared__ __align__(16) double s[];
-  double* sA = s;                 // lower: L ; strictly upper: W^T (sA[j][i] = W[i][j], i > j)
-  double* sD = s + PB * PLD;      // diag of L
-  double* sI = sD + PB;           // diag of W
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* Ab = A + (size_t)blk * PB * ld + (size_t)blk * PB;
-  double* Wb = W + (size_t)blk * PB * ld + (size_t)blk * PB;
-
-  for (int idx = tid; idx < PB * PB; idx += POTF2_THREADS) {
-    int r = idx >> 7, c = idx & 127;
-    sA[r * PLD + c] = (c <= r) ? Ab[(size_t)r * ld + c] : 0.0;
-  }
-  __syncthreads();
-
-  for (int j = 0; j < PB; ++j) {
-    const double d = sA[j * PLD + j];
-    if (!(d > 0.0) && tid == 0 && *info == 0) *info = blk * PB + j + 1;
-    const double sj = sqrt(d);
-    if (tid == 0) sD[j] = sj;
-    for (int i = j + 1 + tid; i < PB; i += POTF2_THREADS) sA[i * PLD + j] /= sj;
-    __syncthreads();
-    for (int i = j + 1 + warp; i < PB; i += POTF2_THREADS / 32) {
-      const double lij = sA[i * PLD + j];
-      for (int k = j + 1 + lane; k <= i; k += 32) sA[i * PLD + k] -= lij * sA[k * PLD + j];
-    }
-    __syncthreads();
-  }
-
-  // W = L^-1 by forward substitution, one column per thread (first 128 threads).
-  if (tid < PB) {
-    const int j = tid;
-    const int jmin = j & ~31;  // first column of this warp: common k range for lockstep lanes
-    const double wjj = 1.0 / sD[j];
-    sI[j] = wjj;
-    for (int i = jmin + 1; i < PB; ++i) {
-      double a0 = 0.0, a1 = 0.0;
-      int k = jmin + 1;
-      for (; k + 1 < i; k += 2) {
-        const double l0 = sA[i * PLD + k], l1 = sA[i * PLD + k + 1];
-        const double w0 = (k > j) ? sA[j * PLD + k] : 0.0;
-        const double w1 = (k + 1 > j) ? sA[j * PLD + k + 1] : 0.0;
-        a0 += l0 * w0;
-        a1 += l1 * w1;
-      }
-      if (k < i) {
-        const double w0 = (k > j) ? sA[j * PLD + k] : 0.0;
-        a0 += sA[i * PLD + k] * w0;
-      }
-      if (i > j) {
-        const double acc = sA[i * PLD + j] * wjj + (a0 + a1);
-        sA[j * PLD + i] = -acc / sD[i];
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-
-  for (int idx = tid; idx < PB * PB; idx += POTF2_THREADS) {
-    int r = idx >> 7, c = idx & 127;
-    double lv, wv;
-    if (c < r) {
-      lv = sA[r * PLD + c];
-      wv = sA[c * PLD + r];
-    } else if (c == r) {
-      lv = sD[r];
-      wv = sI[r];
-    } else {
-      lv = 0.0;
-      wv = 0.0;
-    }
-    Ab[(size_t)r * ld + c] = lv;
-    Wb[(size_t)r * ld + c] = wv;
-  }
-}
 
 // ------------------------------------------------------------------ plan
 struct Range {

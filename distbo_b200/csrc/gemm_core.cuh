@@ -118,17 +118,34 @@ template <int ALAY, int BLAY>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tiles_kernel(GemmArgs p) {
   extern __shared__ __align__(16) double smem[];
   const int4 t = p.tiles[blockIdx.x];
-  double acc[8][4][2];
-#pragma unroll
-  for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-  gemm_mainloop<ALAY, BLAY>(acc, p.A, p.lda, p.B, p.ldb, t.x, t.y, t.z, t.w, smem);
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 2, wn = warp & 3;
   const int lr = lane >> 2, lk = lane & 3;
+  // out = alpha * (acc0 + A B) with acc0 = (beta/alpha) Cin: the C tile is fetched into the
+  // accumulators BEFORE the main loop so that its latency hides behind the pipeline prologue.
+  double acc[8][4][2];
+  if (p.beta != 0.0) {
+    const double f = p.beta / p.alpha;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      const int row = t.x + wm * 64 + mi * 8 + lr;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int col = t.y + wn * 32 + ni * 8 + lk * 2;
+        const double2 c = *reinterpret_cast<const double2*>(p.Cin + (size_t)row * p.ldcin + col);
+        acc[mi][ni][0] = f * c.x;
+        acc[mi][ni][1] = f * c.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  }
+
+  gemm_mainloop<ALAY, BLAY>(acc, p.A, p.lda, p.B, p.ldb, t.x, t.y, t.z, t.w, smem);
+
 #pragma unroll
   for (int mi = 0; mi < 8; ++mi) {
     const int row = t.x + wm * 64 + mi * 8 + lr;
@@ -138,11 +155,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tiles_kernel(GemmArgs p)
       double2 v;
       v.x = p.alpha * acc[mi][ni][0];
       v.y = p.alpha * acc[mi][ni][1];
-      if (p.beta != 0.0) {
-        const double2 c = *reinterpret_cast<const double2*>(p.Cin + (size_t)row * p.ldcin + col);
-        v.x += p.beta * c.x;
-        v.y += p.beta * c.y;
-      }
       *reinterpret_cast<double2*>(p.C + (size_t)row * p.ldc + col) = v;
     }
   }

@@ -1,0 +1,230 @@
+// Diagonal block of the blocked Cholesky: potf2 + inverse of a 128x128 block by ONE CTA.
+//   factor : right-looking over four 32-wide sub-panels; the 32x32 diagonal sub-block is factorised
+//            and inverted by one warp entirely in registers (lane = row / column, operands exchanged
+//            by warp shuffles); the sub-panel solve (x Dinv^T) and the trailing update run on DMMA.
+//   inverse: block forward substitution over the 4x4 grid of 32x32 blocks on DMMA,
+//            W_ij = -W_ii * sum_{k=j}^{i-1} L_ik W_kj, by block distance (3 dependent levels).
+// Shared layout: sA [128][132] holds L in its lower part; the strictly upper 32-blocks (j,i) receive
+// W_ij^T; the four diagonal inverses live in sDinv [4][32][36]; sS [3][32][36] is the S scratch.
+// Row strides 132 / 36 (== 4 mod 16 doubles) make every m8n8k4 fragment load conflict free.
+#pragma once
+#include "common.cuh"
+
+namespace db {
+
+constexpr int PB = 128;
+constexpr int PLD = 132;
+constexpr int SB = 32;
+constexpr int DLD = 36;
+constexpr int POTF2_THREADS = 256;
+constexpr int POTF2_SMEM = (PB * PLD + 4 * SB * DLD + 3 * SB * DLD + SB) * (int)sizeof(double);
+
+// Branch-free 1/sqrt(d) for d > 0 in the float range: MUFU.RSQ seed + two Newton steps (~1 ulp).
+// No slow-path branches, so the surrounding warp stays provably convergent (no WARPSYNC per shuffle).
+__device__ __forceinline__ double rsqrt_nr(double d) {
+  double y = (double)rsqrtf((float)d);
+  const double h = 0.5 * d;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
+}
+
+// Factor the 32x32 block at sA[c0.., c0..] (lower) entirely in registers: lane = row, operands exchanged
+// by warp shuffles.  Executed by EVERY warp of the CTA redundantly so that the shuffles sit in fully
+// convergent code (a warp-id guard would cost a WARPSYNC/ENDCOLLECTIVE pair per shuffle); only warp 0
+// stores.  a[] returns row `lane` of L, myr = 1/L[lane][lane].  Returns the 1-based local index of the
+// first non-positive pivot (0 = ok), identical in all lanes.
+__device__ __forceinline__ int factor_32(double (&a)[SB], double& myr, int lane) {
+  int bad = 0;
+  myr = 0.0;
+#pragma unroll
+  for (int j = 0; j < SB; ++j) {
+    const double d = __shfl_sync(0xffffffffu, a[j], j);
+    bad = (!(d > 0.0) && bad == 0) ? j + 1 : bad;
+    double y = rsqrt_nr(d);
+    double sq = d * y;
+    sq = fma(0.5 * y, fma(-sq, sq, d), sq);   // sqrt(d), one correction step
+    y = fma(y, fma(-sq, y, 1.0), y);          // 1/sqrt(d) consistent with sq
+    a[j] = (lane == j) ? sq : a[j] * y;       // lanes < j hold junk in a[j]; never used
+    myr = (lane == j) ? y : myr;
+#pragma unroll
+    for (int k = 0; k < SB; ++k) {
+      if (k > j) {  // folds at compile time after full unrolling
+        const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+        a[k] = (lane >= k) ? fma(-a[j], lkj, a[k]) : a[k];
+      }
+    }
+  }
+  return bad;
+}
+
+// Inverse of the 32x32 lower-triangular block just stored at sA[c0.., c0..]: lane j owns column j of
+// Dinv; L[i][k] and 1/L[i][i] come from shared memory as broadcast loads (no shuffles: may run under a
+// warp-id guard).  dinv is row-major [32][DLD] with explicit zeros above the diagonal.
+__device__ __forceinline__ void invert_32(const double* sA, int c0, double* dinv, const double* rinv, int lane) {
+  double w[SB];
+#pragma unroll
+  for (int i = 0; i < SB; ++i) {
+    double acc0 = (lane == i) ? 1.0 : 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < SB; ++k) {
+      if (k < i) {
+        const double lik = sA[(c0 + i) * PLD + c0 + k];
+        if (k & 1) acc1 = fma(-lik, w[k], acc1);
+        else acc0 = fma(-lik, w[k], acc0);
+      }
+    }
+    w[i] = (acc0 + acc1) * rinv[i];
+  }
+#pragma unroll
+  for (int k = 0; k < SB; ++k) dinv[k * DLD + lane] = w[k];  // Dinv[k][lane]
+}
+
+__global__ void __launch_bounds__(POTF2_THREADS, 1)
+potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int blk, int32_t* info
+#ifdef POTF2_TIMING
+                 , long long* dbg
+#endif
+) {
+#ifdef POTF2_TIMING
+  int dbgn = 0;
+#define PT_STAMP() do { if (threadIdx.x == 0) dbg[dbgn++] = clock64(); } while (0)
+#else
+#define PT_STAMP() do {} while (0)
+#endif
+  PT_STAMP();
+  extern __shared__ __align__(16) double s[];
+  double* sA = s;
+  double* sDinv = s + PB * PLD;
+  double* sS = sDinv + 4 * SB * DLD;
+  double* sR = sS + 3 * SB * DLD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
+  double* Ab = A + (size_t)blk * PB * ld + (size_t)blk * PB;
+  double* Wb = W + (size_t)blk * PB * ld + (size_t)blk * PB;
+
+#pragma unroll 16
+  for (int it = 0; it < PB * PB / POTF2_THREADS; ++it) {
+    const int idx = tid + it * POTF2_THREADS;
+    const int r = idx >> 7, c = idx & 127;
+    sA[r * PLD + c] = (c <= r) ? Ab[(size_t)r * ld + c] : 0.0;
+  }
+  __syncthreads();
+  PT_STAMP();
+
+  for (int jb = 0; jb < 4; ++jb) {
+    const int c0 = jb * SB;
+    {
+      double a[SB], myr;
+#pragma unroll
+      for (int k = 0; k < SB; ++k) a[k] = sA[(c0 + lane) * PLD + c0 + k];
+      __syncthreads();  // every warp has read the block before warp 0 overwrites it
+      const int bad = factor_32(a, myr, lane);
+      if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < SB; ++k)
+          if (k <= lane) sA[(c0 + lane) * PLD + c0 + k] = a[k];
+        sR[lane] = myr;
+        if (bad && lane == 0 && *info == 0) *info = blk * PB + c0 + bad;
+      }
+    }
+    __syncthreads();
+    PT_STAMP();
+    if (warp == 0) invert_32(sA, c0, sDinv + jb * SB * DLD, sR, lane);
+    __syncthreads();
+    PT_STAMP();
+    const int nrg = (PB - c0 - SB) / 8;  // 8-row groups below the diagonal sub-block
+    // sub-panel solve: P <- P * Dinv^T (each warp owns whole 8-row groups: in place is safe)
+    for (int rg = warp; rg < nrg; rg += 8) {
+      const int r0 = c0 + SB + rg * 8;
+      double af[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) af[kk] = sA[(r0 + lr) * PLD + c0 + kk * 4 + lk];
+      double acc[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          dmma884(acc[nt][0], acc[nt][1], af[kk], sDinv[jb * SB * DLD + (nt * 8 + lr) * DLD + kk * 4 + lk]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        *reinterpret_cast<double2*>(&sA[(r0 + lr) * PLD + c0 + nt * 8 + 2 * lk]) =
+            make_double2(acc[nt][0], acc[nt][1]);
+    }
+    __syncthreads();
+    PT_STAMP();
+    // trailing update of the lower 8x8 tiles: C -= P P^T
+    const int ntile = nrg * (nrg + 1) / 2;
+    for (int t = warp; t < ntile; t += 8) {
+      int ri = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+      while ((ri + 1) * (ri + 2) / 2 <= t) ++ri;
+      while (ri * (ri + 1) / 2 > t) --ri;
+      const int ci = t - ri * (ri + 1) / 2;
+      const int r0 = c0 + SB + ri * 8, q0 = c0 + SB + ci * 8;
+      double2 c = *reinterpret_cast<double2*>(&sA[(r0 + lr) * PLD + q0 + 2 * lk]);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        dmma884(c.x, c.y, -sA[(r0 + lr) * PLD + c0 + kk * 4 + lk], sA[(q0 + lr) * PLD + c0 + kk * 4 + lk]);
+      __syncwarp();
+      *reinterpret_cast<double2*>(&sA[(r0 + lr) * PLD + q0 + 2 * lk]) = c;
+    }
+    __syncthreads();
+    PT_STAMP();
+  }
+
+  // ---- inverse by block distance
+  for (int dist = 1; dist < 4; ++dist) {
+    const int nblk = 4 - dist;
+    for (int t = warp; t < nblk * 16; t += 8) {
+      const int b = t >> 4, tr = (t >> 2) & 3, tc = t & 3;
+      const int j = b, i = b + dist;
+      double c0v = 0.0, c1v = 0.0;
+      for (int kb = j; kb < i; ++kb) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const double av = sA[(SB * i + tr * 8 + lr) * PLD + SB * kb + kk * 4 + lk];
+          const double bv = (kb == j) ? sDinv[j * SB * DLD + (kk * 4 + lk) * DLD + tc * 8 + lr]
+                                      : sA[(SB * j + tc * 8 + lr) * PLD + SB * kb + kk * 4 + lk];
+          dmma884(c0v, c1v, av, bv);
+        }
+      }
+      *reinterpret_cast<double2*>(&sS[b * SB * DLD + (tr * 8 + lr) * DLD + tc * 8 + 2 * lk]) =
+          make_double2(c0v, c1v);
+    }
+    __syncthreads();
+    for (int t = warp; t < nblk * 16; t += 8) {
+      const int b = t >> 4, tr = (t >> 2) & 3, tc = t & 3;
+      const int j = b, i = b + dist;
+      double c0v = 0.0, c1v = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        dmma884(c0v, c1v, sDinv[i * SB * DLD + (tr * 8 + lr) * DLD + kk * 4 + lk],
+                sS[b * SB * DLD + (kk * 4 + lk) * DLD + tc * 8 + lr]);
+      // W_ij[r][c] -> transposed into the upper block (j,i)
+      const int r = tr * 8 + lr, c = tc * 8 + 2 * lk;
+      sA[(SB * j + c) * PLD + SB * i + r] = -c0v;
+      sA[(SB * j + c + 1) * PLD + SB * i + r] = -c1v;
+    }
+    __syncthreads();
+    PT_STAMP();
+  }
+
+#pragma unroll 8
+  for (int it = 0; it < PB * PB / POTF2_THREADS; ++it) {
+    const int idx = tid + it * POTF2_THREADS;
+    const int r = idx >> 7, c = idx & 127;
+    const int rb = r >> 5, cb = c >> 5;
+    double lv = 0.0, wv = 0.0;
+    if (c <= r) lv = sA[r * PLD + c];
+    if (rb == cb) wv = sDinv[rb * SB * DLD + (r & 31) * DLD + (c & 31)];
+    else if (rb > cb) wv = sA[c * PLD + r];
+    Ab[(size_t)r * ld + c] = lv;
+    Wb[(size_t)r * ld + c] = wv;
+  }
+  PT_STAMP();
+}
+
+}  // namespace db
