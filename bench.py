@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the distBO joint-GP hot path on B200 (BASELINE.json).
+
+Workload (BASELINE config 5 "synthetic scale-up"): 64 source tasks x 128
+observations = N 8192, d_theta 8, protein-like datasets (5000 rows x 166 binary features, 2 classes;
+embedding width P = 23), 2^20 uniform EI candidates.  One "step" = one acquisition pass of the hot
+path over all M candidates: K_* generation -> W K_* on FP64 tensor cores -> mean / variance ->
+EI -> arg-max, the candidates sharded over the ranks (strong scaling: M is fixed) and the per-GPU
+best merged by an all-gather.
+
+    python bench.py --gpus N --steps K --warmup W           # this repository (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...           # CPU restatement of the reference
+
+Prints ONE JSON line on rank 0 (see README / DESIGN.md section "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ei_candidates_per_sec_at_N8192"
+UNIT = "candidates/s"
+N_OBS, T_SRC, D_THETA = 8192, 64, 8
+DX, DY, ROWS, BATCH_ROWS = 166, 2, 5000, 1000
+WEIGHT_DIM_X = (20, 10)
+M_DEFAULT = 1 << 20
+XI, KAPPA = 0.01, 2.58           # experiments/train_test.py:63-64
+FP64_FALLBACK_TFLOPS = 35.5      # cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peak.json)
+
+
+# ----------------------------------------------------------------------------------- workload
+def make_workload(n_obs, m_cand, rows, seed=0):
+    """Synthetic inputs of config 5, all from numpy RandomState streams (host)."""
+    rs = np.random.RandomState(seed)
+    per_task = n_obs // T_SRC
+    sizes = [per_task] * T_SRC
+    theta = rs.uniform(-5.0, 5.0, size=(n_obs, D_THETA))
+    w = rs.randn(D_THETA) / np.sqrt(D_THETA)
+    task_shift = np.repeat(rs.randn(T_SRC) * 0.3, per_task)
+    y = np.sin(theta @ w) + task_shift + 0.1 * rs.randn(n_obs)
+    data_X, data_Y = [], []
+    for t in range(T_SRC + 1):
+        rate = 0.2 + 0.2 * rs.rand()
+        data_X.append((rs.rand(rows, DX) < rate).astype(np.float64))
+        lab = (rs.rand(rows) < 0.3).astype(int)
+        data_Y.append(np.eye(DY)[lab])
+    weights = {
+        "weights_x_1": (rs.randn(DX, WEIGHT_DIM_X[0]) * np.sqrt(2.0 / (DX + WEIGHT_DIM_X[0]))).astype(np.float32),
+        "bias_x_1": np.zeros(WEIGHT_DIM_X[0]),
+        "weights_x_2": (rs.randn(*WEIGHT_DIM_X) * np.sqrt(2.0 / sum(WEIGHT_DIM_X))).astype(np.float32),
+    }
+    cand = np.random.RandomState(2).uniform(-5.0, 5.0, size=(m_cand, D_THETA))
+    return dict(theta=theta, y=y, sizes=sizes, data_X=data_X, data_Y=data_Y, weights=weights, cand=cand,
+                y_max=float(y.max()), rows=rows)
+
+
+def fit_kwargs(work, max_epochs, lkh_var):
+    return dict(data_X=work["data_X"][:T_SRC], data_Y=work["data_Y"][:T_SRC], source_embed_ind=None,
+                embed_op="joint", algorithm="GP", weight_dim_x=list(WEIGHT_DIM_X), batch_size=BATCH_ROWS,
+                sizes=work["sizes"], concat_data_size=True, learning_rate=0.005, max_epochs=max_epochs,
+                max_size=work["rows"], likhd_var_init=lkh_var, stratify=True, gradient_clip=False,
+                first_early_stop_epoch=10 ** 9)
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    HW = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_ev = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_ev.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.HW.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_ev.wait(self.period)
+
+    def finish(self):
+        self._stop_ev.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(work, lkh_var, m_sample, steps, warmup):
+    """The reference's CPU op sequence for this path (oracle restatement; TF 1.7 cannot run here):
+    embeddings of the full sample sets, k_dist / k_dist_pred, Gram + Cholesky + V (candidate
+    independent, re-evaluated by the reference on every predict call), then per candidate K_*,
+    L^-1 K_*, mean, variance, EI, arg-max.  Returns seconds: (t_fixed, [t_var per step])."""
+    from oracle import gp_oracle as O
+    p = O.build_params(D_THETA, "dist", in_dim_x=DX, in_dim_y=DY, weight_dim_x=list(WEIGHT_DIM_X),
+                       model_type="classification", embed_op="joint", concat_data_size=True,
+                       likhd_var_init=lkh_var)
+    for k, v in work["weights"].items():
+        p[k] = np.asarray(v, dtype=np.float64)
+    from sklearn.preprocessing import StandardScaler
+    sc = StandardScaler().fit(work["theta"])
+    theta = sc.transform(work["theta"])
+    rows = work["rows"]
+    batch = O.TrainBatch(h_params=theta, obs=work["y"][:, None], sizes=work["sizes"],
+                         batch_X=np.vstack(work["data_X"][:T_SRC]), batch_y=np.vstack(work["data_Y"][:T_SRC]),
+                         embed_sizes=[rows] * T_SRC, data_sizes=[rows] * T_SRC, max_size=rows)
+    t0 = time.perf_counter()
+    k_dist, k_dist_pred = O.embed_grams(O.NP, p, batch, work["data_X"][T_SRC], work["data_Y"][T_SRC], [rows],
+                                        [rows], 1, embed_op="joint", model_type="classification")
+    L, V = O.predict_factor(O.NP, p, "dist", batch, k_dist=k_dist)
+    t_fixed = time.perf_counter() - t0
+    del k_dist
+    cand = sc.transform(work["cand"][:m_sample])
+    t_var = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        mean, var = O.predict_apply(O.NP, p, "dist", batch, L, V, cand, k_dist_pred=k_dist_pred)
+        ei = O.acq_ei(mean, O.std_from_var(var), work["y_max"], XI)
+        best = int(np.argmax(ei))
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            t_var.append(dt)
+    return t_fixed, t_var, best
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    m = args.candidates
+    m_s = min(m, args.cpu_sample)
+    work = make_workload(N_OBS, m_s, ROWS)
+    t_fixed, t_var, _ = cpu_reference(work, args.lkh_var, m_s, args.steps, args.warmup)
+    tv = float(np.mean(t_var))
+    step_s = t_fixed + tv * (m / m_s)          # one acquisition pass over all M candidates
+    value = m / step_s
+    sample = ("oracle restatement (numpy/scipy OpenBLAS fp64): Gram+Cholesky+V timed once (%.2f s), K_*/solve/EI/"
+              "argmax timed per step on the first %d of %d candidates (%.3f s mean); value extrapolates "
+              "linearly in M to the full pass" % (t_fixed, m_s, m, tv))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config5_synthetic_scaleup", "n_obs": N_OBS, "tasks": T_SRC, "d_theta": D_THETA,
+                       "candidates": m, "acq": "ei"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------- CUDA arm
+def fp64_peak(torch, dev):
+    """FP64 tensor-core denominator: MEASURED_PEAKS.json carries no FP64 figure, so cuBLAS DGEMM
+    8192^3 is timed here (best of 5 after warm-up), as the driver does for bf16."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    best = 1e30
+    for i in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / best / 1e9
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from distbo_b200 import _lib
+    from distbo_b200.bayes_opt import UtilityFunction
+    from distbo_b200.train import gp_regressor
+    lib = _lib.load()
+
+    M, K, Wm = args.candidates, args.steps, args.warmup
+    work = make_workload(N_OBS, M, ROWS)
+    tgt = T_SRC
+    gp = gp_regressor("dist", target_X=work["data_X"][tgt], target_Y=work["data_Y"][tgt],
+                      model_type="classification", seed=0, target_embed_ind=np.arange(ROWS), float64=False)
+    gp.initial_weights = work["weights"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- fit: loss + full gradient + Adam, one GPU (rank 0), replicas elsewhere idle
+    fit = {}
+    if rank == 0:
+        gp.maximise_likhd(work["theta"], work["y"][:, None], **fit_kwargs(work, max(Wm, 3), args.lkh_var))
+        torch.cuda.synchronize()
+        lib.distbo_launch_count(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kf = max(K, 3)
+        e0.record()
+        for _ in range(kf):
+            gp.run_epoch()
+        e1.record()
+        torch.cuda.synchronize()
+        loss = gp.engine.read_loss()
+        fit_ms = e0.elapsed_time(e1) / kf
+        fit = {"fit_ms": fit_ms, "fit_launches_per_step": lib.distbo_launch_count(1) // kf, "nll": loss}
+    else:
+        gp.maximise_likhd(work["theta"], work["y"][:, None], **fit_kwargs(work, 1, args.lkh_var))
+    barrier()
+
+    # ---------------- handoff: posterior state on rank 0, broadcast to the scoring ranks
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize()
+    e0.record()
+    gp._fit_generation += 1
+    gp._prepare_predict()
+    e1.record()
+    eng = gp.engine
+    gp.shards.broadcast_fit([eng.W, eng.V, eng.theta_s, eng.sqnorm, eng.kvec, eng.params.flat], src=0)
+    e2.record()
+    torch.cuda.synchronize()
+    refresh_ms, bcast_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+
+    # ---------------- scoring, candidates resident in HBM
+    lo, hi = gp.shards.range(M)
+    cand_host = torch.from_numpy(work["cand"]).pin_memory()
+    cand_dev = cand_host[lo:hi].to(dev)
+    y_max = work["y_max"]
+
+    def step_resident():
+        out = eng.score(cand_dev, acq="ei", y_max=y_max, xi=XI, kappa=KAPPA, want_arrays=False,
+                        index_offset=lo, scaler=gp._scaler_dev)
+        from distbo_b200.sharding import pack_best
+        return gp.shards.all_gather_best(pack_best(out["best_val"], out["best_idx"]))
+
+    for _ in range(Wm):
+        step_resident()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    lib.distbo_launch_count(1)
+    lib.distbo_score_timing(1)
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        recs = step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    launches = int(lib.distbo_launch_count(1))
+    kms, kn = _lib.C.c_double(0.0), _lib.C.c_int64(0)
+    lib.distbo_score_timing_read(_lib.C.byref(kms), _lib.C.byref(kn))
+    lib.distbo_score_timing(0)
+    ms_step = max_over_ranks(ms_local) / K
+    value = M / (ms_step / 1e3)
+    from distbo_b200.sharding import merge_best, unpack_best
+    vals, idxs = unpack_best(recs)
+    best_resident = merge_best(vals.cpu().numpy(), idxs.cpu().numpy())
+
+    # ---------------- end to end through the public API: host candidates in, arg-max out
+    util = UtilityFunction("ei", kappa=KAPPA, xi=XI)
+    for _ in range(2):
+        util.argmax(cand_host, gp, y_max)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        best_e2e = util.argmax(cand_host, gp, y_max)
+    torch.cuda.synchronize()
+    e2e_local = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(e2e_local) / K
+    clk = clocks.finish()
+    assert best_e2e[1] == best_resident[1], (best_e2e, best_resident)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel (score_kernel), peaks
+    peak_src = "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"
+    try:
+        peak = fp64_peak(torch, dev)
+    except Exception:
+        peak, peak_src = FP64_FALLBACK_TFLOPS, "fallback: profiles/r01_fp64_peak.json"
+    n_pad = eng.n_pad
+    chunk = lib.distbo_score_chunk()
+    flops_per_cand = float(N_OBS) ** 2 + 2.0 * N_OBS          # triangular solve + k_*.alpha
+    n_launch = max(int(kn.value), 1)
+    cands_per_launch = (hi - lo) * K / n_launch
+    avg_ms = kms.value / n_launch
+    achieved = flops_per_cand * cands_per_launch / (avg_ms / 1e3) / 1e12
+    roofline = {"kernel": "score_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": avg_ms, "launches_timed": n_launch, "candidates_per_launch": cands_per_launch,
+                "share_of_step": kms.value / ms_local}
+    fit_flops = float(n_pad) ** 3
+    fit["fit_tflops"] = fit_flops / (fit["fit_ms"] / 1e3) / 1e12
+    fit["fit_frac_of_fp64_peak"] = fit["fit_tflops"] / peak
+    fit["fit_flops_counted"] = "N^3 (POTRF N^3/3 + inverse 2N^3/3), N=%d" % n_pad
+
+    # ---------------- CPU baseline (N=1 only): the oracle port on a bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        m_s = min(M, args.cpu_sample)
+        t_fixed, t_var, best_cpu = cpu_reference(work, args.lkh_var, m_s, 1, 0)
+        step_s = t_fixed + t_var[0] * (M / m_s)
+        # same arg-max on the sample as the CUDA path gives on that prefix
+        v_gpu, i_gpu = gp.acquire(work["cand"][:m_s], "ei", y_max=y_max, xi=XI, kappa=KAPPA)
+        cpu = {"value": M / step_s, "unit": UNIT, "cores": host_threads(), "kind": "port",
+               "sample": "Gram+Cholesky+V once %.2f s; K_*/solve/EI/argmax on the first %d candidates %.2f s; "
+                         "extrapolated linearly to M=%d" % (t_fixed, m_s, t_var[0], M),
+               "argmax_matches_gpu_on_sample": bool(best_cpu == i_gpu)}
+
+    bi = (hi - lo) * D_THETA * 8
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config5_synthetic_scaleup", "n_obs": N_OBS, "tasks": T_SRC, "d_theta": D_THETA,
+                       "candidates": M, "acq": "ei", "embed": "protein-like 65x%dx%d fp32, P=23" % (ROWS, DX),
+                       "lkh_var": args.lkh_var, "parallelism": "candidate shards x%d" % world,
+                       "l2": "inputs larger than L2 (W = L^-1 is %d MB, K_* chunk %d MB)" %
+                             (n_pad * n_pad * 8 >> 20, chunk * n_pad * 8 >> 20)},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": M / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 16 * world,
+                    "api": "UtilityFunction.argmax(x_tries_host, gp, y_max) -> gp_regressor.acquire"},
+            "gpu_launches": launches, "clocks": clk,
+            "handoff": {"refresh_ms": refresh_ms, "broadcast_ms": bcast_ms,
+                        "what": "embed 65 full sample sets + task Gram + K + POTRF + TRTRI + V, then NCCL "
+                                "broadcast of W, V, theta, kvec"},
+            "best": {"index": best_resident[1], "value": best_resident[0]}}
+    line.update(fit)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--candidates", type=int, default=M_DEFAULT)
+    ap.add_argument("--lkh-var", type=float, default=1e-2)
+    ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3 if args.candidates == M_DEFAULT else args.warmup
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

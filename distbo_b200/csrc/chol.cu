@@ -54,7 +54,15 @@ static bool longer_k(const int4& a, const int4& b) { return (a.w - a.z) > (b.w -
 
 using namespace db;
 
+long long g_db_launches = 0;
+
 extern "C" int distbo_version(void) { return 1000; }
+
+extern "C" int64_t distbo_launch_count(int reset) {
+  const long long v = g_db_launches;
+  if (reset) g_db_launches = 0;
+  return (int64_t)v;
+}
 
 extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
   if (n_pad <= 0 || n_pad % 128 != 0 || !plan_out) return DISTBO_EARG;

@@ -7,10 +7,14 @@
 #define DISTBO_EARG (-1)
 #define DISTBO_ECUDA (-2)
 
+// Number of kernels this library has launched (distbo_launch_count); host-side bookkeeping only.
+extern long long g_db_launches;
+
 #define DB_CHECK_LAUNCH()                                                  \
   do {                                                                     \
     cudaError_t e__ = cudaGetLastError();                                  \
     if (e__ != cudaSuccess) return DISTBO_ECUDA;                           \
+    ++g_db_launches;                                                       \
   } while (0)
 
 #define DB_CUDA(x)                                                         \

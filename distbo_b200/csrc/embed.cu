@@ -212,6 +212,7 @@ static int embed_fwd_launch(const EmbedArgs<T>& a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   DB_CUDA(cudaLaunchKernelEx(&cfg, embed_fwd_kernel<T>, a));
+  ++g_db_launches;
   return DISTBO_OK;
 }
 

@@ -171,6 +171,7 @@ inline cudaError_t launch_gemm_tiles(const GemmArgs& p, int ntiles, cudaStream_t
     configured = true;
   }
   gemm_tiles_kernel<ALAY, BLAY><<<ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+  ++g_db_launches;
   return cudaGetLastError();
 }
 

@@ -12,6 +12,8 @@
 //                    then the acquisition epilogue and a per-CTA (max value, lowest index);
 //   merge_kernel   : deterministic (max value, min index) merge into the running best.
 #include "../../include/distbo_b200.h"
+#include <vector>
+
 #include "gemm_core.cuh"
 
 namespace db {
@@ -24,7 +26,9 @@ __global__ void __launch_bounds__(256) kst_kernel(const double* __restrict__ the
                                                   const double* __restrict__ log_bw,
                                                   const double* __restrict__ kvec,
                                                   const double* __restrict__ log_scale,
-                                                  const double* __restrict__ theta_c, long long c_begin,
+                                                  const double* __restrict__ theta_c,
+                                                  const double* __restrict__ c_shift,
+                                                  const double* __restrict__ c_scale, long long c_begin,
                                                   long long M, double* __restrict__ Kst) {
   __shared__ double ys[KST_CAND][SCORE_DMAX];
   __shared__ double ysq[KST_CAND];
@@ -34,7 +38,11 @@ __global__ void __launch_bounds__(256) kst_kernel(const double* __restrict__ the
     const int q = tid / SCORE_DMAX, k = tid % SCORE_DMAX;
     const long long c = c_begin + cl0 + q;
     double v = 0.0;
-    if (k < d && c < M) v = theta_c[c * d + k] / exp(log_bw[k]);
+    if (k < d && c < M) {
+      v = theta_c[c * d + k];
+      if (c_shift) v = (v - c_shift[k]) / c_scale[k];  // StandardScaler.transform, gp_regressor.py:161
+      v = v / exp(log_bw[k]);
+    }
     ys[q][k] = v;
   }
   __syncthreads();
@@ -202,9 +210,49 @@ __global__ void merge_best_kernel(const double* __restrict__ bv, const long long
 
 static int g_score_chunk = 0;
 
+// Optional per-launch timing of score_kernel (bench.py's roofline figure): CUDA events recorded on
+// the launching stream around every score_kernel launch while enabled.
+static bool g_timing = false;
+static std::vector<cudaEvent_t> g_ev;   // pairs (begin, end)
+static size_t g_ev_used = 0;
+
+static bool timing_pair(cudaEvent_t* a, cudaEvent_t* b) {
+  if (g_ev_used + 2 > g_ev.size()) {
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return false;
+    g_ev.push_back(e0);
+    g_ev.push_back(e1);
+  }
+  *a = g_ev[g_ev_used];
+  *b = g_ev[g_ev_used + 1];
+  g_ev_used += 2;
+  return true;
+}
+
 }  // namespace db
 
 using namespace db;
+
+extern "C" int distbo_score_timing(int enable) {
+  g_timing = enable != 0;
+  g_ev_used = 0;
+  return DISTBO_OK;
+}
+
+extern "C" int distbo_score_timing_read(double* total_ms, int64_t* launches) {
+  if (!total_ms || !launches) return DISTBO_EARG;
+  double sum = 0.0;
+  for (size_t i = 0; i + 1 < g_ev_used; i += 2) {
+    DB_CUDA(cudaEventSynchronize(g_ev[i + 1]));
+    float ms = 0.f;
+    DB_CUDA(cudaEventElapsedTime(&ms, g_ev[i], g_ev[i + 1]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = (int64_t)(g_ev_used / 2);
+  g_ev_used = 0;
+  return DISTBO_OK;
+}
 
 extern "C" int distbo_score_chunk(void) {
   if (g_score_chunk == 0) {
@@ -221,7 +269,7 @@ extern "C" int distbo_score_chunk(void) {
 extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_pad, const double* theta_s,
                                 const double* sqnorm, int d, const double* log_bw, const double* kvec,
                                 const double* log_scale, const double* mean_param, const double* theta_c,
-                                int64_t M, int acq_kind, double y_max, double xi, double kappa, double* Kst,
+                                const double* cand_shift, const double* cand_scale, int64_t M, int acq_kind, double y_max, double xi, double kappa, double* Kst,
                                 double* out_mean, double* out_std, double* out_acq, double* block_best_val,
                                 int64_t* block_best_idx, double* best_val, int64_t* best_idx,
                                 int64_t index_offset, void* stream) {
@@ -229,7 +277,7 @@ extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_p
       !block_best_val || !block_best_idx || !best_val || !best_idx)
     return DISTBO_EARG;
   if (N <= 0 || n_pad < N || n_pad % 128 || d <= 0 || d > SCORE_DMAX || M <= 0) return DISTBO_EARG;
-  if (acq_kind < 0 || acq_kind > 2) return DISTBO_EARG;
+  if (acq_kind < 0 || acq_kind > 2 || ((cand_shift == nullptr) != (cand_scale == nullptr))) return DISTBO_EARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int chunk = distbo_score_chunk();
   static bool configured = false;
@@ -242,7 +290,8 @@ extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_p
     const int64_t mc = (M - c0 < chunk) ? (M - c0) : chunk;
     const int tiles = (int)((mc + BN - 1) / BN);
     kst_kernel<<<tiles * BN / KST_CAND, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale,
-                                                     theta_c, (long long)c0, (long long)M, Kst);
+                                                     theta_c, cand_shift, cand_scale, (long long)c0, (long long)M,
+                                                     Kst);
     DB_CHECK_LAUNCH();
     ScoreArgs a;
     a.W = W; a.V = V; a.Kst = Kst; a.n_pad = n_pad;
@@ -251,8 +300,12 @@ extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_p
     a.acq_kind = acq_kind; a.y_max = y_max; a.xi = xi; a.kappa = kappa;
     a.out_mean = out_mean; a.out_std = out_std; a.out_acq = out_acq;
     a.block_best_val = block_best_val; a.block_best_idx = (long long*)block_best_idx;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    const bool timed = g_timing && timing_pair(&t0, &t1);
+    if (timed) cudaEventRecord(t0, st);
     score_kernel<<<tiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
     DB_CHECK_LAUNCH();
+    if (timed) cudaEventRecord(t1, st);
     merge_best_kernel<<<1, 32, 0, st>>>(block_best_val, (const long long*)block_best_idx, tiles, first, best_val,
                                         (long long*)best_idx);
     DB_CHECK_LAUNCH();

@@ -306,9 +306,10 @@ class GPEngine:
 
     # ------------------------------------------------------------------ scoring
     def score(self, theta_c, acq="ei", y_max=0.0, xi=0.0, kappa=1.0, want_arrays=True, index_offset=0,
-              kvec=None):
-        """K4 on candidates theta_c [M,d] (device or host array, already scaler-transformed).
-        Returns dict(best_val, best_idx, mean, std, acq) - arrays only when want_arrays."""
+              kvec=None, scaler=None):
+        """K4 on candidates theta_c [M,d] (device or host array).  `scaler` = (mean_, scale_) device
+        tensors [d] of the frozen StandardScaler, applied inside the kernel; None = theta_c is already
+        transformed.  Returns dict(best_val, best_idx, mean, std, acq) - arrays only when want_arrays."""
         assert self.W_valid, "factorize(need_inverse=True) first"
         if not torch.is_tensor(theta_c):
             theta_c = torch.from_numpy(np.ascontiguousarray(theta_c, dtype=np.float64)).to(self.dev)
@@ -330,8 +331,41 @@ class GPEngine:
         rc = self.lib.distbo_score_f64(
             _lib.ptr(self.W), _lib.ptr(self.V), self.N, self.n_pad, _lib.ptr(self.theta_s), _lib.ptr(self.sqnorm),
             self.d, _lib.ptr(p.view("log_bw")), _lib.ptr(kvec), _lib.ptr(p.view("log_scale")),
-            _lib.ptr(p.view("mean")), _lib.ptr(theta_c), M, ACQ[acq], float(y_max), float(xi), float(kappa),
+            _lib.ptr(p.view("mean")), _lib.ptr(theta_c),
+            _lib.ptr(scaler[0]) if scaler is not None else None,
+            _lib.ptr(scaler[1]) if scaler is not None else None, M, ACQ[acq], float(y_max), float(xi), float(kappa),
             _lib.ptr(kst), _lib.ptr(mean), _lib.ptr(std), _lib.ptr(acqv), _lib.ptr(bbv), _lib.ptr(bbi),
             _lib.ptr(self.best_val), _lib.ptr(self.best_idx), int(index_offset), _stream())
         _lib.check(rc, "distbo_score_f64")
         return {"best_val": self.best_val, "best_idx": self.best_idx, "mean": mean, "std": std, "acq": acqv}
+
+    # ------------------------------------------------------------------ one evaluation of loss + gradient
+    def loss_and_grad(self, X=None, Y=None, seg_off=None, E_const=None, size_ratio=None):
+        """One evaluation of the negative log marginal likelihood and its full gradient (what one
+        sess.run([optimize_step, loss]) does in the reference, train/train.py:43-52), as a chain of
+        asynchronous launches on the current stream.  No host synchronisation.
+
+        kernel 'dist'  : X [S,dx], Y [S,dy], seg_off [T+1] = this step's embedding mini-batch;
+                         size_ratio [T] fills the last embedding column (concat_data_size).
+        kernel 'manual': E_const [T,P] meta-features.      kernel 'params': all None.
+        """
+        T = self.T
+        E = None
+        if self.net is not None:
+            if self.E is None or self.E.shape[0] != T or self.E.shape[1] != self.P:
+                self.E = self._f64(T, self.P)
+            E = self.E
+            if size_ratio is not None:
+                E[:, self.P - 1].copy_(size_ratio)
+            self.embed(X, Y, seg_off, out=E)
+        elif E_const is not None:
+            E = E_const
+        KE = self.task_gram(E, T) if E is not None else None
+        self.build_gram(KE)
+        self.factorize(need_inverse=True, need_kinv=True)
+        self.likelihood()
+        self.gram_gradient()
+        if E is not None:
+            dE = self.task_gram_backward(E, T)
+            if self.net is not None:
+                self.embed_backward(X, Y, seg_off, dE)

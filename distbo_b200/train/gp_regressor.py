@@ -1,0 +1,314 @@
+"""Surrogate facade: same interface as the reference's ``gp_regressor`` (train/gp_regressor.py:19-223)
+over the sm_100a engine.
+
+    gp = gp_regressor(kernel, target_X=..., target_Y=..., model_type=..., seed=..., float64=True)
+    loss = gp.maximise_likhd(params, y, **max_lkd_dict)      # Adam on the GP marginal likelihood
+    gp.initialise_predict()
+    mean, std = gp.predict_y(params_pred)                    # numpy [M,1], [M,1]
+    sim = gp.similarity()
+    gp.close()
+
+plus the fused form the BO loop uses when it only needs the maximiser (UtilityFunction.argmax):
+
+    value, index = gp.acquire(params_pred, "ei", y_max=..., xi=...)
+
+State kept across calls, as in the reference: the StandardScaler (frozen after the first fit,
+:58-64), the trainable parameters and Adam slots (:141-143).  Every arithmetic step runs in
+libdistbo_b200.so on the GPU; there is no CPU fallback (GPEngine raises without a device).
+GP arithmetic is fp64 for both values of `float64` (the flag only selects the storage type the
+datasets' rows are embedded from at prediction time: fp32 when False).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+from sklearn.preprocessing import StandardScaler
+from sklearn.utils import check_random_state
+
+from .. import engine as _eng
+from ..sharding import ShardGroup
+from .gp_utils import EmbedBatchSampler, check_dims, init_net_weights
+
+EARLY_STOP_THRESHOLD = 0.0001   # train/train.py:54
+EARLY_STOP_PATIENCE = 100       # train/train.py:55
+
+
+class gp_regressor(object):
+    def __init__(self, kernel, n_cpus=1, target_X=None, target_Y=None, model_type=None, seed=None,
+                 target_embed_ind=None, float64=False):
+        if kernel not in ("dist", "manual", "params"):
+            # 'multi' is the multi-task BO baseline (train/kernels.py:32-55): outside the (theta, mu_D) GP
+            raise NotImplementedError("kernel %r is not part of the joint (theta, embedding) GP path" % (kernel,))
+        self.model_type = model_type
+        self.kernel = kernel
+        self.n_cpus = n_cpus
+        self.float64 = bool(float64)
+        self.seed = seed
+        self.initialise = True
+        self.params_scaler = None
+        self.initial_weights = None      # optional {name: array} injected before the first fit
+        self.shuffle_seed = 0
+        self.engine = None
+        self.shards = ShardGroup()
+        self.loss_history = []
+        self._fit_generation = 0
+        self._predict_generation = -1
+        if target_X is not None:
+            self.data_sizes_target = check_dims([len(target_X)])
+            self.target_embed_ind = target_embed_ind
+            self.target_X, self.target_Y = target_X, target_Y
+
+    # ------------------------------------------------------------------ helpers
+    def _dev(self, a, dtype=torch.float64):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.engine.dev).to(dtype)
+
+    def _stack(self, X_list, Y_list, dtype=torch.float64):
+        sizes = [len(x) for x in X_list]
+        off = np.r_[0, np.cumsum(sizes)].astype(np.int32)
+        X = self._dev(np.vstack([np.asarray(x, dtype=np.float64) for x in X_list]), dtype)
+        Y = self._dev(np.vstack([check_dims(np.asarray(y, dtype=np.float64)) for y in Y_list]), dtype)
+        return X, Y, torch.from_numpy(off).to(self.engine.dev)
+
+    def _build_engine(self, weight_dim_x, weight_dim_y, embed_op, concat_data_size, bw_params_init,
+                      likhd_var_init, target_embed):
+        d = self.in_dim_params
+        net = None
+        P = 0
+        weights = {}
+        if self.kernel == "dist":
+            if embed_op not in ("none", "joint"):
+                raise NotImplementedError("embed_op %r: only 'none' and 'joint' are on the sm_100a path "
+                                          "(SURVEY section 8f ranks 'concat'/'nn' next)" % (embed_op,))
+            weights.update(init_net_weights(self.in_dim_x, weight_dim_x, "x", self.seed))
+            hx, p = int(weight_dim_x[0]), int(weight_dim_x[1])
+            if self.model_type == "classification":
+                net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, 0, 0, y_mode=2)
+            elif embed_op == "joint":
+                weights.update(init_net_weights(self.in_dim_y, weight_dim_y, "y", self.seed))
+                net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, int(weight_dim_y[0]),
+                                   int(weight_dim_y[1]), y_mode=1)
+            else:
+                net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, 0, 0, y_mode=0)
+            # width of the embedding: train/log_gaus_likelihood.py:33-59
+            P = net.pooled_width + (1 if concat_data_size else 0)
+        elif self.kernel == "manual":
+            P = len(target_embed[0])
+        e = _eng.GPEngine(d, n_embed=P, net=net)
+        for k, v in weights.items():
+            e.params.set(k, v)
+        if self.initial_weights:
+            for k, v in self.initial_weights.items():
+                e.params.set(k, v)
+        e.params.set("log_bw", np.log(np.full(d, float(bw_params_init))))
+        e.params.set("log_sigma", 0.5 * math.log(likhd_var_init))   # gp_regressor.py:83
+        self.engine = e
+
+    # ------------------------------------------------------------------ fit
+    def maximise_likhd(self, params, y, data_X=None, data_Y=None, data_embed=None,
+                       source_embed_ind=None, embed_op='joint', algorithm='GP',
+                       weight_dim=None, weight_dim_x=None, num_of_rff=100,
+                       weight_dim_xy=None, weight_dim_y=None, batch_size=250,
+                       sizes=None, target_embed=None, concat_data_size=False,
+                       learning_rate=0.001, max_epochs=200, max_size=None,
+                       bw_params_init=1.0, likhd_var_init=0.01, stratify=True,
+                       gradient_clip=False, first_early_stop_epoch=30):
+        assert len(params) == len(y), 'Configurations and y must be same length'
+        if algorithm != 'GP':
+            raise NotImplementedError("algorithm %r: the BLR surrogate is outside this path (SURVEY 8f)" % (algorithm,))
+        self.target_embed = target_embed
+        self.algorithm = algorithm
+        self.embed_op = embed_op
+        self.concat_data_size = bool(concat_data_size) and self.kernel == "dist"
+        if self.kernel == 'dist':
+            assert len(params) == np.sum(sizes), 'Total sizes must match with number of configurations'
+            assert len(data_X) == len(sizes), 'Number of datasets must equal number of sizes'
+            assert len(data_X) == len(data_Y), 'Number of datasets X must be equal to number of labels'
+            for m, n in zip(data_X, data_Y):
+                assert len(m) == len(n), 'Number of datapoints must equal number of labels'
+            self.in_dim_x = np.shape(data_X[0])[1]
+            self.in_dim_y = np.shape(check_dims(data_Y[0]))[1]
+        self.in_dim_params = np.shape(params)[1]
+        params = np.asarray(params, dtype=np.float64)
+        if self.params_scaler is None:                      # fitted once, then frozen
+            self.params_scaler = StandardScaler()
+            self.params_scaler.fit(params)
+        theta = self.params_scaler.transform(params)
+
+        if self.initialise:
+            self._build_engine(weight_dim_x, weight_dim_y, embed_op, concat_data_size, bw_params_init,
+                               likhd_var_init, target_embed)
+        e = self.engine
+        task_sizes = None if sizes is None or self.kernel == "params" else np.asarray(sizes).reshape(-1)
+        e.set_observations(theta, np.asarray(y, dtype=np.float64).reshape(-1), task_sizes)
+
+        self._E_const = None
+        self._ratio = None
+        sampler = None
+        if self.kernel == 'dist':
+            data_Y = [check_dims(np.asarray(yy)) for yy in data_Y]
+            self._data_sizes = np.asarray([len(x) for x in data_X], dtype=np.float64)
+            self._max_size = max_size
+            if self.concat_data_size:
+                self._ratio = self._dev(self._data_sizes / float(max_size))
+            # rows the embeddings are computed from at prediction time (gp_regressor.py:95-102)
+            if source_embed_ind is None:
+                source_embed_ind = [np.arange(len(x)) for x in data_X]
+            self.source_X = [np.asarray(x)[list(ind)] for x, ind in zip(data_X, source_embed_ind)]
+            self.source_Y = [yy[list(ind)] for yy, ind in zip(data_Y, source_embed_ind)]
+            sampler = EmbedBatchSampler(data_Y, batch_size, check_random_state(self.seed), self.model_type,
+                                        stratify, shuffle_seed=self.shuffle_seed)
+            self._full = self._stack(data_X, data_Y)          # all rows of every dataset, HBM resident
+            full_off = self._full[2].cpu().numpy().astype(np.int64)
+            bs = np.r_[0, np.cumsum(sampler.sizes())].astype(np.int32)
+            batch_off = torch.from_numpy(bs).to(e.dev)
+        elif self.kernel == 'manual':
+            self._E_const = self._dev(np.asarray(data_embed, dtype=np.float64))
+
+        self._sampler, self._full_off = sampler, (full_off if sampler is not None else None)
+        self._batch_off = batch_off if sampler is not None else None
+        self._lr, self._clip = learning_rate, (5.0 if gradient_clip else 0.0)
+        self._scaler_dev = (self._dev(self.params_scaler.mean_), self._dev(self.params_scaler.scale_))
+
+        # ---- training loop: train/train.py:11-71
+        if first_early_stop_epoch is None:
+            first_early_stop_epoch = max_epochs // 5
+        cur_min, countdown = np.inf, np.inf
+        loss = None
+        epoch = -1
+        for epoch in range(int(max_epochs)):
+            self.run_epoch()
+            loss = e.read_loss()
+            self.loss_history.append(loss)
+            if epoch >= first_early_stop_epoch:
+                if (cur_min - loss) > EARLY_STOP_THRESHOLD:
+                    countdown = EARLY_STOP_PATIENCE
+                    cur_min = loss
+                else:
+                    countdown -= 1
+                if countdown <= 0:
+                    break
+        self.last_epoch = epoch
+        self.initialise = False
+        self.pre_compute_embed = True
+        return loss
+
+    def run_epoch(self):
+        """One optimisation step (loss, full gradient, Adam update) queued on the current stream with
+        no host synchronisation: what one sess.run([optimize_step, loss]) is in train/train.py:43-52."""
+        e, sampler = self.engine, self._sampler
+        if sampler is None:
+            e.loss_and_grad(E_const=self._E_const)
+        else:
+            if sampler.constant:
+                bX, bY, boff = self._full
+            else:
+                fo = self._full_off
+                rows = [np.arange(fo[i], fo[i + 1]) if ix is None else fo[i] + ix
+                        for i, ix in enumerate(sampler.next_indices())]
+                gather = torch.from_numpy(np.concatenate(rows)).to(e.dev)
+                bX = self._full[0].index_select(0, gather)
+                bY = self._full[1].index_select(0, gather)
+                boff = self._batch_off
+            e.loss_and_grad(bX, bY, boff, size_ratio=self._ratio)
+        e.adam_step(self._lr, clip_norm=self._clip)
+        self._fit_generation += 1
+
+    # ------------------------------------------------------------------ predict
+    def initialise_predict(self):
+        """The reference builds its prediction graphs here (gp_regressor.py:148-157); the engine has
+        nothing to build, the factorisation for prediction is prepared lazily in predict_y."""
+        return None
+
+    def _embed_sets(self, X_list, Y_list, n_rows_E):
+        """Embeddings of whole sample sets (fp32 rows when float64=False)."""
+        e = self.engine
+        dt = torch.float64 if self.float64 else torch.float32
+        X, Y, off = self._stack(X_list, Y_list, dt)
+        out = torch.zeros(len(X_list), e.P, dtype=dt, device=e.dev)
+        e.embed(X, Y, off, out=out, dtype=dt)
+        return out.double()
+
+    def _prepare_predict(self):
+        """Posterior state at the CURRENT parameters: embeddings of the full sample sets, task Gram over
+        sources + target, K, L, W = L^-1, V, and kvec (what build_predict / build_predict_dist
+        recompute on every call, train/log_gaus_likelihood.py:128-218)."""
+        if self._predict_generation == self._fit_generation:
+            return
+        e = self.engine
+        T = e.T
+        KE = None
+        if self.kernel == "dist":
+            tX = np.asarray(self.target_X)[list(self.target_embed_ind)]
+            tY = check_dims(np.asarray(self.target_Y))[list(self.target_embed_ind)]
+            E_all = self._embed_sets(self.source_X + [tX], self.source_Y + [tY], T + 1)
+            if self.concat_data_size:
+                E_all[:T, e.P - 1] = self._ratio
+                E_all[T, e.P - 1] = float(self.data_sizes_target[0, 0]) / float(self._max_size)
+            self._E_all = E_all
+        elif self.kernel == "manual":
+            self._E_all = torch.cat([self._E_const, self._dev(np.asarray(self.target_embed, dtype=np.float64))], 0)
+        if self.kernel in ("dist", "manual"):
+            KE_all = e.task_gram(self._E_all, T + 1)
+            self._KE_all = KE_all
+            KE = KE_all[:T, :T].contiguous()
+            e.kvec.zero_()
+            e.kvec[:e.N] = KE_all[:T, T][e.task_id.long()]
+        else:
+            e.kvec.zero_()
+            e.kvec[:e.N] = 1.0
+        e.build_gram(KE)
+        e.factorize(need_inverse=True, need_kinv=False)
+        e.likelihood()
+        e.read_loss()          # raises on a failed Cholesky, as TF would
+        self._predict_generation = self._fit_generation
+
+    def predict_y(self, params_pred, refresh_net=False, compute_embed=False):
+        self._prepare_predict()
+        self.pre_compute_embed = bool(compute_embed)
+        # the StandardScaler transform (gp_regressor.py:161) is applied inside the kernel
+        out = self.engine.score(np.asarray(params_pred, dtype=np.float64), acq="ucb", kappa=0.0,
+                                want_arrays=True, scaler=self._scaler_dev)
+        mean = out["mean"].cpu().numpy()[:, None]
+        std = out["std"].cpu().numpy()[:, None]
+        return mean, std
+
+    def acquire(self, params_pred, kind, y_max=0.0, xi=0.0, kappa=1.0, want_values=False):
+        """Fused posterior + acquisition + argmax over the candidate rows `params_pred` [M,d] (host
+        numpy array or host torch tensor, raw scale).  With torch.distributed initialised, every rank passes the SAME array and
+        scores its own contiguous shard; the per-GPU (best value, lowest index) are all-gathered.
+        Returns (best value, best row index[, acquisition values of the local shard])."""
+        self._prepare_predict()
+        e = self.engine
+        M = len(params_pred)
+        lo, hi = self.shards.range(M)
+        if hi > lo:
+            if torch.is_tensor(params_pred):     # host tensor (pinned for an asynchronous copy)
+                cand = params_pred[lo:hi].to(e.dev, non_blocking=True)
+            else:
+                cand = torch.from_numpy(np.ascontiguousarray(params_pred[lo:hi], dtype=np.float64)).to(e.dev)
+            out = e.score(cand, acq=kind, y_max=y_max, xi=xi, kappa=kappa, want_arrays=want_values,
+                          index_offset=lo, scaler=self._scaler_dev)
+            val, idx = out["best_val"], out["best_idx"]
+        else:
+            out = {"acq": None}
+            val = torch.full((1,), float("-inf"), dtype=torch.float64, device=e.dev)
+            idx = torch.full((1,), np.iinfo(np.int64).max, dtype=torch.int64, device=e.dev)
+        best_v, best_i = self.shards.argmax(val, idx)
+        if want_values:
+            return best_v, best_i, (None if out["acq"] is None else out["acq"].cpu().numpy())
+        return best_v, best_i
+
+    def similarity(self, sample_sim=False):
+        """[array [T,1]]: embedding-kernel value between every source task and the target
+        (gp_regressor.py:205-223; train/train.py:86-95)."""
+        if self.kernel == "params":
+            raise ValueError("similarity is defined for the 'dist' and 'manual' kernels")
+        self._prepare_predict()
+        T = self.engine.T
+        return [self._KE_all[:T, T:T + 1].cpu().numpy()]
+
+    def close(self):
+        self.initialise = True
+        self.engine = None

@@ -1,0 +1,112 @@
+"""Host-side helpers of the surrogate (reference distBO/train/gp_utils.py, distBO/utils.py).
+
+Weight initialisation and the per-epoch embedding mini-batch sampler.  Host logic only: the
+arithmetic on the sampled rows happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import math
+import random
+
+import numpy as np
+
+
+def check_dims(array):
+    """Column-vector view of a 1-d array (reference distBO/utils.py:109-112)."""
+    array = np.asarray(array)
+    return array[:, None] if array.ndim == 1 else array
+
+
+def truncated_glorot(rs, fan_in, fan_out):
+    """Glorot-normal weights, |z| <= 2 sigma, float32 values (reference train/gp_utils.py:13-26 uses
+    tf.keras.initializers.glorot_normal, a Philox truncated normal that cannot be reproduced
+    outside TensorFlow - SURVEY F9; numpy's MT19937 with rejection is used here and callers that
+    need a fixed trajectory inject weights through gp_regressor.initial_weights)."""
+    sigma = math.sqrt(2.0 / (fan_in + fan_out))
+    z = rs.standard_normal(size=(fan_in, fan_out))
+    out_of_range = np.abs(z) > 2.0
+    while out_of_range.any():
+        z[out_of_range] = rs.standard_normal(size=int(out_of_range.sum()))
+        out_of_range = np.abs(z) > 2.0
+    return (z * sigma).astype(np.float32)
+
+
+def init_net_weights(in_dim, weight_dim, name, seed):
+    """{weights_<name>_1, bias_<name>_1, weights_<name>_2}: zero bias, no bias on the last layer."""
+    if weight_dim is None or len(weight_dim) != 2:
+        raise NotImplementedError("the sm_100a embedding kernel implements the two-layer feature map "
+                                  "(weight_dim of length 2, as every shipped config uses)")
+    rs = np.random.RandomState(23 if seed is None else seed)
+    h, p = int(weight_dim[0]), int(weight_dim[1])
+    return {
+        "weights_%s_1" % name: truncated_glorot(rs, in_dim, h).astype(np.float64),
+        "bias_%s_1" % name: np.zeros(h),
+        "weights_%s_2" % name: truncated_glorot(rs, h, p).astype(np.float64),
+    }
+
+
+def label_bins(labels, lo=0.0, hi=1.01, intervals=4):
+    """Bin regression labels for stratified sampling (reference distBO/utils.py:13-16)."""
+    return np.digitize(np.squeeze(labels), np.linspace(lo, hi, intervals))
+
+
+class EmbedBatchSampler:
+    """Row indices of each epoch's embedding mini-batch, per dataset (reference train/gp_utils.py:28-104).
+
+    Yields, per epoch, a list of index arrays (one per dataset; None = "all rows, in order").
+    Draw order from `rs` matches the reference: one permutation (or stratified split) per dataset
+    that is larger than batch_size, datasets in order.  The reference's stratified-classification
+    branch shuffles with the unseeded global `random`; `shuffle_seed` makes that stream
+    reproducible.
+    """
+
+    def __init__(self, data_Y, batch_size, rs, model_type, stratify, shuffle_seed=0):
+        self.Y = data_Y
+        self.n = [len(y) for y in data_Y]
+        self.batch_size = int(batch_size)
+        self.rs = rs
+        self.model_type = model_type
+        self.stratify = bool(stratify)
+        self.constant = all(n <= self.batch_size for n in self.n)
+        self._cls = None
+        if not self.constant and self.stratify and model_type == "classification":
+            pyrand = random.Random(shuffle_seed)
+            self._pyrand = pyrand
+            n_classes = data_Y[0].shape[1]
+            self._cls = []
+            for y in data_Y:
+                labels = (y[:, 0] > 0.5).astype(int) if n_classes == 2 else np.argmax(y, axis=1)
+                per_class = []
+                for c in range(n_classes):
+                    members = np.where(labels == c)[0].tolist()
+                    pyrand.shuffle(members)
+                    take = int((float(len(members)) / len(y)) * (self.batch_size + 4))
+                    per_class.append({"members": members, "take": take, "pos": 0})
+                self._cls.append(per_class)
+
+    def sizes(self):
+        return [min(n, self.batch_size) for n in self.n]
+
+    def next_indices(self):
+        out = []
+        for i, n in enumerate(self.n):
+            if n <= self.batch_size:
+                out.append(None)
+            elif self.stratify and self.model_type == "classification":
+                picked = []
+                for c in self._cls[i]:
+                    end = c["pos"] + c["take"]
+                    if end > len(c["members"]):
+                        self._pyrand.shuffle(c["members"])
+                        c["pos"], end = 0, c["take"]
+                    picked += c["members"][c["pos"]:end]
+                    c["pos"] = end
+                out.append(np.asarray(picked[:self.batch_size], dtype=np.int64))
+            elif self.stratify:
+                from sklearn.model_selection import train_test_split
+                _, idx = train_test_split(np.arange(n), stratify=label_bins(self.Y[i]),
+                                          test_size=self.batch_size, random_state=self.rs)
+                out.append(np.asarray(idx, dtype=np.int64))
+            else:
+                out.append(self.rs.permutation(n)[:self.batch_size].astype(np.int64))
+        return out

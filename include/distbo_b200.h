@@ -31,6 +31,9 @@ extern "C" {
 
 /* Library / build identification: returns the compiled arch as an int (1000 for sm_100a). */
 int distbo_version(void);
+/* Number of CUDA kernels this library has launched since load (or since the last reset != 0).
+ * Host-side counter, used by bench.py for its "gpu_launches" claim. */
+int64_t distbo_launch_count(int reset);
 
 /* ---- K1: dataset embedding  (train/distbo_net.py:7-48, train/base.py:9-43) ----------------------
  * Fused tanh-MLP feature map phi_x (and phi_y), per-sample outer product phi_x (x) phi_y, and
@@ -118,10 +121,15 @@ int distbo_adam_f64(double* params, const double* grads, double* m, double* v, i
  * index of the maximum, as numpy argmax).  Kst: workspace of chunk*n_pad doubles with
  * chunk = distbo_score_chunk(); partial workspace of distbo_score_chunk()/128*2 pairs. */
 int distbo_score_chunk(void);
+/* Measurement aid: while enabled, distbo_score_f64 brackets every launch of its contraction kernel
+ * with CUDA events on the launching stream; _read synchronises them and returns the summed device
+ * time (ms) and the number of launches since the last enable/read. */
+int distbo_score_timing(int enable);
+int distbo_score_timing_read(double* total_ms_host, int64_t* launches_host);
 int distbo_score_f64(const double* W, const double* V, int N, int n_pad, const double* theta_s,
                      const double* sqnorm, int d, const double* log_bw, const double* kvec,
                      const double* log_scale, const double* mean_param, const double* theta_c,
-                     int64_t M, int acq_kind, double y_max, double xi, double kappa, double* Kst,
+                     const double* cand_shift, const double* cand_scale, int64_t M, int acq_kind, double y_max, double xi, double kappa, double* Kst,
                      double* out_mean, double* out_std, double* out_acq, double* block_best_val,
                      int64_t* block_best_idx, double* best_val, int64_t* best_idx,
                      int64_t index_offset, void* stream);

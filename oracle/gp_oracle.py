@@ -400,6 +400,47 @@ def neg_log_marg_likhd(B, params, kernel, batch, embed_op="joint", model_type=No
 
 
 # --------------------------------------------------------------------------- posterior
+def predict_factor(B, params, kernel, batch, k_dist=None):
+    """Candidate-independent half of the posterior graph: K, L = chol(K + (sigma^2 + 1e-6) I) and
+    V = L^-1 (y - m)  (log_gaus_likelihood.py:178-184 / :199-214).  The reference re-evaluates this
+    on every predict call; it is split out so the CPU baseline can time it separately."""
+    scale = B.exp(params["log_scale"])
+    stddev = B.exp(params["log_bw"])
+    sigma_sq = B.exp(2.0 * params["log_sigma"])
+    n = batch.h_params.shape[0]
+    k = matern32_kernel(B, batch.h_params, batch.h_params, stddev=stddev)
+    if kernel == "dist":
+        k = scale * k * k_dist
+    elif kernel == "manual":
+        emb = B.repeat_rows(batch.embed, np.asarray(batch.sizes).reshape(-1))
+        k = scale * k * matern32_kernel(B, emb, emb, stddev=B.exp(params["log_bw_embed"]))
+    else:
+        k = scale * k
+    L = B.cholesky(k + (sigma_sq + JITTER) * B.eye(n, k))
+    V = B.solve_lower(L, batch.obs - params["mean"])
+    return L, V
+
+
+def predict_apply(B, params, kernel, batch, L, V, h_params_pred, k_dist_pred=None, embed_pred=None):
+    """Per-candidate half: K_*, A = L^-1 K_*, mean = A^T V + m, var = scale - colsum(A^2)
+    (log_gaus_likelihood.py:178-187 / :203-217)."""
+    scale = B.exp(params["log_scale"])
+    stddev = B.exp(params["log_bw"])
+    k_pred = matern32_kernel(B, batch.h_params, h_params_pred, stddev=stddev)
+    if kernel == "dist":
+        k_pred = scale * k_pred * k_dist_pred
+    elif kernel == "manual":
+        emb = B.repeat_rows(batch.embed, np.asarray(batch.sizes).reshape(-1))
+        emb_p = B.repeat_rows(embed_pred, [h_params_pred.shape[0]])
+        k_pred = scale * k_pred * matern32_kernel(B, emb, emb_p, stddev=B.exp(params["log_bw_embed"]))
+    else:
+        k_pred = scale * k_pred
+    A = B.solve_lower(L, k_pred)
+    mean = B.matmul(B.transpose(A), V) + params["mean"].reshape(1, 1)
+    var = scale - B.sum(B.square(A), axis=0)
+    return mean, var.reshape(-1, 1)
+
+
 def predict(B, params, kernel, batch, h_params_pred, k_dist=None, k_dist_pred=None,
             embed_pred=None):
     """Posterior mean/variance.
@@ -408,31 +449,9 @@ def predict(B, params, kernel, batch, h_params_pred, k_dist=None, k_dist_pred=No
     pre-computed embedding Grams fed in.  Otherwise build_predict (:128-188).
     Returns (mean[M,1], var[M,1]); var is NOT clamped here (gp_regressor.py:197 does it).
     """
-    scale = B.exp(params["log_scale"])
-    stddev = B.exp(params["log_bw"])
-    sigma_sq = B.exp(2.0 * params["log_sigma"])
-    n = batch.h_params.shape[0]
-    k = matern32_kernel(B, batch.h_params, batch.h_params, stddev=stddev)
-    k_pred = matern32_kernel(B, batch.h_params, h_params_pred, stddev=stddev)
-    if kernel == "dist":
-        k = scale * k * k_dist
-        k_pred = scale * k_pred * k_dist_pred
-    elif kernel == "manual":
-        emb = B.repeat_rows(batch.embed, np.asarray(batch.sizes).reshape(-1))
-        m = h_params_pred.shape[0]
-        emb_p = B.repeat_rows(embed_pred, [m])
-        bw = B.exp(params["log_bw_embed"])
-        k = scale * k * matern32_kernel(B, emb, emb, stddev=bw)
-        k_pred = scale * k_pred * matern32_kernel(B, emb, emb_p, stddev=bw)
-    else:
-        k = scale * k
-        k_pred = scale * k_pred
-    L = B.cholesky(k + (sigma_sq + JITTER) * B.eye(n, k))
-    A = B.solve_lower(L, k_pred)
-    V = B.solve_lower(L, batch.obs - params["mean"])
-    mean = B.matmul(B.transpose(A), V) + params["mean"].reshape(1, 1)
-    var = scale - B.sum(B.square(A), axis=0)
-    return mean, var.reshape(-1, 1)
+    L, V = predict_factor(B, params, kernel, batch, k_dist=k_dist)
+    return predict_apply(B, params, kernel, batch, L, V, h_params_pred, k_dist_pred=k_dist_pred,
+                         embed_pred=embed_pred)
 
 
 def embed_grams(B, params, batch, X_pred, y_pred, embed_sizes_pred, data_sizes_pred, n_pred,

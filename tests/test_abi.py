@@ -1,0 +1,83 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports exactly the entry points
+include/distbo_b200.h declares, the ctypes table mirrors the header, and the product refuses to run
+without a CUDA device (no CPU fallback).  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "distbo_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = re.findall(r"\b(?:int|int64_t)\s+(distbo_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    out = {}
+    for name, args in decls:
+        args = args.strip()
+        out[name] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_header_declares_the_path():
+    fns = header_functions()
+    for must in ["distbo_embed_fwd_f32", "distbo_embed_fwd_f64", "distbo_embed_bwd_f64", "distbo_task_gram_f64",
+                 "distbo_gram_f64", "distbo_potrf_f64", "distbo_trtri_f64", "distbo_lauum_f64", "distbo_nll_f64",
+                 "distbo_gram_grad_f64", "distbo_task_gram_bwd_f64", "distbo_adam_f64", "distbo_score_f64"]:
+        assert must in fns, must
+
+
+def test_library_exports_every_header_symbol():
+    from distbo_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the library first (python -c 'import __graft_entry__ as g; g.build()')"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in header_functions():
+        assert hasattr(lib, name), "libdistbo_b200.so does not export %s" % name
+
+
+def test_ctypes_table_mirrors_header():
+    from distbo_b200 import _lib
+    fns = header_functions()
+    assert set(_lib.SIGNATURES) == set(fns), set(_lib.SIGNATURES) ^ set(fns)
+    for name, nargs in fns.items():
+        assert len(_lib.SIGNATURES[name][1]) == nargs, (name, nargs, len(_lib.SIGNATURES[name][1]))
+    lib = _lib.load()
+    assert lib.distbo_version() == 1000          # compiled for sm_100a
+    assert lib.distbo_launch_count(0) == 0       # nothing launched by loading
+
+
+def test_sass_is_sm100a_with_fp64_tensor_ops():
+    """The shared library carries sm_100a SASS and the Cholesky / scoring kernels use DMMA."""
+    import shutil
+    import subprocess
+    from distbo_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    elf = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    per_fn = sass.split("Function : ")[1:]
+    for kernel in ("score_kernel", "gemm_tiles_kernel", "potf2_inv_kernel"):
+        bodies = [b for b in per_fn if kernel in b.split("\n", 1)[0]]
+        assert bodies and all("DMMA" in b for b in bodies), kernel
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from distbo_b200 import _lib, engine
+    with pytest.raises(_lib.DistboError):
+        engine.GPEngine(2)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "distbo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
