@@ -98,7 +98,7 @@ def _polish(ac, gp, y_max, x_seeds, bounds, evaluatedX, x_max, max_acq, eps, max
     replaces the incumbent only when `evaluatedX` is given and shares no coordinate value with it -
     the reference's `res.x not in evaluatedX` is numpy's element-wise membership test."""
     for x_try in x_seeds:
-        res = minimize(lambda x: -ac(x.reshape(1, -1), gp=gp, y_max=y_max), x_try.reshape(1, -1),
+        res = minimize(lambda x: -float(np.squeeze(ac(x.reshape(1, -1), gp=gp, y_max=y_max))), np.ravel(x_try),
                        bounds=bounds, method="L-BFGS-B",
                        options={'eps': eps, 'ftol': 1e-04, 'maxfun': maxfun, 'maxls': 10})
         if not res.success:

@@ -1,0 +1,130 @@
+"""CPU tests of the host glue that surrounds the hot path: TargetSpace, acq_max decisions and the
+BayesianOptimization loop, driven with the oracle's duck-typed regressor (no GPU needed).  The same
+loop is run against the CUDA regressor in tests/test_gpu_trajectory.py."""
+import numpy as np
+import pytest
+
+from distbo_b200.bayes_opt import BayesianOptimization, UtilityFunction, acq_max
+from distbo_b200.bayes_opt.helpers import ensure_rng, unique_rows
+from distbo_b200.bayes_opt.target_space import TargetSpace
+from distbo_b200.data.toy_datasets import one_dim_split_tasks
+from distbo_b200.model_embed import bayes_opt_wrap, set_model
+from oracle.gp_regressor_oracle import OracleGPRegressor
+
+
+def toy_optim_config(**over):
+    cfg = dict(weight_dim=None, weight_dim_x=[20, 10], weight_dim_y=[20, 10], weight_dim_xy=None, n_warmup=300,
+               n_opt_iterations=0, n_epochs=4, lkh_var_init=1e-2, lr=0.005, float64=True, n_cpus=1, stratify=False,
+               embed_op='none', concat_data_size=False, algorithm='GP', gradient_clip=False, num_of_rff=0,
+               batch_size=500, first_early_stop_epoch=2, max_size=None)
+    cfg.update(over)
+    return cfg
+
+
+def test_random_points_draw_scalar_by_scalar():
+    """The fork draws one scalar per coordinate, row-major (target_space.py:254-258); its docstring
+    sample (:244-250) is the upstream column-wise order and does not match its own code."""
+    space = TargetSpace(lambda p2, p1: p1 + p2, {'p2': (1, 100), 'p1': (0, 1)}, random_state=0)
+    u = np.random.RandomState(0).uniform(size=6)
+    want = np.array([[1 + 99 * u[0], u[1]], [1 + 99 * u[2], u[3]], [1 + 99 * u[4], u[5]]])
+    assert np.allclose(space.random_points(3), want, rtol=1e-15)
+    assert want[0, 0] == pytest.approx(55.33253689)      # first value of the reference docstring
+
+
+def test_target_space_growth_and_duplicates():
+    space = TargetSpace(lambda a, b: a - b, {'a': (0, 1), 'b': (0, 1)}, random_state=1)
+    assert space.X is None and len(space) == 0
+    for i in range(9):
+        space.observe_point([0.5, 0.25])            # duplicates are stored again, as in the reference
+    assert len(space) == 9 and space.X.shape == (9, 2) and np.all(space.Y == 0.25)
+    assert [0.5, 0.25] in space
+    assert space.max_point()['max_val'] == 0.25
+    space._assert_internal_invariants()
+    assert unique_rows(space.X).sum() == 1
+    with pytest.raises(ValueError):
+        space._dict_to_points({'a': [1, 2], 'b': [1]})
+
+
+def test_ensure_rng():
+    assert isinstance(ensure_rng(None), np.random.RandomState)
+    assert ensure_rng(3).uniform() == np.random.RandomState(3).uniform()
+    rs = np.random.RandomState(4)
+    assert ensure_rng(rs) is rs
+
+
+class _FakeGP:
+    """predict_y only: mean peaks at x = 0.3, constant std."""
+
+    def predict_y(self, x, **kw):
+        x = np.asarray(x)
+        return -np.sum((x - 0.3) ** 2, axis=1, keepdims=True), np.full((len(x), 1), 0.1)
+
+
+def test_acq_max_argmax_and_fallback():
+    gp = _FakeGP()
+    bounds = np.array([[0.0, 1.0], [0.0, 1.0]])
+    util = UtilityFunction('ucb', kappa=1.0, xi=0.0)
+    x = acq_max(util.utility, gp, 0.0, bounds, np.random.RandomState(0), n_warmup=2000, n_iter=0)
+    tries = np.random.RandomState(0).uniform(bounds[:, 0], bounds[:, 1], size=(2000, 2))
+    assert np.array_equal(x, tries[np.argmax(util.utility(tries, gp, 0.0))])
+    # EI identically zero (y_max far above the mean) -> UCB fallback picks the same point
+    ei = UtilityFunction('ei', kappa=1.0, xi=0.01)
+    assert np.max(ei.utility(tries, gp, 1e6)) == 0.0
+    x2 = acq_max(ei.utility, gp, 1e6, bounds, np.random.RandomState(0), kappa=1.0, n_warmup=2000, n_iter=0)
+    assert np.array_equal(x2, x)
+    # polish: accepted only with evaluatedX (helpers.py:84); result stays inside the bounds
+    x3 = acq_max(util.utility, gp, 0.0, bounds, np.random.RandomState(0), n_warmup=50, n_iter=3,
+                 evaluatedX=np.array([[9.0, 9.0]]))
+    assert np.all(x3 >= 0) and np.all(x3 <= 1) and np.sum((x3 - 0.3) ** 2) < 1e-3
+    x4 = acq_max(util.utility, gp, 0.0, bounds, np.random.RandomState(0), n_warmup=50, n_iter=3)
+    t50 = np.random.RandomState(0).uniform(bounds[:, 0], bounds[:, 1], size=(50, 2))
+    assert np.array_equal(x4, t50[np.argmax(util.utility(t50, gp, 0.0))])
+    with pytest.raises(NotImplementedError):
+        UtilityFunction('es', 1.0, 0.0)
+
+
+@pytest.mark.parametrize("method", ["params", "dist"])
+def test_bo_loop_with_oracle_regressor(method):
+    target, sources, supp = one_dim_split_tasks(0, 1, 1, n_train=40, n_test=40)
+    rs = np.random.RandomState(5)
+    init_list = []
+    for s in sources:          # source evaluations: random search on each source objective
+        f, bounds, _, _ = set_model('toy', s, None)
+        th = rs.uniform(-8, 8, size=6)
+        init_list.append(np.column_stack([th, [f(theta=t) for t in th]]))
+    cfg = toy_optim_config()
+    kw = dict(acq='ei', model='toy', rs=np.random.RandomState(11), optim_config=cfg, xi=0.01, kappa=2.58,
+              bo_it=3, rand_it=0, init_list=init_list, include_init=False, source_data=sources,
+              gp_class=OracleGPRegressor, verbose=0, acq_one_shot='lcb')
+    out = bayes_opt_wrap(method, target, **kw)
+    if method == 'dist':
+        out, sim = out
+        # one similarity row per acquisition: T_src = 2 entries, then 3 once the target task has joined
+        assert [np.size(s) for s in sim] == [2, 3, 3]
+        assert all(np.all(np.asarray(s) > 0) and np.all(np.asarray(s) <= 1 + 1e-12) for s in sim)
+    assert out.shape == (3, 2)
+    f, _, _, _ = set_model('toy', target, None)
+    assert np.allclose(out[:, 1], [f(theta=t) for t in out[:, 0]])
+    assert np.all(np.abs(out[:, 0]) <= 8)
+
+
+def test_bo_bookkeeping_matches_reference_rules():
+    """size_evals grows by one task then by one observation per acquisition; the scaler is fitted
+    once; first_early_stop_epoch drops to 600 from the second in-loop refit on."""
+    target, sources, _ = one_dim_split_tasks(1, 1, 1, n_train=30, n_test=30)
+    calls = []
+
+    class Spy(OracleGPRegressor):
+        def maximise_likhd(self, params, y, **kw):
+            calls.append((len(params), list(np.ravel(kw['sizes'])), kw['first_early_stop_epoch'], len(kw['data_X'])))
+            return super().maximise_likhd(params, y, **kw)
+
+    rs = np.random.RandomState(2)
+    init_list = [np.column_stack([rs.uniform(-8, 8, 5), rs.rand(5)]) for _ in sources]
+    cfg = toy_optim_config(first_early_stop_epoch=1)
+    bayes_opt_wrap('dist', target, acq='ei', model='toy', rs=3, optim_config=cfg, xi=0.01, kappa=2.58, bo_it=4,
+                   rand_it=0, init_list=init_list, source_data=sources, gp_class=Spy, verbose=0)
+    assert [c[0] for c in calls] == [10, 11, 12, 13]
+    assert [c[1] for c in calls] == [[5, 5], [5, 5, 1], [5, 5, 2], [5, 5, 3]]
+    assert [c[2] for c in calls] == [1, 1, 600, 600]
+    assert [c[3] for c in calls] == [2, 3, 3, 3]

@@ -1,0 +1,66 @@
+"""GPU parity of the whole BO trajectory on the toy configuration (BASELINE config 1, reduced sizes so
+the CPU oracle finishes in seconds): the same BayesianOptimization loop, seeds and objective, once
+with the CUDA gp_regressor and once with the oracle's regressor.  The suggested points must be
+IDENTICAL (bit-equal candidate rows: both pick rows of the same RandomState candidate stream)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from distbo_b200.data.toy_datasets import one_dim_split_tasks  # noqa: E402
+from distbo_b200.model_embed import bayes_opt_wrap, set_model  # noqa: E402
+from oracle.gp_regressor_oracle import OracleGPRegressor  # noqa: E402
+
+
+def optim_config(**over):
+    cfg = dict(weight_dim=None, weight_dim_x=[20, 10], weight_dim_y=[20, 10], weight_dim_xy=None, n_warmup=20000,
+               n_opt_iterations=0, n_epochs=25, lkh_var_init=1e-5, lr=0.005, float64=True, n_cpus=1, stratify=False,
+               embed_op='none', concat_data_size=False, algorithm='GP', gradient_clip=False, num_of_rff=0,
+               batch_size=500, first_early_stop_epoch=10, max_size=None)
+    cfg.update(over)
+    return cfg
+
+
+def source_evals(sources, seed, n):
+    rs = np.random.RandomState(seed)
+    out = []
+    for s in sources:
+        f, _, _, _ = set_model('toy', s, None)
+        th = rs.uniform(-8, 8, size=n)
+        out.append(np.column_stack([th, [f(theta=t) for t in th]]))
+    return out
+
+
+@pytest.mark.parametrize("method,embed_op", [("dist", "none"), ("dist", "joint"), ("params", "none")])
+def test_toy_trajectory_identical(cuda_engine_mod, method, embed_op):
+    target, sources, supp = one_dim_split_tasks(0, 3, 2, n_train=120, n_test=120)
+    init_list = source_evals(sources, 1, 12)
+    runs = {}
+    for name, gp_class in (("cuda", None), ("oracle", OracleGPRegressor)):
+        cfg = optim_config(embed_op=embed_op)
+        runs[name] = bayes_opt_wrap(method, target, acq='ei', model='toy', rs=np.random.RandomState(7),
+                                    optim_config=cfg, xi=0.01, kappa=2.58, bo_it=5, rand_it=0,
+                                    init_list=[a.copy() for a in init_list], include_init=False,
+                                    source_data=sources, gp_class=gp_class, verbose=0, acq_one_shot='lcb')
+    if method == "dist":
+        (a, sim_a), (b, sim_b) = runs["cuda"], runs["oracle"]
+        for x, y in zip(sim_a, sim_b):
+            assert np.allclose(np.asarray(x, dtype=float), np.asarray(y, dtype=float), rtol=1e-8, atol=0)
+    else:
+        a, b = runs["cuda"], runs["oracle"]
+    assert a.shape == b.shape == (5, 2)
+    assert np.array_equal(a[:, 0], b[:, 0]), (a[:, 0], b[:, 0])      # identical suggestions
+    assert np.array_equal(a[:, 1], b[:, 1])
+
+
+def test_polish_path_runs_on_gpu(cuda_engine_mod):
+    """n_opt_iterations > 0: L-BFGS-B polish calls the CUDA posterior with single points (HOT LOOP 3)."""
+    target, sources, _ = one_dim_split_tasks(3, 1, 1, n_train=60, n_test=60)
+    init_list = source_evals(sources, 2, 8)
+    cfg = optim_config(n_opt_iterations=3, n_warmup=2000, n_epochs=10)
+    out = bayes_opt_wrap('params', target, acq='ei', model='toy', rs=np.random.RandomState(3), optim_config=cfg,
+                         xi=0.01, kappa=2.58, bo_it=3, rand_it=0, init_list=init_list, include_init=False,
+                         source_data=sources, verbose=0, acq_one_shot='ucb')
+    assert out.shape == (3, 2) and np.all(np.abs(out[:, 0]) <= 8)
