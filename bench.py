@@ -118,7 +118,7 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(work, lkh_var, m_sample, steps, warmup):
+def cpu_reference(work, lkh_var, m_sample, steps, warmup, params_override=None):
     """The reference's CPU op sequence for this path (oracle restatement; TF 1.7 cannot run here):
     embeddings of the full sample sets, k_dist / k_dist_pred, Gram + Cholesky + V (candidate
     independent, re-evaluated by the reference on every predict call), then per candidate K_*,
@@ -129,6 +129,9 @@ def cpu_reference(work, lkh_var, m_sample, steps, warmup):
                        likhd_var_init=lkh_var)
     for k, v in work["weights"].items():
         p[k] = np.asarray(v, dtype=np.float64)
+    if params_override:      # cpu_baseline leg: same hyper-parameters as the fitted CUDA surrogate
+        for k, v in params_override.items():
+            p[k] = np.asarray(v, dtype=np.float64).reshape(np.shape(p[k]))
     from sklearn.preprocessing import StandardScaler
     sc = StandardScaler().fit(work["theta"])
     theta = sc.transform(work["theta"])
@@ -286,10 +289,11 @@ def run_cuda(args):
     cand_dev = cand_host[lo:hi].to(dev)
     y_max = work["y_max"]
 
+    from distbo_b200.sharding import merge_best, pack_best, unpack_best
+
     def step_resident():
         out = eng.score(cand_dev, acq="ei", y_max=y_max, xi=XI, kappa=KAPPA, want_arrays=False,
                         index_offset=lo, scaler=gp._scaler_dev)
-        from distbo_b200.sharding import pack_best
         return gp.shards.all_gather_best(pack_best(out["best_val"], out["best_idx"]))
 
     for _ in range(Wm):
@@ -315,7 +319,6 @@ def run_cuda(args):
     lib.distbo_score_timing(0)
     ms_step = max_over_ranks(ms_local) / K
     value = M / (ms_step / 1e3)
-    from distbo_b200.sharding import merge_best, unpack_best
     vals, idxs = unpack_best(recs)
     best_resident = merge_best(vals.cpu().numpy(), idxs.cpu().numpy())
 
@@ -366,7 +369,8 @@ def run_cuda(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         m_s = min(M, args.cpu_sample)
-        t_fixed, t_var, best_cpu = cpu_reference(work, args.lkh_var, m_s, 1, 0)
+        fitted = {k: eng.params.get(k) for k in eng.params.offsets}
+        t_fixed, t_var, best_cpu = cpu_reference(work, args.lkh_var, m_s, 1, 0, params_override=fitted)
         step_s = t_fixed + t_var[0] * (M / m_s)
         # same arg-max on the sample as the CUDA path gives on that prefix
         v_gpu, i_gpu = gp.acquire(work["cand"][:m_s], "ei", y_max=y_max, xi=XI, kappa=KAPPA)

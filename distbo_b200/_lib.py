@@ -35,10 +35,11 @@ SIGNATURES = {
     "distbo_potrf_f64": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "distbo_trtri_f64": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "distbo_lauum_f64": (_i, [_vp, _vp, _vp, _vp]),
-    "distbo_nll_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "distbo_nll_workspace": (_i64, [_i]),
+    "distbo_nll_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "distbo_gram_grad_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp]),
-    "distbo_task_gram_bwd_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "distbo_task_gram_bwd_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "distbo_adam_f64": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _i64, _d, _vp, _vp]),
     "distbo_score_chunk": (_i, []),
     "distbo_score_timing": (_i, [_i]),

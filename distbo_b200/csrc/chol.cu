@@ -265,25 +265,37 @@ __global__ void __launch_bounds__(256) gemv_lower_kernel(const double* __restric
   if (lane == 0) V[row] = acc;
 }
 
-// alpha[j] = sum_{i>=j} W[i][j] * V[i]   (32 columns x 8 row groups per CTA, fixed-order reduction)
-__global__ void __launch_bounds__(256) gemvT_lower_kernel(const double* __restrict__ W, int n_pad,
-                                                          const double* __restrict__ V,
-                                                          double* __restrict__ alpha) {
-  __shared__ double red[8][33];
-  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + c;
-  const int i0 = blockIdx.x * 32;
-  double acc = 0.0;
-  for (int i = i0 + g; i < n_pad; i += 8)
-    if (i >= j) acc += W[(size_t)i * n_pad + j] * V[i];
-  red[g][c] = acc;
+// alpha[j] = sum_{i>=j} W[i][j] * V[i] in two coalesced passes with a fixed summation order:
+//   partial[b][j] = sum_{i in rows of block b} W[i][j] V[i]   (block b = GVT_ROWS rows; thread = column, so a
+//                   warp reads 256 contiguous bytes of each row; entries above the diagonal inside the
+//                   diagonal 128-block are stored zeros)
+//   alpha[j]      = sum_b partial[b][j] over the blocks whose 128-block row is >= j / 128.
+constexpr int GVT_ROWS = 32;
+__global__ void __launch_bounds__(256) gemvT_partial_kernel(const double* __restrict__ W, int n_pad,
+                                                            const double* __restrict__ V,
+                                                            double* __restrict__ partial) {
+  __shared__ double sv[GVT_ROWS];
+  const int i0 = blockIdx.x * GVT_ROWS;
+  if (threadIdx.x < GVT_ROWS) sv[threadIdx.x] = V[i0 + threadIdx.x];
   __syncthreads();
-  if (g == 0) {
-    double s = 0.0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) s += red[q][c];
-    alpha[j] = s;
+  const int jmax = (i0 / 128 + 1) * 128;
+  for (int j = threadIdx.x; j < jmax; j += 256) {
+    const double* w = W + (size_t)i0 * n_pad + j;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < GVT_ROWS; ++r) acc += w[(size_t)r * n_pad] * sv[r];
+    partial[(size_t)blockIdx.x * n_pad + j] = acc;
   }
+}
+
+__global__ void __launch_bounds__(256) gemvT_reduce_kernel(const double* __restrict__ partial, int n_pad,
+                                                           double* __restrict__ alpha) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= n_pad) return;
+  const int nblk = n_pad / GVT_ROWS;
+  double s = 0.0;
+  for (int b = (j / 128) * (128 / GVT_ROWS); b < nblk; ++b) s += partial[(size_t)b * n_pad + j];
+  alpha[j] = s;
 }
 
 // nll = 0.5 |V|^2 + 0.5 N log(2 pi) + sum_i log L_ii    (reference train/gp_utils.py:141-147)
@@ -312,13 +324,19 @@ __global__ void __launch_bounds__(1024) nll_kernel(const double* __restrict__ L,
 
 }  // namespace db
 
+extern "C" int64_t distbo_nll_workspace(int n_pad) { return (int64_t)(n_pad / GVT_ROWS) * n_pad; }
+
 extern "C" int distbo_nll_f64(const double* L, const double* W, int N, int n_pad, const double* y,
-                              const double* mean, double* V, double* alpha, double* nll, void* stream) {
-  if (!L || !W || !y || !mean || !V || !alpha || !nll || N <= 0 || n_pad < N || n_pad % 128) return DISTBO_EARG;
+                              const double* mean, double* V, double* alpha, double* nll, double* workspace,
+                              void* stream) {
+  if (!L || !W || !y || !mean || !V || !alpha || !nll || !workspace || N <= 0 || n_pad < N || n_pad % 128)
+    return DISTBO_EARG;
   cudaStream_t st = (cudaStream_t)stream;
   gemv_lower_kernel<<<n_pad / 8, 256, 0, st>>>(W, n_pad, N, y, mean, V);
   DB_CHECK_LAUNCH();
-  gemvT_lower_kernel<<<n_pad / 32, 256, 0, st>>>(W, n_pad, V, alpha);
+  gemvT_partial_kernel<<<n_pad / GVT_ROWS, 256, 0, st>>>(W, n_pad, V, workspace);
+  DB_CHECK_LAUNCH();
+  gemvT_reduce_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(workspace, n_pad, alpha);
   DB_CHECK_LAUNCH();
   nll_kernel<<<1, 1024, 0, st>>>(L, n_pad, N, V, nll);
   DB_CHECK_LAUNCH();

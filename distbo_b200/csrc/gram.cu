@@ -258,16 +258,20 @@ __global__ void __launch_bounds__(256) gram_grad_finish_kernel(
 }
 
 // ------------------------------------------------------------------ task Gram backward
-// One thread per embedding column c.  ev[t][u] = exp(-v) (0 where the distance was clamped).
-__global__ void __launch_bounds__(256) task_gram_bwd_kernel(const double* __restrict__ E, int lde, int T,
-                                                            int P, const double* __restrict__ log_bw_embed,
-                                                            const double* __restrict__ H,
-                                                            double* __restrict__ g_log_bw_embed,
-                                                            double* __restrict__ dE) {
-  extern __shared__ __align__(16) double ev[];  // [T*T]
+// One CTA per task row t.  ev[u] = exp(-v_tu) (0 where the distance was clamped: tf.maximum routes the
+// gradient to the constant).  Warp w handles embedding columns c = w, w+8, ...; lanes split u and are
+// combined by a fixed-order butterfly, so the result is deterministic.
+//   dE[t][c]      = sum_u (H[t][u] + H[u][t]) (-1.5 ev_tu) 2 (E_tc - E_uc) / s_c^2
+//   gpart[t][c]   = sum_u  H[t][u] 3 ev_tu (E_tc - E_uc)^2 / s_c^2        (summed over t by the finish kernel)
+__global__ void __launch_bounds__(256) task_gram_bwd_rows_kernel(const double* __restrict__ E, int lde, int T,
+                                                                 int P, const double* __restrict__ log_bw_embed,
+                                                                 const double* __restrict__ H,
+                                                                 double* __restrict__ gpart,
+                                                                 double* __restrict__ dE) {
+  extern __shared__ __align__(16) double ev[];  // [T]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int pair = warp; pair < T * T; pair += 8) {
-    const int t = pair / T, u = pair % T;
+  const int t = blockIdx.x;
+  for (int u = warp; u < T; u += 8) {
     double xy = 0.0, xx = 0.0, yy = 0.0;
     for (int c = lane; c < P; c += 32) {
       const double s = exp(log_bw_embed[c]);
@@ -281,39 +285,49 @@ __global__ void __launch_bounds__(256) task_gram_bwd_kernel(const double* __rest
     yy = warp_sum(yy);
     if (lane == 0) {
       const double d2 = -2.0 * xy + xx + yy;
-      ev[pair] = (d2 > kDistClamp) ? exp(-kSqrt3 * sqrt(d2)) : 0.0;
+      ev[u] = (d2 > kDistClamp) ? exp(-kSqrt3 * sqrt(d2)) : 0.0;
     }
   }
   __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= P) return;
-  const double s = exp(log_bw_embed[c]);
-  const double inv_s2 = 1.0 / (s * s);
-  double gbw = 0.0;
-  for (int t = 0; t < T; ++t) {
+  for (int c = warp; c < P; c += 8) {
+    const double s = exp(log_bw_embed[c]);
+    const double inv_s2 = 1.0 / (s * s);
     const double et = E[(size_t)t * lde + c];
-    double de = 0.0;
-    for (int u = 0; u < T; ++u) {
+    double de = 0.0, gbw = 0.0;
+    for (int u = lane; u < T; u += 32) {
       const double diff = et - E[(size_t)u * lde + c];
-      const double h = H[(size_t)t * T + u], e = ev[t * T + u];
-      // dK/dd2 = -1.5 e ; dd2/dE_tc = 2 diff / s^2 for the pair (t,u) and the same again for (u,t)
+      const double h = H[(size_t)t * T + u], e = ev[u];
       de += (h + H[(size_t)u * T + t]) * (-1.5 * e) * 2.0 * diff * inv_s2;
-      // dd2/dlog s_c = -2 diff^2 / s^2
       gbw += h * 3.0 * e * diff * diff * inv_s2;
     }
-    dE[(size_t)t * lde + c] = de;
+    de = warp_sum(de);
+    gbw = warp_sum(gbw);
+    if (lane == 0) {
+      dE[(size_t)t * lde + c] = de;
+      gpart[(size_t)t * P + c] = gbw;
+    }
   }
-  g_log_bw_embed[c] = gbw;
+}
+
+__global__ void __launch_bounds__(256) task_gram_bwd_finish_kernel(const double* __restrict__ gpart, int T, int P,
+                                                                   double* __restrict__ g_log_bw_embed) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= P) return;
+  double s = 0.0;
+  for (int t = 0; t < T; ++t) s += gpart[(size_t)t * P + c];
+  g_log_bw_embed[c] = s;
 }
 
 // ------------------------------------------------------------------ Adam (TF 1.7 form)
 __global__ void __launch_bounds__(1024) adam_kernel(double* __restrict__ params,
                                                     const double* __restrict__ grads,
                                                     double* __restrict__ m, double* __restrict__ v,
-                                                    long long n, double lr_t, double b1, double b2,
+                                                    long long n, double lr_t_host,
+                                                    const double* __restrict__ lr_t_dev, double b1, double b2,
                                                     double eps, double clip_norm) {
   __shared__ double red[32];
   __shared__ double gscale;
+  const double lr_t = lr_t_dev ? *lr_t_dev : lr_t_host;
   if (clip_norm > 0.0) {
     double s = 0.0;
     for (long long i = threadIdx.x; i < n; i += 1024) s += grads[i] * grads[i];
@@ -418,29 +432,27 @@ extern "C" int distbo_gram_grad_f64(const double* Kinv, const double* alpha, con
 }
 
 extern "C" int distbo_task_gram_bwd_f64(const double* E, int lde, int T, int P, const double* log_bw_embed,
-                                        const double* H, double* g_log_bw_embed, double* dE, void* stream) {
-  if (!E || !log_bw_embed || !H || !g_log_bw_embed || !dE || T <= 0 || P <= 0 || lde < P) return DISTBO_EARG;
-  const int smem = T * T * (int)sizeof(double);
-  if (smem > 200 * 1024) return DISTBO_EARG;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(task_gram_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
-  task_gram_bwd_kernel<<<(P + 255) / 256, 256, smem, (cudaStream_t)stream>>>(E, lde, T, P, log_bw_embed, H,
-                                                                            g_log_bw_embed, dE);
+                                        const double* H, double* g_log_bw_embed, double* dE, double* workspace,
+                                        void* stream) {
+  if (!E || !log_bw_embed || !H || !g_log_bw_embed || !dE || !workspace || T <= 0 || P <= 0 || lde < P)
+    return DISTBO_EARG;
+  if ((size_t)T * sizeof(double) > 48 * 1024) return DISTBO_EARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  task_gram_bwd_rows_kernel<<<T, 256, (size_t)T * sizeof(double), st>>>(E, lde, T, P, log_bw_embed, H, workspace, dE);
+  DB_CHECK_LAUNCH();
+  task_gram_bwd_finish_kernel<<<(P + 255) / 256, 256, 0, st>>>(workspace, T, P, g_log_bw_embed);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
 }
 
 extern "C" int distbo_adam_f64(double* params, const double* grads, double* m, double* v, int64_t n, double lr,
                                double beta1, double beta2, double eps, int64_t step, double clip_norm,
-                               double* scratch, void* stream) {
-  (void)scratch;
-  if (!params || !grads || !m || !v || n <= 0 || step <= 0) return DISTBO_EARG;
-  const double lr_t = lr * sqrt(1.0 - pow(beta2, (double)step)) / (1.0 - pow(beta1, (double)step));
-  adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grads, m, v, (long long)n, lr_t, beta1, beta2, eps,
-                                                    clip_norm);
+                               const double* lr_t_dev, void* stream) {
+  if (!params || !grads || !m || !v || n <= 0 || (step <= 0 && !lr_t_dev)) return DISTBO_EARG;
+  const double lr_t =
+      lr_t_dev ? 0.0 : lr * sqrt(1.0 - pow(beta2, (double)step)) / (1.0 - pow(beta1, (double)step));
+  adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grads, m, v, (long long)n, lr_t, lr_t_dev, beta1, beta2,
+                                                    eps, clip_norm);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
 }

@@ -165,6 +165,7 @@ class GPEngine:
             self.V = self._f64(n_pad)
             self.alpha = self._f64(n_pad)
             self.kvec = self._f64(n_pad)
+            self.nll_ws = self._f64(int(self.lib.distbo_nll_workspace(n_pad)))
             self.plan = Plans.get(n_pad)
         self.N = N
         self.theta = torch.from_numpy(theta).to(self.dev)
@@ -262,7 +263,7 @@ class GPEngine:
     def likelihood(self):
         rc = self.lib.distbo_nll_f64(_lib.ptr(self.K), _lib.ptr(self.W), self.N, self.n_pad, _lib.ptr(self.y),
                                      _lib.ptr(self.params.view("mean")), _lib.ptr(self.V), _lib.ptr(self.alpha),
-                                     _lib.ptr(self.nll), _stream())
+                                     _lib.ptr(self.nll), _lib.ptr(self.nll_ws), _stream())
         _lib.check(rc, "distbo_nll_f64")
 
     def gram_gradient(self):
@@ -282,17 +283,29 @@ class GPEngine:
 
     def task_gram_backward(self, E, Tn):
         dE = self._f64(Tn, E.shape[1])
+        ws = torch.empty(Tn * self.P, dtype=torch.float64, device=self.dev)
         rc = self.lib.distbo_task_gram_bwd_f64(_lib.ptr(E), E.stride(0), Tn, self.P,
                                                _lib.ptr(self.params.view("log_bw_embed")), _lib.ptr(self.H),
-                                               _lib.ptr(self.params.gview("log_bw_embed")), _lib.ptr(dE), _stream())
+                                               _lib.ptr(self.params.gview("log_bw_embed")), _lib.ptr(dE),
+                                               _lib.ptr(ws), _stream())
         _lib.check(rc, "distbo_task_gram_bwd_f64")
         return dE
 
-    def adam_step(self, lr, clip_norm=0.0):
+    @staticmethod
+    def adam_lr_t(lr, step, beta1=0.9, beta2=0.999):
+        """TF AdamOptimizer's per-step rate lr * sqrt(1 - beta2^t) / (1 - beta1^t)."""
+        return lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+
+    def adam_step(self, lr, clip_norm=0.0, lr_t_dev=None):
+        """TF-form Adam update of the flat parameter vector.  With lr_t_dev (device scalar) the launch
+        takes its rate from device memory - the form a CUDA graph replays; the caller advances
+        params.step and refreshes the scalar."""
         p = self.params
-        p.step += 1
+        if lr_t_dev is None:
+            p.step += 1
         rc = self.lib.distbo_adam_f64(_lib.ptr(p.flat), _lib.ptr(p.grad), _lib.ptr(p.m), _lib.ptr(p.v), p.n,
-                                      float(lr), 0.9, 0.999, 1e-8, p.step, float(clip_norm), None, _stream())
+                                      float(lr), 0.9, 0.999, 1e-8, max(p.step, 1), float(clip_norm),
+                                      _lib.ptr(lr_t_dev), _stream())
         _lib.check(rc, "distbo_adam_f64")
 
     def read_loss(self):

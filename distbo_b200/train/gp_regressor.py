@@ -21,6 +21,7 @@ datasets' rows are embedded from at prediction time: fp32 when False)
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -170,6 +171,7 @@ class gp_regressor(object):
         self._batch_off = batch_off if sampler is not None else None
         self._lr, self._clip = learning_rate, (5.0 if gradient_clip else 0.0)
         self._scaler_dev = (self._dev(self.params_scaler.mean_), self._dev(self.params_scaler.scale_))
+        self._setup_epoch_state()
 
         # ---- training loop: train/train.py:11-71
         if first_early_stop_epoch is None:
@@ -194,25 +196,84 @@ class gp_regressor(object):
         self.pre_compute_embed = True
         return loss
 
-    def run_epoch(self):
-        """One optimisation step (loss, full gradient, Adam update) queued on the current stream with
-        no host synchronisation: what one sess.run([optimize_step, loss]) is in train/train.py:43-52."""
+    # One optimisation step = one CUDA graph.  The step's launch sequence (embedding forward, task Gram,
+    # Gram, POTRF with its look-ahead stream, TRTRI, LAUUM, likelihood, gradient contractions, embedding
+    # backward, Adam) is identical from epoch to epoch, so it is captured once per fit and replayed; the
+    # only per-epoch inputs - the mini-batch row indices and Adam's lr_t - reach the graph through
+    # static device buffers refreshed from a small ring of pinned host slots.
+    RING = 4
+
+    def _setup_epoch_state(self):
+        e, sampler = self.engine, self._sampler
+        self._graph = None
+        self._graph_warm = 0
+        self._lrt_dev = torch.zeros(1, dtype=torch.float64, device=e.dev)
+        self._ring = []
+        self._ring_pos = 0
+        n_idx = 0
+        if sampler is not None and not sampler.constant:
+            n_idx = int(sum(sampler.sizes()))
+            self._gather_dev = torch.zeros(n_idx, dtype=torch.int64, device=e.dev)
+            self._bX = torch.empty(n_idx, self._full[0].shape[1], dtype=torch.float64, device=e.dev)
+            self._bY = torch.empty(n_idx, self._full[1].shape[1], dtype=torch.float64, device=e.dev)
+        for _ in range(self.RING):
+            self._ring.append({"idx": torch.empty(max(n_idx, 1), dtype=torch.int64).pin_memory(),
+                               "lrt": torch.empty(1, dtype=torch.float64).pin_memory(),
+                               "ev": torch.cuda.Event()})
+        self._use_graph = os.environ.get("DISTBO_GRAPH", "1") != "0"
+
+    def _stage_inputs(self):
+        """Host side of one epoch: draw the mini-batch rows, compute lr_t, queue both copies."""
+        e, sampler = self.engine, self._sampler
+        slot = self._ring[self._ring_pos]
+        self._ring_pos = (self._ring_pos + 1) % self.RING
+        slot["ev"].synchronize()                 # the copies that last used this slot have completed
+        e.params.step += 1
+        slot["lrt"][0] = e.adam_lr_t(self._lr, e.params.step)
+        self._lrt_dev.copy_(slot["lrt"], non_blocking=True)
+        if sampler is not None and not sampler.constant:
+            fo = self._full_off
+            rows = [np.arange(fo[i], fo[i + 1]) if ix is None else fo[i] + ix
+                    for i, ix in enumerate(sampler.next_indices())]
+            slot["idx"].copy_(torch.from_numpy(np.concatenate(rows)))
+            self._gather_dev.copy_(slot["idx"], non_blocking=True)
+        slot["ev"].record()
+
+    def _epoch_body(self):
         e, sampler = self.engine, self._sampler
         if sampler is None:
             e.loss_and_grad(E_const=self._E_const)
+        elif sampler.constant:
+            e.loss_and_grad(self._full[0], self._full[1], self._full[2], size_ratio=self._ratio)
         else:
-            if sampler.constant:
-                bX, bY, boff = self._full
-            else:
-                fo = self._full_off
-                rows = [np.arange(fo[i], fo[i + 1]) if ix is None else fo[i] + ix
-                        for i, ix in enumerate(sampler.next_indices())]
-                gather = torch.from_numpy(np.concatenate(rows)).to(e.dev)
-                bX = self._full[0].index_select(0, gather)
-                bY = self._full[1].index_select(0, gather)
-                boff = self._batch_off
-            e.loss_and_grad(bX, bY, boff, size_ratio=self._ratio)
-        e.adam_step(self._lr, clip_norm=self._clip)
+            torch.index_select(self._full[0], 0, self._gather_dev, out=self._bX)
+            torch.index_select(self._full[1], 0, self._gather_dev, out=self._bY)
+            e.loss_and_grad(self._bX, self._bY, self._batch_off, size_ratio=self._ratio)
+        e.adam_step(self._lr, clip_norm=self._clip, lr_t_dev=self._lrt_dev)
+
+    def run_epoch(self):
+        """One optimisation step (loss, full gradient, Adam update) queued on the current stream with
+        no host synchronisation: what one sess.run([optimize_step, loss]) is in train/train.py:43-52."""
+        self._stage_inputs()
+        if self._graph is not None:
+            self._graph.replay()
+        elif self._use_graph and self._graph_warm >= 1:
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g):
+                    self._epoch_body()
+                self._graph = g
+                g.replay()
+            except Exception as exc:        # same kernels either way: run the step eagerly
+                import warnings
+                warnings.warn("distbo_b200: CUDA graph capture of the training step failed (%s); "
+                              "launching eagerly" % (exc,))
+                self._use_graph = False
+                torch.cuda.synchronize()
+                self._epoch_body()
+        else:
+            self._epoch_body()              # first epoch of a fit: eager (allocates persistent buffers)
+            self._graph_warm += 1
         self._fit_generation += 1
 
     # ------------------------------------------------------------------ predict

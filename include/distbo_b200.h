@@ -90,9 +90,11 @@ int distbo_trtri_f64(void* plan, const double* L, double* W, double* T, void* st
 /* Kinv (lower 128-tiles) <- W^T W. */
 int distbo_lauum_f64(void* plan, const double* W, double* Kinv, void* stream);
 /* V = W (y - mean), alpha = W^T V, nll = 0.5|V|^2 + 0.5 N log(2 pi) + sum log L_ii.
- * y [N]; V, alpha [n_pad]; mean, nll device scalars. */
+ * y [N]; V, alpha [n_pad]; mean, nll device scalars; workspace: distbo_nll_workspace(n_pad) doubles. */
+int64_t distbo_nll_workspace(int n_pad);
 int distbo_nll_f64(const double* L, const double* W, int N, int n_pad, const double* y,
-                   const double* mean, double* V, double* alpha, double* nll, void* stream);
+                   const double* mean, double* V, double* alpha, double* nll, double* workspace,
+                   void* stream);
 /* Closed-form gradient contraction with G = 0.5 (Kinv - alpha alpha^T), replacing TF autodiff
  * through the Cholesky (train/train.py:33-40):
  *   g_log_bw [d], g_scalars = {d/dlog_scale, d/dmean, d/dlog_sigma}, H [T,T] = dNLL/dKE (full).
@@ -102,14 +104,19 @@ int distbo_gram_grad_f64(const double* Kinv, const double* alpha, const double* 
                          const int32_t* task_off, const double* KE, int T, const double* log_scale,
                          const double* log_sigma, double* g_log_bw, double* g_scalars, double* H,
                          double* workspace, void* stream);
-/* Backward of distbo_task_gram_f64: H [T,T] -> g_log_bw_embed [P], dE [T,lde] (cols < P). */
+/* Backward of distbo_task_gram_f64: H [T,T] -> g_log_bw_embed [P], dE [T,lde] (cols < P).
+ * workspace: T * P doubles. */
 int distbo_task_gram_bwd_f64(const double* E, int lde, int T, int P, const double* log_bw_embed,
-                             const double* H, double* g_log_bw_embed, double* dE, void* stream);
-/* TF-1.7 Adam update on a flat parameter vector (train/gp_regressor.py:141; epsilon-hat form).
- * clip_norm <= 0 disables tf.clip_by_global_norm (train/train.py:33-35). step is 1-based. */
+                             const double* H, double* g_log_bw_embed, double* dE, double* workspace,
+                             void* stream);
+/* TF-1.7 Adam update on a flat parameter vector (train/gp_regressor.py:141; epsilon-hat form):
+ * lr_t = lr sqrt(1 - beta2^step) / (1 - beta1^step); p -= lr_t m / (sqrt(v) + eps).  step is 1-based.
+ * clip_norm <= 0 disables tf.clip_by_global_norm (train/train.py:33-35).
+ * lr_t_dev (optional): device scalar holding lr_t; when non-NULL it is used instead of (lr, step) so
+ * that the launch can be replayed from a CUDA graph with a value the host refreshes per step. */
 int distbo_adam_f64(double* params, const double* grads, double* m, double* v, int64_t n, double lr,
                     double beta1, double beta2, double eps, int64_t step, double clip_norm,
-                    double* scratch, void* stream);
+                    const double* lr_t_dev, void* stream);
 
 /* ---- K4: posterior + acquisition + argmax  (log_gaus_likelihood.py:128-218; gp_regressor.py:197;
  *      bayes_opt/helpers.py:51-68,151-171) ---------------------------------------------------------
