@@ -30,13 +30,141 @@ struct TriNode {
 struct Plan {
   int n = 0, nb = 0;
   int4* d_tiles = nullptr;
-  std::vector<Range> trsm, syrk_first, syrk_rest, tri1, tri2;
+  std::vector<Range> syrk_rest, tri1, tri2;   // trailing update (columns >= kb+2), TRTRI levels
   Range lauum{0, 0};
   cudaStream_t panel_stream = nullptr;
   std::vector<cudaEvent_t> ev_panel, ev_first;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   bool lookahead = true;
+  int* d_flags = nullptr;    // [nb] "inverse of diagonal block kb is published" (fused panel kernel)
+  int sms = 148;
 };
+
+// ------------------------------------------------------------------ fused panel kernel
+// One launch per column block kb, CTA c -> row block i = kb + c:
+//   1. acc = A[i,kb] - L[i,kb-1] L[kb,kb-1]^T        (the update of column kb by the previous panel;
+//                                                    older panels were applied by the trailing kernels)
+//   2. c == 0: the diagonal tile goes to shared memory, is factorised and inverted there (potf2.cuh);
+//              inv(L_kk) is written to W and published through flags[kb]; then L_kk is written to A.
+//      c  > 0: the accumulator tile stays in shared memory as the A operand, the CTA waits for the flag
+//              and multiplies by inv(L_kk)^T (DMMA, B streamed from L2), result -> A[i,kb].
+// The chain update -> potf2 -> solve therefore costs one launch and no global round trip of the tile.
+// Waiting CTAs only ever wait for block 0 of their own grid (<= 64 CTAs, all resident on 148 SMs).
+struct PanelArgs {
+  double* A;
+  double* W;
+  int ld, kb, nb;
+  int32_t* info;
+  int* flags;
+  unsigned long long* tl;   // debug timeline, normally null
+};
+
+constexpr int PANEL_SMEM = (PB * PLD + STAGES * STAGE_ELEMS) * (int)sizeof(double);  // 217088 >= POTF2_SMEM
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int kb = p.kb, ld = p.ld, nb = p.nb;
+  const int n0 = kb * BN;
+  double* sT = smem;  // [128][PLD] tile
+  tl_start(p.tl, 2 * kb);
+  bool flag_seen = false;
+
+  // CTA 0 owns the diagonal block; CTA c >= 1 owns row blocks kb + c, kb + c + (G-1), ...
+  const int stride = (blockIdx.x == 0) ? nb : (int)gridDim.x - 1;
+  for (int i = kb + (int)blockIdx.x; i < nb; i += stride) {
+    const int m0 = i * BM;
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      const int row = m0 + wm * 64 + mi * 8 + lr;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int col = n0 + wn * 32 + ni * 8 + lk * 2;
+        const double2 c = *reinterpret_cast<const double2*>(p.A + (size_t)row * ld + col);
+        acc[mi][ni][0] = -c.x;   // tile = -(acc) = C - A B after the main loop
+        acc[mi][ni][1] = -c.y;
+      }
+    }
+    if (kb > 0) gemm_mainloop<KMAJOR, KMAJOR>(acc, p.A, ld, p.A, ld, m0, n0, n0 - BN, n0, smem);
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      const int r = wm * 64 + mi * 8 + lr;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int c = wn * 32 + ni * 8 + lk * 2;
+        double2 v = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+        if (blockIdx.x == 0) {  // diagonal tile: potf2 expects zeros above the diagonal
+          if (c > r) v.x = 0.0;
+          if (c + 1 > r) v.y = 0.0;
+        }
+        *reinterpret_cast<double2*>(&sT[r * PLD + c]) = v;
+      }
+    }
+    __syncthreads();
+
+    double* Ab = p.A + (size_t)m0 * ld + n0;
+    if (blockIdx.x == 0) {
+      double* Wb = p.W + (size_t)m0 * ld + n0;
+      long long* dbg = nullptr;
+      tl_mark(p.tl, 2 * kb, 2);   // update done, potf2 starts
+      potf2_factor_invert(smem, m0, p.info, dbg);
+      potf2_store_W(smem, Wb, ld);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicExch(p.flags + kb, 1);
+      tl_mark(p.tl, 2 * kb, 3);   // inverse published
+      potf2_store_L(smem, Ab, ld);
+      break;
+    }
+
+    if (!flag_seen) {
+      if (tid == 0) {
+        while (atomicAdd(p.flags + kb, 0) == 0) __nanosleep(100);
+        __threadfence();
+      }
+      __syncthreads();
+      flag_seen = true;
+    }
+    double out[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) out[mi][ni][0] = out[mi][ni][1] = 0.0;
+    // out[m][n] = sum_k tile[m][k] * Winv[n][k]   (B = inv(L_kk), k-major, read through L2 with cp.async.cg)
+    const double* Wd = p.W + (size_t)n0 * ld + n0;
+    gemm_mainloop_smemA<KMAJOR>(out, sT, PLD, Wd, ld, 0, 0, BN, smem + PB * PLD);
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+      const int r = wm * 64 + mi * 8 + lr;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int c = wn * 32 + ni * 8 + lk * 2;
+        *reinterpret_cast<double2*>(Ab + (size_t)r * ld + c) = make_double2(out[mi][ni][0], out[mi][ni][1]);
+      }
+    }
+    // gemm_mainloop_smemA ended with a barrier: sT and the pipeline buffers may be overwritten
+  }
+  tl_end(p.tl, 2 * kb);
+}
+
+// Number of CTAs of the panel kernel for column block kb: as few as keep the panel (update -> potf2 ->
+// solve chain over its row blocks) shorter than the concurrent trailing update, which then gets the
+// remaining SMs; all row blocks in parallel once the trailing update is the shorter of the two.
+static int panel_ctas(int nb, int kb, int sms, int rest_tiles_prev) {
+  const int rows = nb - kb;            // row blocks incl. the diagonal
+  if (rows <= 2) return rows;
+  const double t_tile = 21.0, t_upd = 23.0, t_potf2 = 60.0, t_solve = 22.0;   // microseconds, measured
+  for (int G = 2; G < rows; ++G) {
+    const int per = (rows - 1 + G - 2) / (G - 1);
+    const double panel = t_upd + t_potf2 + t_solve + (per - 1) * (t_upd + t_solve);
+    const double rest = rest_tiles_prev * t_tile / (double)(sms - G);
+    if (panel <= 0.85 * rest) return G;
+  }
+  return rows;
+}
 
 static int build_tri(int o, int cnt, std::vector<std::vector<TriNode>>& levels) {
   if (cnt == 1) return 0;
@@ -55,6 +183,14 @@ static bool longer_k(const int4& a, const int4& b) { return (a.w - a.z) > (b.w -
 using namespace db;
 
 long long g_db_launches = 0;
+static unsigned long long* g_timeline = nullptr;
+
+// Debug aid (tools/potrf_timeline.py): device buffer of 2*nb*4 uint64 (init: slot 0 = ~0, others 0) that the
+// POTRF kernels fill with globaltimer stamps; pass NULL to switch it off.  Not part of the product path.
+extern "C" int distbo_debug_timeline(void* buf) {
+  g_timeline = (unsigned long long*)buf;
+  return DISTBO_OK;
+}
 
 extern "C" int distbo_version(void) { return 1000; }
 
@@ -74,15 +210,6 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
   auto T = [](int i) { return i * 128; };
   for (int kb = 0; kb < nb; ++kb) {
     Range r{(int)tiles.size(), 0};
-    for (int i = kb + 1; i < nb; ++i) tiles.push_back(make_int4(T(i), T(kb), T(kb), T(kb + 1)));
-    r.cnt = (int)tiles.size() - r.off;
-    p->trsm.push_back(r);
-    r = Range{(int)tiles.size(), 0};
-    if (kb + 1 < nb)
-      for (int i = kb + 1; i < nb; ++i) tiles.push_back(make_int4(T(i), T(kb + 1), T(kb), T(kb + 1)));
-    r.cnt = (int)tiles.size() - r.off;
-    p->syrk_first.push_back(r);
-    r = Range{(int)tiles.size(), 0};
     for (int i = kb + 2; i < nb; ++i)
       for (int j = kb + 2; j <= i; ++j) tiles.push_back(make_int4(T(i), T(j), T(kb), T(kb + 1)));
     r.cnt = (int)tiles.size() - r.off;
@@ -139,7 +266,17 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
   cudaEventCreateWithFlags(&p->ev_end, cudaEventDisableTiming);
   const char* la = getenv("DISTBO_LOOKAHEAD");
   p->lookahead = !(la && la[0] == '0');
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (cudaMalloc(&p->d_flags, (size_t)nb * sizeof(int)) != cudaSuccess) {
+    cudaFree(p->d_tiles);
+    delete p;
+    return DISTBO_ECUDA;
+  }
   cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
+  cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
   *plan_out = p;
   return DISTBO_OK;
 }
@@ -154,6 +291,7 @@ extern "C" int distbo_plan_destroy(void* plan) {
   if (p->ev_end) cudaEventDestroy(p->ev_end);
   if (p->panel_stream) cudaStreamDestroy(p->panel_stream);
   if (p->d_tiles) cudaFree(p->d_tiles);
+  if (p->d_flags) cudaFree(p->d_flags);
   delete p;
   return DISTBO_OK;
 }
@@ -165,50 +303,46 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
   const int n = p->n, nb = p->nb;
   DB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), U));
 
-  GemmArgs trsm{};  // A[i-blk, kb] <- A[i-blk, kb] * inv(L_kk)^T   (in place; B = W diagonal block)
-  trsm.A = A; trsm.B = W; trsm.C = A; trsm.Cin = A;
-  trsm.lda = trsm.ldb = trsm.ldc = trsm.ldcin = n;
-  trsm.alpha = 1.0; trsm.beta = 0.0;
-  GemmArgs syrk{};  // C -= P P^T
-  syrk.A = A; syrk.B = A; syrk.C = A; syrk.Cin = A;
-  syrk.lda = syrk.ldb = syrk.ldc = syrk.ldcin = n;
-  syrk.alpha = -1.0; syrk.beta = 1.0;
+  {
+    DB_CUDA(cudaMemsetAsync(p->d_flags, 0, (size_t)nb * sizeof(int), U));
+    GemmArgs rest{};  // C -= P P^T on the tiles (i, j), j >= kb + 2
+    rest.A = A; rest.B = A; rest.C = A; rest.Cin = A;
+    rest.lda = rest.ldb = rest.ldc = rest.ldcin = n;
+    rest.alpha = -1.0; rest.beta = 1.0;
+    const bool fork = p->lookahead && nb > 2;
+    cudaStream_t P = fork ? p->panel_stream : U;
+    if (fork) {
+      DB_CUDA(cudaEventRecord(p->ev_begin, U));
+      DB_CUDA(cudaStreamWaitEvent(P, p->ev_begin, 0));
+    }
+    for (int kb = 0; kb < nb; ++kb) {
+      // column kb must have received the trailing update of panel kb-2 (ev_first doubles as "rest done")
+      if (fork && kb >= 2 && p->syrk_rest[kb - 2].cnt) DB_CUDA(cudaStreamWaitEvent(P, p->ev_first[kb - 2], 0));
+      PanelArgs pa{A, W, n, kb, nb, info, p->d_flags, g_timeline};
+      rest.tl = g_timeline;
+      rest.tl_id = 2 * kb + 1;
+      // panel(kb) runs next to the trailing update of panel kb-1; panel(kb+1) next to this rest(kb)
+      const int g_this = fork ? panel_ctas(nb, kb, p->sms, kb >= 1 ? p->syrk_rest[kb - 1].cnt : 0) : nb - kb;
+      panel_kernel<<<g_this, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
+      DB_CHECK_LAUNCH();
+      if (p->syrk_rest[kb].cnt) {
+        if (fork) {
+          DB_CUDA(cudaEventRecord(p->ev_panel[kb], P));
+          DB_CUDA(cudaStreamWaitEvent(U, p->ev_panel[kb], 0));
+        }
+        rest.tiles = p->d_tiles + p->syrk_rest[kb].off;
+        DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(rest, p->syrk_rest[kb].cnt, U)));
+        if (fork) DB_CUDA(cudaEventRecord(p->ev_first[kb], U));
+      }
+    }
+    if (fork) {
+      DB_CUDA(cudaEventRecord(p->ev_end, P));
+      DB_CUDA(cudaStreamWaitEvent(U, p->ev_end, 0));
+    }
+    return DISTBO_OK;
+  }
 
-  const bool la = p->lookahead && nb > 2;
-  cudaStream_t P = la ? p->panel_stream : U;
-  if (la) {
-    DB_CUDA(cudaEventRecord(p->ev_begin, U));
-    DB_CUDA(cudaStreamWaitEvent(P, p->ev_begin, 0));
-  }
-  for (int kb = 0; kb < nb; ++kb) {
-    potf2_inv_kernel<<<1, POTF2_THREADS, POTF2_SMEM, P>>>(A, n, W, kb, info);
-    DB_CHECK_LAUNCH();
-    if (p->trsm[kb].cnt) {
-      trsm.tiles = p->d_tiles + p->trsm[kb].off;
-      DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(trsm, p->trsm[kb].cnt, P)));
-    }
-    if (la) {
-      DB_CUDA(cudaEventRecord(p->ev_panel[kb], P));
-      DB_CUDA(cudaStreamWaitEvent(U, p->ev_panel[kb], 0));
-    }
-    if (p->syrk_first[kb].cnt) {
-      syrk.tiles = p->d_tiles + p->syrk_first[kb].off;
-      DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(syrk, p->syrk_first[kb].cnt, U)));
-    }
-    if (la) {
-      DB_CUDA(cudaEventRecord(p->ev_first[kb], U));
-      DB_CUDA(cudaStreamWaitEvent(P, p->ev_first[kb], 0));
-    }
-    if (p->syrk_rest[kb].cnt) {
-      syrk.tiles = p->d_tiles + p->syrk_rest[kb].off;
-      DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(syrk, p->syrk_rest[kb].cnt, U)));
-    }
-  }
-  if (la) {
-    DB_CUDA(cudaEventRecord(p->ev_end, P));
-    DB_CUDA(cudaStreamWaitEvent(U, p->ev_end, 0));
-  }
-  return DISTBO_OK;
+  return DISTBO_EARG;  // unreachable: the fused panel path above is the only one
 }
 
 extern "C" int distbo_trtri_f64(void* plan, const double* L, double* W, double* T, void* stream) {

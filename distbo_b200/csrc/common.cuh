@@ -25,6 +25,23 @@ extern long long g_db_launches;
 
 namespace db {
 
+// Debug timeline (tools/potrf_timeline.py): when non-null, instrumented kernels record globaltimer stamps
+// into tl[launch_id * 4 + {0: earliest CTA start, 1: latest CTA end, 2, 3: kernel specific}].
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_start(unsigned long long* tl, int id) {
+  if (tl && threadIdx.x == 0) atomicMin(tl + id * 4 + 0, globaltimer_ns());
+}
+__device__ __forceinline__ void tl_end(unsigned long long* tl, int id) {
+  if (tl && threadIdx.x == 0) atomicMax(tl + id * 4 + 1, globaltimer_ns());
+}
+__device__ __forceinline__ void tl_mark(unsigned long long* tl, int id, int slot) {
+  if (tl && threadIdx.x == 0) atomicMax(tl + id * 4 + slot, globaltimer_ns());
+}
+
 constexpr double kSqrt3 = 1.7320508075688772935;
 constexpr double kDistClamp = 1e-32;  // reference train/kernels.py:25
 constexpr double kVarClamp = 1e-32;   // reference train/gp_regressor.py:197

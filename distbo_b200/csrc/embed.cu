@@ -3,80 +3,51 @@
 // Reference: train/distbo_net.py:7-48 (nn_net, joint / classification branches),
 //            train/base.py:9-43 (mean pooling by a sparse [T,S] matrix with 1/size entries).
 //
-// Forward: one thread-block CLUSTER of EMB_CL CTAs per dataset.  Each CTA streams its share of the
-// dataset's rows through shared memory in k-chunks (coalesced loads), one thread per sample keeps
-// the hidden activations in registers, a second phase accumulates the outer products, and the
-// CTA partials are combined in rank order through distributed shared memory (deterministic, no
-// global workspace, no atomics).
-#include <cooperative_groups.h>
-
+// Work decomposition (both directions): every dataset is cut into row chunks of ROWS = 32*RM rows; a
+// small prep kernel turns seg_off into the chunk table on the device (no host sync).  A CTA owns one
+// chunk at a time (grid-stride).  Per chunk:
+//   layer 1   z = x W1 + b1 as a register-blocked GEMM: the x tile is staged through shared memory in
+//             64-column slices (coalesced global loads), warp = group of 4 hidden units, lane = row
+//             group, each thread keeps RM rows x 4 hidden accumulators; shared loads are 128-bit and
+//             conflict free (row stride = odd multiple of 16 bytes);
+//   layer 2   phi = tanh(z) W2 from shared memory;
+//   pooling   partial[chunk][i*q+j] = sum_rows phi_x[i] phi_y[j]  (fixed row order), then a reduce
+//             kernel adds a dataset's chunks in chunk order and scales by 1/size: deterministic,
+//             no atomics.
+// Backward recomputes the activations per chunk, forms dz in shared memory and accumulates the weight
+// gradients in CTA-private shared memory (each entry owned by one thread) across all of a CTA's
+// chunks (x tile re-read from L2); per-CTA partials are added in CTA order by a reduce kernel.
 #include "../../include/distbo_b200.h"
 #include "common.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace db {
 
-constexpr int EMB_THREADS = 128;  // samples per batch (one per thread)
-constexpr int EMB_CL = 4;         // CTAs per dataset (cluster size)
-constexpr int EMB_KC = 32;        // input columns staged per chunk
-constexpr int EMB_HMAX = 32;      // max hidden width
-constexpr int EMB_PMAX = 16;      // max feature-map output width (p, q)
-constexpr int EMB_ACC = 4;        // output columns per thread: P' <= EMB_ACC * EMB_THREADS
-constexpr int EMB_BWD_GRID = 296;
+constexpr int EMB_KC = 64;         // input columns staged per slice
+constexpr int EMB_HMAX = 32;       // max hidden width
+constexpr int EMB_PMAX = 16;       // max feature-map output width (p, q)
+constexpr int EMB_MAXWARPS = EMB_HMAX / 4;
+constexpr int EMB_BWD_GRID = 296;  // persistent CTAs of the backward kernel (2 per SM)
 
-template <typename T>
-__device__ __forceinline__ T tanh_t(T x);
-template <>
-__device__ __forceinline__ float tanh_t<float>(float x) { return tanhf(x); }
-template <>
-__device__ __forceinline__ double tanh_t<double>(double x) { return tanh(x); }
-
-struct NetDims {
-  int din, h, p;
-};
-
-// shared-memory layout helpers (element counts)
-__host__ __device__ inline int net_w_elems(int din, int h, int p) { return din * h + h + h * p; }
-
-// Computes out[0..p) = tanh(x W1 + b1) W2 for this thread's sample; x streamed from global in
-// k-chunks through sX [EMB_THREADS][EMB_KC+1].  hid[] (tanh activations) is returned for backward.
-template <typename T>
-__device__ __forceinline__ void mlp_forward(const T* __restrict__ Xg, long long row0, int nrows, int din,
-                                            const T* sW1, const T* sb1, const T* sW2, int h, int p, T* sX,
-                                            T (&hid)[EMB_HMAX], T (&out)[EMB_PMAX]) {
-  const int tid = threadIdx.x;
-#pragma unroll
-  for (int j = 0; j < EMB_HMAX; ++j) hid[j] = (j < h) ? sb1[j] : (T)0;
-  for (int k0 = 0; k0 < din; k0 += EMB_KC) {
-    const int kc = min(EMB_KC, din - k0);
-    __syncthreads();
-    for (int idx = tid; idx < EMB_THREADS * kc; idx += EMB_THREADS) {
-      const int r = idx / kc, k = idx % kc;
-      sX[r * (EMB_KC + 1) + k] = (r < nrows) ? Xg[(row0 + r) * din + k0 + k] : (T)0;
-    }
-    __syncthreads();
-    for (int k = 0; k < kc; ++k) {
-      const T x = sX[tid * (EMB_KC + 1) + k];
-      const T* w = sW1 + (size_t)(k0 + k) * h;
-#pragma unroll
-      for (int j = 0; j < EMB_HMAX; ++j)
-        if (j < h) hid[j] += x * w[j];
-    }
+template <typename T> struct EmbT;
+template <> struct EmbT<float> {
+  static constexpr int RM = 4;            // rows per thread -> 128-row chunks
+  static constexpr int XS = EMB_KC + 4;   // 272 B = 17 x 16 B
+  __device__ static float tanh_(float x) { return tanhf(x); }
+  __device__ static void load4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
-#pragma unroll
-  for (int j = 0; j < EMB_HMAX; ++j) hid[j] = (j < h) ? tanh_t<T>(hid[j]) : (T)0;
-#pragma unroll
-  for (int i = 0; i < EMB_PMAX; ++i) out[i] = (T)0;
-#pragma unroll
-  for (int j = 0; j < EMB_HMAX; ++j)
-    if (j < h) {
-      const T hj = hid[j];
-#pragma unroll
-      for (int i = 0; i < EMB_PMAX; ++i)
-        if (i < p) out[i] += hj * sW2[j * p + i];
-    }
-}
+};
+template <> struct EmbT<double> {
+  static constexpr int RM = 2;            // 64-row chunks
+  static constexpr int XS = EMB_KC + 2;   // 528 B = 33 x 16 B
+  __device__ static double tanh_(double x) { return tanh(x); }
+  __device__ static void load4(const double* p, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+};
 
 template <typename T>
 struct EmbedArgs {
@@ -89,278 +60,370 @@ struct EmbedArgs {
   int y_mode;
   T* E;
   int lde;
+  // workspace
+  const int32_t* chunk_ds;     // [max_chunks] dataset of chunk c
+  const int32_t* chunk_row;    // [max_chunks] first row of chunk c (global row index)
+  const int32_t* chunk_first;  // [T+1] first chunk of dataset t
+  T* partial;                  // [max_chunks][pout]
+};
+
+__host__ __device__ inline int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline int gq_of(int y_mode, int q, int dy) { return y_mode == 0 ? 1 : (y_mode == 1 ? q : dy); }
+__host__ __device__ inline int pout_of(int y_mode, int p, int q, int dy) {
+  return y_mode == 0 ? p : p * gq_of(y_mode, q, dy) + (y_mode == 2 ? dy : 0);
+}
+
+// ------------------------------------------------------------------ chunk table
+// chunk_first[t] = sum_{u<t} ceil(len_u / rows); chunk c of dataset t starts at seg_off[t] + (c - first) rows.
+__global__ void __launch_bounds__(256) embed_chunk_table_kernel(const int32_t* __restrict__ seg_off, int T, int rows,
+                                                                int32_t* __restrict__ chunk_first,
+                                                                int32_t* __restrict__ chunk_ds,
+                                                                int32_t* __restrict__ chunk_row) {
+  __shared__ int wsum[8];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < T; base += 256) {
+    const int t = base + tid;
+    const int len = (t < T) ? seg_off[t + 1] - seg_off[t] : 0;
+    const int nc = (len + rows - 1) / rows;
+    int incl = nc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += wsum[w];
+    const int first = carry + woff + incl - nc;
+    if (t < T) {
+      chunk_first[t] = first;
+      for (int c = 0; c < nc; ++c) {
+        chunk_ds[first + c] = t;
+        chunk_row[first + c] = seg_off[t] + c * rows;
+      }
+    }
+    __syncthreads();
+    if (tid == 255) carry = first + nc;
+    __syncthreads();
+  }
+  if (tid == 0) chunk_first[T] = carry;
+}
+
+// ------------------------------------------------------------------ shared building blocks
+// Copies one net's weights into shared memory: sW1 [round_up(din,4)][hp] (zero padded), sb1 [hp], sW2 [h][po].
+template <typename T>
+__device__ __forceinline__ void load_net(const T* __restrict__ W1, const T* __restrict__ b1, const T* __restrict__ W2,
+                                         int din, int h, int po, int hp, T* sW1, T* sb1, T* sW2) {
+  const int dinp = round_up_i(din, 4);
+  for (int i = threadIdx.x; i < dinp * hp; i += blockDim.x) {
+    const int k = i / hp, j = i - k * hp;
+    sW1[i] = (k < din && j < h) ? W1[k * h + j] : (T)0;
+  }
+  for (int j = threadIdx.x; j < hp; j += blockDim.x) sb1[j] = (j < h) ? b1[j] : (T)0;
+  for (int i = threadIdx.x; i < h * po; i += blockDim.x) sW2[i] = W2[i];
+}
+
+// Stage columns [k0, k0+kc) of `n` rows (row stride din) into sX [ROWS][XS]; rows >= n and the columns up
+// to the next multiple of 4 are zero filled.
+template <typename T>
+__device__ __forceinline__ void stage_tile(const T* __restrict__ Xg, int n, int din, int k0, int kc, T* sX) {
+  constexpr int ROWS = 32 * EmbT<T>::RM, XS = EmbT<T>::XS, U = 8;
+  const int kcp = round_up_i(kc, 4);
+  const int total = ROWS * kcp, nthr = blockDim.x;
+  // batches of U independent global loads per thread before the first shared store (memory-level parallelism)
+  for (int base = threadIdx.x; base < total; base += U * nthr) {
+    T v[U];
+    int dst[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * nthr;
+      const int r = idx / kcp, k = idx - r * kcp;
+      dst[u] = (idx < total) ? r * XS + k : -1;
+      v[u] = (idx < total && r < n && k < kc) ? __ldg(Xg + (size_t)r * din + k0 + k) : (T)0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (dst[u] >= 0) sX[dst[u]] = v[u];
+  }
+}
+
+// z[m][c] += sum_k x[rg + 32 m][k] * W1[k0 + k][4 hg + c] over the staged slice.
+template <typename T>
+__device__ __forceinline__ void layer1_slice(const T* sX, const T* sW1, int hp, int k0, int kc, int rg, int hg,
+                                             T (&z)[EmbT<T>::RM][4]) {
+  constexpr int RM = EmbT<T>::RM, XS = EmbT<T>::XS;
+  const int kcp = round_up_i(kc, 4);
+  for (int k = 0; k < kcp; k += 4) {
+    T x[RM][4];
+#pragma unroll
+    for (int m = 0; m < RM; ++m) EmbT<T>::load4(sX + (rg + 32 * m) * XS + k, x[m]);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      T w[4];
+      EmbT<T>::load4(sW1 + (size_t)(k0 + k + kk) * hp + 4 * hg, w);
+#pragma unroll
+      for (int m = 0; m < RM; ++m)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) z[m][c] += x[m][kk] * w[c];
+    }
+  }
+}
+
+// Hidden activations of one net for the chunk's rows: sH [ROWS][hp] = tanh(x W1 + b1) (0 on rows >= n).
+template <typename T>
+__device__ __forceinline__ void hidden_forward(const T* __restrict__ Xg, int n, int din, int h, int hp, const T* sW1,
+                                               const T* sb1, T* sX, T* sH) {
+  constexpr int RM = EmbT<T>::RM;
+  const int rg = threadIdx.x & 31, hg = threadIdx.x >> 5;
+  const bool active = 4 * hg < hp;
+  T z[RM][4];
+#pragma unroll
+  for (int m = 0; m < RM; ++m)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) z[m][c] = active ? sb1[4 * hg + c] : (T)0;
+  for (int k0 = 0; k0 < din; k0 += EMB_KC) {
+    const int kc = min(EMB_KC, din - k0);
+    __syncthreads();
+    stage_tile<T>(Xg, n, din, k0, kc, sX);
+    __syncthreads();
+    if (active) layer1_slice<T>(sX, sW1, hp, k0, kc, rg, hg, z);
+  }
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < RM; ++m) {
+      const int r = rg + 32 * m;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sH[r * hp + 4 * hg + c] = (r < n && 4 * hg + c < h) ? EmbT<T>::tanh_(z[m][c]) : (T)0;
+    }
+  }
+  __syncthreads();
+}
+
+// sF [ROWS][po] = sH W2 (0 on rows >= n because sH is 0 there)
+template <typename T>
+__device__ __forceinline__ void output_forward(const T* sH, const T* sW2, int h, int hp, int po, T* sF, int fs) {
+  constexpr int ROWS = 32 * EmbT<T>::RM;
+  for (int idx = threadIdx.x; idx < ROWS * po; idx += blockDim.x) {
+    const int r = idx / po, i = idx - r * po;
+    T s = (T)0;
+    for (int j = 0; j < h; ++j) s += sH[r * hp + j] * sW2[j * po + i];
+    sF[r * fs + i] = s;
+  }
+}
+
+// shared-memory carve-up shared by forward and backward (every region starts on a 4-element boundary)
+template <typename T>
+struct EmbSmem {
+  T *sW1x, *sb1x, *sW2x, *sW1y, *sb1y, *sW2y, *sX, *sHx, *sHy, *sFx, *sFy, *sDZ, *sDF, *sG;
+  int hpx, hpy, gq, fsx, fsy, dfs;
+  size_t elems;
 };
 
 template <typename T>
-__global__ void __launch_bounds__(EMB_THREADS) embed_fwd_kernel(EmbedArgs<T> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const int seg = blockIdx.x / EMB_CL;
-  const int tid = threadIdx.x;
-
-  const int gq = (a.y_mode == 0) ? 1 : (a.y_mode == 1 ? a.q : a.dy);  // width of the y-side factor
-  const int pout = (a.y_mode == 0) ? a.p : a.p * gq + (a.y_mode == 2 ? a.dy : 0);
-
-  T* sWx = reinterpret_cast<T*>(smem_raw);
-  T* sWy = sWx + net_w_elems(a.dx, a.hx, a.p);
-  T* sX = sWy + ((a.y_mode == 1) ? net_w_elems(a.dy, a.hy, a.q) : 0);
-  T* sF = sX + EMB_THREADS * (EMB_KC + 1);                   // [EMB_THREADS][p + gq]
-  T* sOut = sF + EMB_THREADS * (a.p + gq);                   // [pout]
-
-  for (int i = tid; i < a.dx * a.hx; i += EMB_THREADS) sWx[i] = a.W1x[i];
-  for (int i = tid; i < a.hx; i += EMB_THREADS) sWx[a.dx * a.hx + i] = a.b1x[i];
-  for (int i = tid; i < a.hx * a.p; i += EMB_THREADS) sWx[a.dx * a.hx + a.hx + i] = a.W2x[i];
-  if (a.y_mode == 1) {
-    for (int i = tid; i < a.dy * a.hy; i += EMB_THREADS) sWy[i] = a.W1y[i];
-    for (int i = tid; i < a.hy; i += EMB_THREADS) sWy[a.dy * a.hy + i] = a.b1y[i];
-    for (int i = tid; i < a.hy * a.q; i += EMB_THREADS) sWy[a.dy * a.hy + a.hy + i] = a.W2y[i];
-  }
-  __syncthreads();
-
-  const long long s0 = a.seg_off[seg], s1 = a.seg_off[seg + 1];
-  const long long len = s1 - s0;
-  const long long per = (len + EMB_CL - 1) / EMB_CL;
-  const long long r_begin = s0 + min(len, per * rank), r_end = s0 + min(len, per * (rank + 1));
-
-  T accv[EMB_ACC];
-#pragma unroll
-  for (int c = 0; c < EMB_ACC; ++c) accv[c] = (T)0;
-
-  for (long long row0 = r_begin; row0 < r_end; row0 += EMB_THREADS) {
-    const int nrows = (int)min((long long)EMB_THREADS, r_end - row0);
-    T hid[EMB_HMAX], f[EMB_PMAX];
-    mlp_forward<T>(a.X, row0, nrows, a.dx, sWx, sWx + a.dx * a.hx, sWx + a.dx * a.hx + a.hx, a.hx, a.p, sX, hid, f);
-    T g[EMB_PMAX];
-    if (a.y_mode == 1) {
-      mlp_forward<T>(a.Y, row0, nrows, a.dy, sWy, sWy + a.dy * a.hy, sWy + a.dy * a.hy + a.hy, a.hy, a.q, sX, hid, g);
-    } else if (a.y_mode == 2) {
-#pragma unroll
-      for (int j = 0; j < EMB_PMAX; ++j) g[j] = (j < a.dy && tid < nrows) ? a.Y[(row0 + tid) * a.dy + j] : (T)0;
-    } else {
-      g[0] = (T)1;
-    }
-    __syncthreads();
-    const bool live = tid < nrows;
-#pragma unroll
-    for (int i = 0; i < EMB_PMAX; ++i)
-      if (i < a.p) sF[tid * (a.p + gq) + i] = live ? f[i] : (T)0;
-#pragma unroll
-    for (int j = 0; j < EMB_PMAX; ++j)
-      if (j < gq) sF[tid * (a.p + gq) + a.p + j] = live ? g[j] : (T)0;
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < EMB_ACC; ++c) {
-      const int o = tid + c * EMB_THREADS;
-      if (o < pout) {
-        T s = (T)0;
-        if (o < a.p * gq) {
-          const int i = o / gq, j = o % gq;   // row-major flatten i*q + j (distbo_net.py:40-42)
-          for (int r = 0; r < EMB_THREADS; ++r) s += sF[r * (a.p + gq) + i] * sF[r * (a.p + gq) + a.p + j];
-        } else {
-          const int j = o - a.p * gq;         // class ratios: mean of y (distbo_net.py:45-48)
-          for (int r = 0; r < EMB_THREADS; ++r) s += sF[r * (a.p + gq) + a.p + j];
-        }
-        accv[c] += s;
-      }
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < EMB_ACC; ++c) {
-    const int o = tid + c * EMB_THREADS;
-    if (o < pout) sOut[o] = accv[c];
-  }
-  cluster.sync();
-  if (rank == 0) {
-    const T inv = (T)1 / (T)len;
-    for (int o = tid; o < pout; o += EMB_THREADS) {
-      T s = (T)0;
-      for (int r = 0; r < EMB_CL; ++r) s += *cluster.map_shared_rank(sOut + o, r);
-      a.E[(size_t)seg * a.lde + o] = s * inv;
-    }
-  }
-  cluster.sync();  // keep remote shared memory alive until rank 0 has read it
+__host__ __device__ inline EmbSmem<T> emb_layout(T* base, int dx, int dy, int hx, int p, int hy, int q, int y_mode,
+                                                 bool backward) {
+  constexpr int ROWS = 32 * EmbT<T>::RM, XS = EmbT<T>::XS;
+  EmbSmem<T> s;
+  s.hpx = round_up_i(hx, 4);
+  s.hpy = (y_mode == 1) ? round_up_i(hy, 4) : 0;
+  s.gq = gq_of(y_mode, q, dy);
+  s.fsx = p + 1;
+  s.fsy = s.gq + 1;
+  s.dfs = (p > s.gq ? p : s.gq) + 1;
+  size_t off = 0;
+  auto take = [&](size_t n) { T* ptr = base + off; off += (n + 3) / 4 * 4; return ptr; };
+  s.sW1x = take((size_t)round_up_i(dx, 4) * s.hpx);
+  s.sb1x = take(s.hpx);
+  s.sW2x = take((size_t)hx * p);
+  s.sW1y = take((y_mode == 1) ? (size_t)round_up_i(dy, 4) * s.hpy : 0);
+  s.sb1y = take(s.hpy);
+  s.sW2y = take((y_mode == 1) ? (size_t)hy * q : 0);
+  s.sX = take((size_t)ROWS * XS);
+  s.sHx = take((size_t)ROWS * s.hpx);
+  s.sHy = take((size_t)ROWS * s.hpy);
+  s.sFx = take((size_t)ROWS * s.fsx);
+  s.sFy = take((size_t)ROWS * s.fsy);
+  const int hpm = s.hpx > s.hpy ? s.hpx : s.hpy;
+  s.sDZ = take(backward ? (size_t)ROWS * hpm : 0);
+  s.sDF = take(backward ? (size_t)ROWS * s.dfs : 0);
+  const size_t nparams = (size_t)dx * hx + hx + (size_t)hx * p + ((y_mode == 1) ? (size_t)dy * hy + hy + (size_t)hy * q : 0);
+  s.sG = take(backward ? nparams : 0);
+  s.elems = off;
+  return s;
 }
 
+// Forward features of one chunk into shared memory: sFx [ROWS][p], sFy [ROWS][gq] (and sHx / sHy).
 template <typename T>
-static int embed_fwd_launch(const EmbedArgs<T>& a, cudaStream_t st) {
-  if (!a.X || !a.seg_off || !a.W1x || !a.b1x || !a.W2x || !a.E || a.T_ <= 0 || a.dx <= 0) return DISTBO_EARG;
-  if (a.hx <= 0 || a.hx > EMB_HMAX || a.p <= 0 || a.p > EMB_PMAX) return DISTBO_EARG;
-  if (a.y_mode < 0 || a.y_mode > 2) return DISTBO_EARG;
-  if (a.y_mode == 1 && (!a.Y || !a.W1y || !a.b1y || !a.W2y || a.hy <= 0 || a.hy > EMB_HMAX || a.q <= 0 ||
-                        a.q > EMB_PMAX || a.dy <= 0))
-    return DISTBO_EARG;
-  if (a.y_mode == 2 && (!a.Y || a.dy <= 0 || a.dy > EMB_PMAX)) return DISTBO_EARG;
-  const int gq = (a.y_mode == 0) ? 1 : (a.y_mode == 1 ? a.q : a.dy);
-  const int pout = (a.y_mode == 0) ? a.p : a.p * gq + (a.y_mode == 2 ? a.dy : 0);
-  if (pout > EMB_ACC * EMB_THREADS || a.lde < pout) return DISTBO_EARG;
-  size_t elems = net_w_elems(a.dx, a.hx, a.p) + ((a.y_mode == 1) ? net_w_elems(a.dy, a.hy, a.q) : 0) +
-                 EMB_THREADS * (EMB_KC + 1) + EMB_THREADS * (a.p + gq) + pout;
-  size_t smem = elems * sizeof(T) + 16;
-  if (smem > 220 * 1024) return DISTBO_EARG;
-  DB_CUDA(cudaFuncSetAttribute(embed_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(a.T_ * EMB_CL, 1, 1);
-  cfg.blockDim = dim3(EMB_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = EMB_CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  DB_CUDA(cudaLaunchKernelEx(&cfg, embed_fwd_kernel<T>, a));
-  ++g_db_launches;
-  return DISTBO_OK;
+__device__ __forceinline__ void chunk_features(const EmbedArgs<T>& a, const EmbSmem<T>& s, int row0, int n) {
+  constexpr int ROWS = 32 * EmbT<T>::RM;
+  hidden_forward<T>(a.X + (size_t)row0 * a.dx, n, a.dx, a.hx, s.hpx, s.sW1x, s.sb1x, s.sX, s.sHx);
+  output_forward<T>(s.sHx, s.sW2x, a.hx, s.hpx, a.p, s.sFx, s.fsx);
+  if (a.y_mode == 1) {
+    hidden_forward<T>(a.Y + (size_t)row0 * a.dy, n, a.dy, a.hy, s.hpy, s.sW1y, s.sb1y, s.sX, s.sHy);
+    output_forward<T>(s.sHy, s.sW2y, a.hy, s.hpy, a.q, s.sFy, s.fsy);
+  } else {
+    for (int idx = threadIdx.x; idx < ROWS * s.gq; idx += blockDim.x) {
+      const int r = idx / s.gq, j = idx - r * s.gq;
+      T v = (T)0;
+      if (r < n) v = (a.y_mode == 2) ? a.Y[(size_t)(row0 + r) * a.dy + j] : (T)1;
+      s.sFy[r * s.fsy + j] = v;
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ forward
+template <typename T>
+__global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_fwd_kernel(EmbedArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int ROWS = 32 * EmbT<T>::RM;
+  const EmbSmem<T> s = emb_layout<T>(reinterpret_cast<T*>(smem_raw), a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, false);
+  load_net<T>(a.W1x, a.b1x, a.W2x, a.dx, a.hx, a.p, s.hpx, s.sW1x, s.sb1x, s.sW2x);
+  if (a.y_mode == 1) load_net<T>(a.W1y, a.b1y, a.W2y, a.dy, a.hy, a.q, s.hpy, s.sW1y, s.sb1y, s.sW2y);
+  __syncthreads();   // weights (incl. the biases read right below) are visible to every thread
+  const int n_chunks = a.chunk_first[a.T_];
+  const int pout = pout_of(a.y_mode, a.p, a.q, a.dy);
+  const int gq = s.gq;
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const int t = a.chunk_ds[c], row0 = a.chunk_row[c];
+    const int n = min(ROWS, a.seg_off[t + 1] - row0);
+    chunk_features<T>(a, s, row0, n);
+    for (int o = threadIdx.x; o < pout; o += blockDim.x) {
+      T acc = (T)0;
+      if (o < a.p * gq) {
+        const int i = o / gq, j = o - i * gq;   // row-major flatten i*q + j (distbo_net.py:40-42)
+        for (int r = 0; r < ROWS; ++r) acc += s.sFx[r * s.fsx + i] * s.sFy[r * s.fsy + j];
+      } else {
+        const int j = o - a.p * gq;             // class ratios: mean of y (distbo_net.py:45-48)
+        for (int r = 0; r < ROWS; ++r) acc += s.sFy[r * s.fsy + j];
+      }
+      a.partial[(size_t)c * pout + o] = acc;
+    }
+  }
+}
+
+// E[t][o] = (sum over the dataset's chunks, in chunk order) / len
+template <typename T>
+__global__ void __launch_bounds__(128) embed_fwd_reduce_kernel(EmbedArgs<T> a) {
+  const int t = blockIdx.x;
+  const int pout = pout_of(a.y_mode, a.p, a.q, a.dy);
+  const int c0 = a.chunk_first[t], c1 = a.chunk_first[t + 1];
+  const T inv = (T)1 / (T)(a.seg_off[t + 1] - a.seg_off[t]);
+  for (int o = threadIdx.x; o < pout; o += 128) {
+    T acc = (T)0;
+    for (int c = c0; c < c1; ++c) acc += a.partial[(size_t)c * pout + o];
+    a.E[(size_t)t * a.lde + o] = acc * inv;
+  }
 }
 
 // ------------------------------------------------------------------ backward (fp64)
 struct EmbedBwdArgs {
   EmbedArgs<double> f;
   const double* dE;
-  double* partial;  // [EMB_BWD_GRID][nparams]
+  double* gpartial;  // [EMB_BWD_GRID][nparams]
   int nparams;
 };
 
-// accumulate G[k][j] += sum_r A[r][k] * B[r][j] over the batch, G in shared (owner-exclusive)
-__global__ void __launch_bounds__(EMB_THREADS) embed_bwd_kernel(EmbedBwdArgs b) {
+__global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdArgs b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const EmbedArgs<double>& a = b.f;
-  const int tid = threadIdx.x;
-  const int gq = (a.y_mode == 0) ? 1 : (a.y_mode == 1 ? a.q : a.dy);
-  const int nx = net_w_elems(a.dx, a.hx, a.p);
-  const int ny = (a.y_mode == 1) ? net_w_elems(a.dy, a.hy, a.q) : 0;
-
-  double* sWx = reinterpret_cast<double*>(smem_raw);
-  double* sWy = sWx + nx;
-  double* sG = sWy + ny;                                  // [nx + ny] gradient accumulators
-  double* sX = sG + nx + ny;                              // [EMB_THREADS][EMB_KC+1]
-  double* sH = sX + EMB_THREADS * (EMB_KC + 1);           // [EMB_THREADS][hmax] tanh activations
-  const int hmax = max(a.hx, a.hy);
-  const int pmax = max(a.p, gq);
-  double* sDZ = sH + EMB_THREADS * hmax;                  // [EMB_THREADS][hmax] dL/dpreact
-  double* sDF = sDZ + EMB_THREADS * hmax;                 // [EMB_THREADS][pmax] dL/dout
-
-  for (int i = tid; i < a.dx * a.hx; i += EMB_THREADS) sWx[i] = a.W1x[i];
-  for (int i = tid; i < a.hx; i += EMB_THREADS) sWx[a.dx * a.hx + i] = a.b1x[i];
-  for (int i = tid; i < a.hx * a.p; i += EMB_THREADS) sWx[a.dx * a.hx + a.hx + i] = a.W2x[i];
-  if (a.y_mode == 1) {
-    for (int i = tid; i < a.dy * a.hy; i += EMB_THREADS) sWy[i] = a.W1y[i];
-    for (int i = tid; i < a.hy; i += EMB_THREADS) sWy[a.dy * a.hy + i] = a.b1y[i];
-    for (int i = tid; i < a.hy * a.q; i += EMB_THREADS) sWy[a.dy * a.hy + a.hy + i] = a.W2y[i];
-  }
-  for (int i = tid; i < nx + ny; i += EMB_THREADS) sG[i] = 0.0;
+  typedef double T;
+  constexpr int ROWS = 32 * EmbT<T>::RM, XS = EmbT<T>::XS;
+  const EmbedArgs<T>& a = b.f;
+  const EmbSmem<T> s = emb_layout<T>(reinterpret_cast<T*>(smem_raw), a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, true);
+  load_net<T>(a.W1x, a.b1x, a.W2x, a.dx, a.hx, a.p, s.hpx, s.sW1x, s.sb1x, s.sW2x);
+  if (a.y_mode == 1) load_net<T>(a.W1y, a.b1y, a.W2y, a.dy, a.hy, a.q, s.hpy, s.sW1y, s.sb1y, s.sW2y);
+  for (int i = threadIdx.x; i < b.nparams; i += blockDim.x) s.sG[i] = 0.0;   // owner-exclusive accumulators
   __syncthreads();
+  const int n_chunks = a.chunk_first[a.T_];
+  const int gq = s.gq, dfs = s.dfs;
+  const int nets = (a.y_mode == 1) ? 2 : 1;
+  const int nthr = blockDim.x;
+  const int nx = a.dx * a.hx + a.hx + a.hx * a.p;
 
-  const long long S = a.seg_off[a.T_];
-  const long long nbatch = (S + EMB_THREADS - 1) / EMB_THREADS;
-  for (long long bt = blockIdx.x; bt < nbatch; bt += gridDim.x) {
-    const long long row0 = bt * EMB_THREADS;
-    const int nrows = (int)min((long long)EMB_THREADS, S - row0);
-    const bool live = tid < nrows;
-    // segment of this thread's sample (binary search in seg_off)
-    int seg = 0;
-    double inv_len = 0.0;
-    if (live) {
-      const long long r = row0 + tid;
-      int lo = 0, hi = a.T_;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (a.seg_off[mid] <= r) lo = mid; else hi = mid;
-      }
-      seg = lo;
-      inv_len = 1.0 / (double)(a.seg_off[seg + 1] - a.seg_off[seg]);
-    }
-    double hidx[EMB_HMAX], f[EMB_PMAX], hidy[EMB_HMAX], g[EMB_PMAX];
-    mlp_forward<double>(a.X, row0, nrows, a.dx, sWx, sWx + a.dx * a.hx, sWx + a.dx * a.hx + a.hx, a.hx, a.p, sX,
-                        hidx, f);
-    if (a.y_mode == 1) {
-      mlp_forward<double>(a.Y, row0, nrows, a.dy, sWy, sWy + a.dy * a.hy, sWy + a.dy * a.hy + a.hy, a.hy, a.q, sX,
-                          hidy, g);
-    } else if (a.y_mode == 2) {
-#pragma unroll
-      for (int j = 0; j < EMB_PMAX; ++j) g[j] = (j < a.dy && live) ? a.Y[(row0 + tid) * a.dy + j] : 0.0;
-    } else {
-      g[0] = 1.0;
-    }
-    // upstream gradients of the pooled outer product
-    double df[EMB_PMAX], dg[EMB_PMAX];
-#pragma unroll
-    for (int i = 0; i < EMB_PMAX; ++i) df[i] = dg[i] = 0.0;
-    if (live) {
-      const double* de = b.dE + (size_t)seg * a.lde;
-#pragma unroll
-      for (int i = 0; i < EMB_PMAX; ++i)
-        if (i < a.p) {
-#pragma unroll
-          for (int j = 0; j < EMB_PMAX; ++j)
-            if (j < gq) {
-              const double w = de[i * gq + j] * inv_len;
-              df[i] += w * g[j];
-              dg[j] += w * f[i];
-            }
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const int t = a.chunk_ds[c], row0 = a.chunk_row[c];
+    const int n = min(ROWS, a.seg_off[t + 1] - row0);
+    const double inv_len = 1.0 / (double)(a.seg_off[t + 1] - a.seg_off[t]);
+    chunk_features<T>(a, s, row0, n);
+    const double* de = b.dE + (size_t)t * a.lde;
+    for (int net = 0; net < nets; ++net) {
+      const int din = net ? a.dy : a.dx, h = net ? a.hy : a.hx, po = net ? a.q : a.p, hp = net ? s.hpy : s.hpx;
+      const double* sH = net ? s.sHy : s.sHx;
+      const double* sW2 = net ? s.sW2y : s.sW2x;
+      const double* Xg = (net ? a.Y : a.X) + (size_t)row0 * din;
+      double* G = s.sG + (net ? nx : 0);      // [W1 (din*h) | b1 (h) | W2 (h*po)]
+      // upstream gradient of this net's output: x side dF[r][i] = sum_j dE[t][i*gq+j] phi_y[r][j] / len,
+      //                                         y side dG[r][j] = sum_i dE[t][i*gq+j] phi_x[r][i] / len
+      for (int idx = threadIdx.x; idx < ROWS * po; idx += nthr) {
+        const int r = idx / po, i = idx - r * po;
+        double v = 0.0;
+        if (r < n) {
+          if (net == 0) {
+            for (int j = 0; j < gq; ++j) v += de[i * gq + j] * s.sFy[r * s.fsy + j];
+          } else {
+            for (int k = 0; k < a.p; ++k) v += de[k * gq + i] * s.sFx[r * s.fsx + k];
+          }
+          v *= inv_len;
         }
-    }
-    // ---- x-net: second layer gradients and dz
-    for (int net = 0; net < ((a.y_mode == 1) ? 2 : 1); ++net) {
-      const int din = net ? a.dy : a.dx, h = net ? a.hy : a.hx, po = net ? a.q : a.p;
-      const double* sW = net ? sWy : sWx;
-      const double* sW2 = sW + din * h + h;
-      double* G = sG + (net ? nx : 0);
-      const double* Xg = net ? a.Y : a.X;
-      const double* hid = net ? hidy : hidx;
-      const double* dout = net ? dg : df;
+        s.sDF[r * dfs + i] = v;
+      }
       __syncthreads();
-#pragma unroll
-      for (int j = 0; j < EMB_HMAX; ++j)
-        if (j < h) {
-          double dh = 0.0;
-#pragma unroll
-          for (int i = 0; i < EMB_PMAX; ++i)
-            if (i < po) dh += sW2[j * po + i] * dout[i];
-          const double hj = hid[j];
-          sH[tid * hmax + j] = live ? hj : 0.0;
-          sDZ[tid * hmax + j] = live ? dh * (1.0 - hj * hj) : 0.0;
+      // dz[r][j] = (sum_i W2[j][i] dF[r][i]) (1 - h^2); zero on pad rows / pad hidden units
+      for (int idx = threadIdx.x; idx < ROWS * hp; idx += nthr) {
+        const int r = idx / hp, j = idx - r * hp;
+        double v = 0.0;
+        if (j < h && r < n) {
+          for (int i = 0; i < po; ++i) v += sW2[j * po + i] * s.sDF[r * dfs + i];
+          const double hj = sH[r * hp + j];
+          v *= (1.0 - hj * hj);
         }
-#pragma unroll
-      for (int i = 0; i < EMB_PMAX; ++i)
-        if (i < po) sDF[tid * pmax + i] = live ? dout[i] : 0.0;
+        s.sDZ[r * hp + j] = v;
+      }
       __syncthreads();
-      // dW2[j][i] += sum_r H[r][j] DF[r][i] ; db1[j] += sum_r DZ[r][j]
-      for (int e = tid; e < h * po; e += EMB_THREADS) {
-        const int j = e / po, i = e % po;
-        double s = 0.0;
-        for (int r = 0; r < EMB_THREADS; ++r) s += sH[r * hmax + j] * sDF[r * pmax + i];
-        G[din * h + h + e] += s;
+      // dW2[j][i] += sum_r h[r][j] dF[r][i] ; db1[j] += sum_r dz[r][j]
+      for (int e = threadIdx.x; e < h * po; e += nthr) {
+        const int j = e / po, i = e - j * po;
+        double v = 0.0;
+        for (int r = 0; r < n; ++r) v += sH[r * hp + j] * s.sDF[r * dfs + i];
+        G[din * h + h + e] += v;
       }
-      for (int j = tid; j < h; j += EMB_THREADS) {
-        double s = 0.0;
-        for (int r = 0; r < EMB_THREADS; ++r) s += sDZ[r * hmax + j];
-        G[din * h + j] += s;
+      if ((int)threadIdx.x < h) {
+        double v = 0.0;
+        for (int r = 0; r < n; ++r) v += s.sDZ[r * hp + threadIdx.x];
+        G[din * h + threadIdx.x] += v;
       }
-      // dW1[k][j] += sum_r X[r][k] DZ[r][j], X re-staged in k-chunks
+      // dW1[k][4jg..4jg+3] += sum_r x[r][k] dz[r][4jg..]: the x tile is re-staged slice by slice; the lanes of a
+      // warp take consecutive k (conflict-free column reads), dz is a 2 x 128-bit broadcast load.
       for (int k0 = 0; k0 < din; k0 += EMB_KC) {
         const int kc = min(EMB_KC, din - k0);
         __syncthreads();
-        for (int idx = tid; idx < EMB_THREADS * kc; idx += EMB_THREADS) {
-          const int r = idx / kc, k = idx % kc;
-          sX[r * (EMB_KC + 1) + k] = (r < nrows) ? Xg[(row0 + r) * din + k0 + k] : 0.0;
-        }
+        stage_tile<T>(Xg, n, din, k0, kc, s.sX);
         __syncthreads();
-        for (int e = tid; e < kc * h; e += EMB_THREADS) {
-          const int k = e / h, j = e % h;
-          double s = 0.0;
-          for (int r = 0; r < EMB_THREADS; ++r) s += sX[r * (EMB_KC + 1) + k] * sDZ[r * hmax + j];
-          G[(size_t)(k0 + k) * h + j] += s;
+        const int items = kc * (hp / 4);
+        for (int e = threadIdx.x; e < items; e += nthr) {
+          const int jg = e / kc, k = e - jg * kc;
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int r = 0; r < n; ++r) {
+            const double x = s.sX[r * XS + k];
+            double dz[4];
+            EmbT<T>::load4(s.sDZ + r * hp + 4 * jg, dz);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) acc[cc] += x * dz[cc];
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            if (4 * jg + cc < h) G[(size_t)(k0 + k) * h + 4 * jg + cc] += acc[cc];
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
   __syncthreads();
-  for (int i = tid; i < nx + ny; i += EMB_THREADS) b.partial[(size_t)blockIdx.x * b.nparams + i] = sG[i];
+  for (int i = threadIdx.x; i < b.nparams; i += nthr) b.gpartial[(size_t)blockIdx.x * b.nparams + i] = s.sG[i];
 }
 
 __global__ void embed_bwd_reduce_kernel(const double* __restrict__ partial, int nparts, int nparams, int nx,
@@ -382,64 +445,154 @@ __global__ void embed_bwd_reduce_kernel(const double* __restrict__ partial, int 
   }
 }
 
+// ------------------------------------------------------------------ host side
+inline int net_elems(int din, int h, int po) { return din * h + h + h * po; }
+
+template <typename T>
+inline int64_t max_chunks(int64_t S, int Tn) { return S / (32 * EmbT<T>::RM) + Tn; }
+
+// workspace layout (bytes): chunk_first [T+1] | chunk_ds [mc] | chunk_row [mc] | (align 256) payload
+template <typename T>
+struct EmbWs {
+  int32_t *chunk_first, *chunk_ds, *chunk_row;
+  unsigned char* payload;
+  size_t header_bytes;
+};
+template <typename T>
+inline EmbWs<T> ws_layout(void* ws, int64_t S, int Tn) {
+  EmbWs<T> w;
+  const int64_t mc = max_chunks<T>(S, Tn);
+  w.chunk_first = (int32_t*)ws;
+  w.chunk_ds = w.chunk_first + (Tn + 1);
+  w.chunk_row = w.chunk_ds + mc;
+  size_t hb = (size_t)((Tn + 1) + 2 * mc) * sizeof(int32_t);
+  hb = (hb + 255) / 256 * 256;
+  w.header_bytes = hb;
+  w.payload = (unsigned char*)ws + hb;
+  return w;
+}
+
+template <typename T>
+static int check_args(const EmbedArgs<T>& a, int64_t S) {
+  if (!a.X || !a.seg_off || !a.W1x || !a.b1x || !a.W2x || a.T_ <= 0 || a.dx <= 0 || S <= 0) return DISTBO_EARG;
+  if (S > 0x7fffffffLL) return DISTBO_EARG;
+  if (a.hx <= 0 || a.hx > EMB_HMAX || a.p <= 0 || a.p > EMB_PMAX) return DISTBO_EARG;
+  if (a.y_mode < 0 || a.y_mode > 2) return DISTBO_EARG;
+  if (a.y_mode == 1 && (!a.Y || !a.W1y || !a.b1y || !a.W2y || a.hy <= 0 || a.hy > EMB_HMAX || a.q <= 0 ||
+                        a.q > EMB_PMAX || a.dy <= 0))
+    return DISTBO_EARG;
+  if (a.y_mode == 2 && (!a.Y || a.dy <= 0 || a.dy > EMB_PMAX)) return DISTBO_EARG;
+  if (a.lde < pout_of(a.y_mode, a.p, a.q, a.dy)) return DISTBO_EARG;
+  return DISTBO_OK;
+}
+
+inline int emb_threads(int hx, int hy, int y_mode) {
+  const int h = (y_mode == 1 && hy > hx) ? hy : hx;
+  int warps = (h + 3) / 4;
+  if (warps < 4) warps = 4;   // the generic (strided) phases still want a full CTA
+  return 32 * warps;
+}
+
+template <typename T>
+static int embed_fwd_launch(EmbedArgs<T> a, int64_t S, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  int rc = check_args(a, S);
+  if (rc) return rc;
+  if (!a.E || !workspace) return DISTBO_EARG;
+  const int pout = pout_of(a.y_mode, a.p, a.q, a.dy);
+  const int64_t mc = max_chunks<T>(S, a.T_);
+  EmbWs<T> w = ws_layout<T>(workspace, S, a.T_);
+  if ((int64_t)(w.header_bytes + (size_t)mc * pout * sizeof(T)) > workspace_bytes) return DISTBO_EARG;
+  a.chunk_first = w.chunk_first; a.chunk_ds = w.chunk_ds; a.chunk_row = w.chunk_row;
+  a.partial = (T*)w.payload;
+  const size_t smem = emb_layout<T>((T*)nullptr, a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, false).elems * sizeof(T) + 16;
+  if (smem > 220 * 1024) return DISTBO_EARG;
+  DB_CUDA(cudaFuncSetAttribute(embed_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  embed_chunk_table_kernel<<<1, 256, 0, st>>>(a.seg_off, a.T_, 32 * EmbT<T>::RM, w.chunk_first, w.chunk_ds, w.chunk_row);
+  DB_CHECK_LAUNCH();
+  // persistent CTAs: as many as are resident at once, so that the weights are staged once per CTA
+  const int threads = emb_threads(a.hx, a.hy, a.y_mode);
+  int per_sm = 1, dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, embed_fwd_kernel<T>, threads, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  const int64_t resident = (int64_t)sms * per_sm;
+  const int grid = (int)(mc < resident ? mc : resident);
+  embed_fwd_kernel<T><<<grid, threads, smem, st>>>(a);
+  DB_CHECK_LAUNCH();
+  embed_fwd_reduce_kernel<T><<<a.T_, 128, 0, st>>>(a);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
 }  // namespace db
 
 using namespace db;
 
-extern "C" int distbo_embed_fwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int dx,
-                                    int dy, const double* W1x, const double* b1x, const double* W2x, int hx,
-                                    int p, const double* W1y, const double* b1y, const double* W2y, int hy,
-                                    int q, int y_mode, double* E, int lde, void* stream) {
-  EmbedArgs<double> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, E, lde};
-  return embed_fwd_launch<double>(a, (cudaStream_t)stream);
+extern "C" int64_t distbo_embed_workspace(int64_t S, int T, int dx, int dy, int hx, int p, int hy, int q, int y_mode,
+                                          int elem_bytes, int backward) {
+  if (S <= 0 || T <= 0) return 0;
+  const int pout = pout_of(y_mode, p, q, dy);
+  if (elem_bytes == 4 && !backward) {
+    EmbWs<float> w = ws_layout<float>(nullptr, S, T);
+    return (int64_t)(w.header_bytes + (size_t)max_chunks<float>(S, T) * pout * 4);
+  }
+  EmbWs<double> w = ws_layout<double>(nullptr, S, T);
+  if (!backward) return (int64_t)(w.header_bytes + (size_t)max_chunks<double>(S, T) * pout * 8);
+  const int np = net_elems(dx, hx, p) + (y_mode == 1 ? net_elems(dy, hy, q) : 0);
+  return (int64_t)(w.header_bytes + (size_t)EMB_BWD_GRID * np * 8);
 }
 
-extern "C" int distbo_embed_fwd_f32(const float* X, const float* Y, const int32_t* seg_off, int T, int dx, int dy,
-                                    const float* W1x, const float* b1x, const float* W2x, int hx, int p,
-                                    const float* W1y, const float* b1y, const float* W2y, int hy, int q,
-                                    int y_mode, float* E, int lde, void* stream) {
-  EmbedArgs<float> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, E, lde};
-  return embed_fwd_launch<float>(a, (cudaStream_t)stream);
+extern "C" int distbo_embed_fwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S,
+                                    int dx, int dy, const double* W1x, const double* b1x, const double* W2x, int hx,
+                                    int p, const double* W1y, const double* b1y, const double* W2y, int hy, int q,
+                                    int y_mode, double* E, int lde, void* workspace, int64_t workspace_bytes,
+                                    void* stream) {
+  EmbedArgs<double> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, E, lde,
+                      nullptr, nullptr, nullptr, nullptr};
+  return embed_fwd_launch<double>(a, S, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int64_t distbo_embed_bwd_workspace(int64_t S, int dx, int dy, int hx, int p, int hy, int q) {
-  (void)S;
-  return (int64_t)EMB_BWD_GRID * (net_w_elems(dx, hx, p) + ((hy > 0 && q > 0) ? net_w_elems(dy, hy, q) : 0));
+extern "C" int distbo_embed_fwd_f32(const float* X, const float* Y, const int32_t* seg_off, int T, int64_t S, int dx,
+                                    int dy, const float* W1x, const float* b1x, const float* W2x, int hx, int p,
+                                    const float* W1y, const float* b1y, const float* W2y, int hy, int q, int y_mode,
+                                    float* E, int lde, void* workspace, int64_t workspace_bytes, void* stream) {
+  EmbedArgs<float> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, E, lde,
+                     nullptr, nullptr, nullptr, nullptr};
+  return embed_fwd_launch<float>(a, S, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int dx,
-                                    int dy, const double* W1x, const double* b1x, const double* W2x, int hx,
-                                    int p, const double* W1y, const double* b1y, const double* W2y, int hy,
-                                    int q, int y_mode, const double* dE, int lde, double* gW1x, double* gb1x,
-                                    double* gW2x, double* gW1y, double* gb1y, double* gW2y, double* workspace,
-                                    int64_t workspace_elems, void* stream) {
-  if (!X || !seg_off || !W1x || !b1x || !W2x || !dE || !gW1x || !gb1x || !gW2x || !workspace || T <= 0)
-    return DISTBO_EARG;
-  if (hx <= 0 || hx > EMB_HMAX || p <= 0 || p > EMB_PMAX || y_mode < 0 || y_mode > 2) return DISTBO_EARG;
-  if (y_mode == 1 && (!Y || !W1y || !b1y || !W2y || !gW1y || !gb1y || !gW2y || hy <= 0 || hy > EMB_HMAX ||
-                      q <= 0 || q > EMB_PMAX))
-    return DISTBO_EARG;
-  if (y_mode == 2 && (!Y || dy <= 0 || dy > EMB_PMAX)) return DISTBO_EARG;
+extern "C" int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S,
+                                    int dx, int dy, const double* W1x, const double* b1x, const double* W2x, int hx,
+                                    int p, const double* W1y, const double* b1y, const double* W2y, int hy, int q,
+                                    int y_mode, const double* dE, int lde, double* gW1x, double* gb1x, double* gW2x,
+                                    double* gW1y, double* gb1y, double* gW2y, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  EmbedArgs<double> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, nullptr, lde,
+                      nullptr, nullptr, nullptr, nullptr};
+  int rc = check_args(a, S);
+  if (rc) return rc;
+  if (!dE || !gW1x || !gb1x || !gW2x || !workspace) return DISTBO_EARG;
+  if (y_mode == 1 && (!gW1y || !gb1y || !gW2y)) return DISTBO_EARG;
   cudaStream_t st = (cudaStream_t)stream;
+  const int nx = net_elems(dx, hx, p), ny = (y_mode == 1) ? net_elems(dy, hy, q) : 0;
+  EmbWs<double> w = ws_layout<double>(workspace, S, T);
+  if ((int64_t)(w.header_bytes + (size_t)EMB_BWD_GRID * (nx + ny) * 8) > workspace_bytes) return DISTBO_EARG;
+  a.chunk_first = w.chunk_first; a.chunk_ds = w.chunk_ds; a.chunk_row = w.chunk_row;
   EmbedBwdArgs b;
-  b.f = EmbedArgs<double>{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, nullptr, lde};
+  b.f = a;
   b.dE = dE;
-  const int nx = net_w_elems(dx, hx, p), ny = (y_mode == 1) ? net_w_elems(dy, hy, q) : 0;
+  b.gpartial = (double*)w.payload;
   b.nparams = nx + ny;
-  if (workspace_elems < (int64_t)EMB_BWD_GRID * b.nparams) return DISTBO_EARG;
-  b.partial = workspace;
-  const int gq = (y_mode == 0) ? 1 : (y_mode == 1 ? q : dy);
-  const int hmax = hx > hy ? hx : hy, pmax = p > gq ? p : gq;
-  size_t elems = (size_t)2 * (nx + ny) + EMB_THREADS * (EMB_KC + 1) + (size_t)2 * EMB_THREADS * hmax +
-                 (size_t)EMB_THREADS * pmax;
-  size_t smem = elems * sizeof(double) + 16;
+  const size_t smem = emb_layout<double>((double*)nullptr, dx, dy, hx, p, hy, q, y_mode, true).elems * 8 + 16;
   if (smem > 220 * 1024) return DISTBO_EARG;
   DB_CUDA(cudaFuncSetAttribute(embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = EMB_BWD_GRID;  // grid-stride over 128-sample batches; S = seg_off[T] is read on device
-  embed_bwd_kernel<<<grid, EMB_THREADS, smem, st>>>(b);
+  embed_chunk_table_kernel<<<1, 256, 0, st>>>(seg_off, T, 32 * EmbT<double>::RM, w.chunk_first, w.chunk_ds, w.chunk_row);
   DB_CHECK_LAUNCH();
-  embed_bwd_reduce_kernel<<<(b.nparams + 255) / 256, 256, 0, st>>>(workspace, grid, b.nparams, nx, dx * hx, hx, gW1x,
-                                                                   gb1x, gW2x, dy * hy, hy, gW1y, gb1y, gW2y);
+  embed_bwd_kernel<<<EMB_BWD_GRID, emb_threads(hx, hy, y_mode), smem, st>>>(b);
+  DB_CHECK_LAUNCH();
+  embed_bwd_reduce_kernel<<<(b.nparams + 255) / 256, 256, 0, st>>>(b.gpartial, EMB_BWD_GRID, b.nparams, nx, dx * hx, hx,
+                                                                   gW1x, gb1x, gW2x, dy * hy, hy, gW1y, gb1y, gW2y);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
 }

@@ -104,6 +104,49 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[8][4][2], const doub
   __syncthreads();  // all warps done with smem: safe to reuse it / to overwrite an in-place operand
 }
 
+// Variant with the A operand (128 rows x K) RESIDENT in shared memory (row stride lda_s doubles, k-major) and
+// only B streamed global -> shared through the cp.async pipeline in smemB (STAGES * STAGE_ELEMS doubles).
+// Used by the Cholesky panel kernel, where A is an accumulator tile that never left the SM.
+// lda_s == 4 (mod 16) doubles keeps the fragment loads conflict free (two wavefronts per 32 doubles).
+template <int BLAY>
+__device__ __forceinline__ void gemm_mainloop_smemA(double (&acc)[8][4][2], const double* sAres, int lda_s,
+                                                    const double* __restrict__ B, int ldb, int n0, int k_lo,
+                                                    int k_hi, double* smemB) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int nk = (k_hi - k_lo) / BK;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) load_tile<BLAY>(smemB + s * STAGE_ELEMS, B, ldb, n0, k_lo + s * BK, tid);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int kn = kt + STAGES - 1;
+      if (kn < nk) load_tile<BLAY>(smemB + (kn & (STAGES - 1)) * STAGE_ELEMS, B, ldb, n0, k_lo + kn * BK, tid);
+      cp_async_commit();
+    }
+    const double* b = smemB + (kt & (STAGES - 1)) * STAGE_ELEMS;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi) af[mi] = sAres[(wm * 64 + mi * 8 + lr) * lda_s + kt * BK + k4 * 4 + lk];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) bf[ni] = frag_ld<BLAY>(b, wn * 32 + ni * 8 + lr, k4 * 4 + lk);
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
 struct GemmArgs {
   const double* A;
   const double* B;
@@ -111,27 +154,82 @@ struct GemmArgs {
   const double* Cin;  // may alias C; ignored when beta == 0
   int lda, ldb, ldc, ldcin;
   double alpha, beta;
-  const int4* tiles;  // (m0, n0, k_lo, k_hi)
+  const int4* tiles;  // (m0, n0, k_lo, k_hi) of 128 x 128 macro tiles
+  unsigned long long* tl = nullptr;  // debug timeline (common.cuh), normally null
+  int tl_id = 0;
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Tile-list GEMM.  Each 128 x 128 macro tile of the list is computed by TWO CTAs (128 x 64 halves); a CTA
+// has 8 warps as 4 x 2 with 32 x 32 warp tiles (64 accumulator registers per thread) and a 3-stage cp.async
+// pipeline of 90 KB, so that two CTAs are resident per SM: while one CTA is fetching its C tile, filling its
+// pipeline or storing its result, the other one keeps the DMMA pipe busy.  That hides the per-tile fixed cost,
+// which dominates the k = 128 trailing updates of the Cholesky, and keeps the hardware's dynamic CTA
+// scheduling (needed by the look-ahead: SMs become free for the high-priority panel every few microseconds).
+constexpr int TN = 64;                       // CTA tile width
+constexpr int TSTAGES = 3;
+constexpr int LDXB = TN + 4;                 // row-contiguous B tile: [16][68]
+constexpr int TSTAGE_A = BM * LDK;           // 2560 doubles (>= BK * LDX)
+constexpr int TSTAGE_B = TN * LDK;           // 1280 doubles (>= BK * LDXB = 1088)
+constexpr int TGEMM_SMEM_BYTES = TSTAGES * (TSTAGE_A + TSTAGE_B) * (int)sizeof(double);  // 92160
+
+template <int LAY>
+__device__ __forceinline__ void load_tile_b64(double* s, const double* __restrict__ g, int ld, int x0, int k0,
+                                              int tid) {
+  if (LAY == KMAJOR) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = tid + i * GEMM_THREADS;
+      const int row = c >> 3, kc = c & 7;
+      cp_async16(s + row * LDK + kc * 2, g + (size_t)(x0 + row) * ld + k0 + kc * 2);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = tid + i * GEMM_THREADS;
+      const int kr = c >> 5, xc = c & 31;
+      cp_async16(s + kr * LDXB + xc * 2, g + (size_t)(k0 + kr) * ld + x0 + xc * 2);
+    }
+  }
+}
+
+template <int LAY>
+__device__ __forceinline__ double frag_ld_b64(const double* s, int x, int k) {
+  return LAY == KMAJOR ? s[x * LDK + k] : s[k * LDXB + x];
+}
+
 template <int ALAY, int BLAY>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tiles_kernel(GemmArgs p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tiles_kernel(GemmArgs p) {
   extern __shared__ __align__(16) double smem[];
-  const int4 t = p.tiles[blockIdx.x];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
+  tl_start(p.tl, p.tl_id);
+  const int4 t = p.tiles[blockIdx.x >> 1];
+  const int m0 = t.x, n0 = t.y + TN * (blockIdx.x & 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
   const int lr = lane >> 2, lk = lane & 3;
-  // out = alpha * (acc0 + A B) with acc0 = (beta/alpha) Cin: the C tile is fetched into the
-  // accumulators BEFORE the main loop so that its latency hides behind the pipeline prologue.
-  double acc[8][4][2];
+  double* sA = smem;
+  double* sB = smem + TSTAGES * TSTAGE_A;
+  const int nk = (t.w - t.z) / BK;
+
+#pragma unroll
+  for (int s = 0; s < TSTAGES - 1; ++s) {
+    if (s < nk) {
+      load_tile<ALAY>(sA + s * TSTAGE_A, p.A, p.lda, m0, t.z + s * BK, tid);
+      load_tile_b64<BLAY>(sB + s * TSTAGE_B, p.B, p.ldb, n0, t.z + s * BK, tid);
+    }
+    cp_async_commit();
+  }
+  // out = alpha * (acc0 + A B) with acc0 = (beta / alpha) Cin: the C tile is fetched into the accumulators
+  // while the pipeline fills
+  double acc[4][4][2];
   if (p.beta != 0.0) {
     const double f = p.beta / p.alpha;
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
-      const int row = t.x + wm * 64 + mi * 8 + lr;
+    for (int mi = 0; mi < 4; ++mi) {
+      const int row = m0 + wm * 32 + mi * 8 + lr;
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const int col = t.y + wn * 32 + ni * 8 + lk * 2;
+        const int col = n0 + wn * 32 + ni * 8 + lk * 2;
         const double2 c = *reinterpret_cast<const double2*>(p.Cin + (size_t)row * p.ldcin + col);
         acc[mi][ni][0] = f * c.x;
         acc[mi][ni][1] = f * c.y;
@@ -139,25 +237,55 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tiles_kernel(GemmArgs p)
     }
   } else {
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
   }
 
-  gemm_mainloop<ALAY, BLAY>(acc, p.A, p.lda, p.B, p.ldb, t.x, t.y, t.z, t.w, smem);
-
+  int cs = 0, ps = TSTAGES - 1;
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<TSTAGES - 2>();
+    __syncthreads();
+    {
+      const int kn = kt + TSTAGES - 1;
+      if (kn < nk) {
+        load_tile<ALAY>(sA + ps * TSTAGE_A, p.A, p.lda, m0, t.z + kn * BK, tid);
+        load_tile_b64<BLAY>(sB + ps * TSTAGE_B, p.B, p.ldb, n0, t.z + kn * BK, tid);
+      }
+      cp_async_commit();
+      ps = (ps + 1 == TSTAGES) ? 0 : ps + 1;
+    }
+    const double* a = sA + cs * TSTAGE_A;
+    const double* b = sB + cs * TSTAGE_B;
+    cs = (cs + 1 == TSTAGES) ? 0 : cs + 1;
 #pragma unroll
-  for (int mi = 0; mi < 8; ++mi) {
-    const int row = t.x + wm * 64 + mi * 8 + lr;
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      double af[4], bf[4];
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-      const int col = t.y + wn * 32 + ni * 8 + lk * 2;
-      double2 v;
-      v.x = p.alpha * acc[mi][ni][0];
-      v.y = p.alpha * acc[mi][ni][1];
-      *reinterpret_cast<double2*>(p.C + (size_t)row * p.ldc + col) = v;
+      for (int mi = 0; mi < 4; ++mi) af[mi] = frag_ld<ALAY>(a, wm * 32 + mi * 8 + lr, k4 * 4 + lk);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) bf[ni] = frag_ld_b64<BLAY>(b, wn * 32 + ni * 8 + lr, k4 * 4 + lk);
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
     }
   }
+  cp_async_wait<0>();
+  // no barrier needed: the epilogue touches registers and global memory only (an in-place operand of THIS
+  // tile has been fully consumed by every warp's own loads; other CTAs never read this tile as an operand)
+  __syncthreads();
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    const int row = m0 + wm * 32 + mi * 8 + lr;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int col = n0 + wn * 32 + ni * 8 + lk * 2;
+      *reinterpret_cast<double2*>(p.C + (size_t)row * p.ldc + col) =
+          make_double2(p.alpha * acc[mi][ni][0], p.alpha * acc[mi][ni][1]);
+    }
+  }
+  tl_end(p.tl, p.tl_id);
 }
 
 template <int ALAY, int BLAY>
@@ -166,11 +294,11 @@ inline cudaError_t launch_gemm_tiles(const GemmArgs& p, int ntiles, cudaStream_t
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tiles_kernel<ALAY, BLAY>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, TGEMM_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  gemm_tiles_kernel<ALAY, BLAY><<<ntiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+  gemm_tiles_kernel<ALAY, BLAY><<<2 * ntiles, GEMM_THREADS, TGEMM_SMEM_BYTES, st>>>(p);
   ++g_db_launches;
   return cudaGetLastError();
 }

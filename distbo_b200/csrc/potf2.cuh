@@ -80,38 +80,18 @@ __device__ __forceinline__ void invert_32(const double* sA, int c0, double* dinv
   for (int k = 0; k < SB; ++k) dinv[k * DLD + lane] = w[k];  // Dinv[k][lane]
 }
 
-__global__ void __launch_bounds__(POTF2_THREADS, 1)
-potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int blk, int32_t* info
-#ifdef POTF2_TIMING
-                 , long long* dbg
-#endif
-) {
-#ifdef POTF2_TIMING
-  int dbgn = 0;
-#define PT_STAMP() do { if (threadIdx.x == 0) dbg[dbgn++] = clock64(); } while (0)
-#else
-#define PT_STAMP() do {} while (0)
-#endif
-  PT_STAMP();
-  extern __shared__ __align__(16) double s[];
+#define PT_STAMP(dbg) do { if ((dbg) && threadIdx.x == 0) *(dbg)++ = clock64(); } while (0)
+
+// Factor + invert the 128x128 block held in shared memory (sA [128][PLD], lower part valid, upper zero).
+// On return: lower sA = L; strictly upper 32-blocks (j,i) = W_ij^T; sDinv = the four diagonal inverses.
+// row_base = global row of the block's first row (for `info`).  dbg (optional) receives clock64 stamps.
+__device__ __forceinline__ void potf2_factor_invert(double* s, int row_base, int32_t* info, long long*& dbg) {
   double* sA = s;
   double* sDinv = s + PB * PLD;
   double* sS = sDinv + 4 * SB * DLD;
   double* sR = sS + 3 * SB * DLD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lr = lane >> 2, lk = lane & 3;
-  double* Ab = A + (size_t)blk * PB * ld + (size_t)blk * PB;
-  double* Wb = W + (size_t)blk * PB * ld + (size_t)blk * PB;
-
-#pragma unroll 16
-  for (int it = 0; it < PB * PB / POTF2_THREADS; ++it) {
-    const int idx = tid + it * POTF2_THREADS;
-    const int r = idx >> 7, c = idx & 127;
-    sA[r * PLD + c] = (c <= r) ? Ab[(size_t)r * ld + c] : 0.0;
-  }
-  __syncthreads();
-  PT_STAMP();
-
   for (int jb = 0; jb < 4; ++jb) {
     const int c0 = jb * SB;
     {
@@ -125,14 +105,14 @@ potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int blk
         for (int k = 0; k < SB; ++k)
           if (k <= lane) sA[(c0 + lane) * PLD + c0 + k] = a[k];
         sR[lane] = myr;
-        if (bad && lane == 0 && *info == 0) *info = blk * PB + c0 + bad;
+        if (bad && lane == 0 && *info == 0) *info = row_base + c0 + bad;
       }
     }
     __syncthreads();
-    PT_STAMP();
+    PT_STAMP(dbg);
     if (warp == 0) invert_32(sA, c0, sDinv + jb * SB * DLD, sR, lane);
     __syncthreads();
-    PT_STAMP();
+    PT_STAMP(dbg);
     const int nrg = (PB - c0 - SB) / 8;  // 8-row groups below the diagonal sub-block
     // sub-panel solve: P <- P * Dinv^T (each warp owns whole 8-row groups: in place is safe)
     for (int rg = warp; rg < nrg; rg += 8) {
@@ -155,7 +135,7 @@ potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int blk
             make_double2(acc[nt][0], acc[nt][1]);
     }
     __syncthreads();
-    PT_STAMP();
+    PT_STAMP(dbg);
     // trailing update of the lower 8x8 tiles: C -= P P^T
     const int ntile = nrg * (nrg + 1) / 2;
     for (int t = warp; t < ntile; t += 8) {
@@ -172,7 +152,7 @@ potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int blk
       *reinterpret_cast<double2*>(&sA[(r0 + lr) * PLD + q0 + 2 * lk]) = c;
     }
     __syncthreads();
-    PT_STAMP();
+    PT_STAMP(dbg);
   }
 
   // ---- inverse by block distance
@@ -209,22 +189,61 @@ potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int blk
       sA[(SB * j + c + 1) * PLD + SB * i + r] = -c1v;
     }
     __syncthreads();
-    PT_STAMP();
+    PT_STAMP(dbg);
   }
 
+}
+
+// W block (inverse, lower) from the shared-memory result to global memory.
+__device__ __forceinline__ void potf2_store_W(const double* s, double* __restrict__ Wb, int ld) {
+  const double* sA = s;
+  const double* sDinv = s + PB * PLD;
+  const int tid = threadIdx.x;
 #pragma unroll 8
   for (int it = 0; it < PB * PB / POTF2_THREADS; ++it) {
     const int idx = tid + it * POTF2_THREADS;
     const int r = idx >> 7, c = idx & 127;
     const int rb = r >> 5, cb = c >> 5;
-    double lv = 0.0, wv = 0.0;
-    if (c <= r) lv = sA[r * PLD + c];
+    double wv = 0.0;
     if (rb == cb) wv = sDinv[rb * SB * DLD + (r & 31) * DLD + (c & 31)];
     else if (rb > cb) wv = sA[c * PLD + r];
-    Ab[(size_t)r * ld + c] = lv;
     Wb[(size_t)r * ld + c] = wv;
   }
-  PT_STAMP();
+}
+
+// L block (lower, zeros above the diagonal) to global memory.
+__device__ __forceinline__ void potf2_store_L(const double* s, double* __restrict__ Ab, int ld) {
+  const double* sA = s;
+  const int tid = threadIdx.x;
+#pragma unroll 8
+  for (int it = 0; it < PB * PB / POTF2_THREADS; ++it) {
+    const int idx = tid + it * POTF2_THREADS;
+    const int r = idx >> 7, c = idx & 127;
+    Ab[(size_t)r * ld + c] = (c <= r) ? sA[r * PLD + c] : 0.0;
+  }
+}
+
+// Stand-alone form: one CTA factors and inverts diagonal block `blk` of A in place.
+__global__ void __launch_bounds__(POTF2_THREADS, 1)
+potf2_inv_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int blk, int32_t* info, long long* dbg) {
+  extern __shared__ __align__(16) double s[];
+  double* sA = s;
+  const int tid = threadIdx.x;
+  double* Ab = A + (size_t)blk * PB * ld + (size_t)blk * PB;
+  double* Wb = W + (size_t)blk * PB * ld + (size_t)blk * PB;
+  PT_STAMP(dbg);
+#pragma unroll 16
+  for (int it = 0; it < PB * PB / POTF2_THREADS; ++it) {
+    const int idx = tid + it * POTF2_THREADS;
+    const int r = idx >> 7, c = idx & 127;
+    sA[r * PLD + c] = (c <= r) ? Ab[(size_t)r * ld + c] : 0.0;
+  }
+  __syncthreads();
+  PT_STAMP(dbg);
+  potf2_factor_invert(s, blk * PB, info, dbg);
+  potf2_store_W(s, Wb, ld);
+  potf2_store_L(s, Ab, ld);
+  PT_STAMP(dbg);
 }
 
 }  // namespace db

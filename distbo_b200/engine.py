@@ -139,7 +139,7 @@ class GPEngine:
         self.best_val = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.best_idx = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._score_ws = None
-        self._emb_ws = None
+        self._emb_ws = {}
         self.E = None
         self.KE = None
         self.T = 1
@@ -184,10 +184,22 @@ class GPEngine:
         self.W_valid = False
 
     # ------------------------------------------------------------------ embedding
+    def _embed_workspace(self, S, Tn, elem_bytes, backward):
+        net = self.net
+        need = int(self.lib.distbo_embed_workspace(S, Tn, net.dx, net.dy, net.hx, net.p, net.hy, net.q, net.y_mode,
+                                                   elem_bytes, 1 if backward else 0))
+        key = "bwd" if backward else "fwd"
+        ws = self._emb_ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+            self._emb_ws[key] = ws
+        return ws
+
     def embed(self, X, Y, seg_off, out=None, n_rows=None, dtype=torch.float64):
         """K1 forward: X [S,dx], Y [S,dy] device tensors, seg_off int32 [T+1] -> E rows [T, P]."""
         net = self.net
         Tn = seg_off.numel() - 1
+        S = int(X.shape[0])
         if out is None:
             out = torch.zeros(Tn, max(self.P, net.pooled_width), dtype=dtype, device=self.dev)
         p = self.params
@@ -200,30 +212,30 @@ class GPEngine:
         w = lambda name: cast(p.view(name)) if p.has(name) else None
         wx1, bx1, wx2 = w("weights_x_1"), w("bias_x_1"), w("weights_x_2")
         wy1, by1, wy2 = w("weights_y_1"), w("bias_y_1"), w("weights_y_2")
-        rc = fn(_lib.ptr(X), _lib.ptr(Y), _lib.ptr(seg_off), Tn, net.dx, net.dy,
+        ws = self._embed_workspace(S, Tn, 8 if dtype == torch.float64 else 4, False)
+        rc = fn(_lib.ptr(X), _lib.ptr(Y), _lib.ptr(seg_off), Tn, S, net.dx, net.dy,
                 _lib.ptr(wx1), _lib.ptr(bx1), _lib.ptr(wx2), net.hx, net.p,
                 _lib.ptr(wy1), _lib.ptr(by1), _lib.ptr(wy2), net.hy, net.q,
-                net.y_mode, _lib.ptr(out), out.stride(0), _stream())
+                net.y_mode, _lib.ptr(out), out.stride(0), _lib.ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "distbo_embed_fwd")
         return out
 
     def embed_backward(self, X, Y, seg_off, dE):
         """K1 backward into the gradient slots of the net weights."""
         net, p = self.net, self.params
-        need = self.lib.distbo_embed_bwd_workspace(int(X.shape[0]), net.dx, net.dy, net.hx, net.p, net.hy, net.q)
-        if self._emb_ws is None or self._emb_ws.numel() < need:
-            self._emb_ws = self._f64(need)
+        Tn = seg_off.numel() - 1
+        S = int(X.shape[0])
+        ws = self._embed_workspace(S, Tn, 8, True)
         g = lambda name: _lib.ptr(p.gview(name)) if p.has(name) else None
         w = lambda name: _lib.ptr(p.view(name)) if p.has(name) else None
-        Tn = seg_off.numel() - 1
         rc = self.lib.distbo_embed_bwd_f64(
-            _lib.ptr(X), _lib.ptr(Y), _lib.ptr(seg_off), Tn, net.dx, net.dy,
+            _lib.ptr(X), _lib.ptr(Y), _lib.ptr(seg_off), Tn, S, net.dx, net.dy,
             w("weights_x_1"), w("bias_x_1"), w("weights_x_2"), net.hx, net.p,
             w("weights_y_1"), w("bias_y_1"), w("weights_y_2"), net.hy, net.q, net.y_mode,
             _lib.ptr(dE), dE.stride(0),
             g("weights_x_1"), g("bias_x_1"), g("weights_x_2"),
             g("weights_y_1"), g("bias_y_1"), g("weights_y_2"),
-            _lib.ptr(self._emb_ws), self._emb_ws.numel(), _stream())
+            _lib.ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "distbo_embed_bwd_f64")
 
     # ------------------------------------------------------------------ Gram and fit

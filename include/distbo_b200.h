@@ -35,6 +35,10 @@ int distbo_version(void);
  * Host-side counter, used by bench.py for its "gpu_launches" claim. */
 int64_t distbo_launch_count(int reset);
 
+/* Debug aid: device buffer (2 * n_pad/128 * 4 uint64; slot 0 of every 4 initialised to ~0, the rest to 0)
+ * that distbo_potrf_f64's kernels fill with globaltimer stamps; NULL switches it off. */
+int distbo_debug_timeline(void* buf);
+
 /* ---- K1: dataset embedding  (train/distbo_net.py:7-48, train/base.py:9-43) ----------------------
  * Fused tanh-MLP feature map phi_x (and phi_y), per-sample outer product phi_x (x) phi_y, and
  * per-dataset mean over contiguous row segments seg_off[t]..seg_off[t+1].
@@ -43,26 +47,27 @@ int64_t distbo_launch_count(int reset);
  *          1: 'joint' regression -> p*q  (index i*q+j), y-net (W1y,b1y,W2y) applied to Y
  *          2: classification     -> p*dy + dy  (outer product with one-hot Y, then class ratios)
  *   E [T, lde]: columns [0,P') written, the caller owns any extra columns (size-ratio column).
+ *   S = seg_off[T] (total rows, known to the host).  workspace: distbo_embed_workspace(...) bytes.
  * _f32 / _f64 select the arithmetic type of samples, weights and output. */
-int distbo_embed_fwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int dx, int dy,
-                         const double* W1x, const double* b1x, const double* W2x, int hx, int p,
-                         const double* W1y, const double* b1y, const double* W2y, int hy, int q,
-                         int y_mode, double* E, int lde, void* stream);
-int distbo_embed_fwd_f32(const float* X, const float* Y, const int32_t* seg_off, int T, int dx, int dy,
+int distbo_embed_fwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S, int dx,
+                         int dy, const double* W1x, const double* b1x, const double* W2x, int hx, int p,
+                         const double* W1y, const double* b1y, const double* W2y, int hy, int q, int y_mode,
+                         double* E, int lde, void* workspace, int64_t workspace_bytes, void* stream);
+int distbo_embed_fwd_f32(const float* X, const float* Y, const int32_t* seg_off, int T, int64_t S, int dx, int dy,
                          const float* W1x, const float* b1x, const float* W2x, int hx, int p,
-                         const float* W1y, const float* b1y, const float* W2y, int hy, int q,
-                         int y_mode, float* E, int lde, void* stream);
+                         const float* W1y, const float* b1y, const float* W2y, int hy, int q, int y_mode,
+                         float* E, int lde, void* workspace, int64_t workspace_bytes, void* stream);
 /* Backward of the above (replaces TF autodiff through distbo_net, train/train.py:31-40):
  * dE [T,lde] -> gradients of the net weights (same shapes as the weights; overwritten). */
-int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int dx, int dy,
-                         const double* W1x, const double* b1x, const double* W2x, int hx, int p,
-                         const double* W1y, const double* b1y, const double* W2y, int hy, int q,
-                         int y_mode, const double* dE, int lde,
-                         double* gW1x, double* gb1x, double* gW2x,
-                         double* gW1y, double* gb1y, double* gW2y,
-                         double* workspace, int64_t workspace_elems, void* stream);
-/* workspace size (in doubles) distbo_embed_bwd_f64 needs for S samples */
-int64_t distbo_embed_bwd_workspace(int64_t S, int dx, int dy, int hx, int p, int hy, int q);
+int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S, int dx,
+                         int dy, const double* W1x, const double* b1x, const double* W2x, int hx, int p,
+                         const double* W1y, const double* b1y, const double* W2y, int hy, int q, int y_mode,
+                         const double* dE, int lde, double* gW1x, double* gb1x, double* gW2x, double* gW1y,
+                         double* gb1y, double* gW2y, void* workspace, int64_t workspace_bytes, void* stream);
+/* Bytes of device workspace the calls above need for S = seg_off[T] total rows (chunk table + per-chunk
+ * partial sums; elem_bytes 4 or 8; backward != 0 for distbo_embed_bwd_f64). */
+int64_t distbo_embed_workspace(int64_t S, int T, int dx, int dy, int hx, int p, int hy, int q, int y_mode,
+                               int elem_bytes, int backward);
 
 /* ---- K2: Matern-3/2 product Gram  (train/kernels.py:19-28,58-88; log_gaus_likelihood.py:86-122) --
  * Task-level Gram KE[t,t'] = matern32(E[t]/exp(log_bw_embed), E[t']/exp(log_bw_embed)), [T,T]. */

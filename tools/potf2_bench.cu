@@ -1,5 +1,4 @@
 // Micro-benchmark: per-phase clock64 stamps of potf2_inv_kernel on one 128x128 SPD block.
-#define POTF2_TIMING
 #include <cstdio>
 #include <vector>
 #include <cmath>
