@@ -56,6 +56,8 @@ class gp_regressor(object):
         self.loss_history = []
         self._fit_generation = 0
         self._predict_generation = -1
+        self._pred_sets = None
+        self._target_dev = None
         if target_X is not None:
             self.data_sizes_target = check_dims([len(target_X)])
             self.target_embed_ind = target_embed_ind
@@ -156,8 +158,8 @@ class gp_regressor(object):
             # rows the embeddings are computed from at prediction time (gp_regressor.py:95-102)
             if source_embed_ind is None:
                 source_embed_ind = [np.arange(len(x)) for x in data_X]
-            self.source_X = [np.asarray(x)[list(ind)] for x, ind in zip(data_X, source_embed_ind)]
-            self.source_Y = [yy[list(ind)] for yy, ind in zip(data_Y, source_embed_ind)]
+            self._source_embed_ind = source_embed_ind
+            self._pred_sets = None
             sampler = EmbedBatchSampler(data_Y, batch_size, check_random_state(self.seed), self.model_type,
                                         stratify, shuffle_seed=self.shuffle_seed)
             self._full = self._stack(data_X, data_Y)          # all rows of every dataset, HBM resident
@@ -282,14 +284,39 @@ class gp_regressor(object):
         nothing to build, the factorisation for prediction is prepared lazily in predict_y."""
         return None
 
-    def _embed_sets(self, X_list, Y_list, n_rows_E):
-        """Embeddings of whole sample sets (fp32 rows when float64=False)."""
+    def _prediction_sets(self):
+        """Device-resident rows the embeddings are computed from at prediction time: the `embed_ind`
+        subsample of every source dataset followed by the target's (gp_regressor.py:95-102,163-172).
+        Built once per fit call and cached: the source rows are gathered ON THE DEVICE from the already
+        resident training rows (no second upload); the target set is uploaded once."""
+        if self._pred_sets is not None:
+            return self._pred_sets
         e = self.engine
         dt = torch.float64 if self.float64 else torch.float32
-        X, Y, off = self._stack(X_list, Y_list, dt)
-        out = torch.zeros(len(X_list), e.P, dtype=dt, device=e.dev)
-        e.embed(X, Y, off, out=out, dtype=dt)
-        return out.double()
+        full_off = self._full_off
+        sizes, rows, identity = [], [], True
+        for i, ind in enumerate(self._source_embed_ind):
+            ind = np.asarray(list(ind), dtype=np.int64)
+            n_i = int(full_off[i + 1] - full_off[i])
+            identity = identity and len(ind) == n_i and np.array_equal(ind, np.arange(n_i))
+            rows.append(full_off[i] + ind)
+            sizes.append(len(ind))
+        if identity:
+            sX, sY = self._full[0], self._full[1]
+        else:
+            gather = torch.from_numpy(np.concatenate(rows)).to(e.dev)
+            sX, sY = self._full[0].index_select(0, gather), self._full[1].index_select(0, gather)
+        if self._target_dev is None:
+            tind = list(self.target_embed_ind)
+            tX = np.asarray(self.target_X, dtype=np.float64)[tind]
+            tY = check_dims(np.asarray(self.target_Y, dtype=np.float64))[tind]
+            self._target_dev = (self._dev(tX), self._dev(tY))
+        X = torch.cat([sX, self._target_dev[0]], 0).to(dt)
+        Y = torch.cat([sY, self._target_dev[1]], 0).to(dt)
+        sizes.append(int(self._target_dev[0].shape[0]))
+        off = torch.from_numpy(np.r_[0, np.cumsum(sizes)].astype(np.int32)).to(e.dev)
+        self._pred_sets = (X, Y, off)
+        return self._pred_sets
 
     def _prepare_predict(self):
         """Posterior state at the CURRENT parameters: embeddings of the full sample sets, task Gram over
@@ -301,9 +328,10 @@ class gp_regressor(object):
         T = e.T
         KE = None
         if self.kernel == "dist":
-            tX = np.asarray(self.target_X)[list(self.target_embed_ind)]
-            tY = check_dims(np.asarray(self.target_Y))[list(self.target_embed_ind)]
-            E_all = self._embed_sets(self.source_X + [tX], self.source_Y + [tY], T + 1)
+            X, Y, off = self._prediction_sets()
+            E_all = torch.zeros(T + 1, e.P, dtype=X.dtype, device=e.dev)
+            e.embed(X, Y, off, out=E_all, dtype=X.dtype)
+            E_all = E_all.double()
             if self.concat_data_size:
                 E_all[:T, e.P - 1] = self._ratio
                 E_all[T, e.P - 1] = float(self.data_sizes_target[0, 0]) / float(self._max_size)
