@@ -58,6 +58,49 @@ __device__ __forceinline__ int factor_32(double (&a)[SB], double& myr, int lane)
   return bad;
 }
 
+// Variant used by default: warp 0 alone factors the block (lane = row).  Column j is exchanged through a
+// double-buffered 32-entry shared-memory line (one store + broadcast 128-bit loads) instead of 62 shuffle
+// instructions, there is no per-entry select (entries above the diagonal hold junk that is never read), and
+// the only dependent chain per column is  pivot -> 1/d (float seed + two Newton steps) -> t = a_j / d ->
+// fma into the next pivot;  sqrt / rsqrt for the stored column run off that chain.
+//   update:  a[k] -= (a[j] / d) * c_k,  c_k = unscaled column entry of row k  (= L_ij L_kj)
+__device__ __forceinline__ double rcp_nr(double d) {
+  double x = (double)__frcp_rn((float)d);
+  x = fma(x, fma(-d, x, 1.0), x);
+  x = fma(x, fma(-d, x, 1.0), x);
+  return x;
+}
+
+__device__ __forceinline__ int factor_32_smem(double (&a)[SB], double& myr, int lane, double* sCol /*[2][SB]*/) {
+  int bad = 0;
+  myr = 0.0;
+#pragma unroll
+  for (int j = 0; j < SB; ++j) {
+    double* line = sCol + (j & 1) * SB;
+    line[lane] = a[j];
+    __syncwarp();
+    const double d = line[j];
+    bad = (!(d > 0.0) && bad == 0) ? j + 1 : bad;
+    const double t = a[j] * rcp_nr(d);
+#pragma unroll
+    for (int k2 = 0; k2 < SB; k2 += 2) {
+      if (k2 + 1 > j) {  // folds at compile time after full unrolling
+        const double2 c = *reinterpret_cast<const double2*>(line + k2);
+        if (k2 > j) a[k2] = fma(-t, c.x, a[k2]);
+        a[k2 + 1] = fma(-t, c.y, a[k2 + 1]);
+      }
+    }
+    // off the critical chain: the stored column L[.][j] = a[j] / sqrt(d), L[j][j] = sqrt(d)
+    double y = rsqrt_nr(d);
+    double sq = d * y;
+    sq = fma(0.5 * y, fma(-sq, sq, d), sq);
+    y = fma(y, fma(-sq, y, 1.0), y);
+    a[j] = (lane == j) ? sq : a[j] * y;
+    myr = (lane == j) ? y : myr;
+  }
+  return bad;
+}
+
 // Inverse of the 32x32 lower-triangular block just stored at sA[c0.., c0..]: lane j owns column j of
 // Dinv; L[i][k] and 1/L[i][i] come from shared memory as broadcast loads (no shuffles: may run under a
 // warp-id guard).  dinv is row-major [32][DLD] with explicit zeros above the diagonal.
@@ -99,8 +142,13 @@ __device__ __forceinline__ void potf2_factor_invert(double* s, int row_base, int
 #pragma unroll
       for (int k = 0; k < SB; ++k) a[k] = sA[(c0 + lane) * PLD + c0 + k];
       __syncthreads();  // every warp has read the block before warp 0 overwrites it
+#ifdef DB_FACTOR_SHUFFLE
       const int bad = factor_32(a, myr, lane);
       if (warp == 0) {
+#else
+      if (warp == 0) {
+        const int bad = factor_32_smem(a, myr, lane, sS);
+#endif
 #pragma unroll
         for (int k = 0; k < SB; ++k)
           if (k <= lane) sA[(c0 + lane) * PLD + c0 + k] = a[k];
