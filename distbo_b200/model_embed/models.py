@@ -51,6 +51,12 @@ _BOUNDS = {
 }
 
 
+def register_model(name, fn, model_type, bounds, init_cols=None):
+    """Adds a user objective `fn(data, **params)` under `name`: bounds = {param: (lo, hi)}; init_cols = order
+    of the parameter columns in previous-evaluation arrays (default: sorted names, as bayes_opt_wrap returns)."""
+    _BOUNDS[name] = (fn, model_type, dict(bounds), list(init_cols) if init_cols else sorted(bounds))
+
+
 def set_model(model, data, init):
     """-> (objective(**params), bounds dict, previous evaluations dict or None, model_type).
     `init` rows are [params sorted by name..., value] (models.py:18-104)."""
