@@ -30,7 +30,21 @@ struct TriNode {
 struct Plan {
   int n = 0, nb = 0;
   int4* d_tiles = nullptr;
-  std::vector<Range> syrk_rest, tri1, tri2;   // trailing update (columns >= kb+2), TRTRI levels
+  std::vector<Range> tri1, tri2;   // TRTRI levels
+  // POTRF schedule.  A trailing update ("rest") applies the panels [p_lo, p_hi) to every tile (i, j) with
+  // j >= col_lo; it is issued after panel p_hi-1 and must be complete before the first panel whose column
+  // it touches.  Early on a rest covers TWO panels (k = 256: twice the arithmetic intensity of the rank-128
+  // update, which is what the trailing GEMM is short of while the matrix is large); once the panel chain is
+  // the longer of the two it covers one.  pend_lo[kb] = first panel the panel kernel still has to apply to
+  // column kb itself (its update step runs over k in [pend_lo*128, kb*128)).
+  struct Rest {
+    Range tiles;
+    int p_lo, p_hi, col_lo;
+  };
+  std::vector<Rest> rests;
+  std::vector<int> rest_after;   // [nb] index of the rest issued after panel kb, or -1
+  std::vector<int> wait_rest;    // [nb] index of the rest panel kb must wait for, or -1
+  std::vector<int> pend_lo;      // [nb]
   Range lauum{0, 0};
   cudaStream_t panel_stream = nullptr;
   std::vector<cudaEvent_t> ev_panel, ev_first;
@@ -42,8 +56,8 @@ struct Plan {
 
 // ------------------------------------------------------------------ fused panel kernel
 // One launch per column block kb, CTA c -> row block i = kb + c:
-//   1. acc = A[i,kb] - L[i,kb-1] L[kb,kb-1]^T        (the update of column kb by the previous panel;
-//                                                    older panels were applied by the trailing kernels)
+//   1. acc = A[i,kb] - L[i, pend..kb) L[kb, pend..kb)^T   (the updates of column kb still pending: the last one
+//                                                    to three panels; older ones came from the trailing kernels)
 //   2. c == 0: the diagonal tile goes to shared memory, is factorised and inverted there (potf2.cuh);
 //              inv(L_kk) is written to W and published through flags[kb]; then L_kk is written to A.
 //      c  > 0: the accumulator tile stays in shared memory as the A operand, the CTA waits for the flag
@@ -54,6 +68,7 @@ struct PanelArgs {
   double* A;
   double* W;
   int ld, kb, nb;
+  int pend_lo;   // first panel whose update of column kb is still pending (applied by this kernel)
   int32_t* info;
   int* flags;
   unsigned long long* tl;   // debug timeline, normally null
@@ -88,7 +103,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
         acc[mi][ni][1] = -c.y;
       }
     }
-    if (kb > 0) gemm_mainloop<KMAJOR, KMAJOR>(acc, p.A, ld, p.A, ld, m0, n0, n0 - BN, n0, smem);
+    if (p.pend_lo < kb) gemm_mainloop<KMAJOR, KMAJOR>(acc, p.A, ld, p.A, ld, m0, n0, p.pend_lo * BN, n0, smem);
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
       const int r = wm * 64 + mi * 8 + lr;
@@ -208,12 +223,42 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
   const int nb = p->nb;
   std::vector<int4> tiles;
   auto T = [](int i) { return i * 128; };
-  for (int kb = 0; kb < nb; ++kb) {
-    Range r{(int)tiles.size(), 0};
-    for (int i = kb + 2; i < nb; ++i)
-      for (int j = kb + 2; j <= i; ++j) tiles.push_back(make_int4(T(i), T(j), T(kb), T(kb + 1)));
-    r.cnt = (int)tiles.size() - r.off;
-    p->syrk_rest.push_back(r);
+  {
+    // number of double-depth steps (env DISTBO_POTRF_DOUBLE).  Measured on B200 at N = 8192 (profiles/
+    // r01_potrf_schedule.txt): the k = 256 update is only ~14 % faster per flop than two k = 128 ones while the
+    // panels next to it get slower (longer pending updates), so the default is 0 = single depth throughout.
+    int js = 0;
+    const char* env = getenv("DISTBO_POTRF_DOUBLE");
+    if (env) js = atoi(env);
+    if (js < 0) js = 0;
+    if (2 * js + 2 > nb) js = (nb - 2) / 2 > 0 ? (nb - 2) / 2 : 0;
+    p->rest_after.assign(nb, -1);
+    p->wait_rest.assign(nb, -1);
+    p->pend_lo.assign(nb, 0);
+    auto add_rest = [&](int p_lo, int p_hi, int col_lo) {
+      Plan::Rest r;
+      r.p_lo = p_lo; r.p_hi = p_hi; r.col_lo = col_lo;
+      r.tiles.off = (int)tiles.size();
+      for (int i = col_lo; i < nb; ++i)
+        for (int j = col_lo; j <= i; ++j) tiles.push_back(make_int4(T(i), T(j), T(p_lo), T(p_hi)));
+      r.tiles.cnt = (int)tiles.size() - r.tiles.off;
+      if (r.tiles.cnt == 0) return;
+      p->rest_after[p_hi - 1] = (int)p->rests.size();
+      p->rests.push_back(r);
+    };
+    for (int J = 0; J < js; ++J) add_rest(2 * J, 2 * J + 2, 2 * J + 4);
+    for (int kb = 2 * js; kb < nb; ++kb) add_rest(kb, kb + 1, kb + 2);
+    // per column: which panels are already applied by rests, and the last rest touching it
+    for (int c = 0; c < nb; ++c) {
+      int applied = 0, last = -1;
+      for (size_t q = 0; q < p->rests.size(); ++q)
+        if (p->rests[q].col_lo <= c && p->rests[q].p_hi <= c) {
+          applied = p->rests[q].p_hi;   // rests are contiguous in panel order
+          last = (int)q;
+        }
+      p->pend_lo[c] = applied;
+      p->wait_rest[c] = last;
+    }
   }
   std::vector<std::vector<TriNode>> levels;
   build_tri(0, nb, levels);
@@ -257,11 +302,9 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
     return DISTBO_ECUDA;
   }
   p->ev_panel.resize(nb);
-  p->ev_first.resize(nb);
-  for (int i = 0; i < nb; ++i) {
-    cudaEventCreateWithFlags(&p->ev_panel[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&p->ev_first[i], cudaEventDisableTiming);
-  }
+  p->ev_first.resize(p->rests.size());   // "rest q is complete"
+  for (int i = 0; i < nb; ++i) cudaEventCreateWithFlags(&p->ev_panel[i], cudaEventDisableTiming);
+  for (size_t i = 0; i < p->ev_first.size(); ++i) cudaEventCreateWithFlags(&p->ev_first[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&p->ev_begin, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&p->ev_end, cudaEventDisableTiming);
   const char* la = getenv("DISTBO_LOOKAHEAD");
@@ -315,24 +358,27 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
       DB_CUDA(cudaEventRecord(p->ev_begin, U));
       DB_CUDA(cudaStreamWaitEvent(P, p->ev_begin, 0));
     }
+    int running_rest_tiles = 0;   // tiles of the trailing update that runs next to the panel being launched
     for (int kb = 0; kb < nb; ++kb) {
-      // column kb must have received the trailing update of panel kb-2 (ev_first doubles as "rest done")
-      if (fork && kb >= 2 && p->syrk_rest[kb - 2].cnt) DB_CUDA(cudaStreamWaitEvent(P, p->ev_first[kb - 2], 0));
-      PanelArgs pa{A, W, n, kb, nb, info, p->d_flags, g_timeline};
-      rest.tl = g_timeline;
-      rest.tl_id = 2 * kb + 1;
-      // panel(kb) runs next to the trailing update of panel kb-1; panel(kb+1) next to this rest(kb)
-      const int g_this = fork ? panel_ctas(nb, kb, p->sms, kb >= 1 ? p->syrk_rest[kb - 1].cnt : 0) : nb - kb;
+      // column kb must have received every trailing update that touches it
+      if (fork && p->wait_rest[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_first[p->wait_rest[kb]], 0));
+      PanelArgs pa{A, W, n, kb, nb, p->pend_lo[kb], info, p->d_flags, g_timeline};
+      const int g_this = fork ? panel_ctas(nb, kb, p->sms, running_rest_tiles) : nb - kb;
       panel_kernel<<<g_this, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
       DB_CHECK_LAUNCH();
-      if (p->syrk_rest[kb].cnt) {
+      const int q = p->rest_after[kb];
+      if (q >= 0) {
+        const Plan::Rest& r = p->rests[q];
         if (fork) {
           DB_CUDA(cudaEventRecord(p->ev_panel[kb], P));
           DB_CUDA(cudaStreamWaitEvent(U, p->ev_panel[kb], 0));
         }
-        rest.tiles = p->d_tiles + p->syrk_rest[kb].off;
-        DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(rest, p->syrk_rest[kb].cnt, U)));
-        if (fork) DB_CUDA(cudaEventRecord(p->ev_first[kb], U));
+        rest.tiles = p->d_tiles + r.tiles.off;
+        rest.tl = g_timeline;
+        rest.tl_id = 2 * kb + 1;
+        DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(rest, r.tiles.cnt, U)));
+        if (fork) DB_CUDA(cudaEventRecord(p->ev_first[q], U));
+        running_rest_tiles = r.tiles.cnt * (r.p_hi - r.p_lo);
       }
     }
     if (fork) {
