@@ -149,14 +149,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) out[mi][ni][0] = out[mi][ni][1] = 0.0;
     // out[m][n] = sum_k tile[m][k] * Winv[n][k]   (B = inv(L_kk), k-major, read through L2 with cp.async.cg)
+    // inv(L_kk) is lower triangular: column group wn needs k < 32 (wn + 1).  Warps 0-3 take column groups
+    // 0..3 and warps 4-7 take 3..0, so each SM sub-partition (warp & 3) owns 2 + 8, 4 + 6, ... = 10 k-steps.
     const double* Wd = p.W + (size_t)n0 * ld + n0;
-    gemm_mainloop_smemA<KMAJOR>(out, sT, PLD, Wd, ld, 0, 0, BN, smem + PB * PLD);
+    const int swn = (wm == 0) ? wn : 3 - wn;
+    gemm_mainloop_smemA<KMAJOR>(out, sT, PLD, Wd, ld, 0, 0, BN, smem + PB * PLD, wm, swn, true);
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
       const int r = wm * 64 + mi * 8 + lr;
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const int c = wn * 32 + ni * 8 + lk * 2;
+        const int c = swn * 32 + ni * 8 + lk * 2;
         *reinterpret_cast<double2*>(Ab + (size_t)r * ld + c) = make_double2(out[mi][ni][0], out[mi][ni][1]);
       }
     }

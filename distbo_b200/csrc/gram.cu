@@ -84,23 +84,20 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ th
   __syncthreads();
   const double scale = exp(*log_scale);
   const double diag_add = exp(2.0 * (*log_sigma)) + jitter;
-  const int cg = (tid & 31) * 4;  // 4 consecutive columns per thread: a warp writes one 1 KB row
-  const int w = tid >> 5;
+  const int lane = tid & 31;  // columns lane, lane+32, lane+64, lane+96: conflict-free shared reads, and a warp
+  const int w = tid >> 5;     // stores four 256-byte row segments
   for (int r = w; r < GT; r += 8) {
     const int gi = bi * GT + r;
     double dot[4] = {0.0, 0.0, 0.0, 0.0};
     for (int k = 0; k < d; ++k) {
       const double xi = sI[r * d + k];
-      const double4 yj = *reinterpret_cast<const double4*>(sJt + k * GT + cg);
-      dot[0] += xi * yj.x;
-      dot[1] += xi * yj.y;
-      dot[2] += xi * yj.z;
-      dot[3] += xi * yj.w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dot[q] += xi * sJt[k * GT + lane + 32 * q];
     }
-    double out[4];
+    double* dst = K + (size_t)gi * n_pad + bj * GT;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int c = cg + q, gj = bj * GT + c;
+      const int c = lane + 32 * q, gj = bj * GT + c;
       double v;
       if (gi < N && gj < N) {
         const double d2 = -2.0 * dot[q] + sqI[r] + sqJ[c];
@@ -110,11 +107,8 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ th
       } else {
         v = (gi == gj) ? 1.0 : 0.0;
       }
-      out[q] = v;
+      dst[c] = v;
     }
-    double* dst = K + (size_t)gi * n_pad + bj * GT + cg;
-    *reinterpret_cast<double2*>(dst) = make_double2(out[0], out[1]);
-    *reinterpret_cast<double2*>(dst + 2) = make_double2(out[2], out[3]);
   }
 }
 
@@ -125,59 +119,110 @@ __global__ void __launch_bounds__(256) gram_kernel(const double* __restrict__ th
 //   rowbw[n_pad][d]   : sum_j w g_ij scale KE_ij 3 exp(-v) delta_k^2
 //   rowsc[n_pad][3]   : {alpha_i, Kinv_ii, alpha_i^2}
 template <int D>
-__global__ void __launch_bounds__(256) gram_grad_rows_kernel(
+__global__ void __launch_bounds__(256, 2) gram_grad_rows_kernel(
     const double* __restrict__ Kinv, const double* __restrict__ alpha, const double* __restrict__ theta_s,
     const double* __restrict__ sqnorm, int N, int n_pad, int d, const int32_t* __restrict__ task_id,
     const int32_t* __restrict__ task_off, const double* __restrict__ KE, int T,
     const double* __restrict__ log_scale, double* __restrict__ rowH, double* __restrict__ rowbw,
     double* __restrict__ rowsc) {
-  const int wglobal = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (wglobal >= N) return;
-  const int i = N - 1 - wglobal;
+  // CTA = 8 consecutive rows (one per warp, longest rows first); the columns are walked in chunks of 128 whose
+  // theta rows are staged TRANSPOSED in shared memory once per CTA (conflict-free reads, no strided global
+  // loads); lane = columns lane, lane+32, lane+64, lane+96 of the chunk.  rowH must be zero on entry.
+  __shared__ double sJt[D][128];
+  __shared__ double sSq[128], sAl[128];
+  __shared__ int sTj[128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i_hi = N - 1 - (int)blockIdx.x * 8;
+  const int i = i_hi - warp;
+  const bool row_ok = i >= 0;
   const double scale = exp(*log_scale);
-  const int ti = task_id ? task_id[i] : 0;
-  const double ai = alpha[i], sqi = sqnorm[i];
-  double xi[D];
+  const int ti = (row_ok && task_id) ? task_id[i] : 0;
+  const double ai = row_ok ? alpha[i] : 0.0, sqi = row_ok ? sqnorm[i] : 0.0;
+  double xi[D], gbw[D];
 #pragma unroll
-  for (int k = 0; k < D; ++k) xi[k] = (k < d) ? theta_s[(size_t)i * d + k] : 0.0;
-  double gbw[D];
-#pragma unroll
-  for (int k = 0; k < D; ++k) gbw[k] = 0.0;
-  const double* krow = Kinv + (size_t)i * n_pad;
+  for (int k = 0; k < D; ++k) {
+    xi[k] = (row_ok && k < d) ? theta_s[(size_t)i * d + k] : 0.0;
+    gbw[k] = 0.0;
+  }
+  const double* krow = Kinv + (size_t)(row_ok ? i : 0) * n_pad;
+  int tcur = -1;      // lane 0: running (task, partial sum) of rowH[i][.]
+  double hcur = 0.0;
 
-  for (int tp = 0; tp < T; ++tp) {
-    double h = 0.0;
-    if (tp <= ti) {
-      const int j0 = task_off ? task_off[tp] : 0;
-      const int j1 = min(task_off ? task_off[tp + 1] : N, i + 1);
-      const double ke = KE ? KE[(size_t)ti * T + tp] : 1.0;
-      for (int j = j0 + lane; j < j1; j += 32) {
-        double g = krow[j] - ai * alpha[j];
-        if (j == i) g *= 0.5;
-        double dot = 0.0;
-        double dl[D];
+  // Kinv row values of the next chunk are fetched one chunk ahead (they stream from HBM exactly once)
+  double kq[4];
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-          const double xj = (k < d) ? theta_s[(size_t)j * d + k] : 0.0;
-          dot += xi[k] * xj;
-          dl[k] = xi[k] - xj;
-        }
-        const double d2 = -2.0 * dot + sqi + sqnorm[j];
-        const double r = sqrt(fmax(d2, kDistClamp));
-        const double v = kSqrt3 * r;
-        const double e = exp(-v);
-        h += g * (scale * ((1.0 + v) * e));
-        if (d2 > kDistClamp) {  // tf.maximum routes the gradient to the constant when clamped
-          const double f = g * scale * ke * 3.0 * e;
+  for (int u = 0; u < 4; ++u) kq[u] = (row_ok && lane + 32 * u <= i) ? krow[lane + 32 * u] : 0.0;
+  for (int jb = 0; jb <= i_hi; jb += 128) {
+    double kv[4];
 #pragma unroll
-          for (int k = 0; k < D; ++k) gbw[k] += f * dl[k] * dl[k];
+    for (int u = 0; u < 4; ++u) {
+      kv[u] = kq[u];
+      const int jn = jb + 128 + lane + 32 * u;
+      kq[u] = (row_ok && jn <= i) ? krow[jn] : 0.0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 128 * d; idx += 256) {
+      const int r = idx / d, k = idx - r * d;
+      sJt[k][r] = (jb + r < N) ? theta_s[(size_t)(jb + r) * d + k] : 0.0;
+    }
+    if (threadIdx.x < 128) {
+      const int j = jb + threadIdx.x;
+      sSq[threadIdx.x] = (j < N) ? sqnorm[j] : 0.0;
+      sAl[threadIdx.x] = (j < N) ? alpha[j] : 0.0;
+      sTj[threadIdx.x] = (j < N && task_id) ? task_id[j] : 0;
+    }
+    __syncthreads();
+    if (!row_ok || jb > i) continue;
+    double hc[4], f[4];
+    int tj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = lane + 32 * u, j = jb + c;
+      const bool live = j <= i;
+      double g = live ? kv[u] - ai * sAl[c] : 0.0;
+      if (j == i) g *= 0.5;
+      double dot = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) dot += xi[k] * sJt[k][c];
+      const double d2 = -2.0 * dot + sqi + sSq[c];
+      const double r = sqrt(fmax(d2, kDistClamp));
+      const double v = kSqrt3 * r;
+      const double e = exp(-v);
+      tj[u] = sTj[c];
+      const double gs = g * scale;
+      hc[u] = gs * ((1.0 + v) * e);
+      const double ke = (KE && live) ? KE[(size_t)ti * T + tj[u]] : 1.0;
+      // tf.maximum routes the gradient to the constant when the distance is clamped
+      f[u] = (d2 > kDistClamp) ? gs * ke * 3.0 * e : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double t = xi[k] - sJt[k][lane + 32 * u];
+        gbw[k] += f[u] * t * t;
+      }
+    }
+    // block sums by the columns' task (tasks are contiguous column ranges): one masked warp sum per task
+    const int t_lo = sTj[0], t_hi = sTj[min(127, i - jb)];
+    for (int tp = t_lo; tp <= t_hi; ++tp) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sacc += (tj[u] == tp) ? hc[u] : 0.0;
+      sacc = warp_sum(sacc);
+      if (lane == 0) {
+        if (tp == tcur) {
+          hcur += sacc;
+        } else {
+          if (tcur >= 0) rowH[(size_t)i * T + tcur] = hcur;
+          tcur = tp;
+          hcur = sacc;
         }
       }
-      h = warp_sum(h);
     }
-    if (lane == 0) rowH[(size_t)i * T + tp] = h;
   }
+  if (!row_ok) return;
+  if (lane == 0 && tcur >= 0) rowH[(size_t)i * T + tcur] = hcur;
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     const double s = warp_sum(gbw[k]);
@@ -414,6 +459,7 @@ extern "C" int distbo_gram_grad_f64(const double* Kinv, const double* alpha, con
   double* Hsym = rowsc + (size_t)n_pad * 3;          // [T*T] (fits: workspace has n_pad*(T+d+4))
   if ((size_t)T * T > (size_t)n_pad) return DISTBO_EARG;
   const int grid = (N + 7) / 8;
+  DB_CUDA(cudaMemsetAsync(rowH, 0, (size_t)n_pad * T * sizeof(double), st));   // rows only write the tasks they meet
   if (d <= 4)
     gram_grad_rows_kernel<4><<<grid, 256, 0, st>>>(Kinv, alpha, theta_s, sqnorm, N, n_pad, d, task_id, task_off, KE,
                                                    T, log_scale, rowH, rowbw, rowsc);
