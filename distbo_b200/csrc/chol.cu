@@ -171,15 +171,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
 // Number of CTAs of the panel kernel for column block kb: as few as keep the panel (update -> potf2 ->
 // solve chain over its row blocks) shorter than the concurrent trailing update, which then gets the
 // remaining SMs; all row blocks in parallel once the trailing update is the shorter of the two.
-static int panel_ctas(int nb, int kb, int sms, int rest_tiles_prev) {
+static int panel_ctas(int nb, int kb, int sms, int rest_tiles_prev, int depth, int share) {
+  // depth = pending panels the kernel applies itself; share = panels that run next to the same trailing update
   const int rows = nb - kb;            // row blocks incl. the diagonal
   if (rows <= 2) return rows;
-  const double t_tile = 21.0, t_upd = 23.0, t_potf2 = 60.0, t_solve = 22.0;   // microseconds, measured
+  const double t_tile = 21.0, t_upd = 6.0 + 17.0 * depth, t_potf2 = 52.0, t_solve = 18.0;   // microseconds, measured
   for (int G = 2; G < rows; ++G) {
     const int per = (rows - 1 + G - 2) / (G - 1);
     const double panel = t_upd + t_potf2 + t_solve + (per - 1) * (t_upd + t_solve);
     const double rest = rest_tiles_prev * t_tile / (double)(sms - G);
-    if (panel <= 0.85 * rest) return G;
+    if (panel * share <= 0.85 * rest) return G;
   }
   return rows;
 }
@@ -362,11 +363,12 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
       DB_CUDA(cudaStreamWaitEvent(P, p->ev_begin, 0));
     }
     int running_rest_tiles = 0;   // tiles of the trailing update that runs next to the panel being launched
+    int running_share = 1;        // panels that run next to that same update
     for (int kb = 0; kb < nb; ++kb) {
       // column kb must have received every trailing update that touches it
       if (fork && p->wait_rest[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_first[p->wait_rest[kb]], 0));
       PanelArgs pa{A, W, n, kb, nb, p->pend_lo[kb], info, p->d_flags, g_timeline};
-      const int g_this = fork ? panel_ctas(nb, kb, p->sms, running_rest_tiles) : nb - kb;
+      const int g_this = fork ? panel_ctas(nb, kb, p->sms, running_rest_tiles, kb - p->pend_lo[kb], running_share) : nb - kb;
       panel_kernel<<<g_this, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
       DB_CHECK_LAUNCH();
       const int q = p->rest_after[kb];
@@ -382,6 +384,7 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
         DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(rest, r.tiles.cnt, U)));
         if (fork) DB_CUDA(cudaEventRecord(p->ev_first[q], U));
         running_rest_tiles = r.tiles.cnt * (r.p_hi - r.p_lo);
+        running_share = r.p_hi - r.p_lo;
       }
     }
     if (fork) {
@@ -473,12 +476,22 @@ __global__ void __launch_bounds__(256) gemvT_partial_kernel(const double* __rest
 
 __global__ void __launch_bounds__(256) gemvT_reduce_kernel(const double* __restrict__ partial, int n_pad,
                                                            double* __restrict__ alpha) {
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= n_pad) return;
+  // 32 columns per CTA, 8 row groups striding the row blocks; fixed-order combine through shared memory
+  __shared__ double red[8][33];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + c;
   const int nblk = n_pad / GVT_ROWS;
+  const int b0 = (j / 128) * (128 / GVT_ROWS);
   double s = 0.0;
-  for (int b = (j / 128) * (128 / GVT_ROWS); b < nblk; ++b) s += partial[(size_t)b * n_pad + j];
-  alpha[j] = s;
+  for (int b = b0 + g; b < nblk; b += 8) s += partial[(size_t)b * n_pad + j];
+  red[g][c] = s;
+  __syncthreads();
+  if (g == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][c];
+    alpha[j] = t;
+  }
 }
 
 // nll = 0.5 |V|^2 + 0.5 N log(2 pi) + sum_i log L_ii    (reference train/gp_utils.py:141-147)
@@ -519,7 +532,7 @@ extern "C" int distbo_nll_f64(const double* L, const double* W, int N, int n_pad
   DB_CHECK_LAUNCH();
   gemvT_partial_kernel<<<n_pad / GVT_ROWS, 256, 0, st>>>(W, n_pad, V, workspace);
   DB_CHECK_LAUNCH();
-  gemvT_reduce_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(workspace, n_pad, alpha);
+  gemvT_reduce_kernel<<<n_pad / 32, 256, 0, st>>>(workspace, n_pad, alpha);
   DB_CHECK_LAUNCH();
   nll_kernel<<<1, 1024, 0, st>>>(L, n_pad, N, V, nll);
   DB_CHECK_LAUNCH();
