@@ -43,6 +43,7 @@ SIGNATURES = {
     "distbo_task_gram_bwd_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "distbo_adam_f64": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _i64, _d, _vp, _vp]),
     "distbo_score_chunk": (_i, []),
+    "distbo_score_workspace": (_i64, [_i]),
     "distbo_score_timing": (_i, [_i]),
     "distbo_score_timing_read": (_i, [C.POINTER(_d), C.POINTER(_i64)]),
     "distbo_score_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _d, _d,

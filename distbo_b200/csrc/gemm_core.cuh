@@ -202,50 +202,26 @@ __device__ __forceinline__ double frag_ld_b64(const double* s, int x, int k) {
   return LAY == KMAJOR ? s[x * LDK + k] : s[k * LDXB + x];
 }
 
+// acc (32 x 32 warp tile of the 128 x 64 CTA tile at (m0, n0)) += sum_{k in [k_lo, k_hi)} opA(m, k) opB(k, n).
+// smem: TGEMM_SMEM_BYTES.  Ends with a barrier (the buffers may be reused).
 template <int ALAY, int BLAY>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tiles_kernel(GemmArgs p) {
-  extern __shared__ __align__(16) double smem[];
-  tl_start(p.tl, p.tl_id);
-  const int4 t = p.tiles[blockIdx.x >> 1];
-  const int m0 = t.x, n0 = t.y + TN * (blockIdx.x & 1);
+__device__ __forceinline__ void gemm_mainloop_t64(double (&acc)[4][4][2], const double* __restrict__ A, int lda,
+                                                  const double* __restrict__ B, int ldb, int m0, int n0, int k_lo,
+                                                  int k_hi, double* smem) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;
   const int lr = lane >> 2, lk = lane & 3;
   double* sA = smem;
   double* sB = smem + TSTAGES * TSTAGE_A;
-  const int nk = (t.w - t.z) / BK;
-
+  const int nk = (k_hi - k_lo) / BK;
 #pragma unroll
   for (int s = 0; s < TSTAGES - 1; ++s) {
     if (s < nk) {
-      load_tile<ALAY>(sA + s * TSTAGE_A, p.A, p.lda, m0, t.z + s * BK, tid);
-      load_tile_b64<BLAY>(sB + s * TSTAGE_B, p.B, p.ldb, n0, t.z + s * BK, tid);
+      load_tile<ALAY>(sA + s * TSTAGE_A, A, lda, m0, k_lo + s * BK, tid);
+      load_tile_b64<BLAY>(sB + s * TSTAGE_B, B, ldb, n0, k_lo + s * BK, tid);
     }
     cp_async_commit();
   }
-  // out = alpha * (acc0 + A B) with acc0 = (beta / alpha) Cin: the C tile is fetched into the accumulators
-  // while the pipeline fills
-  double acc[4][4][2];
-  if (p.beta != 0.0) {
-    const double f = p.beta / p.alpha;
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-      const int row = m0 + wm * 32 + mi * 8 + lr;
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const int col = n0 + wn * 32 + ni * 8 + lk * 2;
-        const double2 c = *reinterpret_cast<const double2*>(p.Cin + (size_t)row * p.ldcin + col);
-        acc[mi][ni][0] = f * c.x;
-        acc[mi][ni][1] = f * c.y;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-  }
-
   int cs = 0, ps = TSTAGES - 1;
   for (int kt = 0; kt < nk; ++kt) {
     cp_async_wait<TSTAGES - 2>();
@@ -253,8 +229,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tiles_kernel(GemmArgs p)
     {
       const int kn = kt + TSTAGES - 1;
       if (kn < nk) {
-        load_tile<ALAY>(sA + ps * TSTAGE_A, p.A, p.lda, m0, t.z + kn * BK, tid);
-        load_tile_b64<BLAY>(sB + ps * TSTAGE_B, p.B, p.ldb, n0, t.z + kn * BK, tid);
+        load_tile<ALAY>(sA + ps * TSTAGE_A, A, lda, m0, k_lo + kn * BK, tid);
+        load_tile_b64<BLAY>(sB + ps * TSTAGE_B, B, ldb, n0, k_lo + kn * BK, tid);
       }
       cp_async_commit();
       ps = (ps + 1 == TSTAGES) ? 0 : ps + 1;
@@ -276,9 +252,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tiles_kernel(GemmArgs p)
     }
   }
   cp_async_wait<0>();
-  // no barrier needed: the epilogue touches registers and global memory only (an in-place operand of THIS
-  // tile has been fully consumed by every warp's own loads; other CTAs never read this tile as an operand)
   __syncthreads();
+}
+
+template <int ALAY, int BLAY>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tiles_kernel(GemmArgs p) {
+  extern __shared__ __align__(16) double smem[];
+  tl_start(p.tl, p.tl_id);
+  const int4 t = p.tiles[blockIdx.x >> 1];
+  const int m0 = t.x, n0 = t.y + TN * (blockIdx.x & 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int lr = lane >> 2, lk = lane & 3;
+  // out = alpha * (acc0 + A B) with acc0 = (beta / alpha) Cin: the C tile is requested before the pipeline
+  // prologue, so its latency overlaps the first operand stages
+  double acc[4][4][2];
+  if (p.beta != 0.0) {
+    const double f = p.beta / p.alpha;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int row = m0 + wm * 32 + mi * 8 + lr;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int col = n0 + wn * 32 + ni * 8 + lk * 2;
+        const double2 c = *reinterpret_cast<const double2*>(p.Cin + (size_t)row * p.ldcin + col);
+        acc[mi][ni][0] = f * c.x;
+        acc[mi][ni][1] = f * c.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  }
+  gemm_mainloop_t64<ALAY, BLAY>(acc, p.A, p.lda, p.B, p.ldb, m0, n0, t.z, t.w, smem);
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi) {
     const int row = m0 + wm * 32 + mi * 8 + lr;

@@ -6,10 +6,10 @@
 //
 // Per chunk of candidates (one 128-candidate tile per SM):
 //   kst_kernel     : materialise k_* candidate-major, Kst[c][i] (i contiguous), zero on pad rows;
-//   score_kernel   : persistent CTA per candidate tile; loops over the 128-row blocks of W, runs the
-//                    DMMA main loop for k <= row block (W is lower triangular), and folds each
-//                    accumulator tile into column sums of A^2 and A*V - A is never written;
-//                    then the acquisition epilogue and a per-CTA (max value, lowest index);
+//   score_kernel   : CTA = (128-candidate tile, slice of the 128-row blocks of W); runs the DMMA main loop
+//                    for k <= row block (W is lower triangular) and folds each accumulator tile into
+//                    column sums of A^2 and A*V - A is never written; per-slice partial sums out;
+//   score_finish   : adds a tile's slices in order, acquisition epilogue, per-tile (max value, lowest index);
 //   merge_kernel   : deterministic (max value, min index) merge into the running best.
 #include "../../include/distbo_b200.h"
 #include <vector>
@@ -85,16 +85,19 @@ __device__ __forceinline__ double acquisition(int kind, double mean, double std,
   return mean - kappa * std;
 }
 
+constexpr int SCORE_SLICES = 16;  // CTAs that share one candidate tile (row blocks of W dealt out in snake order)
+
 struct ScoreArgs {
   const double* W;
   const double* V;
   const double* Kst;
-  int n_pad;
+  int n_pad, slices;
   const double* log_scale;
   const double* mean_param;
   long long c_begin, M, index_offset;
   int acq_kind;
   double y_max, xi, kappa;
+  double* partial;        // [64-candidate tiles][slices][64][2]: (sum A^2, sum A V) of the slice's row blocks
   double* out_mean;
   double* out_std;
   double* out_acq;
@@ -102,41 +105,50 @@ struct ScoreArgs {
   long long* block_best_idx;
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) score_kernel(ScoreArgs p) {
+// CTA = (64-candidate tile, slice), two CTAs resident per SM (gemm_core.cuh: 128 x 64 CTA tile, 3-stage
+// pipeline).  Consecutive CTAs are the slices of ONE tile, so the tiles in flight at any time keep their K_*
+// tiles (4 MB each at N = 8192) and the walked part of W in L2; a slice takes the row blocks ib with
+// snake(ib) == slice, which gives every slice the same number of k-steps (work ~ ib + 1).
+__global__ void __launch_bounds__(GEMM_THREADS, 2) score_kernel(ScoreArgs p) {
   extern __shared__ __align__(16) double smem[];
-  __shared__ double red2[2][128], redv[2][128];
-  __shared__ double bval[128];
-  __shared__ long long bidx[128];
+  __shared__ double red2[4][TN], redv[4][TN];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
+  const int wm = warp >> 1, wn = warp & 1;
   const int lr = lane >> 2, lk = lane & 3;
-  const int n0 = blockIdx.x * BN;  // candidate tile (local rows of Kst)
+  const int S = p.slices;
+  const int tile = blockIdx.x / S, slice = blockIdx.x % S;
+  const int n0 = tile * TN;  // candidate tile (local rows of Kst)
   const int nb = p.n_pad / BM;
 
   double s2[4][2], sv[4][2];
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) s2[ni][0] = s2[ni][1] = sv[ni][0] = sv[ni][1] = 0.0;
 
-  for (int ib = 0; ib < nb; ++ib) {
-    double acc[8][4][2];
+  for (int base = 0; base < nb; base += 2 * S) {
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int half = 0; half < 2; ++half) {
+      const int ib = half == 0 ? base + slice : base + 2 * S - 1 - slice;
+      if (ib >= nb) continue;
+      double acc[4][4][2];
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    gemm_mainloop<KMAJOR, KMAJOR>(acc, p.W, p.n_pad, p.Kst, p.n_pad, ib * BM, n0, 0, (ib + 1) * BM, smem);
+      for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
-      const double v = p.V[ib * BM + wm * 64 + mi * 8 + lr];
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      gemm_mainloop_t64<KMAJOR, KMAJOR>(acc, p.W, p.n_pad, p.Kst, p.n_pad, ib * BM, n0, 0, (ib + 1) * BM, smem);
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        s2[ni][0] += acc[mi][ni][0] * acc[mi][ni][0];
-        s2[ni][1] += acc[mi][ni][1] * acc[mi][ni][1];
-        sv[ni][0] += acc[mi][ni][0] * v;
-        sv[ni][1] += acc[mi][ni][1] * v;
+      for (int mi = 0; mi < 4; ++mi) {
+        const double v = p.V[ib * BM + wm * 32 + mi * 8 + lr];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          s2[ni][0] += acc[mi][ni][0] * acc[mi][ni][0];
+          s2[ni][1] += acc[mi][ni][1] * acc[mi][ni][1];
+          sv[ni][0] += acc[mi][ni][0] * v;
+          sv[ni][1] += acc[mi][ni][1] * v;
+        }
       }
     }
   }
-  // reduce over the 8 row-lanes that share a column (lane bits 2..4), then over the two M-warps
+  // reduce over the 8 row-lanes that share a column (lane bits 2..4), then over the four M-warps
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
@@ -154,27 +166,44 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) score_kernel(ScoreArgs p) {
       }
     }
   __syncthreads();
-  if (tid < 128) {
-    const long long c = p.c_begin + n0 + tid;
-    double val = -INFINITY;
-    long long idx = 0x7fffffffffffffffLL;
-    if (c < p.M) {
-      const double sumsq = red2[0][tid] + red2[1][tid];
-      const double dot = redv[0][tid] + redv[1][tid];
-      const double scale = exp(*p.log_scale);
-      const double mean = dot + *p.mean_param;
-      const double var = scale - sumsq;
-      const double std = sqrt(fmax(var, kVarClamp));
-      const double a = acquisition(p.acq_kind, mean, std, p.y_max, p.xi, p.kappa);
-      if (p.out_mean) p.out_mean[c] = mean;
-      if (p.out_std) p.out_std[c] = std;
-      if (p.out_acq) p.out_acq[c] = a;
-      val = a;
-      idx = p.index_offset + c;
-    }
-    bval[tid] = val;
-    bidx[tid] = idx;
+  if (tid < TN) {
+    double* dst = p.partial + ((size_t)blockIdx.x * TN + tid) * 2;
+    dst[0] = (red2[0][tid] + red2[1][tid]) + (red2[2][tid] + red2[3][tid]);
+    dst[1] = (redv[0][tid] + redv[1][tid]) + (redv[2][tid] + redv[3][tid]);
   }
+}
+
+// One CTA per candidate tile: adds the slices in slice order, then posterior moments, acquisition and the
+// tile's (max value, lowest index).
+__global__ void __launch_bounds__(128) score_finish_kernel(ScoreArgs p) {
+  __shared__ double bval[128];
+  __shared__ long long bidx[128];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * BN;
+  const long long c = p.c_begin + n0 + tid;
+  double val = -INFINITY;
+  long long idx = 0x7fffffffffffffffLL;
+  if (c < p.M) {
+    double sumsq = 0.0, dot = 0.0;
+    const int t64 = (n0 + tid) / TN, l64 = (n0 + tid) % TN;
+    for (int sl = 0; sl < p.slices; ++sl) {
+      const double* src = p.partial + (((size_t)t64 * p.slices + sl) * TN + l64) * 2;
+      sumsq += src[0];
+      dot += src[1];
+    }
+    const double scale = exp(*p.log_scale);
+    const double mean = dot + *p.mean_param;
+    const double var = scale - sumsq;
+    const double std = sqrt(fmax(var, kVarClamp));
+    const double a = acquisition(p.acq_kind, mean, std, p.y_max, p.xi, p.kappa);
+    if (p.out_mean) p.out_mean[c] = mean;
+    if (p.out_std) p.out_std[c] = std;
+    if (p.out_acq) p.out_acq[c] = a;
+    val = a;
+    idx = p.index_offset + c;
+  }
+  bval[tid] = val;
+  bidx[tid] = idx;
   __syncthreads();
   for (int s = 64; s > 0; s >>= 1) {
     if (tid < s) {
@@ -254,6 +283,11 @@ extern "C" int distbo_score_timing_read(double* total_ms, int64_t* launches) {
   return DISTBO_OK;
 }
 
+extern "C" int64_t distbo_score_workspace(int n_pad) {
+  const int64_t chunk = distbo_score_chunk();
+  return chunk * n_pad + chunk * SCORE_SLICES * 2;   // K_* chunk, then the per-slice partial sums
+}
+
 extern "C" int distbo_score_chunk(void) {
   if (g_score_chunk == 0) {
     int dev = 0, sms = 148;
@@ -282,7 +316,7 @@ extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_p
   const int chunk = distbo_score_chunk();
   static bool configured = false;
   if (!configured) {
-    DB_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    DB_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TGEMM_SMEM_BYTES));
     configured = true;
   }
   int first = 1;
@@ -295,6 +329,8 @@ extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_p
     DB_CHECK_LAUNCH();
     ScoreArgs a;
     a.W = W; a.V = V; a.Kst = Kst; a.n_pad = n_pad;
+    a.slices = (n_pad / BM < SCORE_SLICES) ? n_pad / BM : SCORE_SLICES;
+    a.partial = Kst + (size_t)chunk * n_pad;
     a.log_scale = log_scale; a.mean_param = mean_param;
     a.c_begin = c0; a.M = M; a.index_offset = index_offset;
     a.acq_kind = acq_kind; a.y_max = y_max; a.xi = xi; a.kappa = kappa;
@@ -303,9 +339,11 @@ extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_p
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     const bool timed = g_timing && timing_pair(&t0, &t1);
     if (timed) cudaEventRecord(t0, st);
-    score_kernel<<<tiles, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
+    score_kernel<<<2 * tiles * a.slices, GEMM_THREADS, TGEMM_SMEM_BYTES, st>>>(a);
     DB_CHECK_LAUNCH();
     if (timed) cudaEventRecord(t1, st);
+    score_finish_kernel<<<tiles, 128, 0, st>>>(a);
+    DB_CHECK_LAUNCH();
     merge_best_kernel<<<1, 32, 0, st>>>(block_best_val, (const long long*)block_best_idx, tiles, first, best_val,
                                         (long long*)best_idx);
     DB_CHECK_LAUNCH();

@@ -340,8 +340,9 @@ class GPEngine:
             theta_c = torch.from_numpy(np.ascontiguousarray(theta_c, dtype=np.float64)).to(self.dev)
         M = int(theta_c.shape[0])
         chunk = self.lib.distbo_score_chunk()
-        if self._score_ws is None or self._score_ws[0].numel() < chunk * self.n_pad:
-            self._score_ws = (torch.empty(chunk * self.n_pad, dtype=torch.float64, device=self.dev),
+        need = int(self.lib.distbo_score_workspace(self.n_pad))
+        if self._score_ws is None or self._score_ws[0].numel() < need:
+            self._score_ws = (torch.empty(need, dtype=torch.float64, device=self.dev),
                               torch.empty(chunk // 128, dtype=torch.float64, device=self.dev),
                               torch.empty(chunk // 128, dtype=torch.int64, device=self.dev))
         kst, bbv, bbi = self._score_ws

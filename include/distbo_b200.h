@@ -130,9 +130,11 @@ int distbo_adam_f64(double* params, const double* grads, double* m, double* v, i
  * var = scale - |A|^2, std = sqrt(max(var,1e-32)), acq in {EI, UCB, LCB}.
  * kvec [n_pad] = KE[task(i), target] (1 for kernel 'params'; 0 on pad rows).
  * Outputs (any may be NULL): mean [M], std [M], acq [M]; best_val[1], best_idx[1] (int64; first
- * index of the maximum, as numpy argmax).  Kst: workspace of chunk*n_pad doubles with
- * chunk = distbo_score_chunk(); partial workspace of distbo_score_chunk()/128*2 pairs. */
+ * index of the maximum, as numpy argmax).  Kst: workspace of distbo_score_workspace(n_pad) doubles;
+ * block_best_val / block_best_idx: distbo_score_chunk() / 128 entries each. */
 int distbo_score_chunk(void);
+/* doubles of workspace distbo_score_f64 needs behind `Kst` (K_* chunk + per-slice partial sums) */
+int64_t distbo_score_workspace(int n_pad);
 /* Measurement aid: while enabled, distbo_score_f64 brackets every launch of its contraction kernel
  * with CUDA events on the launching stream; _read synchronises them and returns the summed device
  * time (ms) and the number of launches since the last enable/read. */
