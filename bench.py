@@ -36,7 +36,7 @@ WEIGHT_DIM_X = (20, 10)
 M_DEFAULT = 1 << 20
 XI, KAPPA = 0.01, 2.58           # experiments/train_test.py:63-64
 FP64_FALLBACK_TFLOPS = 35.5      # cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peak.json)
-SCORE_KERNEL_DRAM_BYTES = 40.3e9  # dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch (ncu)
+SCORE_KERNEL_DRAM_BYTES = 11.87e9  # dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch (ncu)
 
 
 # ----------------------------------------------------------------------------------- workload
@@ -365,7 +365,9 @@ def run_cuda(args):
     roofline = {"kernel": "score_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": SCORE_KERNEL_DRAM_BYTES, "peak_source": peak_src,
                 "traffic_note": "dram read+write per launch from ncu --set full (profiles/r01_score_kernel_ncu_full.txt): "
-                                "148 CTAs each stream the lower triangle of W (268 MB) through L2",
+                                "algorithmic bytes are the K_* chunk (1.24 GB) + the lower triangle of W (0.27 GB); every K_* tile is "
+                                "re-read once per row block of W and 83 % of those re-reads hit L2 (it was 40.3 GB before the "
+                                "CTAs of one tile were made co-resident)",
                 "avg_launch_ms": avg_ms, "launches_timed": n_launch, "candidates_per_launch": cands_per_launch,
                 "share_of_step": kms.value / ms_local}
     fit_flops = float(n_pad) ** 3
