@@ -119,35 +119,59 @@ template <typename T>
 __device__ __forceinline__ void load_net(const T* __restrict__ W1, const T* __restrict__ b1, const T* __restrict__ W2,
                                          int din, int h, int po, int hp, T* sW1, T* sb1, T* sW2) {
   const int dinp = round_up_i(din, 4);
-  for (int i = threadIdx.x; i < dinp * hp; i += blockDim.x) {
-    const int k = i / hp, j = i - k * hp;
-    sW1[i] = (k < din && j < h) ? W1[k * h + j] : (T)0;
+  if (hp == h) {   // rows are already padded: straight copy, then the zero rows
+    for (int i = threadIdx.x; i < din * h; i += blockDim.x) sW1[i] = W1[i];
+    for (int i = din * h + threadIdx.x; i < dinp * hp; i += blockDim.x) sW1[i] = (T)0;
+  } else {
+    for (int i = threadIdx.x; i < dinp * hp; i += blockDim.x) {
+      const int k = i / hp, j = i - k * hp;
+      sW1[i] = (k < din && j < h) ? W1[k * h + j] : (T)0;
+    }
   }
   for (int j = threadIdx.x; j < hp; j += blockDim.x) sb1[j] = (j < h) ? b1[j] : (T)0;
   for (int i = threadIdx.x; i < h * po; i += blockDim.x) sW2[i] = W2[i];
 }
 
-// Stage columns [k0, k0+kc) of `n` rows (row stride din) into sX [ROWS][XS]; rows >= n and the columns up
-// to the next multiple of 4 are zero filled.
-template <typename T>
-__device__ __forceinline__ void stage_tile(const T* __restrict__ Xg, int n, int din, int k0, int kc, T* sX) {
-  constexpr int ROWS = 32 * EmbT<T>::RM, XS = EmbT<T>::XS, U = 8;
+// Asynchronously stage columns [k0, k0+kc) of `n` rows (row stride din) into sX [ROWS][XS] with cp.async in the
+// widest unit (16 / 8 / 4 bytes) that the row pitch keeps aligned; rows >= n and the columns up to the next
+// multiple of 4 are zero filled with ordinary stores.  The caller commits / waits the cp.async group.
+template <int BYTES>
+__device__ __forceinline__ void cp_async_bytes(void* smem_dst, const void* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+  else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
+}
+
+template <typename T, int EPV>
+__device__ __forceinline__ void stage_rows_async(const T* __restrict__ Xg, int n, int din, int k0, int kc, T* sX) {
+  constexpr int ROWS = 32 * EmbT<T>::RM, XS = EmbT<T>::XS;
   const int kcp = round_up_i(kc, 4);
-  const int total = ROWS * kcp, nthr = blockDim.x;
-  // batches of U independent global loads per thread before the first shared store (memory-level parallelism)
-  for (int base = threadIdx.x; base < total; base += U * nthr) {
-    T v[U];
-    int dst[U];
+  const int vpr = kcp / EPV;                       // vectors per row (kcp is a multiple of 4 >= EPV)
+  for (int idx = threadIdx.x; idx < ROWS * vpr; idx += blockDim.x) {
+    const int r = idx / vpr, k = (idx - r * vpr) * EPV;
+    T* dst = sX + r * XS + k;
+    if (r < n && k < kc) {                         // kc is a multiple of EPV: whole vectors only
+      cp_async_bytes<EPV * (int)sizeof(T)>(dst, Xg + (size_t)r * din + k0 + k);
+    } else {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = base + u * nthr;
-      const int r = idx / kcp, k = idx - r * kcp;
-      dst[u] = (idx < total) ? r * XS + k : -1;
-      v[u] = (idx < total && r < n && k < kc) ? __ldg(Xg + (size_t)r * din + k0 + k) : (T)0;
+      for (int e = 0; e < EPV; ++e) dst[e] = (T)0;
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (dst[u] >= 0) sX[dst[u]] = v[u];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_tile_async(const T* __restrict__ Xg, int n, int din, int k0, int kc, T* sX) {
+  // elements per vector: the row pitch din * sizeof(T) and the global base (cudaMalloc, 256 B) decide alignment
+  const bool base16 = (reinterpret_cast<size_t>(Xg) & 15) == 0;
+  const bool base8 = (reinterpret_cast<size_t>(Xg) & 7) == 0;
+  if (sizeof(T) == 8) {
+    if ((din & 1) == 0 && base16) stage_rows_async<T, 2>(Xg, n, din, k0, kc, sX);
+    else stage_rows_async<T, 1>(Xg, n, din, k0, kc, sX);
+  } else {
+    if ((din & 3) == 0 && base16) stage_rows_async<T, 4>(Xg, n, din, k0, kc, sX);
+    else if ((din & 1) == 0 && base8) stage_rows_async<T, 2>(Xg, n, din, k0, kc, sX);
+    else stage_rows_async<T, 1>(Xg, n, din, k0, kc, sX);
   }
 }
 
@@ -174,10 +198,12 @@ __device__ __forceinline__ void layer1_slice(const T* sX, const T* sW1, int hp, 
 }
 
 // Hidden activations of one net for the chunk's rows: sH [ROWS][hp] = tanh(x W1 + b1) (0 on rows >= n).
+// The 64-column slices of x are double buffered (sX = 2 tiles): slice s+1 is in flight (cp.async) while the
+// register-blocked GEMM runs on slice s.
 template <typename T>
 __device__ __forceinline__ void hidden_forward(const T* __restrict__ Xg, int n, int din, int h, int hp, const T* sW1,
                                                const T* sb1, T* sX, T* sH) {
-  constexpr int RM = EmbT<T>::RM;
+  constexpr int RM = EmbT<T>::RM, TILE = 32 * EmbT<T>::RM * EmbT<T>::XS;
   const int rg = threadIdx.x & 31, hg = threadIdx.x >> 5;
   const bool active = 4 * hg < hp;
   T z[RM][4];
@@ -185,13 +211,20 @@ __device__ __forceinline__ void hidden_forward(const T* __restrict__ Xg, int n, 
   for (int m = 0; m < RM; ++m)
 #pragma unroll
     for (int c = 0; c < 4; ++c) z[m][c] = active ? sb1[4 * hg + c] : (T)0;
-  for (int k0 = 0; k0 < din; k0 += EMB_KC) {
+  __syncthreads();                                   // both tiles are free (previous users are done)
+  stage_tile_async<T>(Xg, n, din, 0, min(EMB_KC, din), sX);
+  cp_async_commit();
+  int buf = 0;
+  for (int k0 = 0; k0 < din; k0 += EMB_KC, buf ^= 1) {
     const int kc = min(EMB_KC, din - k0);
+    if (k0 + EMB_KC < din) stage_tile_async<T>(Xg, n, din, k0 + EMB_KC, min(EMB_KC, din - k0 - EMB_KC), sX + (buf ^ 1) * TILE);
+    cp_async_commit();
+    cp_async_wait<1>();                              // slice k0 has landed (the newest group may still fly)
     __syncthreads();
-    stage_tile<T>(Xg, n, din, k0, kc, sX);
-    __syncthreads();
-    if (active) layer1_slice<T>(sX, sW1, hp, k0, kc, rg, hg, z);
+    if (active) layer1_slice<T>(sX + buf * TILE, sW1, hp, k0, kc, rg, hg, z);
+    __syncthreads();                                 // tile `buf` may be refilled two slices later
   }
+  cp_async_wait<0>();
   if (active) {
 #pragma unroll
     for (int m = 0; m < RM; ++m) {
@@ -209,9 +242,17 @@ __device__ __forceinline__ void output_forward(const T* sH, const T* sW2, int h,
   constexpr int ROWS = 32 * EmbT<T>::RM;
   for (int idx = threadIdx.x; idx < ROWS * po; idx += blockDim.x) {
     const int r = idx / po, i = idx - r * po;
-    T s = (T)0;
-    for (int j = 0; j < h; ++j) s += sH[r * hp + j] * sW2[j * po + i];
-    sF[r * fs + i] = s;
+    // four independent chains (sH rows are zero padded to hp = multiple of 4; W2 rows beyond h are not read)
+    T s0 = (T)0, s1 = (T)0, s2 = (T)0, s3 = (T)0;
+    int j = 0;
+    for (; j + 3 < h; j += 4) {
+      s0 += sH[r * hp + j] * sW2[j * po + i];
+      s1 += sH[r * hp + j + 1] * sW2[(j + 1) * po + i];
+      s2 += sH[r * hp + j + 2] * sW2[(j + 2) * po + i];
+      s3 += sH[r * hp + j + 3] * sW2[(j + 3) * po + i];
+    }
+    for (; j < h; ++j) s0 += sH[r * hp + j] * sW2[j * po + i];
+    sF[r * fs + i] = (s0 + s1) + (s2 + s3);
   }
 }
 
@@ -242,7 +283,7 @@ __host__ __device__ inline EmbSmem<T> emb_layout(T* base, int dx, int dy, int hx
   s.sW1y = take((y_mode == 1) ? (size_t)round_up_i(dy, 4) * s.hpy : 0);
   s.sb1y = take(s.hpy);
   s.sW2y = take((y_mode == 1) ? (size_t)hy * q : 0);
-  s.sX = take((size_t)ROWS * XS);
+  s.sX = take((size_t)2 * ROWS * XS);   // two tiles: double-buffered slices
   s.sHx = take((size_t)ROWS * s.hpx);
   s.sHy = take((size_t)ROWS * s.hpy);
   s.sFx = take((size_t)ROWS * s.fsx);
@@ -293,15 +334,25 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_fwd_kernel(EmbedArgs<
     const int n = min(ROWS, a.seg_off[t + 1] - row0);
     chunk_features<T>(a, s, row0, n);
     for (int o = threadIdx.x; o < pout; o += blockDim.x) {
-      T acc = (T)0;
+      T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;   // four interleaved row chains, combined in a fixed order
       if (o < a.p * gq) {
         const int i = o / gq, j = o - i * gq;   // row-major flatten i*q + j (distbo_net.py:40-42)
-        for (int r = 0; r < ROWS; ++r) acc += s.sFx[r * s.fsx + i] * s.sFy[r * s.fsy + j];
+        for (int r = 0; r < ROWS; r += 4) {
+          a0 += s.sFx[r * s.fsx + i] * s.sFy[r * s.fsy + j];
+          a1 += s.sFx[(r + 1) * s.fsx + i] * s.sFy[(r + 1) * s.fsy + j];
+          a2 += s.sFx[(r + 2) * s.fsx + i] * s.sFy[(r + 2) * s.fsy + j];
+          a3 += s.sFx[(r + 3) * s.fsx + i] * s.sFy[(r + 3) * s.fsy + j];
+        }
       } else {
         const int j = o - a.p * gq;             // class ratios: mean of y (distbo_net.py:45-48)
-        for (int r = 0; r < ROWS; ++r) acc += s.sFy[r * s.fsy + j];
+        for (int r = 0; r < ROWS; r += 4) {
+          a0 += s.sFy[r * s.fsy + j];
+          a1 += s.sFy[(r + 1) * s.fsy + j];
+          a2 += s.sFy[(r + 2) * s.fsy + j];
+          a3 += s.sFy[(r + 3) * s.fsy + j];
+        }
       }
-      a.partial[(size_t)c * pout + o] = acc;
+      a.partial[(size_t)c * pout + o] = (a0 + a1) + (a2 + a3);
     }
   }
 }
@@ -387,28 +438,47 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
       // dW2[j][i] += sum_r h[r][j] dF[r][i] ; db1[j] += sum_r dz[r][j]
       for (int e = threadIdx.x; e < h * po; e += nthr) {
         const int j = e / po, i = e - j * po;
-        double v = 0.0;
-        for (int r = 0; r < n; ++r) v += sH[r * hp + j] * s.sDF[r * dfs + i];
-        G[din * h + h + e] += v;
+        // rows >= n hold zeros in sDF, so the loops may run over whole groups of four (ROWS is a multiple of 4)
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        for (int r = 0; r < n; r += 4) {
+          v0 += sH[r * hp + j] * s.sDF[r * dfs + i];
+          v1 += sH[(r + 1) * hp + j] * s.sDF[(r + 1) * dfs + i];
+          v2 += sH[(r + 2) * hp + j] * s.sDF[(r + 2) * dfs + i];
+          v3 += sH[(r + 3) * hp + j] * s.sDF[(r + 3) * dfs + i];
+        }
+        G[din * h + h + e] += (v0 + v1) + (v2 + v3);
       }
       if ((int)threadIdx.x < h) {
-        double v = 0.0;
-        for (int r = 0; r < n; ++r) v += s.sDZ[r * hp + threadIdx.x];
-        G[din * h + threadIdx.x] += v;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        for (int r = 0; r < n; r += 4) {
+          v0 += s.sDZ[r * hp + threadIdx.x];
+          v1 += s.sDZ[(r + 1) * hp + threadIdx.x];
+          v2 += s.sDZ[(r + 2) * hp + threadIdx.x];
+          v3 += s.sDZ[(r + 3) * hp + threadIdx.x];
+        }
+        G[din * h + threadIdx.x] += (v0 + v1) + (v2 + v3);
       }
       // dW1[k][4jg..4jg+3] += sum_r x[r][k] dz[r][4jg..]: the x tile is re-staged slice by slice; the lanes of a
       // warp take consecutive k (conflict-free column reads), dz is a 2 x 128-bit broadcast load.
-      for (int k0 = 0; k0 < din; k0 += EMB_KC) {
+      constexpr int TILE = ROWS * XS;
+      __syncthreads();
+      stage_tile_async<T>(Xg, n, din, 0, min(EMB_KC, din), s.sX);
+      cp_async_commit();
+      int buf = 0;
+      for (int k0 = 0; k0 < din; k0 += EMB_KC, buf ^= 1) {
         const int kc = min(EMB_KC, din - k0);
+        if (k0 + EMB_KC < din)
+          stage_tile_async<T>(Xg, n, din, k0 + EMB_KC, min(EMB_KC, din - k0 - EMB_KC), s.sX + (buf ^ 1) * TILE);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
-        stage_tile<T>(Xg, n, din, k0, kc, s.sX);
-        __syncthreads();
+        const double* tile = s.sX + buf * TILE;
         const int items = kc * (hp / 4);
         for (int e = threadIdx.x; e < items; e += nthr) {
           const int jg = e / kc, k = e - jg * kc;
           double acc[4] = {0.0, 0.0, 0.0, 0.0};
           for (int r = 0; r < n; ++r) {
-            const double x = s.sX[r * XS + k];
+            const double x = tile[r * XS + k];
             double dz[4];
             EmbT<T>::load4(s.sDZ + r * hp + 4 * jg, dz);
 #pragma unroll
@@ -418,7 +488,9 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
           for (int cc = 0; cc < 4; ++cc)
             if (4 * jg + cc < h) G[(size_t)(k0 + k) * h + 4 * jg + cc] += acc[cc];
         }
+        __syncthreads();
       }
+      cp_async_wait<0>();
       __syncthreads();
     }
   }

@@ -97,6 +97,18 @@ def main():
         potrf_only()
     print(json.dumps({"what": "gram+potrf_graph_ms", "ms": timed(g.replay)}), flush=True)
     print(json.dumps({"what": "info", "info": int(e.info.item())}), flush=True)
+    # K1 at prediction time: fp32 embedding of the 65 full sample sets (218 MB of rows)
+    X, Y, off = gp._prediction_sets()
+    out = torch.zeros(e.T + 1, e.P, dtype=X.dtype, device=e.dev)
+    ms = timed(lambda: e.embed(X, Y, off, out=out, dtype=X.dtype), n=10)
+    nbytes = X.numel() * X.element_size() + Y.numel() * Y.element_size()
+    print(json.dumps({"what": "embed_fwd_predict_sets", "dtype": str(X.dtype), "rows": int(X.shape[0]), "ms": ms,
+                      "GB_per_s": nbytes / ms / 1e6}), flush=True)
+    Xd, Yd = X.double(), Y.double()
+    outd = torch.zeros(e.T + 1, e.P, dtype=torch.float64, device=e.dev)
+    ms = timed(lambda: e.embed(Xd, Yd, off, out=outd, dtype=torch.float64), n=10)
+    print(json.dumps({"what": "embed_fwd_predict_sets", "dtype": "float64", "rows": int(X.shape[0]), "ms": ms,
+                      "GB_per_s": 2 * nbytes / ms / 1e6}), flush=True)
 
 
 if __name__ == "__main__":
