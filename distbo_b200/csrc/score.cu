@@ -21,21 +21,22 @@ namespace db {
 constexpr int SCORE_DMAX = 16;
 constexpr int KST_CAND = 8;  // candidates per CTA in kst_kernel
 
-__global__ void __launch_bounds__(256) kst_kernel(const double* __restrict__ theta_s,
-                                                  const double* __restrict__ sqnorm, int N, int n_pad, int d,
-                                                  const double* __restrict__ log_bw,
-                                                  const double* __restrict__ kvec,
-                                                  const double* __restrict__ log_scale,
-                                                  const double* __restrict__ theta_c,
-                                                  const double* __restrict__ c_shift,
-                                                  const double* __restrict__ c_scale, long long c_begin,
-                                                  long long M, double* __restrict__ Kst) {
-  __shared__ double ys[KST_CAND][SCORE_DMAX];
+template <int D>
+__global__ void __launch_bounds__(256, 2) kst_kernel(const double* __restrict__ theta_s,
+                                                     const double* __restrict__ sqnorm, int N, int n_pad, int d,
+                                                     const double* __restrict__ log_bw,
+                                                     const double* __restrict__ kvec,
+                                                     const double* __restrict__ log_scale,
+                                                     const double* __restrict__ theta_c,
+                                                     const double* __restrict__ c_shift,
+                                                     const double* __restrict__ c_scale, long long c_begin,
+                                                     long long M, double* __restrict__ Kst) {
+  __shared__ double ys[KST_CAND][D];
   __shared__ double ysq[KST_CAND];
   const int tid = threadIdx.x;
   const long long cl0 = (long long)blockIdx.x * KST_CAND;  // local candidate row in the chunk
-  if (tid < KST_CAND * SCORE_DMAX) {
-    const int q = tid / SCORE_DMAX, k = tid % SCORE_DMAX;
+  if (tid < KST_CAND * D) {
+    const int q = tid / D, k = tid % D;
     const long long c = c_begin + cl0 + q;
     double v = 0.0;
     if (k < d && c < M) {
@@ -54,20 +55,28 @@ __global__ void __launch_bounds__(256) kst_kernel(const double* __restrict__ the
   __syncthreads();
   const double scale = exp(*log_scale);
   for (int i = tid; i < n_pad; i += 256) {
-    double xi[SCORE_DMAX];
+    double xi[D];
 #pragma unroll
-    for (int k = 0; k < SCORE_DMAX; ++k) xi[k] = (k < d) ? theta_s[(size_t)i * d + k] : 0.0;
+    for (int k = 0; k < D; ++k) xi[k] = (k < d) ? theta_s[(size_t)i * d + k] : 0.0;
     const double sqi = sqnorm[i];
     const double kv = (i < N) ? kvec[i] : 0.0;
+#pragma unroll 1
+    for (int q0 = 0; q0 < KST_CAND; q0 += 2) {   // two independent Matern chains at a time (128-register budget)
+      double dot[2];
 #pragma unroll
-    for (int q = 0; q < KST_CAND; ++q) {
-      double dot = 0.0;
+      for (int u = 0; u < 2; ++u) {
+        dot[u] = 0.0;
 #pragma unroll
-      for (int k = 0; k < SCORE_DMAX; ++k) dot += xi[k] * ys[q][k];
-      const double d2 = -2.0 * dot + sqi + ysq[q];
-      double v = (scale * matern32_from_d2(d2)) * kv;
-      if (i >= N || c_begin + cl0 + q >= M) v = 0.0;
-      Kst[(size_t)(cl0 + q) * n_pad + i] = v;
+        for (int k = 0; k < D; ++k) dot[u] += xi[k] * ys[q0 + u][k];
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int q = q0 + u;
+        const double d2 = -2.0 * dot[u] + sqi + ysq[q];
+        double v = (scale * matern32_from_d2(d2)) * kv;
+        if (i >= N || c_begin + cl0 + q >= M) v = 0.0;
+        Kst[(size_t)(cl0 + q) * n_pad + i] = v;
+      }
     }
   }
 }
@@ -323,9 +332,16 @@ extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_p
   for (int64_t c0 = 0; c0 < M; c0 += chunk) {
     const int64_t mc = (M - c0 < chunk) ? (M - c0) : chunk;
     const int tiles = (int)((mc + BN - 1) / BN);
-    kst_kernel<<<tiles * BN / KST_CAND, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale,
-                                                     theta_c, cand_shift, cand_scale, (long long)c0, (long long)M,
-                                                     Kst);
+    const int kgrid = tiles * BN / KST_CAND;
+    if (d <= 4)
+      kst_kernel<4><<<kgrid, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale, theta_c, cand_shift,
+                                           cand_scale, (long long)c0, (long long)M, Kst);
+    else if (d <= 8)
+      kst_kernel<8><<<kgrid, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale, theta_c, cand_shift,
+                                           cand_scale, (long long)c0, (long long)M, Kst);
+    else
+      kst_kernel<SCORE_DMAX><<<kgrid, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale, theta_c,
+                                                    cand_shift, cand_scale, (long long)c0, (long long)M, Kst);
     DB_CHECK_LAUNCH();
     ScoreArgs a;
     a.W = W; a.V = V; a.Kst = Kst; a.n_pad = n_pad;
