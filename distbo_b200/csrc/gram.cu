@@ -456,8 +456,7 @@ extern "C" int distbo_gram_grad_f64(const double* Kinv, const double* alpha, con
   double* rowH = workspace;                          // [n_pad][T]
   double* rowbw = rowH + (size_t)n_pad * T;          // [n_pad][d]
   double* rowsc = rowbw + (size_t)n_pad * d;         // [n_pad][3]
-  double* Hsym = rowsc + (size_t)n_pad * 3;          // [T*T] (fits: workspace has n_pad*(T+d+4))
-  if ((size_t)T * T > (size_t)n_pad) return DISTBO_EARG;
+  double* Hsym = rowsc + (size_t)n_pad * 3;          // [T*T]; workspace = n_pad * (T + d + 3) + T * T doubles
   const int grid = (N + 7) / 8;
   DB_CUDA(cudaMemsetAsync(rowH, 0, (size_t)n_pad * T * sizeof(double), st));   // rows only write the tasks they meet
   if (d <= 4)

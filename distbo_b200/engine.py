@@ -178,7 +178,7 @@ class GPEngine:
         off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
         self.task_off = torch.from_numpy(off).to(self.dev)
         self.task_id = torch.from_numpy(np.repeat(np.arange(self.T), sizes).astype(np.int32)).to(self.dev)
-        self.gws = self._f64(n_pad * (self.T + self.d + 4))
+        self.gws = self._f64(n_pad * (self.T + self.d + 3) + self.T * self.T)
         self.H = self._f64(self.T, self.T)
         self.gscal = self._f64(3)
         self.W_valid = False

@@ -103,7 +103,7 @@ int distbo_nll_f64(const double* L, const double* W, int N, int n_pad, const dou
 /* Closed-form gradient contraction with G = 0.5 (Kinv - alpha alpha^T), replacing TF autodiff
  * through the Cholesky (train/train.py:33-40):
  *   g_log_bw [d], g_scalars = {d/dlog_scale, d/dmean, d/dlog_sigma}, H [T,T] = dNLL/dKE (full).
- * workspace: n_pad * (T + d + 4) doubles. */
+ * workspace: n_pad * (T + d + 3) + T * T doubles. */
 int distbo_gram_grad_f64(const double* Kinv, const double* alpha, const double* theta_s,
                          const double* sqnorm, int N, int n_pad, int d, const int32_t* task_id,
                          const int32_t* task_off, const double* KE, int T, const double* log_scale,
