@@ -50,8 +50,10 @@ struct Plan {
   std::vector<cudaEvent_t> ev_panel, ev_first;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   bool lookahead = true;
-  int* d_flags = nullptr;    // [nb] "inverse of diagonal block kb is published" (fused panel kernel)
+  int* d_flags = nullptr;    // [nb][NFLAG] sub-step / "inverse published" flags of the panel kernels
+  double* d_relay = nullptr; // [2][128*128] relay products (see panel_kernel)
   int sms = 148;
+  bool relay_on = true;      // DISTBO_POTRF_RELAY=0 switches the relay CTA off (A/B measurements)
 };
 
 // ------------------------------------------------------------------ fused panel kernel
@@ -70,11 +72,14 @@ struct PanelArgs {
   int ld, kb, nb;
   int pend_lo;   // first panel whose update of column kb is still pending (applied by this kernel)
   int32_t* info;
-  int* flags;
+  int* flags;               // [nb][NFLAG]: sub-step flags of the diagonal factor (potf2.cuh)
+  double* relay;            // [2][128*128]: L[kb+1,kb] L[kb+1,kb]^T from the relay CTA of the previous launch
+  int use_relay;            // this launch's diagonal tile takes panel kb-1's update from `relay`
   unsigned long long* tl;   // debug timeline, normally null
 };
 
 constexpr int PANEL_SMEM = (PB * PLD + STAGES * STAGE_ELEMS) * (int)sizeof(double);  // 217088 >= POTF2_SMEM
+constexpr int NFLAG = 4;   // per column block: the four sub-step flags of the diagonal factor (potf2.cuh)
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
   extern __shared__ __align__(16) double smem[];
@@ -85,7 +90,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
   const int n0 = kb * BN;
   double* sT = smem;  // [128][PLD] tile
   tl_start(p.tl, 2 * kb);
-  bool flag_seen = false;
 
   // CTA 0 owns the diagonal block; CTA c >= 1 owns row blocks kb + c, kb + c + (G-1), ...
   const int stride = (blockIdx.x == 0) ? nb : (int)gridDim.x - 1;
@@ -103,7 +107,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
         acc[mi][ni][1] = -c.y;
       }
     }
-    if (p.pend_lo < kb) gemm_mainloop<KMAJOR, KMAJOR>(acc, p.A, ld, p.A, ld, m0, n0, p.pend_lo * BN, n0, smem);
+    const bool diag = blockIdx.x == 0;
+    // the diagonal tile may take the update of panel kb-1 from the relay product of the previous launch
+    const int k_hi = (diag && p.use_relay) ? n0 - BN : n0;
+    if (p.pend_lo * BN < k_hi) gemm_mainloop<KMAJOR, KMAJOR>(acc, p.A, ld, p.A, ld, m0, n0, p.pend_lo * BN, k_hi, smem);
+    if (diag && p.use_relay) {
+      const double* P = p.relay + (size_t)(kb & 1) * PB * PB;
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi) {
+        const int r = wm * 64 + mi * 8 + lr;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int c = wn * 32 + ni * 8 + lk * 2;
+          const double2 v = *reinterpret_cast<const double2*>(P + (size_t)r * PB + c);
+          acc[mi][ni][0] += v.x;   // acc holds -(tile): tile = A - pending - P
+          acc[mi][ni][1] += v.y;
+        }
+      }
+    }
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
       const int r = wm * 64 + mi * 8 + lr;
@@ -111,7 +132,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
       for (int ni = 0; ni < 4; ++ni) {
         const int c = wn * 32 + ni * 8 + lk * 2;
         double2 v = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
-        if (blockIdx.x == 0) {  // diagonal tile: potf2 expects zeros above the diagonal
+        if (diag) {  // diagonal tile: potf2 expects zeros above the diagonal
           if (c > r) v.x = 0.0;
           if (c + 1 > r) v.y = 0.0;
         }
@@ -121,51 +142,164 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
     __syncthreads();
 
     double* Ab = p.A + (size_t)m0 * ld + n0;
-    if (blockIdx.x == 0) {
+    if (diag) {
       double* Wb = p.W + (size_t)m0 * ld + n0;
       long long* dbg = nullptr;
       tl_mark(p.tl, 2 * kb, 2);   // update done, potf2 starts
-      potf2_factor_invert(smem, m0, p.info, dbg);
-      potf2_store_W(smem, Wb, ld);
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) atomicExch(p.flags + kb, 1);
-      tl_mark(p.tl, 2 * kb, 3);   // inverse published
-      potf2_store_L(smem, Ab, ld);
+      // The four sub-steps publish the final rows of L_kk and the 32x32 diagonal inverses as they complete; the
+      // assembly of the full 128x128 inverse (needed by TRTRI only) is deferred to diag_inverse_kernel, which
+      // does all diagonal blocks in parallel instead of one per step on the critical chain.
+      potf2_factor_invert(smem, m0, p.info, dbg, Potf2Publish{Ab, Wb, ld, p.flags + kb * NFLAG}, false);
+      tl_mark(p.tl, 2 * kb, 3);   // last sub-step published
       break;
     }
 
-    if (!flag_seen) {
-      if (tid == 0) {
-        while (atomicAdd(p.flags + kb, 0) == 0) __nanosleep(100);
-        __threadfence();
+    // ---- off-diagonal row block: the solve against L_kk follows the diagonal CTA's four 32-column sub-steps
+    // as they are published - X_s = (B_s - X_{<s} L_kk[s,<s]^T) Dinv_s^T - so L[i,kb] is complete a few
+    // microseconds after the last sub-step; the assembled 128x128 inverse is not needed here (it is only
+    // finished for TRTRI).  The relay CTA (row block kb+1) also accumulates P = L[kb+1,kb] L[kb+1,kb]^T, one
+    // rank-32 update per sub-step, for the NEXT launch's diagonal tile: solve + update of that tile leave the
+    // critical chain potf2(kb) -> potf2(kb+1).
+    {
+      const bool relay = p.relay && blockIdx.x == 1 && i == kb + 1;
+      double* sLr = smem + PB * PLD;            // [32][PLD] rows 32s..32s+31 of L_kk (columns 0..32s-1)
+      double* sDi = sLr + SB * PLD;             // [32][DLD] Dinv_s
+      const double* Lkk = p.A + (size_t)n0 * ld + n0;
+      const double* Wkk = p.W + (size_t)n0 * ld + n0;
+      const int r0 = warp * 16;                 // this warp's 16 rows of the tile
+      double pr[8][4][2];                       // relay only: P accumulators (64 x 32 warp tile)
+      if (relay) {
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) pr[mi][ni][0] = pr[mi][ni][1] = 0.0;
       }
-      __syncthreads();
-      flag_seen = true;
-    }
-    double out[8][4][2];
+      for (int sb = 0; sb < 4; ++sb) {
+        const int c0 = sb * SB;
+        if (tid == 0) {
+          while (atomicAdd(p.flags + kb * NFLAG + sb, 0) == 0) __nanosleep(64);
+          __threadfence();
+        }
+        __syncthreads();                        // flag seen; previous step's staging buffers are free
+        for (int idx = tid; idx < SB * c0; idx += GEMM_THREADS) {
+          const int r = idx / c0, c = idx - r * c0;
+          sLr[r * PLD + c] = __ldcg(Lkk + (size_t)(c0 + r) * ld + c);
+        }
+        for (int idx = tid; idx < SB * SB; idx += GEMM_THREADS) {
+          const int r = idx >> 5, c = idx & 31;
+          sDi[r * DLD + c] = __ldcg(Wkk + (size_t)(c0 + r) * ld + c0 + c);
+        }
+        __syncthreads();
+        double xa[2][4][2];
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) out[mi][ni][0] = out[mi][ni][1] = 0.0;
-    // out[m][n] = sum_k tile[m][k] * Winv[n][k]   (B = inv(L_kk), k-major, read through L2 with cp.async.cg)
-    // inv(L_kk) is lower triangular: column group wn needs k < 32 (wn + 1).  Warps 0-3 take column groups
-    // 0..3 and warps 4-7 take 3..0, so each SM sub-partition (warp & 3) owns 2 + 8, 4 + 6, ... = 10 k-steps.
-    const double* Wd = p.W + (size_t)n0 * ld + n0;
-    const int swn = (wm == 0) ? wn : 3 - wn;
-    gemm_mainloop_smemA<KMAJOR>(out, sT, PLD, Wd, ld, 0, 0, BN, smem + PB * PLD, wm, swn, true);
+          for (int ni = 0; ni < 4; ++ni) {
+            const double2 v = *reinterpret_cast<const double2*>(&sT[(r0 + mi * 8 + lr) * PLD + c0 + ni * 8 + 2 * lk]);
+            xa[mi][ni][0] = v.x;
+            xa[mi][ni][1] = v.y;
+          }
+        for (int k = 0; k < c0; k += 4) {       // B_s - X_{<s} L_kk[s,<s]^T
+          double af[2], bf[4];
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
-      const int r = wm * 64 + mi * 8 + lr;
+          for (int mi = 0; mi < 2; ++mi) af[mi] = -sT[(r0 + mi * 8 + lr) * PLD + k + lk];
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const int c = swn * 32 + ni * 8 + lk * 2;
-        *reinterpret_cast<double2*>(Ab + (size_t)r * ld + c) = make_double2(out[mi][ni][0], out[mi][ni][1]);
+          for (int ni = 0; ni < 4; ++ni) bf[ni] = sLr[(ni * 8 + lr) * PLD + k + lk];
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(xa[mi][ni][0], xa[mi][ni][1], af[mi], bf[ni]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni)
+            *reinterpret_cast<double2*>(&sT[(r0 + mi * 8 + lr) * PLD + c0 + ni * 8 + 2 * lk]) =
+                make_double2(xa[mi][ni][0], xa[mi][ni][1]);
+        __syncwarp();
+        double xo[2][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) xo[mi][ni][0] = xo[mi][ni][1] = 0.0;
+#pragma unroll
+        for (int k = 0; k < SB; k += 4) {       // (.) Dinv_s^T
+          double af[2], bf[4];
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) af[mi] = sT[(r0 + mi * 8 + lr) * PLD + c0 + k + lk];
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) bf[ni] = sDi[(ni * 8 + lr) * DLD + k + lk];
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(xo[mi][ni][0], xo[mi][ni][1], af[mi], bf[ni]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            const int r = r0 + mi * 8 + lr, c = c0 + ni * 8 + 2 * lk;
+            const double2 v = make_double2(xo[mi][ni][0], xo[mi][ni][1]);
+            *reinterpret_cast<double2*>(&sT[r * PLD + c]) = v;
+            *reinterpret_cast<double2*>(Ab + (size_t)r * ld + c) = v;
+          }
+        if (relay) {
+          __syncthreads();                      // columns [c0, c0+32) of L[kb+1,kb] are complete in sT
+#pragma unroll
+          for (int k = 0; k < SB; k += 4) {     // P += X_s X_s^T
+            double af[8], bf[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) af[mi] = sT[(wm * 64 + mi * 8 + lr) * PLD + c0 + k + lk];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) bf[ni] = sT[(wn * 32 + ni * 8 + lr) * PLD + c0 + k + lk];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni) dmma884(pr[mi][ni][0], pr[mi][ni][1], af[mi], bf[ni]);
+          }
+        }
       }
+      if (relay) {
+        double* Pout = p.relay + (size_t)((kb + 1) & 1) * PB * PB;
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) {
+          const int r = wm * 64 + mi * 8 + lr;
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            const int c = wn * 32 + ni * 8 + lk * 2;
+            *reinterpret_cast<double2*>(Pout + (size_t)r * PB + c) = make_double2(pr[mi][ni][0], pr[mi][ni][1]);
+          }
+        }
+      }
+      __syncthreads();                          // sT and the staging buffers may be overwritten
     }
-    // gemm_mainloop_smemA ended with a barrier: sT and the pipeline buffers may be overwritten
   }
   tl_end(p.tl, 2 * kb);
+}
+
+// inv(L_kk) for every diagonal block at once (one CTA each): L_kk and its four 32x32 diagonal inverses, left in
+// A / W by the panel kernels, are brought into shared memory, the off-diagonal 32-blocks of the inverse are
+// assembled by block forward substitution (potf2.cuh) and the 128x128 block is written to W.
+__global__ void __launch_bounds__(POTF2_THREADS, 1) diag_inverse_kernel(const double* __restrict__ A,
+                                                                        double* __restrict__ W, int ld) {
+  extern __shared__ __align__(16) double s[];
+  double* sA = s;
+  double* sDinv = s + PB * PLD;
+  const int tid = threadIdx.x;
+  const size_t off = (size_t)blockIdx.x * PB * ld + (size_t)blockIdx.x * PB;
+  const double* Ab = A + off;
+  double* Wb = W + off;
+  for (int idx = tid; idx < PB * PB; idx += POTF2_THREADS) {
+    const int r = idx >> 7, c = idx & 127;
+    sA[r * PLD + c] = (c <= r) ? Ab[(size_t)r * ld + c] : 0.0;
+    if ((r >> 5) == (c >> 5)) sDinv[(r >> 5) * SB * DLD + (r & 31) * DLD + (c & 31)] = Wb[(size_t)r * ld + c];
+  }
+  __syncthreads();
+  long long* dbg = nullptr;
+  potf2_assemble_inverse(s, dbg);
+  potf2_store_W(s, Wb, ld);
 }
 
 // Number of CTAs of the panel kernel for column block kb: as few as keep the panel (update -> potf2 ->
@@ -313,17 +447,22 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
   cudaEventCreateWithFlags(&p->ev_end, cudaEventDisableTiming);
   const char* la = getenv("DISTBO_LOOKAHEAD");
   p->lookahead = !(la && la[0] == '0');
+  const char* rl = getenv("DISTBO_POTRF_RELAY");
+  p->relay_on = !(rl && rl[0] == '0');
   {
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  if (cudaMalloc(&p->d_flags, (size_t)nb * sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc(&p->d_flags, (size_t)nb * NFLAG * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&p->d_relay, (size_t)2 * PB * PB * sizeof(double)) != cudaSuccess) {
     cudaFree(p->d_tiles);
+    if (p->d_flags) cudaFree(p->d_flags);
     delete p;
     return DISTBO_ECUDA;
   }
   cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
   cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
+  cudaFuncSetAttribute(diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
   *plan_out = p;
   return DISTBO_OK;
 }
@@ -339,6 +478,7 @@ extern "C" int distbo_plan_destroy(void* plan) {
   if (p->panel_stream) cudaStreamDestroy(p->panel_stream);
   if (p->d_tiles) cudaFree(p->d_tiles);
   if (p->d_flags) cudaFree(p->d_flags);
+  if (p->d_relay) cudaFree(p->d_relay);
   delete p;
   return DISTBO_OK;
 }
@@ -351,7 +491,7 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
   DB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), U));
 
   {
-    DB_CUDA(cudaMemsetAsync(p->d_flags, 0, (size_t)nb * sizeof(int), U));
+    DB_CUDA(cudaMemsetAsync(p->d_flags, 0, (size_t)nb * NFLAG * sizeof(int), U));
     GemmArgs rest{};  // C -= P P^T on the tiles (i, j), j >= kb + 2
     rest.A = A; rest.B = A; rest.C = A; rest.Cin = A;
     rest.lda = rest.ldb = rest.ldc = rest.ldcin = n;
@@ -364,11 +504,16 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
     }
     int running_rest_tiles = 0;   // tiles of the trailing update that runs next to the panel being launched
     int running_share = 1;        // panels that run next to that same update
+    int g_prev = 0;
     for (int kb = 0; kb < nb; ++kb) {
       // column kb must have received every trailing update that touches it
       if (fork && p->wait_rest[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_first[p->wait_rest[kb]], 0));
-      PanelArgs pa{A, W, n, kb, nb, p->pend_lo[kb], info, p->d_flags, g_timeline};
       const int g_this = fork ? panel_ctas(nb, kb, p->sms, running_rest_tiles, kb - p->pend_lo[kb], running_share) : nb - kb;
+      // the previous launch had a relay CTA (row block kb) whenever it had more than one CTA
+      const int use_relay = (p->relay_on && kb >= 1 && g_prev >= 2 && p->pend_lo[kb] <= kb - 1) ? 1 : 0;
+      PanelArgs pa{A, W, n, kb, nb, p->pend_lo[kb], info, p->d_flags, p->relay_on ? p->d_relay : nullptr, use_relay,
+                   g_timeline};
+      g_prev = g_this;
       panel_kernel<<<g_this, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
       DB_CHECK_LAUNCH();
       const int q = p->rest_after[kb];
@@ -402,6 +547,8 @@ extern "C" int distbo_trtri_f64(void* plan, const double* L, double* W, double* 
   Plan* p = (Plan*)plan;
   cudaStream_t st = (cudaStream_t)stream;
   const int n = p->n;
+  diag_inverse_kernel<<<p->nb, POTF2_THREADS, POTF2_SMEM, st>>>(L, W, n);
+  DB_CHECK_LAUNCH();
   for (size_t l = 0; l < p->tri1.size(); ++l) {
     GemmArgs g1{};  // T = L21 * W11
     g1.A = L; g1.B = W; g1.C = T; g1.Cin = T;

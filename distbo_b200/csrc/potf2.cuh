@@ -128,7 +128,69 @@ __device__ __forceinline__ void invert_32(const double* sA, int c0, double* dinv
 // Factor + invert the 128x128 block held in shared memory (sA [128][PLD], lower part valid, upper zero).
 // On return: lower sA = L; strictly upper 32-blocks (j,i) = W_ij^T; sDinv = the four diagonal inverses.
 // row_base = global row of the block's first row (for `info`).  dbg (optional) receives clock64 stamps.
-__device__ __forceinline__ void potf2_factor_invert(double* s, int row_base, int32_t* info, long long*& dbg) {
+
+// Block forward substitution over the 4x4 grid of 32x32 blocks: fills the strictly upper 32-blocks (j,i) of sA
+// with W_ij^T given L in the lower part of sA and the four diagonal inverses in sDinv.
+__device__ __forceinline__ void potf2_assemble_inverse(double* s, long long*& dbg) {
+  double* sA = s;
+  double* sDinv = s + PB * PLD;
+  double* sS = sDinv + 4 * SB * DLD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lk = lane & 3;
+  (void)tid;
+  // ---- inverse by block distance
+  for (int dist = 1; dist < 4; ++dist) {
+    const int nblk = 4 - dist;
+    for (int t = warp; t < nblk * 16; t += 8) {
+      const int b = t >> 4, tr = (t >> 2) & 3, tc = t & 3;
+      const int j = b, i = b + dist;
+      double c0v = 0.0, c1v = 0.0;
+      for (int kb = j; kb < i; ++kb) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const double av = sA[(SB * i + tr * 8 + lr) * PLD + SB * kb + kk * 4 + lk];
+          const double bv = (kb == j) ? sDinv[j * SB * DLD + (kk * 4 + lk) * DLD + tc * 8 + lr]
+                                      : sA[(SB * j + tc * 8 + lr) * PLD + SB * kb + kk * 4 + lk];
+          dmma884(c0v, c1v, av, bv);
+        }
+      }
+      *reinterpret_cast<double2*>(&sS[b * SB * DLD + (tr * 8 + lr) * DLD + tc * 8 + 2 * lk]) =
+          make_double2(c0v, c1v);
+    }
+    __syncthreads();
+    for (int t = warp; t < nblk * 16; t += 8) {
+      const int b = t >> 4, tr = (t >> 2) & 3, tc = t & 3;
+      const int j = b, i = b + dist;
+      double c0v = 0.0, c1v = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)
+        dmma884(c0v, c1v, sDinv[i * SB * DLD + (tr * 8 + lr) * DLD + kk * 4 + lk],
+                sS[b * SB * DLD + (kk * 4 + lk) * DLD + tc * 8 + lr]);
+      // W_ij[r][c] -> transposed into the upper block (j,i)
+      const int r = tr * 8 + lr, c = tc * 8 + 2 * lk;
+      sA[(SB * j + c) * PLD + SB * i + r] = -c0v;
+      sA[(SB * j + c + 1) * PLD + SB * i + r] = -c1v;
+    }
+    __syncthreads();
+    PT_STAMP(dbg);
+  }
+}
+
+// Optional early publication of the sub-steps (used by the Cholesky panel kernel): in sub-step jb, as soon as the
+// diagonal 32-block is factored and inverted, the final rows [32 jb, 32 jb + 32) of L and Dinv_jb go to their
+// final places in global memory (Ab / Wb, leading dimension ld) and flags[jb] is set.  (Publishing the block
+// column below separately, so that consumers can start step s+1 earlier, was measured slower: +1.5 us per
+// sub-step on the diagonal CTA against -2 us on the consumers' tail.)
+struct Potf2Publish {
+  double* Ab;
+  double* Wb;
+  int ld;
+  int* flags;   // [4] sub-step flags; null: no publication
+};
+
+__device__ __forceinline__ void potf2_factor_invert(double* s, int row_base, int32_t* info, long long*& dbg,
+                                                    Potf2Publish pub = Potf2Publish{nullptr, nullptr, 0, nullptr},
+                                                    bool assemble = true) {
   double* sA = s;
   double* sDinv = s + PB * PLD;
   double* sS = sDinv + 4 * SB * DLD;
@@ -161,6 +223,21 @@ __device__ __forceinline__ void potf2_factor_invert(double* s, int row_base, int
     if (warp == 0) invert_32(sA, c0, sDinv + jb * SB * DLD, sR, lane);
     __syncthreads();
     PT_STAMP(dbg);
+    if (pub.flags) {   // sub-step jb: rows [32 jb, 32 jb + 32) of L (zeros above the diagonal) and Dinv_jb are final
+      for (int idx = tid; idx < SB * PB; idx += POTF2_THREADS) {
+        const int r = idx >> 7, c = idx & 127;
+        pub.Ab[(size_t)(c0 + r) * pub.ld + c] = (c <= c0 + r) ? sA[(c0 + r) * PLD + c] : 0.0;
+      }
+      for (int idx = tid; idx < SB * SB; idx += POTF2_THREADS) {
+        const int r = idx >> 5, c = idx & 31;
+        pub.Wb[(size_t)(c0 + r) * pub.ld + c0 + c] = sDinv[jb * SB * DLD + r * DLD + c];
+      }
+      __syncthreads();
+      if (tid == 0) {   // cumulative fence: the barrier ordered every thread's stores before this one
+        __threadfence();
+        atomicExch(pub.flags + jb, 1);
+      }
+    }
     const int nrg = (PB - c0 - SB) / 8;  // 8-row groups below the diagonal sub-block
     // sub-panel solve: P <- P * Dinv^T (each warp owns whole 8-row groups: in place is safe)
     for (int rg = warp; rg < nrg; rg += 8) {
@@ -203,43 +280,7 @@ __device__ __forceinline__ void potf2_factor_invert(double* s, int row_base, int
     PT_STAMP(dbg);
   }
 
-  // ---- inverse by block distance
-  for (int dist = 1; dist < 4; ++dist) {
-    const int nblk = 4 - dist;
-    for (int t = warp; t < nblk * 16; t += 8) {
-      const int b = t >> 4, tr = (t >> 2) & 3, tc = t & 3;
-      const int j = b, i = b + dist;
-      double c0v = 0.0, c1v = 0.0;
-      for (int kb = j; kb < i; ++kb) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const double av = sA[(SB * i + tr * 8 + lr) * PLD + SB * kb + kk * 4 + lk];
-          const double bv = (kb == j) ? sDinv[j * SB * DLD + (kk * 4 + lk) * DLD + tc * 8 + lr]
-                                      : sA[(SB * j + tc * 8 + lr) * PLD + SB * kb + kk * 4 + lk];
-          dmma884(c0v, c1v, av, bv);
-        }
-      }
-      *reinterpret_cast<double2*>(&sS[b * SB * DLD + (tr * 8 + lr) * DLD + tc * 8 + 2 * lk]) =
-          make_double2(c0v, c1v);
-    }
-    __syncthreads();
-    for (int t = warp; t < nblk * 16; t += 8) {
-      const int b = t >> 4, tr = (t >> 2) & 3, tc = t & 3;
-      const int j = b, i = b + dist;
-      double c0v = 0.0, c1v = 0.0;
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        dmma884(c0v, c1v, sDinv[i * SB * DLD + (tr * 8 + lr) * DLD + kk * 4 + lk],
-                sS[b * SB * DLD + (kk * 4 + lk) * DLD + tc * 8 + lr]);
-      // W_ij[r][c] -> transposed into the upper block (j,i)
-      const int r = tr * 8 + lr, c = tc * 8 + 2 * lk;
-      sA[(SB * j + c) * PLD + SB * i + r] = -c0v;
-      sA[(SB * j + c + 1) * PLD + SB * i + r] = -c1v;
-    }
-    __syncthreads();
-    PT_STAMP(dbg);
-  }
-
+  if (assemble) potf2_assemble_inverse(s, dbg);
 }
 
 // W block (inverse, lower) from the shared-memory result to global memory.

@@ -90,7 +90,7 @@ int distbo_plan_destroy(void* plan);
 /* A (n_pad x n_pad, lower tiles valid) is overwritten by its lower Cholesky factor L (upper part of
  * the diagonal blocks zeroed); the 128x128 diagonal blocks of W receive inv(L_kk). */
 int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info, void* stream);
-/* W <- L^-1 (lower), given L and the diagonal blocks left in W by distbo_potrf_f64. T: n_pad^2 temp. */
+/* W <- L^-1 (lower), given L and the diagonal sub-block inverses left in W by distbo_potrf_f64. T: n_pad^2 temp. */
 int distbo_trtri_f64(void* plan, const double* L, double* W, double* T, void* stream);
 /* Kinv (lower 128-tiles) <- W^T W. */
 int distbo_lauum_f64(void* plan, const double* W, double* Kinv, void* stream);
