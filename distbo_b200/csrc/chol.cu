@@ -60,12 +60,15 @@ struct Plan {
 // One launch per column block kb, CTA c -> row block i = kb + c:
 //   1. acc = A[i,kb] - L[i, pend..kb) L[kb, pend..kb)^T   (the updates of column kb still pending: the last one
 //                                                    to three panels; older ones came from the trailing kernels)
-//   2. c == 0: the diagonal tile goes to shared memory, is factorised and inverted there (potf2.cuh);
-//              inv(L_kk) is written to W and published through flags[kb]; then L_kk is written to A.
-//      c  > 0: the accumulator tile stays in shared memory as the A operand, the CTA waits for the flag
-//              and multiplies by inv(L_kk)^T (DMMA, B streamed from L2), result -> A[i,kb].
-// The chain update -> potf2 -> solve therefore costs one launch and no global round trip of the tile.
-// Waiting CTAs only ever wait for block 0 of their own grid (<= 64 CTAs, all resident on 148 SMs).
+//   2. c == 0: the diagonal tile goes to shared memory and is factorised there in four 32-column sub-steps
+//              (potf2.cuh); after each sub-step the finished rows of L_kk and the 32x32 diagonal inverse are
+//              written to A / W and published through a flag.
+//      c  > 0: the tile stays in shared memory; the CTA follows the sub-step flags and solves 32 columns at a
+//              time, X_s = (B_s - X_{<s} L_kk[s,<s]^T) Dinv_s^T on DMMA, result -> A[i,kb].  CTA 1 (row block
+//              kb+1, the "relay") also accumulates L[kb+1,kb] L[kb+1,kb]^T for the next launch's diagonal tile.
+// The chain update -> potf2 -> solve therefore costs one launch, no global round trip of the tile, and the
+// solve / next-diagonal update overlap the factorisation.  Waiting CTAs only ever wait for block 0 of their
+// own grid (<= 64 CTAs, all resident on 148 SMs).
 struct PanelArgs {
   double* A;
   double* W;

@@ -104,53 +104,6 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[8][4][2], const doub
   __syncthreads();  // all warps done with smem: safe to reuse it / to overwrite an in-place operand
 }
 
-// Variant with the A operand (128 rows x K) RESIDENT in shared memory (row stride lda_s doubles, k-major) and
-// only B streamed global -> shared through the cp.async pipeline in smemB (STAGES * STAGE_ELEMS doubles).
-// Used by the Cholesky panel kernel, where A is an accumulator tile that never left the SM.
-// lda_s == 4 (mod 16) doubles keeps the fragment loads conflict free (two wavefronts per 32 doubles).
-template <int BLAY>
-__device__ __forceinline__ void gemm_mainloop_smemA(double (&acc)[8][4][2], const double* sAres, int lda_s,
-                                                    const double* __restrict__ B, int ldb, int n0, int k_lo,
-                                                    int k_hi, double* smemB, int wm, int wn, bool b_lower_tri) {
-  // b_lower_tri: B (n x k) is lower triangular, so the warp that owns output columns [32 wn, 32 wn + 32) only
-  // needs k < 32 (wn + 1); the caller maps (wm, wn) so that every SM sub-partition gets the same total work.
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int lr = lane >> 2, lk = lane & 3;
-  const int nk = (k_hi - k_lo) / BK;
-  const int nk_warp = b_lower_tri ? min(nk, (32 * (wn + 1)) / BK) : nk;
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nk) load_tile<BLAY>(smemB + s * STAGE_ELEMS, B, ldb, n0, k_lo + s * BK, tid);
-    cp_async_commit();
-  }
-  for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {
-      const int kn = kt + STAGES - 1;
-      if (kn < nk) load_tile<BLAY>(smemB + (kn & (STAGES - 1)) * STAGE_ELEMS, B, ldb, n0, k_lo + kn * BK, tid);
-      cp_async_commit();
-    }
-    if (kt < nk_warp) {
-      const double* b = smemB + (kt & (STAGES - 1)) * STAGE_ELEMS;
-#pragma unroll
-      for (int k4 = 0; k4 < BK / 4; ++k4) {
-        double af[8], bf[4];
-#pragma unroll
-        for (int mi = 0; mi < 8; ++mi) af[mi] = sAres[(wm * 64 + mi * 8 + lr) * lda_s + kt * BK + k4 * 4 + lk];
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) bf[ni] = frag_ld<BLAY>(b, wn * 32 + ni * 8 + lr, k4 * 4 + lk);
-#pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-      }
-    }
-  }
-  cp_async_wait<0>();
-  __syncthreads();
-}
-
 struct GemmArgs {
   const double* A;
   const double* B;
