@@ -101,3 +101,38 @@ def test_fit_predict_parity(cuda_engine_mod, case):
     mo, so = o.predict_y(cand)
     assert rel(mg, mo) < 1e-8
     g.close()
+
+
+@pytest.mark.parametrize("case", ["dist_joint", "dist_class"])
+def test_fp32_embedding_at_prediction(cuda_engine_mod, case):
+    """float64=False: the datasets' rows are embedded in fp32 at prediction time (north_star: embeddings within
+    1e-5 relative); the GP itself stays fp64, so the posterior moves by ~1e-5 at most relative to the oracle."""
+    rs = np.random.RandomState(17)
+    classification = case == "dist_class"
+    d, T, per = 2, 4, 20
+    dx, dy = (16, 2) if classification else (5, 1)
+    theta, y, sizes, X, Y = make_tasks(rs, T, per, d, dx, dy, 300, classification)
+    model_type = "classification" if classification else "regression"
+    fit = dict(learning_rate=0.005, max_epochs=4, likhd_var_init=1e-2, first_early_stop_epoch=2, data_X=X[:T],
+               data_Y=Y[:T], source_embed_ind=[np.arange(len(x)) for x in X[:T]], sizes=sizes, embed_op="joint",
+               weight_dim_x=[20, 10], weight_dim_y=[20, 10], batch_size=1000, stratify=False, concat_data_size=True,
+               max_size=400)
+    common = dict(model_type=model_type, seed=3, target_X=X[T], target_Y=Y[T], target_embed_ind=np.arange(len(X[T])))
+    from distbo_b200.train import gp_regressor
+    g = gp_regressor("dist", float64=False, **common)
+    o = OracleGPRegressor("dist", float64=True, **common)
+    g.maximise_likhd(theta, y, **fit)
+    o.maximise_likhd(theta, y, **fit)
+    assert rel(g.loss_history, o.loss_history) < 1e-8          # training is fp64 in both
+    cand = rs.uniform(-3, 3, size=(500, d))
+    mg, sg = g.predict_y(cand)
+    mo, so = o.predict_y(cand)
+    E32 = g._E_all.cpu().numpy()
+    assert g._prediction_sets()[0].dtype == torch.float32
+    assert rel(mg, mo) < 2e-4 and np.max(np.abs(sg - so)) < 2e-4
+    # the embeddings themselves: fp32 kernel vs fp64 oracle
+    p = o.p
+    want = O.dist_features(O.NP, p, np.vstack(X), np.vstack(Y), [1] * (T + 1), [len(x) for x in X],
+                           data_sizes=[len(x) for x in X], max_size=400, embed_op="joint", model_type=model_type,
+                           return_pooled=True)
+    assert rel(E32[:, :want.shape[1]], want) < 1e-5

@@ -1,3 +1,3 @@
 python tools/ncu_targets.py > gpurun_out/ncu_e_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'embed_fwd_kernel|embed_chunk_table|embed_fwd_reduce|embed_bwd_kernel' -c 8 -o gpurun_out/prof_embed -f python tools/ncu_targets.py > gpurun_out/ncu_embed.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'embed_fwd_kernel<float' -c 1 -o gpurun_out/prof_embed32 -f python tools/ncu_targets.py > gpurun_out/ncu_embed32.log 2>&1
 echo rc=$?
