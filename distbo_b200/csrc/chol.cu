@@ -54,6 +54,8 @@ struct Plan {
   double* d_relay = nullptr; // [2][128*128] relay products (see panel_kernel)
   int sms = 148;
   bool relay_on = true;      // DISTBO_POTRF_RELAY=0 switches the relay CTA off (A/B measurements)
+  bool small_ok = false;     // the whole-matrix cooperative kernel can be used (n_pad <= 2048, all CTAs resident)
+  int* d_small_flags = nullptr;   // done [nb*nb] | sub [nb*4] | xf [nb*4]
 };
 
 // ------------------------------------------------------------------ fused panel kernel
@@ -83,6 +85,140 @@ struct PanelArgs {
 
 constexpr int PANEL_SMEM = (PB * PLD + STAGES * STAGE_ELEMS) * (int)sizeof(double);  // 217088 >= POTF2_SMEM
 constexpr int NFLAG = 4;   // per column block: the four sub-step flags of the diagonal factor (potf2.cuh)
+
+// Solve of one off-diagonal 128x128 tile B (in shared memory, sT = smem [128][PLD]) against the diagonal block
+// L_kk of block column n0 / 128, following the diagonal CTA's four 32-column sub-steps as they are published
+// through sub[0..3]:  X_s = (B_s - X_{<s} L_kk[s,<s]^T) Dinv_s^T  on DMMA, so L[i,kb] is complete a few
+// microseconds after the last sub-step; the assembled 128x128 inverse is not needed.  X_s is written to the
+// tile in shared memory and to Ab (global, leading dimension ld); if xflags != null, xflags[s] is set once
+// column group s is visible device-wide.  RELAY: also accumulates P = X X^T, one rank-32 update per sub-step,
+// and stores it to Pout [128][128] (the next launch's diagonal tile takes its update from there).
+template <bool RELAY>
+__device__ __forceinline__ void stepwise_solve(double* smem, const double* A, const double* W, int ld, int n0,
+                                               const int* sub, double* Ab, int* xflags, double* Pout) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lk = lane & 3;
+  double* sT = smem;
+  double* sLr = smem + PB * PLD;            // [32][PLD] rows 32s..32s+31 of L_kk (columns 0..32s-1)
+  double* sDi = sLr + SB * PLD;             // [32][DLD] Dinv_s
+  const double* Lkk = A + (size_t)n0 * ld + n0;
+  const double* Wkk = W + (size_t)n0 * ld + n0;
+  const int r0 = warp * 16;                 // this warp's 16 rows of the tile
+  double pr[RELAY ? 8 : 1][4][2];           // relay only: P accumulators (64 x 32 warp tile)
+  if (RELAY) {
+#pragma unroll
+    for (int mi = 0; mi < (RELAY ? 8 : 1); ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) pr[mi][ni][0] = pr[mi][ni][1] = 0.0;
+  }
+  for (int sb = 0; sb < 4; ++sb) {
+    const int c0 = sb * SB;
+    if (tid == 0) {
+      while (atomicAdd(const_cast<int*>(sub) + sb, 0) == 0) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();                        // flag seen; previous step's staging buffers are free
+    for (int idx = tid; idx < SB * c0; idx += GEMM_THREADS) {
+      const int r = idx / c0, c = idx - r * c0;
+      sLr[r * PLD + c] = __ldcg(Lkk + (size_t)(c0 + r) * ld + c);
+    }
+    for (int idx = tid; idx < SB * SB; idx += GEMM_THREADS) {
+      const int r = idx >> 5, c = idx & 31;
+      sDi[r * DLD + c] = __ldcg(Wkk + (size_t)(c0 + r) * ld + c0 + c);
+    }
+    __syncthreads();
+    double xa[2][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const double2 v = *reinterpret_cast<const double2*>(&sT[(r0 + mi * 8 + lr) * PLD + c0 + ni * 8 + 2 * lk]);
+        xa[mi][ni][0] = v.x;
+        xa[mi][ni][1] = v.y;
+      }
+    for (int k = 0; k < c0; k += 4) {       // B_s - X_{<s} L_kk[s,<s]^T
+      double af[2], bf[4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) af[mi] = -sT[(r0 + mi * 8 + lr) * PLD + k + lk];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) bf[ni] = sLr[(ni * 8 + lr) * PLD + k + lk];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(xa[mi][ni][0], xa[mi][ni][1], af[mi], bf[ni]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+        *reinterpret_cast<double2*>(&sT[(r0 + mi * 8 + lr) * PLD + c0 + ni * 8 + 2 * lk]) =
+            make_double2(xa[mi][ni][0], xa[mi][ni][1]);
+    __syncwarp();
+    double xo[2][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) xo[mi][ni][0] = xo[mi][ni][1] = 0.0;
+#pragma unroll
+    for (int k = 0; k < SB; k += 4) {       // (.) Dinv_s^T
+      double af[2], bf[4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) af[mi] = sT[(r0 + mi * 8 + lr) * PLD + c0 + k + lk];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) bf[ni] = sDi[(ni * 8 + lr) * DLD + k + lk];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(xo[mi][ni][0], xo[mi][ni][1], af[mi], bf[ni]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int r = r0 + mi * 8 + lr, c = c0 + ni * 8 + 2 * lk;
+        const double2 v = make_double2(xo[mi][ni][0], xo[mi][ni][1]);
+        *reinterpret_cast<double2*>(&sT[r * PLD + c]) = v;
+        *reinterpret_cast<double2*>(Ab + (size_t)r * ld + c) = v;
+      }
+    if (xflags) {
+      __syncthreads();
+      if (tid == 0) {   // cumulative fence after the barrier, then publish column group sb of this tile
+        __threadfence();
+        atomicExch(xflags + sb, 1);
+      }
+    }
+    if (RELAY) {
+      __syncthreads();                      // columns [c0, c0+32) of the tile are complete in sT
+#pragma unroll
+      for (int k = 0; k < SB; k += 4) {     // P += X_s X_s^T
+        double af[8], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) af[mi] = sT[(wm * 64 + mi * 8 + lr) * PLD + c0 + k + lk];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = sT[(wn * 32 + ni * 8 + lr) * PLD + c0 + k + lk];
+#pragma unroll
+        for (int mi = 0; mi < (RELAY ? 8 : 1); ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) dmma884(pr[mi][ni][0], pr[mi][ni][1], af[mi], bf[ni]);
+      }
+    }
+  }
+  if (RELAY) {
+#pragma unroll
+    for (int mi = 0; mi < (RELAY ? 8 : 1); ++mi) {
+      const int r = wm * 64 + mi * 8 + lr;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int c = wn * 32 + ni * 8 + lk * 2;
+        *reinterpret_cast<double2*>(Pout + (size_t)r * PB + c) = make_double2(pr[mi][ni][0], pr[mi][ni][1]);
+      }
+    }
+  }
+  __syncthreads();                          // sT and the staging buffers may be overwritten
+}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
   extern __shared__ __align__(16) double smem[];
@@ -157,129 +293,133 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
       break;
     }
 
-    // ---- off-diagonal row block: the solve against L_kk follows the diagonal CTA's four 32-column sub-steps
-    // as they are published - X_s = (B_s - X_{<s} L_kk[s,<s]^T) Dinv_s^T - so L[i,kb] is complete a few
-    // microseconds after the last sub-step; the assembled 128x128 inverse is not needed here (it is only
-    // finished for TRTRI).  The relay CTA (row block kb+1) also accumulates P = L[kb+1,kb] L[kb+1,kb]^T, one
-    // rank-32 update per sub-step, for the NEXT launch's diagonal tile: solve + update of that tile leave the
-    // critical chain potf2(kb) -> potf2(kb+1).
+    // ---- off-diagonal row block: stepwise solve (see stepwise_solve); CTA 1's first row block is the relay
     {
       const bool relay = p.relay && blockIdx.x == 1 && i == kb + 1;
-      double* sLr = smem + PB * PLD;            // [32][PLD] rows 32s..32s+31 of L_kk (columns 0..32s-1)
-      double* sDi = sLr + SB * PLD;             // [32][DLD] Dinv_s
-      const double* Lkk = p.A + (size_t)n0 * ld + n0;
-      const double* Wkk = p.W + (size_t)n0 * ld + n0;
-      const int r0 = warp * 16;                 // this warp's 16 rows of the tile
-      double pr[8][4][2];                       // relay only: P accumulators (64 x 32 warp tile)
-      if (relay) {
-#pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) pr[mi][ni][0] = pr[mi][ni][1] = 0.0;
-      }
-      for (int sb = 0; sb < 4; ++sb) {
-        const int c0 = sb * SB;
-        if (tid == 0) {
-          while (atomicAdd(p.flags + kb * NFLAG + sb, 0) == 0) __nanosleep(64);
-          __threadfence();
-        }
-        __syncthreads();                        // flag seen; previous step's staging buffers are free
-        for (int idx = tid; idx < SB * c0; idx += GEMM_THREADS) {
-          const int r = idx / c0, c = idx - r * c0;
-          sLr[r * PLD + c] = __ldcg(Lkk + (size_t)(c0 + r) * ld + c);
-        }
-        for (int idx = tid; idx < SB * SB; idx += GEMM_THREADS) {
-          const int r = idx >> 5, c = idx & 31;
-          sDi[r * DLD + c] = __ldcg(Wkk + (size_t)(c0 + r) * ld + c0 + c);
-        }
-        __syncthreads();
-        double xa[2][4][2];
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) {
-            const double2 v = *reinterpret_cast<const double2*>(&sT[(r0 + mi * 8 + lr) * PLD + c0 + ni * 8 + 2 * lk]);
-            xa[mi][ni][0] = v.x;
-            xa[mi][ni][1] = v.y;
-          }
-        for (int k = 0; k < c0; k += 4) {       // B_s - X_{<s} L_kk[s,<s]^T
-          double af[2], bf[4];
-#pragma unroll
-          for (int mi = 0; mi < 2; ++mi) af[mi] = -sT[(r0 + mi * 8 + lr) * PLD + k + lk];
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) bf[ni] = sLr[(ni * 8 + lr) * PLD + k + lk];
-#pragma unroll
-          for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma884(xa[mi][ni][0], xa[mi][ni][1], af[mi], bf[ni]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni)
-            *reinterpret_cast<double2*>(&sT[(r0 + mi * 8 + lr) * PLD + c0 + ni * 8 + 2 * lk]) =
-                make_double2(xa[mi][ni][0], xa[mi][ni][1]);
-        __syncwarp();
-        double xo[2][4][2];
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) xo[mi][ni][0] = xo[mi][ni][1] = 0.0;
-#pragma unroll
-        for (int k = 0; k < SB; k += 4) {       // (.) Dinv_s^T
-          double af[2], bf[4];
-#pragma unroll
-          for (int mi = 0; mi < 2; ++mi) af[mi] = sT[(r0 + mi * 8 + lr) * PLD + c0 + k + lk];
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) bf[ni] = sDi[(ni * 8 + lr) * DLD + k + lk];
-#pragma unroll
-          for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma884(xo[mi][ni][0], xo[mi][ni][1], af[mi], bf[ni]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) {
-            const int r = r0 + mi * 8 + lr, c = c0 + ni * 8 + 2 * lk;
-            const double2 v = make_double2(xo[mi][ni][0], xo[mi][ni][1]);
-            *reinterpret_cast<double2*>(&sT[r * PLD + c]) = v;
-            *reinterpret_cast<double2*>(Ab + (size_t)r * ld + c) = v;
-          }
-        if (relay) {
-          __syncthreads();                      // columns [c0, c0+32) of L[kb+1,kb] are complete in sT
-#pragma unroll
-          for (int k = 0; k < SB; k += 4) {     // P += X_s X_s^T
-            double af[8], bf[4];
-#pragma unroll
-            for (int mi = 0; mi < 8; ++mi) af[mi] = sT[(wm * 64 + mi * 8 + lr) * PLD + c0 + k + lk];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) bf[ni] = sT[(wn * 32 + ni * 8 + lr) * PLD + c0 + k + lk];
-#pragma unroll
-            for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-              for (int ni = 0; ni < 4; ++ni) dmma884(pr[mi][ni][0], pr[mi][ni][1], af[mi], bf[ni]);
-          }
-        }
-      }
-      if (relay) {
-        double* Pout = p.relay + (size_t)((kb + 1) & 1) * PB * PB;
-#pragma unroll
-        for (int mi = 0; mi < 8; ++mi) {
-          const int r = wm * 64 + mi * 8 + lr;
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) {
-            const int c = wn * 32 + ni * 8 + lk * 2;
-            *reinterpret_cast<double2*>(Pout + (size_t)r * PB + c) = make_double2(pr[mi][ni][0], pr[mi][ni][1]);
-          }
-        }
-      }
-      __syncthreads();                          // sT and the staging buffers may be overwritten
+      const int* sub = p.flags + kb * NFLAG;
+      if (relay) stepwise_solve<true>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, p.relay + (size_t)((kb + 1) & 1) * PB * PB);
+      else stepwise_solve<false>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, nullptr);
     }
   }
   tl_end(p.tl, 2 * kb);
+}
+
+// ------------------------------------------------------------------ whole-matrix kernel for small problems
+// For n_pad <= 16 * 128 the entire factorisation runs in ONE cooperative launch: CTA = one lower tile (r, c),
+// all nbt (nbt + 1) / 2 CTAs resident at once (cooperative launch), dependencies through flags in global memory:
+//   done[r][c]   tile L[r,c] is final (set by its owner)
+//   sub[c][s]    sub-step s of the diagonal factor of column block c is published (potf2.cuh)
+//   xf[c][s]     column group s of L[c+1,c] is final (set by the owner of tile (c+1, c))
+// Owner of (r, c): accumulates A[r,c] - sum_{c'<c} L[r,c'] L[c,c']^T as the operand tiles become final
+// (left-looking, DMMA), then solves against L_cc following the sub-steps (off-diagonal) or factors the tile
+// (diagonal).  A diagonal owner takes its LAST update, L[c,c-1] L[c,c-1]^T, 32 columns at a time as its neighbour
+// publishes them, so potf2(c) starts a few microseconds after potf2(c-1) ends: no launch boundary, no trailing
+// kernel, no relay buffer on the chain.  This is what the reference's shipped configurations need (N <= 1.3 k,
+// 10^4 optimiser steps per fit): the step time there is the latency of this chain.
+struct SmallArgs {
+  double* A;
+  double* W;
+  int ld, nbt;
+  int32_t* info;
+  int* done;   // [nbt][nbt]
+  int* sub;    // [nbt][4]
+  int* xf;     // [nbt][4]
+};
+
+__device__ __forceinline__ void wait_flag(int* f) {
+  if (threadIdx.x == 0) {
+    while (atomicAdd(f, 0) == 0) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_small_kernel(SmallArgs p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int nbt = p.nbt, ld = p.ld;
+  int idx = blockIdx.x, c = 0;            // column-major enumeration: earlier columns get the lower block ids
+  while (idx >= nbt - c) {
+    idx -= nbt - c;
+    ++c;
+  }
+  const int r = c + idx;
+  const int m0 = r * BM, n0 = c * BN;
+  const bool diag = r == c;
+  double* sT = smem;
+
+  double acc[8][4][2];                    // -(tile): tile = A - sum L L^T
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi) {
+    const int row = m0 + wm * 64 + mi * 8 + lr;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int col = n0 + wn * 32 + ni * 8 + lk * 2;
+      const double2 v = *reinterpret_cast<const double2*>(p.A + (size_t)row * ld + col);
+      acc[mi][ni][0] = -v.x;
+      acc[mi][ni][1] = -v.y;
+    }
+  }
+  const int c_hi = (diag && c >= 1) ? c - 1 : c;   // a diagonal owner takes panel c-1 progressively (below)
+  for (int cp = 0; cp < c_hi; ++cp) {
+    wait_flag(p.done + r * nbt + cp);
+    if (!diag) wait_flag(p.done + c * nbt + cp);
+    gemm_mainloop<KMAJOR, KMAJOR>(acc, p.A, ld, p.A, ld, m0, n0, cp * BN, (cp + 1) * BN, smem);
+  }
+  if (diag && c >= 1) {
+    double* sX = smem;                    // [128][DLD] column group of L[c,c-1]
+    const double* Lrow = p.A + (size_t)m0 * ld + (size_t)(c - 1) * BN;
+    for (int sb = 0; sb < 4; ++sb) {
+      wait_flag(p.xf + (c - 1) * 4 + sb);
+      for (int q = tid; q < PB * SB; q += GEMM_THREADS) {
+        const int rr = q >> 5, cc = q & 31;
+        sX[rr * DLD + cc] = __ldcg(Lrow + (size_t)rr * ld + sb * SB + cc);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < SB; k += 4) {
+        double af[8], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi) af[mi] = sX[(wm * 64 + mi * 8 + lr) * DLD + k + lk];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = sX[(wn * 32 + ni * 8 + lr) * DLD + k + lk];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+      }
+      __syncthreads();                    // sX is refilled by the next sub-step
+    }
+  }
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi) {
+    const int rr = wm * 64 + mi * 8 + lr;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int cc = wn * 32 + ni * 8 + lk * 2;
+      double2 v = make_double2(-acc[mi][ni][0], -acc[mi][ni][1]);
+      if (diag) {
+        if (cc > rr) v.x = 0.0;
+        if (cc + 1 > rr) v.y = 0.0;
+      }
+      *reinterpret_cast<double2*>(&sT[rr * PLD + cc]) = v;
+    }
+  }
+  __syncthreads();
+  double* Ab = p.A + (size_t)m0 * ld + n0;
+  if (diag) {
+    double* Wb = p.W + (size_t)m0 * ld + n0;
+    long long* dbg = nullptr;
+    potf2_factor_invert(smem, m0, p.info, dbg, Potf2Publish{Ab, Wb, ld, p.sub + c * 4}, false);
+    return;
+  }
+  stepwise_solve<false>(smem, p.A, p.W, ld, n0, p.sub + c * 4, Ab, (r == c + 1) ? p.xf + c * 4 : nullptr, nullptr);
+  if (tid == 0) {   // stepwise_solve ended with a barrier: every store of the tile is ordered before this fence
+    __threadfence();
+    atomicExch(p.done + r * nbt + c, 1);
+  }
 }
 
 // inv(L_kk) for every diagonal block at once (one CTA each): L_kk and its four 32x32 diagonal inverses, left in
@@ -466,6 +606,18 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
   cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
   cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
   cudaFuncSetAttribute(diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM);
+  {
+    const char* sm = getenv("DISTBO_POTRF_SMALL");
+    int coop = 0, per_sm = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaFuncSetAttribute(potrf_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, potrf_small_kernel, GEMM_THREADS, PANEL_SMEM);
+    const int ctas = nb * (nb + 1) / 2;
+    p->small_ok = !(sm && sm[0] == '0') && coop && nb <= 16 && ctas <= per_sm * p->sms;
+    if (p->small_ok && cudaMalloc(&p->d_small_flags, (size_t)(nb * nb + 8 * nb) * sizeof(int)) != cudaSuccess)
+      p->small_ok = false;
+  }
   *plan_out = p;
   return DISTBO_OK;
 }
@@ -482,6 +634,7 @@ extern "C" int distbo_plan_destroy(void* plan) {
   if (p->d_tiles) cudaFree(p->d_tiles);
   if (p->d_flags) cudaFree(p->d_flags);
   if (p->d_relay) cudaFree(p->d_relay);
+  if (p->d_small_flags) cudaFree(p->d_small_flags);
   delete p;
   return DISTBO_OK;
 }
@@ -492,6 +645,18 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
   cudaStream_t U = (cudaStream_t)stream;
   const int n = p->n, nb = p->nb;
   DB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), U));
+
+  if (p->small_ok) {
+    DB_CUDA(cudaMemsetAsync(p->d_small_flags, 0, (size_t)(nb * nb + 8 * nb) * sizeof(int), U));
+    SmallArgs sa{A, W, n, nb, info, p->d_small_flags, p->d_small_flags + nb * nb, p->d_small_flags + nb * nb + 4 * nb};
+    // Plain launch: a CTA only ever waits for CTAs with a LOWER block index (earlier column, or the diagonal of
+    // its own column), blocks are dispatched in index order and all nb (nb + 1) / 2 <= 136 of them fit on the
+    // device at once, so the waits cannot deadlock; the cooperative-launch API gave the same guarantee but made
+    // CUDA-graph replays of the training step ~1 ms slower per launch.
+    potrf_small_kernel<<<nb * (nb + 1) / 2, GEMM_THREADS, PANEL_SMEM, U>>>(sa);
+    DB_CHECK_LAUNCH();
+    return DISTBO_OK;
+  }
 
   {
     DB_CUDA(cudaMemsetAsync(p->d_flags, 0, (size_t)nb * NFLAG * sizeof(int), U));
