@@ -661,9 +661,12 @@ extern "C" int distbo_embed_bwd_f64(const double* X, const double* Y, const int3
   DB_CUDA(cudaFuncSetAttribute(embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   embed_chunk_table_kernel<<<1, 256, 0, st>>>(seg_off, T, 32 * EmbT<double>::RM, w.chunk_first, w.chunk_ds, w.chunk_row);
   DB_CHECK_LAUNCH();
-  embed_bwd_kernel<<<EMB_BWD_GRID, emb_threads(hx, hy, y_mode), smem, st>>>(b);
+  // no more CTAs than chunks (upper bound S / 64 + T): small problems reduce fewer partials
+  const int64_t mc = max_chunks<double>(S, T);
+  const int grid = (int)(mc < EMB_BWD_GRID ? mc : EMB_BWD_GRID);
+  embed_bwd_kernel<<<grid, emb_threads(hx, hy, y_mode), smem, st>>>(b);
   DB_CHECK_LAUNCH();
-  embed_bwd_reduce_kernel<<<(b.nparams + 255) / 256, 256, 0, st>>>(b.gpartial, EMB_BWD_GRID, b.nparams, nx, dx * hx, hx,
+  embed_bwd_reduce_kernel<<<(b.nparams + 255) / 256, 256, 0, st>>>(b.gpartial, grid, b.nparams, nx, dx * hx, hx,
                                                                    gW1x, gb1x, gW2x, dy * hy, hy, gW1y, gb1y, gW2y);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
