@@ -254,13 +254,13 @@ def run_cuda(args):
     # ---------------- fit: loss + full gradient + Adam, one GPU (rank 0), replicas elsewhere idle
     fit = {}
     if rank == 0:
-        # >= 10 untimed epochs (first eager, second captured as a CUDA graph, the rest replays) so that the
-        # clocks have ramped, then >= 10 timed graph replays with no host synchronisation in between
-        gp.maximise_likhd(work["theta"], work["y"][:, None], **fit_kwargs(work, max(Wm, 10), args.lkh_var))
+        # >= 20 untimed epochs (first eager, second captured as a CUDA graph, the rest replays) so that the
+        # clocks have ramped, then >= 20 timed graph replays with no host synchronisation in between
+        gp.maximise_likhd(work["theta"], work["y"][:, None], **fit_kwargs(work, max(Wm, 20), args.lkh_var))
         torch.cuda.synchronize()
         lib.distbo_launch_count(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kf = max(K, 10)
+        kf = max(K, 20)
         e0.record()
         for _ in range(kf):
             gp.run_epoch()
