@@ -25,12 +25,14 @@ namespace db {
 constexpr int EMB_KC = 64;         // input columns staged per slice
 constexpr int EMB_HMAX = 32;       // max hidden width
 constexpr int EMB_PMAX = 16;       // max feature-map output width (p, q)
-constexpr int EMB_MAXWARPS = EMB_HMAX / 4;
+constexpr int EMB_RSPLIT = 2;       // a chunk's rows are split over this many warp groups (more warps per CTA)
+constexpr int EMB_MAXWARPS = EMB_RSPLIT * EMB_HMAX / 4;
 constexpr int EMB_BWD_GRID = 296;  // persistent CTAs of the backward kernel (2 per SM)
 
 template <typename T> struct EmbT;
 template <> struct EmbT<float> {
-  static constexpr int RM = 4;            // rows per thread -> 128-row chunks
+  static constexpr int RM = 4;            // 32 * RM = 128-row chunks
+  static constexpr int RT = RM / EMB_RSPLIT;   // rows per thread
   static constexpr int XS = EMB_KC + 4;   // 272 B = 17 x 16 B
   __device__ static float tanh_(float x) { return tanhf(x); }
   __device__ static void load4(const float* p, float (&v)[4]) {
@@ -40,6 +42,7 @@ template <> struct EmbT<float> {
 };
 template <> struct EmbT<double> {
   static constexpr int RM = 2;            // 64-row chunks
+  static constexpr int RT = RM / EMB_RSPLIT;
   static constexpr int XS = EMB_KC + 2;   // 528 B = 33 x 16 B
   __device__ static double tanh_(double x) { return tanh(x); }
   __device__ static void load4(const double* p, double (&v)[4]) {
@@ -177,20 +180,20 @@ __device__ __forceinline__ void stage_tile_async(const T* __restrict__ Xg, int n
 
 // z[m][c] += sum_k x[rg + 32 m][k] * W1[k0 + k][4 hg + c] over the staged slice.
 template <typename T>
-__device__ __forceinline__ void layer1_slice(const T* sX, const T* sW1, int hp, int k0, int kc, int rg, int hg,
-                                             T (&z)[EmbT<T>::RM][4]) {
-  constexpr int RM = EmbT<T>::RM, XS = EmbT<T>::XS;
+__device__ __forceinline__ void layer1_slice(const T* sX, const T* sW1, int hp, int k0, int kc, int row_base, int hg,
+                                             T (&z)[EmbT<T>::RT][4]) {
+  constexpr int RT = EmbT<T>::RT, XS = EmbT<T>::XS;
   const int kcp = round_up_i(kc, 4);
   for (int k = 0; k < kcp; k += 4) {
-    T x[RM][4];
+    T x[RT][4];
 #pragma unroll
-    for (int m = 0; m < RM; ++m) EmbT<T>::load4(sX + (rg + 32 * m) * XS + k, x[m]);
+    for (int m = 0; m < RT; ++m) EmbT<T>::load4(sX + (row_base + 32 * m) * XS + k, x[m]);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       T w[4];
       EmbT<T>::load4(sW1 + (size_t)(k0 + k + kk) * hp + 4 * hg, w);
 #pragma unroll
-      for (int m = 0; m < RM; ++m)
+      for (int m = 0; m < RT; ++m)
 #pragma unroll
         for (int c = 0; c < 4; ++c) z[m][c] += x[m][kk] * w[c];
     }
@@ -203,12 +206,15 @@ __device__ __forceinline__ void layer1_slice(const T* sX, const T* sW1, int hp, 
 template <typename T>
 __device__ __forceinline__ void hidden_forward(const T* __restrict__ Xg, int n, int din, int h, int hp, const T* sW1,
                                                const T* sb1, T* sX, T* sH) {
-  constexpr int RM = EmbT<T>::RM, TILE = 32 * EmbT<T>::RM * EmbT<T>::XS;
-  const int rg = threadIdx.x & 31, hg = threadIdx.x >> 5;
+  constexpr int RT = EmbT<T>::RT, TILE = 32 * EmbT<T>::RM * EmbT<T>::XS;
+  // warp -> (hidden group hg, row split rs); lane = row group: rows row_base + 32 m, m < RT
+  const int nhg = (int)(blockDim.x >> 5) / EMB_RSPLIT;
+  const int warp = threadIdx.x >> 5, hg = warp % nhg, rs = warp / nhg;
+  const int row_base = (threadIdx.x & 31) + 32 * RT * rs;
   const bool active = 4 * hg < hp;
-  T z[RM][4];
+  T z[RT][4];
 #pragma unroll
-  for (int m = 0; m < RM; ++m)
+  for (int m = 0; m < RT; ++m)
 #pragma unroll
     for (int c = 0; c < 4; ++c) z[m][c] = active ? sb1[4 * hg + c] : (T)0;
   __syncthreads();                                   // both tiles are free (previous users are done)
@@ -221,14 +227,14 @@ __device__ __forceinline__ void hidden_forward(const T* __restrict__ Xg, int n, 
     cp_async_commit();
     cp_async_wait<1>();                              // slice k0 has landed (the newest group may still fly)
     __syncthreads();
-    if (active) layer1_slice<T>(sX + buf * TILE, sW1, hp, k0, kc, rg, hg, z);
+    if (active) layer1_slice<T>(sX + buf * TILE, sW1, hp, k0, kc, row_base, hg, z);
     __syncthreads();                                 // tile `buf` may be refilled two slices later
   }
   cp_async_wait<0>();
   if (active) {
 #pragma unroll
-    for (int m = 0; m < RM; ++m) {
-      const int r = rg + 32 * m;
+    for (int m = 0; m < RT; ++m) {
+      const int r = row_base + 32 * m;
 #pragma unroll
       for (int c = 0; c < 4; ++c) sH[r * hp + 4 * hg + c] = (r < n && 4 * hg + c < h) ? EmbT<T>::tanh_(z[m][c]) : (T)0;
     }
@@ -560,8 +566,8 @@ static int check_args(const EmbedArgs<T>& a, int64_t S) {
 
 inline int emb_threads(int hx, int hy, int y_mode) {
   const int h = (y_mode == 1 && hy > hx) ? hy : hx;
-  int warps = (h + 3) / 4;
-  if (warps < 4) warps = 4;   // the generic (strided) phases still want a full CTA
+  int warps = EMB_RSPLIT * ((h + 3) / 4);   // (hidden groups of 4) x (row splits)
+  if (warps < 4) warps = 4;                 // the generic (strided) phases still want a full CTA
   return 32 * warps;
 }
 
