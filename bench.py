@@ -22,7 +22,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+if "reference" in sys.argv:
+    # CPU arm: the BLAS thread pools are sized when numpy / scipy are first imported, and torchrun exports
+    # OMP_NUM_THREADS=1 - give the reference every host core before those imports happen
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -174,6 +180,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    try:   # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host core back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     m = args.candidates
     m_s = min(m, args.cpu_sample)
     work = make_workload(N_OBS, m_s, ROWS)
