@@ -67,13 +67,24 @@ struct EmbedArgs {
   const int32_t* chunk_ds;     // [max_chunks] dataset of chunk c
   const int32_t* chunk_row;    // [max_chunks] first row of chunk c (global row index)
   const int32_t* chunk_first;  // [T+1] first chunk of dataset t
-  T* partial;                  // [max_chunks][pout]
+  T* partial;                  // [max_chunks][psum]
+  const T* log_reg;            // 'concat' only: log of the ridge lambda
+  double* raw;                 // 'concat' only: [T][psum] per-dataset sums kept for the backward pass
 };
 
 __host__ __device__ inline int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
-__host__ __device__ inline int gq_of(int y_mode, int q, int dy) { return y_mode == 0 ? 1 : (y_mode == 1 ? q : dy); }
+// y_mode: 0 'none' (phi_x only), 1 'joint' regression (y-net), 2 classification (one-hot y),
+//         3 'concat' regression: marginal mean(phi_x) (+) conditional embedding operator (distbo_net.py:49-89)
+__host__ __device__ inline bool has_ynet(int y_mode) { return y_mode == 1 || y_mode == 3; }
+__host__ __device__ inline int gq_of(int y_mode, int q, int dy) { return y_mode == 0 ? 1 : (has_ynet(y_mode) ? q : dy); }
+// width of the embedding row
 __host__ __device__ inline int pout_of(int y_mode, int p, int q, int dy) {
+  if (y_mode == 3) return p + q * p;
   return y_mode == 0 ? p : p * gq_of(y_mode, q, dy) + (y_mode == 2 ? dy : 0);
+}
+// number of pooled sums per chunk ('concat': sum phi_x [p], Psi^T Phi [q][p], Phi^T Phi [p][p])
+__host__ __device__ inline int psum_of(int y_mode, int p, int q, int dy) {
+  return y_mode == 3 ? p + q * p + p * p : pout_of(y_mode, p, q, dy);
 }
 
 // ------------------------------------------------------------------ chunk table
@@ -276,7 +287,7 @@ __host__ __device__ inline EmbSmem<T> emb_layout(T* base, int dx, int dy, int hx
   constexpr int ROWS = 32 * EmbT<T>::RM, XS = EmbT<T>::XS;
   EmbSmem<T> s;
   s.hpx = round_up_i(hx, 4);
-  s.hpy = (y_mode == 1) ? round_up_i(hy, 4) : 0;
+  s.hpy = has_ynet(y_mode) ? round_up_i(hy, 4) : 0;
   s.gq = gq_of(y_mode, q, dy);
   s.fsx = p + 1;
   s.fsy = s.gq + 1;
@@ -286,9 +297,9 @@ __host__ __device__ inline EmbSmem<T> emb_layout(T* base, int dx, int dy, int hx
   s.sW1x = take((size_t)round_up_i(dx, 4) * s.hpx);
   s.sb1x = take(s.hpx);
   s.sW2x = take((size_t)hx * p);
-  s.sW1y = take((y_mode == 1) ? (size_t)round_up_i(dy, 4) * s.hpy : 0);
+  s.sW1y = take(has_ynet(y_mode) ? (size_t)round_up_i(dy, 4) * s.hpy : 0);
   s.sb1y = take(s.hpy);
-  s.sW2y = take((y_mode == 1) ? (size_t)hy * q : 0);
+  s.sW2y = take(has_ynet(y_mode) ? (size_t)hy * q : 0);
   s.sX = take((size_t)2 * ROWS * XS);   // two tiles: double-buffered slices
   s.sHx = take((size_t)ROWS * s.hpx);
   s.sHy = take((size_t)ROWS * s.hpy);
@@ -297,7 +308,7 @@ __host__ __device__ inline EmbSmem<T> emb_layout(T* base, int dx, int dy, int hx
   const int hpm = s.hpx > s.hpy ? s.hpx : s.hpy;
   s.sDZ = take(backward ? (size_t)ROWS * hpm : 0);
   s.sDF = take(backward ? (size_t)ROWS * s.dfs : 0);
-  const size_t nparams = (size_t)dx * hx + hx + (size_t)hx * p + ((y_mode == 1) ? (size_t)dy * hy + hy + (size_t)hy * q : 0);
+  const size_t nparams = (size_t)dx * hx + hx + (size_t)hx * p + (has_ynet(y_mode) ? (size_t)dy * hy + hy + (size_t)hy * q : 0);
   s.sG = take(backward ? nparams : 0);
   s.elems = off;
   return s;
@@ -309,7 +320,7 @@ __device__ __forceinline__ void chunk_features(const EmbedArgs<T>& a, const EmbS
   constexpr int ROWS = 32 * EmbT<T>::RM;
   hidden_forward<T>(a.X + (size_t)row0 * a.dx, n, a.dx, a.hx, s.hpx, s.sW1x, s.sb1x, s.sX, s.sHx);
   output_forward<T>(s.sHx, s.sW2x, a.hx, s.hpx, a.p, s.sFx, s.fsx);
-  if (a.y_mode == 1) {
+  if (has_ynet(a.y_mode)) {
     hidden_forward<T>(a.Y + (size_t)row0 * a.dy, n, a.dy, a.hy, s.hpy, s.sW1y, s.sb1y, s.sX, s.sHy);
     output_forward<T>(s.sHy, s.sW2y, a.hy, s.hpy, a.q, s.sFy, s.fsy);
   } else {
@@ -330,50 +341,133 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_fwd_kernel(EmbedArgs<
   constexpr int ROWS = 32 * EmbT<T>::RM;
   const EmbSmem<T> s = emb_layout<T>(reinterpret_cast<T*>(smem_raw), a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, false);
   load_net<T>(a.W1x, a.b1x, a.W2x, a.dx, a.hx, a.p, s.hpx, s.sW1x, s.sb1x, s.sW2x);
-  if (a.y_mode == 1) load_net<T>(a.W1y, a.b1y, a.W2y, a.dy, a.hy, a.q, s.hpy, s.sW1y, s.sb1y, s.sW2y);
+  if (has_ynet(a.y_mode)) load_net<T>(a.W1y, a.b1y, a.W2y, a.dy, a.hy, a.q, s.hpy, s.sW1y, s.sb1y, s.sW2y);
   __syncthreads();   // weights (incl. the biases read right below) are visible to every thread
   const int n_chunks = a.chunk_first[a.T_];
-  const int pout = pout_of(a.y_mode, a.p, a.q, a.dy);
+  const int psum = psum_of(a.y_mode, a.p, a.q, a.dy);
   const int gq = s.gq;
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const int t = a.chunk_ds[c], row0 = a.chunk_row[c];
     const int n = min(ROWS, a.seg_off[t + 1] - row0);
     chunk_features<T>(a, s, row0, n);
-    for (int o = threadIdx.x; o < pout; o += blockDim.x) {
+    for (int o = threadIdx.x; o < psum; o += blockDim.x) {
+      // every pooled sum is sum_rows u[r] * v[r] of two feature columns (v = 1 for plain sums)
+      const T* u;
+      const T* v = nullptr;
+      int us, vs = 0;
+      if (a.y_mode == 3) {
+        if (o < a.p) {                            // sum phi_x[i]
+          u = s.sFx + o; us = s.fsx;
+        } else if (o < a.p + a.q * a.p) {         // (Psi^T Phi)[j][i]
+          const int j = (o - a.p) / a.p, i = (o - a.p) - j * a.p;
+          u = s.sFy + j; us = s.fsy; v = s.sFx + i; vs = s.fsx;
+        } else {                                  // (Phi^T Phi)[i][i2]
+          const int o2 = o - a.p - a.q * a.p, i = o2 / a.p, i2 = o2 - i * a.p;
+          u = s.sFx + i; us = s.fsx; v = s.sFx + i2; vs = s.fsx;
+        }
+      } else if (o < a.p * gq) {
+        const int i = o / gq, j = o - i * gq;     // row-major flatten i*q + j (distbo_net.py:40-42)
+        u = s.sFx + i; us = s.fsx; v = s.sFy + j; vs = s.fsy;
+      } else {
+        u = s.sFy + (o - a.p * gq); us = s.fsy;   // class ratios: mean of y (distbo_net.py:45-48)
+      }
       T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;   // four interleaved row chains, combined in a fixed order
-      if (o < a.p * gq) {
-        const int i = o / gq, j = o - i * gq;   // row-major flatten i*q + j (distbo_net.py:40-42)
+      if (v) {
         for (int r = 0; r < ROWS; r += 4) {
-          a0 += s.sFx[r * s.fsx + i] * s.sFy[r * s.fsy + j];
-          a1 += s.sFx[(r + 1) * s.fsx + i] * s.sFy[(r + 1) * s.fsy + j];
-          a2 += s.sFx[(r + 2) * s.fsx + i] * s.sFy[(r + 2) * s.fsy + j];
-          a3 += s.sFx[(r + 3) * s.fsx + i] * s.sFy[(r + 3) * s.fsy + j];
+          a0 += u[r * us] * v[r * vs];
+          a1 += u[(r + 1) * us] * v[(r + 1) * vs];
+          a2 += u[(r + 2) * us] * v[(r + 2) * vs];
+          a3 += u[(r + 3) * us] * v[(r + 3) * vs];
         }
       } else {
-        const int j = o - a.p * gq;             // class ratios: mean of y (distbo_net.py:45-48)
         for (int r = 0; r < ROWS; r += 4) {
-          a0 += s.sFy[r * s.fsy + j];
-          a1 += s.sFy[(r + 1) * s.fsy + j];
-          a2 += s.sFy[(r + 2) * s.fsy + j];
-          a3 += s.sFy[(r + 3) * s.fsy + j];
+          a0 += u[r * us];
+          a1 += u[(r + 1) * us];
+          a2 += u[(r + 2) * us];
+          a3 += u[(r + 3) * us];
         }
       }
-      a.partial[(size_t)c * pout + o] = (a0 + a1) + (a2 + a3);
+      a.partial[(size_t)c * psum + o] = (a0 + a1) + (a2 + a3);
     }
   }
+}
+
+// Small dense helpers for the conditional-embedding operator (p <= 16): in-place inverse of an SPD matrix.
+__device__ inline void spd_inverse(double* A, int n, double* tmp) {
+  // Cholesky A = L L^T (lower, in place), then A^-1 = L^-T L^-1
+  for (int j = 0; j < n; ++j) {
+    double d = A[j * n + j];
+    for (int k = 0; k < j; ++k) d -= A[j * n + k] * A[j * n + k];
+    d = sqrt(d);
+    A[j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double v = A[i * n + j];
+      for (int k = 0; k < j; ++k) v -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = v / d;
+    }
+  }
+  for (int c = 0; c < n; ++c)            // tmp = L^-1 (lower)
+    for (int i = 0; i < n; ++i) {
+      double v = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) v -= A[i * n + k] * tmp[k * n + c];
+      tmp[i * n + c] = (i >= c) ? v / A[i * n + i] : 0.0;
+    }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double v = 0.0;
+      for (int k = (i > j ? i : j); k < n; ++k) v += tmp[k * n + i] * tmp[k * n + j];
+      A[i * n + j] = v;
+    }
 }
 
 // E[t][o] = (sum over the dataset's chunks, in chunk order) / len
 template <typename T>
 __global__ void __launch_bounds__(128) embed_fwd_reduce_kernel(EmbedArgs<T> a) {
+  __shared__ double R[EMB_PMAX + 2 * EMB_PMAX * EMB_PMAX];
+  __shared__ double Inv[EMB_PMAX * EMB_PMAX], Tmp[EMB_PMAX * EMB_PMAX];
   const int t = blockIdx.x;
-  const int pout = pout_of(a.y_mode, a.p, a.q, a.dy);
+  const int psum = psum_of(a.y_mode, a.p, a.q, a.dy);
   const int c0 = a.chunk_first[t], c1 = a.chunk_first[t + 1];
-  const T inv = (T)1 / (T)(a.seg_off[t + 1] - a.seg_off[t]);
-  for (int o = threadIdx.x; o < pout; o += 128) {
+  const int len = a.seg_off[t + 1] - a.seg_off[t];
+  if (a.y_mode != 3) {
+    const T inv = (T)1 / (T)len;
+    for (int o = threadIdx.x; o < psum; o += 128) {
+      T acc = (T)0;
+      for (int c = c0; c < c1; ++c) acc += a.partial[(size_t)c * psum + o];
+      a.E[(size_t)t * a.lde + o] = acc * inv;
+    }
+    return;
+  }
+  // 'concat': E[t] = [ mean(phi_x) | vec(C) ],  C = lambda^-1 (M - M (G + lambda I)^-1 G) = M (G + lambda I)^-1
+  // with M = Psi^T Phi [q][p], G = Phi^T Phi [p][p] (the reference's form loses digits to cancellation; the
+  // product form is the same matrix).  The small algebra runs in fp64 whatever T is.
+  const int p = a.p, q = a.q;
+  for (int o = threadIdx.x; o < psum; o += 128) {
     T acc = (T)0;
-    for (int c = c0; c < c1; ++c) acc += a.partial[(size_t)c * pout + o];
-    a.E[(size_t)t * a.lde + o] = acc * inv;
+    for (int c = c0; c < c1; ++c) acc += a.partial[(size_t)c * psum + o];
+    R[o] = (double)acc;
+    if (a.raw) a.raw[(size_t)t * psum + o] = (double)acc;
+  }
+  __syncthreads();
+  const double lam = exp((double)*a.log_reg);
+  if (threadIdx.x == 0) {
+    const double* G = R + p + q * p;
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j < p; ++j) Inv[i * p + j] = G[i * p + j] + (i == j ? lam : 0.0);
+    spd_inverse(Inv, p, Tmp);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < p + q * p; o += 128) {
+    double v;
+    if (o < p) {
+      v = R[o] / (double)len;
+    } else {
+      const int j = (o - p) / p, i = (o - p) - j * p;
+      const double* M = R + p;
+      v = 0.0;
+      for (int k = 0; k < p; ++k) v += M[j * p + k] * Inv[k * p + i];
+    }
+    a.E[(size_t)t * a.lde + o] = (T)v;
   }
 }
 
@@ -383,7 +477,87 @@ struct EmbedBwdArgs {
   const double* dE;
   double* gpartial;  // [EMB_BWD_GRID][nparams]
   int nparams;
+  const double* coef;  // 'concat' only: [T][coef_len] per-dataset upstream maps (embed_concat_bwd_prep_kernel)
 };
+
+// 'concat' backward, per dataset (one CTA): from dE[t] = [dmean | dC] and the saved sums (M, G) form the linear
+// maps of the per-row upstream gradients
+//   d phi_x[r] = ax + Axy psi[r] + Axx phi_x[r],   d phi_y[r] = Ayx phi_x[r]
+// with C = M Inv, Inv = (G + lambda I)^-1:  dM = dC Inv,  dA = -Inv (M^T dC) Inv,
+//   Axy = dM^T [p][q], Axx = dA + dA^T [p][p], ax = dmean / len [p], Ayx = dM [q][p],  dlog_reg = lambda tr(dA).
+// coef layout per dataset: Axy | Axx | ax | Ayx | dlog_reg   (p q + p p + p + q p + 1 doubles)
+__host__ __device__ inline int coef_len(int p, int q) { return p * q + p * p + p + q * p + 1; }
+
+__global__ void __launch_bounds__(128) embed_concat_bwd_prep_kernel(EmbedArgs<double> a, const double* __restrict__ dE,
+                                                                    double* __restrict__ coef) {
+  __shared__ double Inv[EMB_PMAX * EMB_PMAX], Tmp[EMB_PMAX * EMB_PMAX], Q[EMB_PMAX * EMB_PMAX];
+  __shared__ double dM[EMB_PMAX * EMB_PMAX], dA[EMB_PMAX * EMB_PMAX];
+  const int t = blockIdx.x, p = a.p, q = a.q, tid = threadIdx.x;
+  const int psum = psum_of(3, p, q, a.dy);
+  const double* R = a.raw + (size_t)t * psum;
+  const double* M = R + p;
+  const double* G = R + p + q * p;
+  const double* dmean = dE + (size_t)t * a.lde;
+  const double* dC = dmean + p;
+  const double lam = exp(*a.log_reg);
+  const int len = a.seg_off[t + 1] - a.seg_off[t];
+  if (tid == 0) {
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j < p; ++j) Inv[i * p + j] = G[i * p + j] + (i == j ? lam : 0.0);
+    spd_inverse(Inv, p, Tmp);
+  }
+  __syncthreads();
+  for (int o = tid; o < q * p; o += 128) {          // dM = dC Inv
+    const int j = o / p, i = o - j * p;
+    double v = 0.0;
+    for (int k = 0; k < p; ++k) v += dC[j * p + k] * Inv[k * p + i];
+    dM[o] = v;
+  }
+  for (int o = tid; o < p * p; o += 128) {          // Q = M^T dC
+    const int i = o / p, i2 = o - i * p;
+    double v = 0.0;
+    for (int j = 0; j < q; ++j) v += M[j * p + i] * dC[j * p + i2];
+    Q[o] = v;
+  }
+  __syncthreads();
+  for (int o = tid; o < p * p; o += 128) {          // Tmp = Inv Q
+    const int i = o / p, i2 = o - i * p;
+    double v = 0.0;
+    for (int k = 0; k < p; ++k) v += Inv[i * p + k] * Q[k * p + i2];
+    Tmp[o] = v;
+  }
+  __syncthreads();
+  for (int o = tid; o < p * p; o += 128) {          // dA = -Tmp Inv
+    const int i = o / p, i2 = o - i * p;
+    double v = 0.0;
+    for (int k = 0; k < p; ++k) v += Tmp[i * p + k] * Inv[k * p + i2];
+    dA[o] = -v;
+  }
+  __syncthreads();
+  double* out = coef + (size_t)t * coef_len(p, q);
+  for (int o = tid; o < p * q; o += 128) {          // Axy[i][j] = dM[j][i]
+    const int i = o / q, j = o - i * q;
+    out[o] = dM[j * p + i];
+  }
+  for (int o = tid; o < p * p; o += 128) {          // Axx = dA + dA^T
+    const int i = o / p, i2 = o - i * p;
+    out[p * q + o] = dA[i * p + i2] + dA[i2 * p + i];
+  }
+  for (int o = tid; o < p; o += 128) out[p * q + p * p + o] = dmean[o] / (double)len;
+  for (int o = tid; o < q * p; o += 128) out[p * q + p * p + p + o] = dM[o];
+  if (tid == 0) {
+    double tr = 0.0;
+    for (int i = 0; i < p; ++i) tr += dA[i * p + i];
+    out[p * q + p * p + p + q * p] = lam * tr;
+  }
+}
+
+__global__ void embed_concat_logreg_kernel(const double* __restrict__ coef, int T, int clen, double* __restrict__ g_log_reg) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0.0;
+  for (int t = 0; t < T; ++t) s += coef[(size_t)t * clen + clen - 1];
+  *g_log_reg = s;
+}
 
 __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdArgs b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -392,12 +566,12 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
   const EmbedArgs<T>& a = b.f;
   const EmbSmem<T> s = emb_layout<T>(reinterpret_cast<T*>(smem_raw), a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, true);
   load_net<T>(a.W1x, a.b1x, a.W2x, a.dx, a.hx, a.p, s.hpx, s.sW1x, s.sb1x, s.sW2x);
-  if (a.y_mode == 1) load_net<T>(a.W1y, a.b1y, a.W2y, a.dy, a.hy, a.q, s.hpy, s.sW1y, s.sb1y, s.sW2y);
+  if (has_ynet(a.y_mode)) load_net<T>(a.W1y, a.b1y, a.W2y, a.dy, a.hy, a.q, s.hpy, s.sW1y, s.sb1y, s.sW2y);
   for (int i = threadIdx.x; i < b.nparams; i += blockDim.x) s.sG[i] = 0.0;   // owner-exclusive accumulators
   __syncthreads();
   const int n_chunks = a.chunk_first[a.T_];
   const int gq = s.gq, dfs = s.dfs;
-  const int nets = (a.y_mode == 1) ? 2 : 1;
+  const int nets = has_ynet(a.y_mode) ? 2 : 1;
   const int nthr = blockDim.x;
   const int nx = a.dx * a.hx + a.hx + a.hx * a.p;
 
@@ -419,12 +593,24 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
         const int r = idx / po, i = idx - r * po;
         double v = 0.0;
         if (r < n) {
-          if (net == 0) {
-            for (int j = 0; j < gq; ++j) v += de[i * gq + j] * s.sFy[r * s.fsy + j];
+          if (a.y_mode == 3) {
+            const double* cf = b.coef + (size_t)t * coef_len(a.p, a.q);
+            if (net == 0) {
+              v = cf[a.p * a.q + a.p * a.p + i];
+              for (int j = 0; j < a.q; ++j) v += cf[i * a.q + j] * s.sFy[r * s.fsy + j];
+              for (int k = 0; k < a.p; ++k) v += cf[a.p * a.q + i * a.p + k] * s.sFx[r * s.fsx + k];
+            } else {
+              const double* Ayx = cf + a.p * a.q + a.p * a.p + a.p;
+              for (int k = 0; k < a.p; ++k) v += Ayx[i * a.p + k] * s.sFx[r * s.fsx + k];
+            }
           } else {
-            for (int k = 0; k < a.p; ++k) v += de[k * gq + i] * s.sFx[r * s.fsx + k];
+            if (net == 0) {
+              for (int j = 0; j < gq; ++j) v += de[i * gq + j] * s.sFy[r * s.fsy + j];
+            } else {
+              for (int k = 0; k < a.p; ++k) v += de[k * gq + i] * s.sFx[r * s.fsx + k];
+            }
+            v *= inv_len;
           }
-          v *= inv_len;
         }
         s.sDF[r * dfs + i] = v;
       }
@@ -555,8 +741,8 @@ static int check_args(const EmbedArgs<T>& a, int64_t S) {
   if (!a.X || !a.seg_off || !a.W1x || !a.b1x || !a.W2x || a.T_ <= 0 || a.dx <= 0 || S <= 0) return DISTBO_EARG;
   if (S > 0x7fffffffLL) return DISTBO_EARG;
   if (a.hx <= 0 || a.hx > EMB_HMAX || a.p <= 0 || a.p > EMB_PMAX) return DISTBO_EARG;
-  if (a.y_mode < 0 || a.y_mode > 2) return DISTBO_EARG;
-  if (a.y_mode == 1 && (!a.Y || !a.W1y || !a.b1y || !a.W2y || a.hy <= 0 || a.hy > EMB_HMAX || a.q <= 0 ||
+  if (a.y_mode < 0 || a.y_mode > 3) return DISTBO_EARG;
+  if (has_ynet(a.y_mode) && (!a.Y || !a.W1y || !a.b1y || !a.W2y || a.hy <= 0 || a.hy > EMB_HMAX || a.q <= 0 ||
                         a.q > EMB_PMAX || a.dy <= 0))
     return DISTBO_EARG;
   if (a.y_mode == 2 && (!a.Y || a.dy <= 0 || a.dy > EMB_PMAX)) return DISTBO_EARG;
@@ -565,7 +751,7 @@ static int check_args(const EmbedArgs<T>& a, int64_t S) {
 }
 
 inline int emb_threads(int hx, int hy, int y_mode) {
-  const int h = (y_mode == 1 && hy > hx) ? hy : hx;
+  const int h = (has_ynet(y_mode) && hy > hx) ? hy : hx;
   int warps = EMB_RSPLIT * ((h + 3) / 4);   // (hidden groups of 4) x (row splits)
   if (warps < 4) warps = 4;                 // the generic (strided) phases still want a full CTA
   return 32 * warps;
@@ -576,7 +762,8 @@ static int embed_fwd_launch(EmbedArgs<T> a, int64_t S, void* workspace, int64_t 
   int rc = check_args(a, S);
   if (rc) return rc;
   if (!a.E || !workspace) return DISTBO_EARG;
-  const int pout = pout_of(a.y_mode, a.p, a.q, a.dy);
+  if (a.y_mode == 3 && !a.log_reg) return DISTBO_EARG;
+  const int pout = psum_of(a.y_mode, a.p, a.q, a.dy);
   const int64_t mc = max_chunks<T>(S, a.T_);
   EmbWs<T> w = ws_layout<T>(workspace, S, a.T_);
   if ((int64_t)(w.header_bytes + (size_t)mc * pout * sizeof(T)) > workspace_bytes) return DISTBO_EARG;
@@ -610,58 +797,71 @@ using namespace db;
 extern "C" int64_t distbo_embed_workspace(int64_t S, int T, int dx, int dy, int hx, int p, int hy, int q, int y_mode,
                                           int elem_bytes, int backward) {
   if (S <= 0 || T <= 0) return 0;
-  const int pout = pout_of(y_mode, p, q, dy);
+  const int pout = psum_of(y_mode, p, q, dy);
   if (elem_bytes == 4 && !backward) {
     EmbWs<float> w = ws_layout<float>(nullptr, S, T);
     return (int64_t)(w.header_bytes + (size_t)max_chunks<float>(S, T) * pout * 4);
   }
   EmbWs<double> w = ws_layout<double>(nullptr, S, T);
   if (!backward) return (int64_t)(w.header_bytes + (size_t)max_chunks<double>(S, T) * pout * 8);
-  const int np = net_elems(dx, hx, p) + (y_mode == 1 ? net_elems(dy, hy, q) : 0);
-  return (int64_t)(w.header_bytes + (size_t)EMB_BWD_GRID * np * 8);
+  const int np = net_elems(dx, hx, p) + (has_ynet(y_mode) ? net_elems(dy, hy, q) : 0);
+  return (int64_t)(w.header_bytes + (size_t)EMB_BWD_GRID * np * 8 + (y_mode == 3 ? (size_t)T * coef_len(p, q) * 8 : 0));
 }
 
 extern "C" int distbo_embed_fwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S,
                                     int dx, int dy, const double* W1x, const double* b1x, const double* W2x, int hx,
                                     int p, const double* W1y, const double* b1y, const double* W2y, int hy, int q,
-                                    int y_mode, double* E, int lde, void* workspace, int64_t workspace_bytes,
-                                    void* stream) {
+                                    int y_mode, const double* log_reg, double* raw_sums, double* E, int lde,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
   EmbedArgs<double> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, E, lde,
-                      nullptr, nullptr, nullptr, nullptr};
+                      nullptr, nullptr, nullptr, nullptr, log_reg, raw_sums};
   return embed_fwd_launch<double>(a, S, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int distbo_embed_fwd_f32(const float* X, const float* Y, const int32_t* seg_off, int T, int64_t S, int dx,
                                     int dy, const float* W1x, const float* b1x, const float* W2x, int hx, int p,
                                     const float* W1y, const float* b1y, const float* W2y, int hy, int q, int y_mode,
-                                    float* E, int lde, void* workspace, int64_t workspace_bytes, void* stream) {
+                                    const float* log_reg, double* raw_sums, float* E, int lde, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
   EmbedArgs<float> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, E, lde,
-                     nullptr, nullptr, nullptr, nullptr};
+                     nullptr, nullptr, nullptr, nullptr, log_reg, raw_sums};
   return embed_fwd_launch<float>(a, S, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S,
                                     int dx, int dy, const double* W1x, const double* b1x, const double* W2x, int hx,
                                     int p, const double* W1y, const double* b1y, const double* W2y, int hy, int q,
-                                    int y_mode, const double* dE, int lde, double* gW1x, double* gb1x, double* gW2x,
-                                    double* gW1y, double* gb1y, double* gW2y, void* workspace,
-                                    int64_t workspace_bytes, void* stream) {
+                                    int y_mode, const double* log_reg, const double* raw_sums, const double* dE, int lde,
+                                    double* gW1x, double* gb1x, double* gW2x, double* gW1y, double* gb1y,
+                                    double* gW2y, double* g_log_reg, void* workspace, int64_t workspace_bytes,
+                                    void* stream) {
   EmbedArgs<double> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, nullptr, lde,
-                      nullptr, nullptr, nullptr, nullptr};
+                      nullptr, nullptr, nullptr, nullptr, log_reg, const_cast<double*>(raw_sums)};
   int rc = check_args(a, S);
   if (rc) return rc;
   if (!dE || !gW1x || !gb1x || !gW2x || !workspace) return DISTBO_EARG;
-  if (y_mode == 1 && (!gW1y || !gb1y || !gW2y)) return DISTBO_EARG;
+  if (has_ynet(y_mode) && (!gW1y || !gb1y || !gW2y)) return DISTBO_EARG;
+  if (y_mode == 3 && (!log_reg || !raw_sums || !g_log_reg)) return DISTBO_EARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nx = net_elems(dx, hx, p), ny = (y_mode == 1) ? net_elems(dy, hy, q) : 0;
+  const int nx = net_elems(dx, hx, p), ny = has_ynet(y_mode) ? net_elems(dy, hy, q) : 0;
   EmbWs<double> w = ws_layout<double>(workspace, S, T);
-  if ((int64_t)(w.header_bytes + (size_t)EMB_BWD_GRID * (nx + ny) * 8) > workspace_bytes) return DISTBO_EARG;
+  const size_t coef_bytes = (y_mode == 3) ? (size_t)T * coef_len(p, q) * 8 : 0;
+  if ((int64_t)(w.header_bytes + (size_t)EMB_BWD_GRID * (nx + ny) * 8 + coef_bytes) > workspace_bytes) return DISTBO_EARG;
   a.chunk_first = w.chunk_first; a.chunk_ds = w.chunk_ds; a.chunk_row = w.chunk_row;
   EmbedBwdArgs b;
   b.f = a;
   b.dE = dE;
   b.gpartial = (double*)w.payload;
   b.nparams = nx + ny;
+  b.coef = nullptr;
+  if (y_mode == 3) {
+    double* coef = b.gpartial + (size_t)EMB_BWD_GRID * (nx + ny);
+    embed_concat_bwd_prep_kernel<<<T, 128, 0, st>>>(a, dE, coef);
+    DB_CHECK_LAUNCH();
+    embed_concat_logreg_kernel<<<1, 32, 0, st>>>(coef, T, coef_len(p, q), g_log_reg);
+    DB_CHECK_LAUNCH();
+    b.coef = coef;
+  }
   const size_t smem = emb_layout<double>((double*)nullptr, dx, dy, hx, p, hy, q, y_mode, true).elems * 8 + 16;
   if (smem > 220 * 1024) return DISTBO_EARG;
   DB_CUDA(cudaFuncSetAttribute(embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -60,7 +60,17 @@ class NetSpec:
             return self.p
         if self.y_mode == 1:
             return self.p * self.q
+        if self.y_mode == 3:                      # 'concat': mean(phi_x) + conditional embedding operator
+            return self.p + self.q * self.p
         return self.p * self.dy + self.dy
+
+    @property
+    def has_ynet(self):
+        return self.y_mode in (1, 3)
+
+    @property
+    def n_sums(self):
+        return self.p + self.q * self.p + self.p * self.p if self.y_mode == 3 else self.pooled_width
 
 
 class ParamStore:
@@ -121,10 +131,12 @@ class GPEngine:
             shapes["weights_x_1"] = (net.dx, net.hx)
             shapes["bias_x_1"] = (net.hx,)
             shapes["weights_x_2"] = (net.hx, net.p)
-            if net.y_mode == 1:
+            if net.has_ynet:
                 shapes["weights_y_1"] = (net.dy, net.hy)
                 shapes["bias_y_1"] = (net.hy,)
                 shapes["weights_y_2"] = (net.hy, net.q)
+            if net.y_mode == 3:
+                shapes["log_reg"] = ()            # train/log_gaus_likelihood.py: log of the ridge lambda, init 0
         if self.P > 0:
             shapes["log_bw_embed"] = (self.P,)
         shapes["log_bw"] = (self.d,)
@@ -140,6 +152,7 @@ class GPEngine:
         self.best_idx = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._score_ws = None
         self._emb_ws = {}
+        self._emb_raw = None
         self.E = None
         self.KE = None
         self.T = 1
@@ -213,10 +226,18 @@ class GPEngine:
         wx1, bx1, wx2 = w("weights_x_1"), w("bias_x_1"), w("weights_x_2")
         wy1, by1, wy2 = w("weights_y_1"), w("bias_y_1"), w("weights_y_2")
         ws = self._embed_workspace(S, Tn, 8 if dtype == torch.float64 else 4, False)
+        log_reg = raw = None
+        if net.y_mode == 3:
+            log_reg = cast(p.view("log_reg"))
+            raw = self._emb_ws.get(("raw", Tn))
+            if raw is None:
+                raw = self._emb_ws[("raw", Tn)] = torch.empty(Tn, net.n_sums, dtype=torch.float64, device=self.dev)
+            self._emb_raw = raw                   # kept for embed_backward on the same batch
         rc = fn(_lib.ptr(X), _lib.ptr(Y), _lib.ptr(seg_off), Tn, S, net.dx, net.dy,
                 _lib.ptr(wx1), _lib.ptr(bx1), _lib.ptr(wx2), net.hx, net.p,
                 _lib.ptr(wy1), _lib.ptr(by1), _lib.ptr(wy2), net.hy, net.q,
-                net.y_mode, _lib.ptr(out), out.stride(0), _lib.ptr(ws), ws.numel(), _stream())
+                net.y_mode, _lib.ptr(log_reg), _lib.ptr(raw), _lib.ptr(out), out.stride(0), _lib.ptr(ws), ws.numel(),
+                _stream())
         _lib.check(rc, "distbo_embed_fwd")
         return out
 
@@ -232,9 +253,10 @@ class GPEngine:
             _lib.ptr(X), _lib.ptr(Y), _lib.ptr(seg_off), Tn, S, net.dx, net.dy,
             w("weights_x_1"), w("bias_x_1"), w("weights_x_2"), net.hx, net.p,
             w("weights_y_1"), w("bias_y_1"), w("weights_y_2"), net.hy, net.q, net.y_mode,
+            w("log_reg"), _lib.ptr(self._emb_raw) if net.y_mode == 3 else None,
             _lib.ptr(dE), dE.stride(0),
             g("weights_x_1"), g("bias_x_1"), g("weights_x_2"),
-            g("weights_y_1"), g("bias_y_1"), g("weights_y_2"),
+            g("weights_y_1"), g("bias_y_1"), g("weights_y_2"), g("log_reg"),
             _lib.ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "distbo_embed_bwd_f64")
 

@@ -81,17 +81,19 @@ class gp_regressor(object):
         P = 0
         weights = {}
         if self.kernel == "dist":
-            if embed_op not in ("none", "joint"):
-                raise NotImplementedError("embed_op %r: only 'none' and 'joint' are on the sm_100a path "
-                                          "(SURVEY section 8f ranks 'concat'/'nn' next)" % (embed_op,))
+            if embed_op not in ("none", "joint", "concat"):
+                raise NotImplementedError("embed_op %r: 'none', 'joint' and 'concat' are on the sm_100a path "
+                                          "(SURVEY section 8f ranks 'nn' next)" % (embed_op,))
             weights.update(init_net_weights(self.in_dim_x, weight_dim_x, "x", self.seed))
             hx, p = int(weight_dim_x[0]), int(weight_dim_x[1])
             if self.model_type == "classification":
                 net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, 0, 0, y_mode=2)
-            elif embed_op == "joint":
+            elif embed_op in ("joint", "concat"):
                 weights.update(init_net_weights(self.in_dim_y, weight_dim_y, "y", self.seed))
                 net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, int(weight_dim_y[0]),
-                                   int(weight_dim_y[1]), y_mode=1)
+                                   int(weight_dim_y[1]), y_mode=1 if embed_op == "joint" else 3)
+                if embed_op == "concat":
+                    weights["log_reg"] = 0.0       # log(1.0), log_gaus_likelihood.py:45-48
             else:
                 net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, 0, 0, y_mode=0)
             # width of the embedding: train/log_gaus_likelihood.py:33-59

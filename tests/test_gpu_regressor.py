@@ -39,7 +39,8 @@ def pair(kernel, cuda_engine_mod, **kw):
     return gp_regressor(kernel, **kw), OracleGPRegressor(kernel, **kw)
 
 
-@pytest.mark.parametrize("case", ["params", "manual", "dist_none", "dist_joint", "dist_class", "dist_batched"])
+@pytest.mark.parametrize("case", ["params", "manual", "dist_none", "dist_joint", "dist_class", "dist_batched",
+                                  "dist_concat"])
 def test_fit_predict_parity(cuda_engine_mod, case):
     rs = np.random.RandomState(42)
     classification = case == "dist_class"
@@ -55,7 +56,7 @@ def test_fit_predict_parity(cuda_engine_mod, case):
         ind = np.arange(100)
         common.update(target_X=X[T], target_Y=Y[T], target_embed_ind=ind)
         fit.update(data_X=X[:T], data_Y=Y[:T], source_embed_ind=[np.arange(120)] * T, sizes=sizes,
-                   embed_op="none" if case == "dist_none" else "joint", weight_dim_x=[20, 10], weight_dim_y=[20, 10],
+                   embed_op={"dist_none": "none", "dist_concat": "concat"}.get(case, "joint"), weight_dim_x=[20, 10], weight_dim_y=[20, 10],
                    batch_size=64 if case == "dist_batched" else 500, stratify=False,
                    concat_data_size=(case != "dist_none"), max_size=400)
     elif kernel == "manual":

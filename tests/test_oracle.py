@@ -215,3 +215,26 @@ def test_toy_known_answer_end_to_end():
     grid = np.linspace(-8, 8, 3201)[:, None]
     mean, var = O.predict(O.NP, p, "params", b, sc.transform(grid))
     assert abs(grid[np.argmax(mean), 0] - mu) < 0.15
+
+
+def test_concat_operator_matches_kernel_ridge_form():
+    """'concat' pooling (distbo_net.py:49-89): the reference evaluates the conditional embedding operator through
+    the Woodbury form; the pin is the n x n kernel-ridge form Psi^T (Phi Phi^T + lambda I)^-1 Phi quoted in its
+    comments (Song, Fukumizu, Gretton 2013), evaluated independently here."""
+    rs = np.random.RandomState(3)
+    sizes = [40, 9, 3]
+    S = sum(sizes)
+    X, Y = rs.randn(S, 5), rs.rand(S, 1)
+    p = O.build_params(2, "dist", in_dim_x=5, in_dim_y=1, weight_dim_x=[8, 4], weight_dim_y=[8, 3],
+                       model_type="regression", embed_op="concat", seed=1)
+    p["log_reg"] = np.asarray(-1.3)
+    assert p["log_bw_embed"].shape == (4 * (3 + 1),)
+    got = O.distbo_net(O.NP, X, Y, sizes, p, embed_op="concat", model_type="regression")
+    lam = np.exp(-1.3)
+    b = np.r_[0, np.cumsum(sizes)]
+    for t, (s, e) in enumerate(zip(b[:-1], b[1:])):
+        phi = O.nn_net(O.NP, p, X[s:e], "x")
+        psi = O.nn_net(O.NP, p, Y[s:e], "y")
+        ridge = psi.T @ np.linalg.solve(phi @ phi.T + lam * np.eye(e - s), phi)      # [q, p]
+        np.testing.assert_allclose(got[t, :4], phi.mean(0), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(got[t, 4:], ridge.reshape(-1), rtol=1e-9, atol=1e-12)
