@@ -41,6 +41,8 @@ SIGNATURES = {
     "distbo_gram_grad_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp]),
     "distbo_task_gram_bwd_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "distbo_task_tri_f64": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "distbo_task_tri_bwd_f64": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "distbo_adam_f64": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _i64, _d, _vp, _vp]),
     "distbo_score_chunk": (_i, []),
     "distbo_score_workspace": (_i64, [_i]),

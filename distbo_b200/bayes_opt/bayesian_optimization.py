@@ -142,7 +142,7 @@ class BayesianOptimization(object):
                'first_early_stop_epoch': oc['first_early_stop_epoch']}
         self.util_one_shot = UtilityFunction(kind=acq_one_shot, kappa=kappa, xi=xi)
         if kernel == 'multi':
-            raise NotImplementedError("kernel 'multi' (multi-task BO baseline) is outside the joint-GP path")
+            self.size_evals.append(init_points)     # the target task already holds its initial points (:282-283)
 
         if n_iter != 0:
             seed = self.random_state.randint(2 ** 32)
@@ -168,7 +168,9 @@ class BayesianOptimization(object):
             self.source_Y.append(self.target_Y)
             self.size_evals.append(1)
             fit['source_embed_ind'] = self.source_embed_ind + [self.target_embed_ind]
-        if kernel in ('dist', 'manual'):
+        elif kernel == 'multi':
+            self.size_evals[-1] = self.size_evals[-1] + 1
+        if kernel in ('dist', 'manual', 'multi'):
             self.res['all']['similarity'].append(np.squeeze(self.gp.similarity()))
 
         for i in range(n_iter):
@@ -194,7 +196,7 @@ class BayesianOptimization(object):
                             evaluatedX=self.space.X[int(np.sum(self.size_evals[:-1])):],
                             random_state=self.random_state, n_warmup=oc['n_warmup'],
                             n_iter=oc['n_opt_iterations'])
-            if kernel in ('dist', 'manual'):
+            if kernel in ('dist', 'manual', 'multi'):
                 self.res['all']['similarity'].append(np.squeeze(self.gp.similarity()))
                 self.size_evals[-1] = self.size_evals[-1] + 1
         if hasattr(self, 'gp'):

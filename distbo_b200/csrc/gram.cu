@@ -402,6 +402,80 @@ __global__ void __launch_bounds__(1024) adam_kernel(double* __restrict__ params,
   }
 }
 
+
+// ---- multi-task kernel (train/kernels.py:32-55; log_gaus_likelihood.py:68-75) ---------------------------
+// Task covariance C = D^-1/2 (L L^T) D^-1/2, L = tril(fill_triangular(exp(log_tri))), D = diag(L L^T).
+// T is the number of tasks (tens), so one CTA does all of it; the T x T temporaries live in the caller's
+// workspace (ws: 3 T^2 doubles) and the phases are separated by __syncthreads().
+
+// Index into the length T(T+1)/2 parameter vector of lower-triangle element (i, j >= ... j <= i), following
+// tf.contrib.distributions.fill_triangular: the n*n row-major matrix is concat(x[n:], reverse(x)).
+__device__ __forceinline__ int tri_param_index(int i, int j, int n) {
+  const int m = n * (n + 1) / 2;
+  const int k = i * n + j;
+  return k < m - n ? n + k : 2 * m - n - 1 - k;
+}
+
+__device__ void task_tri_build(const double* __restrict__ log_tri, int T, double* L, double* Bm) {
+  for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+    const int i = e / T, j = e % T;
+    L[e] = j <= i ? exp(log_tri[tri_param_index(i, j, T)]) : 0.0;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+    const int i = e / T, j = e % T;
+    const int kmax = min(i, j);
+    double acc = 0.0;
+    for (int k = 0; k <= kmax; ++k) acc = fma(L[i * T + k], L[j * T + k], acc);
+    Bm[e] = acc;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) task_tri_fwd_kernel(const double* __restrict__ log_tri, int T,
+                                                          double* __restrict__ KE, double* __restrict__ ws) {
+  double* L = ws;
+  double* Bm = ws + (size_t)T * T;
+  task_tri_build(log_tri, T, L, Bm);
+  for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+    const int i = e / T, j = e % T;
+    KE[e] = (Bm[e] / sqrt(Bm[i * T + i])) / sqrt(Bm[j * T + j]);   // rows first, then columns (kernels.py:39-40)
+  }
+}
+
+// H = dNLL/dKE [T,T] (all ordered pairs) -> g_log_tri.
+__global__ void __launch_bounds__(256) task_tri_bwd_kernel(const double* __restrict__ log_tri, int T,
+                                                          const double* __restrict__ H,
+                                                          double* __restrict__ g_log_tri, double* __restrict__ ws) {
+  double* L = ws;
+  double* Bm = ws + (size_t)T * T;
+  double* dB = ws + 2 * (size_t)T * T;
+  task_tri_build(log_tri, T, L, Bm);
+  // direct term dB_ij = H_ij / (s_i s_j)
+  for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+    const int i = e / T, j = e % T;
+    dB[e] = H[e] / (sqrt(Bm[i * T + i]) * sqrt(Bm[j * T + j]));
+  }
+  __syncthreads();
+  // through the normalisers s_i = sqrt(B_ii): dB_ii += ds_i / (2 s_i),
+  // ds_i = -(1 / s_i^2) sum_j (H_ij + H_ji) B_ij / s_j
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    const double si = sqrt(Bm[i * T + i]);
+    double acc = 0.0;
+    for (int j = 0; j < T; ++j) acc += (H[i * T + j] + H[j * T + i]) * Bm[i * T + j] / sqrt(Bm[j * T + j]);
+    dB[i * T + i] += -acc / (si * si) / (2.0 * si);
+  }
+  __syncthreads();
+  // B = L L^T  =>  dL = (dB + dB^T) L ;  L_ik = exp(x)  =>  dx = dL_ik L_ik
+  for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+    const int i = e / T, k = e % T;
+    if (k > i) continue;
+    double acc = 0.0;
+    for (int j = k; j < T; ++j) acc = fma(dB[i * T + j] + dB[j * T + i], L[j * T + k], acc);
+    g_log_tri[tri_param_index(i, k, T)] = acc * L[i * T + k];
+  }
+}
+
 }  // namespace db
 
 using namespace db;
@@ -486,6 +560,21 @@ extern "C" int distbo_task_gram_bwd_f64(const double* E, int lde, int T, int P, 
   task_gram_bwd_rows_kernel<<<T, 256, (size_t)T * sizeof(double), st>>>(E, lde, T, P, log_bw_embed, H, workspace, dE);
   DB_CHECK_LAUNCH();
   task_gram_bwd_finish_kernel<<<(P + 255) / 256, 256, 0, st>>>(workspace, T, P, g_log_bw_embed);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
+extern "C" int distbo_task_tri_f64(const double* log_tri, int T, double* KE, double* workspace, void* stream) {
+  if (!log_tri || !KE || !workspace || T <= 0) return DISTBO_EARG;
+  task_tri_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(log_tri, T, KE, workspace);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
+extern "C" int distbo_task_tri_bwd_f64(const double* log_tri, int T, const double* H, double* g_log_tri,
+                                       double* workspace, void* stream) {
+  if (!log_tri || !H || !g_log_tri || !workspace || T <= 0) return DISTBO_EARG;
+  task_tri_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(log_tri, T, H, g_log_tri, workspace);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
 }

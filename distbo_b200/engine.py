@@ -118,7 +118,7 @@ class ParamStore:
 
 
 class GPEngine:
-    def __init__(self, d_theta, n_embed=0, net=None, device=None):
+    def __init__(self, d_theta, n_embed=0, net=None, device=None, n_multi=0):
         if not torch.cuda.is_available():
             raise _lib.DistboError("distbo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -139,6 +139,10 @@ class GPEngine:
                 shapes["log_reg"] = ()            # train/log_gaus_likelihood.py: log of the ridge lambda, init 0
         if self.P > 0:
             shapes["log_bw_embed"] = (self.P,)
+        self.n_multi = int(n_multi)      # kernel 'multi': number of tasks of the free-form task covariance
+        if self.n_multi > 0:
+            shapes["log_triangular_task"] = (self.n_multi * (self.n_multi + 1) // 2,)
+            self._tri_ws = torch.empty(3 * self.n_multi * self.n_multi, dtype=torch.float64, device=self.dev)
         shapes["log_bw"] = (self.d,)
         shapes["log_scale"] = (1,)
         shapes["mean"] = (1,)
@@ -268,6 +272,21 @@ class GPEngine:
                                            _lib.ptr(self.params.view("log_bw_embed")), _lib.ptr(KE), _stream())
         _lib.check(rc, "distbo_task_gram_f64")
         return KE
+
+    def task_tri(self):
+        """Multi-task covariance KE [T,T] from log_triangular_task (train/kernels.py:32-40)."""
+        T = self.n_multi
+        KE = self._f64(T, T)
+        rc = self.lib.distbo_task_tri_f64(_lib.ptr(self.params.view("log_triangular_task")), T, _lib.ptr(KE),
+                                          _lib.ptr(self._tri_ws), _stream())
+        _lib.check(rc, "distbo_task_tri_f64")
+        return KE
+
+    def task_tri_backward(self):
+        rc = self.lib.distbo_task_tri_bwd_f64(_lib.ptr(self.params.view("log_triangular_task")), self.n_multi,
+                                              _lib.ptr(self.H), _lib.ptr(self.params.gview("log_triangular_task")),
+                                              _lib.ptr(self._tri_ws), _stream())
+        _lib.check(rc, "distbo_task_tri_bwd_f64")
 
     def build_gram(self, KE=None):
         p = self.params
@@ -408,11 +427,17 @@ class GPEngine:
             self.embed(X, Y, seg_off, out=E)
         elif E_const is not None:
             E = E_const
-        KE = self.task_gram(E, T) if E is not None else None
+        if self.n_multi:
+            assert T == self.n_multi, "kernel 'multi': the number of tasks is fixed at the first fit"
+            KE = self.task_tri()
+        else:
+            KE = self.task_gram(E, T) if E is not None else None
         self.build_gram(KE)
         self.factorize(need_inverse=True, need_kinv=True)
         self.likelihood()
         self.gram_gradient()
+        if self.n_multi:
+            self.task_tri_backward()
         if E is not None:
             dE = self.task_gram_backward(E, T)
             if self.net is not None:

@@ -20,7 +20,7 @@ def bayes_opt_wrap(method, target_data, acq, model, rs, optim_config, xi=0, kapp
                    gp_class=None, verbose=1):
     """Runs BayesianOptimization.maximize with kernel `method` on `target_data`.
 
-    Returns [params sorted by name..., value] rows (and the similarity log for 'dist' / 'manual').
+    Returns [params sorted by name..., value] rows (and the similarity log for 'dist' / 'manual' / 'multi').
     `init_list` = per-source arrays of previous evaluations (last column = value)."""
     size_evals, stacked = None, None
     if init_list is not None:
@@ -57,7 +57,7 @@ def bayes_opt_wrap(method, target_data, acq, model, rs, optim_config, xi=0, kapp
     names = sorted(bo.space.keys)
     params = np.array([[p[k] for k in names] for p in bo.res['all']['params']], dtype=float).reshape(-1, len(names))
     out = np.hstack((params, np.expand_dims(bo.res['all']['values'], 1)))
-    if method in ('dist', 'manual'):
+    if method in ('dist', 'manual', 'multi'):
         sims = bo.res['all']['similarity']
         # one row per acquisition; the first has one entry per source task, the later ones also carry the
         # target task (appended to the GP after the one-shot acquisition) -> ragged, as in the reference

@@ -39,9 +39,8 @@ EARLY_STOP_PATIENCE = 100       # train/train.py:55
 class gp_regressor(object):
     def __init__(self, kernel, n_cpus=1, target_X=None, target_Y=None, model_type=None, seed=None,
                  target_embed_ind=None, float64=False):
-        if kernel not in ("dist", "manual", "params"):
-            # 'multi' is the multi-task BO baseline (train/kernels.py:32-55): outside the (theta, mu_D) GP
-            raise NotImplementedError("kernel %r is not part of the joint (theta, embedding) GP path" % (kernel,))
+        if kernel not in ("dist", "manual", "params", "multi"):
+            raise ValueError("kernel %r: expected 'dist', 'manual', 'params' or 'multi'" % (kernel,))
         self.model_type = model_type
         self.kernel = kernel
         self.n_cpus = n_cpus
@@ -75,7 +74,7 @@ class gp_regressor(object):
         return X, Y, torch.from_numpy(off).to(self.engine.dev)
 
     def _build_engine(self, weight_dim_x, weight_dim_y, embed_op, concat_data_size, bw_params_init,
-                      likhd_var_init, target_embed):
+                      likhd_var_init, target_embed, n_tasks=0):
         d = self.in_dim_params
         net = None
         P = 0
@@ -100,7 +99,14 @@ class gp_regressor(object):
             P = net.pooled_width + (1 if concat_data_size else 0)
         elif self.kernel == "manual":
             P = len(target_embed[0])
-        e = _eng.GPEngine(d, n_embed=P, net=net)
+        n_multi = 0
+        if self.kernel == "multi":
+            # log_gaus_likelihood.py:68-72 (np.random.seed(seed); np.random.normal): the same legacy stream,
+            # drawn from a private RandomState so the caller's global generator is left alone
+            n_multi = int(n_tasks)
+            seed = self.seed if self.seed is not None else 23
+            weights["log_triangular_task"] = np.random.RandomState(seed).normal(size=n_multi * (n_multi + 1) // 2)
+        e = _eng.GPEngine(d, n_embed=P, net=net, n_multi=n_multi)
         for k, v in weights.items():
             e.params.set(k, v)
         if self.initial_weights:
@@ -143,7 +149,7 @@ class gp_regressor(object):
 
         if self.initialise:
             self._build_engine(weight_dim_x, weight_dim_y, embed_op, concat_data_size, bw_params_init,
-                               likhd_var_init, target_embed)
+                               likhd_var_init, target_embed, n_tasks=len(sizes) if sizes is not None else 0)
         e = self.engine
         task_sizes = None if sizes is None or self.kernel == "params" else np.asarray(sizes).reshape(-1)
         e.set_observations(theta, np.asarray(y, dtype=np.float64).reshape(-1), task_sizes)
@@ -340,7 +346,13 @@ class gp_regressor(object):
             self._E_all = E_all
         elif self.kernel == "manual":
             self._E_all = torch.cat([self._E_const, self._dev(np.asarray(self.target_embed, dtype=np.float64))], 0)
-        if self.kernel in ("dist", "manual"):
+        if self.kernel == "multi":
+            # candidates belong to the last task (kernels.py:47-49): kvec = column T-1 of the task covariance
+            KE = e.task_tri()
+            self._KE_all = KE
+            e.kvec.zero_()
+            e.kvec[:e.N] = KE[:, T - 1][e.task_id.long()]
+        elif self.kernel in ("dist", "manual"):
             KE_all = e.task_gram(self._E_all, T + 1)
             self._KE_all = KE_all
             KE = KE_all[:T, :T].contiguous()
@@ -398,6 +410,8 @@ class gp_regressor(object):
             raise ValueError("similarity is defined for the 'dist' and 'manual' kernels")
         self._prepare_predict()
         T = self.engine.T
+        if self.kernel == "multi":               # sim_network -> net.k_task_pred with sizes all 1 (train.py:91-92)
+            return [self._KE_all[:, T - 1:T].cpu().numpy()]
         return [self._KE_all[:T, T:T + 1].cpu().numpy()]
 
     def close(self):

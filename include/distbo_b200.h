@@ -122,6 +122,14 @@ int distbo_gram_grad_f64(const double* Kinv, const double* alpha, const double* 
 int distbo_task_gram_bwd_f64(const double* E, int lde, int T, int P, const double* log_bw_embed,
                              const double* H, double* g_log_bw_embed, double* dE, double* workspace,
                              void* stream);
+/* Multi-task kernel (train/kernels.py:32-55, log_gaus_likelihood.py:68-75,114-116): the task covariance
+ * KE = D^-1/2 (L L^T) D^-1/2 with L = tril(fill_triangular(exp(log_tri))), D = diag(L L^T); log_tri has
+ * T(T+1)/2 entries in tf.contrib.distributions.fill_triangular order.  It takes the place of
+ * distbo_task_gram_f64 for kernel 'multi'.  workspace: 3*T*T doubles (both calls). */
+int distbo_task_tri_f64(const double* log_tri, int T, double* KE, double* workspace, void* stream);
+/* Backward: H = dNLL/dKE [T,T] (from distbo_gram_grad_f64) -> g_log_tri [T(T+1)/2]. */
+int distbo_task_tri_bwd_f64(const double* log_tri, int T, const double* H, double* g_log_tri,
+                            double* workspace, void* stream);
 /* TF-1.7 Adam update on a flat parameter vector (train/gp_regressor.py:141; epsilon-hat form):
  * lr_t = lr sqrt(1 - beta2^step) / (1 - beta1^step); p -= lr_t m / (sqrt(v) + eps).  step is 1-based.
  * clip_norm <= 0 disables tf.clip_by_global_norm (train/train.py:33-35).

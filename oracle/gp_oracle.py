@@ -229,7 +229,7 @@ def num_bw_embed(embed_op, model_type, in_dim_y, weight_dim_x, weight_dim_y, wei
 def build_params(in_dim_params, kernel, in_dim_x=None, in_dim_y=None, weight_dim_x=None,
                  weight_dim_y=None, weight_dim_xy=None, model_type="regression",
                  embed_op="joint", concat_data_size=False, in_dim_meta=None,
-                 likhd_var_init=0.01, bw_params_init=1.0, seed=23, dtype=np.float64):
+                 likhd_var_init=0.01, bw_params_init=1.0, seed=23, dtype=np.float64, n_tasks=None):
     """Trainable parameters and their initial values.
 
     train/log_gaus_likelihood.py:33-84; log_sigma_init = 0.5*log(likhd_var_init)
@@ -250,8 +250,13 @@ def build_params(in_dim_params, kernel, in_dim_x=None, in_dim_y=None, weight_dim
         params["log_bw_embed"] = np.zeros(nbw, dtype=dtype)
     elif kernel == "manual":
         params["log_bw_embed"] = np.zeros(in_dim_meta, dtype=dtype)
+    elif kernel == "multi":
+        # log_gaus_likelihood.py:68-72: np.random.seed(seed); np.random.normal(size=T(T+1)/2).  RandomState(seed)
+        # draws the same legacy stream without reseeding the caller's global generator.
+        params["log_triangular_task"] = np.random.RandomState(seed).normal(
+            size=n_tasks * (n_tasks + 1) // 2).astype(dtype)
     elif kernel != "params":
-        raise NotImplementedError("kernel %r is out of scope (multi-task BO baseline)" % kernel)
+        raise NotImplementedError("kernel %r" % kernel)
     params["log_bw"] = np.log(np.full(in_dim_params, bw_params_init, dtype=dtype))
     params["log_scale"] = np.zeros(1, dtype=dtype)
     params["mean"] = np.zeros(1, dtype=dtype)
@@ -342,6 +347,55 @@ def matern32_kernel(B, X, Y, stddev=1.0):
     return (1.0 + value) * B.exp(-value)
 
 
+def fill_triangular_index(n):
+    """Index map of tf.contrib.distributions.fill_triangular (TF 1.7, lower): the n x n row-major matrix is
+    concat(x[n:], reverse(x)) and then band-limited to the lower triangle.  Returns (idx [n,n], mask [n,n])
+    with L = x[idx] * mask.  TF's docstring example: fill_triangular([1..6]) = [[4,0,0],[6,5,0],[3,2,1]]."""
+    m = n * (n + 1) // 2
+    src = np.concatenate([np.arange(n, m), np.arange(m)[::-1]])
+    return src.reshape(n, n), np.tril(np.ones((n, n)))
+
+
+def task_kernel_matrix(B, params, n_tasks):
+    """train/kernels.py:32-40 with log_gaus_likelihood.py:75: L = fill_triangular(exp(log_triangular_task)),
+    L L^T rescaled to unit diagonal (rows first, then columns).  [T,T]."""
+    idx, mask = fill_triangular_index(n_tasks)
+    x = B.exp(params["log_triangular_task"])
+    if B is NP:
+        L = x[idx] * mask
+    else:
+        L = x[B.t.as_tensor(idx)] * B.t.as_tensor(mask)
+    k = B.matmul(L, B.transpose(L))
+    ds = B.sqrt(B.diag(k))
+    k = k / ds.reshape(-1, 1)
+    k = k / ds.reshape(1, -1)
+    return k
+
+
+def _task_rows(sizes):
+    sizes = np.asarray(sizes, dtype=np.int64).reshape(-1)
+    return np.repeat(np.arange(len(sizes)), sizes)
+
+
+def task_kernel(B, params, sizes):
+    """train/kernels.py:41-55 (sizes_2 None): the [T,T] matrix expanded to [N,N] by the task of each row."""
+    t = _task_rows(sizes)
+    k = task_kernel_matrix(B, params, len(np.asarray(sizes).reshape(-1)))
+    if B is not NP:
+        t = B.t.as_tensor(t)
+    return k[t][:, t]
+
+
+def task_kernel_pred(B, params, sizes, n_pred):
+    """train/kernels.py:47-49 (sizes_2 given): every candidate belongs to the LAST task -> [N, M]."""
+    t = _task_rows(sizes)
+    k = task_kernel_matrix(B, params, len(np.asarray(sizes).reshape(-1)))
+    if B is not NP:
+        t = B.t.as_tensor(t)
+    col = k[t][:, -1].reshape(-1, 1)
+    return np.repeat(col, n_pred, axis=1) if B is NP else col.expand(-1, n_pred)
+
+
 @dataclass
 class TrainBatch:
     """What one sess.run of the likelihood graph is fed (train/base.py:91-127)."""
@@ -369,6 +423,8 @@ def kernel_train(B, params, kernel, batch, embed_op="joint", model_type=None):
     elif kernel == "manual":
         emb = B.repeat_rows(batch.embed, np.asarray(batch.sizes).reshape(-1))     # feature_map.py:29-35
         k = k * matern32_kernel(B, emb, emb, stddev=B.exp(params["log_bw_embed"]))
+    elif kernel == "multi":
+        k = k * task_kernel(B, params, batch.sizes)
     return scale * k
 
 
@@ -414,6 +470,8 @@ def predict_factor(B, params, kernel, batch, k_dist=None):
     elif kernel == "manual":
         emb = B.repeat_rows(batch.embed, np.asarray(batch.sizes).reshape(-1))
         k = scale * k * matern32_kernel(B, emb, emb, stddev=B.exp(params["log_bw_embed"]))
+    elif kernel == "multi":
+        k = scale * k * task_kernel(B, params, batch.sizes)
     else:
         k = scale * k
     L = B.cholesky(k + (sigma_sq + JITTER) * B.eye(n, k))
@@ -433,6 +491,8 @@ def predict_apply(B, params, kernel, batch, L, V, h_params_pred, k_dist_pred=Non
         emb = B.repeat_rows(batch.embed, np.asarray(batch.sizes).reshape(-1))
         emb_p = B.repeat_rows(embed_pred, [h_params_pred.shape[0]])
         k_pred = scale * k_pred * matern32_kernel(B, emb, emb_p, stddev=B.exp(params["log_bw_embed"]))
+    elif kernel == "multi":
+        k_pred = scale * k_pred * task_kernel_pred(B, params, batch.sizes, h_params_pred.shape[0])
     else:
         k_pred = scale * k_pred
     A = B.solve_lower(L, k_pred)
@@ -474,9 +534,11 @@ def similarity(B, params, kernel, batch, X_pred=None, y_pred=None, embed_sizes_p
                data_sizes_pred=None, embed_pred=None, embed_op="joint", model_type=None):
     """train/train.py:86-95 with sizes all 1 (base.py:137-139): [T,1] kernel between every
     source embedding and the target embedding."""
-    bw = B.exp(params["log_bw_embed"])
     T = len(np.asarray(batch.sizes).reshape(-1))
     ones = [1] * T
+    if kernel == "multi":                       # net.k_task_pred with sizes all 1: column of the last task
+        return task_kernel_pred(B, params, ones, 1)
+    bw = B.exp(params["log_bw_embed"])
     if kernel == "dist":
         e1 = dist_features(B, params, batch.batch_X, batch.batch_y, ones, batch.embed_sizes,
                            data_sizes=batch.data_sizes, max_size=batch.max_size,

@@ -167,6 +167,8 @@ class OracleGPRegressor(object):
             elif self.kernel == "manual":
                 self.p = O.build_params(self.in_dim_params, "manual",
                                         in_dim_meta=len(target_embed[0]), **kw)
+            elif self.kernel == "multi":                     # gp_regressor.py:124-129
+                self.p = O.build_params(self.in_dim_params, "multi", n_tasks=len(sizes), **kw)
             else:
                 self.p = O.build_params(self.in_dim_params, "params", **kw)
             self.adam = O.TFAdam(learning_rate)
@@ -181,6 +183,8 @@ class OracleGPRegressor(object):
             train["max_size"] = max_size if concat_data_size else None
         elif self.kernel == "manual":
             train["embed"] = np.asarray(data_embed, dtype=np.float64)
+            train["sizes"] = sizes
+        elif self.kernel == "multi":
             train["sizes"] = sizes
         self.train = train
         loss = self._train_network(max_epochs, first_early_stop_epoch, batch_size, stratify,
@@ -248,7 +252,7 @@ class OracleGPRegressor(object):
                                   embed_pred=np.asarray(self.target_embed, dtype=np.float64))
         else:
             batch = self._batch(None, None, None)
-            mean, var = O.predict(B, self.p, "params", batch, params_pred)
+            mean, var = O.predict(B, self.p, self.kernel, batch, params_pred)
         return mean, O.std_from_var(var)
 
     def similarity(self, sample_sim=False):
@@ -266,6 +270,8 @@ class OracleGPRegressor(object):
             batch = self._batch(None, None, None)
             sim = O.similarity(B, self.p, "manual", batch,
                                embed_pred=np.asarray(self.target_embed, dtype=np.float64))
+        elif self.kernel == "multi":
+            sim = O.similarity(B, self.p, "multi", self._batch(None, None, None))
         else:
             raise ValueError(self.kernel)
         return [sim]

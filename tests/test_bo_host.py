@@ -83,7 +83,7 @@ def test_acq_max_argmax_and_fallback():
         UtilityFunction('es', 1.0, 0.0)
 
 
-@pytest.mark.parametrize("method", ["params", "dist"])
+@pytest.mark.parametrize("method", ["params", "dist", "multi"])
 def test_bo_loop_with_oracle_regressor(method):
     target, sources, supp = one_dim_split_tasks(0, 1, 1, n_train=40, n_test=40)
     rs = np.random.RandomState(5)
@@ -94,7 +94,7 @@ def test_bo_loop_with_oracle_regressor(method):
         init_list.append(np.column_stack([th, [f(theta=t) for t in th]]))
     cfg = toy_optim_config()
     kw = dict(acq='ei', model='toy', rs=np.random.RandomState(11), optim_config=cfg, xi=0.01, kappa=2.58,
-              bo_it=3, rand_it=0, init_list=init_list, include_init=False, source_data=sources,
+              bo_it=3, rand_it=2 if method == 'multi' else 0, init_list=init_list, include_init=False, source_data=sources,
               gp_class=OracleGPRegressor, verbose=0, acq_one_shot='lcb')
     out = bayes_opt_wrap(method, target, **kw)
     if method == 'dist':
@@ -102,6 +102,12 @@ def test_bo_loop_with_oracle_regressor(method):
         # one similarity row per acquisition: T_src = 2 entries, then 3 once the target task has joined
         assert [np.size(s) for s in sim] == [2, 3, 3]
         assert all(np.all(np.asarray(s) > 0) and np.all(np.asarray(s) <= 1 + 1e-12) for s in sim)
+    if method == 'multi':
+        out, sim = out
+        # the target is the last of the T = 3 tasks from the start (bayesian_optimization.py:282-283)
+        assert [np.size(s) for s in sim] == [3, 3, 3]
+        assert all(np.asarray(s, dtype=float)[-1] == pytest.approx(1.0) for s in sim)
+        out = out[-3:]                              # the 2 random target initialisations come first
     assert out.shape == (3, 2)
     f, _, _, _ = set_model('toy', target, None)
     assert np.allclose(out[:, 1], [f(theta=t) for t in out[:, 0]])

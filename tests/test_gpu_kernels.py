@@ -272,6 +272,28 @@ def test_embed_backward(cuda_engine_mod, mode):
             assert rel(e.params.get_grad(name), tp[name].grad.numpy()) < 1e-10, name
 
 
+@pytest.mark.parametrize("T", [1, 5, 42, 65])
+def test_multi_task_kernel(cuda_engine_mod, T):
+    """kernel 'multi' (train/kernels.py:32-40): task covariance and its gradient vs the oracle / torch autograd."""
+    eng = cuda_engine_mod
+    rs = np.random.RandomState(T)
+    e = eng.GPEngine(2, n_multi=T)
+    x = rs.normal(size=T * (T + 1) // 2)
+    e.params.set("log_triangular_task", x)
+    KE = e.task_tri().cpu().numpy()
+    want = O.task_kernel_matrix(O.NP, {"log_triangular_task": x}, T)
+    assert rel(KE, want) < 1e-13
+    H = rs.randn(T, T)
+    e.H = torch.from_numpy(H).to(e.dev)
+    e.task_tri_backward()
+    xt = torch.tensor(x, requires_grad=True)
+    (O.task_kernel_matrix(O.TH(), {"log_triangular_task": xt}, T) * torch.from_numpy(H)).sum().backward()
+    if T > 1:
+        assert rel(e.params.get_grad("log_triangular_task"), xt.grad.numpy()) < 1e-10
+    else:
+        assert abs(e.params.get_grad("log_triangular_task")[0]) < 1e-12
+
+
 def test_adam_matches_tf_form(cuda_engine_mod):
     eng = cuda_engine_mod
     e = eng.GPEngine(3)

@@ -39,8 +39,8 @@ def pair(kernel, cuda_engine_mod, **kw):
     return gp_regressor(kernel, **kw), OracleGPRegressor(kernel, **kw)
 
 
-@pytest.mark.parametrize("case", ["params", "manual", "dist_none", "dist_joint", "dist_class", "dist_batched",
-                                  "dist_concat"])
+@pytest.mark.parametrize("case", ["params", "manual", "multi", "dist_none", "dist_joint", "dist_class",
+                                  "dist_batched", "dist_concat"])
 def test_fit_predict_parity(cuda_engine_mod, case):
     rs = np.random.RandomState(42)
     classification = case == "dist_class"
@@ -62,6 +62,8 @@ def test_fit_predict_parity(cuda_engine_mod, case):
     elif kernel == "manual":
         emb = rs.rand(T + 1, 9)
         fit.update(data_embed=emb[:T], target_embed=emb[T:], sizes=sizes)
+    elif kernel == "multi":
+        fit.update(sizes=sizes)                    # the last task is the target (kernels.py:47-49)
     g, o = pair(kernel, cuda_engine_mod, **common)
     lg = g.maximise_likhd(theta, y, **fit)
     lo = o.maximise_likhd(theta, y, **fit)
@@ -95,6 +97,8 @@ def test_fit_predict_parity(cuda_engine_mod, case):
         fit.update(data_X=X, data_Y=Y, source_embed_ind=[np.arange(120)] * (T + 1), sizes=sizes + [1])
     elif kernel == "manual":
         fit.update(data_embed=emb, sizes=sizes + [1])
+    elif kernel == "multi":
+        fit.update(sizes=sizes[:-1] + [sizes[-1] + 1])
     lg = g.maximise_likhd(theta2, y2, **fit)
     lo = o.maximise_likhd(theta2, y2, **fit)
     assert rel(g.loss_history, o.loss_history) < 1e-8

@@ -33,7 +33,8 @@ def source_evals(sources, seed, n):
     return out
 
 
-@pytest.mark.parametrize("method,embed_op", [("dist", "none"), ("dist", "joint"), ("params", "none")])
+@pytest.mark.parametrize("method,embed_op", [("dist", "none"), ("dist", "joint"), ("dist", "concat"), ("params", "none"),
+                                             ("multi", "none")])
 def test_toy_trajectory_identical(cuda_engine_mod, method, embed_op):
     target, sources, supp = one_dim_split_tasks(0, 3, 2, n_train=120, n_test=120)
     init_list = source_evals(sources, 1, 12)
@@ -41,16 +42,16 @@ def test_toy_trajectory_identical(cuda_engine_mod, method, embed_op):
     for name, gp_class in (("cuda", None), ("oracle", OracleGPRegressor)):
         cfg = optim_config(embed_op=embed_op)
         runs[name] = bayes_opt_wrap(method, target, acq='ei', model='toy', rs=np.random.RandomState(7),
-                                    optim_config=cfg, xi=0.01, kappa=2.58, bo_it=5, rand_it=0,
-                                    init_list=[a.copy() for a in init_list], include_init=False,
+                                    optim_config=cfg, xi=0.01, kappa=2.58, bo_it=5,
+                                    rand_it=3 if method == "multi" else 0, init_list=[a.copy() for a in init_list], include_init=False,
                                     source_data=sources, gp_class=gp_class, verbose=0, acq_one_shot='lcb')
-    if method == "dist":
+    if method in ("dist", "multi"):
         (a, sim_a), (b, sim_b) = runs["cuda"], runs["oracle"]
         for x, y in zip(sim_a, sim_b):
             assert np.allclose(np.asarray(x, dtype=float), np.asarray(y, dtype=float), rtol=1e-8, atol=0)
     else:
         a, b = runs["cuda"], runs["oracle"]
-    assert a.shape == b.shape == (5, 2)
+    assert a.shape == b.shape == ((8, 2) if method == "multi" else (5, 2))
     assert np.array_equal(a[:, 0], b[:, 0]), (a[:, 0], b[:, 0])      # identical suggestions
     assert np.array_equal(a[:, 1], b[:, 1])
 

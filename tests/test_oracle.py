@@ -238,3 +238,40 @@ def test_concat_operator_matches_kernel_ridge_form():
         ridge = psi.T @ np.linalg.solve(phi @ phi.T + lam * np.eye(e - s), phi)      # [q, p]
         np.testing.assert_allclose(got[t, :4], phi.mean(0), rtol=1e-12, atol=1e-14)
         np.testing.assert_allclose(got[t, 4:], ridge.reshape(-1), rtol=1e-9, atol=1e-12)
+
+
+def test_multi_task_kernel_restatement():
+    """kernel 'multi': fill_triangular order is TF's documented example ([1..6] -> [[4,0,0],[6,5,0],[3,2,1]]);
+    the task covariance has unit diagonal and is positive semi-definite; its autograd gradient agrees with
+    central finite differences."""
+    import torch
+    idx, mask = O.fill_triangular_index(3)
+    x = np.arange(1.0, 7.0)
+    np.testing.assert_array_equal(x[idx] * mask, [[4, 0, 0], [6, 5, 0], [3, 2, 1]])
+    for n in (1, 2, 7):
+        idx, mask = O.fill_triangular_index(n)
+        assert sorted(idx[mask > 0]) == list(range(n * (n + 1) // 2))         # a bijection onto the triangle
+    rs = np.random.RandomState(0)
+    T = 6
+    x = rs.normal(size=T * (T + 1) // 2)
+    k = O.task_kernel_matrix(O.NP, {"log_triangular_task": x}, T)
+    np.testing.assert_allclose(np.diag(k), 1.0, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(k, k.T, atol=1e-15)
+    assert np.linalg.eigvalsh(k).min() > -1e-12
+    assert (k > 0).all()                                                       # "positive correlation" (:74)
+    H = rs.randn(T, T)
+    xt = torch.tensor(x, requires_grad=True)
+    (O.task_kernel_matrix(O.TH(), {"log_triangular_task": xt}, T) * torch.from_numpy(H)).sum().backward()
+    fd = np.zeros_like(x)
+    for i in range(len(x)):
+        d = np.zeros_like(x)
+        d[i] = 1e-6
+        fd[i] = ((O.task_kernel_matrix(O.NP, {"log_triangular_task": x + d}, T) * H).sum()
+                 - (O.task_kernel_matrix(O.NP, {"log_triangular_task": x - d}, T) * H).sum()) / 2e-6
+    np.testing.assert_allclose(xt.grad.numpy(), fd, rtol=1e-6, atol=1e-8)
+    # expanded to observations: row/column t(i) of the task matrix; candidates sit in the last task
+    sizes = [2, 1, 3, 1, 1, 2]
+    t = np.repeat(np.arange(T), sizes)
+    np.testing.assert_array_equal(O.task_kernel(O.NP, {"log_triangular_task": x}, sizes), k[np.ix_(t, t)])
+    np.testing.assert_array_equal(O.task_kernel_pred(O.NP, {"log_triangular_task": x}, sizes, 4),
+                                  np.repeat(k[t, -1][:, None], 4, axis=1))
