@@ -125,9 +125,19 @@ def acq_max(ac, gp, y_max, bounds, random_state, algorithm=None, kernel=None,
             n_warmup=100000, n_iter=250):
     """Maximiser of the acquisition function: `n_warmup` uniform candidates, arg-max, optional
     L-BFGS-B polish from the best `n_iter` of them, all-zero-EI -> UCB fallback (helpers.py:9-111)."""
-    if algorithm == 'BLR':
-        raise NotImplementedError("BLR warm start (helpers.py:54-65) belongs to the BLR surrogate (SURVEY 8f)")
     x_tries = random_state.uniform(bounds[:, 0], bounds[:, 1], size=(n_warmup, bounds.shape[0]))
+    if algorithm == 'BLR' and kernel in ('dist', 'manual', 'multi'):
+        # BLR warm start (helpers.py:54-65): the candidates are the best theta of every source task but the last
+        # (the random draw above still advances the caller's stream, as in the reference); no polish
+        if kernel == 'multi':
+            size_evals = size_evals[:-1]
+        cumsum_size = [0] + np.cumsum(size_evals).tolist()
+        init_loc = []
+        for i in range(len(size_evals) - 1):
+            init_Y_task = prev_Y[cumsum_size[i]:cumsum_size[i + 1]]
+            init_loc.append(cumsum_size[i] + init_Y_task.argsort()[-1])
+        x_tries = prev_X[init_loc]
+        n_iter = 0
     util = _as_utility(ac)
     x_max, max_acq, x_seeds = _sweep(ac, util, gp, y_max, x_tries, n_iter)
     if n_iter != 0:

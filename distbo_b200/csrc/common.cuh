@@ -72,6 +72,20 @@ __device__ __forceinline__ double matern32_from_d2(double d2) {
   return (1.0 + v) * exp(-v);
 }
 
+// EI / UCB / LCB (bayes_opt/helpers.py:151-171); kind = DISTBO_ACQ_* of include/distbo_b200.h.
+__device__ __forceinline__ double acquisition(int kind, double mean, double std, double y_max, double xi,
+                                              double kappa) {
+  if (kind == 0) {
+    const double imp = mean - y_max - xi;
+    const double z = imp / std;
+    const double cdf = 0.5 * erfc(-z * 0.70710678118654752440);
+    const double pdf = exp(-z * z / 2.0) / 2.5066282746310005024;
+    return imp * cdf + std * pdf;
+  }
+  if (kind == 1) return mean + kappa * std;
+  return mean - kappa * std;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -81,19 +81,6 @@ __global__ void __launch_bounds__(256, 2) kst_kernel(const double* __restrict__ 
   }
 }
 
-__device__ __forceinline__ double acquisition(int kind, double mean, double std, double y_max, double xi,
-                                              double kappa) {
-  if (kind == DISTBO_ACQ_EI) {
-    const double imp = mean - y_max - xi;
-    const double z = imp / std;
-    const double cdf = 0.5 * erfc(-z * 0.70710678118654752440);
-    const double pdf = exp(-z * z / 2.0) / 2.5066282746310005024;
-    return imp * cdf + std * pdf;
-  }
-  if (kind == DISTBO_ACQ_UCB) return mean + kappa * std;
-  return mean - kappa * std;
-}
-
 constexpr int SCORE_SLICES = 16;  // CTAs that share one candidate tile (row blocks of W dealt out in snake order)
 
 struct ScoreArgs {

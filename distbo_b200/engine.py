@@ -117,6 +117,22 @@ class ParamStore:
         return name in self.offsets
 
 
+def net_param_shapes(net):
+    """Trainable tensors of the embedding nets (train/gp_utils.py:13-26; log_gaus_likelihood.py:33-48)."""
+    shapes = {}
+    if net is not None:
+        shapes["weights_x_1"] = (net.dx, net.hx)
+        shapes["bias_x_1"] = (net.hx,)
+        shapes["weights_x_2"] = (net.hx, net.p)
+        if net.has_ynet:
+            shapes["weights_y_1"] = (net.dy, net.hy)
+            shapes["bias_y_1"] = (net.hy,)
+            shapes["weights_y_2"] = (net.hy, net.q)
+        if net.y_mode == 3:
+            shapes["log_reg"] = ()                # log of the ridge lambda of the 'concat' operator, init 0
+    return shapes
+
+
 class GPEngine:
     def __init__(self, d_theta, n_embed=0, net=None, device=None, n_multi=0):
         if not torch.cuda.is_available():
@@ -126,17 +142,7 @@ class GPEngine:
         self.d = int(d_theta)
         self.P = int(n_embed)            # embedding width incl. size-ratio column (0: kernel 'params')
         self.net = net
-        shapes = {}
-        if net is not None:
-            shapes["weights_x_1"] = (net.dx, net.hx)
-            shapes["bias_x_1"] = (net.hx,)
-            shapes["weights_x_2"] = (net.hx, net.p)
-            if net.has_ynet:
-                shapes["weights_y_1"] = (net.dy, net.hy)
-                shapes["bias_y_1"] = (net.hy,)
-                shapes["weights_y_2"] = (net.hy, net.q)
-            if net.y_mode == 3:
-                shapes["log_reg"] = ()            # train/log_gaus_likelihood.py: log of the ridge lambda, init 0
+        shapes = net_param_shapes(net)
         if self.P > 0:
             shapes["log_bw_embed"] = (self.P,)
         self.n_multi = int(n_multi)      # kernel 'multi': number of tasks of the free-form task covariance

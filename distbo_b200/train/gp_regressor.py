@@ -28,6 +28,7 @@ import torch
 from sklearn.preprocessing import StandardScaler
 from sklearn.utils import check_random_state
 
+from .. import blr_engine as _blr
 from .. import engine as _eng
 from ..sharding import ShardGroup
 from .gp_utils import EmbedBatchSampler, check_dims, init_net_weights
@@ -74,7 +75,7 @@ class gp_regressor(object):
         return X, Y, torch.from_numpy(off).to(self.engine.dev)
 
     def _build_engine(self, weight_dim_x, weight_dim_y, embed_op, concat_data_size, bw_params_init,
-                      likhd_var_init, target_embed, n_tasks=0):
+                      likhd_var_init, target_embed, n_tasks=0, weight_dim=None):
         d = self.in_dim_params
         net = None
         P = 0
@@ -83,6 +84,9 @@ class gp_regressor(object):
             if embed_op not in ("none", "joint", "concat"):
                 raise NotImplementedError("embed_op %r: 'none', 'joint' and 'concat' are on the sm_100a path "
                                           "(SURVEY section 8f ranks 'nn' next)" % (embed_op,))
+            if len(weight_dim_x) != 2 or (weight_dim_y is not None and len(weight_dim_y) not in (0, 2)):
+                raise NotImplementedError("the sm_100a embedding kernel implements the two-layer feature map "
+                                          "(weight_dim_x / weight_dim_y of length 2, as every shipped config uses)")
             weights.update(init_net_weights(self.in_dim_x, weight_dim_x, "x", self.seed))
             hx, p = int(weight_dim_x[0]), int(weight_dim_x[1])
             if self.model_type == "classification":
@@ -99,6 +103,20 @@ class gp_regressor(object):
             P = net.pooled_width + (1 if concat_data_size else 0)
         elif self.kernel == "manual":
             P = len(target_embed[0])
+        if self.algorithm == "BLR":
+            # log_gaus_likelihood_feature.py:30-79: feature row = [embedding part | theta]
+            if self.kernel == "multi":
+                P = int(n_tasks)
+            weights.update(init_net_weights(P + d, weight_dim, "", self.seed))
+            e = _blr.BLREngine(d, weight_dim, n_embed=P, net=net)
+            for k, v in weights.items():
+                e.params.set(k, v)
+            if self.initial_weights:
+                for k, v in self.initial_weights.items():
+                    e.params.set(k, v)
+            e.params.set("log_sigma", 0.5 * math.log(likhd_var_init))
+            self.engine = e
+            return
         n_multi = 0
         if self.kernel == "multi":
             # log_gaus_likelihood.py:68-72 (np.random.seed(seed); np.random.normal): the same legacy stream,
@@ -126,8 +144,11 @@ class gp_regressor(object):
                        bw_params_init=1.0, likhd_var_init=0.01, stratify=True,
                        gradient_clip=False, first_early_stop_epoch=30):
         assert len(params) == len(y), 'Configurations and y must be same length'
-        if algorithm != 'GP':
-            raise NotImplementedError("algorithm %r: the BLR surrogate is outside this path (SURVEY 8f)" % (algorithm,))
+        if algorithm not in ('GP', 'BLR'):
+            raise ValueError("algorithm %r: expected 'GP' or 'BLR'" % (algorithm,))
+        if algorithm == 'BLR' and num_of_rff:
+            raise NotImplementedError("BLR with a random Fourier map (num_of_rff > 0, feature_map.py:19-26) is not on "
+                                      "the sm_100a path; every shipped config uses num_of_rff = 0")
         self.target_embed = target_embed
         self.algorithm = algorithm
         self.embed_op = embed_op
@@ -149,7 +170,8 @@ class gp_regressor(object):
 
         if self.initialise:
             self._build_engine(weight_dim_x, weight_dim_y, embed_op, concat_data_size, bw_params_init,
-                               likhd_var_init, target_embed, n_tasks=len(sizes) if sizes is not None else 0)
+                               likhd_var_init, target_embed, n_tasks=len(sizes) if sizes is not None else 0,
+                               weight_dim=weight_dim)
         e = self.engine
         task_sizes = None if sizes is None or self.kernel == "params" else np.asarray(sizes).reshape(-1)
         e.set_observations(theta, np.asarray(y, dtype=np.float64).reshape(-1), task_sizes)
@@ -176,6 +198,8 @@ class gp_regressor(object):
             batch_off = torch.from_numpy(bs).to(e.dev)
         elif self.kernel == 'manual':
             self._E_const = self._dev(np.asarray(data_embed, dtype=np.float64))
+        elif self.kernel == 'multi' and algorithm == 'BLR':
+            self._E_const = torch.eye(e.T, dtype=torch.float64, device=e.dev)   # task_features, feature_map.py:37-46
 
         self._sampler, self._full_off = sampler, (full_off if sampler is not None else None)
         self._batch_off = batch_off if sampler is not None else None
@@ -346,6 +370,18 @@ class gp_regressor(object):
             self._E_all = E_all
         elif self.kernel == "manual":
             self._E_all = torch.cat([self._E_const, self._dev(np.asarray(self.target_embed, dtype=np.float64))], 0)
+        if self.algorithm == "BLR":
+            # build_predict_feature / build_predict_dist_feature (log_gaus_likelihood_feature.py:145-225): the
+            # D x D factor from the training rows; every candidate's feature row carries the target's embedding part
+            E = emb_t = None
+            if self.kernel in ("dist", "manual"):
+                E, emb_t = self._E_all[:T].contiguous(), self._E_all[T].contiguous()
+            elif self.kernel == "multi":
+                E, emb_t = self._E_const, self._E_const[T - 1].contiguous()
+            e.prepare_posterior(E, emb_t)
+            e.read_loss()
+            self._predict_generation = self._fit_generation
+            return
         if self.kernel == "multi":
             # candidates belong to the last task (kernels.py:47-49): kvec = column T-1 of the task covariance
             KE = e.task_tri()
@@ -406,8 +442,10 @@ class gp_regressor(object):
     def similarity(self, sample_sim=False):
         """[array [T,1]]: embedding-kernel value between every source task and the target
         (gp_regressor.py:205-223; train/train.py:86-95)."""
+        if self.algorithm == "BLR":
+            return ['none']                      # gp_regressor.py:221-222
         if self.kernel == "params":
-            raise ValueError("similarity is defined for the 'dist' and 'manual' kernels")
+            raise ValueError("similarity is defined for the 'dist', 'manual' and 'multi' kernels")
         self._prepare_predict()
         T = self.engine.T
         if self.kernel == "multi":               # sim_network -> net.k_task_pred with sizes all 1 (train.py:91-92)

@@ -32,17 +32,22 @@ def truncated_glorot(rs, fan_in, fan_out):
 
 
 def init_net_weights(in_dim, weight_dim, name, seed):
-    """{weights_<name>_1, bias_<name>_1, weights_<name>_2}: zero bias, no bias on the last layer."""
-    if weight_dim is None or len(weight_dim) != 2:
-        raise NotImplementedError("the sm_100a embedding kernel implements the two-layer feature map "
-                                  "(weight_dim of length 2, as every shipped config uses)")
+    """{weights_<name>_1, bias_<name>_1, weights_<name>_2[, bias_<name>_2, weights_<name>_3]}: zero biases, no
+    bias on the last layer (reference train/gp_utils.py:13-26)."""
+    if weight_dim is None or len(weight_dim) not in (2, 3):
+        raise NotImplementedError("feature maps of 2 or 3 layers (weight_dim of length 2 or 3, as every shipped "
+                                  "config uses)")
     rs = np.random.RandomState(23 if seed is None else seed)
     h, p = int(weight_dim[0]), int(weight_dim[1])
-    return {
+    out = {
         "weights_%s_1" % name: truncated_glorot(rs, in_dim, h).astype(np.float64),
         "bias_%s_1" % name: np.zeros(h),
         "weights_%s_2" % name: truncated_glorot(rs, h, p).astype(np.float64),
     }
+    if len(weight_dim) == 3:
+        out["bias_%s_2" % name] = np.zeros(p)
+        out["weights_%s_3" % name] = truncated_glorot(rs, p, int(weight_dim[2])).astype(np.float64)
+    return out
 
 
 def label_bins(labels, lo=0.0, hi=1.01, intervals=4):

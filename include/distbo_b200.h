@@ -130,6 +130,39 @@ int distbo_task_tri_f64(const double* log_tri, int T, double* KE, double* worksp
 /* Backward: H = dNLL/dKE [T,T] (from distbo_gram_grad_f64) -> g_log_tri [T(T+1)/2]. */
 int distbo_task_tri_bwd_f64(const double* log_tri, int T, const double* H, double* g_log_tri,
                             double* workspace, void* stream);
+/* ---- BLR surrogate on deep features (algorithm='BLR')  (train/log_gaus_likelihood_feature.py:13-225,
+ *      train/feature_map.py:12-46) ------------------------------------------------------------------
+ * Feature row F_i = [emb[task_id[i]] (Pe) | theta_i (d)];  Phi = tanh(F W1 + b1) W2 (n_layers 2, D = h2) or
+ * tanh(tanh(F W1 + b1) W2 + b2) W3 (n_layers 3); W1 [Pe+d,h1], W2 [h1,h2], W3 [h2,D] row-major, widths <= 64,
+ * d <= 16.  A = I + (alpha/sigma^2) Phi^T Phi = L L^T, e = L^-1 Phi^T y,
+ * loss = (1/sigma^2)(|y|^2 - (alpha/sigma^2)|e|^2) + N log sigma^2 + 2 sum log L_ii      (:107-143).
+ * Outputs: Linv [64*64] (row-major, ld 64, zero padded), evec [64], loss, info (0, or k+1 when pivot k is not
+ * positive).  want_grad != 0 also fills the gradients of every weight, of log_sigma / log_alpha, and dE [T,ldE]
+ * (d loss / d emb; may be NULL) - the closed form of what TF autodiff returns (train/train.py:31-40).
+ * Pe == 0: no embedding part (kernel 'params'); E, task_id, task_off are ignored.
+ * The random Fourier map (num_of_rff > 0, feature_map.py:19-26) is not part of this entry point.
+ * workspace: distbo_blr_workspace(N, T, d, h1, h2, D) doubles. */
+int64_t distbo_blr_workspace(int64_t N, int T, int d, int h1, int h2, int D);
+int distbo_blr_fit_f64(const double* theta, const double* y, int N, int d, const double* E, int ldE, int Pe,
+                       const int32_t* task_id, const int32_t* task_off, int T, const double* W1,
+                       const double* b1, const double* W2, const double* b2, const double* W3, int n_layers,
+                       int h1, int h2, int D, const double* log_sigma, const double* log_alpha, double* Linv,
+                       double* evec, double* loss, int32_t* info, double* gW1, double* gb1, double* gW2,
+                       double* gb2, double* gW3, double* g_log_sigma, double* g_log_alpha, double* dE,
+                       double* workspace, int want_grad, void* stream);
+/* Posterior + acquisition + arg-max over candidates (build_predict_feature, :145-190; helpers.py:51-68,151-171):
+ * mean = (alpha/sigma^2) e^T L^-1 phi, var = alpha |L^-1 phi|^2, std = sqrt(max(var, 1e-32)).  cand [M,d] raw
+ * (cand_shift / cand_scale = frozen StandardScaler, or both NULL), emb [Pe] = embedding of the candidates' task.
+ * block_best_*: distbo_blr_score_blocks() entries.  Optional outputs may be NULL. */
+int distbo_blr_score_blocks(void);
+int distbo_blr_score_f64(const double* cand, const double* cand_shift, const double* cand_scale, int64_t M,
+                         int d, const double* emb, int Pe, const double* W1, const double* b1,
+                         const double* W2, const double* b2, const double* W3, int n_layers, int h1, int h2,
+                         int D, const double* Linv, const double* evec, const double* log_sigma,
+                         const double* log_alpha, int acq_kind, double y_max, double xi, double kappa,
+                         double* out_mean, double* out_std, double* out_acq, double* block_best_val,
+                         int64_t* block_best_idx, double* best_val, int64_t* best_idx, int64_t index_offset,
+                         void* stream);
 /* TF-1.7 Adam update on a flat parameter vector (train/gp_regressor.py:141; epsilon-hat form):
  * lr_t = lr sqrt(1 - beta2^step) / (1 - beta1^step); p -= lr_t m / (sqrt(v) + eps).  step is 1-based.
  * clip_norm <= 0 disables tf.clip_by_global_norm (train/train.py:33-35).

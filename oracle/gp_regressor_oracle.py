@@ -13,6 +13,7 @@ from sklearn.model_selection import train_test_split
 from sklearn.preprocessing import StandardScaler
 from sklearn.utils import check_random_state
 
+from . import blr_oracle as BO
 from . import gp_oracle as O
 
 
@@ -134,7 +135,8 @@ class OracleGPRegressor(object):
                        bw_params_init=1.0, likhd_var_init=0.01, stratify=True,
                        gradient_clip=False, first_early_stop_epoch=30):
         assert len(params) == len(y)
-        assert algorithm == "GP"
+        assert algorithm in ("GP", "BLR")
+        self.num_of_rff = num_of_rff
         self.target_embed = target_embed
         self.algorithm = algorithm
         self.embed_op = embed_op
@@ -156,7 +158,19 @@ class OracleGPRegressor(object):
         if self.initialise:
             kw = dict(likhd_var_init=likhd_var_init, bw_params_init=bw_params_init,
                       seed=self.seed if self.seed is not None else 23)
-            if self.kernel == "dist":
+            if algorithm == "BLR":                           # gp_regressor.py:70-74
+                self.n_tasks = len(sizes) if sizes is not None else None
+                self.p, self.rff_input_dim = BO.build_params_blr(
+                    self.in_dim_params, self.kernel, weight_dim, num_of_rff=num_of_rff,
+                    in_dim_x=getattr(self, "in_dim_x", None), in_dim_y=getattr(self, "in_dim_y", None),
+                    weight_dim_x=weight_dim_x, weight_dim_y=weight_dim_y, model_type=self.model_type,
+                    embed_op=embed_op, concat_data_size=concat_data_size,
+                    in_dim_meta=len(target_embed[0]) if self.kernel == "manual" else None,
+                    n_tasks=self.n_tasks, likhd_var_init=likhd_var_init, seed=kw["seed"])
+                if self.kernel == "dist":
+                    self.samp_target_X, self.samp_target_Y = sample(
+                        self.target_X, self.target_Y, embed_ind=self.target_embed_ind, source_list=False)
+            elif self.kernel == "dist":
                 self.p = O.build_params(self.in_dim_params, "dist", in_dim_x=self.in_dim_x,
                                         in_dim_y=self.in_dim_y, weight_dim_x=weight_dim_x,
                                         weight_dim_y=weight_dim_y, weight_dim_xy=weight_dim_xy,
@@ -211,8 +225,13 @@ class OracleGPRegressor(object):
         for epoch, (bX, by, es) in enumerate(loop_batches(self.train, batch_size, max_epochs, rs,
                                                           self.model_type, stratify=stratify)):
             batch = self._batch(bX, by, es)
-            loss, grads = O.loss_and_grads(self.p, self.kernel, batch, embed_op=self.embed_op,
-                                           model_type=self.model_type)
+            if self.algorithm == "BLR":
+                loss, grads = BO.blr_loss_and_grads(self.p, self.kernel, batch, self.rff_input_dim, self.num_of_rff,
+                                                    embed_op=self.embed_op, model_type=self.model_type,
+                                                    n_tasks=self.n_tasks)
+            else:
+                loss, grads = O.loss_and_grads(self.p, self.kernel, batch, embed_op=self.embed_op,
+                                               model_type=self.model_type)
             self.p = self.adam.step(self.p, grads, clip_norm=5.0 if gradient_clip else None)
             self.loss_history.append(loss)
             if epoch >= first_early_stop_epoch:
@@ -234,6 +253,8 @@ class OracleGPRegressor(object):
         """train/gp_regressor.py:159-198."""
         params_pred = self.params_scaler.transform(params_pred)
         B = O.NP
+        if self.algorithm == "BLR":
+            return self._predict_blr(params_pred, compute_embed)
         if self.kernel == "dist":
             batch = self._batch(self.samp_source_X, self.samp_source_Y,
                                 check_dims([len(s) for s in self.source_X]))
@@ -255,8 +276,45 @@ class OracleGPRegressor(object):
             mean, var = O.predict(B, self.p, self.kernel, batch, params_pred)
         return mean, O.std_from_var(var)
 
+    def _predict_blr(self, params_pred, compute_embed):
+        """gp_regressor.py:163-198 with algorithm == 'BLR' (build_predict_feature / build_predict_dist_feature)."""
+        B = O.NP
+        M = params_pred.shape[0]
+        if self.kernel == "dist":
+            batch = self._batch(self.samp_source_X, self.samp_source_Y,
+                                check_dims([len(s) for s in self.source_X]))
+            if compute_embed or self.pre_compute_embed:     # embed_network -> (dist_fea, dist_fea_pred)
+                self.dist = O.dist_features(B, self.p, batch.batch_X, batch.batch_y, batch.sizes,
+                                            batch.embed_sizes, data_sizes=batch.data_sizes,
+                                            max_size=batch.max_size, embed_op=self.embed_op,
+                                            model_type=self.model_type)
+                self.dist_pred = O.dist_features(B, self.p, self.samp_target_X, self.samp_target_Y, [1],
+                                                 check_dims([len(self.target_embed_ind)]),
+                                                 data_sizes=self.data_sizes_target, max_size=batch.max_size,
+                                                 embed_op=self.embed_op, model_type=self.model_type)
+                self.pre_compute_embed = bool(compute_embed)
+            fea = np.concatenate([self.dist, batch.h_params], 1)
+            fea_pred = np.concatenate([np.repeat(self.dist_pred, M, axis=0), params_pred], 1)
+        else:
+            batch = self._batch(None, None, None)
+            fea = BO.train_feature(B, self.p, self.kernel, batch, n_tasks=self.n_tasks)
+            if self.kernel == "manual":
+                emb = np.repeat(np.asarray(self.target_embed, dtype=np.float64), M, axis=0)
+                fea_pred = np.concatenate([emb, params_pred], 1)
+            elif self.kernel == "multi":
+                fea_pred = np.concatenate([BO.task_one_hot(B, self.n_tasks, [M], params_pred, pred=True),
+                                           params_pred], 1)
+            else:
+                fea_pred = params_pred
+        nn_fea = BO.nn_features(B, self.p, fea, self.rff_input_dim, self.num_of_rff)
+        nn_fea_pred = BO.nn_features(B, self.p, fea_pred, self.rff_input_dim, self.num_of_rff)
+        mean, var = BO.blr_predict(B, self.p, nn_fea, batch.obs, nn_fea_pred)
+        return mean, O.std_from_var(var)
+
     def similarity(self, sample_sim=False):
         """train/gp_regressor.py:205-223."""
+        if self.algorithm == "BLR":
+            return ['none']
         B = O.NP
         if self.kernel == "dist":
             batch = self._batch(self.samp_source_X, self.samp_source_Y,

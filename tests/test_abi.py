@@ -61,7 +61,8 @@ def test_sass_is_sm100a_with_fp64_tensor_ops():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     per_fn = sass.split("Function : ")[1:]
     for kernel in ("score_kernel", "gemm_tiles_kernel", "potf2_inv_kernel"):
-        bodies = [b for b in per_fn if kernel in b.split("\n", 1)[0]]
+        mangled = "%d%s" % (len(kernel), kernel)           # exact Itanium name component, not a substring
+        bodies = [b for b in per_fn if mangled in b.split("\n", 1)[0]]
         assert bodies and all("DMMA" in b for b in bodies), kernel
 
 

@@ -275,3 +275,42 @@ def test_multi_task_kernel_restatement():
     np.testing.assert_array_equal(O.task_kernel(O.NP, {"log_triangular_task": x}, sizes), k[np.ix_(t, t)])
     np.testing.assert_array_equal(O.task_kernel_pred(O.NP, {"log_triangular_task": x}, sizes, 4),
                                   np.repeat(k[t, -1][:, None], 4, axis=1))
+
+
+def test_blr_restatement_pins():
+    """algorithm='BLR' (log_gaus_likelihood_feature.py): the loss is -2 log N(y | 0, sigma^2 I + alpha Phi Phi^T)
+    - N log 2 pi (scipy), the posterior is the textbook weight-space posterior, and the random Fourier map
+    converges to sklearn's Matern(nu=1.5) kernel (the author's own check, RandomFourierMaternFeatureMapper.py:69-82)."""
+    from scipy.stats import multivariate_normal
+    from sklearn.gaussian_process.kernels import Matern
+    from oracle import blr_oracle as BO
+    rs = np.random.RandomState(4)
+    N, d, T = 40, 3, 4
+    sizes = [10] * T
+    theta, y = rs.randn(N, d), rs.randn(N, 1)
+    p, rff_in = BO.build_params_blr(d, "multi", [16, 12, 9], n_tasks=T, likhd_var_init=0.05, seed=3)
+    assert rff_in == 9 and p["weights__1"].shape == (T + d, 16) and p["weights__3"].shape == (12, 9)
+    p["log_alpha"] = np.asarray(0.3)
+    p["bias__1"] = rs.randn(16) * 0.1
+    p["bias__2"] = rs.randn(12) * 0.1
+    batch = O.TrainBatch(h_params=theta, obs=y, sizes=sizes)
+    loss = float(BO.blr_loss(O.NP, p, "multi", batch, rff_in, 0, n_tasks=T))
+    fea = BO.train_feature(O.NP, p, "multi", batch, n_tasks=T)
+    np.testing.assert_array_equal(fea[:, :T], np.eye(T)[np.repeat(np.arange(T), 10)])
+    phi = BO.nn_features(O.NP, p, fea, rff_in, 0)
+    sig2, alpha = np.exp(2 * p["log_sigma"]), np.exp(p["log_alpha"])
+    cov = sig2 * np.eye(N) + alpha * phi @ phi.T
+    want = -2.0 * multivariate_normal(np.zeros(N), cov).logpdf(y.ravel()) - N * np.log(2 * np.pi)
+    assert loss == pytest.approx(want, rel=1e-10)
+    # posterior: weights ~ N(0, alpha I)  =>  Sigma_w = (I/alpha + Phi^T Phi / sigma^2)^-1, m_w = Sigma_w Phi^T y / sigma^2
+    cand = np.concatenate([np.eye(T)[[T - 1] * 6], rs.randn(6, d)], 1)
+    phi_c = BO.nn_features(O.NP, p, cand, rff_in, 0)
+    mean, var = BO.blr_predict(O.NP, p, phi, y, phi_c)
+    Sw = np.linalg.inv(np.eye(9) / alpha + phi.T @ phi / sig2)
+    np.testing.assert_allclose(mean, phi_c @ (Sw @ phi.T @ y / sig2), rtol=1e-9)
+    np.testing.assert_allclose(var.ravel(), np.einsum("ij,jk,ik->i", phi_c, Sw, phi_c), rtol=1e-9)
+    # random Fourier map: E[phi(x) phi(x')^T] = Matern-3/2(x, x')
+    x = rs.randn(30, 2)
+    feat = BO.nn_features(O.NP, {"log_bw": np.zeros(2)}, x, 2, 40000)
+    assert feat.dtype == np.float64 and feat.shape == (30, 40000)
+    assert np.max(np.abs(feat @ feat.T - Matern(length_scale=1.0, nu=1.5)(x))) < 0.03
