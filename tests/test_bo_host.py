@@ -134,3 +134,47 @@ def test_bo_bookkeeping_matches_reference_rules():
     assert [c[1] for c in calls] == [[5, 5], [5, 5, 1], [5, 5, 2], [5, 5, 3]]
     assert [c[2] for c in calls] == [1, 1, 600, 600]
     assert [c[3] for c in calls] == [2, 3, 3, 3]
+
+
+def test_blr_warm_start_candidates():
+    """algorithm='BLR' with a transfer kernel (helpers.py:54-65): the one-shot acquisition is evaluated on the best
+    theta of every source task except the last one, the uniform draw still advances the stream, no polish."""
+    seen = {}
+
+    class GP:
+        def predict_y(self, x, compute_embed=False):
+            seen.setdefault('x', []).append(np.array(x))
+            return np.asarray(x)[:, :1] * 1.0, np.full((len(x), 1), 0.5)
+
+    util = UtilityFunction('ucb', 1.0, 0.0)
+    bounds = np.array([[0.0, 1.0], [0.0, 1.0]])
+    prev_X = np.arange(24, dtype=float).reshape(12, 2) / 24.0
+    prev_Y = np.array([0.1, 0.9, 0.3, 0.2, 0.5, 0.4, 0.8, 0.7, 0.0, 0.6, 0.95, 0.05])
+    rs = np.random.RandomState(0)
+    x = acq_max(util.utility, GP(), 0.0, bounds, rs, algorithm='BLR', kernel='dist', size_evals=[4, 5, 3],
+                prev_X=prev_X, prev_Y=prev_Y, n_warmup=50, n_iter=3)
+    np.testing.assert_array_equal(seen['x'][0], prev_X[[1, 4 + 2]])         # argmax of tasks 0 and 1 only
+    assert np.array_equal(x, prev_X[6])                                    # larger first coordinate -> larger UCB
+    assert rs.uniform() == np.random.RandomState(0).uniform(size=101)[-1]  # 50 x 2 draws were consumed
+    seen.clear()
+    acq_max(util.utility, GP(), 0.0, bounds, np.random.RandomState(0), algorithm='BLR', kernel='multi',
+            size_evals=[4, 5, 3], prev_X=prev_X, prev_Y=prev_Y, n_warmup=50, n_iter=3)
+    np.testing.assert_array_equal(seen['x'][0], prev_X[[1]])                # target dropped, then last source skipped
+
+
+def test_bo_loop_blr_with_oracle_regressor():
+    target, sources, supp = one_dim_split_tasks(0, 2, 1, n_train=40, n_test=40)
+    rs = np.random.RandomState(5)
+    init_list = []
+    for s in sources:
+        f, bounds, _, _ = set_model('toy', s, None)
+        th = rs.uniform(-8, 8, size=6)
+        init_list.append(np.column_stack([th, [f(theta=t) for t in th]]))
+    cfg = toy_optim_config(algorithm='BLR', weight_dim=[12, 12, 12], embed_op='joint')
+    out, sim = bayes_opt_wrap('dist', target, acq='ei', model='toy', rs=np.random.RandomState(11), optim_config=cfg,
+                              xi=0.01, kappa=2.58, bo_it=3, rand_it=0, init_list=init_list, include_init=False,
+                              source_data=sources, gp_class=OracleGPRegressor, verbose=0, acq_one_shot='lcb')
+    assert out.shape == (3, 2) and all(s == 'none' for s in np.ravel(sim))
+    # first suggestion = best theta of one of the first two source tasks (BLR warm start)
+    firsts = [init[np.argmax(init[:, 1]), 0] for init in init_list[:2]]
+    assert out[0, 0] in firsts
