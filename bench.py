@@ -386,6 +386,34 @@ def run_cuda(args):
     fit["fit_frac_of_fp64_peak"] = fit["fit_tflops"] / peak
     fit["fit_flops_counted"] = "N^3 (POTRF N^3/3 + inverse 2N^3/3), N=%d" % n_pad
 
+    # ---------------- secondary: the BLR surrogate (algorithm='BLR') on the same workload, N=1 only
+    blr = None
+    if world == 1 and not args.no_blr:
+        gb = gp_regressor("dist", target_X=work["data_X"][tgt], target_Y=work["data_Y"][tgt],
+                          model_type="classification", seed=0, target_embed_ind=np.arange(ROWS), float64=False)
+        kw = fit_kwargs(work, 20, args.lkh_var)
+        kw.update(algorithm="BLR", weight_dim=[50, 50, 50], num_of_rff=0)
+        gb.maximise_likhd(work["theta"], work["y"][:, None], **kw)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(50):
+            gb.run_epoch()
+        b1.record()
+        torch.cuda.synchronize()
+        gb.engine.read_loss()
+        for _ in range(2):
+            util.argmax(cand_host, gb, y_max)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            util.argmax(cand_host, gb, y_max)
+        torch.cuda.synchronize()
+        blr_ms = (time.perf_counter() - t0) * 1e3 / K
+        blr = {"what": "algorithm='BLR', weight_dim (50,50,50), num_of_rff 0 (the shipped BLR setting), same data",
+               "fit_ms": b0.elapsed_time(b1) / 50, "e2e_candidates_per_s": M / (blr_ms / 1e3), "e2e_ms_per_step": blr_ms}
+        gb.close()
+
     # ---------------- CPU baseline (N=1 only): the oracle port on a bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -417,7 +445,7 @@ def run_cuda(args):
             "handoff": {"refresh_ms": refresh_ms, "broadcast_ms": bcast_ms,
                         "what": "embed 65 full sample sets + task Gram + K + POTRF + TRTRI + V, then NCCL "
                                 "broadcast of W, V, theta, kvec"},
-            "best": {"index": best_resident[1], "value": best_resident[0]}}
+            "best": {"index": best_resident[1], "value": best_resident[0]}, "blr": blr}
     line.update(fit)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -435,6 +463,7 @@ def main():
     ap.add_argument("--lkh-var", type=float, default=1e-2)
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-blr", action="store_true", help="skip the secondary BLR-surrogate measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

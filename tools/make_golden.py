@@ -65,11 +65,68 @@ def stage_case(name, seed, T, per, d, dx, dy, rows, classification, embed_op, co
     print(name, "N=%d" % N, "nll=%.6f" % float(loss), "argmax(ei)=%d" % int(np.argmax(out["ei"])))
 
 
+def multi_case(name, seed, T, per, d):
+    """kernel 'multi' (train/kernels.py:32-55): loss, gradients, posterior, similarity."""
+    rs = np.random.RandomState(seed)
+    N, sizes = T * per, [per] * T
+    theta, y = rs.randn(N, d), rs.randn(N, 1)
+    p = O.build_params(d, "multi", n_tasks=T, likhd_var_init=1e-2, seed=seed)
+    p["log_bw"] = rs.randn(d) * 0.3
+    p["log_scale"] = np.array([0.1])
+    p["mean"] = np.array([0.05])
+    batch = O.TrainBatch(h_params=theta, obs=y, sizes=sizes)
+    loss, grads = O.loss_and_grads(p, "multi", batch)
+    cand = rs.randn(300, d) * 1.5
+    mean, var = O.predict(O.NP, p, "multi", batch, cand)
+    out = dict(theta=theta, y=y, sizes=np.array(sizes), cand=cand, nll=loss, mean=mean, var=var,
+               KE=O.task_kernel_matrix(O.NP, p, T), sim=O.similarity(O.NP, p, "multi", batch))
+    out.update({"p_" + k: np.asarray(v) for k, v in p.items()})
+    out.update({"g_" + k: np.asarray(v) for k, v in grads.items()})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "N=%d" % N, "nll=%.6f" % loss)
+
+
+def blr_case(name, seed, T, per, d, P, weight_dim):
+    """algorithm='BLR' on meta-features (train/log_gaus_likelihood_feature.py): loss, gradients, posterior."""
+    from oracle import blr_oracle as BO
+    rs = np.random.RandomState(seed)
+    N, sizes = T * per, [per] * T
+    theta, y = rs.randn(N, d), rs.randn(N, 1)
+    meta = rs.rand(T + 1, P)
+    p, rff_in = BO.build_params_blr(d, "manual", weight_dim, in_dim_meta=P, likhd_var_init=2e-2, seed=seed)
+    for k in p:
+        if k.startswith("bias"):
+            p[k] = rs.randn(*p[k].shape) * 0.2
+    p["log_alpha"] = np.asarray(0.25)
+    batch = O.TrainBatch(h_params=theta, obs=y, sizes=sizes, embed=meta[:T])
+    loss, grads = BO.blr_loss_and_grads(p, "manual", batch, rff_in, 0)
+    cand = rs.randn(300, d) * 1.5
+    phi = BO.nn_features(O.NP, p, BO.train_feature(O.NP, p, "manual", batch), rff_in, 0)
+    phi_c = BO.nn_features(O.NP, p, np.concatenate([np.repeat(meta[T:], 300, 0), cand], 1), rff_in, 0)
+    mean, var = BO.blr_predict(O.NP, p, phi, y, phi_c)
+    out = dict(theta=theta, y=y, sizes=np.array(sizes), meta=meta, cand=cand, loss=loss, mean=mean, var=var,
+               weight_dim=np.array(weight_dim))
+    out.update({"p_" + k: np.asarray(v) for k, v in p.items()})
+    out.update({"g_" + k: np.asarray(v) for k, v in grads.items()})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "N=%d" % N, "loss=%.6f" % loss)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--new-only" in sys.argv:      # the three original fixtures stay byte-identical
+        stage_case("stages_reg_concat", 104, T=4, per=30, d=2, dx=5, dy=1, rows=70, classification=False,
+                   embed_op="concat", concat=True)
+        multi_case("multi_small", 105, T=5, per=24, d=3)
+        blr_case("blr_manual", 106, T=4, per=33, d=3, P=7, weight_dim=[50, 50, 50])
+        sys.exit(0)
     stage_case("stages_class_concat", 101, T=4, per=40, d=3, dx=16, dy=2, rows=120, classification=True,
                embed_op="joint", concat=True)
     stage_case("stages_reg_joint", 102, T=3, per=50, d=2, dx=7, dy=1, rows=90, classification=False,
                embed_op="joint", concat=False)
     stage_case("stages_reg_none", 103, T=5, per=31, d=1, dx=1, dy=1, rows=200, classification=False,
                embed_op="none", concat=False)
+    stage_case("stages_reg_concat", 104, T=4, per=30, d=2, dx=5, dy=1, rows=70, classification=False,
+               embed_op="concat", concat=True)
+    multi_case("multi_small", 105, T=5, per=24, d=3)
+    blr_case("blr_manual", 106, T=4, per=33, d=3, P=7, weight_dim=[50, 50, 50])
