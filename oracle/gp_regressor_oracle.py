@@ -6,7 +6,6 @@ driven with either this class or the CUDA product and the trajectories compared.
 """
 from __future__ import annotations
 
-import random
 
 import numpy as np
 from sklearn.model_selection import train_test_split
@@ -44,12 +43,12 @@ def sample(data_X, data_Y, embed_ind=None, source_list=True):
 
 def loop_batches(train, batch_size, max_epochs, rs, model_type, stratify=False, shuffle_seed=0):
     """train/gp_utils.py:28-104.  The reference's stratified-classification branch uses the
-    unseeded global ``random.shuffle`` (:53,78); here a ``random.Random(shuffle_seed)`` is
-    used instead so the stream is reproducible."""
+    unseeded global ``random.shuffle`` (:53,78), so it has no reproducible stream of its own; a
+    ``numpy.random.RandomState(shuffle_seed).shuffle`` stands in for it."""
     if "X" in train and "y" in train:
         X_list, Y_list = train["X"], train["y"]
         n_datasets = len(X_list)
-        pyrand = random.Random(shuffle_seed)
+        pyrand = np.random.RandomState(shuffle_seed)
         if model_type == "classification":
             n_classes = Y_list[0].shape[1]
         if model_type == "classification" and stratify:
@@ -64,7 +63,7 @@ def loop_batches(train, batch_size, max_epochs, rs, model_type, stratify=False, 
                     class_y = np.argmax(dataY, axis=1)
                 c_l, c_r, c_i = [], [], []
                 for l in range(n_classes):
-                    index = np.where(class_y == l)[0].tolist()
+                    index = np.where(class_y == l)[0]
                     pyrand.shuffle(index)
                     c_l.append(index)
                     c_r.append(int((float(len(index)) / len(dataY)) * (batch_size + 4)))
@@ -88,7 +87,7 @@ def loop_batches(train, batch_size, max_epochs, rs, model_type, stratify=False, 
                                 pyrand.shuffle(cls_list[i][k])
                                 cls_index[i][k] = 0
                                 end = cls_ratio[i][k]
-                            class_index = class_index + cls_list[i][k][cls_index[i][k]:end]
+                            class_index = class_index + cls_list[i][k][cls_index[i][k]:end].tolist()
                             cls_index[i][k] = end
                         class_index = class_index[:batch_size]
                         sX, sY = dataX[class_index, :], dataY[class_index, :]
