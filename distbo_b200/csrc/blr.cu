@@ -241,15 +241,24 @@ __global__ void __launch_bounds__(256) blr_reduce_kernel(ReduceArgs a) {
   const ReduceSeg s = a.s[blockIdx.y];
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (!s.dst || i >= s.n) return;
+  const double* src = s.partial + s.off + i;
   double v = 0.0;
-  for (int t = 0; t < a.tiles; ++t) v += s.partial[(size_t)t * s.rec + s.off + i];
+  int t = 0;
+  for (; t + 8 <= a.tiles; t += 8) {      // eight loads in flight, added in tile order (fixed association)
+    double x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = src[(size_t)(t + u) * s.rec];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v += x[u];
+  }
+  for (; t < a.tiles; ++t) v += src[(size_t)t * s.rec];
   s.dst[i] = v;
 }
 
 // ---- D x D solve: A = I + c G, Cholesky, L^-1, e, loss and the seeds of the backward pass -------------------------
 struct SolveArgs {
-  const double *pGG, *pGy, *pyy;     // partials of Phi^T Phi, Phi^T y, y^T y
-  int tiles, N, D;
+  const double *G, *b, *yy;          // Phi^T Phi [D*D], Phi^T y [D], y^T y (already summed over the tiles)
+  int N, D;
   const double *log_sigma, *log_alpha;
   double *Linv, *evec;               // [BLR_W][BLR_W] (lower, zero padded), [BLR_W]
   double* loss;
@@ -268,57 +277,43 @@ __global__ void __launch_bounds__(BLR_THREADS) blr_solve_kernel(SolveArgs a) {
   double* e = b + BLR_W;
   double* w = e + BLR_W;
   double* red = w + BLR_W;                // [BLR_THREADS]
-  __shared__ double yy_s;
   __shared__ int bad;
   const int tid = threadIdx.x, D = a.D;
   const double sigma_sq = exp(2.0 * *a.log_sigma);
   const double s = 1.0 / sigma_sq;
   const double alpha = exp(*a.log_alpha);
   const double c = alpha * s;
+  const double yy_s = *a.yy;
   if (tid == 0) bad = 0;
   for (int idx = tid; idx < BLR_W * BLR_W; idx += BLR_THREADS) {
     const int i = idx / BLR_W, j = idx % BLR_W;
-    double g = 0.0;
-    if (i < D && j < D)
-      for (int t = 0; t < a.tiles; ++t) g += a.pGG[(size_t)t * (D * D + D) + i * D + j];
+    const double g = (i < D && j < D) ? a.G[i * D + j] : 0.0;
     G[idx] = g;
     L[idx] = (i < D && j < D) ? ((i == j ? 1.0 : 0.0) + c * g) : 0.0;
     Li[idx] = 0.0;
   }
-  if (tid < BLR_W) {
-    double v = 0.0;
-    if (tid < D)
-      for (int t = 0; t < a.tiles; ++t) v += a.pGy[(size_t)t * (D + 1) + tid];
-    b[tid] = v;
-  }
-  if (tid == BLR_W) {
-    double v = 0.0;
-    for (int t = 0; t < a.tiles; ++t) v += a.pyy[(size_t)t * 2];
-    yy_s = v;
-  }
+  if (tid < BLR_W) b[tid] = tid < D ? a.b[tid] : 0.0;
   __syncthreads();
-  // right-looking Cholesky of the D x D matrix in L (lower part)
+  // Right-looking Cholesky, one barrier per column: the trailing update uses the unscaled column,
+  // A[i][j] -= A[i][k] A[j][k] / A[k][k]; the columns are scaled by 1 / sqrt(pivot) afterwards.
   for (int k = 0; k < D; ++k) {
-    if (tid == 0) {
-      const double piv = L[k * BLR_W + k];
-      if (!(piv > 0.0) && !bad) bad = k + 1;
-      L[k * BLR_W + k] = sqrt(piv);
-    }
-    __syncthreads();
-    const double dk = L[k * BLR_W + k];
-    for (int i = k + 1 + tid; i < D; i += BLR_THREADS) L[i * BLR_W + k] /= dk;
-    __syncthreads();
+    const double piv = L[k * BLR_W + k];
+    if (tid == 0 && !(piv > 0.0) && !bad) bad = k + 1;
+    const double inv = 1.0 / piv;
     const int m = D - k - 1;
     for (int idx = tid; idx < m * m; idx += BLR_THREADS) {
       const int i = k + 1 + idx / m, j = k + 1 + idx % m;
-      if (j <= i) L[i * BLR_W + j] -= L[i * BLR_W + k] * L[j * BLR_W + k];
+      if (j <= i) L[i * BLR_W + j] -= L[i * BLR_W + k] * L[j * BLR_W + k] * inv;
     }
     __syncthreads();
   }
   for (int idx = tid; idx < D * D; idx += BLR_THREADS) {
     const int i = idx / D, j = idx % D;
     if (j > i) L[i * BLR_W + j] = 0.0;
+    else if (j < i) L[i * BLR_W + j] /= sqrt(L[j * BLR_W + j]);      // diagonal still holds the pivots
   }
+  __syncthreads();
+  if (tid < D) L[tid * BLR_W + tid] = sqrt(L[tid * BLR_W + tid]);
   __syncthreads();
   // L^-1: column j by forward substitution (thread = column)
   if (tid < D) {
@@ -457,7 +452,16 @@ __global__ void __launch_bounds__(BLR_W) blr_task_bwd_kernel(BlrNet net, const d
   __shared__ double s1[BLR_W];
   const int t = blockIdx.x, h = threadIdx.x;
   double v = 0.0;
-  for (int i = task_off[t]; i < task_off[t + 1]; ++i) v += DA1[(size_t)i * BLR_W + h];
+  int i = task_off[t];
+  const int i_end = task_off[t + 1];
+  for (; i + 8 <= i_end; i += 8) {
+    double x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = DA1[(size_t)(i + u) * BLR_W + h];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v += x[u];
+  }
+  for (; i < i_end; ++i) v += DA1[(size_t)i * BLR_W + h];
   s1[h] = v;
   S1[t * BLR_W + h] = v;
   __syncthreads();
@@ -477,7 +481,18 @@ __global__ void __launch_bounds__(256) blr_task_finish_kernel(BlrNet net, const 
   if (idx >= net.Pe * net.h1) return;
   const int p = idx / net.h1, h = idx % net.h1;
   double v = 0.0;
-  for (int t = 0; t < T; ++t) v = fma(E[(size_t)t * ldE + p], S1[t * BLR_W + h], v);
+  int t = 0;
+  for (; t + 8 <= T; t += 8) {            // loads in flight together, accumulated in task order
+    double x[8], y[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x[u] = E[(size_t)(t + u) * ldE + p];
+      y[u] = S1[(t + u) * BLR_W + h];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v = fma(x[u], y[u], v);
+  }
+  for (; t < T; ++t) v = fma(E[(size_t)t * ldE + p], S1[t * BLR_W + h], v);
   gW1[idx] = v;
 }
 
@@ -654,7 +669,7 @@ static inline int64_t blr_tiles(int64_t N) { return (N + BLR_R - 1) / BLR_R; }
 
 // workspace layout (doubles); T >= 1
 struct BlrWs {
-  double *c1, *S1, *H1, *H2, *Phi, *DPhi, *DZ2, *DA1, *Q, *rvec, *pGG, *pGy, *pyy, *pW3, *pW2, *pW1;
+  double *c1, *S1, *H1, *H2, *Phi, *DPhi, *DZ2, *DA1, *Q, *rvec, *G, *bvec, *pGG, *pGy, *pyy, *pW3, *pW2, *pW1;
   int64_t total;
 };
 static BlrWs blr_ws(double* base, int64_t N, int T, int d, int h1, int h2, int D) {
@@ -676,6 +691,8 @@ static BlrWs blr_ws(double* base, int64_t N, int T, int d, int h1, int h2, int D
   w.DA1 = take(N * BLR_W);
   w.Q = take(BLR_W * BLR_W);
   w.rvec = take(BLR_W);
+  w.G = take(BLR_W * BLR_W);
+  w.bvec = take(2 * BLR_W);
   w.pGG = take(tiles * ((int64_t)D * D + D));
   w.pGy = take(tiles * ((int64_t)D + 1));
   w.pyy = take(tiles * 2);
@@ -724,7 +741,14 @@ extern "C" int distbo_blr_fit_f64(const double* theta, const double* y, int N, i
   s.p[2] = {y, 1, 1, y, 1, 1, w.pyy};
   blr_atb_kernel<<<dim3(tiles, 3), BLR_THREADS, atb_smem, st>>>(s);
   DB_CHECK_LAUNCH();
-  SolveArgs sa{w.pGG, w.pGy, w.pyy, tiles, N, D, log_sigma, log_alpha, Linv, evec, loss, info,
+  ReduceArgs rs{};
+  rs.tiles = tiles;
+  rs.s[0] = {w.pGG, D * D + D, 0, D * D, w.G};
+  rs.s[1] = {w.pGy, D + 1, 0, D, w.bvec};
+  rs.s[2] = {w.pyy, 2, 0, 1, w.bvec + BLR_W};
+  blr_reduce_kernel<<<dim3((BLR_W * BLR_W + 255) / 256, 3), 256, 0, st>>>(rs);
+  DB_CHECK_LAUNCH();
+  SolveArgs sa{w.G, w.bvec, w.bvec + BLR_W, N, D, log_sigma, log_alpha, Linv, evec, loss, info,
                want_grad ? w.Q : nullptr, want_grad ? w.rvec : nullptr, want_grad ? g_log_sigma : nullptr,
                want_grad ? g_log_alpha : nullptr};
   blr_solve_kernel<<<1, BLR_THREADS, (4 * BLR_W * BLR_W + 3 * BLR_W + BLR_THREADS) * sizeof(double), st>>>(sa);
