@@ -45,6 +45,21 @@ struct Plan {
   std::vector<int> rest_after;   // [nb] index of the rest issued after panel kb, or -1
   std::vector<int> wait_rest;    // [nb] index of the rest panel kb must wait for, or -1
   std::vector<int> pend_lo;      // [nb]
+  // Near / far schedule (DISTBO_POTRF_FAR = W > 0): after panel kb the "near" update brings the next W block
+  // columns fully up to date (rank-128 steps, or a longer catch-up for a column that just entered the window);
+  // the columns far behind the window are updated only every G panels, with k = 128 G in one pass (higher
+  // arithmetic intensity, fewer passes over the trailing matrix), on a low-priority stream next to the
+  // panel / near chain.  Every tile carries its own k range, so both kinds are plain tile lists.
+  struct Step {
+    Range near{0, 0}, far{0, 0};
+    int near_wait_far = -1;        // far launch (step index) the near launch must wait for
+    double near_work = 0.0, far_work = 0.0;   // tiles x panels
+  };
+  std::vector<Step> steps;         // [nb] (empty: uniform schedule above)
+  std::vector<int> wait_near, wait_far;       // [nb] step whose near / far launch panel kb waits for, or -1
+  std::vector<cudaEvent_t> ev_near, ev_far;
+  cudaStream_t near_stream = nullptr, far_stream = nullptr;
+  cudaEvent_t ev_near_end = nullptr, ev_far_end = nullptr;
   Range lauum{0, 0};
   cudaStream_t panel_stream = nullptr;
   std::vector<cudaEvent_t> ev_panel, ev_first;
@@ -481,7 +496,7 @@ using namespace db;
 long long g_db_launches = 0;
 static unsigned long long* g_timeline = nullptr;
 
-// Debug aid (tools/potrf_timeline.py): device buffer of 2*nb*4 uint64 (init: slot 0 = ~0, others 0) that the
+// Debug aid (tools/potrf_timeline.py): device buffer of 3*nb*4 uint64 (init: slot 0 = ~0, others 0) that the
 // POTRF kernels fill with globaltimer stamps; pass NULL to switch it off.  Not part of the product path.
 extern "C" int distbo_debug_timeline(void* buf) {
   g_timeline = (unsigned long long*)buf;
@@ -541,6 +556,50 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
       p->wait_rest[c] = last;
     }
   }
+  {
+    // Measured on B200 (profiles/r01_potrf_schedule.txt): N = 8192 8.90 -> 8.42 ms with W = 4, G = 4 (W = 2..12 and
+    // G = 2 are within 2 % of that, G >= 6 is slower); N <= 4096 is faster with the uniform schedule, whose panel
+    // chain is the bound there.  Default: on from 56 column blocks (N >= 7168); DISTBO_POTRF_FAR=0 switches it off.
+    int W = nb >= 56 ? 4 : 0, G = 4;
+    if (const char* env = getenv("DISTBO_POTRF_FAR")) W = atoi(env);
+    if (const char* env = getenv("DISTBO_POTRF_FARG")) G = atoi(env);
+    if (W >= 2 && G >= 2 && nb >= 3 * G + W) {
+      std::vector<int> applied(nb, 0), last_near(nb, -1), last_far(nb, -1);
+      p->steps.assign(nb, Plan::Step());
+      p->wait_near.assign(nb, -1);
+      p->wait_far.assign(nb, -1);
+      for (int kb = 0; kb < nb; ++kb) {
+        p->pend_lo[kb] = applied[kb];          // the panel kernel applies [applied, kb) itself
+        p->wait_near[kb] = last_near[kb];
+        p->wait_far[kb] = last_far[kb];
+        Plan::Step& st = p->steps[kb];
+        std::vector<int4> nt;
+        for (int c = kb + 2; c < nb && c <= kb + W; ++c) {
+          for (int i = c; i < nb; ++i) nt.push_back(make_int4(T(i), T(c), T(applied[c]), T(kb + 1)));
+          st.near_work += (double)(nb - c) * (kb + 1 - applied[c]);
+          applied[c] = kb + 1;
+          st.near_wait_far = std::max(st.near_wait_far, last_far[c]);
+          last_near[c] = kb;
+        }
+        std::stable_sort(nt.begin(), nt.end(), longer_k);
+        st.near = Range{(int)tiles.size(), (int)nt.size()};
+        tiles.insert(tiles.end(), nt.begin(), nt.end());
+        if ((kb + 1) % G == 0) {
+          // columns that no near window of the next G steps reaches
+          std::vector<int4> ft;
+          for (int c = kb + 1 + G + W; c < nb; ++c) {
+            if (applied[c] >= kb + 1) continue;
+            for (int i = c; i < nb; ++i) ft.push_back(make_int4(T(i), T(c), T(applied[c]), T(kb + 1)));
+            st.far_work += (double)(nb - c) * (kb + 1 - applied[c]);
+            applied[c] = kb + 1;
+            last_far[c] = kb;
+          }
+          st.far = Range{(int)tiles.size(), (int)ft.size()};
+          tiles.insert(tiles.end(), ft.begin(), ft.end());
+        }
+      }
+    }
+  }
   std::vector<std::vector<TriNode>> levels;
   build_tri(0, nb, levels);
   for (size_t l = 1; l < levels.size(); ++l) {
@@ -581,6 +640,23 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
     cudaFree(p->d_tiles);
     delete p;
     return DISTBO_ECUDA;
+  }
+  if (!p->steps.empty()) {
+    const int mid = (lo + hi) / 2;       // priorities: panel (hi) > near (mid) > far (lo)
+    if (cudaStreamCreateWithPriority(&p->near_stream, cudaStreamNonBlocking, mid) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&p->far_stream, cudaStreamNonBlocking, lo) != cudaSuccess) {
+      cudaFree(p->d_tiles);
+      delete p;
+      return DISTBO_ECUDA;
+    }
+    p->ev_near.resize(nb);
+    p->ev_far.resize(nb);
+    for (int i = 0; i < nb; ++i) {
+      cudaEventCreateWithFlags(&p->ev_near[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&p->ev_far[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&p->ev_near_end, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&p->ev_far_end, cudaEventDisableTiming);
   }
   p->ev_panel.resize(nb);
   p->ev_first.resize(p->rests.size());   // "rest q is complete"
@@ -630,6 +706,12 @@ extern "C" int distbo_plan_destroy(void* plan) {
   for (auto e : p->ev_first) cudaEventDestroy(e);
   if (p->ev_begin) cudaEventDestroy(p->ev_begin);
   if (p->ev_end) cudaEventDestroy(p->ev_end);
+  for (auto e : p->ev_near) cudaEventDestroy(e);
+  for (auto e : p->ev_far) cudaEventDestroy(e);
+  if (p->ev_near_end) cudaEventDestroy(p->ev_near_end);
+  if (p->ev_far_end) cudaEventDestroy(p->ev_far_end);
+  if (p->near_stream) cudaStreamDestroy(p->near_stream);
+  if (p->far_stream) cudaStreamDestroy(p->far_stream);
   if (p->panel_stream) cudaStreamDestroy(p->panel_stream);
   if (p->d_tiles) cudaFree(p->d_tiles);
   if (p->d_flags) cudaFree(p->d_flags);
@@ -655,6 +737,59 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
     // CUDA-graph replays of the training step ~1 ms slower per launch.
     potrf_small_kernel<<<nb * (nb + 1) / 2, GEMM_THREADS, PANEL_SMEM, U>>>(sa);
     DB_CHECK_LAUNCH();
+    return DISTBO_OK;
+  }
+
+  if (!p->steps.empty() && p->lookahead) {
+    DB_CUDA(cudaMemsetAsync(p->d_flags, 0, (size_t)nb * NFLAG * sizeof(int), U));
+    GemmArgs upd{};   // C -= L[i, k range) L[j, k range)^T, k range per tile
+    upd.A = A; upd.B = A; upd.C = A; upd.Cin = A;
+    upd.lda = upd.ldb = upd.ldc = upd.ldcin = n;
+    upd.alpha = -1.0; upd.beta = 1.0;
+    upd.tl = g_timeline;
+    cudaStream_t P = p->panel_stream, Nn = p->near_stream, F = p->far_stream;
+    DB_CUDA(cudaEventRecord(p->ev_begin, U));
+    DB_CUDA(cudaStreamWaitEvent(P, p->ev_begin, 0));
+    DB_CUDA(cudaStreamWaitEvent(Nn, p->ev_begin, 0));
+    DB_CUDA(cudaStreamWaitEvent(F, p->ev_begin, 0));
+    double running = 0.0, far_share = 0.0;   // update work (tiles x panels) that runs next to the panel
+    int g_prev = 0;
+    for (int kb = 0; kb < nb; ++kb) {
+      if (p->wait_near[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_near[p->wait_near[kb]], 0));
+      if (p->wait_far[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_far[p->wait_far[kb]], 0));
+      const int g_this = panel_ctas(nb, kb, p->sms, (int)(running + far_share), kb - p->pend_lo[kb], 1);
+      const int use_relay = (p->relay_on && kb >= 1 && g_prev >= 2 && p->pend_lo[kb] <= kb - 1) ? 1 : 0;
+      PanelArgs pa{A, W, n, kb, nb, p->pend_lo[kb], info, p->d_flags, p->relay_on ? p->d_relay : nullptr, use_relay,
+                   g_timeline};
+      g_prev = g_this;
+      panel_kernel<<<g_this, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
+      DB_CHECK_LAUNCH();
+      const Plan::Step& st = p->steps[kb];
+      if (st.near.cnt > 0 || st.far.cnt > 0) DB_CUDA(cudaEventRecord(p->ev_panel[kb], P));
+      if (st.near.cnt > 0) {
+        DB_CUDA(cudaStreamWaitEvent(Nn, p->ev_panel[kb], 0));
+        if (st.near_wait_far >= 0) DB_CUDA(cudaStreamWaitEvent(Nn, p->ev_far[st.near_wait_far], 0));
+        upd.tiles = p->d_tiles + st.near.off;
+        upd.tl_id = 2 * kb + 1;
+        DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(upd, st.near.cnt, Nn)));
+        DB_CUDA(cudaEventRecord(p->ev_near[kb], Nn));
+      }
+      running = st.near_work;
+      if (st.far.cnt > 0) {
+        DB_CUDA(cudaStreamWaitEvent(F, p->ev_panel[kb], 0));
+        upd.tiles = p->d_tiles + st.far.off;
+        upd.tl_id = 2 * nb + kb;          // far launches have their own timeline rows (buffer: 3 nb rows)
+        DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(upd, st.far.cnt, F)));
+        DB_CUDA(cudaEventRecord(p->ev_far[kb], F));
+        far_share = st.far_work / 4.0;
+      }
+    }
+    DB_CUDA(cudaEventRecord(p->ev_end, P));
+    DB_CUDA(cudaEventRecord(p->ev_near_end, Nn));
+    DB_CUDA(cudaEventRecord(p->ev_far_end, F));
+    DB_CUDA(cudaStreamWaitEvent(U, p->ev_end, 0));
+    DB_CUDA(cudaStreamWaitEvent(U, p->ev_near_end, 0));
+    DB_CUDA(cudaStreamWaitEvent(U, p->ev_far_end, 0));
     return DISTBO_OK;
   }
 

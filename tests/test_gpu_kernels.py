@@ -113,6 +113,34 @@ def test_cholesky_inverse(cuda_engine_mod, N):
         assert not e.V.cpu().numpy()[N:].any() and not e.alpha.cpu().numpy()[N:].any()
 
 
+@pytest.mark.parametrize("far,group", [("3", "2"), ("6", "4"), ("0", "4")])
+def test_potrf_schedules_agree(cuda_engine_mod, monkeypatch, far, group):
+    """The near / far trailing-update schedule (DISTBO_POTRF_FAR / _FARG; default at N >= 7168) and the uniform one
+    give the same factor, inverse and likelihood at a size the multi-launch path handles (n_pad = 3328: 26 column
+    blocks, above the single-launch kernel's 16)."""
+    eng = cuda_engine_mod
+    monkeypatch.setenv("DISTBO_POTRF_FAR", far)
+    monkeypatch.setenv("DISTBO_POTRF_FARG", group)
+    N = 3300
+    eng.Plans._cache.pop((torch.cuda.current_device(), eng.round_up(N, 128)), None)   # the schedule is chosen when the plan is built
+    rs, theta, y, _ = make_problem(N, 4, seed=3)
+    e = setup_engine(eng, theta, y)
+    Kfull = torch.tril(e.K[:N, :N].clone())
+    Kfull = Kfull + torch.tril(Kfull, -1).T
+    e.factorize(need_inverse=True, need_kinv=True)
+    e.likelihood()
+    nll = e.read_loss()
+    Lref = torch.linalg.cholesky(Kfull)
+    assert rel(torch.tril(e.K[:N, :N]).cpu().numpy(), Lref.cpu().numpy()) < 1e-11
+    Wref = torch.linalg.solve_triangular(Lref, torch.eye(N, dtype=torch.float64, device=e.dev), upper=False)
+    assert rel(torch.tril(e.W[:N, :N]).cpu().numpy(), Wref.cpu().numpy()) < 1e-9
+    yc = torch.from_numpy(y - float(e.params.get("mean")[0])).to(e.dev)
+    a = torch.linalg.solve_triangular(Lref, yc[:, None], upper=False)
+    ref = float(0.5 * (a * a).sum() + 0.5 * N * np.log(2 * np.pi) + torch.log(torch.diagonal(Lref)).sum())
+    assert abs(nll - ref) <= 1e-10 * abs(ref)
+    eng.Plans._cache.pop((torch.cuda.current_device(), eng.round_up(N, 128)), None)
+
+
 def test_cholesky_not_pd_raises(cuda_engine_mod):
     rs, theta, y, _ = make_problem(150, 2)
     e = setup_engine(cuda_engine_mod, theta, y)

@@ -21,7 +21,7 @@ def potrf():
 for _ in range(3):
     potrf()
 torch.cuda.synchronize()
-buf = torch.zeros(2 * nb, 4, dtype=torch.int64, device=e.dev)
+buf = torch.zeros(3 * nb, 4, dtype=torch.int64, device=e.dev)
 buf[:, 0] = torch.iinfo(torch.int64).max     # atomicMin target (as unsigned: large)
 e.lib.distbo_debug_timeline(_lib.ptr(buf))
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -33,11 +33,13 @@ e.lib.distbo_debug_timeline(None)
 t = buf.cpu().numpy().astype(np.float64)
 t0 = t[0, 0]
 print("potrf %.3f ms (instrumented), info %d" % (a.elapsed_time(b), int(e.info.item())))
-print("%3s | %9s %9s %9s %9s | %9s %9s | %7s %7s %7s" % ("kb", "p.start", "potf2", "publish", "p.end", "r.start", "r.end", "upd", "potf2", "solve"))
+print("%3s | %9s %9s %9s %9s | %9s %9s | %7s %7s %7s | %9s %9s" % ("kb", "p.start", "potf2", "publish", "p.end", "r.start", "r.end", "upd", "potf2", "solve", "far.start", "far.end"))
 for kb in range(nb):
     p = (t[2 * kb] - t0) / 1e3
     r = (t[2 * kb + 1] - t0) / 1e3
     has_r = t[2 * kb + 1, 1] > 0
-    print("%3d | %9.1f %9.1f %9.1f %9.1f | %9s %9s | %7.1f %7.1f %7.1f" % (
+    f = (t[2 * nb + kb] - t0) / 1e3
+    has_f = t[2 * nb + kb, 1] > 0
+    print("%3d | %9.1f %9.1f %9.1f %9.1f | %9s %9s | %7.1f %7.1f %7.1f | %9s %9s" % (
         kb, p[0], p[2], p[3], p[1], ("%9.1f" % r[0]) if has_r else "-", ("%9.1f" % r[1]) if has_r else "-",
-        p[2] - p[0], p[3] - p[2], p[1] - p[3]))
+        p[2] - p[0], p[3] - p[2], p[1] - p[3], ("%9.1f" % f[0]) if has_f else "-", ("%9.1f" % f[1]) if has_f else "-"))
