@@ -50,16 +50,27 @@ struct Plan {
   // the columns far behind the window are updated only every G panels, with k = 128 G in one pass (higher
   // arithmetic intensity, fewer passes over the trailing matrix), on a low-priority stream next to the
   // panel / near chain.  Every tile carries its own k range, so both kinds are plain tile lists.
+  // The near launch is split in two: "next" = column kb+2 alone (the only one panel kb+2 waits for: <= 62 tiles, so
+  // it is short and never the bound of the panel chain) and "window" = columns kb+4 .. kb+W on a stream of its own
+  // (column kb+3 is left to the next step's "next" launch, which catches it up with k = 256).
   struct Step {
-    Range near{0, 0}, far{0, 0};
-    int near_wait_far = -1;        // far launch (step index) the near launch must wait for
-    double near_work = 0.0, far_work = 0.0;   // tiles x panels
+    Range next{0, 0}, window{0, 0}, far{0, 0};
+    int next_wait_window = -1, next_wait_far = -1;   // earlier launches (step index) on the same tiles
+    int window_wait_far = -1;
+    double near_work = 0.0, far_work = 0.0;          // tiles x panels
   };
   std::vector<Step> steps;         // [nb] (empty: uniform schedule above)
-  std::vector<int> wait_near, wait_far;       // [nb] step whose near / far launch panel kb waits for, or -1
-  std::vector<cudaEvent_t> ev_near, ev_far;
-  cudaStream_t near_stream = nullptr, far_stream = nullptr;
-  cudaEvent_t ev_near_end = nullptr, ev_far_end = nullptr;
+  std::vector<int> wait_next, wait_window, wait_far;   // [nb] step whose launch panel kb waits for, or -1
+  std::vector<cudaEvent_t> ev_next, ev_window, ev_far;
+  cudaStream_t near_stream = nullptr, window_stream = nullptr, far_stream = nullptr;
+  cudaEvent_t ev_near_end = nullptr, ev_window_end = nullptr, ev_far_end = nullptr;
+  // chained panels: even / odd column blocks on two streams, dependencies between consecutive panels through
+  // device flags (PanelArgs::done / relay_ready), so potf2(kb+1) starts as soon as the relay product is there
+  // instead of after the last consumer of panel kb has left
+  bool chain = false;
+  cudaStream_t panel_stream2 = nullptr;
+  cudaEvent_t ev_end2 = nullptr;
+  int* d_done = nullptr;           // [nb * nb] done flags followed by [nb + 1] relay_ready flags
   Range lauum{0, 0};
   cudaStream_t panel_stream = nullptr;
   std::vector<cudaEvent_t> ev_panel, ev_first;
@@ -86,6 +97,14 @@ struct Plan {
 // The chain update -> potf2 -> solve therefore costs one launch, no global round trip of the tile, and the
 // solve / next-diagonal update overlap the factorisation.  Waiting CTAs only ever wait for block 0 of their
 // own grid (<= 64 CTAs, all resident on 148 SMs).
+__device__ __forceinline__ void wait_flag(int* f) {
+  if (threadIdx.x == 0) {
+    while (atomicAdd(f, 0) == 0) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 struct PanelArgs {
   double* A;
   double* W;
@@ -96,6 +115,11 @@ struct PanelArgs {
   double* relay;            // [2][128*128]: L[kb+1,kb] L[kb+1,kb]^T from the relay CTA of the previous launch
   int use_relay;            // this launch's diagonal tile takes panel kb-1's update from `relay`
   unsigned long long* tl;   // debug timeline, normally null
+  // Chained mode (consecutive panels on alternating streams, overlapping in time): what panel kb needs from panel
+  // kb-1 arrives through flags instead of the launch boundary.  done[q * nb + i] = L[i, q] is final;
+  // relay_ready[kb] = the relay product for diagonal tile kb is in `relay`.  Null: launches are serialised.
+  int* done;
+  int* relay_ready;
 };
 
 constexpr int PANEL_SMEM = (PB * PLD + STAGES * STAGE_ELEMS) * (int)sizeof(double);  // 217088 >= POTF2_SMEM
@@ -264,8 +288,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
     const bool diag = blockIdx.x == 0;
     // the diagonal tile may take the update of panel kb-1 from the relay product of the previous launch
     const int k_hi = (diag && p.use_relay) ? n0 - BN : n0;
+    if (p.done && kb >= 1 && p.pend_lo <= kb - 1 && k_hi == n0) {
+      // panel kb-1 may still be running (older panels are complete: same stream): its rows i and kb
+      wait_flag(p.done + (kb - 1) * nb + i);
+      if (!diag) wait_flag(p.done + (kb - 1) * nb + kb);
+    }
     if (p.pend_lo * BN < k_hi) gemm_mainloop<KMAJOR, KMAJOR>(acc, p.A, ld, p.A, ld, m0, n0, p.pend_lo * BN, k_hi, smem);
     if (diag && p.use_relay) {
+      if (p.relay_ready) wait_flag(p.relay_ready + kb);
       const double* P = p.relay + (size_t)(kb & 1) * PB * PB;
 #pragma unroll
       for (int mi = 0; mi < 8; ++mi) {
@@ -273,7 +303,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
           const int c = wn * 32 + ni * 8 + lk * 2;
-          const double2 v = *reinterpret_cast<const double2*>(P + (size_t)r * PB + c);
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(P + (size_t)r * PB + c));   // L2: may be fresh
           acc[mi][ni][0] += v.x;   // acc holds -(tile): tile = A - pending - P
           acc[mi][ni][1] += v.y;
         }
@@ -314,6 +344,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
       const int* sub = p.flags + kb * NFLAG;
       if (relay) stepwise_solve<true>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, p.relay + (size_t)((kb + 1) & 1) * PB * PB);
       else stepwise_solve<false>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, nullptr);
+      if (p.done && tid == 0) {   // stepwise_solve ended with a barrier: cumulative fence, then publish
+        __threadfence();
+        atomicExch(p.done + kb * nb + i, 1);
+        if (relay) atomicExch(p.relay_ready + kb + 1, 1);
+      }
     }
   }
   tl_end(p.tl, 2 * kb);
@@ -340,14 +375,6 @@ struct SmallArgs {
   int* sub;    // [nbt][4]
   int* xf;     // [nbt][4]
 };
-
-__device__ __forceinline__ void wait_flag(int* f) {
-  if (threadIdx.x == 0) {
-    while (atomicAdd(f, 0) == 0) __nanosleep(64);
-    __threadfence();
-  }
-  __syncthreads();
-}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_small_kernel(SmallArgs p) {
   extern __shared__ __align__(16) double smem[];
@@ -557,40 +584,58 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
     }
   }
   {
-    // Measured on B200 (profiles/r01_potrf_schedule.txt): N = 8192 8.90 -> 8.42 ms with W = 4, G = 4 (W = 2..12 and
-    // G = 2 are within 2 % of that, G >= 6 is slower); N <= 4096 is faster with the uniform schedule, whose panel
-    // chain is the bound there.  Default: on from 56 column blocks (N >= 7168); DISTBO_POTRF_FAR=0 switches it off.
-    int W = nb >= 56 ? 4 : 0, G = 4;
+    // Measured on B200 (profiles/r01_potrf_schedule.txt): Gram + POTRF as a CUDA graph at N = 8192 8.97 -> 8.31 ms
+    // with W = 6, G = 4 (W = 4..8 within 1 %, W = 12 or G = 2 slower); N <= 4096 is faster with the uniform
+    // schedule, whose panel chain is the bound there.  Default: on from 56 column blocks (N >= 7168);
+    // DISTBO_POTRF_FAR=0 switches it off.
+    int W = nb >= 56 ? 6 : 0, G = 4;
     if (const char* env = getenv("DISTBO_POTRF_FAR")) W = atoi(env);
     if (const char* env = getenv("DISTBO_POTRF_FARG")) G = atoi(env);
     if (W >= 2 && G >= 2 && nb >= 3 * G + W) {
-      std::vector<int> applied(nb, 0), last_near(nb, -1), last_far(nb, -1);
+      std::vector<int> applied(nb, 0), last_next(nb, -1), last_window(nb, -1), last_far(nb, -1);
       p->steps.assign(nb, Plan::Step());
-      p->wait_near.assign(nb, -1);
+      p->wait_next.assign(nb, -1);
+      p->wait_window.assign(nb, -1);
       p->wait_far.assign(nb, -1);
+      auto column_tiles = [&](std::vector<int4>& out, int c, int upto) {
+        for (int i = c; i < nb; ++i) out.push_back(make_int4(T(i), T(c), T(applied[c]), T(upto)));
+        return (double)(nb - c) * (upto - applied[c]);
+      };
       for (int kb = 0; kb < nb; ++kb) {
         p->pend_lo[kb] = applied[kb];          // the panel kernel applies [applied, kb) itself
-        p->wait_near[kb] = last_near[kb];
+        p->wait_next[kb] = last_next[kb];
+        p->wait_window[kb] = last_window[kb];
         p->wait_far[kb] = last_far[kb];
         Plan::Step& st = p->steps[kb];
-        std::vector<int4> nt;
-        for (int c = kb + 2; c < nb && c <= kb + W; ++c) {
-          for (int i = c; i < nb; ++i) nt.push_back(make_int4(T(i), T(c), T(applied[c]), T(kb + 1)));
-          st.near_work += (double)(nb - c) * (kb + 1 - applied[c]);
+        if (kb + 2 < nb) {
+          const int c = kb + 2;
+          std::vector<int4> nt;
+          st.near_work += column_tiles(nt, c, kb + 1);
           applied[c] = kb + 1;
-          st.near_wait_far = std::max(st.near_wait_far, last_far[c]);
-          last_near[c] = kb;
+          st.next_wait_window = last_window[c];
+          st.next_wait_far = last_far[c];
+          last_next[c] = kb;
+          st.next = Range{(int)tiles.size(), (int)nt.size()};
+          tiles.insert(tiles.end(), nt.begin(), nt.end());
         }
-        std::stable_sort(nt.begin(), nt.end(), longer_k);
-        st.near = Range{(int)tiles.size(), (int)nt.size()};
-        tiles.insert(tiles.end(), nt.begin(), nt.end());
+        {
+          std::vector<int4> wt;
+          for (int c = kb + 4; c < nb && c <= kb + W; ++c) {
+            st.near_work += column_tiles(wt, c, kb + 1);
+            applied[c] = kb + 1;
+            st.window_wait_far = std::max(st.window_wait_far, last_far[c]);
+            last_window[c] = kb;
+          }
+          std::stable_sort(wt.begin(), wt.end(), longer_k);
+          st.window = Range{(int)tiles.size(), (int)wt.size()};
+          tiles.insert(tiles.end(), wt.begin(), wt.end());
+        }
         if ((kb + 1) % G == 0) {
-          // columns that no near window of the next G steps reaches
+          // columns that no near launch of the next G steps reaches
           std::vector<int4> ft;
           for (int c = kb + 1 + G + W; c < nb; ++c) {
             if (applied[c] >= kb + 1) continue;
-            for (int i = c; i < nb; ++i) ft.push_back(make_int4(T(i), T(c), T(applied[c]), T(kb + 1)));
-            st.far_work += (double)(nb - c) * (kb + 1 - applied[c]);
+            st.far_work += column_tiles(ft, c, kb + 1);
             applied[c] = kb + 1;
             last_far[c] = kb;
           }
@@ -643,20 +688,36 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
   }
   if (!p->steps.empty()) {
     const int mid = (lo + hi) / 2;       // priorities: panel (hi) > near (mid) > far (lo)
+    const int wprio = mid + (lo > hi ? 1 : -1) * (mid != lo ? 1 : 0);   // one step towards the low end
     if (cudaStreamCreateWithPriority(&p->near_stream, cudaStreamNonBlocking, mid) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&p->window_stream, cudaStreamNonBlocking, wprio) != cudaSuccess ||
         cudaStreamCreateWithPriority(&p->far_stream, cudaStreamNonBlocking, lo) != cudaSuccess) {
       cudaFree(p->d_tiles);
       delete p;
       return DISTBO_ECUDA;
     }
-    p->ev_near.resize(nb);
+    p->ev_next.resize(nb);
+    p->ev_window.resize(nb);
     p->ev_far.resize(nb);
     for (int i = 0; i < nb; ++i) {
-      cudaEventCreateWithFlags(&p->ev_near[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&p->ev_next[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&p->ev_window[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&p->ev_far[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&p->ev_near_end, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&p->ev_window_end, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&p->ev_far_end, cudaEventDisableTiming);
+    // measured: no gain at N = 8192 (8.31 ms either way, the panels' stream-level waits decide when they start),
+    // 2-3 % at N = 3000-4096 where this schedule is not the default; off unless DISTBO_POTRF_CHAIN=1
+    const char* ch = getenv("DISTBO_POTRF_CHAIN");
+    p->chain = ch ? ch[0] != '0' : false;
+    if (p->chain) {
+      if (cudaStreamCreateWithPriority(&p->panel_stream2, cudaStreamNonBlocking, hi) != cudaSuccess ||
+          cudaMalloc(&p->d_done, (size_t)(nb * nb + nb + 1) * sizeof(int)) != cudaSuccess)
+        p->chain = false;
+      else
+        cudaEventCreateWithFlags(&p->ev_end2, cudaEventDisableTiming);
+    }
   }
   p->ev_panel.resize(nb);
   p->ev_first.resize(p->rests.size());   // "rest q is complete"
@@ -706,10 +767,16 @@ extern "C" int distbo_plan_destroy(void* plan) {
   for (auto e : p->ev_first) cudaEventDestroy(e);
   if (p->ev_begin) cudaEventDestroy(p->ev_begin);
   if (p->ev_end) cudaEventDestroy(p->ev_end);
-  for (auto e : p->ev_near) cudaEventDestroy(e);
+  for (auto e : p->ev_next) cudaEventDestroy(e);
+  for (auto e : p->ev_window) cudaEventDestroy(e);
   for (auto e : p->ev_far) cudaEventDestroy(e);
   if (p->ev_near_end) cudaEventDestroy(p->ev_near_end);
+  if (p->ev_window_end) cudaEventDestroy(p->ev_window_end);
+  if (p->window_stream) cudaStreamDestroy(p->window_stream);
   if (p->ev_far_end) cudaEventDestroy(p->ev_far_end);
+  if (p->panel_stream2) cudaStreamDestroy(p->panel_stream2);
+  if (p->ev_end2) cudaEventDestroy(p->ev_end2);
+  if (p->d_done) cudaFree(p->d_done);
   if (p->near_stream) cudaStreamDestroy(p->near_stream);
   if (p->far_stream) cudaStreamDestroy(p->far_stream);
   if (p->panel_stream) cudaStreamDestroy(p->panel_stream);
@@ -747,32 +814,53 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
     upd.lda = upd.ldb = upd.ldc = upd.ldcin = n;
     upd.alpha = -1.0; upd.beta = 1.0;
     upd.tl = g_timeline;
-    cudaStream_t P = p->panel_stream, Nn = p->near_stream, F = p->far_stream;
+    cudaStream_t Pst[2] = {p->panel_stream, p->chain ? p->panel_stream2 : p->panel_stream};
+    cudaStream_t Nn = p->near_stream, Nw = p->window_stream, F = p->far_stream;
+    int* done = p->chain ? p->d_done : nullptr;
+    int* relay_ready = p->chain ? p->d_done + nb * nb : nullptr;
+    if (p->chain) DB_CUDA(cudaMemsetAsync(p->d_done, 0, (size_t)(nb * nb + nb + 1) * sizeof(int), U));
     DB_CUDA(cudaEventRecord(p->ev_begin, U));
-    DB_CUDA(cudaStreamWaitEvent(P, p->ev_begin, 0));
+    DB_CUDA(cudaStreamWaitEvent(Pst[0], p->ev_begin, 0));
+    if (p->chain) DB_CUDA(cudaStreamWaitEvent(Pst[1], p->ev_begin, 0));
     DB_CUDA(cudaStreamWaitEvent(Nn, p->ev_begin, 0));
+    DB_CUDA(cudaStreamWaitEvent(Nw, p->ev_begin, 0));
     DB_CUDA(cudaStreamWaitEvent(F, p->ev_begin, 0));
     double running = 0.0, far_share = 0.0;   // update work (tiles x panels) that runs next to the panel
     int g_prev = 0;
     for (int kb = 0; kb < nb; ++kb) {
-      if (p->wait_near[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_near[p->wait_near[kb]], 0));
-      if (p->wait_far[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_far[p->wait_far[kb]], 0));
       const int g_this = panel_ctas(nb, kb, p->sms, (int)(running + far_share), kb - p->pend_lo[kb], 1);
+      // While the trailing updates are the bound, a panel runs on few SMs for a long time and its successor would
+      // only spin next to it: consecutive panels overlap (alternate streams) once every row block has its own CTA,
+      // i.e. when the panel chain is the bound.  Panel kb-2 is complete either way (same stream, or through the
+      // "next" launch of step kb-2 that panel kb waits for).
+      cudaStream_t P = (g_this == nb - kb) ? Pst[kb & 1] : Pst[0];
+      if (p->wait_next[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_next[p->wait_next[kb]], 0));
+      if (p->wait_window[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_window[p->wait_window[kb]], 0));
+      if (p->wait_far[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_far[p->wait_far[kb]], 0));
       const int use_relay = (p->relay_on && kb >= 1 && g_prev >= 2 && p->pend_lo[kb] <= kb - 1) ? 1 : 0;
       PanelArgs pa{A, W, n, kb, nb, p->pend_lo[kb], info, p->d_flags, p->relay_on ? p->d_relay : nullptr, use_relay,
-                   g_timeline};
+                   g_timeline, done, relay_ready};
       g_prev = g_this;
       panel_kernel<<<g_this, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
       DB_CHECK_LAUNCH();
       const Plan::Step& st = p->steps[kb];
-      if (st.near.cnt > 0 || st.far.cnt > 0) DB_CUDA(cudaEventRecord(p->ev_panel[kb], P));
-      if (st.near.cnt > 0) {
+      if (st.next.cnt > 0 || st.window.cnt > 0 || st.far.cnt > 0) DB_CUDA(cudaEventRecord(p->ev_panel[kb], P));
+      if (st.next.cnt > 0) {
         DB_CUDA(cudaStreamWaitEvent(Nn, p->ev_panel[kb], 0));
-        if (st.near_wait_far >= 0) DB_CUDA(cudaStreamWaitEvent(Nn, p->ev_far[st.near_wait_far], 0));
-        upd.tiles = p->d_tiles + st.near.off;
+        if (st.next_wait_window >= 0) DB_CUDA(cudaStreamWaitEvent(Nn, p->ev_window[st.next_wait_window], 0));
+        if (st.next_wait_far >= 0) DB_CUDA(cudaStreamWaitEvent(Nn, p->ev_far[st.next_wait_far], 0));
+        upd.tiles = p->d_tiles + st.next.off;
         upd.tl_id = 2 * kb + 1;
-        DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(upd, st.near.cnt, Nn)));
-        DB_CUDA(cudaEventRecord(p->ev_near[kb], Nn));
+        DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(upd, st.next.cnt, Nn)));
+        DB_CUDA(cudaEventRecord(p->ev_next[kb], Nn));
+      }
+      if (st.window.cnt > 0) {
+        DB_CUDA(cudaStreamWaitEvent(Nw, p->ev_panel[kb], 0));
+        if (st.window_wait_far >= 0) DB_CUDA(cudaStreamWaitEvent(Nw, p->ev_far[st.window_wait_far], 0));
+        upd.tiles = p->d_tiles + st.window.off;
+        upd.tl_id = 2 * kb + 1;
+        DB_CUDA((launch_gemm_tiles<KMAJOR, KMAJOR>(upd, st.window.cnt, Nw)));
+        DB_CUDA(cudaEventRecord(p->ev_window[kb], Nw));
       }
       running = st.near_work;
       if (st.far.cnt > 0) {
@@ -784,11 +872,17 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
         far_share = st.far_work / 4.0;
       }
     }
-    DB_CUDA(cudaEventRecord(p->ev_end, P));
+    DB_CUDA(cudaEventRecord(p->ev_end, Pst[0]));
+    if (p->chain) {
+      DB_CUDA(cudaEventRecord(p->ev_end2, Pst[1]));
+      DB_CUDA(cudaStreamWaitEvent(U, p->ev_end2, 0));
+    }
     DB_CUDA(cudaEventRecord(p->ev_near_end, Nn));
+    DB_CUDA(cudaEventRecord(p->ev_window_end, Nw));
     DB_CUDA(cudaEventRecord(p->ev_far_end, F));
     DB_CUDA(cudaStreamWaitEvent(U, p->ev_end, 0));
     DB_CUDA(cudaStreamWaitEvent(U, p->ev_near_end, 0));
+    DB_CUDA(cudaStreamWaitEvent(U, p->ev_window_end, 0));
     DB_CUDA(cudaStreamWaitEvent(U, p->ev_far_end, 0));
     return DISTBO_OK;
   }
@@ -815,7 +909,7 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
       // the previous launch had a relay CTA (row block kb) whenever it had more than one CTA
       const int use_relay = (p->relay_on && kb >= 1 && g_prev >= 2 && p->pend_lo[kb] <= kb - 1) ? 1 : 0;
       PanelArgs pa{A, W, n, kb, nb, p->pend_lo[kb], info, p->d_flags, p->relay_on ? p->d_relay : nullptr, use_relay,
-                   g_timeline};
+                   g_timeline, nullptr, nullptr};
       g_prev = g_this;
       panel_kernel<<<g_this, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
       DB_CHECK_LAUNCH();
