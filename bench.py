@@ -288,6 +288,9 @@ def run_cuda(args):
     # ---------------- handoff: posterior state on rank 0, broadcast to the scoring ranks
     gp._fit_generation += 1
     gp._prepare_predict()          # first hand-off also stages the prediction sample sets (one-time)
+    eng = gp.engine
+    gp.shards.broadcast_fit([eng.W, eng.V, eng.theta_s, eng.sqnorm, eng.kvec, eng.params.flat], src=0)   # untimed:
+    #                                NCCL sets up its channels / buffers on the first broadcast of this size
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     torch.cuda.synchronize()
     e0.record()
