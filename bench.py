@@ -165,6 +165,33 @@ def cpu_reference(work, lkh_var, m_sample, steps, warmup, params_override=None):
     return t_fixed, t_var, best
 
 
+def cpu_fit_reference(work, lkh_var, params_override=None):
+    """One evaluation of the loss and its full gradient on the host (oracle restatement: the reference's graph
+    evaluated with torch-CPU autograd standing in for TF's, all host threads) on the training mini-batch shape
+    of the CUDA fit step (first BATCH_ROWS rows per dataset).  Returns (seconds, loss)."""
+    from oracle import gp_oracle as O
+    import torch
+    torch.set_num_threads(host_threads())
+    p = O.build_params(D_THETA, "dist", in_dim_x=DX, in_dim_y=DY, weight_dim_x=list(WEIGHT_DIM_X),
+                       model_type="classification", embed_op="joint", concat_data_size=True,
+                       likhd_var_init=lkh_var)
+    for k, v in work["weights"].items():
+        p[k] = np.asarray(v, dtype=np.float64)
+    if params_override:
+        for k, v in params_override.items():
+            p[k] = np.asarray(v, dtype=np.float64).reshape(np.shape(p[k]))
+    from sklearn.preprocessing import StandardScaler
+    theta = StandardScaler().fit(work["theta"]).transform(work["theta"])
+    rows = work["rows"]
+    bX = np.vstack([x[:BATCH_ROWS] for x in work["data_X"][:T_SRC]])
+    bY = np.vstack([y[:BATCH_ROWS] for y in work["data_Y"][:T_SRC]])
+    batch = O.TrainBatch(h_params=theta, obs=work["y"][:, None], sizes=work["sizes"], batch_X=bX, batch_y=bY,
+                         embed_sizes=[BATCH_ROWS] * T_SRC, data_sizes=[rows] * T_SRC, max_size=rows)
+    t0 = time.perf_counter()
+    loss, _ = O.loss_and_grads(p, "dist", batch, embed_op="joint", model_type="classification")
+    return time.perf_counter() - t0, loss
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -430,6 +457,12 @@ def run_cuda(args):
                "sample": "Gram+Cholesky+V once %.2f s; K_*/solve/EI/argmax on the first %d candidates %.2f s; "
                          "extrapolated linearly to M=%d" % (t_fixed, m_s, t_var[0], M),
                "argmax_matches_gpu_on_sample": bool(best_cpu == i_gpu)}
+        # fit step on the host: one loss + full-gradient evaluation at N = 8192, same mini-batch shape
+        fit_s, fit_loss = cpu_fit_reference(work, args.lkh_var, params_override=fitted)
+        cpu["fit_ms"] = fit_s * 1e3
+        cpu["fit_what"] = "one loss + autograd gradient evaluation at N=%d on the host (torch-CPU fp64, %d threads)" % (
+            N_OBS, host_threads())
+        cpu["fit_speedup_gpu_over_cpu"] = fit_s * 1e3 / fit["fit_ms"]
 
     bi = (hi - lo) * D_THETA * 8
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
