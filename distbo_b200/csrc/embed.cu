@@ -696,7 +696,15 @@ __global__ void embed_bwd_reduce_kernel(const double* __restrict__ partial, int 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nparams) return;
   double s = 0.0;
-  for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * nparams + i];
+  int c = 0;
+  for (; c + 16 <= nparts; c += 16) {     // sixteen loads in flight, added in CTA order (same sum as a plain loop)
+    double x[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) x[u] = partial[(size_t)(c + u) * nparams + i];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s += x[u];
+  }
+  for (; c < nparts; ++c) s += partial[(size_t)c * nparams + i];
   if (i < nx) {
     if (i < dxh) gW1x[i] = s;
     else if (i < dxh + hx) gb1x[i - dxh] = s;

@@ -136,3 +136,37 @@ def test_gradient_directional_derivative(big):
     fd = (nll_at(h, dirs, dE) - nll_at(-h, dirs, dE)) / (2 * h)
     nll_at(0.0, dirs, dE)
     assert abs(fd - g_dot) <= 2e-6 * max(1.0, abs(g_dot)), (fd, g_dot)
+
+
+def test_fit_kernels_bitwise_reproducible():
+    """The multi-stream POTRF schedule (panel / next / window / far streams), TRTRI and LAUUM use fixed tile
+    products in fixed orders: L, L^-1, K^-1 and the likelihood of the same matrix are bitwise identical from run to
+    run, eagerly and as a CUDA-graph replay (a race between the streams would show up here; tools/stress_potrf.py
+    is the long version)."""
+    from distbo_b200 import engine as eng
+    N = 7300                                   # 58 column blocks: the near / far schedule
+    rs = np.random.RandomState(1)
+    e = eng.GPEngine(8)
+    e.params.set("log_sigma", 0.5 * np.log(1e-2))
+    e.set_observations(rs.randn(N, 8), rs.randn(N))
+
+    def run():
+        e.build_gram(None)
+        e.factorize(need_inverse=True, need_kinv=True)
+        e.likelihood()
+
+    run()
+    torch.cuda.synchronize()
+    assert int(e.info.item()) == 0
+    ref = [e.K.clone(), e.W.clone(), e.Tm.clone(), e.nll.clone()]
+    for _ in range(4):
+        run()
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip((e.K, e.W, e.Tm, e.nll), ref))
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        run()
+    for _ in range(4):
+        g.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip((e.K, e.W, e.Tm, e.nll), ref))
