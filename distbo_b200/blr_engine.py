@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import ACQ, GPEngine, ParamStore, _stream, net_param_shapes
+from .engine import ACQ, D_MAX, GPEngine, ParamStore, _stream, net_param_shapes
 
 BLR_W = 64          # widest layer the kernels take (blr.cu)
 
@@ -28,6 +28,8 @@ class BLREngine(GPEngine):
         if len(weight_dim) not in (2, 3) or max(weight_dim) > BLR_W:
             raise NotImplementedError("BLR feature map: weight_dim of 2 or 3 layers, widths <= %d (got %r)"
                                       % (BLR_W, weight_dim))
+        if not 1 <= int(d_theta) <= D_MAX:
+            raise ValueError("d_theta = %d: 1 <= d_theta <= %d" % (int(d_theta), D_MAX))
         self.lib = _lib.load()
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.d = int(d_theta)

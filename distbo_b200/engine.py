@@ -23,6 +23,7 @@ from . import _lib
 
 JITTER = 0.000001  # reference train/log_gaus_likelihood.py:122,210
 ACQ = {"ei": 0, "ucb": 1, "lcb": 2}
+D_MAX = 16         # gram.cu DMAX / score.cu SCORE_DMAX
 
 
 def round_up(n, m):
@@ -51,8 +52,18 @@ class Plans:
 class NetSpec:
     """Shapes of the embedding nets (reference train/gp_utils.py:13-26, two-layer form)."""
 
+    H_MAX, P_MAX = 32, 16       # hidden / output widths the embedding kernels hold in registers (embed.cu)
+
     def __init__(self, dx, dy, hx, p, hy=0, q=0, y_mode=0):
         self.dx, self.dy, self.hx, self.p, self.hy, self.q, self.y_mode = dx, dy, hx, p, hy, q, y_mode
+        if y_mode not in (0, 1, 2, 3):
+            raise ValueError("y_mode %r: 0 (x only), 1 (joint), 2 (classification), 3 (concat)" % (y_mode,))
+        if not (1 <= hx <= self.H_MAX and 1 <= p <= self.P_MAX):
+            raise ValueError("embedding net x: hidden width <= %d and output width <= %d (got %d, %d); the shipped "
+                             "configs use (20, 10)" % (self.H_MAX, self.P_MAX, hx, p))
+        if y_mode in (1, 3) and not (1 <= hy <= self.H_MAX and 1 <= q <= self.P_MAX):
+            raise ValueError("embedding net y: hidden width <= %d and output width <= %d (got %d, %d)"
+                             % (self.H_MAX, self.P_MAX, hy, q))
 
     @property
     def pooled_width(self):
@@ -137,6 +148,10 @@ class GPEngine:
     def __init__(self, d_theta, n_embed=0, net=None, device=None, n_multi=0):
         if not torch.cuda.is_available():
             raise _lib.DistboError("distbo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if not 1 <= int(d_theta) <= D_MAX:
+            raise ValueError("d_theta = %d: the Gram / scoring kernels hold a hyper-parameter row in registers, "
+                             "1 <= d_theta <= %d (the reference's search spaces have 1..7 dimensions)"
+                             % (int(d_theta), D_MAX))
         self.lib = _lib.load()
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.d = int(d_theta)

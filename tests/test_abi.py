@@ -82,3 +82,16 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_dimension_limits_are_reported():
+    """Widths the kernels keep in registers are checked on the host with a message (the C ABI itself returns -1)."""
+    from distbo_b200.engine import NetSpec
+    NetSpec(166, 2, 20, 10, y_mode=2)
+    NetSpec(7, 1, 32, 16, 32, 16, y_mode=3)
+    with pytest.raises(ValueError):
+        NetSpec(7, 1, 33, 10)
+    with pytest.raises(ValueError):
+        NetSpec(7, 1, 20, 10, 20, 17, y_mode=1)
+    with pytest.raises(ValueError):
+        NetSpec(7, 1, 20, 10, y_mode=5)
