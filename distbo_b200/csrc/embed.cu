@@ -19,6 +19,8 @@
 // chunks (x tile re-read from L2); per-CTA partials are added in CTA order by a reduce kernel.
 #include "../../include/distbo_b200.h"
 #include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace db {
 
@@ -93,9 +95,12 @@ __global__ void __launch_bounds__(256) embed_chunk_table_kernel(const int32_t* _
                                                                 int32_t* __restrict__ chunk_first,
                                                                 int32_t* __restrict__ chunk_ds,
                                                                 int32_t* __restrict__ chunk_row) {
+  constexpr int TS = 2048;                 // datasets whose scan fits in shared memory: the fill runs chunk-parallel
   __shared__ int wsum[8];
   __shared__ int carry;
+  __shared__ int sfirst[TS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool par = T <= TS;
   if (tid == 0) carry = 0;
   __syncthreads();
   for (int base = 0; base < T; base += 256) {
@@ -115,16 +120,35 @@ __global__ void __launch_bounds__(256) embed_chunk_table_kernel(const int32_t* _
     const int first = carry + woff + incl - nc;
     if (t < T) {
       chunk_first[t] = first;
-      for (int c = 0; c < nc; ++c) {
-        chunk_ds[first + c] = t;
-        chunk_row[first + c] = seg_off[t] + c * rows;
+      if (par) {
+        sfirst[t] = first;
+      } else {
+        for (int c = 0; c < nc; ++c) {
+          chunk_ds[first + c] = t;
+          chunk_row[first + c] = seg_off[t] + c * rows;
+        }
       }
     }
     __syncthreads();
     if (tid == 255) carry = first + nc;
     __syncthreads();
   }
-  if (tid == 0) chunk_first[T] = carry;
+  const int total = carry;
+  if (tid == 0) {
+    chunk_first[T] = total;
+    if (par) sfirst[T] = total;
+  }
+  if (!par) return;
+  __syncthreads();
+  for (int c = tid; c < total; c += 256) {   // dataset of chunk c: last t with sfirst[t] <= c (empty datasets skipped)
+    int lo = 0, hi = T;                      // invariant: sfirst[lo] <= c < sfirst[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (sfirst[mid] <= c) lo = mid; else hi = mid;
+    }
+    chunk_ds[c] = lo;
+    chunk_row[c] = seg_off[lo] + (c - sfirst[lo]) * rows;
+  }
 }
 
 // ------------------------------------------------------------------ shared building blocks
@@ -471,6 +495,398 @@ __global__ void __launch_bounds__(128) embed_fwd_reduce_kernel(EmbedArgs<T> a) {
   }
 }
 
+// ------------------------------------------------------------------ fp32 forward on the tensor cores
+// Prediction-time embedding of the full sample sets (north_star subsystem 1: the HBM-bound pass over every
+// dataset row).  Used for the x-net-only poolings (y_mode 0 'none' and 2 classification, the protein fingerprints).
+//   * a chunk = up to 32 consecutive rows of one dataset = ONE contiguous block of global memory, fetched by a
+//     single bulk async copy (cp.async.bulk, the 1-D TMA path) into a shared-memory ring of S stages guarded by
+//     full / empty mbarriers.  A producer warp owns the ring (lane l = stage l: reads the chunk table, waits for the
+//     stage to be released, issues the copy); the <16-byte head / tail of a block whose ends are not 16-byte
+//     aligned are copied by that lane with ordinary accesses, so nothing outside [X, X + S dx) is ever read.
+//   * W consumer warps take chunks round-robin and never meet at a CTA barrier: while one warp is in its MMAs
+//     another is in tanh / pooling, so tensor pipe, shared-memory pipe and ALU overlap with the copies in flight.
+//   * layer 1 (x W1) = mma.sync.m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, w = hi + lo; lo*hi + hi*lo + hi*hi,
+//     fp32 accumulate): fp32-level accuracy on the tensor pipe.  A warp owns two 16-row tiles and all hidden
+//     columns; A fragments are read straight from the staged rows, the W1 fragments are pre-split once per CTA in
+//     fragment order (one 128-bit load per lane, k-step and column tile, shared by the two row tiles).  The lo(x)
+//     MMA is skipped for a k-step whose lo parts are all zero (exact: binary fingerprints are TF32 numbers).
+//   * the last layer is linear (distbo_net.py:10, no bias / activation), so the per-dataset mean commutes with it:
+//     a warp pools Q[h][j] = sum_rows tanh(z)[h] * fy[j] over its 32 rows (warp shuffles, fixed order) and the
+//     per-dataset reduce applies W2 once: E[i*gq+j] = sum_h W2[h][i] Q[h][j] / len.
+namespace tc {
+constexpr int ROWS = 32;       // rows per chunk = two 16-row MMA tiles of one warp
+constexpr int GQMAX = 4;       // widest one-hot Y handled here (wider: the generic kernel)
+constexpr int MAXSTAGES = 16;
+
+struct Args {
+  const float* X; const float* Y; const int32_t* seg_off;
+  int T_, dx, dy;
+  const float* W1; const float* b1; const float* W2;
+  int hx, p, y_mode;
+  float* E; int lde;
+  const int32_t* chunk_ds; const int32_t* chunk_row; const int32_t* chunk_first;
+  float* partial;
+  int ksteps, gq, qw;          // qw = (8 NT + 1) gq pooled sums per chunk
+  int stages, consumers;       // ring depth, consumer warps (block = (consumers + 1) warps)
+  unsigned x_region, y_region; // bytes of one stage's X / Y area (each starts with a 16-byte head slot)
+};
+
+__host__ __device__ inline unsigned region_bytes(int din) { return 16u + ((unsigned)(ROWS * din * 4) + 15u) / 16u * 16u + 16u; }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ unsigned to_tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return r;
+}
+// D(16x8) += A(16x8) B(8x8), TF32 inputs, fp32 accumulate.  SASS: HMMA.1688.F32.TF32.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Rows [row0, row0+n) of a [*, din] fp32 matrix go into `region` so that element e of the block sits at float
+// index 4 - head + e (head = floats before the first 16-byte boundary of the block).  This copies the unaligned
+// head / tail floats with ordinary accesses and describes the 16-byte-aligned middle for the bulk copy.
+struct Bulk { unsigned dst; const void* src; unsigned bytes; };
+__device__ __forceinline__ int head_of(const float* g) { return (int)(((16 - (reinterpret_cast<size_t>(g) & 15)) & 15) >> 2); }
+__device__ __forceinline__ Bulk prepare_block(const float* g, int n, int din, float* region) {
+  const size_t addr = reinterpret_cast<size_t>(g);
+  const size_t end = addr + (size_t)n * din * 4;
+  const size_t a0 = (addr + 15) & ~(size_t)15, a1 = end & ~(size_t)15;
+  const int head = (int)((a0 - addr) >> 2);
+  float* base = region + 4 - head;                       // smem address of element 0
+  const int total = n * din;
+  Bulk b{smem_u32(region + 4), reinterpret_cast<const void*>(a0), 0u};
+  if (a1 <= a0) {                                        // no whole 16-byte granule inside the block
+    for (int e = 0; e < total; ++e) base[e] = g[e];
+    return b;
+  }
+  for (int e = 0; e < head; ++e) base[e] = g[e];
+  for (int e = (int)((a1 - addr) >> 2); e < total; ++e) base[e] = g[e];
+  b.bytes = (unsigned)(a1 - a0);
+  return b;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(32 * (MAXSTAGES + 1), 1) embed_fwd_tc_kernel(Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: full[S] empty[S] mbarriers (256 B) | meta int4 [S] (256 B) | sB uint4 [ksteps][NT][32] | sb1 [8 NT] | stages
+  const unsigned bar_full = smem_u32(smem_raw), bar_empty = bar_full + 8u * MAXSTAGES;
+  int4* meta = reinterpret_cast<int4*>(smem_raw + 256);
+  uint4* sB = reinterpret_cast<uint4*>(smem_raw + 512);
+  float* sb1 = reinterpret_cast<float*>(sB + (size_t)a.ksteps * NT * 32);
+  unsigned char* stage_base = reinterpret_cast<unsigned char*>(sb1 + 8 * NT);
+  const unsigned stage_bytes = a.x_region + a.y_region;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int S = a.stages, W = a.consumers;
+  const int n_chunks = a.chunk_first[a.T_];
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  // W1 in fragment order, split into TF32 hi / lo: lane (g,t) of k-step ks, column tile nt holds
+  // b0 = W1[8 ks + t][8 nt + g], b1 = W1[8 ks + t + 4][8 nt + g]   as (hi b0, hi b1, lo b0, lo b1)
+  for (int idx = tid; idx < a.ksteps * NT * 32; idx += blockDim.x) {
+    const int ln = idx & 31, nt = (idx >> 5) % NT, ks = (idx >> 5) / NT;
+    const int k = 8 * ks + (ln & 3), col = 8 * nt + (ln >> 2);
+    const float w0 = (k < a.dx && col < a.hx) ? a.W1[(size_t)k * a.hx + col] : 0.f;
+    const float w1 = (k + 4 < a.dx && col < a.hx) ? a.W1[(size_t)(k + 4) * a.hx + col] : 0.f;
+    uint4 v;
+    v.x = to_tf32(w0); v.y = to_tf32(w1);
+    v.z = to_tf32(w0 - __uint_as_float(v.x)); v.w = to_tf32(w1 - __uint_as_float(v.y));
+    sB[idx] = v;
+  }
+  for (int j = tid; j < 8 * NT; j += blockDim.x) sb1[j] = (j < a.hx) ? a.b1[j] : 0.f;
+  __syncthreads();                                       // barriers initialised, weights staged; no CTA barrier below
+
+  if (warp == W) {
+    // ---- producer warp: lane l owns stage l and feeds it the chunks i = l, l + S, l + 2S, ... of this CTA
+    if (lane < S) {
+      const unsigned full = bar_full + 8u * lane, empty = bar_empty + 8u * lane;
+      unsigned char* st = stage_base + (size_t)lane * stage_bytes;
+      long long c = (long long)blockIdx.x + (long long)lane * gridDim.x;
+      int ds = 0, row0 = 0, n = 0;
+      auto lookup = [&]() {
+        if (c < n_chunks) {
+          ds = a.chunk_ds[c];
+          row0 = a.chunk_row[c];
+          n = min(ROWS, a.seg_off[ds + 1] - row0);
+        }
+      };
+      lookup();
+      for (int k = 0; c < n_chunks; ++k) {
+        const long long c_now = c;
+        const int row_now = row0, n_now = n;
+        c += (long long)S * gridDim.x;
+        lookup();                                        // the next use's table entries are in flight during the wait
+        if (k > 0) mbar_wait(empty, (unsigned)(k - 1) & 1u);   // the consumer of the previous use has left
+        const float* gx = a.X + (size_t)row_now * a.dx;
+        const Bulk bx = prepare_block(gx, n_now, a.dx, reinterpret_cast<float*>(st));
+        Bulk by{0u, nullptr, 0u};
+        int heady = 0;
+        if (a.y_mode == 2) {
+          const float* gy = a.Y + (size_t)row_now * a.dy;
+          heady = head_of(gy);
+          by = prepare_block(gy, n_now, a.dy, reinterpret_cast<float*>(st + a.x_region));
+        }
+        meta[lane] = make_int4((int)c_now, n_now, head_of(gx), heady);
+        // release: the meta record and the plain head / tail stores are visible to the warp that passes the wait
+        mbar_arrive_expect_tx(full, bx.bytes + by.bytes);
+        if (bx.bytes) bulk_g2s(bx.dst, bx.src, bx.bytes, full);
+        if (by.bytes) bulk_g2s(by.dst, by.src, by.bytes, full);
+      }
+    }
+    return;
+  }
+  if (warp > W) return;
+
+  // ---- consumer warp: chunks i = warp, warp + W, ...
+  const int gq = a.gq, dx = a.dx;
+  for (int i = warp;; i += W) {
+    const long long cc = (long long)blockIdx.x + (long long)i * gridDim.x;
+    if (cc >= n_chunks) break;
+    const int s = i % S;
+    mbar_wait(bar_full + 8u * s, (unsigned)(i / S) & 1u);
+    const int4 m = meta[s];
+    const int c = m.x, n = m.y;
+    const float* xs = reinterpret_cast<const float*>(stage_base + (size_t)s * stage_bytes) + 4 - m.z;
+    const float* ys = reinterpret_cast<const float*>(stage_base + (size_t)s * stage_bytes + a.x_region) + 4 - m.w;
+
+    // ---- layer 1 on the tensor cores: row tiles mt = 0, 1; thread rows 16 mt + g and 16 mt + g + 8
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+    const float* px[4];                                  // this thread's four rows at column t
+#pragma unroll
+    for (int r4 = 0; r4 < 4; ++r4) px[r4] = xs + (size_t)(8 * r4 + g) * dx + t;
+    // one k-step: f = the 8 A values (two row tiles); hi = top 19 bits (the tensor core ignores the 13 low mantissa
+    // bits of a TF32 operand), lo = f - hi exactly; lo is passed as it is (its own truncation is below 2^-22 |f|)
+    auto kstep = [&](const float (&f)[2][4], const uint4* bp) {
+      unsigned hi[2][4], lo[2][4];
+      unsigned nz = 0;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hi[mt][e] = __float_as_uint(f[mt][e]) & 0xffffe000u;
+          lo[mt][e] = __float_as_uint(f[mt][e] - __uint_as_float(hi[mt][e]));
+          nz |= lo[mt][e];
+        }
+      const bool any_lo = __any_sync(0xffffffffu, (nz << 1) != 0);
+      uint4 b[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[nt] = bp[nt * 32];
+      if (any_lo) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], lo[mt], b[nt].x, b[nt].y);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], hi[mt], b[nt].z, b[nt].w);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], hi[mt], b[nt].x, b[nt].y);
+    };
+    const uint4* bp = sB + lane;
+    const int kfull = dx >> 3;                           // k-steps with all 8 columns inside the row
+#pragma unroll 2
+    for (int ks = 0; ks < kfull; ++ks, bp += NT * 32) {
+      float f[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        f[mt][0] = px[2 * mt][8 * ks];
+        f[mt][1] = px[2 * mt + 1][8 * ks];
+        f[mt][2] = px[2 * mt][8 * ks + 4];
+        f[mt][3] = px[2 * mt + 1][8 * ks + 4];
+      }
+      kstep(f, bp);
+    }
+    if (kfull < a.ksteps) {                              // ragged last k-step: columns >= dx are zeros
+      const int k0 = 8 * kfull;
+      const bool in0 = k0 + t < dx, in1 = k0 + t + 4 < dx;
+      float f[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        f[mt][0] = in0 ? px[2 * mt][k0] : 0.f;
+        f[mt][1] = in0 ? px[2 * mt + 1][k0] : 0.f;
+        f[mt][2] = in1 ? px[2 * mt][k0 + 4] : 0.f;
+        f[mt][3] = in1 ? px[2 * mt + 1][k0 + 4] : 0.f;
+      }
+      kstep(f, bp);
+    }
+    // y features of this thread's four rows (mode 0: the constant 1), zero on the rows past the end of the dataset
+    float fy[4][GQMAX];
+#pragma unroll
+    for (int r4 = 0; r4 < 4; ++r4) {
+      const int r = 8 * r4 + g;                          // r4 = 2 mt + half
+#pragma unroll
+      for (int j = 0; j < GQMAX; ++j) {
+        if (a.y_mode == 2) fy[r4][j] = (j < gq && r < n) ? ys[r * a.dy + j] : 0.f;
+        else fy[r4][j] = (j == 0 && r < n) ? 1.f : 0.f;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8u * s);      // every lane's reads of the stage have completed
+
+    // ---- tanh, pooling over the 32 rows: 4 rows in the thread, then a shuffle over g; lanes g == 0 store
+    float* q = a.partial + (size_t)c * a.qw;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int col = 8 * nt + 2 * t + ch;
+        const float bias = sb1[col];
+        float h[4];
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4)
+          h[r4] = (8 * r4 + g < n && col < a.hx) ? tanhf(acc[r4 >> 1][nt][2 * (r4 & 1) + ch] + bias) : 0.f;
+#pragma unroll
+        for (int j = 0; j < GQMAX; ++j) {
+          if (j < gq) {
+            float v = (h[0] * fy[0][j] + h[1] * fy[1][j]) + (h[2] * fy[2][j] + h[3] * fy[3][j]);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0) q[col * gq + j] = v;
+          }
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < GQMAX; ++j) {
+      if (j < gq) {                                      // sum_rows fy[j]: the class ratios (distbo_net.py:45-48)
+        float v = (fy[0][j] + fy[1][j]) + (fy[2][j] + fy[3][j]);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lane == 0) q[8 * NT * gq + j] = v;
+      }
+    }
+  }
+}
+
+// E[t] = W2^T (sum of the dataset's chunk partials) / len, plus the class ratios.  256 threads = 64 columns x 4
+// parts: part k adds a contiguous quarter of the dataset's chunks in chunk order (8 loads in flight), the parts are
+// then added in part order: a fixed order whatever the grid was.
+__global__ void __launch_bounds__(256) embed_fwd_tc_reduce_kernel(Args a, int nt8) {
+  __shared__ double part[4][64];
+  __shared__ double Q[(EMB_HMAX + 1) * GQMAX];
+  const int t = blockIdx.x;
+  const int c0 = a.chunk_first[t], c1 = a.chunk_first[t + 1];
+  const int gq = a.gq;
+  const int col = threadIdx.x & 63, k = threadIdx.x >> 6;
+  const int per = (c1 - c0 + 3) / 4;
+  const int b0 = c0 + k * per, b1 = min(c1, b0 + per);
+  for (int o0 = 0; o0 < a.qw; o0 += 64) {
+    const int o = o0 + col;
+    double acc = 0.0;
+    if (o < a.qw) {
+      int c = b0;
+      for (; c + 8 <= b1; c += 8) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = a.partial[(size_t)(c + u) * a.qw + o];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += (double)x[u];
+      }
+      for (; c < b1; ++c) acc += (double)a.partial[(size_t)c * a.qw + o];
+    }
+    part[k][col] = acc;
+    __syncthreads();
+    if (k == 0 && o < a.qw) Q[o] = ((part[0][col] + part[1][col]) + part[2][col]) + part[3][col];
+    __syncthreads();
+  }
+  const double inv = 1.0 / (double)(a.seg_off[t + 1] - a.seg_off[t]);
+  const int pout = a.p * gq + (a.y_mode == 2 ? gq : 0);
+  for (int o = threadIdx.x; o < pout; o += 256) {
+    double v = 0.0;
+    if (o < a.p * gq) {
+      const int i = o / gq, j = o - i * gq;
+      for (int h = 0; h < a.hx; ++h) v += (double)a.W2[h * a.p + i] * Q[h * gq + j];
+    } else {
+      v = Q[nt8 * gq + (o - a.p * gq)];
+    }
+    a.E[(size_t)t * a.lde + o] = (float)(v * inv);
+  }
+}
+
+inline int nt_of(int hx) { return (hx + 7) / 8; }
+inline int qw_of(int hx, int gq) { return (8 * nt_of(hx) + 1) * gq; }
+inline int64_t max_chunks(int64_t S, int Tn) { return S / ROWS + Tn; }
+inline size_t fixed_smem(int dx, int hx) { return 512 + (size_t)((dx + 7) / 8) * nt_of(hx) * 32 * 16 + (size_t)8 * nt_of(hx) * 4; }
+inline size_t stage_smem(int dx, int dy, int y_mode) { return (size_t)region_bytes(dx) + (y_mode == 2 ? region_bytes(dy) : 0); }
+// Ring depth and consumer warps for a shape: as many stages as fit (<= MAXSTAGES); two of them stay in flight.
+inline void plan(int dx, int dy, int hx, int y_mode, int* stages, int* consumers) {
+  const size_t avail = 227 * 1024 - fixed_smem(dx, hx);
+  int s = (int)(avail / stage_smem(dx, dy, y_mode));
+  if (s > MAXSTAGES) s = MAXSTAGES;
+  int w = s - 2;
+  if (const char* e = getenv("DISTBO_EMBED_TC_WARPS")) {   // measurement knob
+    const int v = atoi(e);
+    if (v >= 1 && v < s) w = v;
+  }
+  if (w > 12) w = 12;
+  *stages = s;
+  *consumers = w;
+}
+// Shapes this path takes (everything else runs on the generic kernel).
+inline bool eligible(int dx, int dy, int hx, int p, int y_mode) {
+  const char* e = getenv("DISTBO_EMBED_TC");            // measurement knob: 0 = generic kernel
+  if (e && e[0] == '0') return false;
+  if (!(y_mode == 0 || y_mode == 2)) return false;
+  if (y_mode == 2 && (dy < 1 || dy > GQMAX)) return false;
+  if (hx < 1 || hx > EMB_HMAX || p < 1 || p > EMB_PMAX || dx < 1) return false;
+  if (fixed_smem(dx, hx) + 4 * stage_smem(dx, dy, y_mode) > 227 * 1024) return false;   // at least 4 stages
+  return true;
+}
+// workspace: chunk_first [T+1] | chunk_ds [mc] | chunk_row [mc] | (align 256) partial [mc][qw]
+inline size_t header_bytes(int64_t S, int Tn) {
+  return ((size_t)((Tn + 1) + 2 * max_chunks(S, Tn)) * sizeof(int32_t) + 255) / 256 * 256;
+}
+inline size_t workspace_bytes(int64_t S, int Tn, int hx, int gq) {
+  return header_bytes(S, Tn) + (size_t)max_chunks(S, Tn) * qw_of(hx, gq) * sizeof(float);
+}
+}  // namespace tc
+
 // ------------------------------------------------------------------ backward (fp64)
 struct EmbedBwdArgs {
   EmbedArgs<double> f;
@@ -690,21 +1106,36 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
   for (int i = threadIdx.x; i < b.nparams; i += nthr) b.gpartial[(size_t)blockIdx.x * b.nparams + i] = s.sG[i];
 }
 
-__global__ void embed_bwd_reduce_kernel(const double* __restrict__ partial, int nparts, int nparams, int nx,
-                                        int dxh, int hx, double* gW1x, double* gb1x, double* gW2x, int dyh,
-                                        int hy, double* gW1y, double* gb1y, double* gW2y) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nparams) return;
+// Sums the per-CTA gradient partials in a fixed order: a block handles 32 consecutive parameters (lane = parameter,
+// coalesced), its 8 warps each add one contiguous eighth of the partials (8 loads in flight), and warp 0 adds the
+// eight sums in warp order.  Deterministic; ~5 dependent load rounds instead of nparts / 16.
+__global__ void __launch_bounds__(256) embed_bwd_reduce_kernel(const double* __restrict__ partial, int nparts,
+                                                               int nparams, int nx, int dxh, int hx, double* gW1x,
+                                                               double* gb1x, double* gW2x, int dyh, int hy,
+                                                               double* gW1y, double* gb1y, double* gW2y) {
+  __shared__ double part[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int per = (nparts + 7) / 8;
+  const int c0 = grp * per, c1 = min(nparts, c0 + per);
   double s = 0.0;
-  int c = 0;
-  for (; c + 16 <= nparts; c += 16) {     // sixteen loads in flight, added in CTA order (same sum as a plain loop)
-    double x[16];
+  if (i < nparams) {
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
+      double x[8];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) x[u] = partial[(size_t)(c + u) * nparams + i];
+      for (int u = 0; u < 8; ++u) x[u] = partial[(size_t)(c + u) * nparams + i];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) s += x[u];
+      for (int u = 0; u < 8; ++u) s += x[u];
+    }
+    for (; c < c1; ++c) s += partial[(size_t)c * nparams + i];
   }
-  for (; c < nparts; ++c) s += partial[(size_t)c * nparams + i];
+  part[grp][lane] = s;
+  __syncthreads();
+  if (grp != 0 || i >= nparams) return;
+  s = part[0][lane];
+#pragma unroll
+  for (int g = 1; g < 8; ++g) s += part[g][lane];
   if (i < nx) {
     if (i < dxh) gW1x[i] = s;
     else if (i < dxh + hx) gb1x[i - dxh] = s;
@@ -798,6 +1229,54 @@ static int embed_fwd_launch(EmbedArgs<T> a, int64_t S, void* workspace, int64_t 
   return DISTBO_OK;
 }
 
+// fp32 forward through the tensor-core kernel (x-net-only poolings).
+template <int NT>
+static int embed_fwd_tc_launch_nt(const tc::Args& t, int grid, size_t smem, cudaStream_t st) {
+  DB_CUDA(cudaFuncSetAttribute(tc::embed_fwd_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc::embed_fwd_tc_kernel<NT><<<grid, 32 * (t.consumers + 1), smem, st>>>(t);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
+static int embed_fwd_tc_launch(const EmbedArgs<float>& a, int64_t S, void* workspace, int64_t workspace_bytes,
+                               cudaStream_t st) {
+  if (!a.E || !workspace) return DISTBO_EARG;
+  const int gq = a.y_mode == 2 ? a.dy : 1;
+  if ((int64_t)tc::workspace_bytes(S, a.T_, a.hx, gq) > workspace_bytes) return DISTBO_EARG;
+  const int64_t mc = tc::max_chunks(S, a.T_);
+  tc::Args t;
+  t.X = a.X; t.Y = a.Y; t.seg_off = a.seg_off; t.T_ = a.T_; t.dx = a.dx; t.dy = a.dy;
+  t.W1 = a.W1x; t.b1 = a.b1x; t.W2 = a.W2x; t.hx = a.hx; t.p = a.p; t.y_mode = a.y_mode;
+  t.E = a.E; t.lde = a.lde;
+  int32_t* chunk_first = (int32_t*)workspace;
+  int32_t* chunk_ds = chunk_first + (a.T_ + 1);
+  int32_t* chunk_row = chunk_ds + mc;
+  t.chunk_ds = chunk_ds; t.chunk_row = chunk_row; t.chunk_first = chunk_first;
+  t.partial = (float*)((unsigned char*)workspace + tc::header_bytes(S, a.T_));
+  t.ksteps = (a.dx + 7) / 8; t.gq = gq; t.qw = tc::qw_of(a.hx, gq);
+  tc::plan(a.dx, a.dy, a.hx, a.y_mode, &t.stages, &t.consumers);
+  t.x_region = tc::region_bytes(a.dx);
+  t.y_region = a.y_mode == 2 ? tc::region_bytes(a.dy) : 0u;
+  const size_t smem = tc::fixed_smem(a.dx, a.hx) + (size_t)t.stages * tc::stage_smem(a.dx, a.dy, a.y_mode);
+  embed_chunk_table_kernel<<<1, 256, 0, st>>>(a.seg_off, a.T_, tc::ROWS, chunk_first, chunk_ds, chunk_row);
+  DB_CHECK_LAUNCH();
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (mc + t.consumers - 1) / t.consumers;
+  const int grid = (int)(want < sms ? want : sms);      // one persistent CTA per SM
+  const int NT = tc::nt_of(a.hx);
+  int rc;
+  if (NT == 1) rc = embed_fwd_tc_launch_nt<1>(t, grid, smem, st);
+  else if (NT == 2) rc = embed_fwd_tc_launch_nt<2>(t, grid, smem, st);
+  else if (NT == 3) rc = embed_fwd_tc_launch_nt<3>(t, grid, smem, st);
+  else rc = embed_fwd_tc_launch_nt<4>(t, grid, smem, st);
+  if (rc) return rc;
+  tc::embed_fwd_tc_reduce_kernel<<<a.T_, 256, 0, st>>>(t, 8 * NT);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
 }  // namespace db
 
 using namespace db;
@@ -808,7 +1287,10 @@ extern "C" int64_t distbo_embed_workspace(int64_t S, int T, int dx, int dy, int 
   const int pout = psum_of(y_mode, p, q, dy);
   if (elem_bytes == 4 && !backward) {
     EmbWs<float> w = ws_layout<float>(nullptr, S, T);
-    return (int64_t)(w.header_bytes + (size_t)max_chunks<float>(S, T) * pout * 4);
+    size_t need = w.header_bytes + (size_t)max_chunks<float>(S, T) * pout * 4;
+    if (y_mode == 0 || y_mode == 2)                        // the tensor-core path: 32-row chunks, (hidden + 1) * gq sums each
+      need = std::max(need, tc::workspace_bytes(S, T, hx, y_mode == 2 ? dy : 1));
+    return (int64_t)need;
   }
   EmbWs<double> w = ws_layout<double>(nullptr, S, T);
   if (!backward) return (int64_t)(w.header_bytes + (size_t)max_chunks<double>(S, T) * pout * 8);
@@ -833,7 +1315,13 @@ extern "C" int distbo_embed_fwd_f32(const float* X, const float* Y, const int32_
                                     int64_t workspace_bytes, void* stream) {
   EmbedArgs<float> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, E, lde,
                      nullptr, nullptr, nullptr, nullptr, log_reg, raw_sums};
+  if (check_args(a, S) == DISTBO_OK && tc::eligible(dx, dy, hx, p, y_mode))
+    return embed_fwd_tc_launch(a, S, workspace, workspace_bytes, (cudaStream_t)stream);
   return embed_fwd_launch<float>(a, S, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int distbo_embed_f32_on_tensor_cores(int dx, int dy, int hx, int p, int y_mode) {
+  return tc::eligible(dx, dy, hx, p, y_mode) ? 1 : 0;
 }
 
 extern "C" int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S,
@@ -880,7 +1368,7 @@ extern "C" int distbo_embed_bwd_f64(const double* X, const double* Y, const int3
   const int grid = (int)(mc < EMB_BWD_GRID ? mc : EMB_BWD_GRID);
   embed_bwd_kernel<<<grid, emb_threads(hx, hy, y_mode), smem, st>>>(b);
   DB_CHECK_LAUNCH();
-  embed_bwd_reduce_kernel<<<(b.nparams + 255) / 256, 256, 0, st>>>(b.gpartial, grid, b.nparams, nx, dx * hx, hx,
+  embed_bwd_reduce_kernel<<<(b.nparams + 31) / 32, 256, 0, st>>>(b.gpartial, grid, b.nparams, nx, dx * hx, hx,
                                                                    gW1x, gb1x, gW2x, dy * hy, hy, gW1y, gb1y, gW2y);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;

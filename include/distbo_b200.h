@@ -63,6 +63,10 @@ int distbo_embed_fwd_f32(const float* X, const float* Y, const int32_t* seg_off,
                          const float* W1y, const float* b1y, const float* W2y, int hy, int q, int y_mode,
                          const float* log_reg, double* raw_sums, float* E, int lde, void* workspace,
                          int64_t workspace_bytes, void* stream);
+/* 1 when distbo_embed_fwd_f32 runs this shape on the tensor-core kernel (x-net-only poolings: y_mode 0 and 2 with
+ * dy <= 4, shared-memory ring fits): rows fetched by bulk async copies, layer 1 as 3xTF32 mma.sync, the linear last
+ * layer applied after the per-dataset mean.  0: the generic kernel.  (DISTBO_EMBED_TC=0 forces 0.) */
+int distbo_embed_f32_on_tensor_cores(int dx, int dy, int hx, int p, int y_mode);
 /* Backward of the above (replaces TF autodiff through distbo_net, train/train.py:31-40):
  * dE [T,lde] -> gradients of the net weights (same shapes as the weights; overwritten); y_mode 3 also
  * needs log_reg, the raw_sums its forward pass stored, and returns g_log_reg (device scalar). */

@@ -258,6 +258,62 @@ def test_embed_forward(cuda_engine_mod, dtype, tol, mode):
     assert rel(Eg[:, :want.shape[1]], want) < tol
 
 
+@pytest.mark.parametrize("case", [
+    # (dx, dy, hx, p, classification, binary X, sizes, rows sliced off the front of the buffer)
+    (166, 2, 20, 10, True, True, [1037, 128, 4434, 1, 255, 129], 0),     # protein fingerprints (data.py:27-38)
+    (166, 2, 20, 10, True, False, [640, 3, 500], 1),                       # real-valued rows: the lo(x) MMA runs
+    (17, 0, 20, 10, False, False, [97, 1, 130, 260], 3),                   # 'none' pooling, 68-byte rows
+    (7, 3, 5, 3, True, False, [300, 17, 1000, 129, 1], 1),                 # 28-byte rows, 3 classes, one column tile
+    (40, 4, 32, 16, True, False, [129, 383, 2], 0),                        # widest net / widest one-hot handled
+    (1, 0, 20, 10, False, False, [500] * 4 + [3], 1),                      # toy: d_x = 1 (toy_datasets.py:44-46)
+])
+def test_embed_forward_tensor_core(cuda_engine_mod, case, monkeypatch):
+    """fp32 prediction-time embedding on the tensor-core kernel (bulk-copy ring + 3xTF32): against the fp64 oracle
+    (north_star: 1e-5 relative) and against the generic fp32 kernel on the same inputs; ragged datasets and row
+    blocks whose ends are not 16-byte aligned (head / tail copies)."""
+    eng = cuda_engine_mod
+    dx, dy, hx, pw, classification, binary, sizes, skip = case
+    rs = np.random.RandomState(dx * 31 + hx)
+    S = sum(sizes)
+    X = (rs.rand(S + skip, dx) < 0.3).astype(np.float64) if binary else rs.randn(S + skip, dx)
+    if classification:
+        Y = np.eye(dy)[rs.randint(0, dy, size=S + skip)]
+        y_mode, model_type, embed_op = 2, "classification", "joint"
+    else:
+        dy = 1
+        Y = rs.rand(S + skip, 1)
+        y_mode, model_type, embed_op = 0, "regression", "none"
+    net = eng.NetSpec(dx, dy, hx, pw, 0, 0, y_mode)
+    e = eng.GPEngine(2, n_embed=net.pooled_width, net=net)
+    p = O.build_params(2, "dist", in_dim_x=dx, in_dim_y=dy, weight_dim_x=[hx, pw], weight_dim_y=[hx, pw],
+                       model_type=model_type, embed_op=embed_op, seed=7)
+    p["bias_x_1"] = rs.randn(hx) * 0.1
+    for k, v in p.items():
+        if e.params.has(k) and k.startswith(("weights", "bias")):
+            e.params.set(k, v)
+    # fp32 inputs; the oracle sees the same fp32-rounded samples and weights in fp64
+    Xd = torch.from_numpy(X).to(e.dev).float()[skip:]
+    Yd = torch.from_numpy(Y).to(e.dev).float()[skip:]
+    assert Xd.is_contiguous() and Yd.is_contiguous()
+    off = torch.from_numpy(np.r_[0, np.cumsum(sizes)].astype(np.int32)).to(e.dev)
+    p32 = {k: np.asarray(v, dtype=np.float32).astype(np.float64) for k, v in p.items()}
+    want = O.distbo_net(O.NP, Xd.double().cpu().numpy(), Yd.double().cpu().numpy(), sizes, p32, embed_op=embed_op,
+                        model_type=model_type)
+    monkeypatch.setenv("DISTBO_EMBED_TC", "1")
+    assert eng._lib.load().distbo_embed_f32_on_tensor_cores(dx, dy, hx, pw, y_mode) == 1
+    got = e.embed(Xd, Yd, off, dtype=torch.float32).double().cpu().numpy()[:, :want.shape[1]]
+    monkeypatch.setenv("DISTBO_EMBED_TC", "0")
+    assert eng._lib.load().distbo_embed_f32_on_tensor_cores(dx, dy, hx, pw, y_mode) == 0
+    generic = e.embed(Xd, Yd, off, dtype=torch.float32).double().cpu().numpy()[:, :want.shape[1]]
+    assert rel(got, want) < 1e-5
+    assert rel(generic, want) < 1e-5
+    assert rel(got, generic) < 1e-5
+    # deterministic: fixed-order reductions, no atomics
+    monkeypatch.setenv("DISTBO_EMBED_TC", "1")
+    again = e.embed(Xd, Yd, off, dtype=torch.float32).double().cpu().numpy()[:, :want.shape[1]]
+    assert np.array_equal(got, again)
+
+
 @pytest.mark.parametrize("mode", ["none", "joint", "class", "concat"])
 def test_embed_backward(cuda_engine_mod, mode):
     eng = cuda_engine_mod
