@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(256) embed_chunk_table_kernel(const int32_t* _
   __shared__ int sfirst[TS + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool par = T <= TS;
+  if (!par && blockIdx.x != 0) return;     // the serial fill is block 0's; with par every block repeats the (cheap) scan
+  const bool writer = blockIdx.x == 0;
   if (tid == 0) carry = 0;
   __syncthreads();
   for (int base = 0; base < T; base += 256) {
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(256) embed_chunk_table_kernel(const int32_t* _
     for (int w = 0; w < warp; ++w) woff += wsum[w];
     const int first = carry + woff + incl - nc;
     if (t < T) {
-      chunk_first[t] = first;
+      if (writer) chunk_first[t] = first;
       if (par) {
         sfirst[t] = first;
       } else {
@@ -135,12 +137,12 @@ __global__ void __launch_bounds__(256) embed_chunk_table_kernel(const int32_t* _
   }
   const int total = carry;
   if (tid == 0) {
-    chunk_first[T] = total;
+    if (writer) chunk_first[T] = total;
     if (par) sfirst[T] = total;
   }
   if (!par) return;
   __syncthreads();
-  for (int c = tid; c < total; c += 256) {   // dataset of chunk c: last t with sfirst[t] <= c (empty datasets skipped)
+  for (int c = blockIdx.x * 256 + tid; c < total; c += gridDim.x * 256) {   // dataset of chunk c: last t with sfirst[t] <= c (empty datasets skipped)
     int lo = 0, hi = T;                      // invariant: sfirst[lo] <= c < sfirst[hi]
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -500,8 +502,8 @@ __global__ void __launch_bounds__(128) embed_fwd_reduce_kernel(EmbedArgs<T> a) {
 // dataset row).  Used for the x-net-only poolings (y_mode 0 'none' and 2 classification, the protein fingerprints).
 //   * a chunk = up to 32 consecutive rows of one dataset = ONE contiguous block of global memory, fetched by a
 //     single bulk async copy (cp.async.bulk, the 1-D TMA path) into a shared-memory ring of S stages guarded by
-//     full / empty mbarriers.  A producer warp owns the ring (lane l = stage l: reads the chunk table, waits for the
-//     stage to be released, issues the copy); the <16-byte head / tail of a block whose ends are not 16-byte
+//     full / empty mbarriers.  A producer warp owns the ring (its lanes prefetch the chunk table, one lane waits for
+//     each stage to be released and issues the copy); the <16-byte head / tail of a block whose ends are not 16-byte
 //     aligned are copied by that lane with ordinary accesses, so nothing outside [X, X + S dx) is ever read.
 //   * W consumer warps take chunks round-robin and never meet at a CTA barrier: while one warp is in its MMAs
 //     another is in tanh / pooling, so tensor pipe, shared-memory pipe and ALU overlap with the copies in flight.
@@ -514,9 +516,10 @@ __global__ void __launch_bounds__(128) embed_fwd_reduce_kernel(EmbedArgs<T> a) {
 //     a warp pools Q[h][j] = sum_rows tanh(z)[h] * fy[j] over its 32 rows (warp shuffles, fixed order) and the
 //     per-dataset reduce applies W2 once: E[i*gq+j] = sum_h W2[h][i] Q[h][j] / len.
 namespace tc {
-constexpr int ROWS = 32;       // rows per chunk = two 16-row MMA tiles of one warp
 constexpr int GQMAX = 4;       // widest one-hot Y handled here (wider: the generic kernel)
-constexpr int MAXSTAGES = 16;
+constexpr int MAXSTAGES = 24;
+constexpr int MAXWARPS = 16;   // consumer warps
+constexpr int PRODUCERS = 4;   // most producer warps (one issuing lane each)
 
 struct Args {
   const float* X; const float* Y; const int32_t* seg_off;
@@ -527,11 +530,24 @@ struct Args {
   const int32_t* chunk_ds; const int32_t* chunk_row; const int32_t* chunk_first;
   float* partial;
   int ksteps, gq, qw;          // qw = (8 NT + 1) gq pooled sums per chunk
-  int stages, consumers;       // ring depth, consumer warps (block = (consumers + 1) warps)
-  unsigned x_region, y_region; // bytes of one stage's X / Y area (each starts with a 16-byte head slot)
+  int rows;                    // rows per chunk (= per stage): 16 x (row tiles per warp) x wps
+  int wps;                     // consumer warps sharing one stage (each takes a 16 MT-row slice of it)
+  int stages, consumers;       // ring depth, consumer warps (block = consumers + PRODUCERS warps)
+  unsigned x_region;           // bytes of one stage (starts with a 16-byte head slot)
+  int producers;               // producer warps; divides `stages`, so a stage is always refilled by the same warp
+  int skip_compute;            // measurement only (DISTBO_EMBED_TC_SKIP=1): consumers release the stage untouched
 };
 
-__host__ __device__ inline unsigned region_bytes(int din) { return 16u + ((unsigned)(ROWS * din * 4) + 15u) / 16u * 16u + 16u; }
+__host__ __device__ inline unsigned region_bytes(int rows, int din) { return 16u + ((unsigned)(rows * din * 4) + 15u) / 16u * 16u + 16u; }
+// tanh for the fp32 path: 1 - 2 / (1 + e^{2x}) on the special-function unit (absolute error ~1e-7), and the odd
+// Taylor polynomial where that form would cancel (|x| < 0.125: truncation below 3e-9 relative)
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(2.f * x);
+  const float big = 1.f - __fdividef(2.f, 1.f + e);
+  const float x2 = x * x;
+  const float small = x * (1.f + x2 * (-0.33333334f + x2 * (0.13333334f + x2 * (-0.053968254f + x2 * 0.021869488f))));
+  return fabsf(x) < 0.125f ? small : big;
+}
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -594,16 +610,17 @@ __device__ __forceinline__ Bulk prepare_block(const float* g, int n, int din, fl
   return b;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(32 * (MAXSTAGES + 1), 1) embed_fwd_tc_kernel(Args a) {
+template <int NT, int MT>
+__global__ void __launch_bounds__(32 * (MAXWARPS + PRODUCERS), 1) embed_fwd_tc_kernel(Args a) {
+  constexpr int ROWS = 16 * MT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: full[S] empty[S] mbarriers (256 B) | meta int4 [S] (256 B) | sB uint4 [ksteps][NT][32] | sb1 [8 NT] | stages
+  // layout: full[S] empty[S] mbarriers (384 B) | meta int4 [S] (384 B) | sB uint4 [ksteps][NT][32] | sb1 [8 NT] | stages
   const unsigned bar_full = smem_u32(smem_raw), bar_empty = bar_full + 8u * MAXSTAGES;
-  int4* meta = reinterpret_cast<int4*>(smem_raw + 256);
-  uint4* sB = reinterpret_cast<uint4*>(smem_raw + 512);
+  int4* meta = reinterpret_cast<int4*>(smem_raw + 16 * MAXSTAGES);
+  uint4* sB = reinterpret_cast<uint4*>(smem_raw + 32 * MAXSTAGES);
   float* sb1 = reinterpret_cast<float*>(sB + (size_t)a.ksteps * NT * 32);
   unsigned char* stage_base = reinterpret_cast<unsigned char*>(sb1 + 8 * NT);
-  const unsigned stage_bytes = a.x_region + a.y_region;
+  const unsigned stage_bytes = a.x_region;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int S = a.stages, W = a.consumers;
   const int n_chunks = a.chunk_first[a.T_];
@@ -611,7 +628,7 @@ __global__ void __launch_bounds__(32 * (MAXSTAGES + 1), 1) embed_fwd_tc_kernel(A
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8u * s, 1);
-      mbar_init(bar_empty + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, (unsigned)a.wps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -631,77 +648,106 @@ __global__ void __launch_bounds__(32 * (MAXSTAGES + 1), 1) embed_fwd_tc_kernel(A
   for (int j = tid; j < 8 * NT; j += blockDim.x) sb1[j] = (j < a.hx) ? a.b1[j] : 0.f;
   __syncthreads();                                       // barriers initialised, weights staged; no CTA barrier below
 
-  if (warp == W) {
-    // ---- producer warp: lane l owns stage l and feeds it the chunks i = l, l + S, l + 2S, ... of this CTA
-    if (lane < S) {
-      const unsigned full = bar_full + 8u * lane, empty = bar_empty + 8u * lane;
-      unsigned char* st = stage_base + (size_t)lane * stage_bytes;
-      long long c = (long long)blockIdx.x + (long long)lane * gridDim.x;
-      int ds = 0, row0 = 0, n = 0;
-      auto lookup = [&]() {
-        if (c < n_chunks) {
-          ds = a.chunk_ds[c];
-          row0 = a.chunk_row[c];
-          n = min(ROWS, a.seg_off[ds + 1] - row0);
+  if (warp >= W) {
+    // ---- producer warps: warp pw of PW feeds the CTA's chunks i = pw, pw + PW, ... (stage i % S) in order.  Its
+    // lanes read the table entries of 32 of its chunks at a time (the next batch is in flight while this one is
+    // issued); lane 0 waits for the stage to be released and issues the copy.  Warp-uniform: no lane spins alone.
+    const int pw = warp - W, PW = a.producers;
+    auto lookup = [&](int m, int& row0, int& n) {        // m-th chunk of this producer warp
+      const long long c = (long long)blockIdx.x + (long long)(pw + PW * m) * gridDim.x;
+      row0 = 0; n = 0;
+      if (c < n_chunks) {
+        const int ds = a.chunk_ds[c];
+        row0 = a.chunk_row[c];
+        n = min(a.rows, a.seg_off[ds + 1] - row0);
+      }
+    };
+    int row_next, n_next;
+    lookup(lane, row_next, n_next);
+    int st_i = pw % S, use = pw / S;                     // stage and use count of chunk i, advanced by PW per chunk
+    for (int m0 = 0;; m0 += 32) {
+      const int row_cur = row_next, n_cur = n_next;
+      if ((long long)blockIdx.x + (long long)(pw + PW * m0) * gridDim.x >= n_chunks) break;
+      lookup(m0 + 32 + lane, row_next, n_next);
+      for (int j = 0; j < 32; ++j) {
+        const long long c = (long long)blockIdx.x + (long long)(pw + PW * (m0 + j)) * gridDim.x;
+        if (c >= n_chunks) break;
+        const int row0 = __shfl_sync(0xffffffffu, row_cur, j), n = __shfl_sync(0xffffffffu, n_cur, j);
+        if (lane == 0) {
+          const unsigned full = bar_full + 8u * st_i, empty = bar_empty + 8u * st_i;
+          if (use > 0) mbar_wait(empty, (unsigned)(use - 1) & 1u);   // the consumer of the previous use has left
+          const float* gx = a.X + (size_t)row0 * a.dx;
+          const Bulk bx = prepare_block(gx, n, a.dx, reinterpret_cast<float*>(stage_base + (size_t)st_i * stage_bytes));
+          meta[st_i] = make_int4((int)c, n, head_of(gx), row0);
+          // release: the meta record and the plain head / tail stores are visible to the warp that passes the wait
+          mbar_arrive_expect_tx(full, bx.bytes);
+          if (bx.bytes) bulk_g2s(bx.dst, bx.src, bx.bytes, full);
         }
-      };
-      lookup();
-      for (int k = 0; c < n_chunks; ++k) {
-        const long long c_now = c;
-        const int row_now = row0, n_now = n;
-        c += (long long)S * gridDim.x;
-        lookup();                                        // the next use's table entries are in flight during the wait
-        if (k > 0) mbar_wait(empty, (unsigned)(k - 1) & 1u);   // the consumer of the previous use has left
-        const float* gx = a.X + (size_t)row_now * a.dx;
-        const Bulk bx = prepare_block(gx, n_now, a.dx, reinterpret_cast<float*>(st));
-        Bulk by{0u, nullptr, 0u};
-        int heady = 0;
-        if (a.y_mode == 2) {
-          const float* gy = a.Y + (size_t)row_now * a.dy;
-          heady = head_of(gy);
-          by = prepare_block(gy, n_now, a.dy, reinterpret_cast<float*>(st + a.x_region));
-        }
-        meta[lane] = make_int4((int)c_now, n_now, head_of(gx), heady);
-        // release: the meta record and the plain head / tail stores are visible to the warp that passes the wait
-        mbar_arrive_expect_tx(full, bx.bytes + by.bytes);
-        if (bx.bytes) bulk_g2s(bx.dst, bx.src, bx.bytes, full);
-        if (by.bytes) bulk_g2s(by.dst, by.src, by.bytes, full);
+        st_i += PW;
+        while (st_i >= S) { st_i -= S; ++use; }
       }
     }
     return;
   }
-  if (warp > W) return;
 
-  // ---- consumer warp: chunks i = warp, warp + W, ...
+  // ---- consumer warps: team = wps warps sharing a stage (warp `half` takes rows [ROWS half, ROWS half + ROWS) of
+  // it); the teams take the chunks i = team, team + teams, ...
   const int gq = a.gq, dx = a.dx;
-  for (int i = warp;; i += W) {
+  const int teams = W / a.wps, team = warp / a.wps, half = warp - team * a.wps;
+  for (int i = team;; i += teams) {
     const long long cc = (long long)blockIdx.x + (long long)i * gridDim.x;
     if (cc >= n_chunks) break;
     const int s = i % S;
-    mbar_wait(bar_full + 8u * s, (unsigned)(i / S) & 1u);
+    // A parity wait cannot tell "this use is loaded" from "the previous use is still loading" (a warp that runs a
+    // whole ring ahead would pass at once): the chunk index in the stage's meta record settles it, and the second
+    // wait is then a true wait for this use.
+    const unsigned par = (unsigned)(i / S) & 1u;
+    do {
+      mbar_wait(bar_full + 8u * s, par);
+    } while (reinterpret_cast<const volatile int*>(meta + s)[0] != (int)cc);
+    mbar_wait(bar_full + 8u * s, par);
     const int4 m = meta[s];
-    const int c = m.x, n = m.y;
-    const float* xs = reinterpret_cast<const float*>(stage_base + (size_t)s * stage_bytes) + 4 - m.z;
-    const float* ys = reinterpret_cast<const float*>(stage_base + (size_t)s * stage_bytes + a.x_region) + 4 - m.w;
-
-    // ---- layer 1 on the tensor cores: row tiles mt = 0, 1; thread rows 16 mt + g and 16 mt + g + 8
-    float acc[2][NT][4];
+    const int c = m.x * a.wps + half;                    // index of this warp's partial sums
+    const int n = max(0, min(ROWS, m.y - ROWS * half));  // valid rows of this warp's slice
+    const int row_g = m.w + ROWS * half;                 // global row of the slice
+    const float* xs = reinterpret_cast<const float*>(stage_base + (size_t)s * stage_bytes) + 4 - m.z + (size_t)ROWS * half * dx;
+    // y features of this thread's rows (mode 0: the constant 1), zero on the rows past the end of the dataset.
+    // The one-hot rows are a few bytes each: ordinary loads issued here, their latency hidden by the MMA loop.
+    float fy[2 * MT][GQMAX];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int r4 = 0; r4 < 2 * MT; ++r4) {
+      const int r = 8 * r4 + g;
+#pragma unroll
+      for (int j = 0; j < GQMAX; ++j) {
+        if (a.y_mode == 2) fy[r4][j] = (j < gq && r < n) ? __ldg(a.Y + (size_t)(row_g + r) * a.dy + j) : 0.f;
+        else fy[r4][j] = (j == 0 && r < n) ? 1.f : 0.f;
+      }
+    }
+
+    if (a.skip_compute) {                                // copy-ring ceiling: no MMAs, no pooling (results are zeros)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8u * s);
+      if (lane < a.qw) a.partial[(size_t)c * a.qw + lane] = xs[lane] * 0.f + fy[0][0] * 0.f;
+      continue;
+    }
+    // ---- layer 1 on the tensor cores: row tiles mt < MT; thread rows 16 mt + g and 16 mt + g + 8
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
-    const float* px[4];                                  // this thread's four rows at column t
+    const float* px[2 * MT];                             // this thread's rows 8 r4 + g at column t
 #pragma unroll
-    for (int r4 = 0; r4 < 4; ++r4) px[r4] = xs + (size_t)(8 * r4 + g) * dx + t;
+    for (int r4 = 0; r4 < 2 * MT; ++r4) px[r4] = xs + (size_t)(8 * r4 + g) * dx + t;
     // one k-step: f = the 8 A values (two row tiles); hi = top 19 bits (the tensor core ignores the 13 low mantissa
     // bits of a TF32 operand), lo = f - hi exactly; lo is passed as it is (its own truncation is below 2^-22 |f|)
-    auto kstep = [&](const float (&f)[2][4], const uint4* bp) {
-      unsigned hi[2][4], lo[2][4];
+    auto kstep = [&](const float (&f)[MT][4], const uint4* bp) {
+      unsigned hi[MT][4], lo[MT][4];
       unsigned nz = 0;
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           hi[mt][e] = __float_as_uint(f[mt][e]) & 0xffffe000u;
@@ -716,24 +762,24 @@ __global__ void __launch_bounds__(32 * (MAXSTAGES + 1), 1) embed_fwd_tc_kernel(A
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], lo[mt], b[nt].x, b[nt].y);
+          for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], lo[mt], b[nt].x, b[nt].y);
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], hi[mt], b[nt].z, b[nt].w);
+        for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], hi[mt], b[nt].z, b[nt].w);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_tf32(acc[mt][nt], hi[mt], b[nt].x, b[nt].y);
+        for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], hi[mt], b[nt].x, b[nt].y);
     };
     const uint4* bp = sB + lane;
     const int kfull = dx >> 3;                           // k-steps with all 8 columns inside the row
 #pragma unroll 2
     for (int ks = 0; ks < kfull; ++ks, bp += NT * 32) {
-      float f[2][4];
+      float f[MT][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         f[mt][0] = px[2 * mt][8 * ks];
         f[mt][1] = px[2 * mt + 1][8 * ks];
         f[mt][2] = px[2 * mt][8 * ks + 4];
@@ -744,26 +790,15 @@ __global__ void __launch_bounds__(32 * (MAXSTAGES + 1), 1) embed_fwd_tc_kernel(A
     if (kfull < a.ksteps) {                              // ragged last k-step: columns >= dx are zeros
       const int k0 = 8 * kfull;
       const bool in0 = k0 + t < dx, in1 = k0 + t + 4 < dx;
-      float f[2][4];
+      float f[MT][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         f[mt][0] = in0 ? px[2 * mt][k0] : 0.f;
         f[mt][1] = in0 ? px[2 * mt + 1][k0] : 0.f;
         f[mt][2] = in1 ? px[2 * mt][k0 + 4] : 0.f;
         f[mt][3] = in1 ? px[2 * mt + 1][k0 + 4] : 0.f;
       }
       kstep(f, bp);
-    }
-    // y features of this thread's four rows (mode 0: the constant 1), zero on the rows past the end of the dataset
-    float fy[4][GQMAX];
-#pragma unroll
-    for (int r4 = 0; r4 < 4; ++r4) {
-      const int r = 8 * r4 + g;                          // r4 = 2 mt + half
-#pragma unroll
-      for (int j = 0; j < GQMAX; ++j) {
-        if (a.y_mode == 2) fy[r4][j] = (j < gq && r < n) ? ys[r * a.dy + j] : 0.f;
-        else fy[r4][j] = (j == 0 && r < n) ? 1.f : 0.f;
-      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8u * s);      // every lane's reads of the stage have completed
@@ -776,14 +811,15 @@ __global__ void __launch_bounds__(32 * (MAXSTAGES + 1), 1) embed_fwd_tc_kernel(A
       for (int ch = 0; ch < 2; ++ch) {
         const int col = 8 * nt + 2 * t + ch;
         const float bias = sb1[col];
-        float h[4];
+        float h[2 * MT];
 #pragma unroll
-        for (int r4 = 0; r4 < 4; ++r4)
-          h[r4] = (8 * r4 + g < n && col < a.hx) ? tanhf(acc[r4 >> 1][nt][2 * (r4 & 1) + ch] + bias) : 0.f;
+        for (int r4 = 0; r4 < 2 * MT; ++r4)
+          h[r4] = (8 * r4 + g < n && col < a.hx) ? tanh_fast(acc[r4 >> 1][nt][2 * (r4 & 1) + ch] + bias) : 0.f;
 #pragma unroll
         for (int j = 0; j < GQMAX; ++j) {
           if (j < gq) {
-            float v = (h[0] * fy[0][j] + h[1] * fy[1][j]) + (h[2] * fy[2][j] + h[3] * fy[3][j]);
+            float v = h[0] * fy[0][j] + h[1] * fy[1][j];
+            if (MT == 2) v += h[2 * MT - 2] * fy[2 * MT - 2][j] + h[2 * MT - 1] * fy[2 * MT - 1][j];
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
@@ -794,7 +830,8 @@ __global__ void __launch_bounds__(32 * (MAXSTAGES + 1), 1) embed_fwd_tc_kernel(A
 #pragma unroll
     for (int j = 0; j < GQMAX; ++j) {
       if (j < gq) {                                      // sum_rows fy[j]: the class ratios (distbo_net.py:45-48)
-        float v = (fy[0][j] + fy[1][j]) + (fy[2][j] + fy[3][j]);
+        float v = fy[0][j] + fy[1][j];
+        if (MT == 2) v += fy[2 * MT - 2][j] + fy[2 * MT - 1][j];
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
@@ -804,18 +841,18 @@ __global__ void __launch_bounds__(32 * (MAXSTAGES + 1), 1) embed_fwd_tc_kernel(A
   }
 }
 
-// E[t] = W2^T (sum of the dataset's chunk partials) / len, plus the class ratios.  256 threads = 64 columns x 4
-// parts: part k adds a contiguous quarter of the dataset's chunks in chunk order (8 loads in flight), the parts are
+// E[t] = W2^T (sum of the dataset's chunk partials) / len, plus the class ratios.  1024 threads = 64 columns x 16
+// parts: part k adds a contiguous sixteenth of the dataset's partials in order (8 loads in flight), the parts are
 // then added in part order: a fixed order whatever the grid was.
-__global__ void __launch_bounds__(256) embed_fwd_tc_reduce_kernel(Args a, int nt8) {
-  __shared__ double part[4][64];
+__global__ void __launch_bounds__(1024) embed_fwd_tc_reduce_kernel(Args a, int nt8) {
+  __shared__ double part[16][64];
   __shared__ double Q[(EMB_HMAX + 1) * GQMAX];
   const int t = blockIdx.x;
-  const int c0 = a.chunk_first[t], c1 = a.chunk_first[t + 1];
+  const int c0 = a.chunk_first[t] * a.wps, c1 = a.chunk_first[t + 1] * a.wps;   // wps partials per chunk
   const int gq = a.gq;
   const int col = threadIdx.x & 63, k = threadIdx.x >> 6;
-  const int per = (c1 - c0 + 3) / 4;
-  const int b0 = c0 + k * per, b1 = min(c1, b0 + per);
+  const int per = (c1 - c0 + 15) / 16;
+  const int b0 = min(c1, c0 + k * per), b1 = min(c1, b0 + per);
   for (int o0 = 0; o0 < a.qw; o0 += 64) {
     const int o = o0 + col;
     double acc = 0.0;
@@ -832,12 +869,17 @@ __global__ void __launch_bounds__(256) embed_fwd_tc_reduce_kernel(Args a, int nt
     }
     part[k][col] = acc;
     __syncthreads();
-    if (k == 0 && o < a.qw) Q[o] = ((part[0][col] + part[1][col]) + part[2][col]) + part[3][col];
+    if (k == 0 && o < a.qw) {
+      double v = part[0][col];
+#pragma unroll
+      for (int u = 1; u < 16; ++u) v += part[u][col];
+      Q[o] = v;
+    }
     __syncthreads();
   }
   const double inv = 1.0 / (double)(a.seg_off[t + 1] - a.seg_off[t]);
   const int pout = a.p * gq + (a.y_mode == 2 ? gq : 0);
-  for (int o = threadIdx.x; o < pout; o += 256) {
+  for (int o = threadIdx.x; o < pout; o += 1024) {
     double v = 0.0;
     if (o < a.p * gq) {
       const int i = o / gq, j = o - i * gq;
@@ -851,22 +893,42 @@ __global__ void __launch_bounds__(256) embed_fwd_tc_reduce_kernel(Args a, int nt
 
 inline int nt_of(int hx) { return (hx + 7) / 8; }
 inline int qw_of(int hx, int gq) { return (8 * nt_of(hx) + 1) * gq; }
-inline int64_t max_chunks(int64_t S, int Tn) { return S / ROWS + Tn; }
-inline size_t fixed_smem(int dx, int hx) { return 512 + (size_t)((dx + 7) / 8) * nt_of(hx) * 32 * 16 + (size_t)8 * nt_of(hx) * 4; }
-inline size_t stage_smem(int dx, int dy, int y_mode) { return (size_t)region_bytes(dx) + (y_mode == 2 ? region_bytes(dy) : 0); }
-// Ring depth and consumer warps for a shape: as many stages as fit (<= MAXSTAGES); two of them stay in flight.
-inline void plan(int dx, int dy, int hx, int y_mode, int* stages, int* consumers) {
+// Decomposition: default = 32-row stages shared by two warps with one 16-row tile each (most warps per byte of
+// ring).  DISTBO_EMBED_TC_MODE=mt2: one warp with two row tiles per 32-row stage; mt1: 16-row stages, one warp each.
+inline void mode(int* mt, int* wps) {
+  const char* e = getenv("DISTBO_EMBED_TC_MODE");
+  *mt = 1; *wps = 2;
+  if (e && e[0] == 'm' && e[1] == 't' && e[2] == '2') { *mt = 2; *wps = 1; }
+  else if (e && e[0] == 'm' && e[1] == 't' && e[2] == '1') { *mt = 1; *wps = 1; }
+}
+inline int64_t max_chunks(int64_t S, int Tn) { return S / 16 + 2 * (int64_t)Tn; }    // partial-sum slots, any mode
+inline size_t fixed_smem(int dx, int hx) { return 32 * MAXSTAGES + (size_t)((dx + 7) / 8) * nt_of(hx) * 32 * 16 + (size_t)8 * nt_of(hx) * 4; }
+inline size_t stage_smem(int rows, int dx, int, int) { return (size_t)region_bytes(rows, dx); }
+// Ring depth and consumer warps for a shape: as many stages as fit (<= MAXSTAGES); a few stay in flight.
+inline void plan(int rows, int wps, int dx, int dy, int hx, int y_mode, int* stages, int* consumers, int* producers) {
   const size_t avail = 227 * 1024 - fixed_smem(dx, hx);
-  int s = (int)(avail / stage_smem(dx, dy, y_mode));
+  int s = (int)(avail / stage_smem(rows, dx, dy, y_mode));
   if (s > MAXSTAGES) s = MAXSTAGES;
-  int w = s - 2;
-  if (const char* e = getenv("DISTBO_EMBED_TC_WARPS")) {   // measurement knob
+  int teams = s - 1;                                     // stages under consumption (measured best: the consumers,
+                                                         // not the copies, are the bottleneck); the rest are in flight
+  if (const char* e = getenv("DISTBO_EMBED_TC_WARPS")) {   // measurement knob (teams)
     const int v = atoi(e);
-    if (v >= 1 && v < s) w = v;
+    if (v >= 1 && v < s) teams = v;
   }
-  if (w > 12) w = 12;
+  if (teams * wps > MAXWARPS) teams = MAXWARPS / wps;
+  if (teams < 1) teams = 1;
+  // producer warps: a divisor of the ring depth (a stage then always belongs to one producer, which has itself
+  // seen every earlier phase of the stage's empty barrier); an odd prime depth gives up one stage
+  int pw = 1;
+  for (;;) {
+    pw = s % 4 == 0 ? 4 : (s % 3 == 0 ? 3 : (s % 2 == 0 ? 2 : 1));
+    if (pw > 1 || s <= 4) break;
+    --s;
+  }
+  if (teams >= s) teams = s - 1;
   *stages = s;
-  *consumers = w;
+  *consumers = teams * wps;
+  *producers = pw;
 }
 // Shapes this path takes (everything else runs on the generic kernel).
 inline bool eligible(int dx, int dy, int hx, int p, int y_mode) {
@@ -875,7 +937,7 @@ inline bool eligible(int dx, int dy, int hx, int p, int y_mode) {
   if (!(y_mode == 0 || y_mode == 2)) return false;
   if (y_mode == 2 && (dy < 1 || dy > GQMAX)) return false;
   if (hx < 1 || hx > EMB_HMAX || p < 1 || p > EMB_PMAX || dx < 1) return false;
-  if (fixed_smem(dx, hx) + 4 * stage_smem(dx, dy, y_mode) > 227 * 1024) return false;   // at least 4 stages
+  if (fixed_smem(dx, hx) + 4 * stage_smem(32, dx, dy, y_mode) > 227 * 1024) return false;   // at least 4 stages
   return true;
 }
 // workspace: chunk_first [T+1] | chunk_ds [mc] | chunk_row [mc] | (align 256) partial [mc][qw]
@@ -1230,12 +1292,19 @@ static int embed_fwd_launch(EmbedArgs<T> a, int64_t S, void* workspace, int64_t 
 }
 
 // fp32 forward through the tensor-core kernel (x-net-only poolings).
-template <int NT>
+template <int NT, int MT>
 static int embed_fwd_tc_launch_nt(const tc::Args& t, int grid, size_t smem, cudaStream_t st) {
-  DB_CUDA(cudaFuncSetAttribute(tc::embed_fwd_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::embed_fwd_tc_kernel<NT><<<grid, 32 * (t.consumers + 1), smem, st>>>(t);
+  DB_CUDA(cudaFuncSetAttribute(tc::embed_fwd_tc_kernel<NT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc::embed_fwd_tc_kernel<NT, MT><<<grid, 32 * (t.consumers + t.producers), smem, st>>>(t);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
+}
+template <int MT>
+static int embed_fwd_tc_launch_mt(const tc::Args& t, int NT, int grid, size_t smem, cudaStream_t st) {
+  if (NT == 1) return embed_fwd_tc_launch_nt<1, MT>(t, grid, smem, st);
+  if (NT == 2) return embed_fwd_tc_launch_nt<2, MT>(t, grid, smem, st);
+  if (NT == 3) return embed_fwd_tc_launch_nt<3, MT>(t, grid, smem, st);
+  return embed_fwd_tc_launch_nt<4, MT>(t, grid, smem, st);
 }
 
 static int embed_fwd_tc_launch(const EmbedArgs<float>& a, int64_t S, void* workspace, int64_t workspace_bytes,
@@ -1254,25 +1323,28 @@ static int embed_fwd_tc_launch(const EmbedArgs<float>& a, int64_t S, void* works
   t.chunk_ds = chunk_ds; t.chunk_row = chunk_row; t.chunk_first = chunk_first;
   t.partial = (float*)((unsigned char*)workspace + tc::header_bytes(S, a.T_));
   t.ksteps = (a.dx + 7) / 8; t.gq = gq; t.qw = tc::qw_of(a.hx, gq);
-  tc::plan(a.dx, a.dy, a.hx, a.y_mode, &t.stages, &t.consumers);
-  t.x_region = tc::region_bytes(a.dx);
-  t.y_region = a.y_mode == 2 ? tc::region_bytes(a.dy) : 0u;
-  const size_t smem = tc::fixed_smem(a.dx, a.hx) + (size_t)t.stages * tc::stage_smem(a.dx, a.dy, a.y_mode);
-  embed_chunk_table_kernel<<<1, 256, 0, st>>>(a.seg_off, a.T_, tc::ROWS, chunk_first, chunk_ds, chunk_row);
+  int MT;
+  tc::mode(&MT, &t.wps);
+  t.rows = 16 * MT * t.wps;
+  tc::plan(t.rows, t.wps, a.dx, a.dy, a.hx, a.y_mode, &t.stages, &t.consumers, &t.producers);
+  const char* skip = getenv("DISTBO_EMBED_TC_SKIP");
+  t.skip_compute = (skip && skip[0] == '1') ? 1 : 0;
+  t.x_region = tc::region_bytes(t.rows, a.dx);
+  const size_t smem = tc::fixed_smem(a.dx, a.hx) + (size_t)t.stages * tc::stage_smem(t.rows, a.dx, a.dy, a.y_mode);
+  const int64_t chunks_ub = S / t.rows + a.T_;
+  const int table_grid = (int)std::min<int64_t>(64, (chunks_ub + 255) / 256);
+  embed_chunk_table_kernel<<<table_grid, 256, 0, st>>>(a.seg_off, a.T_, t.rows, chunk_first, chunk_ds, chunk_row);
   DB_CHECK_LAUNCH();
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t want = (mc + t.consumers - 1) / t.consumers;
+  const int teams = t.consumers / t.wps;
+  const int64_t want = (chunks_ub + teams - 1) / teams;
   const int grid = (int)(want < sms ? want : sms);      // one persistent CTA per SM
   const int NT = tc::nt_of(a.hx);
-  int rc;
-  if (NT == 1) rc = embed_fwd_tc_launch_nt<1>(t, grid, smem, st);
-  else if (NT == 2) rc = embed_fwd_tc_launch_nt<2>(t, grid, smem, st);
-  else if (NT == 3) rc = embed_fwd_tc_launch_nt<3>(t, grid, smem, st);
-  else rc = embed_fwd_tc_launch_nt<4>(t, grid, smem, st);
+  const int rc = MT == 2 ? embed_fwd_tc_launch_mt<2>(t, NT, grid, smem, st) : embed_fwd_tc_launch_mt<1>(t, NT, grid, smem, st);
   if (rc) return rc;
-  tc::embed_fwd_tc_reduce_kernel<<<a.T_, 256, 0, st>>>(t, 8 * NT);
+  tc::embed_fwd_tc_reduce_kernel<<<a.T_, 1024, 0, st>>>(t, 8 * NT);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
 }
