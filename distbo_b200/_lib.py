@@ -21,14 +21,15 @@ SIGNATURES = {
     "distbo_version": (_i, []),
     "distbo_launch_count": (_i64, [_i]),
     "distbo_debug_timeline": (_i, [_vp]),
-    "distbo_embed_fwd_f64": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i,
-                                  _i, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
-    "distbo_embed_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i,
-                                  _i, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
-    "distbo_embed_bwd_f64": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i,
-                                  _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "distbo_embed_f32_on_tensor_cores": (_i, [_i, _i, _i, _i, _i]),
-    "distbo_embed_workspace": (_i64, [_i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "distbo_embed_fwd_f64": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                                  _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
+    "distbo_embed_fwd_f32": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                                  _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
+    "distbo_embed_bwd_f64": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                                  _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _i64, _vp]),
+    "distbo_embed_f32_on_tensor_cores": (_i, [_i, _i, _i, _i, _i, _i]),
+    "distbo_embed_workspace": (_i64, [_i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "distbo_task_gram_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "distbo_scale_theta_f64": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "distbo_gram_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _d, _vp, _vp]),

@@ -72,17 +72,27 @@ struct EmbedArgs {
   T* partial;                  // [max_chunks][psum]
   const T* log_reg;            // 'concat' only: log of the ridge lambda
   double* raw;                 // 'concat' only: [T][psum] per-dataset sums kept for the backward pass
+  // optional third layer of the x net (nn_net's 'weights_3' branch, distbo_net.py:11-13): pm > 0 means
+  // W2x is [hx, pm], mid = tanh(h W2x + b2x), phi_x = mid W3x with W3x [pm, p]; pm == 0: phi_x = h W2x, W2x [hx, p]
+  int pm = 0;
+  const T* b2x = nullptr;
+  const T* W3x = nullptr;
 };
 
 __host__ __device__ inline int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
 // y_mode: 0 'none' (phi_x only), 1 'joint' regression (y-net), 2 classification (one-hot y),
 //         3 'concat' regression: marginal mean(phi_x) (+) conditional embedding operator (distbo_net.py:49-89)
+//         4 phi_x only, then the class ratios mean(y): the 'nn' operator on classification data (distbo_net.py:18-20,43-48)
 __host__ __device__ inline bool has_ynet(int y_mode) { return y_mode == 1 || y_mode == 3; }
-__host__ __device__ inline int gq_of(int y_mode, int q, int dy) { return y_mode == 0 ? 1 : (has_ynet(y_mode) ? q : dy); }
+__host__ __device__ inline int gq_of(int y_mode, int q, int dy) {
+  return (y_mode == 0 || y_mode == 4) ? 1 : (has_ynet(y_mode) ? q : dy);
+}
+// columns of the staged y-feature tile (mode 4 keeps [1 | y] so that the class ratios pool from shared memory)
+__host__ __device__ inline int fyw_of(int y_mode, int q, int dy) { return y_mode == 4 ? 1 + dy : gq_of(y_mode, q, dy); }
 // width of the embedding row
 __host__ __device__ inline int pout_of(int y_mode, int p, int q, int dy) {
   if (y_mode == 3) return p + q * p;
-  return y_mode == 0 ? p : p * gq_of(y_mode, q, dy) + (y_mode == 2 ? dy : 0);
+  return y_mode == 0 ? p : p * gq_of(y_mode, q, dy) + ((y_mode == 2 || y_mode == 4) ? dy : 0);
 }
 // number of pooled sums per chunk ('concat': sum phi_x [p], Psi^T Phi [q][p], Phi^T Phi [p][p])
 __host__ __device__ inline int psum_of(int y_mode, int p, int q, int dy) {
@@ -170,6 +180,13 @@ __device__ __forceinline__ void load_net(const T* __restrict__ W1, const T* __re
   }
   for (int j = threadIdx.x; j < hp; j += blockDim.x) sb1[j] = (j < h) ? b1[j] : (T)0;
   for (int i = threadIdx.x; i < h * po; i += blockDim.x) sW2[i] = W2[i];
+}
+
+// Third layer of the x net: sb2 [pm], sW3 [pm][p].
+template <typename T>
+__device__ __forceinline__ void load_layer3(const T* __restrict__ b2, const T* __restrict__ W3, int pm, int p, T* sb2, T* sW3) {
+  for (int j = threadIdx.x; j < pm; j += blockDim.x) sb2[j] = b2[j];
+  for (int i = threadIdx.x; i < pm * p; i += blockDim.x) sW3[i] = W3[i];
 }
 
 // Asynchronously stage columns [k0, k0+kc) of `n` rows (row stride din) into sX [ROWS][XS] with cp.async in the
@@ -303,26 +320,31 @@ __device__ __forceinline__ void output_forward(const T* sH, const T* sW2, int h,
 template <typename T>
 struct EmbSmem {
   T *sW1x, *sb1x, *sW2x, *sW1y, *sb1y, *sW2y, *sX, *sHx, *sHy, *sFx, *sFy, *sDZ, *sDF, *sG;
-  int hpx, hpy, gq, fsx, fsy, dfs;
+  T *sb2x, *sW3x, *sMx, *sDM;   // third layer of the x net: bias, weights, mid activations, their upstream gradient
+  int hpx, hpy, gq, fsx, fsy, dfs, msx;
   size_t elems;
 };
 
 template <typename T>
 __host__ __device__ inline EmbSmem<T> emb_layout(T* base, int dx, int dy, int hx, int p, int hy, int q, int y_mode,
-                                                 bool backward) {
+                                                 bool backward, int pm = 0) {
   constexpr int ROWS = 32 * EmbT<T>::RM, XS = EmbT<T>::XS;
   EmbSmem<T> s;
   s.hpx = round_up_i(hx, 4);
   s.hpy = has_ynet(y_mode) ? round_up_i(hy, 4) : 0;
   s.gq = gq_of(y_mode, q, dy);
   s.fsx = p + 1;
-  s.fsy = s.gq + 1;
+  s.fsy = fyw_of(y_mode, q, dy) + 1;
   s.dfs = (p > s.gq ? p : s.gq) + 1;
+  s.msx = pm + 1;
+  const int po2 = pm > 0 ? pm : p;                       // output width of the x net's second layer
   size_t off = 0;
   auto take = [&](size_t n) { T* ptr = base + off; off += (n + 3) / 4 * 4; return ptr; };
   s.sW1x = take((size_t)round_up_i(dx, 4) * s.hpx);
   s.sb1x = take(s.hpx);
-  s.sW2x = take((size_t)hx * p);
+  s.sW2x = take((size_t)hx * po2);
+  s.sb2x = take(pm);
+  s.sW3x = take((size_t)pm * p);
   s.sW1y = take(has_ynet(y_mode) ? (size_t)round_up_i(dy, 4) * s.hpy : 0);
   s.sb1y = take(s.hpy);
   s.sW2y = take(has_ynet(y_mode) ? (size_t)hy * q : 0);
@@ -331,10 +353,13 @@ __host__ __device__ inline EmbSmem<T> emb_layout(T* base, int dx, int dy, int hx
   s.sHy = take((size_t)ROWS * s.hpy);
   s.sFx = take((size_t)ROWS * s.fsx);
   s.sFy = take((size_t)ROWS * s.fsy);
+  s.sMx = take(pm > 0 ? (size_t)ROWS * s.msx : 0);
+  s.sDM = take(backward && pm > 0 ? (size_t)ROWS * s.msx : 0);
   const int hpm = s.hpx > s.hpy ? s.hpx : s.hpy;
   s.sDZ = take(backward ? (size_t)ROWS * hpm : 0);
   s.sDF = take(backward ? (size_t)ROWS * s.dfs : 0);
-  const size_t nparams = (size_t)dx * hx + hx + (size_t)hx * p + (has_ynet(y_mode) ? (size_t)dy * hy + hy + (size_t)hy * q : 0);
+  const size_t nparams = (size_t)dx * hx + hx + (size_t)hx * po2 + (pm > 0 ? (size_t)pm + (size_t)pm * p : 0) +
+                         (has_ynet(y_mode) ? (size_t)dy * hy + hy + (size_t)hy * q : 0);
   s.sG = take(backward ? nparams : 0);
   s.elems = off;
   return s;
@@ -345,15 +370,31 @@ template <typename T>
 __device__ __forceinline__ void chunk_features(const EmbedArgs<T>& a, const EmbSmem<T>& s, int row0, int n) {
   constexpr int ROWS = 32 * EmbT<T>::RM;
   hidden_forward<T>(a.X + (size_t)row0 * a.dx, n, a.dx, a.hx, s.hpx, s.sW1x, s.sb1x, s.sX, s.sHx);
-  output_forward<T>(s.sHx, s.sW2x, a.hx, s.hpx, a.p, s.sFx, s.fsx);
+  if (a.pm > 0) {                                        // three-layer x net: mid = tanh(h W2 + b2), phi_x = mid W3
+    output_forward<T>(s.sHx, s.sW2x, a.hx, s.hpx, a.pm, s.sMx, s.msx);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ROWS * a.pm; idx += blockDim.x) {
+      const int r = idx / a.pm, j = idx - r * a.pm;
+      s.sMx[r * s.msx + j] = (r < n) ? EmbT<T>::tanh_(s.sMx[r * s.msx + j] + s.sb2x[j]) : (T)0;
+    }
+    __syncthreads();
+    output_forward<T>(s.sMx, s.sW3x, a.pm, s.msx, a.p, s.sFx, s.fsx);
+  } else {
+    output_forward<T>(s.sHx, s.sW2x, a.hx, s.hpx, a.p, s.sFx, s.fsx);
+  }
   if (has_ynet(a.y_mode)) {
     hidden_forward<T>(a.Y + (size_t)row0 * a.dy, n, a.dy, a.hy, s.hpy, s.sW1y, s.sb1y, s.sX, s.sHy);
     output_forward<T>(s.sHy, s.sW2y, a.hy, s.hpy, a.q, s.sFy, s.fsy);
   } else {
-    for (int idx = threadIdx.x; idx < ROWS * s.gq; idx += blockDim.x) {
-      const int r = idx / s.gq, j = idx - r * s.gq;
+    const int fyw = fyw_of(a.y_mode, a.q, a.dy);
+    for (int idx = threadIdx.x; idx < ROWS * fyw; idx += blockDim.x) {
+      const int r = idx / fyw, j = idx - r * fyw;
       T v = (T)0;
-      if (r < n) v = (a.y_mode == 2) ? a.Y[(size_t)(row0 + r) * a.dy + j] : (T)1;
+      if (r < n) {
+        if (a.y_mode == 2) v = a.Y[(size_t)(row0 + r) * a.dy + j];
+        else if (a.y_mode == 4 && j > 0) v = a.Y[(size_t)(row0 + r) * a.dy + j - 1];
+        else v = (T)1;
+      }
       s.sFy[r * s.fsy + j] = v;
     }
   }
@@ -365,8 +406,9 @@ template <typename T>
 __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_fwd_kernel(EmbedArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int ROWS = 32 * EmbT<T>::RM;
-  const EmbSmem<T> s = emb_layout<T>(reinterpret_cast<T*>(smem_raw), a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, false);
-  load_net<T>(a.W1x, a.b1x, a.W2x, a.dx, a.hx, a.p, s.hpx, s.sW1x, s.sb1x, s.sW2x);
+  const EmbSmem<T> s = emb_layout<T>(reinterpret_cast<T*>(smem_raw), a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, false, a.pm);
+  load_net<T>(a.W1x, a.b1x, a.W2x, a.dx, a.hx, a.pm > 0 ? a.pm : a.p, s.hpx, s.sW1x, s.sb1x, s.sW2x);
+  if (a.pm > 0) load_layer3<T>(a.b2x, a.W3x, a.pm, a.p, s.sb2x, s.sW3x);
   if (has_ynet(a.y_mode)) load_net<T>(a.W1y, a.b1y, a.W2y, a.dy, a.hy, a.q, s.hpy, s.sW1y, s.sb1y, s.sW2y);
   __syncthreads();   // weights (incl. the biases read right below) are visible to every thread
   const int n_chunks = a.chunk_first[a.T_];
@@ -395,7 +437,7 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_fwd_kernel(EmbedArgs<
         const int i = o / gq, j = o - i * gq;     // row-major flatten i*q + j (distbo_net.py:40-42)
         u = s.sFx + i; us = s.fsx; v = s.sFy + j; vs = s.fsy;
       } else {
-        u = s.sFy + (o - a.p * gq); us = s.fsy;   // class ratios: mean of y (distbo_net.py:45-48)
+        u = s.sFy + (o - a.p * gq) + (a.y_mode == 4 ? 1 : 0); us = s.fsy;   // class ratios: mean of y (distbo_net.py:45-48)
       }
       T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;   // four interleaved row chains, combined in a fixed order
       if (v) {
@@ -857,15 +899,13 @@ __global__ void __launch_bounds__(1024) embed_fwd_tc_reduce_kernel(Args a, int n
     const int o = o0 + col;
     double acc = 0.0;
     if (o < a.qw) {
-      int c = b0;
-      for (; c + 8 <= b1; c += 8) {
-        float x[8];
+      for (int c = b0; c < b1; c += 16) {                // 16 independent (masked) loads per round, added in order
+        float x[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = a.partial[(size_t)(c + u) * a.qw + o];
+        for (int u = 0; u < 16; ++u) x[u] = (c + u < b1) ? a.partial[(size_t)(c + u) * a.qw + o] : 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc += (double)x[u];
+        for (int u = 0; u < 16; ++u) acc += (double)x[u];
       }
-      for (; c < b1; ++c) acc += (double)a.partial[(size_t)c * a.qw + o];
     }
     part[k][col] = acc;
     __syncthreads();
@@ -1042,8 +1082,9 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
   typedef double T;
   constexpr int ROWS = 32 * EmbT<T>::RM, XS = EmbT<T>::XS;
   const EmbedArgs<T>& a = b.f;
-  const EmbSmem<T> s = emb_layout<T>(reinterpret_cast<T*>(smem_raw), a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, true);
-  load_net<T>(a.W1x, a.b1x, a.W2x, a.dx, a.hx, a.p, s.hpx, s.sW1x, s.sb1x, s.sW2x);
+  const EmbSmem<T> s = emb_layout<T>(reinterpret_cast<T*>(smem_raw), a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, true, a.pm);
+  load_net<T>(a.W1x, a.b1x, a.W2x, a.dx, a.hx, a.pm > 0 ? a.pm : a.p, s.hpx, s.sW1x, s.sb1x, s.sW2x);
+  if (a.pm > 0) load_layer3<T>(a.b2x, a.W3x, a.pm, a.p, s.sb2x, s.sW3x);
   if (has_ynet(a.y_mode)) load_net<T>(a.W1y, a.b1y, a.W2y, a.dy, a.hy, a.q, s.hpy, s.sW1y, s.sb1y, s.sW2y);
   for (int i = threadIdx.x; i < b.nparams; i += blockDim.x) s.sG[i] = 0.0;   // owner-exclusive accumulators
   __syncthreads();
@@ -1051,7 +1092,8 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
   const int gq = s.gq, dfs = s.dfs;
   const int nets = has_ynet(a.y_mode) ? 2 : 1;
   const int nthr = blockDim.x;
-  const int nx = a.dx * a.hx + a.hx + a.hx * a.p;
+  const int po2x = a.pm > 0 ? a.pm : a.p;                // output width of the x net's second layer
+  const int nx = a.dx * a.hx + a.hx + a.hx * po2x + (a.pm > 0 ? a.pm + a.pm * a.p : 0);
 
   for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const int t = a.chunk_ds[c], row0 = a.chunk_row[c];
@@ -1060,11 +1102,14 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
     chunk_features<T>(a, s, row0, n);
     const double* de = b.dE + (size_t)t * a.lde;
     for (int net = 0; net < nets; ++net) {
-      const int din = net ? a.dy : a.dx, h = net ? a.hy : a.hx, po = net ? a.q : a.p, hp = net ? s.hpy : s.hpx;
+      const int din = net ? a.dy : a.dx, h = net ? a.hy : a.hx, hp = net ? s.hpy : s.hpx;
+      int po = net ? a.q : a.p;               // width of the net's output (of its second layer once layer 3 is peeled)
       const double* sH = net ? s.sHy : s.sHx;
       const double* sW2 = net ? s.sW2y : s.sW2x;
       const double* Xg = (net ? a.Y : a.X) + (size_t)row0 * din;
-      double* G = s.sG + (net ? nx : 0);      // [W1 (din*h) | b1 (h) | W2 (h*po)]
+      double* G = s.sG + (net ? nx : 0);      // [W1 (din*h) | b1 (h) | W2 (h*po2)] and, x net with 3 layers, [b2 (pm) | W3 (pm*p)]
+      const double* sDO = s.sDF;              // upstream gradient of the second layer's output, row stride dos
+      int dos = dfs;
       // upstream gradient of this net's output: x side dF[r][i] = sum_j dE[t][i*gq+j] phi_y[r][j] / len,
       //                                         y side dG[r][j] = sum_i dE[t][i*gq+j] phi_x[r][i] / len
       for (int idx = threadIdx.x; idx < ROWS * po; idx += nthr) {
@@ -1093,12 +1138,51 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
         s.sDF[r * dfs + i] = v;
       }
       __syncthreads();
+      if (net == 0 && a.pm > 0) {
+        // third layer peeled: dW3[j][i] += sum_r mid[r][j] dF[r][i];  dmid[r][j] = (sum_i W3[j][i] dF[r][i]) (1 - mid^2);
+        // db2[j] += sum_r dmid[r][j].  dmid then plays dF's part for the two layers below.
+        const int pm = a.pm, msx = s.msx;
+        double* G3 = G + din * h + h + h * pm;            // [b2 | W3]
+        for (int e = threadIdx.x; e < pm * po; e += nthr) {
+          const int j = e / po, i = e - j * po;
+          double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+          for (int r = 0; r < n; r += 4) {                // rows >= n hold zeros in sDF
+            v0 += s.sMx[r * msx + j] * s.sDF[r * dfs + i];
+            v1 += s.sMx[(r + 1) * msx + j] * s.sDF[(r + 1) * dfs + i];
+            v2 += s.sMx[(r + 2) * msx + j] * s.sDF[(r + 2) * dfs + i];
+            v3 += s.sMx[(r + 3) * msx + j] * s.sDF[(r + 3) * dfs + i];
+          }
+          G3[pm + e] += (v0 + v1) + (v2 + v3);
+        }
+        for (int idx = threadIdx.x; idx < ROWS * pm; idx += nthr) {
+          const int r = idx / pm, j = idx - r * pm;
+          double v = 0.0;
+          if (r < n) {
+            for (int i = 0; i < po; ++i) v += s.sW3x[j * po + i] * s.sDF[r * dfs + i];
+            const double mj = s.sMx[r * msx + j];
+            v *= (1.0 - mj * mj);
+          }
+          s.sDM[r * msx + j] = v;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < pm) {
+          double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+          for (int r = 0; r < n; r += 4) {
+            v0 += s.sDM[r * msx + threadIdx.x];
+            v1 += s.sDM[(r + 1) * msx + threadIdx.x];
+            v2 += s.sDM[(r + 2) * msx + threadIdx.x];
+            v3 += s.sDM[(r + 3) * msx + threadIdx.x];
+          }
+          G3[threadIdx.x] += (v0 + v1) + (v2 + v3);
+        }
+        sDO = s.sDM; dos = msx; po = pm;
+      }
       // dz[r][j] = (sum_i W2[j][i] dF[r][i]) (1 - h^2); zero on pad rows / pad hidden units
       for (int idx = threadIdx.x; idx < ROWS * hp; idx += nthr) {
         const int r = idx / hp, j = idx - r * hp;
         double v = 0.0;
         if (j < h && r < n) {
-          for (int i = 0; i < po; ++i) v += sW2[j * po + i] * s.sDF[r * dfs + i];
+          for (int i = 0; i < po; ++i) v += sW2[j * po + i] * sDO[r * dos + i];
           const double hj = sH[r * hp + j];
           v *= (1.0 - hj * hj);
         }
@@ -1111,10 +1195,10 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
         // rows >= n hold zeros in sDF, so the loops may run over whole groups of four (ROWS is a multiple of 4)
         double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
         for (int r = 0; r < n; r += 4) {
-          v0 += sH[r * hp + j] * s.sDF[r * dfs + i];
-          v1 += sH[(r + 1) * hp + j] * s.sDF[(r + 1) * dfs + i];
-          v2 += sH[(r + 2) * hp + j] * s.sDF[(r + 2) * dfs + i];
-          v3 += sH[(r + 3) * hp + j] * s.sDF[(r + 3) * dfs + i];
+          v0 += sH[r * hp + j] * sDO[r * dos + i];
+          v1 += sH[(r + 1) * hp + j] * sDO[(r + 1) * dos + i];
+          v2 += sH[(r + 2) * hp + j] * sDO[(r + 2) * dos + i];
+          v3 += sH[(r + 3) * hp + j] * sDO[(r + 3) * dos + i];
         }
         G[din * h + h + e] += (v0 + v1) + (v2 + v3);
       }
@@ -1171,10 +1255,14 @@ __global__ void __launch_bounds__(32 * EMB_MAXWARPS) embed_bwd_kernel(EmbedBwdAr
 // Sums the per-CTA gradient partials in a fixed order: a block handles 32 consecutive parameters (lane = parameter,
 // coalesced), its 8 warps each add one contiguous eighth of the partials (8 loads in flight), and warp 0 adds the
 // eight sums in warp order.  Deterministic; ~5 dependent load rounds instead of nparts / 16.
+// The flat parameter index is mapped to the caller's gradient tensors through up to 8 (start, pointer) segments.
+struct GradSegs {
+  int n;
+  int start[9];          // start[k] .. start[k+1] belongs to out[k]
+  double* out[8];
+};
 __global__ void __launch_bounds__(256) embed_bwd_reduce_kernel(const double* __restrict__ partial, int nparts,
-                                                               int nparams, int nx, int dxh, int hx, double* gW1x,
-                                                               double* gb1x, double* gW2x, int dyh, int hy,
-                                                               double* gW1y, double* gb1y, double* gW2y) {
+                                                               int nparams, GradSegs segs) {
   __shared__ double part[8][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
@@ -1198,20 +1286,14 @@ __global__ void __launch_bounds__(256) embed_bwd_reduce_kernel(const double* __r
   s = part[0][lane];
 #pragma unroll
   for (int g = 1; g < 8; ++g) s += part[g][lane];
-  if (i < nx) {
-    if (i < dxh) gW1x[i] = s;
-    else if (i < dxh + hx) gb1x[i - dxh] = s;
-    else gW2x[i - dxh - hx] = s;
-  } else {
-    const int k = i - nx;
-    if (k < dyh) gW1y[k] = s;
-    else if (k < dyh + hy) gb1y[k - dyh] = s;
-    else gW2y[k - dyh - hy] = s;
-  }
+  for (int k = 0; k < segs.n; ++k)
+    if (i >= segs.start[k] && i < segs.start[k + 1]) segs.out[k][i - segs.start[k]] = s;
 }
 
 // ------------------------------------------------------------------ host side
-inline int net_elems(int din, int h, int po) { return din * h + h + h * po; }
+inline int net_elems(int din, int h, int po, int pm = 0) {   // pm > 0: three layers din -> h -> pm -> po
+  return pm > 0 ? din * h + h + h * pm + pm + pm * po : din * h + h + h * po;
+}
 
 template <typename T>
 inline int64_t max_chunks(int64_t S, int Tn) { return S / (32 * EmbT<T>::RM) + Tn; }
@@ -1242,11 +1324,12 @@ static int check_args(const EmbedArgs<T>& a, int64_t S) {
   if (!a.X || !a.seg_off || !a.W1x || !a.b1x || !a.W2x || a.T_ <= 0 || a.dx <= 0 || S <= 0) return DISTBO_EARG;
   if (S > 0x7fffffffLL) return DISTBO_EARG;
   if (a.hx <= 0 || a.hx > EMB_HMAX || a.p <= 0 || a.p > EMB_PMAX) return DISTBO_EARG;
-  if (a.y_mode < 0 || a.y_mode > 3) return DISTBO_EARG;
+  if (a.y_mode < 0 || a.y_mode > 4) return DISTBO_EARG;
+  if (a.pm < 0 || a.pm > EMB_PMAX || (a.pm > 0 && (!a.b2x || !a.W3x))) return DISTBO_EARG;
   if (has_ynet(a.y_mode) && (!a.Y || !a.W1y || !a.b1y || !a.W2y || a.hy <= 0 || a.hy > EMB_HMAX || a.q <= 0 ||
                         a.q > EMB_PMAX || a.dy <= 0))
     return DISTBO_EARG;
-  if (a.y_mode == 2 && (!a.Y || a.dy <= 0 || a.dy > EMB_PMAX)) return DISTBO_EARG;
+  if ((a.y_mode == 2 || a.y_mode == 4) && (!a.Y || a.dy <= 0 || a.dy > EMB_PMAX)) return DISTBO_EARG;
   if (a.lde < pout_of(a.y_mode, a.p, a.q, a.dy)) return DISTBO_EARG;
   return DISTBO_OK;
 }
@@ -1270,7 +1353,7 @@ static int embed_fwd_launch(EmbedArgs<T> a, int64_t S, void* workspace, int64_t 
   if ((int64_t)(w.header_bytes + (size_t)mc * pout * sizeof(T)) > workspace_bytes) return DISTBO_EARG;
   a.chunk_first = w.chunk_first; a.chunk_ds = w.chunk_ds; a.chunk_row = w.chunk_row;
   a.partial = (T*)w.payload;
-  const size_t smem = emb_layout<T>((T*)nullptr, a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, false).elems * sizeof(T) + 16;
+  const size_t smem = emb_layout<T>((T*)nullptr, a.dx, a.dy, a.hx, a.p, a.hy, a.q, a.y_mode, false, a.pm).elems * sizeof(T) + 16;
   if (smem > 220 * 1024) return DISTBO_EARG;
   DB_CUDA(cudaFuncSetAttribute(embed_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   embed_chunk_table_kernel<<<1, 256, 0, st>>>(a.seg_off, a.T_, 32 * EmbT<T>::RM, w.chunk_first, w.chunk_ds, w.chunk_row);
@@ -1353,65 +1436,72 @@ static int embed_fwd_tc_launch(const EmbedArgs<float>& a, int64_t S, void* works
 
 using namespace db;
 
-extern "C" int64_t distbo_embed_workspace(int64_t S, int T, int dx, int dy, int hx, int p, int hy, int q, int y_mode,
-                                          int elem_bytes, int backward) {
+extern "C" int64_t distbo_embed_workspace(int64_t S, int T, int dx, int dy, int hx, int p, int pm, int hy, int q,
+                                          int y_mode, int elem_bytes, int backward) {
   if (S <= 0 || T <= 0) return 0;
   const int pout = psum_of(y_mode, p, q, dy);
   if (elem_bytes == 4 && !backward) {
     EmbWs<float> w = ws_layout<float>(nullptr, S, T);
     size_t need = w.header_bytes + (size_t)max_chunks<float>(S, T) * pout * 4;
-    if (y_mode == 0 || y_mode == 2)                        // the tensor-core path: 32-row chunks, (hidden + 1) * gq sums each
+    if (pm == 0 && (y_mode == 0 || y_mode == 2))           // the tensor-core path: (hidden + 1) * gq sums per 16 rows
       need = std::max(need, tc::workspace_bytes(S, T, hx, y_mode == 2 ? dy : 1));
     return (int64_t)need;
   }
   EmbWs<double> w = ws_layout<double>(nullptr, S, T);
   if (!backward) return (int64_t)(w.header_bytes + (size_t)max_chunks<double>(S, T) * pout * 8);
-  const int np = net_elems(dx, hx, p) + (has_ynet(y_mode) ? net_elems(dy, hy, q) : 0);
+  const int np = net_elems(dx, hx, p, pm) + (has_ynet(y_mode) ? net_elems(dy, hy, q) : 0);
   return (int64_t)(w.header_bytes + (size_t)EMB_BWD_GRID * np * 8 + (y_mode == 3 ? (size_t)T * coef_len(p, q) * 8 : 0));
 }
 
 extern "C" int distbo_embed_fwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S,
                                     int dx, int dy, const double* W1x, const double* b1x, const double* W2x, int hx,
-                                    int p, const double* W1y, const double* b1y, const double* W2y, int hy, int q,
-                                    int y_mode, const double* log_reg, double* raw_sums, double* E, int lde,
-                                    void* workspace, int64_t workspace_bytes, void* stream) {
+                                    int p, int pm, const double* b2x, const double* W3x, const double* W1y,
+                                    const double* b1y, const double* W2y, int hy, int q, int y_mode,
+                                    const double* log_reg, double* raw_sums, double* E, int lde, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
   EmbedArgs<double> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, E, lde,
                       nullptr, nullptr, nullptr, nullptr, log_reg, raw_sums};
+  a.pm = pm; a.b2x = b2x; a.W3x = W3x;
   return embed_fwd_launch<double>(a, S, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int distbo_embed_fwd_f32(const float* X, const float* Y, const int32_t* seg_off, int T, int64_t S, int dx,
                                     int dy, const float* W1x, const float* b1x, const float* W2x, int hx, int p,
-                                    const float* W1y, const float* b1y, const float* W2y, int hy, int q, int y_mode,
-                                    const float* log_reg, double* raw_sums, float* E, int lde, void* workspace,
-                                    int64_t workspace_bytes, void* stream) {
+                                    int pm, const float* b2x, const float* W3x, const float* W1y, const float* b1y,
+                                    const float* W2y, int hy, int q, int y_mode, const float* log_reg,
+                                    double* raw_sums, float* E, int lde, void* workspace, int64_t workspace_bytes,
+                                    void* stream) {
   EmbedArgs<float> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, E, lde,
                      nullptr, nullptr, nullptr, nullptr, log_reg, raw_sums};
-  if (check_args(a, S) == DISTBO_OK && tc::eligible(dx, dy, hx, p, y_mode))
+  a.pm = pm; a.b2x = b2x; a.W3x = W3x;
+  if (pm == 0 && check_args(a, S) == DISTBO_OK && tc::eligible(dx, dy, hx, p, y_mode))
     return embed_fwd_tc_launch(a, S, workspace, workspace_bytes, (cudaStream_t)stream);
   return embed_fwd_launch<float>(a, S, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int distbo_embed_f32_on_tensor_cores(int dx, int dy, int hx, int p, int y_mode) {
-  return tc::eligible(dx, dy, hx, p, y_mode) ? 1 : 0;
+extern "C" int distbo_embed_f32_on_tensor_cores(int dx, int dy, int hx, int p, int pm, int y_mode) {
+  return (pm == 0 && tc::eligible(dx, dy, hx, p, y_mode)) ? 1 : 0;
 }
 
 extern "C" int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S,
                                     int dx, int dy, const double* W1x, const double* b1x, const double* W2x, int hx,
-                                    int p, const double* W1y, const double* b1y, const double* W2y, int hy, int q,
-                                    int y_mode, const double* log_reg, const double* raw_sums, const double* dE, int lde,
-                                    double* gW1x, double* gb1x, double* gW2x, double* gW1y, double* gb1y,
-                                    double* gW2y, double* g_log_reg, void* workspace, int64_t workspace_bytes,
-                                    void* stream) {
+                                    int p, int pm, const double* b2x, const double* W3x, const double* W1y,
+                                    const double* b1y, const double* W2y, int hy, int q, int y_mode,
+                                    const double* log_reg, const double* raw_sums, const double* dE, int lde,
+                                    double* gW1x, double* gb1x, double* gW2x, double* gb2x, double* gW3x,
+                                    double* gW1y, double* gb1y, double* gW2y, double* g_log_reg, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
   EmbedArgs<double> a{X, Y, seg_off, T, dx, dy, W1x, b1x, W2x, hx, p, W1y, b1y, W2y, hy, q, y_mode, nullptr, lde,
                       nullptr, nullptr, nullptr, nullptr, log_reg, const_cast<double*>(raw_sums)};
+  a.pm = pm; a.b2x = b2x; a.W3x = W3x;
   int rc = check_args(a, S);
   if (rc) return rc;
   if (!dE || !gW1x || !gb1x || !gW2x || !workspace) return DISTBO_EARG;
+  if (pm > 0 && (!gb2x || !gW3x)) return DISTBO_EARG;
   if (has_ynet(y_mode) && (!gW1y || !gb1y || !gW2y)) return DISTBO_EARG;
   if (y_mode == 3 && (!log_reg || !raw_sums || !g_log_reg)) return DISTBO_EARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nx = net_elems(dx, hx, p), ny = has_ynet(y_mode) ? net_elems(dy, hy, q) : 0;
+  const int nx = net_elems(dx, hx, p, pm), ny = has_ynet(y_mode) ? net_elems(dy, hy, q) : 0;
   EmbWs<double> w = ws_layout<double>(workspace, S, T);
   const size_t coef_bytes = (y_mode == 3) ? (size_t)T * coef_len(p, q) * 8 : 0;
   if ((int64_t)(w.header_bytes + (size_t)EMB_BWD_GRID * (nx + ny) * 8 + coef_bytes) > workspace_bytes) return DISTBO_EARG;
@@ -1430,7 +1520,7 @@ extern "C" int distbo_embed_bwd_f64(const double* X, const double* Y, const int3
     DB_CHECK_LAUNCH();
     b.coef = coef;
   }
-  const size_t smem = emb_layout<double>((double*)nullptr, dx, dy, hx, p, hy, q, y_mode, true).elems * 8 + 16;
+  const size_t smem = emb_layout<double>((double*)nullptr, dx, dy, hx, p, hy, q, y_mode, true, pm).elems * 8 + 16;
   if (smem > 220 * 1024) return DISTBO_EARG;
   DB_CUDA(cudaFuncSetAttribute(embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   embed_chunk_table_kernel<<<1, 256, 0, st>>>(seg_off, T, 32 * EmbT<double>::RM, w.chunk_first, w.chunk_ds, w.chunk_row);
@@ -1440,8 +1530,16 @@ extern "C" int distbo_embed_bwd_f64(const double* X, const double* Y, const int3
   const int grid = (int)(mc < EMB_BWD_GRID ? mc : EMB_BWD_GRID);
   embed_bwd_kernel<<<grid, emb_threads(hx, hy, y_mode), smem, st>>>(b);
   DB_CHECK_LAUNCH();
-  embed_bwd_reduce_kernel<<<(b.nparams + 31) / 32, 256, 0, st>>>(b.gpartial, grid, b.nparams, nx, dx * hx, hx,
-                                                                   gW1x, gb1x, gW2x, dy * hy, hy, gW1y, gb1y, gW2y);
+  // flat gradient layout: x net [W1 | b1 | W2 (| b2 | W3)], then the y net [W1 | b1 | W2]
+  GradSegs segs;
+  int k = 0, off = 0;
+  auto seg = [&](double* ptr, int len) { segs.start[k] = off; segs.out[k] = ptr; off += len; ++k; };
+  seg(gW1x, dx * hx); seg(gb1x, hx); seg(gW2x, hx * (pm > 0 ? pm : p));
+  if (pm > 0) { seg(gb2x, pm); seg(gW3x, pm * p); }
+  if (ny) { seg(gW1y, dy * hy); seg(gb1y, hy); seg(gW2y, hy * q); }
+  segs.start[k] = off;
+  segs.n = k;
+  embed_bwd_reduce_kernel<<<(b.nparams + 31) / 32, 256, 0, st>>>(b.gpartial, grid, b.nparams, segs);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
 }

@@ -50,17 +50,23 @@ class Plans:
 
 
 class NetSpec:
-    """Shapes of the embedding nets (reference train/gp_utils.py:13-26, two-layer form)."""
+    """Shapes of the embedding nets (reference train/gp_utils.py:13-26).
+
+    The x net is dx -> hx -> p, or dx -> hx -> pm -> p when `pm` > 0 (the three-layer form nn_net takes when
+    'weights_3' exists, train/distbo_net.py:11-13).  `xname` is the reference's parameter-name infix: 'x', or 'xy'
+    for the 'nn' operator, whose single net reads the concatenated [x | y] rows (dx then counts both)."""
 
     H_MAX, P_MAX = 32, 16       # hidden / output widths the embedding kernels hold in registers (embed.cu)
 
-    def __init__(self, dx, dy, hx, p, hy=0, q=0, y_mode=0):
+    def __init__(self, dx, dy, hx, p, hy=0, q=0, y_mode=0, pm=0, xname="x"):
         self.dx, self.dy, self.hx, self.p, self.hy, self.q, self.y_mode = dx, dy, hx, p, hy, q, y_mode
-        if y_mode not in (0, 1, 2, 3):
-            raise ValueError("y_mode %r: 0 (x only), 1 (joint), 2 (classification), 3 (concat)" % (y_mode,))
-        if not (1 <= hx <= self.H_MAX and 1 <= p <= self.P_MAX):
-            raise ValueError("embedding net x: hidden width <= %d and output width <= %d (got %d, %d); the shipped "
-                             "configs use (20, 10)" % (self.H_MAX, self.P_MAX, hx, p))
+        self.pm, self.xname = int(pm), xname
+        if y_mode not in (0, 1, 2, 3, 4):
+            raise ValueError("y_mode %r: 0 (x only), 1 (joint), 2 (classification), 3 (concat), 4 (x only + class "
+                             "ratios)" % (y_mode,))
+        if not (1 <= hx <= self.H_MAX and 1 <= p <= self.P_MAX and 0 <= self.pm <= self.P_MAX):
+            raise ValueError("embedding net %s: hidden width <= %d, middle and output widths <= %d (got %d, %d, %d); "
+                             "the shipped configs use (20, 10)" % (xname, self.H_MAX, self.P_MAX, hx, self.pm, p))
         if y_mode in (1, 3) and not (1 <= hy <= self.H_MAX and 1 <= q <= self.P_MAX):
             raise ValueError("embedding net y: hidden width <= %d and output width <= %d (got %d, %d)"
                              % (self.H_MAX, self.P_MAX, hy, q))
@@ -73,6 +79,8 @@ class NetSpec:
             return self.p * self.q
         if self.y_mode == 3:                      # 'concat': mean(phi_x) + conditional embedding operator
             return self.p + self.q * self.p
+        if self.y_mode == 4:                      # 'nn' on classification data: mean(phi_xy) + class ratios
+            return self.p + self.dy
         return self.p * self.dy + self.dy
 
     @property
@@ -132,9 +140,13 @@ def net_param_shapes(net):
     """Trainable tensors of the embedding nets (train/gp_utils.py:13-26; log_gaus_likelihood.py:33-48)."""
     shapes = {}
     if net is not None:
-        shapes["weights_x_1"] = (net.dx, net.hx)
-        shapes["bias_x_1"] = (net.hx,)
-        shapes["weights_x_2"] = (net.hx, net.p)
+        x = net.xname
+        shapes["weights_%s_1" % x] = (net.dx, net.hx)
+        shapes["bias_%s_1" % x] = (net.hx,)
+        shapes["weights_%s_2" % x] = (net.hx, net.pm if net.pm else net.p)
+        if net.pm:
+            shapes["bias_%s_2" % x] = (net.pm,)
+            shapes["weights_%s_3" % x] = (net.pm, net.p)
         if net.has_ynet:
             shapes["weights_y_1"] = (net.dy, net.hy)
             shapes["bias_y_1"] = (net.hy,)
@@ -224,8 +236,8 @@ class GPEngine:
     # ------------------------------------------------------------------ embedding
     def _embed_workspace(self, S, Tn, elem_bytes, backward):
         net = self.net
-        need = int(self.lib.distbo_embed_workspace(S, Tn, net.dx, net.dy, net.hx, net.p, net.hy, net.q, net.y_mode,
-                                                   elem_bytes, 1 if backward else 0))
+        need = int(self.lib.distbo_embed_workspace(S, Tn, net.dx, net.dy, net.hx, net.p, net.pm, net.hy, net.q,
+                                                   net.y_mode, elem_bytes, 1 if backward else 0))
         key = "bwd" if backward else "fwd"
         ws = self._emb_ws.get(key)
         if ws is None or ws.numel() < need:
@@ -248,7 +260,9 @@ class GPEngine:
             fn = self.lib.distbo_embed_fwd_f32
             cast = lambda t: t.float().contiguous()
         w = lambda name: cast(p.view(name)) if p.has(name) else None
-        wx1, bx1, wx2 = w("weights_x_1"), w("bias_x_1"), w("weights_x_2")
+        x = net.xname
+        wx1, bx1, wx2 = w("weights_%s_1" % x), w("bias_%s_1" % x), w("weights_%s_2" % x)
+        bx2, wx3 = w("bias_%s_2" % x), w("weights_%s_3" % x)
         wy1, by1, wy2 = w("weights_y_1"), w("bias_y_1"), w("weights_y_2")
         ws = self._embed_workspace(S, Tn, 8 if dtype == torch.float64 else 4, False)
         log_reg = raw = None
@@ -259,7 +273,7 @@ class GPEngine:
                 raw = self._emb_ws[("raw", Tn)] = torch.empty(Tn, net.n_sums, dtype=torch.float64, device=self.dev)
             self._emb_raw = raw                   # kept for embed_backward on the same batch
         rc = fn(_lib.ptr(X), _lib.ptr(Y), _lib.ptr(seg_off), Tn, S, net.dx, net.dy,
-                _lib.ptr(wx1), _lib.ptr(bx1), _lib.ptr(wx2), net.hx, net.p,
+                _lib.ptr(wx1), _lib.ptr(bx1), _lib.ptr(wx2), net.hx, net.p, net.pm, _lib.ptr(bx2), _lib.ptr(wx3),
                 _lib.ptr(wy1), _lib.ptr(by1), _lib.ptr(wy2), net.hy, net.q,
                 net.y_mode, _lib.ptr(log_reg), _lib.ptr(raw), _lib.ptr(out), out.stride(0), _lib.ptr(ws), ws.numel(),
                 _stream())
@@ -274,13 +288,15 @@ class GPEngine:
         ws = self._embed_workspace(S, Tn, 8, True)
         g = lambda name: _lib.ptr(p.gview(name)) if p.has(name) else None
         w = lambda name: _lib.ptr(p.view(name)) if p.has(name) else None
+        x = net.xname
         rc = self.lib.distbo_embed_bwd_f64(
             _lib.ptr(X), _lib.ptr(Y), _lib.ptr(seg_off), Tn, S, net.dx, net.dy,
-            w("weights_x_1"), w("bias_x_1"), w("weights_x_2"), net.hx, net.p,
+            w("weights_%s_1" % x), w("bias_%s_1" % x), w("weights_%s_2" % x), net.hx, net.p, net.pm,
+            w("bias_%s_2" % x), w("weights_%s_3" % x),
             w("weights_y_1"), w("bias_y_1"), w("weights_y_2"), net.hy, net.q, net.y_mode,
             w("log_reg"), _lib.ptr(self._emb_raw) if net.y_mode == 3 else None,
             _lib.ptr(dE), dE.stride(0),
-            g("weights_x_1"), g("bias_x_1"), g("weights_x_2"),
+            g("weights_%s_1" % x), g("bias_%s_1" % x), g("weights_%s_2" % x), g("bias_%s_2" % x), g("weights_%s_3" % x),
             g("weights_y_1"), g("bias_y_1"), g("weights_y_2"), g("log_reg"),
             _lib.ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "distbo_embed_bwd_f64")

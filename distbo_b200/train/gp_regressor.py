@@ -72,33 +72,53 @@ class gp_regressor(object):
         off = np.r_[0, np.cumsum(sizes)].astype(np.int32)
         X = self._dev(np.vstack([np.asarray(x, dtype=np.float64) for x in X_list]), dtype)
         Y = self._dev(np.vstack([check_dims(np.asarray(y, dtype=np.float64)) for y in Y_list]), dtype)
-        return X, Y, torch.from_numpy(off).to(self.engine.dev)
+        return self._join_xy(X, Y), Y, torch.from_numpy(off).to(self.engine.dev)
+
+    def _join_xy(self, X, Y):
+        """'nn' operator: the net reads the rows [x | y] (tf.concat([x, y], axis=1), train/distbo_net.py:19)."""
+        if getattr(self, "embed_op", None) == "nn" and self.kernel == "dist":
+            return torch.cat([X, Y.to(X.dtype)], 1).contiguous()
+        return X
 
     def _build_engine(self, weight_dim_x, weight_dim_y, embed_op, concat_data_size, bw_params_init,
-                      likhd_var_init, target_embed, n_tasks=0, weight_dim=None):
+                      likhd_var_init, target_embed, n_tasks=0, weight_dim=None, weight_dim_xy=None):
         d = self.in_dim_params
         net = None
         P = 0
         weights = {}
         if self.kernel == "dist":
-            if embed_op not in ("none", "joint", "concat"):
-                raise NotImplementedError("embed_op %r: 'none', 'joint' and 'concat' are on the sm_100a path "
-                                          "(SURVEY section 8f ranks 'nn' next)" % (embed_op,))
-            if len(weight_dim_x) != 2 or (weight_dim_y is not None and len(weight_dim_y) not in (0, 2)):
-                raise NotImplementedError("the sm_100a embedding kernel implements the two-layer feature map "
-                                          "(weight_dim_x / weight_dim_y of length 2, as every shipped config uses)")
+            if embed_op not in ("none", "joint", "concat", "nn"):
+                raise ValueError("embed_op %r: expected 'none', 'joint', 'concat' or 'nn'" % (embed_op,))
+        if self.kernel == "dist" and embed_op == "nn":
+            # one net over the concatenated [x | y] rows, two or three layers (train/distbo_net.py:18-20,
+            # log_gaus_likelihood.py:51-55); pooling = plain mean (+ class ratios on classification data, :43-48)
+            wd = [int(v) for v in weight_dim_xy]
+            if len(wd) not in (2, 3):
+                raise ValueError("weight_dim_xy must have 2 or 3 entries (train/gp_utils.py:13-26), got %r" % (wd,))
+            din = self.in_dim_x + self.in_dim_y
+            weights.update(init_net_weights(din, wd, "xy", self.seed))
+            net = _eng.NetSpec(din, self.in_dim_y, wd[0], wd[-1], 0, 0,
+                               y_mode=4 if self.model_type == "classification" else 0,
+                               pm=wd[1] if len(wd) == 3 else 0, xname="xy")
+            P = net.pooled_width + (1 if concat_data_size else 0)
+        elif self.kernel == "dist":
+            if len(weight_dim_x) not in (2, 3) or (weight_dim_y is not None and len(weight_dim_y) not in (0, 2)):
+                raise NotImplementedError("the sm_100a embedding kernel implements x nets of two or three layers and "
+                                          "y nets of two (the reference's CLI builds two-layer x / y nets only, "
+                                          "experiments/train_test.py:195-202)")
             weights.update(init_net_weights(self.in_dim_x, weight_dim_x, "x", self.seed))
-            hx, p = int(weight_dim_x[0]), int(weight_dim_x[1])
+            hx, p = int(weight_dim_x[0]), int(weight_dim_x[-1])
+            pm = int(weight_dim_x[1]) if len(weight_dim_x) == 3 else 0
             if self.model_type == "classification":
-                net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, 0, 0, y_mode=2)
+                net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, 0, 0, y_mode=2, pm=pm)
             elif embed_op in ("joint", "concat"):
                 weights.update(init_net_weights(self.in_dim_y, weight_dim_y, "y", self.seed))
                 net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, int(weight_dim_y[0]),
-                                   int(weight_dim_y[1]), y_mode=1 if embed_op == "joint" else 3)
+                                   int(weight_dim_y[1]), y_mode=1 if embed_op == "joint" else 3, pm=pm)
                 if embed_op == "concat":
                     weights["log_reg"] = 0.0       # log(1.0), log_gaus_likelihood.py:45-48
             else:
-                net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, 0, 0, y_mode=0)
+                net = _eng.NetSpec(self.in_dim_x, self.in_dim_y, hx, p, 0, 0, y_mode=0, pm=pm)
             # width of the embedding: train/log_gaus_likelihood.py:33-59
             P = net.pooled_width + (1 if concat_data_size else 0)
         elif self.kernel == "manual":
@@ -171,7 +191,7 @@ class gp_regressor(object):
         if self.initialise:
             self._build_engine(weight_dim_x, weight_dim_y, embed_op, concat_data_size, bw_params_init,
                                likhd_var_init, target_embed, n_tasks=len(sizes) if sizes is not None else 0,
-                               weight_dim=weight_dim)
+                               weight_dim=weight_dim, weight_dim_xy=weight_dim_xy)
         e = self.engine
         task_sizes = None if sizes is None or self.kernel == "params" else np.asarray(sizes).reshape(-1)
         e.set_observations(theta, np.asarray(y, dtype=np.float64).reshape(-1), task_sizes)
@@ -342,7 +362,8 @@ class gp_regressor(object):
             tind = list(self.target_embed_ind)
             tX = np.asarray(self.target_X, dtype=np.float64)[tind]
             tY = check_dims(np.asarray(self.target_Y, dtype=np.float64))[tind]
-            self._target_dev = (self._dev(tX), self._dev(tY))
+            tYd = self._dev(tY)
+            self._target_dev = (self._join_xy(self._dev(tX), tYd), tYd)
         X = torch.cat([sX, self._target_dev[0]], 0).to(dt)
         Y = torch.cat([sY, self._target_dev[1]], 0).to(dt)
         sizes.append(int(self._target_dev[0].shape[0]))

@@ -43,42 +43,48 @@ int distbo_debug_timeline(void* buf);
  * Fused tanh-MLP feature map phi_x (and phi_y), per-sample outer product phi_x (x) phi_y, and
  * per-dataset mean over contiguous row segments seg_off[t]..seg_off[t+1].
  *   X [S,dx], Y [S,dy] row-major; nets: W1 [d_in,h], b1 [h], W2 [h,p] (no bias on the last layer).
+ *   x net with three layers (nn_net's weights_3 branch, train/distbo_net.py:11-13): pm > 0, W2x [hx,pm], b2x [pm],
+ *   W3x [pm,p]: phi_x = tanh(tanh(x W1x + b1x) W2x + b2x) W3x.  pm == 0 (b2x, W3x NULL): the two-layer map.
+ *   The 'nn' operator (distbo_net.py:18-20) is this x net applied to the caller's [x | y] rows with y_mode 0 or 4.
  *   y_mode 0: embed_op 'none'  -> out cols = p                      (phi_x only)
  *          1: 'joint' regression -> p*q  (index i*q+j), y-net (W1y,b1y,W2y) applied to Y
  *          2: classification     -> p*dy + dy  (outer product with one-hot Y, then class ratios)
  *          3: 'concat' regression -> p + q*p: mean(phi_x), then the conditional embedding operator
  *             C = Psi^T Phi (Phi^T Phi + lambda I)^-1 flattened [q][p], lambda = exp(*log_reg)
  *             (train/distbo_net.py:49-89); raw_sums [T, p + q*p + p*p] doubles receives the per-dataset sums
- *             the backward pass needs.  log_reg / raw_sums may be NULL for y_mode 0..2.
+ *             the backward pass needs.  log_reg / raw_sums may be NULL for y_mode 0..2 and 4.
+ *          4: phi_x only, then the class ratios mean(Y) -> p + dy   ('nn' on classification data, :43-48)
  *   E [T, lde]: columns [0,P') written, the caller owns any extra columns (size-ratio column).
  *   S = seg_off[T] (total rows, known to the host).  workspace: distbo_embed_workspace(...) bytes.
  * _f32 / _f64 select the arithmetic type of samples, weights and output. */
 int distbo_embed_fwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S, int dx,
-                         int dy, const double* W1x, const double* b1x, const double* W2x, int hx, int p,
-                         const double* W1y, const double* b1y, const double* W2y, int hy, int q, int y_mode,
-                         const double* log_reg, double* raw_sums, double* E, int lde, void* workspace,
-                         int64_t workspace_bytes, void* stream);
+                         int dy, const double* W1x, const double* b1x, const double* W2x, int hx, int p, int pm,
+                         const double* b2x, const double* W3x, const double* W1y, const double* b1y,
+                         const double* W2y, int hy, int q, int y_mode, const double* log_reg, double* raw_sums,
+                         double* E, int lde, void* workspace, int64_t workspace_bytes, void* stream);
 int distbo_embed_fwd_f32(const float* X, const float* Y, const int32_t* seg_off, int T, int64_t S, int dx, int dy,
-                         const float* W1x, const float* b1x, const float* W2x, int hx, int p,
-                         const float* W1y, const float* b1y, const float* W2y, int hy, int q, int y_mode,
-                         const float* log_reg, double* raw_sums, float* E, int lde, void* workspace,
-                         int64_t workspace_bytes, void* stream);
-/* 1 when distbo_embed_fwd_f32 runs this shape on the tensor-core kernel (x-net-only poolings: y_mode 0 and 2 with
- * dy <= 4, shared-memory ring fits): rows fetched by bulk async copies, layer 1 as 3xTF32 mma.sync, the linear last
- * layer applied after the per-dataset mean.  0: the generic kernel.  (DISTBO_EMBED_TC=0 forces 0.) */
-int distbo_embed_f32_on_tensor_cores(int dx, int dy, int hx, int p, int y_mode);
-/* Backward of the above (replaces TF autodiff through distbo_net, train/train.py:31-40):
- * dE [T,lde] -> gradients of the net weights (same shapes as the weights; overwritten); y_mode 3 also
- * needs log_reg, the raw_sums its forward pass stored, and returns g_log_reg (device scalar). */
-int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S, int dx,
-                         int dy, const double* W1x, const double* b1x, const double* W2x, int hx, int p,
-                         const double* W1y, const double* b1y, const double* W2y, int hy, int q, int y_mode,
-                         const double* log_reg, const double* raw_sums, const double* dE, int lde, double* gW1x,
-                         double* gb1x, double* gW2x, double* gW1y, double* gb1y, double* gW2y, double* g_log_reg,
+                         const float* W1x, const float* b1x, const float* W2x, int hx, int p, int pm,
+                         const float* b2x, const float* W3x, const float* W1y, const float* b1y, const float* W2y,
+                         int hy, int q, int y_mode, const float* log_reg, double* raw_sums, float* E, int lde,
                          void* workspace, int64_t workspace_bytes, void* stream);
+/* 1 when distbo_embed_fwd_f32 runs this shape on the tensor-core kernel (two-layer x net, x-net-only poolings:
+ * y_mode 0 and 2 with dy <= 4, shared-memory ring fits): rows fetched by bulk async copies, layer 1 as 3xTF32
+ * mma.sync, the linear last layer applied after the per-dataset mean.  0: the generic kernel.
+ * (DISTBO_EMBED_TC=0 forces 0.) */
+int distbo_embed_f32_on_tensor_cores(int dx, int dy, int hx, int p, int pm, int y_mode);
+/* Backward of the above (replaces TF autodiff through distbo_net, train/train.py:31-40):
+ * dE [T,lde] -> gradients of the net weights (same shapes as the weights; overwritten; gb2x / gW3x only with
+ * pm > 0); y_mode 3 also needs log_reg, the raw_sums its forward pass stored, and returns g_log_reg (device scalar). */
+int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_off, int T, int64_t S, int dx,
+                         int dy, const double* W1x, const double* b1x, const double* W2x, int hx, int p, int pm,
+                         const double* b2x, const double* W3x, const double* W1y, const double* b1y,
+                         const double* W2y, int hy, int q, int y_mode, const double* log_reg,
+                         const double* raw_sums, const double* dE, int lde, double* gW1x, double* gb1x,
+                         double* gW2x, double* gb2x, double* gW3x, double* gW1y, double* gb1y, double* gW2y,
+                         double* g_log_reg, void* workspace, int64_t workspace_bytes, void* stream);
 /* Bytes of device workspace the calls above need for S = seg_off[T] total rows (chunk table + per-chunk
  * partial sums; elem_bytes 4 or 8; backward != 0 for distbo_embed_bwd_f64). */
-int64_t distbo_embed_workspace(int64_t S, int T, int dx, int dy, int hx, int p, int hy, int q, int y_mode,
+int64_t distbo_embed_workspace(int64_t S, int T, int dx, int dy, int hx, int p, int pm, int hy, int q, int y_mode,
                                int elem_bytes, int backward);
 
 /* ---- K2: Matern-3/2 product Gram  (train/kernels.py:19-28,58-88; log_gaus_likelihood.py:86-122) --

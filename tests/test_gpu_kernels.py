@@ -214,6 +214,73 @@ def test_score(cuda_engine_mod, N, d, M, acq):
     assert float(out["best_val"].item()) == pytest.approx(float(np.max(a)), rel=1e-9, abs=1e-12)
 
 
+def _nn_case(eng, mode, rs, sizes, seed):
+    """'nn' operator cases (train/distbo_net.py:18-20): one two- or three-layer net over [x | y]; classification
+    appends the class ratios (:43-48).  Returns (net, oracle params, X, Y, XY, model_type)."""
+    S = sum(sizes)
+    if mode == "nn3class":
+        dx, dy, model_type = 16, 2, "classification"
+        X = (rs.rand(S, dx) < 0.3).astype(np.float64)
+        Y = np.eye(2)[(rs.rand(S) < 0.3).astype(int)]
+    else:
+        dx, dy, model_type = 7, 1, "regression"
+        X = rs.randn(S, dx)
+        Y = rs.rand(S, dy)
+    wd = [20, 10] if mode == "nn2" else [20, 12, 10]
+    net = eng.NetSpec(dx + dy, dy, wd[0], wd[-1], 0, 0, 4 if model_type == "classification" else 0,
+                      pm=wd[1] if len(wd) == 3 else 0, xname="xy")
+    p = O.build_params(2, "dist", in_dim_x=dx, in_dim_y=dy, weight_dim_xy=wd, model_type=model_type,
+                       embed_op="nn", seed=seed)
+    p["bias_xy_1"] = rs.randn(wd[0]) * 0.1
+    if len(wd) == 3:
+        p["bias_xy_2"] = rs.randn(wd[1]) * 0.1
+    return net, p, X, Y, np.hstack([X, Y]), model_type
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 1e-5)])
+@pytest.mark.parametrize("mode", ["nn2", "nn3", "nn3class"])
+def test_embed_forward_nn(cuda_engine_mod, dtype, tol, mode):
+    eng = cuda_engine_mod
+    rs = np.random.RandomState(21)
+    sizes = [300, 17, 1000, 129, 1]
+    net, p, X, Y, XY, model_type = _nn_case(eng, mode, rs, sizes, 5)
+    e = eng.GPEngine(2, n_embed=net.pooled_width, net=net)
+    for k, v in p.items():
+        if e.params.has(k) and k.startswith(("weights", "bias")):
+            e.params.set(k, v)
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    off = torch.from_numpy(np.r_[0, np.cumsum(sizes)].astype(np.int32)).to(e.dev)
+    Eg = e.embed(torch.from_numpy(XY).to(e.dev).to(tdt), torch.from_numpy(Y).to(e.dev).to(tdt), off,
+                 dtype=tdt).double().cpu().numpy()
+    want = O.distbo_net(O.NP, X, Y, sizes, p, embed_op="nn", model_type=model_type)
+    assert want.shape[1] == net.pooled_width
+    assert rel(Eg[:, :want.shape[1]], want) < tol
+
+
+@pytest.mark.parametrize("mode", ["nn2", "nn3", "nn3class"])
+def test_embed_backward_nn(cuda_engine_mod, mode):
+    eng = cuda_engine_mod
+    rs = np.random.RandomState(22)
+    sizes = [200, 130, 77, 1]
+    net, p, X, Y, XY, model_type = _nn_case(eng, mode, rs, sizes, 6)
+    e = eng.GPEngine(2, n_embed=net.pooled_width, net=net)
+    for k, v in p.items():
+        if e.params.has(k) and k.startswith(("weights", "bias")):
+            e.params.set(k, v)
+    off = torch.from_numpy(np.r_[0, np.cumsum(sizes)].astype(np.int32)).to(e.dev)
+    dE = rs.randn(len(sizes), net.pooled_width)
+    e.embed_backward(torch.from_numpy(XY).to(e.dev), torch.from_numpy(Y).to(e.dev), off, torch.from_numpy(dE).to(e.dev))
+    tp = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=True) for k, v in p.items()}
+    out = O.distbo_net(O.TH(), torch.from_numpy(X), torch.from_numpy(Y), sizes, tp, embed_op="nn", model_type=model_type)
+    (out * torch.from_numpy(dE)).sum().backward()
+    n_checked = 0
+    for name in e.params.offsets:
+        if name.startswith(("weights", "bias")):
+            assert rel(e.params.get_grad(name), tp[name].grad.numpy()) < 1e-10, name
+            n_checked += 1
+    assert n_checked == (3 if mode == "nn2" else 5)
+
+
 @pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 1e-5)])
 @pytest.mark.parametrize("mode", ["none", "joint", "class", "concat"])
 def test_embed_forward(cuda_engine_mod, dtype, tol, mode):
@@ -300,10 +367,10 @@ def test_embed_forward_tensor_core(cuda_engine_mod, case, monkeypatch):
     want = O.distbo_net(O.NP, Xd.double().cpu().numpy(), Yd.double().cpu().numpy(), sizes, p32, embed_op=embed_op,
                         model_type=model_type)
     monkeypatch.setenv("DISTBO_EMBED_TC", "1")
-    assert eng._lib.load().distbo_embed_f32_on_tensor_cores(dx, dy, hx, pw, y_mode) == 1
+    assert eng._lib.load().distbo_embed_f32_on_tensor_cores(dx, dy, hx, pw, 0, y_mode) == 1
     got = e.embed(Xd, Yd, off, dtype=torch.float32).double().cpu().numpy()[:, :want.shape[1]]
     monkeypatch.setenv("DISTBO_EMBED_TC", "0")
-    assert eng._lib.load().distbo_embed_f32_on_tensor_cores(dx, dy, hx, pw, y_mode) == 0
+    assert eng._lib.load().distbo_embed_f32_on_tensor_cores(dx, dy, hx, pw, 0, y_mode) == 0
     generic = e.embed(Xd, Yd, off, dtype=torch.float32).double().cpu().numpy()[:, :want.shape[1]]
     assert rel(got, want) < 1e-5
     assert rel(generic, want) < 1e-5

@@ -40,10 +40,10 @@ def pair(kernel, cuda_engine_mod, **kw):
 
 
 @pytest.mark.parametrize("case", ["params", "manual", "multi", "dist_none", "dist_joint", "dist_class",
-                                  "dist_batched", "dist_concat"])
+                                  "dist_batched", "dist_concat", "dist_nn", "dist_nn3", "dist_nn3class", "dist_x3"])
 def test_fit_predict_parity(cuda_engine_mod, case):
     rs = np.random.RandomState(42)
-    classification = case == "dist_class"
+    classification = case in ("dist_class", "dist_nn3class")
     d, T, per_task = 3, 5, 24
     dx, dy = (12, 2) if classification else (6, 1)
     theta, y, sizes, X, Y = make_tasks(rs, T, per_task, d, dx, dy, 150, classification)
@@ -56,7 +56,12 @@ def test_fit_predict_parity(cuda_engine_mod, case):
         ind = np.arange(100)
         common.update(target_X=X[T], target_Y=Y[T], target_embed_ind=ind)
         fit.update(data_X=X[:T], data_Y=Y[:T], source_embed_ind=[np.arange(120)] * T, sizes=sizes,
-                   embed_op={"dist_none": "none", "dist_concat": "concat"}.get(case, "joint"), weight_dim_x=[20, 10], weight_dim_y=[20, 10],
+                   embed_op={"dist_none": "none", "dist_concat": "concat", "dist_nn": "nn", "dist_nn3": "nn",
+                             "dist_nn3class": "nn", "dist_x3": "none"}.get(case, "joint"),
+                   # 'nn' (train/distbo_net.py:18-20): one net over [x | y], two or three layers; dist_x3: a three-layer
+                   # x net under the 'none' pooling (nn_net's weights_3 branch, :11-13)
+                   weight_dim_x=[20, 12, 10] if case == "dist_x3" else [20, 10], weight_dim_y=[20, 10],
+                   weight_dim_xy=[20, 10] if case == "dist_nn" else [20, 12, 10],
                    batch_size=64 if case == "dist_batched" else 500, stratify=False,
                    concat_data_size=(case != "dist_none"), max_size=400)
     elif kernel == "manual":
