@@ -184,6 +184,11 @@ class OracleGPRegressor(object):
                 self.p = O.build_params(self.in_dim_params, "multi", n_tasks=len(sizes), **kw)
             else:
                 self.p = O.build_params(self.in_dim_params, "params", **kw)
+            # optional injected initial values {name: array} (TF's glorot stream is not reproducible, so
+            # parity runs start every implementation from the same recorded weights)
+            for k, v in (getattr(self, "initial_weights", None) or {}).items():
+                if k in self.p:
+                    self.p[k] = np.asarray(v, dtype=np.float64).reshape(np.shape(self.p[k]))
             self.adam = O.TFAdam(learning_rate)
         if self.kernel == "dist":
             self.source_X, self.source_Y = sample(data_X, data_Y, embed_ind=source_embed_ind,

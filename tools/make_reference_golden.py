@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Golden vectors produced by the REFERENCE'S OWN SOURCES (run in the build container, where /root/reference exists).
+
+hcllaw/distBO needs Python 2 + TensorFlow 1.7 (README.md:13); neither can be installed here.  Its GP path is
+nevertheless plain Python over ~55 TensorFlow ops, so this script imports distBO/train/gp_regressor.py UNMODIFIED
+from /root/reference with `tensorflow` bound to tools/tf1_shim.py (a lazy graph evaluated op for op with torch CPU
+fp64) and drives the reference's public surrogate interface:
+
+    gp_regressor(...).maximise_likhd(...)   -> train/train.py train_network + gp_utils.loop_batches + Adam
+    .initialise_predict(); .predict_y(...)  -> log_gaus_likelihood.build_predict(_dist), embed_network, eval_network
+    .similarity()
+
+The recorded numbers (loss per epoch, fitted parameters, posterior mean / std, similarities) are what the
+reference's code computes; only the TF runtime under it is substituted.  Initial network weights come from the
+shim's stand-in for glorot_normal (TF's Philox stream is not reproducible) and are stored, so that the oracle and
+the CUDA path start from the same values.
+
+    python tools/make_reference_golden.py [/root/reference]      -> tests/golden/ref_*.npz
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+sys.path.insert(0, HERE)
+import tf1_shim  # noqa: E402
+
+tf = tf1_shim.install()
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(REF, "distBO", "train"))     # train.py:8 `from gp_utils import ...` (py2 implicit relative)
+np.float = float                                                # py2-era alias (bayes_opt/target_space.py:50)
+from distBO.train.gp_regressor import gp_regressor  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def make_tasks(rs, T, per_task, d, dx, dy, rows, classification):
+    sizes = [per_task] * T
+    theta = rs.uniform(-3, 3, size=(T * per_task, d))
+    y = np.sin(theta.sum(1)) + np.repeat(rs.randn(T) * 0.2, per_task) + 0.05 * rs.randn(T * per_task)
+    X, Y = [], []
+    for t in range(T + 1):
+        n = rows + 7 * t
+        if classification:
+            X.append((rs.rand(n, dx) < 0.3).astype(np.float64))
+            Y.append(np.eye(dy)[(rs.rand(n) < 0.4).astype(int)])
+        else:
+            X.append(rs.randn(n, dx) + 0.3 * t)
+            Y.append(rs.rand(n, dy))
+    return theta, y[:, None], sizes, X, Y
+
+
+CASES = {
+    # name: (kernel, classification, embed_op, extra fit kwargs)
+    "params": ("params", False, None, {}),
+    "manual": ("manual", False, None, {}),
+    "multi": ("multi", False, None, {}),
+    "dist_none": ("dist", False, "none", dict(concat_data_size=False)),
+    "dist_joint_clip": ("dist", False, "joint", dict(concat_data_size=True, gradient_clip=True)),
+    "dist_joint_batched": ("dist", False, "joint", dict(concat_data_size=True, batch_size=64, stratify=False)),
+    "dist_joint_stratified": ("dist", False, "joint", dict(concat_data_size=False, batch_size=64, stratify=True)),
+    "dist_class": ("dist", True, "joint", dict(concat_data_size=True)),
+    "dist_concat": ("dist", False, "concat", dict(concat_data_size=True)),
+    "dist_nn3": ("dist", False, "nn", dict(concat_data_size=True, weight_dim_xy=[20, 12, 10])),
+    "dist_nn2class": ("dist", True, "nn", dict(concat_data_size=False, weight_dim_xy=[20, 10])),
+}
+
+
+def run_case(name):
+    kernel, classification, embed_op, extra = CASES[name]
+    tf.reset_default_graph()
+    tf1_shim._EAGER_SEED[0] = 0
+    rs = np.random.RandomState(abs(hash(name)) % 1000 if False else sum(map(ord, name)))
+    d, T, per_task = 3, 4, 20
+    dx, dy = (12, 2) if classification else (6, 1)
+    theta, y, sizes, X, Y = make_tasks(rs, T, per_task, d, dx, dy, 110, classification)
+    model_type = "classification" if classification else "regression"
+    common = dict(model_type=model_type, seed=7, float64=True)
+    fit = dict(learning_rate=0.005, max_epochs=8, likhd_var_init=1e-2, first_early_stop_epoch=3)
+    arrays = {"theta": theta, "y": y, "sizes": np.asarray(sizes)}
+    if kernel == "dist":
+        tind = np.arange(90)
+        sind = [np.arange(100)] * T
+        common.update(target_X=X[T], target_Y=Y[T], target_embed_ind=tind)
+        fit.update(data_X=X[:T], data_Y=Y[:T], source_embed_ind=sind, sizes=sizes, embed_op=embed_op,
+                   weight_dim_x=[20, 10], weight_dim_y=[20, 10], batch_size=500, stratify=False, max_size=400)
+        fit.update(extra)
+        for t in range(T + 1):
+            arrays["X%d" % t], arrays["Y%d" % t] = X[t], Y[t]
+        arrays["target_embed_ind"] = tind
+        arrays["source_embed_ind"] = np.asarray(sind)
+    elif kernel == "manual":
+        emb = rs.rand(T + 1, 9)
+        fit.update(data_embed=emb[:T], target_embed=emb[T:], sizes=sizes)
+        arrays["embed"] = emb
+    elif kernel == "multi":
+        fit.update(sizes=sizes)
+    g = gp_regressor(kernel, **common)
+    loss = g.maximise_likhd(theta, y, **fit)
+    init = {k: tf1_shim.INIT_VALUES[id(v)] for k, v in g.net.params.items()}
+    final = {k: v.value.detach().numpy().copy() for k, v in g.net.params.items()}
+    g.initialise_predict()
+    cand = rs.uniform(-3, 3, size=(60, d))
+    mean, std = g.predict_y(cand, compute_embed=True)
+    out = dict(arrays)
+    out.update(cand=cand, loss_log=np.asarray(g.sess.loss_log), final_loss=np.asarray(loss), pred_mean=mean, pred_std=std)
+    if kernel != "params":
+        out["similarity"] = np.asarray(g.similarity()[0])
+    for k, v in init.items():
+        out["init__" + k] = v
+    for k, v in final.items():
+        out["final__" + k] = v
+    meta = {"kernel": kernel, "model_type": model_type, "seed": 7, "T": T,
+            "fit": {k: v for k, v in fit.items() if k not in ("data_X", "data_Y", "source_embed_ind", "data_embed",
+                                                               "target_embed", "sizes")}}
+    out["meta"] = np.asarray(json.dumps(meta))
+    np.savez_compressed(os.path.join(OUT, "ref_%s.npz" % name), **out)
+    print("%-24s epochs %d  loss %.10f -> %.10f  mean[0] %.8f" % (name, len(g.sess.loss_log), g.sess.loss_log[0], loss,
+                                                                 mean[0, 0]))
+    g.close()
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    for name in CASES:
+        run_case(name)
