@@ -24,7 +24,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+REF = next((a for a in sys.argv[1:] if not a.startswith("--")), "/root/reference")
 sys.path.insert(0, HERE)
 import tf1_shim  # noqa: E402
 
@@ -123,7 +123,116 @@ def run_case(name):
     g.close()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--bo-only" not in sys.argv:
     os.makedirs(OUT, exist_ok=True)
     for name in CASES:
         run_case(name)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BO trajectories: the reference's own BO driver (model_embed/bayes_optimise.py bayes_opt_wrap ->
+# bayes_opt/bayesian_optimization.py BayesianOptimization.maximize -> helpers.py acq_max / UtilityFunction,
+# target_space.py TargetSpace, model_embed/models.py set_model + n_toy) over the same shim.  The datasets come from
+# this repo's py3 toy loader (the reference's imports sklearn.cluster.k_means_, removed from sklearn); they are
+# inputs and are stored in the file.
+BO_CASES = {
+    # name: (method, embed_op, rand_it, acq_one_shot, extra optim_config)
+    "bo_dist_none": ("dist", "none", 0, "lcb", {}),
+    "bo_dist_joint": ("dist", "joint", 0, "lcb", {}),
+    "bo_params": ("params", "none", 0, "lcb", {}),
+    "bo_multi": ("multi", "none", 3, "lcb", {}),
+    "bo_manual": ("manual", "none", 0, "ei", {}),
+    "bo_params_polish": ("params", "none", 0, "ucb", dict(n_opt_iterations=3, n_warmup=2000)),
+}
+
+
+def bo_optim_config(**over):
+    cfg = dict(weight_dim=None, weight_dim_x=[20, 10], weight_dim_y=[20, 10], weight_dim_xy=None, n_warmup=20000,
+               n_opt_iterations=0, n_epochs=25, lkh_var_init=1e-5, lr=0.005, float64=True, n_cpus=1, stratify=False,
+               embed_op='none', concat_data_size=False, algorithm='GP', gradient_clip=False, num_of_rff=0,
+               batch_size=500, first_early_stop_epoch=10, max_size=None)
+    cfg.update(over)
+    return cfg
+
+
+def run_bo_case(name):
+    import distBO.train.gp_regressor as ref_gp
+    from distBO.model_embed.bayes_optimise import bayes_opt_wrap as ref_wrap
+    from distBO.model_embed.models import set_model as ref_set_model
+    sys.path.insert(0, os.path.dirname(HERE))
+    from distbo_b200.data.toy_datasets import one_dim_split_tasks
+
+    method, embed_op, rand_it, one_shot, extra = BO_CASES[name]
+    tf.reset_default_graph()
+    tf1_shim._EAGER_SEED[0] = 0
+    target, sources, _ = one_dim_split_tasks(0, 3, 2, n_train=120, n_test=120)
+    rs = np.random.RandomState(1)
+    init_list = []
+    for s in sources:                                   # 12 evaluated configurations per source task
+        f, _, _, _ = ref_set_model('toy', s, None)
+        th = rs.uniform(-8, 8, size=12)
+        init_list.append(np.column_stack([th, [f(theta=t) for t in th]]))
+    if method == "manual":                              # manual meta-features: 4 numbers per dataset (inputs)
+        ers = np.random.RandomState(5)
+        for dset in sources + [target]:
+            dset.embed = ers.rand(4)
+    # record the initial values of the surrogate's variables (close() drops the graph)
+    inits = []
+    orig_close = ref_gp.gp_regressor.close
+
+    def recording_close(self):
+        inits.append({k: tf1_shim.INIT_VALUES[id(v)] for k, v in self.net.params.items()})
+        return orig_close(self)
+    ref_gp.gp_regressor.close = recording_close
+
+    # numpy >= 1.24 refuses the ragged np.array(list of similarity vectors) at bayes_optimise.py:60 that older numpy
+    # turned into an object array: give that module a numpy proxy with the old behaviour (nothing numeric changes)
+    import distBO.model_embed.bayes_optimise as ref_bo_mod
+
+    class _NumpyCompat(object):
+        def __getattr__(self, k):
+            return getattr(np, k)
+
+        @staticmethod
+        def array(obj, *a, **kw):
+            try:
+                return np.array(obj, *a, **kw)
+            except ValueError:
+                out = np.empty(len(obj), dtype=object)
+                for i, v in enumerate(obj):
+                    out[i] = v
+                return out
+    ref_bo_mod.np = _NumpyCompat()
+    # scipy >= 1.11 rejects the 2-D x0 that helpers.py:75-77 passes to minimize (older scipy ravelled it)
+    import distBO.bayes_opt.helpers as ref_helpers
+    from scipy.optimize import minimize as _minimize
+    ref_helpers.minimize = lambda fun, x0, *a, **kw: _minimize(fun, np.asarray(x0).ravel(), *a, **kw)
+    try:
+        out = ref_wrap(method, target, acq='ei', model='toy', rs=np.random.RandomState(7),
+                       optim_config=bo_optim_config(embed_op=embed_op, **extra), xi=0.01, kappa=2.58, bo_it=5,
+                       rand_it=rand_it, init_list=[a.copy() for a in init_list], include_init=False,
+                       source_data=sources, acq_one_shot=one_shot)
+    finally:
+        ref_gp.gp_regressor.close = orig_close
+        ref_bo_mod.np = np
+        ref_helpers.minimize = _minimize
+    traj, sim = (out if method in ("dist", "manual", "multi") else (out, None))
+    arrays = {"trajectory": np.asarray(traj, dtype=np.float64)}
+    if sim is not None:                                  # ragged (one more task after the first suggestion): zero padded
+        rows = [np.asarray(s_, dtype=np.float64).reshape(-1) for s_ in sim]
+        arrays["similarity"] = np.asarray([np.r_[r, np.full(max(map(len, rows)) - len(r), np.nan)] for r in rows])
+    for k, v in inits[0].items():
+        arrays["init__" + k] = v
+    for i, a in enumerate(init_list):
+        arrays["init_list%d" % i] = a
+    if method == "manual":
+        arrays["embed"] = np.asarray([d.embed for d in sources + [target]])
+    arrays["meta"] = np.asarray(json.dumps({"method": method, "embed_op": embed_op, "rand_it": rand_it,
+                                           "acq_one_shot": one_shot, "extra": extra}))
+    np.savez_compressed(os.path.join(OUT, "refbo_%s.npz" % name[3:]), **arrays)
+    print("%-24s suggestions %s" % (name, np.array2string(np.asarray(traj)[:, 0], precision=6)))
+
+
+if __name__ == "__main__":
+    for name in BO_CASES:
+        run_bo_case(name)

@@ -627,7 +627,7 @@ class _GlorotNormal(object):
 
     def __call__(self, shape, dtype=None, partition_info=None):
         _EAGER_SEED[0] += 1
-        rs = np.random.RandomState(self.seed * 1000 + _EAGER_SEED[0])
+        rs = np.random.RandomState((self.seed * 1000 + _EAGER_SEED[0]) % (2 ** 32))
         std = math.sqrt(2.0 / (shape[0] + shape[1]))
         vals = rs.normal(size=tuple(shape))
         bad = np.abs(vals) > 2.0
