@@ -66,7 +66,9 @@ def check(reg, z, meta, fit, final, get_param, tol):
     mean, std = reg.predict_y(z["cand"], compute_embed=True)
     assert mean.shape == z["pred_mean"].shape and std.shape == z["pred_std"].shape
     assert rel(mean, z["pred_mean"]) < tol
-    scale = float(np.exp(np.asarray(final["log_scale"]).reshape(-1)[0]))
+    # variance relative to the prior scale: exp(log_scale) for the GP, alpha |phi|^2 ~ the largest variance for BLR
+    scale = float(np.exp(np.asarray(final["log_scale"]).reshape(-1)[0])) if "log_scale" in final else \
+        float(np.max(z["pred_std"] ** 2))
     assert np.max(np.abs(std ** 2 - z["pred_std"] ** 2)) < tol * scale
     if "similarity" in z.files:
         assert rel(reg.similarity()[0], z["similarity"]) < tol
@@ -74,7 +76,8 @@ def check(reg, z, meta, fit, final, get_param, tol):
 
 def test_fixture_set_is_complete():
     assert {"params", "manual", "multi", "dist_none", "dist_joint_clip", "dist_joint_batched", "dist_joint_stratified",
-            "dist_class", "dist_concat", "dist_nn3", "dist_nn2class"} <= set(CASES)
+            "dist_class", "dist_concat", "dist_nn3", "dist_nn2class", "blr_params", "blr_manual", "blr_multi",
+            "blr_dist_joint", "blr_dist_class"} <= set(CASES)
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -66,6 +66,14 @@ CASES = {
     "dist_concat": ("dist", False, "concat", dict(concat_data_size=True)),
     "dist_nn3": ("dist", False, "nn", dict(concat_data_size=True, weight_dim_xy=[20, 12, 10])),
     "dist_nn2class": ("dist", True, "nn", dict(concat_data_size=False, weight_dim_xy=[20, 10])),
+    # BLR surrogate (train/log_gaus_likelihood_feature.py), the shipped setting: weight_dim (50,50,50), num_of_rff 0
+    "blr_params": ("params", False, None, dict(algorithm="BLR", weight_dim=[50, 50, 50], num_of_rff=0)),
+    "blr_manual": ("manual", False, None, dict(algorithm="BLR", weight_dim=[50, 50, 50], num_of_rff=0)),
+    "blr_multi": ("multi", False, None, dict(algorithm="BLR", weight_dim=[50, 50, 50], num_of_rff=0)),
+    "blr_dist_joint": ("dist", False, "joint", dict(algorithm="BLR", weight_dim=[50, 50, 50], num_of_rff=0,
+                                                    concat_data_size=True)),
+    "blr_dist_class": ("dist", True, "joint", dict(algorithm="BLR", weight_dim=[30, 20], num_of_rff=0,
+                                                   concat_data_size=True)),
 }
 
 
@@ -95,9 +103,13 @@ def run_case(name):
     elif kernel == "manual":
         emb = rs.rand(T + 1, 9)
         fit.update(data_embed=emb[:T], target_embed=emb[T:], sizes=sizes)
+        fit.update(extra)
         arrays["embed"] = emb
     elif kernel == "multi":
         fit.update(sizes=sizes)
+        fit.update(extra)
+    else:
+        fit.update(extra)
     g = gp_regressor(kernel, **common)
     loss = g.maximise_likhd(theta, y, **fit)
     init = {k: tf1_shim.INIT_VALUES[id(v)] for k, v in g.net.params.items()}
@@ -107,7 +119,7 @@ def run_case(name):
     mean, std = g.predict_y(cand, compute_embed=True)
     out = dict(arrays)
     out.update(cand=cand, loss_log=np.asarray(g.sess.loss_log), final_loss=np.asarray(loss), pred_mean=mean, pred_std=std)
-    if kernel != "params":
+    if kernel != "params" and fit.get("algorithm", "GP") == "GP":
         out["similarity"] = np.asarray(g.similarity()[0])
     for k, v in init.items():
         out["init__" + k] = v
