@@ -1,7 +1,8 @@
 """CPU restatement of the distBO joint-GP hot path (TEST INFRASTRUCTURE ONLY).
 
-PARITY UNPINNED (see oracle/__init__.py): the reference ships no golden vectors and
-cannot run here; this file restates its TensorFlow-1.7 graph op-for-op.  All
+PARITY PIN (see oracle/__init__.py): the reference ships no golden vectors and TensorFlow 1.7 cannot
+run here; this file restates its TensorFlow-1.7 graph op-for-op and is checked against numbers the
+reference's own sources produce over a TF op shim (tests/golden/ref_*.npz, tests/test_reference_golden.py).  All
 ``file:line`` citations are relative to the reference repository (hcllaw/distBO).
 
 The same forward code runs on two array backends:

@@ -1,5 +1,6 @@
 """Oracle surrogate facade: CPU restatement of train/gp_regressor.py + train/train.py
-(TEST INFRASTRUCTURE ONLY; PARITY UNPINNED, see oracle/__init__.py).
+(TEST INFRASTRUCTURE ONLY; pinned by tests/test_reference_golden.py against the reference's own sources run over a
+TF op shim, see oracle/__init__.py).
 
 Same duck-typed interface as the reference ``gp_regressor`` so that the BO loop can be
 driven with either this class or the CUDA product and the trajectories compared.

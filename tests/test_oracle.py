@@ -1,5 +1,5 @@
-"""Pins for the CPU oracle (the reference ships no tests or golden vectors for this path and cannot
-run here: SURVEY 8c "parity unpinned").  Each restated function is checked against an INDEPENDENT
+"""Independent pins for the CPU oracle (the reference ships no tests or golden vectors for this path; the pin
+against the reference's own sources is tests/test_reference_golden.py).  Each restated function is checked against an INDEPENDENT
 implementation: sklearn's Matern(nu=1.5) (the cross-check the reference's author used,
 train/RandomFourierMaternFeatureMapper.py:69-82), sklearn's GaussianProcessRegressor, scipy's
 multivariate normal, mpmath at 50 digits, finite differences, and the closed-form toy optimum."""
