@@ -74,7 +74,35 @@ CASES = {
                                                     concat_data_size=True)),
     "blr_dist_class": ("dist", True, "joint", dict(algorithm="BLR", weight_dim=[30, 20], num_of_rff=0,
                                                    concat_data_size=True)),
+    # the reference's own data (subsets committed as tests/golden/protein_subset.npz / parkinson_subset.npz by
+    # tools/make_real_fixtures.py): MACCS fingerprints of ChEMBL targets, 166 bits, 2 classes (config 2) and
+    # per-patient Parkinson telemonitoring rows, 17 features (config 3)
+    "real_protein": ("dist", True, "joint", dict(concat_data_size=True, batch_size=100, stratify=False)),
+    "real_parkinson": ("dist", False, "joint", dict(concat_data_size=False)),
 }
+
+
+def real_tasks(name, rs, T, per_task, d):
+    gold = os.path.join(os.path.dirname(HERE), "tests", "golden")
+    if name == "real_protein":
+        z = np.load(os.path.join(gold, "protein_subset.npz"))
+        bits = np.unpackbits(z["bits"], axis=2)[:, :, :166].astype(np.float64)
+        # unequal dataset sizes, so that the size-ratio column (concat_data_size) carries a gradient
+        X = [bits[i][:360 - 23 * i] for i in range(T + 1)]
+        Y = [np.eye(2)[z["labels"][i].astype(int)][:360 - 23 * i] for i in range(T + 1)]
+    else:
+        from sklearn import preprocessing
+        z = np.load(os.path.join(gold, "parkinson_subset.npz"))
+        X, Y = [], []
+        for i in range(T + 1):
+            pat = z["patient_%d" % i]
+            X.append(preprocessing.scale(pat[:, :-2][:, 2:]))
+            yy = pat[:, -1:]
+            Y.append((yy - yy.min()) / (yy.max() - yy.min()))
+    sizes = [per_task] * T
+    theta = rs.uniform(-3, 3, size=(T * per_task, d))
+    y = np.sin(theta.sum(1)) + np.repeat(rs.randn(T) * 0.2, per_task) + 0.05 * rs.randn(T * per_task)
+    return theta, y[:, None], sizes, X, Y
 
 
 def run_case(name):
@@ -84,7 +112,10 @@ def run_case(name):
     rs = np.random.RandomState(abs(hash(name)) % 1000 if False else sum(map(ord, name)))
     d, T, per_task = 3, 4, 20
     dx, dy = (12, 2) if classification else (6, 1)
-    theta, y, sizes, X, Y = make_tasks(rs, T, per_task, d, dx, dy, 110, classification)
+    if name.startswith("real_"):
+        theta, y, sizes, X, Y = real_tasks(name, rs, T, per_task, d)
+    else:
+        theta, y, sizes, X, Y = make_tasks(rs, T, per_task, d, dx, dy, 110, classification)
     model_type = "classification" if classification else "regression"
     common = dict(model_type=model_type, seed=7, float64=True)
     fit = dict(learning_rate=0.005, max_epochs=8, likhd_var_init=1e-2, first_early_stop_epoch=3)
