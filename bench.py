@@ -294,11 +294,11 @@ def run_cuda(args):
     if rank == 0:
         # >= 20 untimed epochs (first eager, second captured as a CUDA graph, the rest replays) so that the
         # clocks have ramped, then >= 20 timed graph replays with no host synchronisation in between
-        gp.maximise_likhd(work["theta"], work["y"][:, None], **fit_kwargs(work, max(Wm, 20), args.lkh_var))
+        gp.maximise_likhd(work["theta"], work["y"][:, None], **fit_kwargs(work, max(Wm, args.fit_epochs), args.lkh_var))
         torch.cuda.synchronize()
         lib.distbo_launch_count(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kf = max(K, 20)
+        kf = max(K, args.fit_epochs)
         e0.record()
         for _ in range(kf):
             gp.run_epoch()
@@ -534,6 +534,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-blr", action="store_true", help="skip the secondary BLR-surrogate measurement")
+    ap.add_argument("--fit-epochs", type=int, default=20,
+                    help="untimed and timed fit epochs (default 20 + 20; the ncu launch-list command uses 1 so that the "
+                         "capture window reaches the scoring steps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

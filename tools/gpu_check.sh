@@ -9,7 +9,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; 
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "${SKIP_NCU:-0}" = "0" ]; then
-SMALL="python bench.py --candidates 75776 --steps 1 --warmup 1 --no-cpu-baseline --no-blr"
+SMALL="python bench.py --candidates 75776 --steps 1 --warmup 1 --no-cpu-baseline --no-blr --fit-epochs 1"
 $SMALL > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"

@@ -49,6 +49,13 @@ def launches(src, dst):
         f.write("%-72s %7s %12s %11s %7s\n" % ("kernel", "n", "total_us", "avg_us", "share"))
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("%-72s %7d %12.1f %11.1f %6.2f%%\n" % (k[:72], n, t, t / n, 100 * t / total))
+        # the bench's "step" is one acquisition pass: K_* generation, the contraction kernel, its finish and merge
+        step = {k: v for k, v in agg.items() if re.search(r"kst_kernel|score_kernel|score_finish_kernel|merge_best_kernel", k)}
+        if step:
+            st = sum(v[1] for v in step.values())
+            f.write("\n# kernels of the scoring step only (bench.py roofline.share_of_step is score_kernel's share of these)\n")
+            for k, (n, t) in sorted(step.items(), key=lambda kv: -kv[1][1]):
+                f.write("%-72s %7d %12.1f %11.1f %6.2f%%\n" % (k[:72], n, t, t / n, 100 * t / st))
 
 
 def report(src, dst):
