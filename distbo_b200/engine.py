@@ -250,6 +250,7 @@ class GPEngine:
         net = self.net
         Tn = seg_off.numel() - 1
         S = int(X.shape[0])
+        X, Y = X.contiguous(), Y.contiguous()     # the kernels read row-major [S, d] (no-op for the regressor's buffers)
         if out is None:
             out = torch.zeros(Tn, max(self.P, net.pooled_width), dtype=dtype, device=self.dev)
         p = self.params
@@ -285,6 +286,7 @@ class GPEngine:
         net, p = self.net, self.params
         Tn = seg_off.numel() - 1
         S = int(X.shape[0])
+        X, Y = X.contiguous(), Y.contiguous()
         ws = self._embed_workspace(S, Tn, 8, True)
         g = lambda name: _lib.ptr(p.gview(name)) if p.has(name) else None
         w = lambda name: _lib.ptr(p.view(name)) if p.has(name) else None

@@ -12,9 +12,9 @@ distbo_net.py, feature_map.py, base.py, gp_utils.py, and the BO driver bayes_opt
 model_embed/bayes_optimise.py, models.py) are imported unmodified from /root/reference and
 executed over ``tools/tf1_shim.py`` - a lazy TF-1.x op shim evaluated with torch CPU fp64 - by
 ``tools/make_reference_golden.py``.  The numbers they produce (loss per Adam epoch, fitted
-parameters, posterior mean / std, similarities for 16 kernel / operator / surrogate
-combinations, and 6 whole BO trajectories) are committed as ``tests/golden/ref_*.npz`` /
-``refbo_*.npz``; ``tests/test_reference_golden.py`` checks that this oracle reproduces them
+parameters, posterior mean / std, similarities for 18 kernel / operator / surrogate
+combinations, fp32 embeddings on the reference's own data, and 6 whole BO trajectories) are committed as ``tests/golden/ref_*.npz`` /
+``refembed_f32.npz`` / ``refbo_*.npz``; ``tests/test_reference_golden.py`` checks that this oracle reproduces them
 (1e-9; suggestions bit-equal) and that the CUDA path does (1e-8).  What the shim restates is
 the semantics of single TF ops, not the reference's algorithm; the TF runtime itself remains
 absent, which is the residual gap of this pin.  The restatement below follows the reference

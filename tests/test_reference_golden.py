@@ -165,3 +165,47 @@ def test_oracle_bo_trajectory_matches_reference(name):
 def test_cuda_bo_trajectory_matches_reference(cuda_engine_mod, name):
     from distbo_b200.train import gp_regressor
     run_bo(name, gp_regressor)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp32 embeddings computed by the reference's distbo_net in tf.float32 on the reference's own data (subsets):
+# tests/golden/refembed_f32.npz.  north_star: embeddings within 1e-5 relative (fp32).
+EMBED_CASES = {"protein_class": ("joint", "classification", 2), "parkinson_none": ("none", "regression", 0),
+               "parkinson_joint": ("joint", "regression", 1)}
+
+
+def load_embed(tag):
+    z = np.load(os.path.join(GOLD, "refembed_f32.npz"))
+    w = {k[len(tag) + 2:]: z[k] for k in z.files if k.startswith(tag + "__weights") or k.startswith(tag + "__bias")}
+    return z[tag + "__X"], z[tag + "__Y"], [int(v) for v in z[tag + "__sizes"]], w, z[tag + "__E"]
+
+
+@pytest.mark.parametrize("tag", sorted(EMBED_CASES))
+def test_oracle_embedding_matches_reference_fp32(tag):
+    from oracle import gp_oracle as O
+    X, Y, sizes, w, E = load_embed(tag)
+    embed_op, model_type, _ = EMBED_CASES[tag]
+    p = {k: v.astype(np.float64) for k, v in w.items()}
+    got = O.distbo_net(O.NP, X.astype(np.float64), Y.astype(np.float64), sizes, p, embed_op=embed_op, model_type=model_type)
+    assert got.shape == E.shape
+    assert rel(got, E) < 1e-5          # fp64 evaluation of the same fp32 inputs vs the reference's fp32 arithmetic
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted(EMBED_CASES))
+def test_cuda_fp32_embedding_matches_reference(cuda_engine_mod, tag):
+    import torch
+    eng = cuda_engine_mod
+    X, Y, sizes, w, E = load_embed(tag)
+    embed_op, model_type, y_mode = EMBED_CASES[tag]
+    dx, dy = X.shape[1], Y.shape[1]
+    net = eng.NetSpec(dx, dy, 20, 10, 20 if y_mode == 1 else 0, 10 if y_mode == 1 else 0, y_mode)
+    e = eng.GPEngine(2, n_embed=net.pooled_width, net=net)
+    for k, v in w.items():
+        e.params.set(k, v.astype(np.float64))
+    off = torch.from_numpy(np.r_[0, np.cumsum(sizes)].astype(np.int32)).to(e.dev)
+    on_tc = eng._lib.load().distbo_embed_f32_on_tensor_cores(dx, dy, 20, 10, 0, y_mode)
+    assert on_tc == (0 if y_mode == 1 else 1)      # fingerprints / 'none' pooling: the bulk-copy + TF32 tensor-core kernel
+    got = e.embed(torch.from_numpy(X).to(e.dev), torch.from_numpy(Y).to(e.dev), off, dtype=torch.float32)
+    got = got.double().cpu().numpy()[:, :E.shape[1]]
+    assert rel(got, E) < 1e-5

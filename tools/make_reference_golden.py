@@ -279,3 +279,66 @@ def run_bo_case(name):
 if __name__ == "__main__":
     for name in BO_CASES:
         run_bo_case(name)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp32 embeddings: the reference's distbo_net / nn_net / sparse_joint_op (train/distbo_net.py, base.py) evaluated in
+# tf.float32, the arithmetic type of its CLI default (train_test.py:87) and of north_star's embedding tolerance
+# (1e-5 relative).  Inputs: the committed subsets of the reference's own data.
+def run_embed_f32():
+    from distBO.train.distbo_net import distbo_net
+    from distBO.train.base import sum_matrix as ref_sum_matrix
+    gold = os.path.join(os.path.dirname(HERE), "tests", "golden")
+    rs = np.random.RandomState(11)
+    out = {}
+
+    def weights(din, h, p, name):
+        return {"weights_%s_1" % name: (rs.randn(din, h) * np.sqrt(2.0 / (din + h))).astype(np.float32),
+                "bias_%s_1" % name: (rs.randn(h) * 0.1).astype(np.float32),
+                "weights_%s_2" % name: (rs.randn(h, p) * np.sqrt(2.0 / (h + p))).astype(np.float32)}
+
+    def embed(tag, X, Y, sizes, w, embed_op, model_type):
+        tf.reset_default_graph()
+        params = {k: tf.constant(v, dtype=tf.float32) for k, v in w.items()}
+        sm = ref_sum_matrix(None, np.asarray(sizes).reshape(-1, 1))
+        sm_t = type(sm)(indices=tf.constant(sm.indices, dtype=tf.int64), values=tf.constant(sm.values, dtype=tf.float32),
+                        dense_shape=tf.constant(sm.dense_shape, dtype=tf.int64))
+        E = distbo_net(tf.constant(X, dtype=tf.float32), tf.constant(Y, dtype=tf.float32),
+                       tf.constant(np.asarray(sizes, dtype=np.float32).reshape(-1, 1), dtype=tf.float32), params,
+                       embed_op=embed_op, model_type=model_type, sum_matrix=sm_t, dtype=tf.float32)
+        e = tf.Session().run(E)
+        assert e.dtype == np.float32
+        out[tag + "__E"] = e
+        out[tag + "__X"] = np.ascontiguousarray(X, dtype=np.float32)
+        out[tag + "__Y"] = np.ascontiguousarray(Y, dtype=np.float32)
+        out[tag + "__sizes"] = np.asarray(sizes)
+        for k, v in w.items():
+            out[tag + "__" + k] = v
+        print("%-28s E %s  |E|max %.6f" % (tag, e.shape, np.abs(e).max()))
+
+    z = np.load(os.path.join(gold, "protein_subset.npz"))
+    bits = np.unpackbits(z["bits"], axis=2)[:, :, :166].astype(np.float32)
+    sizes = [360 - 37 * i for i in range(7)]            # ragged: 360, 323, ..., 138 rows
+    X = np.vstack([bits[i][:n] for i, n in enumerate(sizes)])
+    Y = np.vstack([np.eye(2, dtype=np.float32)[z["labels"][i].astype(int)][:n] for i, n in enumerate(sizes)])
+    embed("protein_class", X, Y, sizes, weights(166, 20, 10, "x"), "joint", "classification")
+
+    from sklearn import preprocessing
+    zp = np.load(os.path.join(gold, "parkinson_subset.npz"))
+    Xs, Ys = [], []
+    for i in range(10):
+        pat = zp["patient_%d" % i]
+        Xs.append(preprocessing.scale(pat[:, :-2][:, 2:]).astype(np.float32))
+        yy = pat[:, -1:]
+        Ys.append(((yy - yy.min()) / (yy.max() - yy.min())).astype(np.float32))
+    sizes = [len(x) for x in Xs]
+    w = weights(17, 20, 10, "x")
+    embed("parkinson_none", np.vstack(Xs), np.vstack(Ys), sizes, w, "none", "regression")
+    w2 = dict(w)
+    w2.update(weights(1, 20, 10, "y"))
+    embed("parkinson_joint", np.vstack(Xs), np.vstack(Ys), sizes, w2, "joint", "regression")
+    np.savez_compressed(os.path.join(OUT, "refembed_f32.npz"), **out)
+
+
+if __name__ == "__main__":
+    run_embed_f32()
