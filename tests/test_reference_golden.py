@@ -209,3 +209,31 @@ def test_cuda_fp32_embedding_matches_reference(cuda_engine_mod, tag):
     got = e.embed(torch.from_numpy(X).to(e.dev), torch.from_numpy(Y).to(e.dev), off, dtype=torch.float32)
     got = got.double().cpu().numpy()[:, :E.shape[1]]
     assert rel(got, E) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# acquisition values from the reference's UtilityFunction (bayes_opt/helpers.py:114-177): tests/golden/refacq.npz
+def test_acquisition_functions_match_reference():
+    from oracle import gp_oracle as O
+    from distbo_b200.bayes_opt.helpers import UtilityFunction
+    z = np.load(os.path.join(GOLD, "refacq.npz"))
+    mean, std = z["mean"], z["std"]
+    y_max, xi, kappa = float(z["y_max"]), float(z["xi"]), float(z["kappa"])
+    assert np.allclose(np.reshape(O.acq_ei(mean, std, y_max, xi), -1), z["ei"], rtol=1e-12, atol=1e-300)
+    assert np.allclose(np.reshape(O.acq_ucb(mean, std, kappa), -1), z["ucb"], rtol=1e-14)
+    assert np.allclose(np.reshape(O.acq_lcb(mean, std, kappa), -1), z["lcb"], rtol=1e-14)
+
+    class StubGP(object):                       # duck-typed surrogate without the fused device path
+        def predict_y(self, x_, **kw):
+            return mean[:len(x_)], std[:len(x_)]
+    x = np.zeros((len(mean), 2))
+    for kind in ("ei", "ucb", "lcb", "poi"):
+        got = UtilityFunction(kind=kind, kappa=kappa, xi=xi).utility(x, StubGP(), y_max)
+        assert np.allclose(np.reshape(got, -1), z[kind], rtol=1e-12, atol=1e-300), kind
+        v, i = UtilityFunction(kind=kind, kappa=kappa, xi=xi).argmax(x, StubGP(), y_max)
+        assert i == int(np.argmax(z[kind])) and v == pytest.approx(float(np.max(z[kind])), rel=1e-12)
+
+
+def test_early_stopping_epoch_matches_reference():
+    z = np.load(os.path.join(GOLD, "ref_params_early_stop.npz"))
+    assert 100 < len(z["loss_log"]) < 140      # the reference's run stopped on its countdown, not on max_epochs

@@ -56,6 +56,9 @@ def make_tasks(rs, T, per_task, d, dx, dy, rows, classification):
 CASES = {
     # name: (kernel, classification, embed_op, extra fit kwargs)
     "params": ("params", False, None, {}),
+    # early stopping (train/train.py:53-65): with a tiny learning rate no epoch improves the loss by 1e-4, so the
+    # countdown set at first_early_stop_epoch runs out after 100 more epochs, well before max_epochs
+    "params_early_stop": ("params", False, None, dict(learning_rate=1e-9, max_epochs=140, first_early_stop_epoch=5)),
     "manual": ("manual", False, None, {}),
     "multi": ("multi", False, None, {}),
     "dist_none": ("dist", False, "none", dict(concat_data_size=False)),
@@ -342,3 +345,29 @@ def run_embed_f32():
 
 if __name__ == "__main__":
     run_embed_f32()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# acquisition functions: the reference's UtilityFunction (bayes_opt/helpers.py:114-177) on fixed (mean, std) pairs
+def run_acquisition():
+    from distBO.bayes_opt.helpers import UtilityFunction
+    rs = np.random.RandomState(3)
+    M = 400
+    mean = rs.randn(M, 1) * 0.7
+    std = np.abs(rs.randn(M, 1)) * 0.5 + 1e-3
+    std[:5] = 1e-16                                        # the clamped-variance regime (gp_regressor.py:197)
+    x = rs.rand(M, 2)
+
+    class StubGP(object):
+        def predict_y(self, x_, **kw):
+            return mean[:len(x_)], std[:len(x_)]
+    out = {"mean": mean, "std": std, "y_max": np.asarray(0.4), "xi": np.asarray(0.01), "kappa": np.asarray(2.58)}
+    for kind in ("ei", "ucb", "lcb", "poi"):
+        u = UtilityFunction(kind=kind, kappa=2.58, xi=0.01)
+        out[kind] = np.asarray(u.utility(x, StubGP(), 0.4), dtype=np.float64).reshape(-1)
+        print("%-8s max %.8f argmax %d" % (kind, out[kind].max(), int(out[kind].argmax())))
+    np.savez_compressed(os.path.join(OUT, "refacq.npz"), **out)
+
+
+if __name__ == "__main__":
+    run_acquisition()
