@@ -381,6 +381,78 @@ def test_embed_forward_tensor_core(cuda_engine_mod, case, monkeypatch):
     assert np.array_equal(got, again)
 
 
+@pytest.mark.parametrize("mode", ["joint", "class", "concat"])
+def test_embed_three_layer_x_net_with_y_side(cuda_engine_mod, mode):
+    """x net of three layers (nn_net's weights_3 branch, distbo_net.py:11-13) under the poolings that have a y side:
+    forward (fp64, fp32) and the closed-form backward against torch autograd through the oracle."""
+    eng = cuda_engine_mod
+    rs = np.random.RandomState(31)
+    sizes = [150, 64, 77, 1, 200]
+    S = sum(sizes)
+    if mode == "class":
+        dx, dy, y_mode, model_type, embed_op = 16, 2, 2, "classification", "joint"
+        X = (rs.rand(S, dx) < 0.3).astype(np.float64)
+        Y = np.eye(2)[(rs.rand(S) < 0.3).astype(int)]
+    else:
+        dx, dy, model_type = 9, 1, "regression"
+        y_mode, embed_op = {"joint": (1, "joint"), "concat": (3, "concat")}[mode]
+        X = rs.randn(S, dx)
+        Y = rs.rand(S, dy)
+    net = eng.NetSpec(dx, dy, 20, 10, 20 if y_mode in (1, 3) else 0, 10 if y_mode in (1, 3) else 0, y_mode, pm=12)
+    e = eng.GPEngine(2, n_embed=net.pooled_width, net=net)
+    p = O.build_params(2, "dist", in_dim_x=dx, in_dim_y=dy, weight_dim_x=[20, 12, 10], weight_dim_y=[20, 10],
+                       model_type=model_type, embed_op=embed_op, seed=8)
+    p["bias_x_1"] = rs.randn(20) * 0.1
+    p["bias_x_2"] = rs.randn(12) * 0.1
+    if "log_reg" in p:
+        p["log_reg"] = np.asarray(0.3)
+    for k, v in p.items():
+        if e.params.has(k) and k.startswith(("weights", "bias", "log_reg")):
+            e.params.set(k, v)
+    off = torch.from_numpy(np.r_[0, np.cumsum(sizes)].astype(np.int32)).to(e.dev)
+    want = O.distbo_net(O.NP, X, Y, sizes, p, embed_op=embed_op, model_type=model_type)
+    Xd, Yd = torch.from_numpy(X).to(e.dev), torch.from_numpy(Y).to(e.dev)
+    got32 = e.embed(Xd.float(), Yd.float(), off, dtype=torch.float32).double().cpu().numpy()[:, :want.shape[1]]
+    assert rel(got32, want) < 1e-5
+    got = e.embed(Xd, Yd, off).cpu().numpy()[:, :want.shape[1]]       # fp64 last: its per-dataset sums feed the backward
+    assert rel(got, want) < (1e-10 if mode == "concat" else 1e-12)
+    dE = rs.randn(len(sizes), net.pooled_width)
+    e.embed_backward(Xd, Yd, off, torch.from_numpy(dE).to(e.dev))
+    tp = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=True) for k, v in p.items()}
+    out = O.distbo_net(O.TH(), torch.from_numpy(X), torch.from_numpy(Y), sizes, tp, embed_op=embed_op, model_type=model_type)
+    (out * torch.from_numpy(dE)).sum().backward()
+    n = 0
+    for name in e.params.offsets:
+        if name.startswith(("weights", "bias", "log_reg")):
+            assert rel(e.params.get_grad(name), tp[name].grad.numpy()) < 1e-10, name
+            n += 1
+    assert n == {"joint": 8, "class": 5, "concat": 9}[mode]
+
+
+@pytest.mark.parametrize("T,dtype", [(2100, "f64"), (2100, "f32"), (1, "f32"), (1, "f64")])
+def test_embed_many_tiny_datasets_and_single_dataset(cuda_engine_mod, T, dtype):
+    """Chunk table beyond its shared-memory scan (T > 2048: serial fill path) and the degenerate single short dataset
+    (one partial chunk); fp32 goes through the tensor-core kernel."""
+    eng = cuda_engine_mod
+    rs = np.random.RandomState(T)
+    sizes = list(rs.randint(1, 4, size=T)) if T > 1 else [5]
+    S = int(sum(sizes))
+    dx = 5
+    X, Y = rs.randn(S, dx), rs.rand(S, 1)
+    net = eng.NetSpec(dx, 1, 20, 10, 0, 0, 0)
+    e = eng.GPEngine(2, n_embed=net.pooled_width, net=net)
+    p = O.build_params(2, "dist", in_dim_x=dx, in_dim_y=1, weight_dim_x=[20, 10], weight_dim_y=[20, 10],
+                       model_type="regression", embed_op="none", seed=3)
+    for k, v in p.items():
+        if e.params.has(k) and k.startswith(("weights", "bias")):
+            e.params.set(k, v)
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    off = torch.from_numpy(np.r_[0, np.cumsum(sizes)].astype(np.int32)).to(e.dev)
+    got = e.embed(torch.from_numpy(X).to(e.dev).to(tdt), torch.from_numpy(Y).to(e.dev).to(tdt), off, dtype=tdt)
+    want = O.distbo_net(O.NP, X, Y, sizes, p, embed_op="none", model_type="regression")
+    assert rel(got.double().cpu().numpy()[:, :10], want) < (1e-12 if dtype == "f64" else 1e-5)
+
+
 @pytest.mark.parametrize("mode", ["none", "joint", "class", "concat"])
 def test_embed_backward(cuda_engine_mod, mode):
     eng = cuda_engine_mod
