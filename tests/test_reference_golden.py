@@ -237,3 +237,36 @@ def test_acquisition_functions_match_reference():
 def test_early_stopping_epoch_matches_reference():
     z = np.load(os.path.join(GOLD, "ref_params_early_stop.npz"))
     assert 100 < len(z["loss_log"]) < 140      # the reference's run stopped on its countdown, not on max_epochs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# manual meta-features from the reference's model_embed/meta_fea.py meta(): tests/golden/refmeta.npz
+@pytest.mark.parametrize("tag", ["protein", "parkinson"])
+def test_manual_meta_features_match_reference(tag):
+    import warnings
+    from sklearn.utils import check_random_state
+    from distbo_b200.data.load_datasets import parkinson_tasks, protein_tasks
+    from distbo_b200.model_embed.meta_fea import meta
+    z = np.load(os.path.join(GOLD, "refmeta.npz"))
+    if tag == "protein":
+        zz = np.load(os.path.join(GOLD, "protein_subset.npz"))
+        bits = np.unpackbits(zz["bits"], axis=2)[:, :, :166].astype(np.float64)
+        tables = [np.hstack([np.zeros((bits.shape[1], 1)), bits[i], zz["labels"][i][:, None].astype(np.float64)])
+                  for i in range(bits.shape[0])]
+        t, s, _ = protein_tasks(tables, [str(n) for n in zz["names"]], target=2, random_state=check_random_state(3),
+                                test_size=0.4)
+        model = "forest"
+    else:
+        zz = np.load(os.path.join(GOLD, "parkinson_subset.npz"))
+        t, s, _ = parkinson_tasks([zz["patient_%d" % i] for i in range(10)], target=4,
+                                  random_state=check_random_state(1), test_size=0.4)
+        model = "ridge"
+    dsets = [t] + s
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # constant fingerprint bits give NaN skewness, as in the reference
+        scaler = meta(dsets, model, max_size=max(len(d.train_x) for d in dsets), random_state=5)
+    got = np.asarray([d.embed for d in dsets])
+    assert got.shape == z[tag].shape
+    assert np.allclose(got, z[tag], rtol=1e-10, atol=1e-12, equal_nan=True)
+    assert np.allclose(scaler.data_min_, z[tag + "__data_min"], rtol=1e-10, atol=1e-12, equal_nan=True)
+    assert np.allclose(scaler.data_max_, z[tag + "__data_max"], rtol=1e-10, atol=1e-12, equal_nan=True)

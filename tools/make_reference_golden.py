@@ -371,3 +371,45 @@ def run_acquisition():
 
 if __name__ == "__main__":
     run_acquisition()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# manual meta-features: the reference's model_embed/meta_fea.py meta() on datasets built from the committed subsets
+# of its own data (sklearn.datasets.load_boston, imported but unused by that module, no longer exists: stubbed).
+def meta_datasets():
+    sys.path.insert(0, os.path.dirname(HERE))
+    from sklearn.utils import check_random_state
+    from distbo_b200.data.load_datasets import parkinson_tasks, protein_tasks
+    gold = os.path.join(os.path.dirname(HERE), "tests", "golden")
+    z = np.load(os.path.join(gold, "protein_subset.npz"))
+    bits = np.unpackbits(z["bits"], axis=2)[:, :, :166].astype(np.float64)
+    tables = [np.hstack([np.zeros((bits.shape[1], 1)), bits[i], z["labels"][i][:, None].astype(np.float64)])
+              for i in range(bits.shape[0])]
+    pt, ps, _ = protein_tasks(tables, [str(n) for n in z["names"]], target=2, random_state=check_random_state(3),
+                              test_size=0.4)
+    zp = np.load(os.path.join(gold, "parkinson_subset.npz"))
+    kt, ks, _ = parkinson_tasks([zp["patient_%d" % i] for i in range(10)], target=4,
+                                random_state=check_random_state(1), test_size=0.4)
+    return {"protein": ([pt] + ps, "forest"), "parkinson": ([kt] + ks, "ridge")}
+
+
+def run_meta_features():
+    import sklearn.datasets
+    sklearn.datasets.__dict__.setdefault("load_boston", lambda *a, **k: None)   # removed in scikit-learn 1.2
+    from distBO.model_embed.meta_fea import meta as ref_meta
+    import contextlib
+    import io
+    out = {}
+    for tag, (dsets, model) in meta_datasets().items():
+        max_size = max(len(d.train_x) for d in dsets)
+        with contextlib.redirect_stdout(io.StringIO()):
+            scaler = ref_meta(dsets, model, max_size=max_size, random_state=5)
+        out[tag] = np.asarray([d.embed for d in dsets])
+        out[tag + "__data_min"] = scaler.data_min_
+        out[tag + "__data_max"] = scaler.data_max_
+        print("%-12s meta-features %s" % (tag, out[tag].shape))
+    np.savez_compressed(os.path.join(OUT, "refmeta.npz"), **out)
+
+
+if __name__ == "__main__":
+    run_meta_features()
