@@ -270,3 +270,41 @@ def test_manual_meta_features_match_reference(tag):
     assert np.allclose(got, z[tag], rtol=1e-10, atol=1e-12, equal_nan=True)
     assert np.allclose(scaler.data_min_, z[tag + "__data_min"], rtol=1e-10, atol=1e-12, equal_nan=True)
     assert np.allclose(scaler.data_max_, z[tag + "__data_max"], rtol=1e-10, atol=1e-12, equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# data loaders and the train/test container vs the reference's own (tests/golden/refdata.npz holds digests)
+def _digest(d):
+    return {"shape": np.asarray(d.train_x.shape + d.test_x.shape), "colsum": d.train_x.sum(0), "ysum": d.train_y.sum(0),
+            "test_colsum": d.test_x.sum(0), "row0": d.train_x[0], "embed_ind": np.asarray(list(d.embed_ind))[:64],
+            "n_embed": np.asarray(len(list(d.embed_ind)))}
+
+
+def test_train_test_container_matches_reference():
+    from sklearn.utils import check_random_state
+    from distbo_b200.data.data import data
+    z = np.load(os.path.join(GOLD, "refdata.npz"))
+    x, yr, yc = z["container__x"], z["container__yr"], z["container__yc"]
+    d1 = data(x[:200], x[200:], yr[:200], yr[200:], embed_size=50, random_state=check_random_state(9))
+    d2 = data(x[:200], x[200:], yc[:200, None], yc[200:, None], embed_size=50, random_state=check_random_state(9),
+              prob_type='classification')
+    assert np.array_equal(np.asarray(list(d1.embed_ind)), z["container__reg_embed_ind"])
+    assert np.array_equal(np.asarray(list(d2.embed_ind)), z["container__cls_embed_ind"])
+    assert np.array_equal(d2.train_y, z["container__cls_train_y"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/protein"), reason="the reference's data folders exist only in the build container")
+@pytest.mark.parametrize("tag", ["protein", "parkinson"])
+def test_loaders_match_reference_on_its_data_folders(tag):
+    from sklearn.utils import check_random_state
+    from distbo_b200.data.load_datasets import load_parkinson, load_protein
+    z = np.load(os.path.join(GOLD, "refdata.npz"))
+    if tag == "protein":
+        t, s, names = load_protein(2, "/root/reference/protein", random_state=check_random_state(3), test_size=0.4)
+    else:
+        t, s, names = load_parkinson(4, "/root/reference/parkinson", random_state=check_random_state(1), test_size=0.4)
+    assert [str(n) for n in names] == [str(n) for n in z[tag + "__names"]]
+    for i, d in enumerate([t] + s):
+        for k, v in _digest(d).items():
+            want = z["%s__%d__%s" % (tag, i, k)]
+            assert np.allclose(v, want, rtol=1e-13, atol=1e-13), (tag, i, k)

@@ -413,3 +413,48 @@ def run_meta_features():
 
 if __name__ == "__main__":
     run_meta_features()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# data loaders and the train/test container: the reference's data/load_datasets.py load_protein / load_parkinson and
+# data/data.py data (py2 `range(...).remove` at load_datasets.py:42-43,82-83 -> the module gets a list-returning range)
+def _digest(d):
+    return {"shape": np.asarray(d.train_x.shape + d.test_x.shape), "colsum": d.train_x.sum(0), "ysum": d.train_y.sum(0),
+            "test_colsum": d.test_x.sum(0), "row0": d.train_x[0], "embed_ind": np.asarray(list(d.embed_ind))[:64],
+            "n_embed": np.asarray(len(list(d.embed_ind)))}
+
+
+def run_loaders():
+    import builtins
+    import contextlib
+    import io
+    from sklearn.utils import check_random_state
+    import distBO.data.load_datasets as ref_ld
+    from distBO.data.data import data as ref_data
+    ref_ld.range = lambda *a: list(builtins.range(*a))
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        pt, ps, pn = ref_ld.load_protein(2, random_state=check_random_state(3), test_size=0.4)
+        kt, ks, kn = ref_ld.load_parkinson(4, random_state=check_random_state(1), test_size=0.4)
+    for tag, dsets, names in (("protein", [pt] + ps, pn), ("parkinson", [kt] + ks, kn)):
+        out[tag + "__names"] = np.asarray([str(n) for n in names])
+        for i, d in enumerate(dsets):
+            for k, v in _digest(d).items():
+                out["%s__%d__%s" % (tag, i, k)] = v
+        print("%-10s %d datasets, target %s" % (tag, len(dsets), names[0]))
+    # embed_ind subsampling of the container (data.py:40-62): regression and class-proportional classification
+    rs = np.random.RandomState(0)
+    x, yr = rs.randn(300, 4), rs.rand(300)
+    yc = (rs.rand(300) < 0.3).astype(float)
+    d1 = ref_data(x[:200], x[200:], yr[:200], yr[200:], embed_size=50, random_state=check_random_state(9))
+    d2 = ref_data(x[:200], x[200:], yc[:200, None], yc[200:, None], embed_size=50, random_state=check_random_state(9),
+                  prob_type='classification')
+    out["container__x"], out["container__yr"], out["container__yc"] = x, yr, yc
+    out["container__reg_embed_ind"] = np.asarray(list(d1.embed_ind))
+    out["container__cls_embed_ind"] = np.asarray(list(d2.embed_ind))
+    out["container__cls_train_y"] = d2.train_y
+    np.savez_compressed(os.path.join(OUT, "refdata.npz"), **out)
+
+
+if __name__ == "__main__":
+    run_loaders()
