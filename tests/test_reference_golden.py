@@ -308,3 +308,17 @@ def test_loaders_match_reference_on_its_data_folders(tag):
         for k, v in _digest(d).items():
             want = z["%s__%d__%s" % (tag, i, k)]
             assert np.allclose(v, want, rtol=1e-13, atol=1e-13), (tag, i, k)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# toy task family (config 1) from the reference's generate_data / one_d_split: tests/golden/reftoy.npz
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_toy_tasks_match_reference(tag):
+    from distbo_b200.data.toy_datasets import one_dim_split_tasks
+    z = np.load(os.path.join(GOLD, "reftoy.npz"))
+    seed, fake, true, n = (int(v) for v in z[tag + "__cfg"])
+    target, sources, supp = one_dim_split_tasks(seed, fake, true, n_train=n, n_test=n)
+    assert np.array_equal(np.asarray(supp, dtype=np.float64), z[tag + "__supp"])
+    for i, d in enumerate([target] + sources):
+        assert np.array_equal(d.train_x, z["%s__%d__train_x" % (tag, i)])
+        assert float(d.test_x.sum()) == float(z["%s__%d__test_sum" % (tag, i)])

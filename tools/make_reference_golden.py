@@ -458,3 +458,34 @@ def run_loaders():
 
 if __name__ == "__main__":
     run_loaders()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# toy task family of config 1: the reference's data/generate_data.py generate_data (dataset 'one_dim_split') and
+# toy_datasets.one_d_split (its import of sklearn.cluster.k_means_._init_centroids, unused here, is stubbed)
+def run_toy_tasks():
+    import types as _types
+    import sklearn.datasets
+    sklearn.datasets.__dict__.setdefault("load_boston", lambda *a, **k: None)
+    km = _types.ModuleType("sklearn.cluster.k_means_")
+    km._init_centroids = None
+    sys.modules.setdefault("sklearn.cluster.k_means_", km)
+    from distBO.data.generate_data import generate_data
+    out = {}
+    for tag, (seed, fake, true, n) in {"a": (0, 3, 2, 120), "b": (7, 12, 3, 500)}.items():
+        args = _types.SimpleNamespace(dataset='one_dim_split', data_seed=seed, dim=None, preprocess='standardise',
+                                      max_embed_size=10000, n_train=n, n_test=n, fake_source_num=fake,
+                                      true_source_num=true, mu_sd=1.0)
+        res = generate_data(args)
+        target, sources, supp = res[0], res[1], res[2]
+        out[tag + "__cfg"] = np.asarray([seed, fake, true, n])
+        out[tag + "__supp"] = np.asarray(supp, dtype=np.float64)
+        for i, d in enumerate([target] + list(sources)):
+            out["%s__%d__train_x" % (tag, i)] = d.train_x
+            out["%s__%d__test_sum" % (tag, i)] = np.asarray(d.test_x.sum())
+        print("toy %s: %d sources, mu_target %.6f" % (tag, len(sources), supp[0]))
+    np.savez_compressed(os.path.join(OUT, "reftoy.npz"), **out)
+
+
+if __name__ == "__main__":
+    run_toy_tasks()
