@@ -322,3 +322,58 @@ def test_toy_tasks_match_reference(tag):
     for i, d in enumerate([target] + sources):
         assert np.array_equal(d.train_x, z["%s__%d__train_x" % (tag, i)])
         assert float(d.test_x.sum()) == float(z["%s__%d__test_sum" % (tag, i)])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BO trajectory at the Parkinson configuration through the reference's driver and ridge objective:
+# tests/golden/refpark_bo_ridge.npz (joint embedding of 17-feature patient datasets, P = 100)
+def run_bo_parkinson(make_regressor):
+    from sklearn.utils import check_random_state
+    from distbo_b200.data.load_datasets import parkinson_tasks
+    from distbo_b200.model_embed import bayes_opt_wrap
+    z = np.load(os.path.join(GOLD, "refpark_bo_ridge.npz"))
+    zp = np.load(os.path.join(GOLD, "parkinson_subset.npz"))
+    target, sources, _ = parkinson_tasks([zp["patient_%d" % i] for i in range(10)], target=4,
+                                         random_state=check_random_state(1), test_size=0.4)
+    sources = sources[:5]
+    init = {k[len("init__"):]: z[k] for k in z.files if k.startswith("init__")}
+    init_list = [z["init_list%d" % i].copy() for i in range(len(sources))]
+
+    def factory(kernel, **kw):
+        reg = make_regressor(kernel, **kw)
+        reg.initial_weights = init
+        return reg
+    cfg = bo_optim_config(embed_op='joint', n_warmup=5000, n_epochs=20, stratify=False, batch_size=1000)
+    traj, _ = bayes_opt_wrap('dist', target, acq='ei', model='ridge', rs=np.random.RandomState(11), optim_config=cfg,
+                             xi=0.01, kappa=2.58, bo_it=4, rand_it=0, init_list=init_list, include_init=False,
+                             source_data=sources, gp_class=factory, verbose=0, acq_one_shot='ei')
+    want = z["trajectory"]
+    assert traj.shape == want.shape == (4, 3)
+    assert np.array_equal(traj[:, :2], want[:, :2]), (traj, want)          # identical suggestions
+    assert np.allclose(traj[:, 2], want[:, 2], rtol=1e-12)                 # the ridge objective's R^2 at them
+
+
+def test_init_list_of_parkinson_run_is_the_reference_ridge_objective():
+    """The stored previous evaluations were produced by the reference's own ridge objective: ours returns the same."""
+    from sklearn.utils import check_random_state
+    from distbo_b200.data.load_datasets import parkinson_tasks
+    from distbo_b200.model_embed import set_model
+    z = np.load(os.path.join(GOLD, "refpark_bo_ridge.npz"))
+    zp = np.load(os.path.join(GOLD, "parkinson_subset.npz"))
+    _, sources, _ = parkinson_tasks([zp["patient_%d" % i] for i in range(10)], target=4,
+                                    random_state=check_random_state(1), test_size=0.4)
+    for i, s in enumerate(sources[:5]):
+        f, bounds, _, _ = set_model('ridge', s, None)
+        rows = z["init_list%d" % i]
+        for la, lg, val in rows[:3]:
+            assert f(log_alpha=la, log_gamma=lg) == pytest.approx(val, rel=1e-10)
+
+
+def test_oracle_parkinson_bo_trajectory_matches_reference():
+    run_bo_parkinson(OracleGPRegressor)
+
+
+@pytest.mark.gpu
+def test_cuda_parkinson_bo_trajectory_matches_reference(cuda_engine_mod):
+    from distbo_b200.train import gp_regressor
+    run_bo_parkinson(gp_regressor)

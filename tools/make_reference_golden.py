@@ -489,3 +489,74 @@ def run_toy_tasks():
 
 if __name__ == "__main__":
     run_toy_tasks()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BO trajectory at the Parkinson configuration (config 3): the reference's driver and its own ridge objective
+# (model_embed/models.py ridge: 200 random Fourier features under np.random.seed(23)) on the committed subset of its
+# patient files, joint embedding (17 features x 1 label -> P = 100).
+def run_bo_parkinson():
+    import distBO.train.gp_regressor as ref_gp
+    import distBO.model_embed.bayes_optimise as ref_bo_mod
+    from distBO.model_embed.models import set_model as ref_set_model
+    from sklearn.utils import check_random_state
+    sys.path.insert(0, os.path.dirname(HERE))
+    from distbo_b200.data.load_datasets import parkinson_tasks
+    tf.reset_default_graph()
+    tf1_shim._EAGER_SEED[0] = 0
+    zp = np.load(os.path.join(os.path.dirname(HERE), "tests", "golden", "parkinson_subset.npz"))
+    target, sources, _ = parkinson_tasks([zp["patient_%d" % i] for i in range(10)], target=4,
+                                         random_state=check_random_state(1), test_size=0.4)
+    sources = sources[:5]
+    rs = np.random.RandomState(6)
+    init_list = []
+    for s_ in sources:                                   # 6 random-search evaluations per source patient
+        f, bounds, _, _ = ref_set_model('ridge', s_, None)
+        names = sorted(bounds)
+        rows = []
+        for _ in range(6):
+            th = {k: rs.uniform(*bounds[k]) for k in names}
+            rows.append([th[k] for k in names] + [f(**th)])
+        init_list.append(np.array(rows))
+    inits = []
+    orig_close = ref_gp.gp_regressor.close
+
+    def recording_close(self):
+        inits.append({k: tf1_shim.INIT_VALUES[id(v)] for k, v in self.net.params.items()})
+        return orig_close(self)
+    ref_gp.gp_regressor.close = recording_close
+
+    class _NumpyCompat(object):
+        def __getattr__(self, k):
+            return getattr(np, k)
+
+        @staticmethod
+        def array(obj, *a, **kw):
+            try:
+                return np.array(obj, *a, **kw)
+            except ValueError:
+                out = np.empty(len(obj), dtype=object)
+                for i, v in enumerate(obj):
+                    out[i] = v
+                return out
+    ref_bo_mod.np = _NumpyCompat()
+    cfg = bo_optim_config(embed_op='joint', n_warmup=5000, n_epochs=20, stratify=False, batch_size=1000)
+    try:
+        traj, sim = ref_bo_mod.bayes_opt_wrap('dist', target, acq='ei', model='ridge', rs=np.random.RandomState(11),
+                                              optim_config=cfg, xi=0.01, kappa=2.58, bo_it=4, rand_it=0,
+                                              init_list=[a.copy() for a in init_list], include_init=False,
+                                              source_data=sources, acq_one_shot='ei')
+    finally:
+        ref_gp.gp_regressor.close = orig_close
+        ref_bo_mod.np = np
+    arrays = {"trajectory": np.asarray(traj, dtype=np.float64)}
+    for k, v in inits[0].items():
+        arrays["init__" + k] = v
+    for i, a in enumerate(init_list):
+        arrays["init_list%d" % i] = a
+    np.savez_compressed(os.path.join(OUT, "refpark_bo_ridge.npz"), **arrays)
+    print("bo_parkinson suggestions\n%s" % np.array2string(np.asarray(traj), precision=6))
+
+
+if __name__ == "__main__":
+    run_bo_parkinson()
