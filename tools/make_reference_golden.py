@@ -189,6 +189,11 @@ BO_CASES = {
     "bo_multi": ("multi", "none", 3, "lcb", {}),
     "bo_manual": ("manual", "none", 0, "ei", {}),
     "bo_params_polish": ("params", "none", 0, "ucb", dict(n_opt_iterations=3, n_warmup=2000)),
+    # BLR surrogate: acq_max's warm start from the best previous theta of every source task (helpers.py:54-65)
+    "bo_blr_dist_joint": ("dist", "joint", 0, "lcb", dict(algorithm="BLR", weight_dim=[50, 50, 50], lkh_var_init=1e-2,
+                                                         n_epochs=10, first_early_stop_epoch=4, n_warmup=2000)),
+    "bo_blr_multi": ("multi", "none", 3, "lcb", dict(algorithm="BLR", weight_dim=[50, 50, 50], lkh_var_init=1e-2,
+                                                    n_epochs=10, first_early_stop_epoch=4, n_warmup=2000)),
 }
 
 
@@ -264,7 +269,8 @@ def run_bo_case(name):
         ref_helpers.minimize = _minimize
     traj, sim = (out if method in ("dist", "manual", "multi") else (out, None))
     arrays = {"trajectory": np.asarray(traj, dtype=np.float64)}
-    if sim is not None:                                  # ragged (one more task after the first suggestion): zero padded
+    if sim is not None and extra.get("algorithm", "GP") == "GP":   # (BLR logs the string 'none', gp_regressor.py:221-222)
+        # ragged (one more task after the first suggestion): NaN padded
         rows = [np.asarray(s_, dtype=np.float64).reshape(-1) for s_ in sim]
         arrays["similarity"] = np.asarray([np.r_[r, np.full(max(map(len, rows)) - len(r), np.nan)] for r in rows])
     for k, v in inits[0].items():
