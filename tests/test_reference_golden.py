@@ -377,3 +377,54 @@ def test_oracle_parkinson_bo_trajectory_matches_reference():
 def test_cuda_parkinson_bo_trajectory_matches_reference(cuda_engine_mod):
     from distbo_b200.train import gp_regressor
     run_bo_parkinson(gp_regressor)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The headline configuration at full size (N = 8192, 64 tasks, d_theta = 8, P = 23) through the reference's
+# gp_regressor: tests/golden/refconfig5.npz (outputs only; the inputs are bench.make_workload's seeded streams)
+def run_config5(make_regressor, tol):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import bench
+    z = np.load(os.path.join(GOLD, "refconfig5.npz"))
+    work = bench.make_workload(bench.N_OBS, 256, 1000)
+    T = bench.T_SRC
+    X = [work["data_X"][t][:1000 - 3 * t] for t in range(T + 1)]
+    Y = [work["data_Y"][t][:1000 - 3 * t] for t in range(T + 1)]
+    reg = make_regressor("dist", model_type="classification", seed=0, float64=True, target_X=X[T], target_Y=Y[T],
+                         target_embed_ind=np.arange(len(X[T])))
+    reg.initial_weights = {k[len("init__"):]: z[k] for k in z.files if k.startswith("init__")}
+    loss = reg.maximise_likhd(
+        work["theta"], work["y"][:, None], data_X=X[:T], data_Y=Y[:T],
+        source_embed_ind=[np.arange(len(x)) for x in X[:T]], embed_op="joint", algorithm="GP", weight_dim_x=[20, 10],
+        weight_dim_y=[20, 10], batch_size=1000, sizes=work["sizes"], concat_data_size=True, learning_rate=0.005,
+        max_epochs=2, max_size=1000, likhd_var_init=1e-2, stratify=False, gradient_clip=False,
+        first_early_stop_epoch=10 ** 9)
+    assert rel(reg.loss_history, z["loss_log"]) < tol
+    assert abs(loss - float(z["final_loss"])) <= tol * abs(float(z["final_loss"]))
+    reg.initialise_predict()
+    mean, std = reg.predict_y(work["cand"], compute_embed=True)
+    assert rel(mean, z["pred_mean"]) < tol
+    scale = float(np.exp(z["final__log_scale"].reshape(-1)[0]))
+    assert np.max(np.abs(std ** 2 - z["pred_std"] ** 2)) < tol * scale
+    assert rel(reg.similarity()[0], z["similarity"]) < tol
+    return reg
+
+
+def test_oracle_reproduces_reference_at_config5_full_size():
+    o = run_config5(OracleGPRegressor, 1e-9)
+    z = np.load(os.path.join(GOLD, "refconfig5.npz"))
+    for k in z.files:
+        if k.startswith("final__"):      # parameters after two Adam steps: the full-size gradient is the reference's
+            assert rel(np.asarray(o.p[k[7:]]).reshape(-1), z[k].reshape(-1)) < 1e-9, k
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_at_config5_full_size(cuda_engine_mod):
+    from distbo_b200.train import gp_regressor
+    g = run_config5(gp_regressor, 1e-8)
+    z = np.load(os.path.join(GOLD, "refconfig5.npz"))
+    for k in z.files:
+        if k.startswith("final__") and g.engine.params.has(k[7:]):
+            assert rel(g.engine.params.get(k[7:]).reshape(-1), z[k].reshape(-1)) < 1e-8, k
+    g.close()

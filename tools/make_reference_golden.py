@@ -566,3 +566,52 @@ def run_bo_parkinson():
 
 if __name__ == "__main__":
     run_bo_parkinson()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The headline configuration at FULL size (BASELINE config 5: N = 8192 observations = 64 tasks x 128, d_theta = 8,
+# protein-like datasets of 166 binary features / 2 classes, P = 23): two Adam epochs and the posterior on 256
+# candidates through the reference's gp_regressor.  Inputs come from bench.make_workload (seeded), so the file holds
+# outputs only.
+def config5_inputs():
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+    work = bench.make_workload(bench.N_OBS, 256, 1000)
+    T = bench.T_SRC
+    # unequal dataset sizes (1000, 997, ...), so that the size-ratio column carries a gradient
+    X = [work["data_X"][t][:1000 - 3 * t] for t in range(T + 1)]
+    Y = [work["data_Y"][t][:1000 - 3 * t] for t in range(T + 1)]
+    common = dict(model_type="classification", seed=0, float64=True, target_X=X[T], target_Y=Y[T],
+                  target_embed_ind=np.arange(len(X[T])))
+    fit = dict(data_X=X[:T], data_Y=Y[:T], source_embed_ind=[np.arange(len(x)) for x in X[:T]], embed_op="joint",
+               algorithm="GP", weight_dim_x=[20, 10], weight_dim_y=[20, 10], batch_size=1000, sizes=work["sizes"],
+               concat_data_size=True, learning_rate=0.005, max_epochs=2, max_size=1000, likhd_var_init=1e-2,
+               stratify=False, gradient_clip=False, first_early_stop_epoch=10 ** 9)
+    return work, common, fit
+
+
+def run_config5():
+    import time
+    tf.reset_default_graph()
+    tf1_shim._EAGER_SEED[0] = 0
+    work, common, fit = config5_inputs()
+    t0 = time.time()
+    g = gp_regressor("dist", **common)
+    loss = g.maximise_likhd(work["theta"], work["y"][:, None], **fit)
+    init = {k: tf1_shim.INIT_VALUES[id(v)] for k, v in g.net.params.items()}
+    final = {k: v.value.detach().numpy().copy() for k, v in g.net.params.items()}
+    g.initialise_predict()
+    mean, std = g.predict_y(work["cand"], compute_embed=True)
+    out = {"loss_log": np.asarray(g.sess.loss_log), "final_loss": np.asarray(loss), "pred_mean": mean, "pred_std": std,
+           "similarity": np.asarray(g.similarity()[0])}
+    for k, v in init.items():
+        out["init__" + k] = v
+    for k, v in final.items():
+        out["final__" + k] = v
+    np.savez_compressed(os.path.join(OUT, "refconfig5.npz"), **out)
+    print("config5 N=%d: loss %s, mean[0] %.10f, %.0f s" % (len(work["theta"]), g.sess.loss_log, mean[0, 0], time.time() - t0))
+    g.close()
+
+
+if __name__ == "__main__":
+    run_config5()
