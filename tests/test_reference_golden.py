@@ -408,6 +408,19 @@ def run_config5(make_regressor, tol):
     scale = float(np.exp(z["final__log_scale"].reshape(-1)[0]))
     assert np.max(np.abs(std ** 2 - z["pred_std"] ** 2)) < tol * scale
     assert rel(reg.similarity()[0], z["similarity"]) < tol
+    # acquisition sweep: the reference's acq_max picked a row of the bench's candidate stream
+    from distbo_b200.bayes_opt.helpers import UtilityFunction
+    cand = np.random.RandomState(2).uniform(-5.0, 5.0, size=(4096, 8))
+    want_i = int(np.argmax(z["acq_ei"]))
+    assert np.array_equal(cand[want_i], z["acq_x_max"])
+    util = UtilityFunction(kind='ei', kappa=2.58, xi=0.01)
+    ei = np.reshape(util.utility(cand, reg, work["y_max"]), -1)
+    assert int(np.argmax(ei)) == want_i
+    assert np.max(np.abs(ei - z["acq_ei"])) < max(tol, 1e-8) * max(1.0, float(np.max(np.abs(z["acq_ei"]))))
+    if hasattr(reg, "acquire"):          # the fused device pass (posterior + EI + arg-max in one sweep)
+        v, i = util.argmax(cand, reg, work["y_max"])
+        assert i == want_i
+        assert v == pytest.approx(float(z["acq_ei"][want_i]), rel=1e-7)
     return reg
 
 

@@ -604,6 +604,16 @@ def run_config5():
     mean, std = g.predict_y(work["cand"], compute_embed=True)
     out = {"loss_log": np.asarray(g.sess.loss_log), "final_loss": np.asarray(loss), "pred_mean": mean, "pred_std": std,
            "similarity": np.asarray(g.similarity()[0])}
+    # the acquisition sweep of the BO loop (HOT LOOP 2): the reference's acq_max over the first 4096 rows of the
+    # bench's candidate stream (RandomState(2), U(-5, 5)^8; the full 2^20 would need 69 GB per [N, M] temporary)
+    from distBO.bayes_opt.helpers import UtilityFunction, acq_max
+    util = UtilityFunction(kind='ei', kappa=2.58, xi=0.01)
+    bounds = np.array([[-5.0, 5.0]] * 8)
+    x_max = acq_max(ac=util.utility, gp=g, y_max=work["y_max"], bounds=bounds, random_state=np.random.RandomState(2),
+                    n_warmup=4096, n_iter=0)
+    cand = np.random.RandomState(2).uniform(-5.0, 5.0, size=(4096, 8))
+    out["acq_x_max"] = np.asarray(x_max)
+    out["acq_ei"] = np.asarray(util.utility(cand, g, work["y_max"]), dtype=np.float64).reshape(-1)
     for k, v in init.items():
         out["init__" + k] = v
     for k, v in final.items():
