@@ -29,6 +29,20 @@ def ridge(data, log_alpha, log_gamma):
     return max(model.score(test, data.test_y), -1.0)
 
 
+def dim_ridge(data, log_alpha, log_bw1, log_bw2, log_bw3, log_bw4, log_bw5, log_bw6):
+    """R^2 (floored at -1) of ridge regression on 200 random Fourier features (gamma 0.5, random_state 0) of the six
+    features divided by per-dimension bandwidths: the 7-d objective of config 4 (models.py:177-195)."""
+    from sklearn.kernel_approximation import RBFSampler
+    from sklearn.linear_model import Ridge
+    bw = np.exp(np.array([log_bw1, log_bw2, log_bw3, log_bw4, log_bw5, log_bw6]))
+    rff = RBFSampler(gamma=0.5, n_components=200, random_state=0)
+    train = rff.fit_transform(np.divide(data.train_x, bw))
+    test = rff.transform(np.divide(data.test_x, bw))
+    model = Ridge(alpha=np.exp(log_alpha))
+    model.fit(train, data.train_y)
+    return max(model.score(test, data.test_y), -1.0)
+
+
 def random_forest(data, depth, min_samples_leaf, min_samples_split, n_trees):
     """Test AUC of an (unseeded, as in the reference) random forest (models.py:225-237)."""
     from sklearn.ensemble import RandomForestClassifier
@@ -44,6 +58,12 @@ _BOUNDS = {
     'ridge': (ridge, 'regression', {'log_alpha': (np.log(10.0 ** -10), np.log(0.1)),
                                     'log_gamma': (np.log(2.0 ** -7), np.log(2.0 ** 5))},
               ['log_alpha', 'log_gamma']),
+    'dim_ridge': (dim_ridge, 'regression',
+                  # insertion order as in the reference's dict literal (models.py:84-88): it is the column order of
+                  # theta inside the GP and of the candidate stream (target_space.py:47 keeps dict order)
+                  dict([('log_bw%d' % i, (np.log(2.0 ** -7), np.log(2.0 ** 6))) for i in range(1, 7)] +
+                       [('log_alpha', (np.log(10.0 ** -8), np.log(0.1)))]),
+                  ['log_alpha'] + ['log_bw%d' % i for i in range(1, 7)]),
     'forest': (random_forest, 'classification', {'n_trees': (1, 200), 'depth': (1, 32),
                                                  'min_samples_leaf': (0.01, 0.5),
                                                  'min_samples_split': (0.01, 1.0)},

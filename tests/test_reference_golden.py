@@ -441,3 +441,63 @@ def test_cuda_reproduces_reference_at_config5_full_size(cuda_engine_mod):
         if k.startswith("final__") and g.engine.params.has(k[7:]):
             assert rel(g.engine.params.get(k[7:]).reshape(-1), z[k].reshape(-1)) < 1e-8, k
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Config 4 (counter_manual): the reference's manualBO pipeline end to end - generate_data('counter_manual'),
+# meta_fea.meta(), the 7-d dim_ridge objective, manual-kernel BO loop: tests/golden/refcounter_manual_bo.npz
+def counter_manual_setup():
+    import warnings
+    from distbo_b200.data.toy_datasets import counter_manual_tasks
+    from distbo_b200.model_embed.meta_fea import meta
+    z = np.load(os.path.join(GOLD, "refcounter_manual_bo.npz"))
+    target, sources, _ = counter_manual_tasks(3, noise=0.5, n_train=300, n_test=300)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        meta([target] + sources, 'dim_ridge', max_size=None, random_state=5)
+    return z, target, sources
+
+
+def test_counter_manual_inputs_match_reference():
+    """Datasets, meta-features and objective of config 4 are the reference's."""
+    from distbo_b200.model_embed import set_model
+    z, target, sources = counter_manual_setup()
+    assert np.array_equal(target.train_x, z["target_train_x"]) and np.array_equal(target.train_y, z["target_train_y"])
+    assert np.array_equal(sources[0].train_x, z["source0_train_x"])
+    assert np.allclose(np.asarray([d.embed for d in [target] + sources]), z["embed"], rtol=1e-10, atol=1e-12)
+    names = ['log_alpha'] + ['log_bw%d' % i for i in range(1, 7)]
+    for i, s in enumerate(sources):
+        f, bounds, _, model_type = set_model('dim_ridge', s, None)
+        assert model_type == 'regression' and sorted(bounds) == sorted(names)
+        for row in z["init_list%d" % i][:3]:
+            assert f(**dict(zip(names, row[:-1]))) == pytest.approx(row[-1], rel=1e-9, abs=1e-12)
+
+
+def run_counter_manual_bo(make_regressor):
+    from distbo_b200.model_embed import bayes_opt_wrap
+    z, target, sources = counter_manual_setup()
+    init = {k[len("init__"):]: z[k] for k in z.files if k.startswith("init__")}
+    init_list = [z["init_list%d" % i].copy() for i in range(len(sources))]
+
+    def factory(kernel, **kw):
+        reg = make_regressor(kernel, **kw)
+        reg.initial_weights = init
+        return reg
+    cfg = bo_optim_config(n_warmup=5000, n_epochs=20, lkh_var_init=1e-5)
+    traj, _ = bayes_opt_wrap('manual', target, acq='ei', model='dim_ridge', rs=np.random.RandomState(13),
+                             optim_config=cfg, xi=0.01, kappa=2.58, bo_it=4, rand_it=0, init_list=init_list,
+                             include_init=False, source_data=sources, gp_class=factory, verbose=0, acq_one_shot='ei')
+    want = z["trajectory"]
+    assert traj.shape == want.shape == (4, 8)
+    assert np.array_equal(traj[:, :7], want[:, :7]), (traj, want)          # identical 7-d suggestions
+    assert np.allclose(traj[:, 7], want[:, 7], rtol=1e-10)
+
+
+def test_oracle_counter_manual_bo_matches_reference():
+    run_counter_manual_bo(OracleGPRegressor)
+
+
+@pytest.mark.gpu
+def test_cuda_counter_manual_bo_matches_reference(cuda_engine_mod):
+    from distbo_b200.train import gp_regressor
+    run_counter_manual_bo(gp_regressor)

@@ -625,3 +625,89 @@ def run_config5():
 
 if __name__ == "__main__":
     run_config5()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Config 4 (counter_manual): the reference's whole manualBO pipeline - generate_data('counter_manual') datasets,
+# meta_fea.meta() features, the 7-d dim_ridge objective and the manual-kernel BO loop of bayes_opt_wrap.
+def run_bo_counter_manual():
+    import contextlib
+    import io
+    import types as _types
+    import sklearn.datasets
+    sklearn.datasets.__dict__.setdefault("load_boston", lambda *a, **k: None)
+    km = _types.ModuleType("sklearn.cluster.k_means_")
+    km._init_centroids = None
+    sys.modules.setdefault("sklearn.cluster.k_means_", km)
+    import distBO.train.gp_regressor as ref_gp
+    import distBO.model_embed.bayes_optimise as ref_bo_mod
+    from distBO.data.generate_data import generate_data
+    from distBO.model_embed.meta_fea import meta as ref_meta
+    from distBO.model_embed.models import set_model as ref_set_model
+    tf.reset_default_graph()
+    tf1_shim._EAGER_SEED[0] = 0
+    args = _types.SimpleNamespace(dataset='counter_manual', data_seed=3, dim=6, preprocess='standardise',
+                                  max_embed_size=10000, n_train=300, n_test=300, noise=0.5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = generate_data(args)
+        target, sources = res[0], list(res[1])
+        ref_meta([target] + sources, 'dim_ridge', max_size=None, random_state=5)
+    rs = np.random.RandomState(8)
+    init_list = []
+    for s_ in sources:                                   # 10 random-search evaluations per source task
+        f, bounds, _, _ = ref_set_model('dim_ridge', s_, None)
+        names = ['log_alpha'] + ['log_bw%d' % i for i in range(1, 7)]
+        rows = []
+        for _ in range(10):                              # drawn from the well-behaved corner of the search box
+            th = {k: rs.uniform(np.log(1e-3), np.log(0.1)) if k == 'log_alpha' else rs.uniform(0.0, np.log(16.0))
+                  for k in names}
+            with contextlib.redirect_stdout(io.StringIO()):
+                rows.append([th[k] for k in names] + [f(**th)])
+        init_list.append(np.array(rows))
+    inits = []
+    orig_close = ref_gp.gp_regressor.close
+
+    def recording_close(self):
+        inits.append({k: tf1_shim.INIT_VALUES[id(v)] for k, v in self.net.params.items()})
+        return orig_close(self)
+    ref_gp.gp_regressor.close = recording_close
+
+    class _NumpyCompat(object):          # ragged np.array(...) at bayes_optimise.py:60, see run_bo_case
+        def __getattr__(self, k):
+            return getattr(np, k)
+
+        @staticmethod
+        def array(obj, *a, **kw):
+            try:
+                return np.array(obj, *a, **kw)
+            except ValueError:
+                out = np.empty(len(obj), dtype=object)
+                for i, v in enumerate(obj):
+                    out[i] = v
+                return out
+    ref_bo_mod.np = _NumpyCompat()
+    cfg = bo_optim_config(n_warmup=5000, n_epochs=20, lkh_var_init=1e-5)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            traj, sim = ref_bo_mod.bayes_opt_wrap('manual', target, acq='ei', model='dim_ridge',
+                                                  rs=np.random.RandomState(13), optim_config=cfg, xi=0.01, kappa=2.58,
+                                                  bo_it=4, rand_it=0, init_list=[a.copy() for a in init_list],
+                                                  include_init=False, source_data=sources, acq_one_shot='ei')
+    finally:
+        ref_gp.gp_regressor.close = orig_close
+        ref_bo_mod.np = np
+    arrays = {"trajectory": np.asarray(traj, dtype=np.float64),
+              "embed": np.asarray([d.embed for d in [target] + sources]),
+              "target_train_x": target.train_x, "target_train_y": target.train_y,
+              "source0_train_x": sources[0].train_x}
+    for k, v in inits[0].items():
+        arrays["init__" + k] = v
+    for i, a in enumerate(init_list):
+        arrays["init_list%d" % i] = a
+    np.savez_compressed(os.path.join(OUT, "refcounter_manual_bo.npz"), **arrays)
+    print("counter_manual: %d meta-features, suggestions\n%s" % (arrays["embed"].shape[1],
+                                                                np.array2string(np.asarray(traj), precision=4)))
+
+
+if __name__ == "__main__":
+    run_bo_counter_manual()
