@@ -43,6 +43,19 @@ def dim_ridge(data, log_alpha, log_bw1, log_bw2, log_bw3, log_bw4, log_bw5, log_
     return max(model.score(test, data.test_y), -1.0)
 
 
+def jaccard_svm(data, log_C):
+    """Test accuracy of an SVM on the precomputed Jaccard kernel of the binary fingerprints: the deterministic
+    1-d objective the reference offers for the protein tasks (models.py:122-139)."""
+    from scipy.spatial.distance import cdist
+    from sklearn.svm import SVC
+    train_y, test_y = data.lb.inverse_transform(data.train_y), data.lb.inverse_transform(data.test_y)
+    k_train = 1 - cdist(data.train_x, data.train_x, 'jaccard')
+    k_test = 1 - cdist(data.test_x, data.train_x, 'jaccard')
+    clf = SVC(C=np.exp(log_C), kernel='precomputed')
+    clf.fit(k_train, train_y)
+    return clf.score(k_test, test_y)
+
+
 def random_forest(data, depth, min_samples_leaf, min_samples_split, n_trees):
     """Test AUC of an (unseeded, as in the reference) random forest (models.py:225-237)."""
     from sklearn.ensemble import RandomForestClassifier
@@ -64,6 +77,7 @@ _BOUNDS = {
                   dict([('log_bw%d' % i, (np.log(2.0 ** -7), np.log(2.0 ** 6))) for i in range(1, 7)] +
                        [('log_alpha', (np.log(10.0 ** -8), np.log(0.1)))]),
                   ['log_alpha'] + ['log_bw%d' % i for i in range(1, 7)]),
+    'jaccard_svm': (jaccard_svm, 'classification', {'log_C': (np.log(2 ** -7), np.log(2 ** 10))}, ['log_C']),
     'forest': (random_forest, 'classification', {'n_trees': (1, 200), 'depth': (1, 32),
                                                  'min_samples_leaf': (0.01, 0.5),
                                                  'min_samples_split': (0.01, 1.0)},

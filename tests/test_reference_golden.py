@@ -501,3 +501,46 @@ def test_oracle_counter_manual_bo_matches_reference():
 def test_cuda_counter_manual_bo_matches_reference(cuda_engine_mod):
     from distbo_b200.train import gp_regressor
     run_counter_manual_bo(gp_regressor)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BO trajectory at the protein configuration (config 2) through the reference's driver with its deterministic
+# jaccard_svm objective: tests/golden/refprotein_bo_jaccard.npz (6 + 1 ChEMBL targets, 166 bits, 2 classes, P = 23)
+def run_bo_protein(make_regressor):
+    from sklearn.utils import check_random_state
+    from distbo_b200.data.load_datasets import protein_tasks
+    from distbo_b200.model_embed import bayes_opt_wrap, set_model
+    z = np.load(os.path.join(GOLD, "refprotein_bo_jaccard.npz"))
+    zz = np.load(os.path.join(GOLD, "protein_subset.npz"))
+    bits = np.unpackbits(zz["bits"], axis=2)[:, :, :166].astype(np.float64)
+    tables = [np.hstack([np.zeros((bits.shape[1], 1)), bits[i], zz["labels"][i][:, None].astype(np.float64)])
+              for i in range(bits.shape[0])]
+    target, sources, _ = protein_tasks(tables, [str(n) for n in zz["names"]], target=2,
+                                       random_state=check_random_state(3), test_size=0.4)
+    init_list = [z["init_list%d" % i].copy() for i in range(len(sources))]
+    f, _, _, _ = set_model('jaccard_svm', sources[0], None)          # the stored evaluations are this objective's
+    assert f(log_C=init_list[0][0, 0]) == pytest.approx(init_list[0][0, 1], rel=1e-12)
+    init = {k[len("init__"):]: z[k] for k in z.files if k.startswith("init__")}
+
+    def factory(kernel, **kw):
+        reg = make_regressor(kernel, **kw)
+        reg.initial_weights = init
+        return reg
+    cfg = bo_optim_config(embed_op='joint', concat_data_size=True, max_size=int(z["max_size"]), n_warmup=5000,
+                          n_epochs=20, stratify=True, batch_size=1000)
+    traj, _ = bayes_opt_wrap('dist', target, acq='ei', model='jaccard_svm', rs=np.random.RandomState(11),
+                             optim_config=cfg, xi=0.01, kappa=2.58, bo_it=4, rand_it=0, init_list=init_list,
+                             include_init=False, source_data=sources, gp_class=factory, verbose=0, acq_one_shot='lcb')
+    want = z["trajectory"]
+    assert traj.shape == want.shape == (4, 2)
+    assert np.array_equal(traj, want), (traj, want)
+
+
+def test_oracle_protein_bo_trajectory_matches_reference():
+    run_bo_protein(OracleGPRegressor)
+
+
+@pytest.mark.gpu
+def test_cuda_protein_bo_trajectory_matches_reference(cuda_engine_mod):
+    from distbo_b200.train import gp_regressor
+    run_bo_protein(gp_regressor)

@@ -711,3 +711,81 @@ def run_bo_counter_manual():
 
 if __name__ == "__main__":
     run_bo_counter_manual()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BO trajectory at the protein configuration (config 2): 6 source ChEMBL targets + 1 target (committed subset of the
+# reference's files), 166 binary features, 2 classes, P = 10*2 + 2 + 1 = 23, through the reference's driver with its
+# deterministic jaccard_svm objective (the default random forest is unseeded, models.py:225-237).
+def run_bo_protein():
+    import contextlib
+    import io
+    import distBO.train.gp_regressor as ref_gp
+    import distBO.model_embed.bayes_optimise as ref_bo_mod
+    from distBO.model_embed.models import set_model as ref_set_model
+    from sklearn.utils import check_random_state
+    sys.path.insert(0, os.path.dirname(HERE))
+    from distbo_b200.data.load_datasets import protein_tasks
+    tf.reset_default_graph()
+    tf1_shim._EAGER_SEED[0] = 0
+    z = np.load(os.path.join(os.path.dirname(HERE), "tests", "golden", "protein_subset.npz"))
+    bits = np.unpackbits(z["bits"], axis=2)[:, :, :166].astype(np.float64)
+    tables = [np.hstack([np.zeros((bits.shape[1], 1)), bits[i], z["labels"][i][:, None].astype(np.float64)])
+              for i in range(bits.shape[0])]
+    target, sources, _ = protein_tasks(tables, [str(n) for n in z["names"]], target=2,
+                                       random_state=check_random_state(3), test_size=0.4)
+    rs = np.random.RandomState(5)
+    init_list = []
+    for s_ in sources:                                   # 8 random-search evaluations per source target
+        f, bounds, _, _ = ref_set_model('jaccard_svm', s_, None)
+        rows = []
+        for _ in range(8):
+            c = rs.uniform(*bounds['log_C'])
+            with contextlib.redirect_stdout(io.StringIO()):
+                rows.append([c, f(log_C=c)])
+        init_list.append(np.array(rows))
+    inits = []
+    orig_close = ref_gp.gp_regressor.close
+
+    def recording_close(self):
+        inits.append({k: tf1_shim.INIT_VALUES[id(v)] for k, v in self.net.params.items()})
+        return orig_close(self)
+    ref_gp.gp_regressor.close = recording_close
+
+    class _NumpyCompat(object):          # ragged np.array(...) at bayes_optimise.py:60, see run_bo_case
+        def __getattr__(self, k):
+            return getattr(np, k)
+
+        @staticmethod
+        def array(obj, *a, **kw):
+            try:
+                return np.array(obj, *a, **kw)
+            except ValueError:
+                out = np.empty(len(obj), dtype=object)
+                for i, v in enumerate(obj):
+                    out[i] = v
+                return out
+    ref_bo_mod.np = _NumpyCompat()
+    max_size = max([len(target.train_x)] + [len(s_.train_x) for s_ in sources])
+    cfg = bo_optim_config(embed_op='joint', concat_data_size=True, max_size=max_size, n_warmup=5000, n_epochs=20,
+                          stratify=True, batch_size=1000)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            traj, sim = ref_bo_mod.bayes_opt_wrap('dist', target, acq='ei', model='jaccard_svm',
+                                                  rs=np.random.RandomState(11), optim_config=cfg, xi=0.01, kappa=2.58,
+                                                  bo_it=4, rand_it=0, init_list=[a.copy() for a in init_list],
+                                                  include_init=False, source_data=sources, acq_one_shot='lcb')
+    finally:
+        ref_gp.gp_regressor.close = orig_close
+        ref_bo_mod.np = np
+    arrays = {"trajectory": np.asarray(traj, dtype=np.float64), "max_size": np.asarray(max_size)}
+    for k, v in inits[0].items():
+        arrays["init__" + k] = v
+    for i, a in enumerate(init_list):
+        arrays["init_list%d" % i] = a
+    np.savez_compressed(os.path.join(OUT, "refprotein_bo_jaccard.npz"), **arrays)
+    print("bo_protein suggestions\n%s" % np.array2string(np.asarray(traj), precision=6))
+
+
+if __name__ == "__main__":
+    run_bo_protein()
