@@ -64,6 +64,12 @@ def test_sass_is_sm100a_with_fp64_tensor_ops():
         mangled = "%d%s" % (len(kernel), kernel)           # exact Itanium name component, not a substring
         bodies = [b for b in per_fn if mangled in b.split("\n", 1)[0]]
         assert bodies and all("DMMA" in b for b in bodies), kernel
+    # K1 fp32 forward: rows arrive by bulk async copies (the 1-D TMA path, SASS UBLKCP) guarded by mbarriers (SYNCS),
+    # layer 1 runs on the tensor pipe (mma.sync TF32 -> HMMA.1688.F32.TF32)
+    bodies = [b for b in per_fn if "19embed_fwd_tc_kernel" in b.split("\n", 1)[0]]
+    assert len(bodies) == 8            # column tiles 1..4 x row tiles 1..2
+    for b in bodies:
+        assert "UBLKCP" in b and "SYNCS" in b and "HMMA.1688.F32.TF32" in b
 
 
 def test_no_cpu_fallback():
