@@ -29,18 +29,21 @@ from . import gp_oracle as O
 def build_params_blr(in_dim_params, kernel, weight_dim, num_of_rff=0, in_dim_x=None, in_dim_y=None,
                      weight_dim_x=None, weight_dim_y=None, model_type="regression", embed_op="joint",
                      concat_data_size=False, in_dim_meta=None, n_tasks=None, likhd_var_init=0.01, seed=23,
-                     dtype=np.float64):
+                     dtype=np.float64, weight_dim_xy=None):
     """log_gaus_likelihood_feature.py:30-79.  Returns (params, rff_input_dim)."""
     params = {}
     if kernel == "dist":
-        if embed_op not in ("none", "joint", "concat"):
+        if embed_op not in ("none", "joint", "concat", "nn"):
             raise NotImplementedError(embed_op)
-        O.nn_weight_setter(params, in_dim_x, weight_dim_x, "x", seed=seed, dtype=dtype)
-        if embed_op in ("joint", "concat") and model_type == "regression":
-            O.nn_weight_setter(params, in_dim_y, weight_dim_y, "y", seed=seed, dtype=dtype)
-            if embed_op == "concat":
-                params["log_reg"] = np.zeros((), dtype=dtype)
-        embed_dim = O.num_bw_embed(embed_op, model_type, in_dim_y, weight_dim_x, weight_dim_y, None,
+        if embed_op == "nn":                                 # :49-53: one net over [x | y]
+            O.nn_weight_setter(params, in_dim_x + in_dim_y, weight_dim_xy, "xy", seed=seed, dtype=dtype)
+        else:
+            O.nn_weight_setter(params, in_dim_x, weight_dim_x, "x", seed=seed, dtype=dtype)
+            if embed_op in ("joint", "concat") and model_type == "regression":
+                O.nn_weight_setter(params, in_dim_y, weight_dim_y, "y", seed=seed, dtype=dtype)
+                if embed_op == "concat":
+                    params["log_reg"] = np.zeros((), dtype=dtype)
+        embed_dim = O.num_bw_embed(embed_op, model_type, in_dim_y, weight_dim_x, weight_dim_y, weight_dim_xy,
                                    concat_data_size)
     elif kernel == "manual":
         embed_dim = in_dim_meta

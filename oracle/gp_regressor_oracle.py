@@ -163,8 +163,8 @@ class OracleGPRegressor(object):
                 self.p, self.rff_input_dim = BO.build_params_blr(
                     self.in_dim_params, self.kernel, weight_dim, num_of_rff=num_of_rff,
                     in_dim_x=getattr(self, "in_dim_x", None), in_dim_y=getattr(self, "in_dim_y", None),
-                    weight_dim_x=weight_dim_x, weight_dim_y=weight_dim_y, model_type=self.model_type,
-                    embed_op=embed_op, concat_data_size=concat_data_size,
+                    weight_dim_x=weight_dim_x, weight_dim_y=weight_dim_y, weight_dim_xy=weight_dim_xy,
+                    model_type=self.model_type, embed_op=embed_op, concat_data_size=concat_data_size,
                     in_dim_meta=len(target_embed[0]) if self.kernel == "manual" else None,
                     n_tasks=self.n_tasks, likhd_var_init=likhd_var_init, seed=kw["seed"])
                 if self.kernel == "dist":

@@ -77,6 +77,8 @@ CASES = {
                                                     concat_data_size=True)),
     "blr_dist_class": ("dist", True, "joint", dict(algorithm="BLR", weight_dim=[30, 20], num_of_rff=0,
                                                    concat_data_size=True)),
+    "blr_dist_nn3": ("dist", False, "nn", dict(algorithm="BLR", weight_dim=[30, 20], num_of_rff=0,
+                                               concat_data_size=True, weight_dim_xy=[20, 12, 10])),
     # the reference's own data (subsets committed as tests/golden/protein_subset.npz / parkinson_subset.npz by
     # tools/make_real_fixtures.py): MACCS fingerprints of ChEMBL targets, 166 bits, 2 classes (config 2) and
     # per-patient Parkinson telemonitoring rows, 17 features (config 3)
