@@ -60,9 +60,11 @@ class EmbedBatchSampler:
     Yields, per epoch, a list of index arrays (one per dataset; None = "all rows, in order").
     Draw order from `rs` matches the reference: one permutation (or stratified split) per dataset
     that is larger than batch_size, datasets in order.  The reference's stratified-classification
-    branch shuffles with the unseeded global `random` (no reproducible stream of its own); a
-    numpy RandomState(shuffle_seed) stands in for it - class members are numpy arrays, so an
-    epoch costs a few slices per dataset and a reshuffle ~25 us instead of milliseconds of Python list work.
+    branch shuffles Python lists with the unseeded global `random` (gp_utils.py:53,78); here the same
+    `random.shuffle` algorithm runs on a private `random.Random(shuffle_seed)`, i.e. the stream the reference
+    draws after `random.seed(shuffle_seed)` (tests/golden/ref_dist_class_stratified.npz).  Shuffles
+    happen at set-up and when a class runs out of unseen rows; between them the members are numpy arrays, so
+    an epoch costs a few slices per dataset.
     """
 
     def __init__(self, data_Y, batch_size, rs, model_type, stratify, shuffle_seed=0):
@@ -75,7 +77,8 @@ class EmbedBatchSampler:
         self.constant = all(n <= self.batch_size for n in self.n)
         self._cls = None
         if not self.constant and self.stratify and model_type == "classification":
-            pyrand = np.random.RandomState(shuffle_seed)
+            import random
+            pyrand = random.Random(shuffle_seed)
             self._pyrand = pyrand
             n_classes = data_Y[0].shape[1]
             self._cls = []
@@ -83,11 +86,15 @@ class EmbedBatchSampler:
                 labels = (y[:, 0] > 0.5).astype(int) if n_classes == 2 else np.argmax(y, axis=1)
                 per_class = []
                 for c in range(n_classes):
-                    members = np.where(labels == c)[0].astype(np.int64)
-                    pyrand.shuffle(members)
+                    members = self._shuffled(np.where(labels == c)[0].astype(np.int64))
                     take = int((float(len(members)) / len(y)) * (self.batch_size + 4))
                     per_class.append({"members": members, "take": take, "pos": 0})
                 self._cls.append(per_class)
+
+    def _shuffled(self, members):
+        lst = members.tolist()
+        self._pyrand.shuffle(lst)               # Python's list shuffle, as the reference calls it
+        return np.asarray(lst, dtype=np.int64)
 
     def sizes(self):
         return [min(n, self.batch_size) for n in self.n]
@@ -102,7 +109,7 @@ class EmbedBatchSampler:
                 for c in self._cls[i]:
                     end = c["pos"] + c["take"]
                     if end > len(c["members"]):
-                        self._pyrand.shuffle(c["members"])
+                        c["members"] = self._shuffled(c["members"])
                         c["pos"], end = 0, c["take"]
                     picked.append(c["members"][c["pos"]:end])
                     c["pos"] = end

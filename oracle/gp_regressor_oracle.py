@@ -43,13 +43,14 @@ def sample(data_X, data_Y, embed_ind=None, source_list=True):
 
 
 def loop_batches(train, batch_size, max_epochs, rs, model_type, stratify=False, shuffle_seed=0):
-    """train/gp_utils.py:28-104.  The reference's stratified-classification branch uses the
-    unseeded global ``random.shuffle`` (:53,78), so it has no reproducible stream of its own; a
-    ``numpy.random.RandomState(shuffle_seed).shuffle`` stands in for it."""
+    """train/gp_utils.py:28-104.  The reference's stratified-classification branch shuffles Python lists with
+    the unseeded global ``random.shuffle`` (:53,78); a private ``random.Random(shuffle_seed)`` reproduces the stream
+    the reference draws after ``random.seed(shuffle_seed)``."""
     if "X" in train and "y" in train:
         X_list, Y_list = train["X"], train["y"]
         n_datasets = len(X_list)
-        pyrand = np.random.RandomState(shuffle_seed)
+        import random
+        pyrand = random.Random(shuffle_seed)
         if model_type == "classification":
             n_classes = Y_list[0].shape[1]
         if model_type == "classification" and stratify:
@@ -64,7 +65,7 @@ def loop_batches(train, batch_size, max_epochs, rs, model_type, stratify=False, 
                     class_y = np.argmax(dataY, axis=1)
                 c_l, c_r, c_i = [], [], []
                 for l in range(n_classes):
-                    index = np.where(class_y == l)[0]
+                    index = np.where(class_y == l)[0].tolist()
                     pyrand.shuffle(index)
                     c_l.append(index)
                     c_r.append(int((float(len(index)) / len(dataY)) * (batch_size + 4)))
@@ -88,7 +89,7 @@ def loop_batches(train, batch_size, max_epochs, rs, model_type, stratify=False, 
                                 pyrand.shuffle(cls_list[i][k])
                                 cls_index[i][k] = 0
                                 end = cls_ratio[i][k]
-                            class_index = class_index + cls_list[i][k][cls_index[i][k]:end].tolist()
+                            class_index = class_index + cls_list[i][k][cls_index[i][k]:end]
                             cls_index[i][k] = end
                         class_index = class_index[:batch_size]
                         sX, sY = dataX[class_index, :], dataY[class_index, :]

@@ -66,6 +66,10 @@ CASES = {
     "dist_joint_batched": ("dist", False, "joint", dict(concat_data_size=True, batch_size=64, stratify=False)),
     "dist_joint_stratified": ("dist", False, "joint", dict(concat_data_size=False, batch_size=64, stratify=True)),
     "dist_class": ("dist", True, "joint", dict(concat_data_size=True)),
+    # stratified class mini-batches (gp_utils.py:38-84): the reference shuffles with the global `random`, seeded
+    # below with 0 = the product's / oracle's shuffle_seed
+    "dist_class_stratified": ("dist", True, "joint", dict(concat_data_size=True, batch_size=48, stratify=True,
+                                                          max_epochs=12)),
     "dist_concat": ("dist", False, "concat", dict(concat_data_size=True)),
     "dist_nn3": ("dist", False, "nn", dict(concat_data_size=True, weight_dim_xy=[20, 12, 10])),
     "dist_nn2class": ("dist", True, "nn", dict(concat_data_size=False, weight_dim_xy=[20, 10])),
@@ -112,6 +116,8 @@ def real_tasks(name, rs, T, per_task, d):
 
 def run_case(name):
     kernel, classification, embed_op, extra = CASES[name]
+    import random
+    random.seed(0)
     tf.reset_default_graph()
     tf1_shim._EAGER_SEED[0] = 0
     rs = np.random.RandomState(abs(hash(name)) % 1000 if False else sum(map(ord, name)))
