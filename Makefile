@@ -2,7 +2,7 @@
 NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
-SRC := distbo_b200/csrc/chol.cu distbo_b200/csrc/gram.cu distbo_b200/csrc/score.cu distbo_b200/csrc/embed.cu distbo_b200/csrc/blr.cu
+SRC := distbo_b200/csrc/chol.cu distbo_b200/csrc/gram.cu distbo_b200/csrc/score.cu distbo_b200/csrc/embed.cu distbo_b200/csrc/blr.cu distbo_b200/csrc/hostutil.cu
 OBJ := $(SRC:.cu=.o)
 LIB := distbo_b200/libdistbo_b200.so
 

@@ -54,6 +54,29 @@ def label_bins(labels, lo=0.0, hi=1.01, intervals=4):
     return np.digitize(np.squeeze(labels), np.linspace(lo, hi, intervals))
 
 
+class PyShuffle:
+    """`random.Random(seed).shuffle` on int64 numpy arrays at C speed: the Mersenne-Twister state of the Python
+    generator is handed to `distbo_py_shuffle_i64` (csrc/hostutil.cu), which advances it exactly as CPython's
+    shuffle / _randbelow / getrandbits do.  tests/test_bo_host.py checks it against `random.shuffle` itself."""
+
+    def __init__(self, seed):
+        import random
+        from .. import _lib
+        state = random.Random(seed).getstate()[1]
+        self._mt = np.ascontiguousarray(np.asarray(state[:624], dtype=np.uint32))
+        self._idx = np.asarray([state[624]], dtype=np.int32)
+        self._fn = _lib.load().distbo_py_shuffle_i64
+        self._C = _lib.C
+
+    def shuffle(self, members):
+        out = np.ascontiguousarray(members, dtype=np.int64).copy()
+        vp = self._C.c_void_p
+        rc = self._fn(vp(self._mt.ctypes.data), vp(self._idx.ctypes.data), vp(out.ctypes.data), int(out.size))
+        if rc:
+            raise RuntimeError("distbo_py_shuffle_i64 failed (%d)" % rc)
+        return out
+
+
 class EmbedBatchSampler:
     """Row indices of each epoch's embedding mini-batch, per dataset (reference train/gp_utils.py:28-104).
 
@@ -77,9 +100,7 @@ class EmbedBatchSampler:
         self.constant = all(n <= self.batch_size for n in self.n)
         self._cls = None
         if not self.constant and self.stratify and model_type == "classification":
-            import random
-            pyrand = random.Random(shuffle_seed)
-            self._pyrand = pyrand
+            self._pyrand = PyShuffle(shuffle_seed)
             n_classes = data_Y[0].shape[1]
             self._cls = []
             for y in data_Y:
@@ -92,9 +113,7 @@ class EmbedBatchSampler:
                 self._cls.append(per_class)
 
     def _shuffled(self, members):
-        lst = members.tolist()
-        self._pyrand.shuffle(lst)               # Python's list shuffle, as the reference calls it
-        return np.asarray(lst, dtype=np.int64)
+        return self._pyrand.shuffle(members)    # Python's list shuffle, as the reference calls it
 
     def sizes(self):
         return [min(n, self.batch_size) for n in self.n]

@@ -87,6 +87,13 @@ int distbo_embed_bwd_f64(const double* X, const double* Y, const int32_t* seg_of
 int64_t distbo_embed_workspace(int64_t S, int T, int dx, int dy, int hx, int p, int pm, int hy, int q, int y_mode,
                                int elem_bytes, int backward);
 
+/* ---- host helper of the mini-batch sampler (train/gp_utils.py:38-84) ---------------------------------
+ * CPython's random.shuffle(x) on an int64 array, bit for bit: mt_state [624] and *mt_index are the Mersenne-Twister
+ * state of a random.Random (getstate()[1][:624], [624]), advanced in place.  The reference shuffles class-member
+ * lists with the global `random`; this keeps its stream without Python-speed shuffles on the training thread.
+ * Host memory only; no device work. */
+int distbo_py_shuffle_i64(uint32_t* mt_state, int32_t* mt_index, int64_t* x, int64_t n);
+
 /* ---- K2: Matern-3/2 product Gram  (train/kernels.py:19-28,58-88; log_gaus_likelihood.py:86-122) --
  * Task-level Gram KE[t,t'] = matern32(E[t]/exp(log_bw_embed), E[t']/exp(log_bw_embed)), [T,T]. */
 int distbo_task_gram_f64(const double* E, int lde, int T, int P, const double* log_bw_embed,

@@ -178,3 +178,16 @@ def test_bo_loop_blr_with_oracle_regressor():
     # first suggestion = best theta of one of the first two source tasks (BLR warm start)
     firsts = [init[np.argmax(init[:, 1]), 0] for init in init_list[:2]]
     assert out[0, 0] in firsts
+
+
+def test_c_shuffle_is_pythons_random_shuffle():
+    """distbo_py_shuffle_i64 (host helper of the stratified sampler) = random.Random(seed).shuffle, call after call."""
+    import random
+    from distbo_b200.train.gp_utils import PyShuffle
+    for seed in (0, 7, 2 ** 31 + 5):
+        ref, mine = random.Random(seed), PyShuffle(seed)
+        for n in (1, 2, 3, 17, 624, 625, 1000, 4434, 33, 0):
+            lst = list(range(100, 100 + n))
+            ref.shuffle(lst)
+            got = mine.shuffle(np.arange(100, 100 + n))
+            assert got.tolist() == lst, (seed, n)
