@@ -177,10 +177,6 @@ def run_case(name):
     g.close()
 
 
-if __name__ == "__main__" and "--bo-only" not in sys.argv:
-    os.makedirs(OUT, exist_ok=True)
-    for name in CASES:
-        run_case(name)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -293,9 +289,6 @@ def run_bo_case(name):
     print("%-24s suggestions %s" % (name, np.array2string(np.asarray(traj)[:, 0], precision=6)))
 
 
-if __name__ == "__main__":
-    for name in BO_CASES:
-        run_bo_case(name)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -357,8 +350,6 @@ def run_embed_f32():
     np.savez_compressed(os.path.join(OUT, "refembed_f32.npz"), **out)
 
 
-if __name__ == "__main__":
-    run_embed_f32()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -383,8 +374,6 @@ def run_acquisition():
     np.savez_compressed(os.path.join(OUT, "refacq.npz"), **out)
 
 
-if __name__ == "__main__":
-    run_acquisition()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -425,8 +414,6 @@ def run_meta_features():
     np.savez_compressed(os.path.join(OUT, "refmeta.npz"), **out)
 
 
-if __name__ == "__main__":
-    run_meta_features()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -470,8 +457,6 @@ def run_loaders():
     np.savez_compressed(os.path.join(OUT, "refdata.npz"), **out)
 
 
-if __name__ == "__main__":
-    run_loaders()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -501,8 +486,6 @@ def run_toy_tasks():
     np.savez_compressed(os.path.join(OUT, "reftoy.npz"), **out)
 
 
-if __name__ == "__main__":
-    run_toy_tasks()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -572,8 +555,6 @@ def run_bo_parkinson():
     print("bo_parkinson suggestions\n%s" % np.array2string(np.asarray(traj), precision=6))
 
 
-if __name__ == "__main__":
-    run_bo_parkinson()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -631,8 +612,6 @@ def run_config5():
     g.close()
 
 
-if __name__ == "__main__":
-    run_config5()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -717,8 +696,6 @@ def run_bo_counter_manual():
                                                                 np.array2string(np.asarray(traj), precision=4)))
 
 
-if __name__ == "__main__":
-    run_bo_counter_manual()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -795,5 +772,23 @@ def run_bo_protein():
     print("bo_protein suggestions\n%s" % np.array2string(np.asarray(traj), precision=6))
 
 
-if __name__ == "__main__":
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    if "--bo-only" not in sys.argv:
+        for name in CASES:
+            run_case(name)
+    for name in BO_CASES:
+        run_bo_case(name)
+    run_embed_f32()
+    run_acquisition()
+    run_meta_features()
+    run_loaders()
+    run_toy_tasks()
+    run_bo_parkinson()
+    run_config5()
+    run_bo_counter_manual()
     run_bo_protein()
+
+
+if __name__ == "__main__":
+    main()
