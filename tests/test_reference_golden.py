@@ -544,3 +544,30 @@ def test_oracle_protein_bo_trajectory_matches_reference():
 def test_cuda_protein_bo_trajectory_matches_reference(cuda_engine_mod):
     from distbo_b200.train import gp_regressor
     run_bo_protein(gp_regressor)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# observation store vs the reference's TargetSpace (bayes_opt/target_space.py): tests/golden/reftargetspace.npz
+def test_target_space_matches_reference():
+    from distbo_b200.bayes_opt.target_space import TargetSpace
+    z = np.load(os.path.join(GOLD, "reftargetspace.npz"))
+    calls = []
+
+    def f(a, b, c):
+        calls.append((a, b, c))
+        return a * b - c
+    sp = TargetSpace(f, {'b': (0, 1), 'a': (-2.0, 3.0), 'c': (10, 20)}, random_state=4)
+    assert [str(k) for k in sp.keys] == [str(k) for k in z["keys"]]      # dict order, not sorted (target_space.py:47)
+    pts = sp.random_points(6)
+    assert np.array_equal(np.asarray(pts), z["points"])
+    ys = [sp.observe_point(x) for x in pts]
+    assert np.array_equal(np.asarray(ys), z["ys"])
+    sp.observe_point(pts[2])
+    sp.add_observation(np.array([0.5, 1.0, 15.0]), 7.0)
+    sp.set_bounds({'a': (-1.0, 1.0)})
+    assert np.array_equal(np.asarray(sp.random_points(3)), z["more"])
+    assert len(calls) == int(z["n_calls"])
+    assert np.array_equal(sp.X, z["X"]) and np.array_equal(sp.Y, z["Y"]) and np.array_equal(sp.bounds, z["bounds"])
+    mp = sp.max_point()
+    assert mp['max_val'] == float(z["max_val"])
+    assert np.array_equal(np.asarray([mp['max_params'][k] for k in sp.keys]), z["max_params"])

@@ -772,6 +772,30 @@ def run_bo_protein():
     print("bo_protein suggestions\n%s" % np.array2string(np.asarray(traj), precision=6))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# observation store: the reference's bayes_opt/target_space.py TargetSpace (np.float alias restored above)
+def run_target_space():
+    from distBO.bayes_opt.target_space import TargetSpace
+    calls = []
+
+    def f(a, b, c):
+        calls.append((a, b, c))
+        return a * b - c
+    sp = TargetSpace(f, {'b': (0, 1), 'a': (-2.0, 3.0), 'c': (10, 20)}, random_state=4)
+    pts = sp.random_points(6)
+    ys = [sp.observe_point(x) for x in pts]
+    sp.observe_point(pts[2])                               # cached: no second evaluation
+    sp.add_observation(np.array([0.5, 1.0, 15.0]), 7.0)
+    sp.set_bounds({'a': (-1.0, 1.0)})
+    more = sp.random_points(3)
+    mp = sp.max_point()
+    out = {"keys": np.asarray(sp.keys), "bounds": sp.bounds, "points": np.asarray(pts), "ys": np.asarray(ys),
+           "n_calls": np.asarray(len(calls)), "X": sp.X, "Y": sp.Y, "more": np.asarray(more),
+           "max_val": np.asarray(mp['max_val']), "max_params": np.asarray([mp['max_params'][k] for k in sp.keys])}
+    np.savez_compressed(os.path.join(OUT, "reftargetspace.npz"), **out)
+    print("target space: keys %s, %d evaluations, %d rows" % (list(sp.keys), len(calls), len(sp.X)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--bo-only" not in sys.argv:
@@ -788,6 +812,7 @@ def main():
     run_config5()
     run_bo_counter_manual()
     run_bo_protein()
+    run_target_space()
 
 
 if __name__ == "__main__":
