@@ -12,8 +12,8 @@ Follows, in order (file:line relative to the reference repository):
   train/gp_regressor.py:70-74,153-156,179-196   how gp_regressor drives it
 
 Parity: the reference ships no tests and TF 1.7 cannot run here; tests/test_reference_golden.py pins this file
-against numbers the reference's own log_gaus_likelihood_feature.py produces over a TF op shim (ref_blr_*.npz,
-num_of_rff = 0 as shipped).  Further pins in tests/test_oracle.py:
+against numbers the reference's own log_gaus_likelihood_feature.py produces over a TF op shim (ref_blr_*.npz:
+num_of_rff = 0 as shipped, and one case with the random Fourier map).  Further pins in tests/test_oracle.py:
 the loss equals -2 log N(y | 0, sigma^2 I + alpha Phi Phi^T) - N log 2 pi (scipy), the posterior equals the
 textbook weight-space posterior, and the random Fourier map converges to sklearn's Matern(nu=1.5) (the
 author's own check, RandomFourierMaternFeatureMapper.py:69-82).

@@ -50,6 +50,9 @@ def load_case(name):
 
 
 def check(reg, z, meta, fit, final, get_param, tol):
+    # the random Fourier block runs in float32 inside the reference (feature_map.py:20-25): its posterior agrees to
+    # fp32 rounding of cos / matmul between libraries, not to 1e-9
+    pred_tol = 1e-5 if fit.get("num_of_rff") else tol
     loss = reg.maximise_likhd(z["theta"], z["y"], **fit)
     want = z["loss_log"]
     assert len(reg.loss_history) == len(want)
@@ -65,7 +68,8 @@ def check(reg, z, meta, fit, final, get_param, tol):
     reg.initialise_predict()
     mean, std = reg.predict_y(z["cand"], compute_embed=True)
     assert mean.shape == z["pred_mean"].shape and std.shape == z["pred_std"].shape
-    assert rel(mean, z["pred_mean"]) < tol
+    assert rel(mean, z["pred_mean"]) < pred_tol
+    tol = pred_tol
     # variance relative to the prior scale: exp(log_scale) for the GP, alpha |phi|^2 ~ the largest variance for BLR
     scale = float(np.exp(np.asarray(final["log_scale"]).reshape(-1)[0])) if "log_scale" in final else \
         float(np.max(z["pred_std"] ** 2))
@@ -95,6 +99,10 @@ def test_cuda_reproduces_reference(cuda_engine_mod, name):
     z, meta, common, fit, init, final = load_case(name)
     g = gp_regressor(meta["kernel"], **common)
     g.initial_weights = init
+    if fit.get("num_of_rff"):        # not on the sm_100a path: refused loudly, no CPU fallback
+        with pytest.raises(NotImplementedError):
+            g.maximise_likhd(z["theta"], z["y"], **fit)
+        return
     check(g, z, meta, fit, final, lambda k: g.engine.params.get(k) if g.engine.params.has(k) else None, 1e-8)
     g.close()
 

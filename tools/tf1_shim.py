@@ -306,6 +306,8 @@ log = _unary(torch.log)
 sqrt = _unary(torch.sqrt)
 square = _unary(torch.square)
 tanh = _unary(torch.tanh)
+cos = _unary(torch.cos)
+sin = _unary(torch.sin)
 ones_like = _unary(torch.ones_like)
 
 
