@@ -390,12 +390,22 @@ def test_cuda_parkinson_bo_trajectory_matches_reference(cuda_engine_mod):
 # ---------------------------------------------------------------------------------------------------------------
 # The headline configuration at full size (N = 8192, 64 tasks, d_theta = 8, P = 23) through the reference's
 # gp_regressor: tests/golden/refconfig5.npz (outputs only; the inputs are bench.make_workload's seeded streams)
-def run_config5(make_regressor, tol):
+# Two files: refconfig5.npz (sigma^2 = 1e-2, 256 posterior candidates) and refconfig5_s1e-5.npz (the reference's
+# DEFAULT noise sigma^2 = 1e-5 + 1e-6 jitter, experiments/train_test.py:79, 4096 posterior candidates, with
+# cond(K_sigma) of the matrix the reference factorises recorded in the file).
+CONFIG5 = {"s1e-2": ("refconfig5.npz", 1e-2, 256), "s1e-5": ("refconfig5_s1e-5.npz", 1e-5, 4096)}
+
+
+def run_config5(make_regressor, tol, variant="s1e-2"):
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
     import bench
-    z = np.load(os.path.join(GOLD, "refconfig5.npz"))
-    work = bench.make_workload(bench.N_OBS, 256, 1000)
+    fname, lkh_var, n_cand = CONFIG5[variant]
+    z = np.load(os.path.join(GOLD, fname))
+    if "lkh_var_init" in z.files:
+        assert float(z["lkh_var_init"]) == lkh_var
+        assert 1.0 < float(z["cond_K_sigma"]) < 1e12
+    work = bench.make_workload(bench.N_OBS, n_cand, 1000)
     T = bench.T_SRC
     X = [work["data_X"][t][:1000 - 3 * t] for t in range(T + 1)]
     Y = [work["data_Y"][t][:1000 - 3 * t] for t in range(T + 1)]
@@ -406,7 +416,7 @@ def run_config5(make_regressor, tol):
         work["theta"], work["y"][:, None], data_X=X[:T], data_Y=Y[:T],
         source_embed_ind=[np.arange(len(x)) for x in X[:T]], embed_op="joint", algorithm="GP", weight_dim_x=[20, 10],
         weight_dim_y=[20, 10], batch_size=1000, sizes=work["sizes"], concat_data_size=True, learning_rate=0.005,
-        max_epochs=2, max_size=1000, likhd_var_init=1e-2, stratify=False, gradient_clip=False,
+        max_epochs=2, max_size=1000, likhd_var_init=lkh_var, stratify=False, gradient_clip=False,
         first_early_stop_epoch=10 ** 9)
     assert rel(reg.loss_history, z["loss_log"]) < tol
     assert abs(loss - float(z["final_loss"])) <= tol * abs(float(z["final_loss"]))
@@ -432,19 +442,21 @@ def run_config5(make_regressor, tol):
     return reg
 
 
-def test_oracle_reproduces_reference_at_config5_full_size():
-    o = run_config5(OracleGPRegressor, 1e-9)
-    z = np.load(os.path.join(GOLD, "refconfig5.npz"))
+@pytest.mark.parametrize("variant", sorted(CONFIG5))
+def test_oracle_reproduces_reference_at_config5_full_size(variant):
+    o = run_config5(OracleGPRegressor, 1e-9, variant)
+    z = np.load(os.path.join(GOLD, CONFIG5[variant][0]))
     for k in z.files:
         if k.startswith("final__"):      # parameters after two Adam steps: the full-size gradient is the reference's
             assert rel(np.asarray(o.p[k[7:]]).reshape(-1), z[k].reshape(-1)) < 1e-9, k
 
 
 @pytest.mark.gpu
-def test_cuda_reproduces_reference_at_config5_full_size(cuda_engine_mod):
+@pytest.mark.parametrize("variant", sorted(CONFIG5))
+def test_cuda_reproduces_reference_at_config5_full_size(cuda_engine_mod, variant):
     from distbo_b200.train import gp_regressor
-    g = run_config5(gp_regressor, 1e-8)
-    z = np.load(os.path.join(GOLD, "refconfig5.npz"))
+    g = run_config5(gp_regressor, 1e-8, variant)
+    z = np.load(os.path.join(GOLD, CONFIG5[variant][0]))
     for k in z.files:
         if k.startswith("final__") and g.engine.params.has(k[7:]):
             assert rel(g.engine.params.get(k[7:]).reshape(-1), z[k].reshape(-1)) < 1e-8, k

@@ -268,6 +268,7 @@ class Session(object):
         self.loss_log = []           # the second fetch of every [optimize_step, loss] run (train/train.py:49-50)
 
     def run(self, fetches, feed_dict=None):
+        self.last_feed = feed_dict
         env = {}
         for k, v in (feed_dict or {}).items():
             if v is None:
