@@ -289,12 +289,13 @@ def run_cuda(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- fit: loss + full gradient + Adam, one GPU (rank 0), replicas elsewhere idle
+    # ---------------- fit: loss + full gradient + Adam on ONE GPU.  Every rank makes the same product call; inside
+    # it the fitting rank (gp.fit_rank = 0) runs the Adam loop and the others wait for its result
     fit = {}
+    # >= 20 untimed epochs (first eager, second captured as a CUDA graph, the rest replays) so that the clocks
+    # have ramped, then >= 20 timed graph replays with no host synchronisation in between
+    gp.maximise_likhd(work["theta"], work["y"][:, None], **fit_kwargs(work, max(Wm, args.fit_epochs), args.lkh_var))
     if rank == 0:
-        # >= 20 untimed epochs (first eager, second captured as a CUDA graph, the rest replays) so that the
-        # clocks have ramped, then >= 20 timed graph replays with no host synchronisation in between
-        gp.maximise_likhd(work["theta"], work["y"][:, None], **fit_kwargs(work, max(Wm, args.fit_epochs), args.lkh_var))
         torch.cuda.synchronize()
         lib.distbo_launch_count(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -307,28 +308,19 @@ def run_cuda(args):
         loss = gp.engine.read_loss()
         fit_ms = e0.elapsed_time(e1) / kf
         fit = {"fit_ms": fit_ms, "fit_epochs_timed": kf, "fit_mode": "cuda_graph_replay" if gp._graph is not None else "eager",
-               "nll": loss}
-    else:
-        gp.maximise_likhd(work["theta"], work["y"][:, None], **fit_kwargs(work, 1, args.lkh_var))
+               "nll": loss, "lkh_var_init": args.lkh_var}
     barrier()
 
-    # ---------------- handoff: posterior state on rank 0, broadcast to the scoring ranks
-    gp._fit_generation += 1
-    gp._prepare_predict()          # first hand-off also stages the prediction sample sets (one-time)
-    eng = gp.engine
-    gp.shards.broadcast_fit([eng.W, eng.V, eng.theta_s, eng.sqnorm, eng.kvec, eng.params.flat], src=0)   # untimed:
-    #                                NCCL sets up its channels / buffers on the first broadcast of this size
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    # ---------------- fit -> score hand-off, performed by the product API itself (gp_regressor.refresh_posterior =
+    # what the first predict_y / acquire after a fit does): posterior state on the fitting rank, broadcast of
+    # W = L^-1, V, scaled theta, kvec, parameters, task Gram to the scoring ranks
+    gp.refresh_posterior()         # untimed: stages the prediction sample sets; NCCL sets up its channels
     torch.cuda.synchronize()
-    e0.record()
-    gp._fit_generation += 1
-    gp._prepare_predict()
-    e1.record()
+    barrier()
+    hand = gp.refresh_posterior()
+    refresh_ms, bcast_ms, bcast_bytes = hand["refresh_ms"], hand["bcast_ms"], hand["bytes"]
+    refresh_ms, bcast_ms = max_over_ranks(refresh_ms), max_over_ranks(bcast_ms)
     eng = gp.engine
-    gp.shards.broadcast_fit([eng.W, eng.V, eng.theta_s, eng.sqnorm, eng.kvec, eng.params.flat], src=0)
-    e2.record()
-    torch.cuda.synchronize()
-    refresh_ms, bcast_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
 
     # ---------------- scoring, candidates resident in HBM
     lo, hi = gp.shards.range(M)
@@ -512,9 +504,12 @@ def run_cuda(args):
                     "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 16 * world,
                     "api": "UtilityFunction.argmax(x_tries_host, gp, y_max) -> gp_regressor.acquire"},
             "gpu_launches": launches, "clocks": clk,
-            "handoff": {"refresh_ms": refresh_ms, "broadcast_ms": bcast_ms,
-                        "what": "embed 65 full sample sets + task Gram + K + POTRF + TRTRI + V, then NCCL "
-                                "broadcast of W, V, theta, kvec"},
+            "handoff": {"refresh_ms": refresh_ms, "broadcast_ms": bcast_ms, "broadcast_bytes": bcast_bytes,
+                        "api": "gp_regressor.refresh_posterior() = what the first acquire / predict_y after "
+                               "maximise_likhd performs on every rank",
+                        "what": "fitting rank: embed 65 full sample sets + task Gram + K + POTRF + TRTRI + V; then "
+                                "torch.distributed broadcast of W, V, theta, kvec, parameters, task Gram to the "
+                                "scoring ranks (max over ranks, CUDA events inside the product call)"},
             "best": {"index": best_resident[1], "value": best_resident[0]}, "blr": blr, "k1_embed": k1}
     line.update(fit)
     print(json.dumps(line), flush=True)

@@ -52,7 +52,7 @@ SIGNATURES = {
     "distbo_blr_score_blocks": (_i, []),
     "distbo_blr_score_f64": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp,
                                   _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "distbo_adam_f64": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _i64, _d, _vp, _vp]),
+    "distbo_adam_f64": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _i64, _d, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "distbo_score_chunk": (_i, []),
     "distbo_score_workspace": (_i64, [_i]),
     "distbo_score_timing": (_i, [_i]),

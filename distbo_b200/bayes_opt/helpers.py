@@ -93,14 +93,162 @@ def _as_utility(ac):
     return owner if isinstance(owner, UtilityFunction) else None
 
 
+class LockstepEvaluator(object):
+    """One device call for the pending evaluations of SEVERAL optimiser threads.
+
+    Each L-BFGS-B run of the polish lives in its own thread and calls `evaluate(X)` (rows = points it needs now);
+    the call blocks until every still-running thread is waiting, then the last one to arrive evaluates the
+    concatenation of all requests with ONE call of `f_batch` and hands every thread its slice.  An evaluation
+    depends only on its own row (the scoring kernel treats candidates independently), so each run sees exactly
+    the numbers it would see alone - the batching changes the number of device calls, not a single bit."""
+
+    def __init__(self, f_batch, n_threads):
+        import threading
+        self.f_batch = f_batch
+        self.cv = threading.Condition()
+        self.active = n_threads
+        self.requests = {}          # thread ident -> X
+        self.results = {}
+        self.calls = 0              # device calls made
+        self.points = 0             # rows evaluated
+        self.error = None
+
+    def _flush(self):
+        """Caller holds the lock and every active thread has a request pending."""
+        order = sorted(self.requests)
+        X = np.concatenate([self.requests[k] for k in order], axis=0)
+        try:
+            vals = np.reshape(np.asarray(self.f_batch(X), dtype=np.float64), -1)
+        except BaseException as exc:      # hand the failure to every waiting thread
+            self.error = exc
+            vals = np.full(len(X), np.nan)
+        self.calls += 1
+        self.points += len(X)
+        pos = 0
+        for k in order:
+            n = len(self.requests[k])
+            self.results[k] = vals[pos:pos + n]
+            pos += n
+        self.requests.clear()
+        self.cv.notify_all()
+
+    def evaluate(self, X):
+        import threading
+        me = threading.get_ident()
+        with self.cv:
+            self.requests[me] = np.atleast_2d(np.asarray(X, dtype=np.float64))
+            if len(self.requests) == self.active:
+                self._flush()
+            while me not in self.results:
+                self.cv.wait()
+            out = self.results.pop(me)
+            if self.error is not None:
+                raise self.error
+            return out
+
+    def retire(self):
+        with self.cv:
+            self.active -= 1
+            if self.active > 0 and len(self.requests) == self.active:
+                self._flush()
+
+
+class _SpeculativeObjective(object):
+    """Negated acquisition for one L-BFGS-B run, evaluated through a LockstepEvaluator.
+
+    scipy estimates the gradient with its forward-difference stencil (eps given, steps flipped at the upper
+    bound): d more evaluations after every f(x).  `fun` asks for x TOGETHER with the d stencil points it expects
+    scipy to want next and keeps them; `map` (handed to scipy as its `workers` map, so the stencil is scipy's own,
+    point for point) serves them from that cache and evaluates only what is missing.  A wrong guess costs one more
+    call, never a different number."""
+
+    def __init__(self, evaluator, bounds, eps):
+        self.ev, self.lo, self.hi, self.eps = evaluator, bounds[:, 0], bounds[:, 1], eps
+        self.cache = {}
+
+    def _stencil(self, x):
+        pts = []
+        for i in range(x.size):
+            p = x.copy()
+            h = self.eps
+            if x[i] + h > self.hi[i] and x[i] - h >= self.lo[i]:
+                h = -h
+            p[i] = x[i] + h
+            pts.append(p)
+        return pts
+
+    def fun(self, x):
+        x = np.asarray(x, dtype=np.float64).ravel()
+        hit = self.cache.get(x.tobytes())
+        if hit is not None:
+            return hit
+        pts = [x] + self._stencil(x)
+        vals = self.ev.evaluate(np.stack(pts))
+        self.cache = {p.tobytes(): -float(v) for p, v in zip(pts, vals)}
+        return self.cache[x.tobytes()]
+
+    def map(self, wrapped_fun, xs):
+        xs = [np.asarray(x, dtype=np.float64).ravel() for x in xs]
+        missing = [x for x in xs if x.tobytes() not in self.cache]
+        if missing:
+            vals = self.ev.evaluate(np.stack(missing))
+            for p, v in zip(missing, vals):
+                self.cache[p.tobytes()] = -float(v)
+        return [self.cache[x.tobytes()] for x in xs]
+
+
+POLISH_STATS = {"device_calls": 0, "points": 0, "runs": 0}    # cumulative, for profiles/ (tools/probe_polish.py)
+
+
+def _polish_runs_batched(ac, gp, y_max, x_seeds, bounds, eps, maxfun):
+    """The L-BFGS-B runs of `_polish`, all seeds in lock-step on the fused device path: one `gp.acquire`-style call
+    serves the pending evaluations of every run (value + scipy's finite-difference stencil)."""
+    import threading
+    seeds = [np.ravel(x) for x in x_seeds]
+    ev = LockstepEvaluator(lambda X: ac(X, gp=gp, y_max=y_max), len(seeds))
+    results = [None] * len(seeds)
+
+    def run(k):
+        try:
+            obj = _SpeculativeObjective(ev, np.asarray(bounds, dtype=np.float64), eps)
+            results[k] = minimize(obj.fun, seeds[k], bounds=bounds, method="L-BFGS-B",
+                                  options={'eps': eps, 'ftol': 1e-04, 'maxfun': maxfun, 'maxls': 10,
+                                           'workers': obj.map})
+        except BaseException as exc:
+            results[k] = exc
+        finally:
+            ev.retire()
+    threads = [threading.Thread(target=run, args=(k,), daemon=True) for k in range(len(seeds))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for r in results:
+        if isinstance(r, BaseException):
+            raise r
+    POLISH_STATS["device_calls"] += ev.calls
+    POLISH_STATS["points"] += ev.points
+    POLISH_STATS["runs"] += len(seeds)
+    return results
+
+
+def _polish_runs_serial(ac, gp, y_max, x_seeds, bounds, eps, maxfun):
+    """One L-BFGS-B run after the other, one single-point evaluation per function value (helpers.py:70-86)."""
+    return [minimize(lambda x: -float(np.squeeze(ac(x.reshape(1, -1), gp=gp, y_max=y_max))), np.ravel(x_try),
+                     bounds=bounds, method="L-BFGS-B",
+                     options={'eps': eps, 'ftol': 1e-04, 'maxfun': maxfun, 'maxls': 10}) for x_try in x_seeds]
+
+
 def _polish(ac, gp, y_max, x_seeds, bounds, evaluatedX, x_max, max_acq, eps, maxfun):
     """L-BFGS-B from each seed with finite-difference gradients (helpers.py:70-86 / :94-107).  A result
     replaces the incumbent only when `evaluatedX` is given and shares no coordinate value with it -
-    the reference's `res.x not in evaluatedX` is numpy's element-wise membership test."""
-    for x_try in x_seeds:
-        res = minimize(lambda x: -float(np.squeeze(ac(x.reshape(1, -1), gp=gp, y_max=y_max))), np.ravel(x_try),
-                       bounds=bounds, method="L-BFGS-B",
-                       options={'eps': eps, 'ftol': 1e-04, 'maxfun': maxfun, 'maxls': 10})
+    the reference's `res.x not in evaluatedX` is numpy's element-wise membership test.  On the fused device
+    path the runs advance in lock-step and share their device calls (LockstepEvaluator); the runs themselves,
+    their stencils and the order in which their results are compared are the reference's."""
+    util = _as_utility(ac)
+    batched = util is not None and util._fused(gp) and getattr(gp.shards, "world", 1) == 1 and len(x_seeds) > 0
+    runs = (_polish_runs_batched if batched else _polish_runs_serial)(ac, gp, y_max, x_seeds, bounds, eps, maxfun)
+    for res in runs:
         if not res.success:
             continue
         value = -float(np.squeeze(res.fun))

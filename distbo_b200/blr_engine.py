@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import ACQ, D_MAX, GPEngine, ParamStore, _stream, net_param_shapes
+from .engine import ACQ, D_MAX, GPEngine, ParamStore, _stream, net_param_shapes, on_device
 
 BLR_W = 64          # widest layer the kernels take (blr.cu)
 
@@ -32,6 +32,9 @@ class BLREngine(GPEngine):
             raise ValueError("d_theta = %d: 1 <= d_theta <= %d" % (int(d_theta), D_MAX))
         self.lib = _lib.load()
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        self._plan = None
         self.d = int(d_theta)
         self.P = int(n_embed)            # width of the embedding part of a feature row (0: kernel 'params')
         self.net = net
@@ -67,6 +70,7 @@ class BLREngine(GPEngine):
         self._ws = None
         self.emb_target = None           # [P] embedding of the candidates' task
 
+    @on_device
     def set_observations(self, theta, y, sizes=None):
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
@@ -94,6 +98,7 @@ class BLREngine(GPEngine):
         return (w("weights__1"), w("bias__1"), w("weights__2"), w("bias__2"), w("weights__3"), self.n_layers,
                 self.h1, self.h2, self.D)
 
+    @on_device
     def fit(self, E, want_grad=True):
         """Loss (into self.nll), Linv, e and - with want_grad - the gradient of every BLR parameter and
         dE = d loss / d E  (one evaluation of net.loss and tf.gradients, log_gaus_likelihood_feature.py:107-143)."""
@@ -110,6 +115,7 @@ class BLREngine(GPEngine):
             1 if want_grad else 0, _stream())
         _lib.check(rc, "distbo_blr_fit_f64")
 
+    @on_device
     def loss_and_grad(self, X=None, Y=None, seg_off=None, E_const=None, size_ratio=None):
         """One evaluation of the BLR loss and its full gradient, queued on the current stream.
         kernel 'dist': X, Y, seg_off = this step's embedding mini-batch (size_ratio fills the last column);
@@ -128,12 +134,14 @@ class BLREngine(GPEngine):
         if self.net is not None:
             self.embed_backward(X, Y, seg_off, self.dE)
 
+    @on_device
     def prepare_posterior(self, E, emb_target):
         """Linv and e at the current parameters for features built from E [T,P]; emb_target [P] is the embedding
         part of every candidate's feature row (build_predict_feature / build_predict_dist_feature, :145-225)."""
         self.fit(E, want_grad=False)
         self.emb_target = emb_target
 
+    @on_device
     def score(self, theta_c, acq="ei", y_max=0.0, xi=0.0, kappa=1.0, want_arrays=True, index_offset=0,
               kvec=None, scaler=None):
         if not torch.is_tensor(theta_c):

@@ -634,21 +634,11 @@ static bool blr_net_ok(const BlrNet& n) {
   return true;
 }
 
-static int g_blr_sms = 0;
-static int blr_sms() {
-  if (g_blr_sms == 0) {
-    int dev = 0;
-    cudaDeviceProp prop;
-    g_blr_sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
-      g_blr_sms = prop.multiProcessorCount;
-  }
-  return g_blr_sms;
-}
+static int blr_sms() { return device_sm_count(); }
 
 static int blr_configure() {
-  static bool done = false;
-  if (!done) {
+  static PerDeviceOnce once;
+  if (once.needed()) {
     DB_CUDA(cudaFuncSetAttribute(blr_rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLR_SMEM_BYTES));
     DB_CUDA(cudaFuncSetAttribute(blr_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLR_SMEM_BYTES));
     DB_CUDA(cudaFuncSetAttribute(blr_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLR_SMEM_BYTES));
@@ -656,7 +646,7 @@ static int blr_configure() {
                                  (int)((BLR_R * BLR_LD + BLR_R * BLR_W) * sizeof(double))));
     DB_CUDA(cudaFuncSetAttribute(blr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((4 * BLR_W * BLR_W + 3 * BLR_W + BLR_THREADS) * sizeof(double))));
-    done = true;
+    once.mark();
   }
   return DISTBO_OK;
 }

@@ -97,11 +97,27 @@ struct Plan {
 // The chain update -> potf2 -> solve therefore costs one launch, no global round trip of the tile, and the
 // solve / next-diagonal update overlap the factorisation.  Waiting CTAs only ever wait for block 0 of their
 // own grid (<= 64 CTAs, all resident on 148 SMs).
-__device__ __forceinline__ void wait_flag(int* f) {
-  if (threadIdx.x == 0) {
-    while (atomicAdd(f, 0) == 0) __nanosleep(64);
-    __threadfence();
+//
+// Every inter-CTA wait is BOUNDED: the producers a CTA waits for are co-resident in practice (lower block
+// indices of the same grid, dispatched first, everything fits on the device), but a plain launch does not
+// guarantee that.  If a flag does not arrive within SPIN_LIMIT polls (>= 64 ns each, i.e. >= ~0.5 s - five orders
+// of magnitude above the longest legitimate wait) the waiter records DISTBO_INFO_TIMEOUT in `info` and goes on;
+// the factor is then garbage, and the host raises on the non-zero info exactly as for a failed pivot, so a
+// scheduling surprise is an error instead of a hung GPU.
+constexpr int SPIN_LIMIT = 1 << 23;
+__device__ __noinline__ void spin_until_set(int* f, int32_t* info) {
+  int polls = 0;
+  while (atomicAdd(f, 0) == 0) {
+    __nanosleep(64);
+    if (++polls > SPIN_LIMIT) {
+      if (info) atomicExch(info, DISTBO_INFO_TIMEOUT);
+      break;
+    }
   }
+  __threadfence();
+}
+__device__ __forceinline__ void wait_flag(int* f, int32_t* info) {
+  if (threadIdx.x == 0) spin_until_set(f, info);
   __syncthreads();
 }
 
@@ -134,7 +150,8 @@ constexpr int NFLAG = 4;   // per column block: the four sub-step flags of the d
 // and stores it to Pout [128][128] (the next launch's diagonal tile takes its update from there).
 template <bool RELAY>
 __device__ __forceinline__ void stepwise_solve(double* smem, const double* A, const double* W, int ld, int n0,
-                                               const int* sub, double* Ab, int* xflags, double* Pout) {
+                                               const int* sub, double* Ab, int* xflags, double* Pout,
+                                               int32_t* info) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
   const int lr = lane >> 2, lk = lane & 3;
@@ -153,10 +170,7 @@ __device__ __forceinline__ void stepwise_solve(double* smem, const double* A, co
   }
   for (int sb = 0; sb < 4; ++sb) {
     const int c0 = sb * SB;
-    if (tid == 0) {
-      while (atomicAdd(const_cast<int*>(sub) + sb, 0) == 0) __nanosleep(64);
-      __threadfence();
-    }
+    if (tid == 0) spin_until_set(const_cast<int*>(sub) + sb, info);
     __syncthreads();                        // flag seen; previous step's staging buffers are free
     for (int idx = tid; idx < SB * c0; idx += GEMM_THREADS) {
       const int r = idx / c0, c = idx - r * c0;
@@ -290,12 +304,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
     const int k_hi = (diag && p.use_relay) ? n0 - BN : n0;
     if (p.done && kb >= 1 && p.pend_lo <= kb - 1 && k_hi == n0) {
       // panel kb-1 may still be running (older panels are complete: same stream): its rows i and kb
-      wait_flag(p.done + (kb - 1) * nb + i);
-      if (!diag) wait_flag(p.done + (kb - 1) * nb + kb);
+      wait_flag(p.done + (kb - 1) * nb + i, p.info);
+      if (!diag) wait_flag(p.done + (kb - 1) * nb + kb, p.info);
     }
     if (p.pend_lo * BN < k_hi) gemm_mainloop<KMAJOR, KMAJOR>(acc, p.A, ld, p.A, ld, m0, n0, p.pend_lo * BN, k_hi, smem);
     if (diag && p.use_relay) {
-      if (p.relay_ready) wait_flag(p.relay_ready + kb);
+      if (p.relay_ready) wait_flag(p.relay_ready + kb, p.info);
       const double* P = p.relay + (size_t)(kb & 1) * PB * PB;
 #pragma unroll
       for (int mi = 0; mi < 8; ++mi) {
@@ -342,8 +356,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
     {
       const bool relay = p.relay && blockIdx.x == 1 && i == kb + 1;
       const int* sub = p.flags + kb * NFLAG;
-      if (relay) stepwise_solve<true>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, p.relay + (size_t)((kb + 1) & 1) * PB * PB);
-      else stepwise_solve<false>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, nullptr);
+      if (relay) stepwise_solve<true>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, p.relay + (size_t)((kb + 1) & 1) * PB * PB, p.info);
+      else stepwise_solve<false>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, nullptr, p.info);
       if (p.done && tid == 0) {   // stepwise_solve ended with a barrier: cumulative fence, then publish
         __threadfence();
         atomicExch(p.done + kb * nb + i, 1);
@@ -406,15 +420,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_small_kernel(SmallArgs 
   }
   const int c_hi = (diag && c >= 1) ? c - 1 : c;   // a diagonal owner takes panel c-1 progressively (below)
   for (int cp = 0; cp < c_hi; ++cp) {
-    wait_flag(p.done + r * nbt + cp);
-    if (!diag) wait_flag(p.done + c * nbt + cp);
+    wait_flag(p.done + r * nbt + cp, p.info);
+    if (!diag) wait_flag(p.done + c * nbt + cp, p.info);
     gemm_mainloop<KMAJOR, KMAJOR>(acc, p.A, ld, p.A, ld, m0, n0, cp * BN, (cp + 1) * BN, smem);
   }
   if (diag && c >= 1) {
     double* sX = smem;                    // [128][DLD] column group of L[c,c-1]
     const double* Lrow = p.A + (size_t)m0 * ld + (size_t)(c - 1) * BN;
     for (int sb = 0; sb < 4; ++sb) {
-      wait_flag(p.xf + (c - 1) * 4 + sb);
+      wait_flag(p.xf + (c - 1) * 4 + sb, p.info);
       for (int q = tid; q < PB * SB; q += GEMM_THREADS) {
         const int rr = q >> 5, cc = q & 31;
         sX[rr * DLD + cc] = __ldcg(Lrow + (size_t)rr * ld + sb * SB + cc);
@@ -457,7 +471,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_small_kernel(SmallArgs 
     potf2_factor_invert(smem, m0, p.info, dbg, Potf2Publish{Ab, Wb, ld, p.sub + c * 4}, false);
     return;
   }
-  stepwise_solve<false>(smem, p.A, p.W, ld, n0, p.sub + c * 4, Ab, (r == c + 1) ? p.xf + c * 4 : nullptr, nullptr);
+  stepwise_solve<false>(smem, p.A, p.W, ld, n0, p.sub + c * 4, Ab, (r == c + 1) ? p.xf + c * 4 : nullptr, nullptr, p.info);
   if (tid == 0) {   // stepwise_solve ended with a barrier: every store of the tile is ordered before this fence
     __threadfence();
     atomicExch(p.done + r * nbt + c, 1);
@@ -799,9 +813,10 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
     DB_CUDA(cudaMemsetAsync(p->d_small_flags, 0, (size_t)(nb * nb + 8 * nb) * sizeof(int), U));
     SmallArgs sa{A, W, n, nb, info, p->d_small_flags, p->d_small_flags + nb * nb, p->d_small_flags + nb * nb + 4 * nb};
     // Plain launch: a CTA only ever waits for CTAs with a LOWER block index (earlier column, or the diagonal of
-    // its own column), blocks are dispatched in index order and all nb (nb + 1) / 2 <= 136 of them fit on the
-    // device at once, so the waits cannot deadlock; the cooperative-launch API gave the same guarantee but made
-    // CUDA-graph replays of the training step ~1 ms slower per launch.
+    // its own column), blocks are dispatched in index order and all nb (nb + 1) / 2 <= 136 of them fit on an idle
+    // device at once.  CUDA does not promise either for a non-cooperative launch (the cooperative API does, but made
+    // CUDA-graph replays of the training step ~1 ms slower per launch), so the waits are bounded (spin_until_set):
+    // if the device is shared and a producer is not resident, info = DISTBO_INFO_TIMEOUT and the host raises.
     potrf_small_kernel<<<nb * (nb + 1) / 2, GEMM_THREADS, PANEL_SMEM, U>>>(sa);
     DB_CHECK_LAUNCH();
     return DISTBO_OK;

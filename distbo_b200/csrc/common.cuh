@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #define DISTBO_OK 0
 #define DISTBO_EARG (-1)
 #define DISTBO_ECUDA (-2)
@@ -24,6 +26,31 @@ extern long long g_db_launches;
   } while (0)
 
 namespace db {
+
+// cudaFuncSetAttribute opt-ins and SM counts are per DEVICE: one-shot guards keyed by the current device ordinal
+// (a process may drive several GPUs).  Thread safe: racing first calls repeat a harmless attribute write.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  int dev = 0;
+  bool needed() {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return !(done.load(std::memory_order_acquire) >> (dev & 63) & 1ull);
+  }
+  void mark() { done.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+
+inline int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int v = cache[dev & 63].load(std::memory_order_relaxed);
+  if (v == 0) {
+    v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev & 63].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 
 // Debug timeline (tools/potrf_timeline.py): when non-null, instrumented kernels record globaltimer stamps
 // into tl[launch_id * 4 + {0: earliest CTA start, 1: latest CTA end, 2, 3: kernel specific}].

@@ -256,12 +256,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tiles_kernel(GemmArgs p)
 template <int ALAY, int BLAY>
 inline cudaError_t launch_gemm_tiles(const GemmArgs& p, int ntiles, cudaStream_t st) {
   if (ntiles <= 0) return cudaSuccess;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.needed()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tiles_kernel<ALAY, BLAY>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, TGEMM_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
+    once.mark();
   }
   gemm_tiles_kernel<ALAY, BLAY><<<2 * ntiles, GEMM_THREADS, TGEMM_SMEM_BYTES, st>>>(p);
   ++g_db_launches;

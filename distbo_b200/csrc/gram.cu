@@ -369,9 +369,27 @@ __global__ void __launch_bounds__(1024) adam_kernel(double* __restrict__ params,
                                                     double* __restrict__ m, double* __restrict__ v,
                                                     long long n, double lr_t_host,
                                                     const double* __restrict__ lr_t_dev, double b1, double b2,
-                                                    double eps, double clip_norm) {
+                                                    double eps, double clip_norm, double* __restrict__ ctrl,
+                                                    const double* __restrict__ nll,
+                                                    const int32_t* __restrict__ info,
+                                                    double* __restrict__ loss_hist, long long hist_cap) {
   __shared__ double red[32];
   __shared__ double gscale;
+  // Training-loop control on the device (train/train.py:43-65), so that the host never reads the loss back
+  // between epochs: once the early-stopping rule has fired (ctrl[STOP] = 1) or a factorisation has failed
+  // (= 2, TF would have raised inside sess.run before applying the update) every later launch is a no-op, and
+  // the parameters stay those of the epoch the reference breaks at.
+  if (ctrl) {
+    if (ctrl[DISTBO_CTRL_STOP] != 0.0) return;
+    const int32_t inf = info ? *info : 0;
+    if (inf != 0) {
+      if (threadIdx.x == 0) {
+        ctrl[DISTBO_CTRL_STOP] = 2.0;
+        ctrl[DISTBO_CTRL_INFO] = (double)inf;
+      }
+      return;
+    }
+  }
   const double lr_t = lr_t_dev ? *lr_t_dev : lr_t_host;
   if (clip_norm > 0.0) {
     double s = 0.0;
@@ -399,6 +417,27 @@ __global__ void __launch_bounds__(1024) adam_kernel(double* __restrict__ params,
     m[i] = mi;
     v[i] = vi;
     params[i] -= lr_t * mi / (sqrt(vi) + eps);
+  }
+  if (ctrl && threadIdx.x == 0) {
+    // this epoch's loss (evaluated BEFORE the update, as sess.run([optimize_step, loss]) returns it) and the
+    // early-stopping rule of train/train.py:53-65: cur_min / countdown start at +inf
+    const double loss = nll ? *nll : 0.0;
+    const long long epoch = (long long)ctrl[DISTBO_CTRL_EPOCHS];
+    if (loss_hist && hist_cap > 0) loss_hist[epoch % hist_cap] = loss;
+    ctrl[DISTBO_CTRL_LAST_LOSS] = loss;
+    ctrl[DISTBO_CTRL_EPOCHS] = (double)(epoch + 1);
+    if ((double)epoch >= ctrl[DISTBO_CTRL_FIRST_EPOCH]) {
+      double cur_min = ctrl[DISTBO_CTRL_CUR_MIN], countdown = ctrl[DISTBO_CTRL_COUNTDOWN];
+      if ((cur_min - loss) > ctrl[DISTBO_CTRL_THRESHOLD]) {
+        countdown = ctrl[DISTBO_CTRL_PATIENCE];
+        cur_min = loss;
+      } else {
+        countdown -= 1.0;
+      }
+      ctrl[DISTBO_CTRL_CUR_MIN] = cur_min;
+      ctrl[DISTBO_CTRL_COUNTDOWN] = countdown;
+      if (countdown <= 0.0) ctrl[DISTBO_CTRL_STOP] = 1.0;
+    }
   }
 }
 
@@ -506,10 +545,10 @@ extern "C" int distbo_gram_f64(const double* theta_s, const double* sqnorm, int 
   if (KE && (!task_id || T <= 0)) return DISTBO_EARG;
   const int nb = n_pad / GT;
   const int smem = (2 * GT * d + 2 * GT) * (int)sizeof(double) + 2 * GT * (int)sizeof(int);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    configured = true;
+  static PerDeviceOnce once;
+  if (once.needed()) {
+    DB_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    once.mark();
   }
   gram_kernel<<<nb * (nb + 1) / 2, 256, smem, (cudaStream_t)stream>>>(theta_s, sqnorm, N, n_pad, d, task_id, KE, T,
                                                                      log_scale, log_sigma, jitter, K);
@@ -581,12 +620,14 @@ extern "C" int distbo_task_tri_bwd_f64(const double* log_tri, int T, const doubl
 
 extern "C" int distbo_adam_f64(double* params, const double* grads, double* m, double* v, int64_t n, double lr,
                                double beta1, double beta2, double eps, int64_t step, double clip_norm,
-                               const double* lr_t_dev, void* stream) {
+                               const double* lr_t_dev, double* ctrl, const double* nll, const int32_t* info,
+                               double* loss_hist, int64_t hist_cap, void* stream) {
   if (!params || !grads || !m || !v || n <= 0 || (step <= 0 && !lr_t_dev)) return DISTBO_EARG;
+  if (ctrl && (!nll || !info || hist_cap < 0)) return DISTBO_EARG;
   const double lr_t =
       lr_t_dev ? 0.0 : lr * sqrt(1.0 - pow(beta2, (double)step)) / (1.0 - pow(beta1, (double)step));
   adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grads, m, v, (long long)n, lr_t, lr_t_dev, beta1, beta2,
-                                                    eps, clip_norm);
+                                                    eps, clip_norm, ctrl, nll, info, loss_hist, (long long)hist_cap);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
 }

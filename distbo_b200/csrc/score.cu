@@ -233,8 +233,6 @@ __global__ void merge_best_kernel(const double* __restrict__ bv, const long long
   *best_idx = i;
 }
 
-static int g_score_chunk = 0;
-
 // Optional per-launch timing of score_kernel (bench.py's roofline figure): CUDA events recorded on
 // the launching stream around every score_kernel launch while enabled.
 static bool g_timing = false;
@@ -285,15 +283,7 @@ extern "C" int64_t distbo_score_workspace(int n_pad) {
 }
 
 extern "C" int distbo_score_chunk(void) {
-  if (g_score_chunk == 0) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) {
-      cudaDeviceProp prop;
-      if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) sms = prop.multiProcessorCount;
-    }
-    g_score_chunk = sms * BN;  // one 128-candidate tile per SM: a single, perfectly balanced wave
-  }
-  return g_score_chunk;
+  return device_sm_count() * BN;  // one 128-candidate tile per SM of the current device: a single, balanced wave
 }
 
 extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_pad, const double* theta_s,
@@ -310,10 +300,10 @@ extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_p
   if (acq_kind < 0 || acq_kind > 2 || ((cand_shift == nullptr) != (cand_scale == nullptr))) return DISTBO_EARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int chunk = distbo_score_chunk();
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.needed()) {
     DB_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TGEMM_SMEM_BYTES));
-    configured = true;
+    once.mark();
   }
   int first = 1;
   for (int64_t c0 = 0; c0 < M; c0 += chunk) {

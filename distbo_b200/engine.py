@@ -14,6 +14,7 @@ Layout in HBM (row-major, fp64 unless noted; n_pad = roundup(N, 128)):
 """
 from __future__ import annotations
 
+import functools
 import math
 
 import numpy as np
@@ -22,6 +23,9 @@ import torch
 from . import _lib
 
 JITTER = 0.000001  # reference train/log_gaus_likelihood.py:122,210
+# slots of the device-side training control block (include/distbo_b200.h DISTBO_CTRL_*)
+CTRL_CUR_MIN, CTRL_COUNTDOWN, CTRL_STOP, CTRL_EPOCHS, CTRL_LAST_LOSS, CTRL_FIRST_EPOCH, CTRL_INFO = range(7)
+CTRL_THRESHOLD, CTRL_PATIENCE, CTRL_SLOTS = 7, 8, 16
 ACQ = {"ei": 0, "ucb": 1, "lcb": 2}
 D_MAX = 16         # gram.cu DMAX / score.cu SCORE_DMAX
 
@@ -34,19 +38,41 @@ def _stream():
     return _lib.C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-class Plans:
-    """One fit plan per (device, n_pad)."""
-    _cache = {}
+def on_device(fn):
+    """Runs an engine method with the engine's device current: kernel launches, stream lookups and the
+    library's per-device state all follow the CURRENT device, not the tensors' device."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        if torch.cuda.current_device() == self.dev.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(self.dev):
+            return fn(self, *a, **kw)
+    return wrapped
 
-    @classmethod
-    def get(cls, n_pad):
-        key = (torch.cuda.current_device(), n_pad)
-        if key not in cls._cache:
-            lib = _lib.load()
-            h = _lib.C.c_void_p()
-            _lib.check(lib.distbo_plan_create(n_pad, _lib.C.byref(h)), "distbo_plan_create")
-            cls._cache[key] = h
-        return cls._cache[key]
+
+class FitPlan:
+    """The factorisation plan of ONE engine (tile lists, internal streams, events, inter-CTA flags and the relay
+    buffer).  A plan carries mutable device state and is single-stream, so engines never share one; it lives on
+    the device that was current when it was created and is destroyed with its engine."""
+
+    def __init__(self, n_pad):
+        self.lib = _lib.load()
+        self.n_pad = n_pad
+        self.device = torch.cuda.current_device()
+        self.handle = _lib.C.c_void_p()
+        _lib.check(self.lib.distbo_plan_create(n_pad, _lib.C.byref(self.handle)), "distbo_plan_create")
+
+    def destroy(self):
+        h, self.handle = self.handle, None
+        if h is not None and self.lib is not None:
+            try:
+                with torch.cuda.device(self.device):
+                    self.lib.distbo_plan_destroy(h)
+            except Exception:       # interpreter shutdown: the driver reclaims everything
+                pass
+
+    def __del__(self):
+        self.destroy()
 
 
 class NetSpec:
@@ -166,6 +192,9 @@ class GPEngine:
                              % (int(d_theta), D_MAX))
         self.lib = _lib.load()
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        self._plan = None
         self.d = int(d_theta)
         self.P = int(n_embed)            # embedding width incl. size-ratio column (0: kernel 'params')
         self.net = net
@@ -194,10 +223,18 @@ class GPEngine:
         self.KE = None
         self.T = 1
 
+    def close(self):
+        """Frees the factorisation plan (streams, events, flag buffers); the tensors go with the object."""
+        if self._plan is not None:
+            self._plan.destroy()
+            self._plan = None
+            self.plan = None
+
     # ------------------------------------------------------------------ buffers
     def _f64(self, *shape):
         return torch.zeros(*shape, dtype=torch.float64, device=self.dev)
 
+    @on_device
     def set_observations(self, theta, y, sizes=None):
         """theta [N,d] (already StandardScaler-transformed), y [N]; sizes = observations per task."""
         theta = np.ascontiguousarray(theta, dtype=np.float64)
@@ -216,7 +253,10 @@ class GPEngine:
             self.alpha = self._f64(n_pad)
             self.kvec = self._f64(n_pad)
             self.nll_ws = self._f64(int(self.lib.distbo_nll_workspace(n_pad)))
-            self.plan = Plans.get(n_pad)
+            if self._plan is not None:
+                self._plan.destroy()
+            self._plan = FitPlan(n_pad)
+            self.plan = self._plan.handle
         self.N = N
         self.theta = torch.from_numpy(theta).to(self.dev)
         self.y = torch.from_numpy(y).to(self.dev)
@@ -245,6 +285,7 @@ class GPEngine:
             self._emb_ws[key] = ws
         return ws
 
+    @on_device
     def embed(self, X, Y, seg_off, out=None, n_rows=None, dtype=torch.float64):
         """K1 forward: X [S,dx], Y [S,dy] device tensors, seg_off int32 [T+1] -> E rows [T, P]."""
         net = self.net
@@ -281,6 +322,7 @@ class GPEngine:
         _lib.check(rc, "distbo_embed_fwd")
         return out
 
+    @on_device
     def embed_backward(self, X, Y, seg_off, dE):
         """K1 backward into the gradient slots of the net weights."""
         net, p = self.net, self.params
@@ -304,6 +346,7 @@ class GPEngine:
         _lib.check(rc, "distbo_embed_bwd_f64")
 
     # ------------------------------------------------------------------ Gram and fit
+    @on_device
     def task_gram(self, E, Tn):
         """KE [Tn,Tn] over the first Tn rows of E (width P)."""
         KE = self._f64(Tn, Tn)
@@ -312,6 +355,7 @@ class GPEngine:
         _lib.check(rc, "distbo_task_gram_f64")
         return KE
 
+    @on_device
     def task_tri(self):
         """Multi-task covariance KE [T,T] from log_triangular_task (train/kernels.py:32-40)."""
         T = self.n_multi
@@ -321,12 +365,14 @@ class GPEngine:
         _lib.check(rc, "distbo_task_tri_f64")
         return KE
 
+    @on_device
     def task_tri_backward(self):
         rc = self.lib.distbo_task_tri_bwd_f64(_lib.ptr(self.params.view("log_triangular_task")), self.n_multi,
                                               _lib.ptr(self.H), _lib.ptr(self.params.gview("log_triangular_task")),
                                               _lib.ptr(self._tri_ws), _stream())
         _lib.check(rc, "distbo_task_tri_bwd_f64")
 
+    @on_device
     def build_gram(self, KE=None):
         p = self.params
         rc = self.lib.distbo_scale_theta_f64(_lib.ptr(self.theta), self.N, self.d, _lib.ptr(p.view("log_bw")),
@@ -339,6 +385,7 @@ class GPEngine:
         _lib.check(rc, "distbo_gram_f64")
         self.KE = KE
 
+    @on_device
     def factorize(self, need_inverse=True, need_kinv=False):
         """K (in self.K) -> L in place; W = L^-1; optionally Kinv = W^T W (into self.Tm)."""
         st = _stream()
@@ -352,12 +399,14 @@ class GPEngine:
             _lib.check(self.lib.distbo_lauum_f64(self.plan, _lib.ptr(self.W), _lib.ptr(self.Tm), st),
                        "distbo_lauum_f64")
 
+    @on_device
     def likelihood(self):
         rc = self.lib.distbo_nll_f64(_lib.ptr(self.K), _lib.ptr(self.W), self.N, self.n_pad, _lib.ptr(self.y),
                                      _lib.ptr(self.params.view("mean")), _lib.ptr(self.V), _lib.ptr(self.alpha),
                                      _lib.ptr(self.nll), _lib.ptr(self.nll_ws), _stream())
         _lib.check(rc, "distbo_nll_f64")
 
+    @on_device
     def gram_gradient(self):
         """Fills the gradient slots of log_bw, log_scale, mean, log_sigma and self.H = dNLL/dKE."""
         p = self.params
@@ -373,6 +422,7 @@ class GPEngine:
         p.gview("mean").copy_(self.gscal[1:2])
         p.gview("log_sigma").copy_(self.gscal[2:3])
 
+    @on_device
     def task_gram_backward(self, E, Tn):
         dE = self._f64(Tn, E.shape[1])
         ws = torch.empty(Tn * self.P, dtype=torch.float64, device=self.dev)
@@ -388,28 +438,43 @@ class GPEngine:
         """TF AdamOptimizer's per-step rate lr * sqrt(1 - beta2^t) / (1 - beta1^t)."""
         return lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
 
-    def adam_step(self, lr, clip_norm=0.0, lr_t_dev=None):
+    @on_device
+    def adam_step(self, lr, clip_norm=0.0, lr_t_dev=None, ctrl=None, loss_hist=None):
         """TF-form Adam update of the flat parameter vector.  With lr_t_dev (device scalar) the launch
         takes its rate from device memory - the form a CUDA graph replays; the caller advances
-        params.step and refreshes the scalar."""
+        params.step and refreshes the scalar.  With ctrl (TrainControl.dev) the same launch also records
+        the epoch's loss and evaluates the early-stopping rule on the device (include/distbo_b200.h)."""
         p = self.params
         if lr_t_dev is None:
             p.step += 1
         rc = self.lib.distbo_adam_f64(_lib.ptr(p.flat), _lib.ptr(p.grad), _lib.ptr(p.m), _lib.ptr(p.v), p.n,
                                       float(lr), 0.9, 0.999, 1e-8, max(p.step, 1), float(clip_norm),
-                                      _lib.ptr(lr_t_dev), _stream())
+                                      _lib.ptr(lr_t_dev), _lib.ptr(ctrl), _lib.ptr(self.nll) if ctrl is not None else None,
+                                      _lib.ptr(self.info) if ctrl is not None else None, _lib.ptr(loss_hist),
+                                      int(loss_hist.numel()) if loss_hist is not None else 0, _stream())
         _lib.check(rc, "distbo_adam_f64")
 
+    def check_info(self, info):
+        """Raises for a non-zero factorisation status, like TF's InvalidArgumentError."""
+        info = int(info)
+        if info < 0:
+            raise _lib.DistboError("Cholesky decomposition was not successful: an inter-CTA wait timed out "
+                                   "(info %d; the GPU is shared with other work and a producer CTA was not "
+                                   "resident) - rerun, or set DISTBO_POTRF_SMALL=0" % info)
+        if info != 0:
+            raise _lib.DistboError("Cholesky decomposition was not successful: non-positive pivot at row %d "
+                                   "(matrix not positive definite)" % info)
+
+    @on_device
     def read_loss(self):
         """One device->host sync: (nll, info).  Raises on a failed Cholesky like TF's
         InvalidArgumentError."""
         out = torch.stack([self.nll[0], self.info[0].double()]).cpu().numpy()
-        if int(out[1]) != 0:
-            raise _lib.DistboError("Cholesky decomposition was not successful: non-positive pivot at row %d "
-                                   "(matrix not positive definite)" % int(out[1]))
+        self.check_info(out[1])
         return float(out[0])
 
     # ------------------------------------------------------------------ scoring
+    @on_device
     def score(self, theta_c, acq="ei", y_max=0.0, xi=0.0, kappa=1.0, want_arrays=True, index_offset=0,
               kvec=None, scaler=None):
         """K4 on candidates theta_c [M,d] (device or host array).  `scaler` = (mean_, scale_) device
@@ -446,6 +511,7 @@ class GPEngine:
         return {"best_val": self.best_val, "best_idx": self.best_idx, "mean": mean, "std": std, "acq": acqv}
 
     # ------------------------------------------------------------------ one evaluation of loss + gradient
+    @on_device
     def loss_and_grad(self, X=None, Y=None, seg_off=None, E_const=None, size_ratio=None):
         """One evaluation of the negative log marginal likelihood and its full gradient (what one
         sess.run([optimize_step, loss]) does in the reference, train/train.py:43-52), as a chain of

@@ -20,6 +20,8 @@ datasets' rows are embedded from at prediction time: fp32 when False)
 """
 from __future__ import annotations
 
+import collections
+import functools
 import math
 import os
 
@@ -31,10 +33,63 @@ from sklearn.utils import check_random_state
 from .. import blr_engine as _blr
 from .. import engine as _eng
 from ..sharding import ShardGroup
-from .gp_utils import EmbedBatchSampler, check_dims, init_net_weights
+from .gp_utils import EmbedBatchSampler, PyShuffle, check_dims, init_net_weights
 
 EARLY_STOP_THRESHOLD = 0.0001   # train/train.py:54
 EARLY_STOP_PATIENCE = 100       # train/train.py:55
+LOSS_HISTORY_CAP = 1 << 22      # device ring of per-epoch losses (the shipped configs run <= 10 000 epochs per fit)
+
+
+def _on_engine_device(fn):
+    """Public entry points run with the surrogate's device current (kernel launches, streams and graph capture
+    follow the CURRENT device): a process may hold regressors on several GPUs."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        dev = self.engine.dev if self.engine is not None else None
+        if dev is None and self.device is not None:
+            dev = torch.device(self.device)
+        if dev is None or dev.index is None or torch.cuda.current_device() == dev.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
+class TrainControl:
+    """Device-side state of one fit's training loop (include/distbo_b200.h DISTBO_CTRL_*): the early-stopping rule
+    of train/train.py:53-65 is evaluated by the Adam launch itself, the losses go to a device ring, and the host
+    only looks at an asynchronous copy of this block every few epochs."""
+
+    def __init__(self, dev, max_epochs, first_early_stop_epoch):
+        init = np.zeros(_eng.CTRL_SLOTS)
+        init[_eng.CTRL_CUR_MIN] = init[_eng.CTRL_COUNTDOWN] = np.inf
+        init[_eng.CTRL_FIRST_EPOCH] = float(first_early_stop_epoch)
+        init[_eng.CTRL_THRESHOLD] = EARLY_STOP_THRESHOLD
+        init[_eng.CTRL_PATIENCE] = EARLY_STOP_PATIENCE
+        self.dev = torch.from_numpy(init).to(dev)
+        self.loss_hist = torch.zeros(max(1, min(int(max_epochs), LOSS_HISTORY_CAP)), dtype=torch.float64, device=dev)
+        self._free, self._pending = [], collections.deque()
+
+    def post_check(self):
+        """Queues an asynchronous copy of the control block into pinned memory."""
+        slot = self._free.pop() if self._free else (torch.empty(_eng.CTRL_SLOTS, dtype=torch.float64).pin_memory(),
+                                                    torch.cuda.Event())
+        slot[0].copy_(self.dev, non_blocking=True)
+        slot[1].record()
+        self._pending.append(slot)
+
+    def stopped(self):
+        """True once a completed check shows STOP != 0.  Never blocks."""
+        seen = False
+        while self._pending and self._pending[0][1].query():
+            slot = self._pending.popleft()
+            seen = seen or slot[0][_eng.CTRL_STOP].item() != 0.0
+            self._free.append(slot)
+        return seen
+
+    def final(self):
+        """Blocking read of the block after the last epoch has been queued."""
+        return self.dev.cpu().numpy()
 
 
 class gp_regressor(object):
@@ -53,6 +108,11 @@ class gp_regressor(object):
         self.shuffle_seed = 0
         self.engine = None
         self.shards = ShardGroup()
+        self.fit_rank = 0                # with torch.distributed: the rank that runs the Adam loop
+        self.device = None               # optional "cuda:k" the engine is built on (default: the current device)
+        self.check_every = int(os.environ.get("DISTBO_CHECK_EVERY", "8"))   # epochs between stop-flag checks
+        self._pyshuffle = None           # the stratified sampler's shuffle stream: ONE per regressor, never re-seeded
+        self.handoff_ms = None
         self.loss_history = []
         self._fit_generation = 0
         self._predict_generation = -1
@@ -128,7 +188,7 @@ class gp_regressor(object):
             if self.kernel == "multi":
                 P = int(n_tasks)
             weights.update(init_net_weights(P + d, weight_dim, "", self.seed))
-            e = _blr.BLREngine(d, weight_dim, n_embed=P, net=net)
+            e = _blr.BLREngine(d, weight_dim, n_embed=P, net=net, device=self.device)
             for k, v in weights.items():
                 e.params.set(k, v)
             if self.initial_weights:
@@ -144,7 +204,7 @@ class gp_regressor(object):
             n_multi = int(n_tasks)
             seed = self.seed if self.seed is not None else 23
             weights["log_triangular_task"] = np.random.RandomState(seed).normal(size=n_multi * (n_multi + 1) // 2)
-        e = _eng.GPEngine(d, n_embed=P, net=net, n_multi=n_multi)
+        e = _eng.GPEngine(d, n_embed=P, net=net, n_multi=n_multi, device=self.device)
         for k, v in weights.items():
             e.params.set(k, v)
         if self.initial_weights:
@@ -155,6 +215,7 @@ class gp_regressor(object):
         self.engine = e
 
     # ------------------------------------------------------------------ fit
+    @_on_engine_device
     def maximise_likhd(self, params, y, data_X=None, data_Y=None, data_embed=None,
                        source_embed_ind=None, embed_op='joint', algorithm='GP',
                        weight_dim=None, weight_dim_x=None, num_of_rff=100,
@@ -210,8 +271,11 @@ class gp_regressor(object):
                 source_embed_ind = [np.arange(len(x)) for x in data_X]
             self._source_embed_ind = source_embed_ind
             self._pred_sets = None
+            if self._pyshuffle is None and stratify and self.model_type == "classification" and \
+                    any(len(yy) > int(batch_size) for yy in data_Y):
+                self._pyshuffle = PyShuffle(self.shuffle_seed)
             sampler = EmbedBatchSampler(data_Y, batch_size, check_random_state(self.seed), self.model_type,
-                                        stratify, shuffle_seed=self.shuffle_seed)
+                                        stratify, shuffle_seed=self.shuffle_seed, pyrand=self._pyshuffle)
             self._full = self._stack(data_X, data_Y)          # all rows of every dataset, HBM resident
             full_off = self._full[2].cpu().numpy().astype(np.int64)
             bs = np.r_[0, np.cumsum(sampler.sizes())].astype(np.int32)
@@ -225,30 +289,80 @@ class gp_regressor(object):
         self._batch_off = batch_off if sampler is not None else None
         self._lr, self._clip = learning_rate, (5.0 if gradient_clip else 0.0)
         self._scaler_dev = (self._dev(self.params_scaler.mean_), self._dev(self.params_scaler.scale_))
-        self._setup_epoch_state()
-
+        self._ctrl = None
         # ---- training loop: train/train.py:11-71
         if first_early_stop_epoch is None:
             first_early_stop_epoch = max_epochs // 5
-        cur_min, countdown = np.inf, np.inf
-        loss = None
-        epoch = -1
-        for epoch in range(int(max_epochs)):
-            self.run_epoch()
-            loss = e.read_loss()
-            self.loss_history.append(loss)
-            if epoch >= first_early_stop_epoch:
-                if (cur_min - loss) > EARLY_STOP_THRESHOLD:
-                    countdown = EARLY_STOP_PATIENCE
-                    cur_min = loss
-                else:
-                    countdown -= 1
-                if countdown <= 0:
-                    break
-        self.last_epoch = epoch
+        max_epochs = int(max_epochs)
+        if self.shards.world > 1 and self.shards.rank != self.fit_rank:
+            # the fit is single-GPU (SURVEY 8e "replicas only"): this rank waits for the fitting rank's result
+            # and receives the posterior state in _prepare_predict
+            loss = self._receive_fit_result()
+        else:
+            loss, failure = None, None
+            try:
+                loss = self._train(max_epochs, first_early_stop_epoch)
+            except _eng._lib.DistboError as exc:
+                failure = exc
+            if self.shards.world > 1:
+                self._send_fit_result(loss, failure)
+            if failure is not None:
+                raise failure
+        self._fit_generation += 1
         self.initialise = False
         self.pre_compute_embed = True
         return loss
+
+    def _train(self, max_epochs, first_early_stop_epoch):
+        """The Adam loop with NO host synchronisation per epoch: every epoch is one CUDA-graph replay whose last
+        launch (Adam) also records the loss and applies the early-stopping rule on the device; the host queues
+        epochs, looks at an asynchronously copied stop flag every `check_every` epochs and, once it is set, stops
+        queueing - the epochs already queued behind the stop are no-ops on the device."""
+        e = self.engine
+        self._setup_epoch_state()
+        ctrl = self._ctrl = TrainControl(e.dev, max_epochs, first_early_stop_epoch)
+        step0 = e.params.step
+        self._shuffle_marks = []
+        for epoch in range(max_epochs):
+            self.run_epoch()
+            if (epoch + 1) % self.check_every == 0:
+                ctrl.post_check()
+                if ctrl.stopped():
+                    break
+        final = ctrl.final()
+        done = int(final[_eng.CTRL_EPOCHS])
+        e.params.step = step0 + done                    # Adam's step count = updates actually applied
+        if done:
+            self.loss_history.extend(ctrl.loss_hist[:min(done, ctrl.loss_hist.numel())].cpu().numpy().tolist())
+        self._rewind_shuffle_stream(done)
+        self.last_epoch = done - 1
+        if int(final[_eng.CTRL_STOP]) == 2:
+            e.check_info(final[_eng.CTRL_INFO])         # raises, as TF's InvalidArgumentError would
+        return float(final[_eng.CTRL_LAST_LOSS]) if done else None
+
+    def _rewind_shuffle_stream(self, epochs_done):
+        """Mini-batches are drawn ahead of the device; the reference draws one per epoch it runs (its generator
+        is advanced only after the stop test, train/train.py:43-65).  The shuffle stream persists across fits, so
+        it is put back to where it stood after the draw of the last epoch that ran."""
+        if self._pyshuffle is None or not self._shuffle_marks:
+            return
+        keep = [st for ep, st in self._shuffle_marks if ep < max(epochs_done, 1)]
+        self._pyshuffle.restore(keep[-1] if keep else self._shuffle_marks[0][1])
+
+    def _send_fit_result(self, loss, failure):
+        rec = torch.tensor([0.0 if failure is None else 1.0, float("nan") if loss is None else loss,
+                            float(getattr(self, "last_epoch", -1))], dtype=torch.float64, device=self.engine.dev)
+        self.shards.broadcast_fit([rec], src=self.fit_rank)
+
+    def _receive_fit_result(self):
+        rec = torch.zeros(3, dtype=torch.float64, device=self.engine.dev)
+        self.shards.broadcast_fit([rec], src=self.fit_rank)
+        rec = rec.cpu().numpy()
+        if rec[0] != 0.0:
+            raise _eng._lib.DistboError("the fit failed on rank %d (Cholesky decomposition was not successful)"
+                                        % self.fit_rank)
+        self.last_epoch = int(rec[2])
+        return None if np.isnan(rec[1]) else float(rec[1])
 
     # One optimisation step = one CUDA graph.  The step's launch sequence (embedding forward, task Gram,
     # Gram, POTRF with its look-ahead stream, TRTRI, LAUUM, likelihood, gradient contractions, embedding
@@ -261,6 +375,9 @@ class gp_regressor(object):
         e, sampler = self.engine, self._sampler
         self._graph = None
         self._graph_warm = 0
+        self._epochs_staged = 0
+        if not hasattr(self, "_shuffle_marks"):
+            self._shuffle_marks = None
         self._lrt_dev = torch.zeros(1, dtype=torch.float64, device=e.dev)
         self._ring = []
         self._ring_pos = 0
@@ -291,6 +408,11 @@ class gp_regressor(object):
                     for i, ix in enumerate(sampler.next_indices())]
             slot["idx"].copy_(torch.from_numpy(np.concatenate(rows)))
             self._gather_dev.copy_(slot["idx"], non_blocking=True)
+            if sampler.uses_shuffle_stream and self._shuffle_marks is not None:
+                ps = self._pyshuffle
+                if not self._shuffle_marks or self._shuffle_marks[-1][1][0] != ps.version:
+                    self._shuffle_marks.append((self._epochs_staged, ps.state()))
+        self._epochs_staged += 1
         slot["ev"].record()
 
     def _epoch_body(self):
@@ -303,8 +425,11 @@ class gp_regressor(object):
             torch.index_select(self._full[0], 0, self._gather_dev, out=self._bX)
             torch.index_select(self._full[1], 0, self._gather_dev, out=self._bY)
             e.loss_and_grad(self._bX, self._bY, self._batch_off, size_ratio=self._ratio)
-        e.adam_step(self._lr, clip_norm=self._clip, lr_t_dev=self._lrt_dev)
+        ctrl = self._ctrl
+        e.adam_step(self._lr, clip_norm=self._clip, lr_t_dev=self._lrt_dev,
+                    ctrl=ctrl.dev if ctrl is not None else None, loss_hist=ctrl.loss_hist if ctrl is not None else None)
 
+    @_on_engine_device
     def run_epoch(self):
         """One optimisation step (loss, full gradient, Adam update) queued on the current stream with
         no host synchronisation: what one sess.run([optimize_step, loss]) is in train/train.py:43-52."""
@@ -328,7 +453,7 @@ class gp_regressor(object):
         else:
             self._epoch_body()              # first epoch of a fit: eager (allocates persistent buffers)
             self._graph_warm += 1
-        self._fit_generation += 1
+        self._fit_generation += 1           # (also bumped by maximise_likhd: covers callers that drive run_epoch)
 
     # ------------------------------------------------------------------ predict
     def initialise_predict(self):
@@ -372,11 +497,75 @@ class gp_regressor(object):
         return self._pred_sets
 
     def _prepare_predict(self):
-        """Posterior state at the CURRENT parameters: embeddings of the full sample sets, task Gram over
-        sources + target, K, L, W = L^-1, V, and kvec (what build_predict / build_predict_dist
-        recompute on every call, train/log_gaus_likelihood.py:128-218)."""
+        """Posterior state at the CURRENT parameters.  Single process: computed here.  With torch.distributed
+        (candidates sharded over the ranks) the fit is single-GPU: the fitting rank computes the state
+        and BROADCASTS it - W = L^-1, V, the scaled observations, kvec, the parameter vector, the task Gram - and
+        the other ranks only receive (north_star: "L and alpha are broadcast").  `handoff_ms` keeps the device
+        times of the last hand-off: {"refresh_ms", "bcast_ms", "bytes"}."""
         if self._predict_generation == self._fit_generation:
             return
+        sh = self.shards
+        timed = self.engine.dev.type == "cuda"
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timed else None
+        if timed:
+            ev[0].record()
+        failure = None
+        if sh.world == 1 or sh.rank == self.fit_rank:
+            try:
+                self._compute_posterior_state()
+            except _eng._lib.DistboError as exc:
+                if sh.world == 1:
+                    raise
+                failure = exc
+        if timed:
+            ev[1].record()
+        nbytes = 0
+        if sh.world > 1:
+            status = torch.tensor([0.0 if failure is None else 1.0], dtype=torch.float64, device=self.engine.dev)
+            sh.broadcast_fit([status], src=self.fit_rank)
+            if status.item() != 0.0:
+                raise failure if failure is not None else _eng._lib.DistboError(
+                    "the posterior state could not be prepared on rank %d (Cholesky decomposition was not "
+                    "successful)" % self.fit_rank)
+            state = self._posterior_state_tensors()
+            sh.broadcast_fit(state, src=self.fit_rank)
+            nbytes = sum(t.numel() * t.element_size() for t in state)
+        if timed:
+            ev[2].record()
+            ev[2].synchronize()
+            self.handoff_ms = {"refresh_ms": ev[0].elapsed_time(ev[1]), "bcast_ms": ev[1].elapsed_time(ev[2]),
+                               "bytes": nbytes}
+        self._predict_generation = self._fit_generation
+
+    @_on_engine_device
+    def refresh_posterior(self):
+        """Recomputes (and, with torch.distributed, re-broadcasts) the posterior state at the current parameters.
+        Collective: with world > 1 every rank must call it.  maximise_likhd makes the next predict_y / acquire do
+        this implicitly; callers that step the optimiser themselves through run_epoch() call it explicitly."""
+        self._fit_generation += 1
+        self._prepare_predict()
+        return self.handoff_ms
+
+    def _posterior_state_tensors(self):
+        """The tensors scoring and similarity() read, in broadcast order; allocated here on receiving ranks."""
+        e = self.engine
+        T = e.T
+        if self.algorithm == "BLR":
+            if e.P and e.emb_target is None:
+                e.emb_target = torch.zeros(e.P, dtype=torch.float64, device=e.dev)
+            return [e.Linv, e.evec, e.params.flat] + ([e.emb_target] if e.P else [])
+        out = [e.W, e.V, e.theta_s, e.sqnorm, e.kvec, e.params.flat]
+        if self.kernel != "params":
+            shape = (T, T) if self.kernel == "multi" else (T + 1, T + 1)
+            if getattr(self, "_KE_all", None) is None or tuple(self._KE_all.shape) != shape:
+                self._KE_all = torch.zeros(*shape, dtype=torch.float64, device=e.dev)
+            out.append(self._KE_all)
+        e.W_valid = True
+        return out
+
+    def _compute_posterior_state(self):
+        """Embeddings of the full sample sets, task Gram over sources + target, K, L, W = L^-1, V, and kvec
+        (what build_predict / build_predict_dist recompute on every call, train/log_gaus_likelihood.py:128-218)."""
         e = self.engine
         T = e.T
         KE = None
@@ -401,7 +590,6 @@ class gp_regressor(object):
                 E, emb_t = self._E_const, self._E_const[T - 1].contiguous()
             e.prepare_posterior(E, emb_t)
             e.read_loss()
-            self._predict_generation = self._fit_generation
             return
         if self.kernel == "multi":
             # candidates belong to the last task (kernels.py:47-49): kvec = column T-1 of the task covariance
@@ -422,8 +610,8 @@ class gp_regressor(object):
         e.factorize(need_inverse=True, need_kinv=False)
         e.likelihood()
         e.read_loss()          # raises on a failed Cholesky, as TF would
-        self._predict_generation = self._fit_generation
 
+    @_on_engine_device
     def predict_y(self, params_pred, refresh_net=False, compute_embed=False):
         self._prepare_predict()
         self.pre_compute_embed = bool(compute_embed)
@@ -434,6 +622,7 @@ class gp_regressor(object):
         std = out["std"].cpu().numpy()[:, None]
         return mean, std
 
+    @_on_engine_device
     def acquire(self, params_pred, kind, y_max=0.0, xi=0.0, kappa=1.0, want_values=False):
         """Fused posterior + acquisition + argmax over the candidate rows `params_pred` [M,d] (host
         numpy array or host torch tensor, raw scale).  With torch.distributed initialised, every rank passes the SAME array and
@@ -460,6 +649,7 @@ class gp_regressor(object):
             return best_v, best_i, (None if out["acq"] is None else out["acq"].cpu().numpy())
         return best_v, best_i
 
+    @_on_engine_device
     def similarity(self, sample_sim=False):
         """[array [T,1]]: embedding-kernel value between every source task and the target
         (gp_regressor.py:205-223; train/train.py:86-95)."""
@@ -475,4 +665,7 @@ class gp_regressor(object):
 
     def close(self):
         self.initialise = True
+        if self.engine is not None:
+            self.engine.close()         # frees the factorisation plan (streams, events, flag buffers)
         self.engine = None
+        self._graph = None

@@ -67,8 +67,19 @@ class PyShuffle:
         self._idx = np.asarray([state[624]], dtype=np.int32)
         self._fn = _lib.load().distbo_py_shuffle_i64
         self._C = _lib.C
+        self.version = 0            # number of shuffles drawn so far
+
+    def state(self):
+        """(version, Mersenne-Twister words, position): restore() rewinds the stream to this point."""
+        return self.version, self._mt.copy(), self._idx.copy()
+
+    def restore(self, state):
+        self.version = state[0]
+        self._mt[:] = state[1]
+        self._idx[:] = state[2]
 
     def shuffle(self, members):
+        self.version += 1
         out = np.ascontiguousarray(members, dtype=np.int64).copy()
         vp = self._C.c_void_p
         rc = self._fn(vp(self._mt.ctypes.data), vp(self._idx.ctypes.data), vp(out.ctypes.data), int(out.size))
@@ -90,7 +101,7 @@ class EmbedBatchSampler:
     an epoch costs a few slices per dataset.
     """
 
-    def __init__(self, data_Y, batch_size, rs, model_type, stratify, shuffle_seed=0):
+    def __init__(self, data_Y, batch_size, rs, model_type, stratify, shuffle_seed=0, pyrand=None):
         self.Y = data_Y
         self.n = [len(y) for y in data_Y]
         self.batch_size = int(batch_size)
@@ -100,7 +111,9 @@ class EmbedBatchSampler:
         self.constant = all(n <= self.batch_size for n in self.n)
         self._cls = None
         if not self.constant and self.stratify and model_type == "classification":
-            self._pyrand = PyShuffle(shuffle_seed)
+            # the reference never re-seeds the global `random`, so its stream runs on from fit to fit: a regressor
+            # that refits hands in its own persistent PyShuffle
+            self._pyrand = pyrand if pyrand is not None else PyShuffle(shuffle_seed)
             n_classes = data_Y[0].shape[1]
             self._cls = []
             for y in data_Y:
@@ -115,8 +128,23 @@ class EmbedBatchSampler:
     def _shuffled(self, members):
         return self._pyrand.shuffle(members)    # Python's list shuffle, as the reference calls it
 
+    @property
+    def uses_shuffle_stream(self):
+        return self._cls is not None
+
     def sizes(self):
-        return [min(n, self.batch_size) for n in self.n]
+        """Rows per dataset in every epoch's mini-batch.  Class-stratified batches hold sum_c int(frac_c *
+        (batch_size + 4)) rows cut at batch_size (gp_utils.py:57,72-83), which falls below batch_size once there
+        are six or more classes; the count is the same in every epoch of a fit."""
+        out = []
+        for i, n in enumerate(self.n):
+            if n <= self.batch_size:
+                out.append(n)
+            elif self._cls is not None:
+                out.append(min(self.batch_size, sum(c["take"] for c in self._cls[i])))
+            else:
+                out.append(self.batch_size)
+        return out
 
     def next_indices(self):
         out = []

@@ -13,7 +13,9 @@
  *    never synchronises the device (distbo_plan_create / destroy excepted);
  *  - return value: 0 ok, <0 bad argument (-1) or CUDA error (-2).  A failed Cholesky is reported
  *    asynchronously through the device int `info` (LAPACK style: 1-based index of the first
- *    non-positive pivot, 0 = success); the caller reads it back with the loss.
+ *    non-positive pivot, 0 = success; DISTBO_INFO_TIMEOUT (< 0) = an inter-CTA wait inside the
+ *    factorisation ran out, i.e. the device is shared and a producer CTA was not resident: the
+ *    factor is invalid); the caller reads it back with the loss.
  *  - not re-entrant per plan; one plan per (device, n_pad).
  */
 #ifndef DISTBO_B200_H
@@ -24,6 +26,8 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+#define DISTBO_INFO_TIMEOUT (-1000) /* value of `info` after a bounded inter-CTA wait expired */
 
 #define DISTBO_ACQ_EI 0  /* bayes_opt/helpers.py:165-171 */
 #define DISTBO_ACQ_UCB 1 /* bayes_opt/helpers.py:151-156 */
@@ -184,10 +188,29 @@ int distbo_blr_score_f64(const double* cand, const double* cand_shift, const dou
  * lr_t = lr sqrt(1 - beta2^step) / (1 - beta1^step); p -= lr_t m / (sqrt(v) + eps).  step is 1-based.
  * clip_norm <= 0 disables tf.clip_by_global_norm (train/train.py:33-35).
  * lr_t_dev (optional): device scalar holding lr_t; when non-NULL it is used instead of (lr, step) so
- * that the launch can be replayed from a CUDA graph with a value the host refreshes per step. */
+ * that the launch can be replayed from a CUDA graph with a value the host refreshes per step.
+ * ctrl (optional, DISTBO_CTRL_SLOTS doubles on the device): the training loop's control block - the
+ * early-stopping rule of train/train.py:53-65 evaluated ON THE DEVICE so that the host never has to read the
+ * loss between epochs.  With ctrl: the launch is a no-op once ctrl[DISTBO_CTRL_STOP] != 0; if *info != 0 (failed
+ * factorisation) STOP = 2, INFO = *info and the update is NOT applied (TF raises inside sess.run); otherwise
+ * after the update the epoch's loss *nll goes to loss_hist[EPOCHS % hist_cap] and LAST_LOSS, EPOCHS += 1, and for
+ * EPOCHS-before >= FIRST_EPOCH: (CUR_MIN - loss) > THRESHOLD ? (COUNTDOWN = PATIENCE, CUR_MIN = loss)
+ * : COUNTDOWN -= 1; COUNTDOWN <= 0 -> STOP = 1.  The caller initialises CUR_MIN = COUNTDOWN = +inf, STOP = EPOCHS = 0,
+ * FIRST_EPOCH, THRESHOLD (1e-4) and PATIENCE (100) before the first epoch of a fit. */
+#define DISTBO_CTRL_CUR_MIN 0
+#define DISTBO_CTRL_COUNTDOWN 1
+#define DISTBO_CTRL_STOP 2
+#define DISTBO_CTRL_EPOCHS 3
+#define DISTBO_CTRL_LAST_LOSS 4
+#define DISTBO_CTRL_FIRST_EPOCH 5
+#define DISTBO_CTRL_INFO 6
+#define DISTBO_CTRL_THRESHOLD 7
+#define DISTBO_CTRL_PATIENCE 8
+#define DISTBO_CTRL_SLOTS 16
 int distbo_adam_f64(double* params, const double* grads, double* m, double* v, int64_t n, double lr,
                     double beta1, double beta2, double eps, int64_t step, double clip_norm,
-                    const double* lr_t_dev, void* stream);
+                    const double* lr_t_dev, double* ctrl, const double* nll, const int32_t* info,
+                    double* loss_hist, int64_t hist_cap, void* stream);
 
 /* ---- K4: posterior + acquisition + argmax  (log_gaus_likelihood.py:128-218; gp_regressor.py:197;
  *      bayes_opt/helpers.py:51-68,151-171) ---------------------------------------------------------

@@ -42,15 +42,17 @@ def sample(data_X, data_Y, embed_ind=None, source_list=True):
     return sx, sy
 
 
-def loop_batches(train, batch_size, max_epochs, rs, model_type, stratify=False, shuffle_seed=0):
+def loop_batches(train, batch_size, max_epochs, rs, model_type, stratify=False, shuffle_seed=0, pyrand=None):
     """train/gp_utils.py:28-104.  The reference's stratified-classification branch shuffles Python lists with
     the unseeded global ``random.shuffle`` (:53,78); a private ``random.Random(shuffle_seed)`` reproduces the stream
-    the reference draws after ``random.seed(shuffle_seed)``."""
+    the reference draws after ``random.seed(shuffle_seed)``.  The global stream is never re-seeded by
+    the reference, so it runs on from fit to fit: callers that refit pass their own persistent `pyrand`."""
     if "X" in train and "y" in train:
         X_list, Y_list = train["X"], train["y"]
         n_datasets = len(X_list)
         import random
-        pyrand = random.Random(shuffle_seed)
+        if pyrand is None:
+            pyrand = random.Random(shuffle_seed)
         if model_type == "classification":
             n_classes = Y_list[0].shape[1]
         if model_type == "classification" and stratify:
@@ -228,8 +230,11 @@ class OracleGPRegressor(object):
         rs = check_random_state(self.seed)
         loss = None
         epoch = -1
+        if getattr(self, "_pyrand", None) is None:
+            import random
+            self._pyrand = random.Random(getattr(self, "shuffle_seed", 0))   # one stream for all fits of this regressor
         for epoch, (bX, by, es) in enumerate(loop_batches(self.train, batch_size, max_epochs, rs,
-                                                          self.model_type, stratify=stratify)):
+                                                          self.model_type, stratify=stratify, pyrand=self._pyrand)):
             batch = self._batch(bX, by, es)
             if self.algorithm == "BLR":
                 loss, grads = BO.blr_loss_and_grads(self.p, self.kernel, batch, self.rff_input_dim, self.num_of_rff,

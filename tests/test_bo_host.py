@@ -191,3 +191,82 @@ def test_c_shuffle_is_pythons_random_shuffle():
             ref.shuffle(lst)
             got = mine.shuffle(np.arange(100, 100 + n))
             assert got.tolist() == lst, (seed, n)
+
+
+def _reference_style_batches(Y_list, batch_size, epochs, pyrand):
+    """loop_batches' class-stratified branch (reference train/gp_utils.py:38-84) on index lists, driven by `pyrand`."""
+    from oracle.gp_regressor_oracle import loop_batches
+    X_list = [np.arange(len(y), dtype=np.float64)[:, None] for y in Y_list]
+    gen = loop_batches({"X": X_list, "y": Y_list}, batch_size, epochs, np.random.RandomState(0), "classification",
+                       stratify=True, pyrand=pyrand)
+    return [(bx[:, 0].astype(np.int64), es.reshape(-1).astype(int)) for bx, _, es in gen]
+
+
+def test_class_stratified_sampler_many_classes_and_persistent_stream():
+    """Six or more classes: the stratified batch has fewer than batch_size rows (gp_utils.py:57,72-83) and sizes()
+    must say so; and the shuffle stream is ONE stream over all fits of a regressor (the reference never re-seeds
+    the global `random`), rewound by restore() when mini-batches were drawn ahead of an early stop."""
+    import random
+    from distbo_b200.train.gp_utils import EmbedBatchSampler, PyShuffle
+    rs = np.random.RandomState(3)
+    n_classes, batch = 12, 40
+    Y_list = [np.eye(n_classes)[rs.randint(0, n_classes, size=n)] for n in (150, 30, 97)]
+    ref_rand = random.Random(5)
+    stream = PyShuffle(5)
+    for fit in range(3):                                   # three fits, one stream
+        want = _reference_style_batches(Y_list, batch, 9, ref_rand)
+        s = EmbedBatchSampler(Y_list, batch, np.random.RandomState(0), "classification", True, pyrand=stream)
+        sizes = s.sizes()
+        assert sizes[1] == 30 and sizes[0] < batch and sizes[2] < batch      # int() truncation per class: < 40 rows
+        marks = []
+        for ep in range(9 + 4):                            # the host runs four epochs ahead of the "stop"
+            idx = s.next_indices()
+            marks.append(stream.state())
+            if ep < 9:
+                rows = np.concatenate([np.arange(len(Y_list[i])) if ix is None else ix for i, ix in enumerate(idx)])
+                off = np.r_[0, np.cumsum(want[ep][1])]
+                got_sizes = [len(Y_list[i]) if ix is None else len(ix) for i, ix in enumerate(idx)]
+                assert got_sizes == sizes == list(want[ep][1])
+                # dataset-local row indices, dataset by dataset
+                assert np.array_equal(rows, want[ep][0]), (fit, ep)
+        stream.restore(marks[8])                           # back to the state after the ninth draw
+
+
+def test_lockstep_polish_is_the_serial_polish():
+    """The batched polish (all L-BFGS-B runs in lock-step, value + scipy's own forward-difference stencil per device
+    call; reference helpers.py:70-86) returns, run for run, the serial result bit for bit - x, value, nfev, nit -
+    including seeds on / next to a bound (flipped stencil steps), with ~25x fewer acquisition calls."""
+    from distbo_b200.bayes_opt import helpers as H
+    rs = np.random.RandomState(0)
+    d = 4
+    bounds = np.array([[-2.0, 3.0]] * d)
+    C = rs.randn(5, d)
+    calls = [0]
+
+    def acq(X, gp=None, y_max=None):           # evaluated row by row: independent of the batch by construction
+        calls[0] += 1
+        X = np.atleast_2d(X)
+        out = np.array([sum(np.exp(-np.sum((x - c) ** 2)) for c in C) + 0.1 * np.sin(3 * x).sum() for x in X])
+        return out if len(out) > 1 else np.squeeze(out)
+    seeds = rs.uniform(-2, 3, size=(10, d))
+    seeds[3, 1], seeds[5, 0], seeds[7, 2] = 3.0, 2.98, -2.0
+    serial = H._polish_runs_serial(acq, None, 0.0, seeds, bounds, 0.05, 2000)
+    n_serial, calls[0] = calls[0], 0
+    batched = H._polish_runs_batched(acq, None, 0.0, seeds, bounds, 0.05, 2000)
+    for a, b in zip(serial, batched):
+        assert np.array_equal(a.x, b.x) and a.fun == b.fun and a.nfev == b.nfev and a.nit == b.nit
+        assert a.success == b.success
+    assert calls[0] * 10 < n_serial
+    # a tiny maxfun budget ends the runs on the same evaluation count as well
+    a = H._polish_runs_serial(acq, None, 0.0, seeds[:3], bounds, 0.05, 12)
+    b = H._polish_runs_batched(acq, None, 0.0, seeds[:3], bounds, 0.05, 12)
+    assert [(r.nfev, r.success, r.fun) for r in a] == [(r.nfev, r.success, r.fun) for r in b]
+
+
+def test_lockstep_evaluator_propagates_errors():
+    from distbo_b200.bayes_opt import helpers as H
+
+    def bad(X, gp=None, y_max=None):
+        raise RuntimeError("device call failed")
+    with pytest.raises(RuntimeError, match="device call failed"):
+        H._polish_runs_batched(bad, None, 0.0, np.zeros((3, 2)), np.array([[-1.0, 1.0]] * 2), 0.05, 100)

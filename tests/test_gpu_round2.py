@@ -1,0 +1,371 @@
+"""GPU tests of the round-2 pieces: the host-sync-free training loop (device-side early stopping), the
+lock-step polish (8f-2), the product-level fit hand-off (8e), per-device library state, bounded inter-CTA waits,
+template variants the earlier sweeps never reached (d_theta 9..16, widest embedding nets), and an ill-conditioned
+Gram at the reference's default noise.  Checker: the CPU oracle."""
+import math
+import os
+import socket
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import gp_oracle as O  # noqa: E402
+from oracle.gp_regressor_oracle import OracleGPRegressor  # noqa: E402
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def toy_problem(seed=0, T=4, per_task=25, d=2):
+    rs = np.random.RandomState(seed)
+    theta = rs.uniform(-3, 3, size=(T * per_task, d))
+    y = np.sin(theta.sum(1)) + np.repeat(rs.randn(T) * 0.2, per_task) + 0.05 * rs.randn(T * per_task)
+    embed = [rs.rand(5) for _ in range(T + 1)]
+    return theta, y[:, None], [per_task] * T, embed
+
+
+def manual_fit_kwargs(sizes, embed, **over):
+    kw = dict(data_embed=embed[:-1], target_embed=np.asarray(embed[-1])[None, :], sizes=sizes, learning_rate=0.005,
+              max_epochs=12, likhd_var_init=1e-2, first_early_stop_epoch=4)
+    kw.update(over)
+    return kw
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f1: training loop without a host synchronisation per epoch (train/train.py:43-65 evaluated on the device)
+@pytest.mark.parametrize("check_every", [1, 3, 64])
+def test_device_side_early_stopping_matches_oracle(cuda_engine_mod, check_every):
+    """lr 1e-9: no epoch improves the loss by 1e-4, so the countdown set at first_early_stop_epoch runs out 100 epochs
+    later.  The stop epoch, every epoch's loss and the parameters (no update after the stop, although the host has
+    queued more epochs) are the oracle's, for any interval between the host's looks at the stop flag."""
+    from distbo_b200.train import gp_regressor
+    theta, y, sizes, embed = toy_problem()
+    fit = manual_fit_kwargs(sizes, embed, learning_rate=1e-9, max_epochs=400, first_early_stop_epoch=7)
+    g, o = gp_regressor("manual", seed=3, float64=True), OracleGPRegressor("manual", seed=3, float64=True)
+    g.check_every = check_every
+    lg, lo = g.maximise_likhd(theta, y, **fit), o.maximise_likhd(theta, y, **fit)
+    assert g.last_epoch == o.last_epoch == 7 + 100
+    assert len(g.loss_history) == len(o.loss_history) == 108
+    assert rel(g.loss_history, o.loss_history) < 1e-9 and abs(lg - lo) <= 1e-9 * abs(lo)
+    assert g.engine.params.step == 108                   # Adam's step count = updates applied, not epochs queued
+    # a second fit continues from the same Adam state (gp_regressor.py:143) and stops on its own schedule
+    fit2 = dict(fit, learning_rate=0.005, max_epochs=30, first_early_stop_epoch=10 ** 9)
+    lg, lo = g.maximise_likhd(theta, y, **fit2), o.maximise_likhd(theta, y, **fit2)
+    assert g.last_epoch == o.last_epoch == 29 and g.engine.params.step == 138
+    assert rel(g.loss_history, o.loss_history) < 1e-8
+    for k in ("log_bw", "log_bw_embed", "log_scale", "mean", "log_sigma"):
+        assert rel(g.engine.params.get(k).reshape(-1), np.asarray(o.p[k]).reshape(-1)) < 1e-8, k
+    g.close()
+
+
+def test_failed_factorisation_during_training_raises_and_freezes_parameters(cuda_engine_mod):
+    from distbo_b200.train import gp_regressor
+    theta, y, sizes, embed = toy_problem()
+    g = gp_regressor("manual", seed=3, float64=True)
+    g.maximise_likhd(theta, y, **manual_fit_kwargs(sizes, embed, max_epochs=3))
+    before = g.engine.params.flat.clone()
+    bad = theta.copy()
+    bad[17, 0] = np.nan                                    # NaN row -> NaN pivot: TF's cholesky op fails
+    with pytest.raises(RuntimeError, match="not successful"):
+        g.params_scaler = None
+        g.maximise_likhd(bad, y, **manual_fit_kwargs(sizes, embed, max_epochs=40))
+    after = g.engine.params.flat
+    assert torch.equal(torch.nan_to_num(before), torch.nan_to_num(after))     # no update was applied
+    g.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f2: lock-step polish on the fused device path
+def fitted_regressor(d=3, seed=5):
+    from distbo_b200.train import gp_regressor
+    theta, y, sizes, embed = toy_problem(seed, d=d)
+    g = gp_regressor("manual", seed=3, float64=True)
+    g.maximise_likhd(theta, y, **manual_fit_kwargs(sizes, embed, max_epochs=15, likhd_var_init=1e-5))
+    return g, theta, y
+
+
+def test_scored_rows_do_not_depend_on_their_batch(cuda_engine_mod):
+    """A candidate's posterior and acquisition value are bitwise the same alone, inside a small batch and inside a
+    batch that spans tiles - what lets the polish share device calls without changing a number."""
+    from distbo_b200.bayes_opt import UtilityFunction
+    g, theta, y = fitted_regressor()
+    rs = np.random.RandomState(1)
+    X = rs.uniform(-3, 3, size=(301, 3))
+    m_all, s_all = g.predict_y(X)
+    util = UtilityFunction("ei", kappa=2.58, xi=0.01)
+    a_all = np.reshape(util.utility(X, g, float(y.max())), -1)
+    for lo, hi in [(0, 1), (5, 6), (130, 139), (127, 130), (300, 301)]:
+        m, s = g.predict_y(X[lo:hi])
+        assert np.array_equal(m, m_all[lo:hi]) and np.array_equal(s, s_all[lo:hi])
+        a = np.reshape(util.utility(X[lo:hi], g, float(y.max())), -1)
+        assert np.array_equal(a, a_all[lo:hi])
+    g.close()
+
+
+@pytest.mark.parametrize("kind,eps,maxfun", [("ei", 0.05, 2000), ("ucb", 0.1, 1500)])
+def test_lockstep_polish_on_device_is_the_serial_polish(cuda_engine_mod, kind, eps, maxfun):
+    from distbo_b200.bayes_opt import UtilityFunction
+    from distbo_b200.bayes_opt import helpers as H
+    g, theta, y = fitted_regressor()
+    util = UtilityFunction(kind, kappa=2.58, xi=0.01)
+    bounds = np.array([[-3.0, 3.0]] * 3)
+    rs = np.random.RandomState(2)
+    cand = rs.uniform(-3, 3, size=(20000, 3))
+    ys = np.reshape(util.utility(cand, g, float(y.max())), -1)
+    seeds = cand[np.argsort(ys)[-10:]]
+    t0 = time.perf_counter()
+    serial = H._polish_runs_serial(util.utility, g, float(y.max()), seeds, bounds, eps, maxfun)
+    t1 = time.perf_counter()
+    before = dict(H.POLISH_STATS)
+    batched = H._polish_runs_batched(util.utility, g, float(y.max()), seeds, bounds, eps, maxfun)
+    t2 = time.perf_counter()
+    for a, b in zip(serial, batched):
+        assert np.array_equal(a.x, b.x) and a.fun == b.fun and a.nfev == b.nfev and a.success == b.success
+    calls = H.POLISH_STATS["device_calls"] - before["device_calls"]
+    nfev = sum(r.nfev for r in serial)
+    print("polish %s: %d function values; serial %d device calls %.1f ms, lock-step %d device calls %.1f ms" % (
+        kind, nfev, nfev, (t1 - t0) * 1e3, calls, (t2 - t1) * 1e3))
+    assert calls * 5 < nfev
+    g.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ill-conditioned K at the reference's default noise: 1-d theta (toy configuration), sigma^2 = 1e-5 + 1e-6
+def test_ill_conditioned_gram_default_noise(cuda_engine_mod):
+    """Config 1's regime at a larger N: 1-d theta on a fine grid, 16 similar tasks, sigma^2 = 1e-5 -> cond(K) ~ 1e8.
+    Scoring contracts with the explicit W = L^-1 (GEMM) where the reference solves with L (TRSM); both carry errors
+    of order eps * cond, and the variance tolerance north_star states (1e-8, relative to the prior scale) holds."""
+    eng = cuda_engine_mod
+    rs = np.random.RandomState(11)
+    T, per, d = 16, 96, 1
+    N = T * per
+    theta = rs.uniform(-8, 8, size=(N, d)) / 4.6
+    E = rs.randn(T + 1, 10) * 0.15
+    y = np.exp(-0.5 * (theta[:, 0] * 4.6 - np.repeat(rs.randn(T), per)) ** 2)
+    e = eng.GPEngine(d, n_embed=10)
+    e.params.set("log_sigma", 0.5 * math.log(1e-5))
+    e.set_observations(theta, y, [per] * T)
+    Ed = torch.from_numpy(E).to(e.dev)
+    KE_all = e.task_gram(Ed, T + 1)
+    e.build_gram(KE_all[:T, :T].contiguous())
+    Kfull = torch.tril(e.K[:N, :N]).cpu().numpy()
+    Kfull = Kfull + np.tril(Kfull, -1).T
+    ev = np.linalg.eigvalsh(Kfull)
+    cond = ev[-1] / ev[0]
+    e.factorize(need_inverse=True, need_kinv=False)
+    e.likelihood()
+    nll = e.read_loss()
+    e.kvec.zero_()
+    e.kvec[:N] = KE_all[:T, T][e.task_id.long()]
+    cand = rs.uniform(-8, 8, size=(4096, d)) / 4.6
+    out = e.score(cand, acq="ei", y_max=float(y.max()), xi=0.01)
+    p = {k: e.params.get(k) for k in e.params.offsets}
+    emb = np.repeat(E[:T], per, axis=0)
+    kd = O.matern32_kernel(O.NP, emb, emb, np.exp(p["log_bw_embed"]))
+    kdp = O.matern32_kernel(O.NP, emb, E[T:T + 1], np.exp(p["log_bw_embed"]))
+    b = O.TrainBatch(h_params=theta, obs=y[:, None])
+    mean, var = O.predict(O.NP, p, "dist", b, cand, k_dist=kd, k_dist_pred=kdp)
+    acq = O.acq_ei(mean, O.std_from_var(var), float(y.max()), 0.01)
+    dv = float(np.max(np.abs(out["std"].cpu().numpy() ** 2 - np.maximum(var[:, 0], 1e-32))))
+    dm = rel(out["mean"].cpu().numpy(), mean[:, 0])
+    print("ill-conditioned: N=%d cond(K_sigma)=%.3e  |dvar|=%.2e (prior scale 1)  mean rel %.2e" % (N, cond, dv, dm))
+    assert cond > 1e6
+    assert dv < 1e-8 and dm < 1e-8
+    assert int(out["best_idx"].item()) == int(np.argmax(acq))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# template variants: d_theta up to 16 (gram_grad_rows_kernel<16>, kst_kernel<16>), widest embedding nets
+@pytest.mark.parametrize("d", [9, 12, 16])
+def test_wide_theta(cuda_engine_mod, d):
+    eng = cuda_engine_mod
+    rs = np.random.RandomState(d)
+    N, T, P, M = 300, 3, 6, 513
+    sizes = [100, 150, 50]
+    theta, y = rs.randn(N, d), rs.randn(N)
+    e = eng.GPEngine(d, n_embed=P)
+    e.params.set("log_sigma", 0.5 * math.log(1e-2))
+    e.params.set("log_bw", 0.5 + rs.randn(d) * 0.2)
+    e.params.set("log_bw_embed", rs.randn(P) * 0.3)
+    E = rs.randn(T, P) * 0.4
+    e.E = torch.from_numpy(E).to(e.dev)
+    e.set_observations(theta, y, sizes)
+    e.build_gram(e.task_gram(e.E, T))
+    e.factorize(need_inverse=True, need_kinv=True)
+    e.likelihood()
+    nll = e.read_loss()
+    e.gram_gradient()
+    p = {k: e.params.get(k) for k in e.params.offsets}
+    B = O.TH()
+    tp = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=True) for k, v in p.items()}
+    k = O.matern32_kernel(B, torch.from_numpy(theta), torch.from_numpy(theta), torch.exp(tp["log_bw"]))
+    emb = B.repeat_rows(torch.tensor(E), sizes)
+    k = torch.exp(tp["log_scale"]) * k * O.matern32_kernel(B, emb, emb, torch.exp(tp["log_bw_embed"]))
+    ks = k + (torch.exp(2.0 * tp["log_sigma"]) + O.JITTER) * torch.eye(N, dtype=torch.float64)
+    Lref = torch.linalg.cholesky(ks)
+    loss = -O.multivariate_normal_logpdf(B, torch.from_numpy(y[:, None]),
+                                         tp["mean"] * torch.ones(N, 1, dtype=torch.float64), Lref).reshape(())
+    loss.backward()
+    assert abs(nll - float(loss.detach())) <= 1e-9 * abs(float(loss.detach()))
+    for name in ["log_bw", "log_scale", "mean", "log_sigma", "log_bw_embed"]:
+        got = e.params.get_grad(name)
+        assert rel(got, tp[name].grad.numpy().reshape(got.shape)) < 1e-7, name
+    kv = rs.rand(N) * 0.5 + 0.5
+    e.kvec.zero_()
+    e.kvec[:N] = torch.from_numpy(kv).to(e.dev)
+    cand = rs.randn(M, d)
+    out = e.score(cand, acq="ei", y_max=float(y.max()), xi=0.01)
+    emb_np = np.repeat(E, sizes, axis=0)
+    kd = O.matern32_kernel(O.NP, emb_np, emb_np, np.exp(p["log_bw_embed"]))
+    mean, v = O.predict(O.NP, p, "dist", O.TrainBatch(h_params=theta, obs=y[:, None]), cand, k_dist=kd,
+                        k_dist_pred=kv[:, None])
+    acq = O.acq_ei(mean, O.std_from_var(v), float(y.max()), 0.01)
+    assert rel(out["mean"].cpu().numpy(), mean[:, 0]) < 1e-8
+    assert int(out["best_idx"].item()) == int(np.argmax(acq))
+
+
+def test_widest_embedding_nets(cuda_engine_mod):
+    """NetSpec's limits: hidden width 32, middle and output widths 16 (three-layer x net + y net), joint pooling
+    P = 16 x 16; loss trajectory and posterior against the oracle."""
+    from distbo_b200.train import gp_regressor
+    rs = np.random.RandomState(9)
+    T, per, d = 3, 20, 2
+    theta = rs.uniform(-3, 3, size=(T * per, d))
+    y = np.sin(theta.sum(1))[:, None]
+    X = [rs.randn(90 + 11 * t, 7) + 0.2 * t for t in range(T + 1)]
+    Y = [rs.rand(90 + 11 * t, 1) for t in range(T + 1)]
+    common = dict(model_type="regression", seed=4, float64=True, target_X=X[T], target_Y=Y[T],
+                  target_embed_ind=np.arange(len(X[T])))
+    fit = dict(data_X=X[:T], data_Y=Y[:T], source_embed_ind=[np.arange(len(x)) for x in X[:T]], sizes=[per] * T,
+               embed_op="joint", weight_dim_x=[32, 16, 16], weight_dim_y=[32, 16], batch_size=1000,
+               learning_rate=0.005, max_epochs=5, likhd_var_init=1e-2, first_early_stop_epoch=10 ** 9)
+    g, o = gp_regressor("dist", **common), OracleGPRegressor("dist", **common)
+    lg, lo = g.maximise_likhd(theta, y, **fit), o.maximise_likhd(theta, y, **fit)
+    assert rel(g.loss_history, o.loss_history) < 1e-8
+    cand = rs.uniform(-3, 3, size=(200, d))
+    (mg, sg), (mo, so) = g.predict_y(cand, compute_embed=True), o.predict_y(cand, compute_embed=True)
+    assert rel(mg, mo) < 1e-8 and np.max(np.abs(sg ** 2 - so ** 2)) < 1e-8
+    g.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bounded inter-CTA waits: the single-launch factorisation on a device shared with a co-running kernel
+def test_small_factorisation_next_to_other_work(cuda_engine_mod):
+    """potrf_small_kernel's CTAs wait for each other through device flags.  With other streams keeping SMs busy the
+    factor must still come out right (or, had a wait expired, info < 0 would raise) - never hang."""
+    eng = cuda_engine_mod
+    rs = np.random.RandomState(0)
+    N, d = 1900, 3
+    theta, y = rs.randn(N, d), rs.randn(N)
+    e = eng.GPEngine(d)
+    e.params.set("log_sigma", 0.5 * math.log(1e-2))
+    e.set_observations(theta, y)
+    side = torch.cuda.Stream()
+    a = torch.randn(4096, 4096, device=e.dev)
+    ref = None
+    for it in range(6):
+        with torch.cuda.stream(side):
+            for _ in range(8):
+                a = torch.tanh(a @ a) * 0.01
+        e.build_gram(None)
+        e.factorize(need_inverse=True, need_kinv=False)
+        e.likelihood()
+        nll = e.read_loss()
+        if ref is None:
+            ref = nll
+        assert nll == ref
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# several devices in one process; torch.distributed hand-off on two GPUs
+needs_two = pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+
+
+@needs_two
+def test_second_device_in_one_process(cuda_engine_mod):
+    """Per-device library state (dynamic shared-memory opt-ins, SM counts, plans): a fit + a scoring pass on cuda:1
+    after cuda:0, with cuda:0 still the current device, give the same numbers as on cuda:0."""
+    from distbo_b200.train import gp_regressor
+    theta, y, sizes, embed = toy_problem(2, T=5, per_task=60, d=3)
+    cand = np.random.RandomState(3).uniform(-3, 3, size=(20000, 3))
+    res = []
+    for dev in ("cuda:0", "cuda:1"):
+        g = gp_regressor("manual", seed=3, float64=True)
+        g.device = dev
+        loss = g.maximise_likhd(theta, y, **manual_fit_kwargs(sizes, embed, max_epochs=10))
+        v, i = g.acquire(cand, "ei", y_max=float(y.max()), xi=0.01)
+        assert g.engine.K.device == torch.device(dev)
+        res.append((loss, v, i))
+        assert torch.cuda.current_device() == 0
+        g.close()
+    assert res[0] == res[1]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _bo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from distbo_b200.bayes_opt import UtilityFunction
+        from distbo_b200.train import gp_regressor
+        theta, y, sizes, embed = toy_problem(2, T=5, per_task=60, d=3)
+        g = gp_regressor("manual", seed=3, float64=True)
+        trained = []
+        orig = g._train
+        g._train = lambda *a: (trained.append(rank), orig(*a))[1]
+        loss = g.maximise_likhd(theta, y, **manual_fit_kwargs(sizes, embed, max_epochs=10))
+        cand = np.random.RandomState(3).uniform(-3, 3, size=(30011, 3))
+        v, i = UtilityFunction("ei", kappa=2.58, xi=0.01).argmax(cand, g, float(y.max()))
+        sim = np.asarray(g.similarity()[0]).reshape(-1).tolist()
+        loss2 = g.maximise_likhd(theta, y, **manual_fit_kwargs(sizes, embed, max_epochs=5))   # refit + second hand-off
+        v2, i2 = g.acquire(cand, "ucb", kappa=2.58)
+        q.put((rank, loss, v, i, sim, loss2, v2, i2, trained, g.handoff_ms["bytes"]))
+        g.close()
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@needs_two
+def test_two_gpu_fit_handoff_through_the_product_api(cuda_engine_mod):
+    """Under torch.distributed every rank makes the same gp_regressor calls; rank 0 alone trains, the posterior state
+    is broadcast inside the first acquire after each fit, candidates are sharded - and every number equals the
+    single-process run."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    single = ctx.Process(target=_bo_worker, args=(0, 1, _free_port(), q))
+    single.start()
+    want = q.get(timeout=600)
+    single.join(timeout=60)
+    port = _free_port()
+    procs = [ctx.Process(target=_bo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert out[0][8] == [0, 0] and out[1][8] == []            # two fits, both on rank 0 only
+    assert out[0][9] > 0 and out[1][9] > 0                    # a broadcast happened inside the product call
+    for o in out:
+        assert o[1:8] == want[1:8], (o, want)
