@@ -79,6 +79,16 @@ def fit_kwargs(work, max_epochs, lkh_var):
                 first_early_stop_epoch=10 ** 9)
 
 
+def bench_config(m, lkh_var, world):
+    """The `config` object of the JSON line: identical in both arms (--impl cuda / --impl reference)."""
+    n_pad = (N_OBS + 127) // 128 * 128
+    return {"workload": "config5_synthetic_scaleup", "n_obs": N_OBS, "tasks": T_SRC, "d_theta": D_THETA,
+            "candidates": int(m), "acq": "ei", "embed": "protein-like 65x%dx%d fp32, P=23" % (ROWS, DX),
+            "lkh_var": lkh_var, "parallelism": "candidate shards x%d" % world,
+            "l2": "inputs larger than L2 (W = L^-1 is %d MB, one K_* chunk 148*128 x %d doubles = %d MB)" %
+                  (n_pad * n_pad * 8 >> 20, n_pad, 148 * 128 * n_pad * 8 >> 20)}
+
+
 # ----------------------------------------------------------------------------------- clocks
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
@@ -125,6 +135,15 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------- CPU reference arm
+def one_thread_scoring(work, lkh_var, m_sample, params_override=None):
+    """candidates/s of the same op sequence on ONE host thread - the reference's default (`--n-cpus`,
+    experiments/train_test.py:91) - on a smaller bounded sample."""
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=1):
+        t_fixed, t_var, _ = cpu_reference(work, lkh_var, m_sample, 1, 0, params_override=params_override)
+    return t_fixed, t_var[0]
+
+
 def cpu_reference(work, lkh_var, m_sample, steps, warmup, params_override=None):
     """The reference's CPU op sequence for this path (oracle restatement; TF 1.7 cannot run here):
     embeddings of the full sample sets, k_dist / k_dist_pred, Gram + Cholesky + V (candidate
@@ -215,19 +234,24 @@ def run_reference(args):
     m = args.candidates
     m_s = min(m, args.cpu_sample)
     work = make_workload(N_OBS, m_s, ROWS)
-    t_fixed, t_var, _ = cpu_reference(work, args.lkh_var, m_s, args.steps, args.warmup)
+    warm = max(args.warmup, 1)              # at least one untimed pass (BLAS thread pools, page faults)
+    t_fixed, t_var, _ = cpu_reference(work, args.lkh_var, m_s, args.steps, warm)
     tv = float(np.mean(t_var))
     step_s = t_fixed + tv * (m / m_s)          # one acquisition pass over all M candidates
     value = m / step_s
+    m_1 = min(m_s, 2048)
+    f1, v1 = one_thread_scoring(work, args.lkh_var, m_1)
+    value_1 = m / (f1 + v1 * (m / m_1))
     sample = ("oracle restatement (numpy/scipy OpenBLAS fp64): Gram+Cholesky+V timed once (%.2f s), K_*/solve/EI/"
-              "argmax timed per step on the first %d of %d candidates (%.3f s mean); value extrapolates "
-              "linearly in M to the full pass" % (t_fixed, m_s, m, tv))
+              "argmax timed per step on the first %d of %d candidates (%.3f s mean over %d steps after %d warm-up); "
+              "value extrapolates linearly in M to the full pass.  One thread (the reference's default --n-cpus): "
+              "%.2f s + %.3f s per %d candidates" % (t_fixed, m_s, m, tv, len(t_var), warm, f1, v1, m_1))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config5_synthetic_scaleup", "n_obs": N_OBS, "tasks": T_SRC, "d_theta": D_THETA,
-                       "candidates": m, "acq": "ei"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample},
+            "config": bench_config(m, args.lkh_var, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample,
+                             "value_1thread": value_1, "sample_candidates": m_s},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -475,13 +499,20 @@ def run_cuda(args):
     if world == 1 and not args.no_cpu_baseline:
         m_s = min(M, args.cpu_sample)
         fitted = {k: eng.params.get(k) for k in eng.params.offsets}
+        # one untimed pass on a small prefix (BLAS pools, page faults), then the timed sample
+        cpu_reference(work, args.lkh_var, min(256, m_s), 1, 0, params_override=fitted)
         t_fixed, t_var, best_cpu = cpu_reference(work, args.lkh_var, m_s, 1, 0, params_override=fitted)
         step_s = t_fixed + t_var[0] * (M / m_s)
+        m_1 = min(m_s, 2048)
+        f1, v1 = one_thread_scoring(work, args.lkh_var, m_1, params_override=fitted)
         # same arg-max on the sample as the CUDA path gives on that prefix
         v_gpu, i_gpu = gp.acquire(work["cand"][:m_s], "ei", y_max=y_max, xi=XI, kappa=KAPPA)
         cpu = {"value": M / step_s, "unit": UNIT, "cores": host_threads(), "kind": "port",
-               "sample": "Gram+Cholesky+V once %.2f s; K_*/solve/EI/argmax on the first %d candidates %.2f s; "
+               "sample": "warmed; Gram+Cholesky+V once %.2f s; K_*/solve/EI/argmax on the first %d candidates %.2f s; "
                          "extrapolated linearly to M=%d" % (t_fixed, m_s, t_var[0], M),
+               "value_1thread": M / (f1 + v1 * (M / m_1)),
+               "sample_1thread": "one host thread (the reference's default --n-cpus 1): %.2f s + %.2f s on %d candidates"
+                                 % (f1, v1, m_1),
                "argmax_matches_gpu_on_sample": bool(best_cpu == i_gpu)}
         # fit step on the host: one loss + full-gradient evaluation at N = 8192, same mini-batch shape
         fit_s, fit_loss = cpu_fit_reference(work, args.lkh_var, params_override=fitted)
@@ -494,11 +525,7 @@ def run_cuda(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config5_synthetic_scaleup", "n_obs": N_OBS, "tasks": T_SRC, "d_theta": D_THETA,
-                       "candidates": M, "acq": "ei", "embed": "protein-like 65x%dx%d fp32, P=23" % (ROWS, DX),
-                       "lkh_var": args.lkh_var, "parallelism": "candidate shards x%d" % world,
-                       "l2": "inputs larger than L2 (W = L^-1 is %d MB, K_* chunk %d MB)" %
-                             (n_pad * n_pad * 8 >> 20, chunk * n_pad * 8 >> 20)},
+            "config": bench_config(M, args.lkh_var, world),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": M / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 16 * world,
@@ -526,7 +553,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--candidates", type=int, default=M_DEFAULT)
     ap.add_argument("--lkh-var", type=float, default=1e-2)
-    ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 14,
+                    help="candidates of the CPU legs' bounded sample (BASELINE.md section 3: 2^14)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-blr", action="store_true", help="skip the secondary BLR-surrogate measurement")
     ap.add_argument("--fit-epochs", type=int, default=20,

@@ -287,7 +287,10 @@ class gp_regressor(object):
 
         self._sampler, self._full_off = sampler, (full_off if sampler is not None else None)
         self._batch_off = batch_off if sampler is not None else None
-        self._lr, self._clip = learning_rate, (5.0 if gradient_clip else 0.0)
+        if self.initialise or not hasattr(self, "_lr"):
+            # the optimiser is built once, at the first fit: later calls keep ITS learning rate and clipping
+            # (train/train.py:29-41 runs only when `initialise`, gp_regressor.py:130-143)
+            self._lr, self._clip = learning_rate, (5.0 if gradient_clip else 0.0)
         self._scaler_dev = (self._dev(self.params_scaler.mean_), self._dev(self.params_scaler.scale_))
         self._ctrl = None
         # ---- training loop: train/train.py:11-71

@@ -194,6 +194,9 @@ class OracleGPRegressor(object):
                 if k in self.p:
                     self.p[k] = np.asarray(v, dtype=np.float64).reshape(np.shape(self.p[k]))
             self.adam = O.TFAdam(learning_rate)
+            # the optimiser (learning rate, clip_by_global_norm) is part of the graph built at the first fit only
+            # (train/train.py:29-41): later fits keep it, whatever they pass
+            self._gradient_clip = bool(gradient_clip)
         if self.kernel == "dist":
             self.source_X, self.source_Y = sample(data_X, data_Y, embed_ind=source_embed_ind,
                                                   source_list=True)
@@ -210,7 +213,7 @@ class OracleGPRegressor(object):
             train["sizes"] = sizes
         self.train = train
         loss = self._train_network(max_epochs, first_early_stop_epoch, batch_size, stratify,
-                                   gradient_clip)
+                                   self._gradient_clip)
         self.initialise = False
         self.pre_compute_embed = True
         return loss

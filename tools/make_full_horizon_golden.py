@@ -10,7 +10,7 @@ script records what a replay needs and what a divergence report needs:
 
   init__<name>          initial values of the target surrogate's variables (TF's glorot stream is not reproducible)
   fit_epochs, fit_loss  epochs run and last loss of every maximise_likhd call of the target search
-  fit_params__<name>    fitted parameters after every target fit
+  fit_params__<j>__<name>  fitted parameters after target fit j;  fit_loss_log__<j>: its loss at every epoch
   sweep_top2            the two largest acquisition values of every candidate sweep and their row indices
                         (the margin that decides the suggestion: arbiter input)
 
@@ -129,7 +129,7 @@ def main():
     ref_load.range = lambda *a: list(range(*a))
 
     rec = {"inits": [], "fit_epochs": [], "fit_loss": [], "fit_params": [], "fit_kernel": [], "fit_seconds": [],
-           "sweeps": []}
+           "sweeps": [], "fit_loss_log": []}
     orig_fit = ref_gp.gp_regressor.maximise_likhd
     orig_close = ref_gp.gp_regressor.close
     t_start = time.time()
@@ -144,6 +144,7 @@ def main():
         rec["fit_kernel"].append(self.kernel)
         rec["fit_seconds"].append(time.time() - t0)
         rec["fit_params"].append({k: v.value.detach().numpy().copy() for k, v in self.net.params.items()})
+        rec["fit_loss_log"].append(np.asarray(self.sess.loss_log[n0:n1]) if self.kernel != "params" else None)
         print("[full-horizon %s] fit %d kernel=%s N=%d epochs=%d loss=%.8f %.1fs (total %.0fs)" % (
             name, len(rec["fit_loss"]), self.kernel, len(a[0]), n1 - n0, loss, time.time() - t0,
             time.time() - t_start), file=sys.stderr, flush=True)
@@ -213,6 +214,7 @@ def main():
     for j, i in enumerate(tgt):
         for k, v in rec["fit_params"][i].items():
             arrays["fit_params__%d__%s" % (j, k)] = v
+        arrays["fit_loss_log__%d" % j] = rec["fit_loss_log"][i]      # every epoch's loss (divergence reports)
     arrays["sweep_top2"] = np.asarray(rec["sweeps"], dtype=np.float64).reshape(-1, 6)
     for kernel, init in rec["inits"]:
         if kernel != "params":

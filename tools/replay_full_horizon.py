@@ -55,6 +55,10 @@ def main():
     ap.add_argument("--impl", choices=["cuda", "oracle"], default="cuda")
     ap.add_argument("--out", default=None)
     ap.add_argument("--max-iterations", type=int, default=None, help="replay only the first k target iterations")
+    ap.add_argument("--teacher-forced", action="store_true",
+                    help="skip training: load the REFERENCE'S fitted parameters of every fit into the surrogate, so that "
+                         "each of the acquisitions (posterior + EI over 300 000 candidates + arg-max [+ polish]) is "
+                         "compared on the same surrogate, free of the training run's sensitivity")
     opt = ap.parse_args()
 
     from distbo_b200 import experiments as X
@@ -81,7 +85,7 @@ def main():
     else:
         from oracle.gp_regressor_oracle import OracleGPRegressor as base   # checker code: tools/ only
 
-    fits = []
+    fits, first_fit_losses = [], []
 
     def factory(kernel, **kw):
         reg = base(kernel, **kw)
@@ -90,7 +94,24 @@ def main():
 
         def recording(*a, **k):
             t0 = time.time()
+            if opt.teacher_forced:
+                k = dict(k, max_epochs=0)
             loss = orig(*a, **k)
+            if opt.teacher_forced:
+                j = len(fits)
+                for name in list(reg.engine.params.offsets if opt.impl == "cuda" else reg.p):
+                    key = "fit_params__%d__%s" % (j, name)
+                    if key in z.files:
+                        if opt.impl == "cuda":
+                            reg.engine.params.set(name, z[key])
+                        else:
+                            reg.p[name] = np.asarray(z[key], dtype=np.float64).reshape(np.shape(reg.p[name]))
+                if opt.impl == "cuda":
+                    reg._fit_generation += 1
+                loss = float(z["fit_loss"][j])
+                reg.last_epoch = int(z["fit_epochs"][j]) - 1
+            elif not fits:
+                first_fit_losses.extend(reg.loss_history)
             if opt.impl == "cuda":
                 p = {n: reg.engine.params.get(n) for n in reg.engine.params.offsets}
             else:
@@ -169,7 +190,8 @@ def main():
                 worst = max(worst, float(np.max(np.abs(g - ref) / np.maximum(np.abs(ref), 1e-300))))
         sim_drift = worst
     report = {
-        "config": opt.name, "impl": opt.impl, "argv": argv, "iterations": n, "polish": polish,
+        "config": opt.name, "impl": opt.impl, "teacher_forced": bool(opt.teacher_forced), "argv": argv,
+        "iterations": n, "polish": polish,
         "suggestions_equal": eq, "all_equal": first_bad is None, "first_differing_iteration": first_bad,
         "objective_values_equal": bool(np.array_equal(got_y[:n], want_y[:n])),
         "max_abs_suggestion_diff": float(np.max(np.abs(got_x[:n] - want_x[:n]))) if n else None,
@@ -179,10 +201,13 @@ def main():
         "wall_seconds": wall,
         "polish_stats": dict(H.POLISH_STATS),
     }
-    out = opt.out or os.path.join(ROOT, "profiles", "r02_full_horizon_%s_%s.json" % (opt.name, opt.impl))
+    tag = "%s_%s%s" % (opt.name, opt.impl, "_teacher_forced" if opt.teacher_forced else "")
+    out = opt.out or os.path.join(ROOT, "profiles", "r02_full_horizon_%s.json" % tag)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     with open(out, "w") as fh:
         json.dump(report, fh, indent=1)
+    if first_fit_losses:                  # every epoch's loss of the first fit: input of the divergence report
+        np.save(out[:-5] + "_first_fit_losses.npy", np.asarray(first_fit_losses))
     print("[replay %s/%s] %d iterations, all suggestions equal: %s (first difference: %s); target search %.1f s "
           "(reference over the shim: %.1f s) -> %s" % (opt.name, opt.impl, n, first_bad is None, first_bad,
                                                        d["target_time"], float(z["target_time"]), out))
