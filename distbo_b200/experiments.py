@@ -21,10 +21,43 @@ from copy import deepcopy
 import numpy as np
 from sklearn.utils import check_random_state
 
-from .data.load_datasets import load_parkinson, load_protein
+from .data.load_datasets import load_parkinson, load_protein, parkinson_tasks, protein_tasks
 from .data.toy_datasets import counter_manual_tasks, one_dim_split_tasks
 from .model_embed.bayes_optimise import bayes_opt_wrap
 from .model_embed.meta_fea import meta
+
+_COMMON = ["--float64", "--kappa", "2.58", "--xi", "0.01", "--learning-rate", "0.005", "--n-warmup", "300000",
+           "--num-of-rff", "0", "--warm-start-method", "manual", "--warm-start-tasks", "3", "--n-warm-per-task", "3",
+           "--weight_dim_1", "0", "--weight_dim_2", "0", "--weight_dim_3", "0",
+           "--weight_dim_1_xy", "0", "--weight_dim_2_xy", "0", "--weight_dim_3_xy", "0"]
+
+# The command lines the reference ships for the BASELINE configurations (seed 0, GP surrogate): what
+# experiments/one_dim_toy_config.py, protein_config.py and counter_manual_config.py print for their first grid
+# entry, and the CLI defaults for Parkinson (no config script; train_test.py:28-91) with --float64.
+SHIPPED_COMMAND_LINES = {
+    "config1": ["one_dim_split", "--n-train", "500", "--n-test", "500", "--data-seed", "0", "--opt-seed", "0",
+                "--bo-source-type", "BO", "--source-rand-iterations", "10", "--source-iterations", "20",
+                "--algorithm", "GP", "--bo-target-type", "distBO", "--target-iterations", "15",
+                "--target-rand-iterations", "0", "--embed-op", "none", "--max-embed-size", "500",
+                "--batch-size", "500", "--dont-stratify", "--n-epochs", "10000", "--n-opt-iterations", "0",
+                "--first_early_stop_epoch", "5000", "--weight_dim_1_x", "20", "--weight_dim_2_x", "10",
+                "--weight_dim_1_y", "0", "--weight_dim_2_y", "0"] + _COMMON,
+    "config2": ["protein_vary", "--target-group", "0", "--test-size", "0.4", "--data-seed", "0", "--opt-seed", "0",
+                "--bo-source-type", "BO", "--source-rand-iterations", "10", "--source-iterations", "10",
+                "--concat-data-size", "--algorithm", "GP", "--bo-target-type", "distBO",
+                "--target-iterations", "20", "--target-rand-iterations", "0", "--embed-op", "joint",
+                "--max-embed-size", "5000", "--batch-size", "1000", "--n-epochs", "10000",
+                "--n-opt-iterations", "10", "--first_early_stop_epoch", "5000", "--weight_dim_1_x", "20",
+                "--weight_dim_2_x", "10", "--weight_dim_1_y", "20", "--weight_dim_2_y", "10"] + _COMMON,
+    "config3": ["patient_vary", "--data-seed", "0", "--opt-seed", "0", "--float64"],
+    "config4": ["counter_manual", "--n-train", "5000", "--n-test", "5000", "--data-seed", "0", "--opt-seed", "0",
+                "--bo-source-type", "BO", "--source-rand-iterations", "75", "--source-iterations", "75",
+                "--algorithm", "GP", "--bo-target-type", "manualBO", "--target-iterations", "100",
+                "--target-rand-iterations", "0", "--embed-op", "none", "--max-embed-size", "5000",
+                "--batch-size", "0", "--n-epochs", "10000", "--n-opt-iterations", "10",
+                "--first_early_stop_epoch", "5000", "--weight_dim_1_x", "0", "--weight_dim_2_x", "0",
+                "--weight_dim_1_y", "0", "--weight_dim_2_y", "0"] + _COMMON,
+}
 
 RESULT_KEYS = ("args", "supp", "source_params", "source_evals", "source_time", "target_sim", "target_params",
                "target_evals", "target_time")         # train_test.py:170-338
@@ -136,11 +169,25 @@ def generate_data(args):
         args.model = 'ridge'
         if args.park_labels == 'both':
             raise NotImplementedError("--park-labels both (84 tasks) is not part of any BASELINE configuration")
-        return load_parkinson(args.target_group, _data_dir(args, 'parkinson'), random_state=rs,
+        src = _data_dir(args, 'parkinson')
+        if src.endswith('.npz'):      # the 42 patient tables packed into one file (tests/golden/parkinson_full.npz)
+            z = np.load(src)
+            return parkinson_tasks([z["patient_%d" % i] for i in range(42)], args.target_group, random_state=rs,
+                                   preprocess=args.preprocess, label=args.park_labels, test_size=args.test_size)
+        return load_parkinson(args.target_group, src, random_state=rs,
                               preprocess=args.preprocess, label=args.park_labels, test_size=args.test_size)
     if args.dataset == 'protein_vary':
         args.model = getattr(args, "protein_model", 'forest')     # generate_data.py:22 (or 'jaccard_svm')
-        return load_protein(args.target_group, _data_dir(args, 'protein'), random_state=rs,
+        src = _data_dir(args, 'protein')
+        if src.endswith('.npz'):      # the 7 ChEMBL tables, fingerprints bit-packed (tests/golden/protein_full.npz)
+            z = np.load(src)
+            tables = []
+            for i in range(len(z["names"])):
+                bits = np.unpackbits(z["bits_%d" % i], axis=1)[:, :166].astype(np.float64)
+                tables.append(np.hstack([np.zeros((len(bits), 1)), bits, z["labels_%d" % i].astype(np.float64)[:, None]]))
+            return protein_tasks(tables, [str(n) for n in z["names"]], args.target_group, random_state=rs,
+                                 test_size=args.test_size)
+        return load_protein(args.target_group, src, random_state=rs,
                             preprocess=args.preprocess, test_size=args.test_size)
     if args.dataset == 'one_dim_split':
         args.model = 'toy'
@@ -158,6 +205,8 @@ def _data_dir(args, name):
     if d is None:
         raise ValueError("--data-dir (or DISTBO_DATA_DIR) must point at the folder that holds the reference's "
                          "%s/ files" % name)
+    if os.path.isfile(d):
+        return d
     return d if os.path.basename(os.path.normpath(d)) == name or not os.path.isdir(os.path.join(d, name)) \
         else os.path.join(d, name)
 

@@ -39,34 +39,13 @@ import tf1_shim  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
-COMMON = ["--float64", "--kappa", "2.58", "--xi", "0.01", "--learning-rate", "0.005", "--n-warmup", "300000",
-          "--num-of-rff", "0", "--warm-start-method", "manual", "--warm-start-tasks", "3", "--n-warm-per-task", "3",
-          "--weight_dim_1", "0", "--weight_dim_2", "0", "--weight_dim_3", "0",
-          "--weight_dim_1_x", "20", "--weight_dim_2_x", "10",
-          "--weight_dim_1_xy", "0", "--weight_dim_2_xy", "0", "--weight_dim_3_xy", "0"]
+from distbo_b200.experiments import SHIPPED_COMMAND_LINES  # noqa: E402
 
-# the command lines experiments/*_config.py print for seed 0, method distBO, algorithm GP
-CONFIGS = {
-    # experiments/one_dim_toy_config.py:72-136 (grid_distbo_gp[0])
-    "toy": ["one_dim_split", "--n-train", "500", "--n-test", "500", "--data-seed", "0", "--opt-seed", "0",
-            "--bo-source-type", "BO", "--source-rand-iterations", "10", "--source-iterations", "20",
-            "--algorithm", "GP", "--bo-target-type", "distBO", "--target-iterations", "15",
-            "--target-rand-iterations", "0", "--embed-op", "none", "--max-embed-size", "500", "--batch-size", "500",
-            "--dont-stratify", "--n-epochs", "10000", "--n-opt-iterations", "0", "--first_early_stop_epoch", "5000",
-            "--weight_dim_1_y", "0", "--weight_dim_2_y", "0"] + COMMON,
-    # experiments/protein_config.py:77-143 (target 0), with the deterministic jaccard_svm objective the reference
-    # offers for this data set (distBO/data/generate_data.py:22 selects it by editing one line; its default random
-    # forest is unseeded, so no trajectory of it is reproducible even by the reference itself)
-    "protein": ["protein_vary", "--target-group", "0", "--test-size", "0.4", "--data-seed", "0", "--opt-seed", "0",
-                "--bo-source-type", "BO", "--source-rand-iterations", "10", "--source-iterations", "10",
-                "--concat-data-size", "--algorithm", "GP", "--bo-target-type", "distBO", "--target-iterations", "20",
-                "--target-rand-iterations", "0", "--embed-op", "joint", "--max-embed-size", "5000",
-                "--batch-size", "1000", "--n-epochs", "10000", "--n-opt-iterations", "10",
-                "--first_early_stop_epoch", "5000", "--weight_dim_1_y", "20", "--weight_dim_2_y", "10"] + COMMON,
-    # Parkinson (BASELINE config 3): no config script; CLI defaults of experiments/train_test.py:28-91 (30 random
-    # source evaluations, 30 target iterations, 5000 epochs, early stop from 1000, batch 1000, polish 10) + --float64
-    "parkinson": ["patient_vary", "--data-seed", "0", "--opt-seed", "0", "--float64"],
-}
+# the command lines experiments/*_config.py print for seed 0, method distBO, algorithm GP (config 3: CLI defaults);
+# protein runs the reference's default objective, an unseeded random forest (models.py:225-237) drawing from numpy's
+# global stream, which main() seeds once - its state at the start of the target search is recorded for the replays
+CONFIGS = {"toy": SHIPPED_COMMAND_LINES["config1"], "protein": SHIPPED_COMMAND_LINES["config2"],
+           "parkinson": SHIPPED_COMMAND_LINES["config3"]}
 
 
 def install_py3_shims():

@@ -30,23 +30,9 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 def real_data(name, args):
     """The reference's data files, committed as fixtures (bit-packed fingerprints / patient tables)."""
-    from sklearn.utils import check_random_state
-    from distbo_b200.data.load_datasets import parkinson_tasks, protein_tasks
-    rs = check_random_state(args.data_seed)
-    if name == "protein":
-        z = np.load(os.path.join(GOLD, "protein_full.npz"))
-        tables = []
-        for i in range(len(z["names"])):
-            bits = np.unpackbits(z["bits_%d" % i], axis=1)[:, :166].astype(np.float64)
-            lab = z["labels_%d" % i].astype(np.float64)
-            tables.append(np.hstack([np.zeros((len(bits), 1)), bits, lab[:, None]]))
-        args.model = "forest"
-        return protein_tasks(tables, [str(n) for n in z["names"]], args.target_group, random_state=rs,
-                             test_size=args.test_size)
-    z = np.load(os.path.join(GOLD, "parkinson_full.npz"))
-    args.model = "ridge"
-    return parkinson_tasks([z["patient_%d" % i] for i in range(42)], args.target_group, random_state=rs,
-                           preprocess=args.preprocess, label=args.park_labels, test_size=args.test_size)
+    from distbo_b200 import experiments as X
+    args.data_dir = os.path.join(GOLD, "%s_full.npz" % name)
+    return X.generate_data(args)
 
 
 def main():
