@@ -76,10 +76,11 @@ struct Plan {
   std::vector<cudaEvent_t> ev_panel, ev_first;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   bool lookahead = true;
-  int* d_flags = nullptr;    // [nb][NFLAG] sub-step / "inverse published" flags of the panel kernels
+  int* d_flags = nullptr;    // [nb][NFLAG] sub-step flags of the panel kernels, then [nb] "second relay CTA has its copy"
   double* d_relay = nullptr; // [2][128*128] relay products (see panel_kernel)
   int sms = 148;
   bool relay_on = true;      // DISTBO_POTRF_RELAY=0 switches the relay CTA off (A/B measurements)
+  bool relay2_on = true;     // DISTBO_POTRF_RELAY2=0: the relay product stays on one CTA (A/B measurements)
   bool small_ok = false;     // the whole-matrix cooperative kernel can be used (n_pad <= 2048, all CTAs resident)
   int* d_small_flags = nullptr;   // done [nb*nb] | sub [nb*4] | xf [nb*4]
 };
@@ -136,6 +137,8 @@ struct PanelArgs {
   // relay_ready[kb] = the relay product for diagonal tile kb is in `relay`.  Null: launches are serialised.
   int* done;
   int* relay_ready;
+  int relay2;               // 1: the LAST CTA of the grid is the second relay CTA (half 1 of the relay product)
+  int* r2_loaded;           // relay2: set by the second relay CTA once it holds its copy of tile (kb+1, kb)
 };
 
 constexpr int PANEL_SMEM = (PB * PLD + STAGES * STAGE_ELEMS) * (int)sizeof(double);  // 217088 >= POTF2_SMEM
@@ -148,12 +151,60 @@ constexpr int NFLAG = 4;   // per column block: the four sub-step flags of the d
 // tile in shared memory and to Ab (global, leading dimension ld); if xflags != null, xflags[s] is set once
 // column group s is visible device-wide.  RELAY: also accumulates P = X X^T, one rank-32 update per sub-step,
 // and stores it to Pout [128][128] (the next launch's diagonal tile takes its update from there).
-template <bool RELAY>
+// Relay product P = X X^T (X = the solved tile of row block kb+1, 128 x 128): the next launch's diagonal tile only
+// reads its LOWER triangle, i.e. 10 of the 16 32x32 blocks, and one SM needs 17 us for the full 128^3 product - as
+// long as the whole panel chain of round 1.  The 10 blocks are therefore split over TWO CTAs ("halves", 80 8x8
+// tiles each; both solve the same row block, only the first stores X):
+//   half 0: blocks (0,0) (1,0) (1,1) (2,0) (2,1)        half 1: blocks (2,2) (3,0) (3,1) (3,2) (3,3)
+// Warp w of a half owns a strip of 8 tiles in one 8-row tile row (A fragment shared) plus 2 tiles of the half's
+// leftover 32x32 block: 12 shared-memory fragment loads per 10 DMMAs and k-step.
+struct RelayMap {
+  int mr0, mc0;   // main strip: rows mr0..mr0+7, columns mc0 .. mc0+63 (8 tiles)
+  int er0, ec0;   // extra pair: rows er0..er0+7, columns ec0 .. ec0+15 (2 tiles)
+};
+__device__ __forceinline__ RelayMap relay_map(int half, int w) {
+  RelayMap m;
+  if (half == 0) {
+    m.mr0 = 32 + w * 8; m.mc0 = 0; m.er0 = (w >> 1) * 8; m.ec0 = (w & 1) * 16;
+  } else {
+    m.mr0 = 96 + (w >> 1) * 8; m.mc0 = (w & 1) * 64; m.er0 = 64 + (w >> 1) * 8; m.ec0 = 64 + (w & 1) * 16;
+  }
+  return m;
+}
+// pr[0..7] main strip, pr[8..9] extra pair;  P += X[:, c0 .. c0+31] X[:, c0 .. c0+31]^T on the map's tiles
+__device__ __forceinline__ void relay_accumulate(double (&pr)[10][2], const RelayMap& m, const double* sT, int c0,
+                                                 int lr, int lk) {
+#pragma unroll
+  for (int k = 0; k < SB; k += 4) {
+    const double am = sT[(m.mr0 + lr) * PLD + c0 + k + lk];
+    const double ae = sT[(m.er0 + lr) * PLD + c0 + k + lk];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dmma884(pr[t][0], pr[t][1], am, sT[(m.mc0 + t * 8 + lr) * PLD + c0 + k + lk]);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) dmma884(pr[8 + t][0], pr[8 + t][1], ae, sT[(m.ec0 + t * 8 + lr) * PLD + c0 + k + lk]);
+  }
+}
+__device__ __forceinline__ void relay_store(const double (&pr)[10][2], const RelayMap& m, double* Pout, int lr, int lk) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+    *reinterpret_cast<double2*>(Pout + (size_t)(m.mr0 + lr) * PB + m.mc0 + t * 8 + 2 * lk) = make_double2(pr[t][0], pr[t][1]);
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+    *reinterpret_cast<double2*>(Pout + (size_t)(m.er0 + lr) * PB + m.ec0 + t * 8 + 2 * lk) =
+        make_double2(pr[8 + t][0], pr[8 + t][1]);
+}
+
+// RELAY: 0 = plain consumer; 1 = one half of the relay product (`half`); 2 = both halves (no second relay CTA).
+// store_x: write the solved column groups to Ab (false on the second relay CTA, which only duplicates the solve).
+// gate: the tile is solved IN PLACE in global memory, and the second relay CTA reads the unsolved tile when it
+// starts - the storing CTA therefore waits for *gate (set by the second CTA once its copy is in shared memory)
+// before its first global store.
+template <int RELAY>
 __device__ __forceinline__ void stepwise_solve(double* smem, const double* A, const double* W, int ld, int n0,
                                                const int* sub, double* Ab, int* xflags, double* Pout,
-                                               int32_t* info) {
+                                               int32_t* info, int half = 0, bool store_x = true,
+                                               int* gate = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
   const int lr = lane >> 2, lk = lane & 3;
   double* sT = smem;
   double* sLr = smem + PB * PLD;            // [32][PLD] rows 32s..32s+31 of L_kk (columns 0..32s-1)
@@ -161,25 +212,23 @@ __device__ __forceinline__ void stepwise_solve(double* smem, const double* A, co
   const double* Lkk = A + (size_t)n0 * ld + n0;
   const double* Wkk = W + (size_t)n0 * ld + n0;
   const int r0 = warp * 16;                 // this warp's 16 rows of the tile
-  double pr[RELAY ? 8 : 1][4][2];           // relay only: P accumulators (64 x 32 warp tile)
-  if (RELAY) {
+  double pr[10][2], pr2[10][2];             // dead (and removed) in the instantiations that do not use them
+  const RelayMap map = relay_map(RELAY == 2 ? 0 : half, warp), map2 = relay_map(1, warp);
+  if constexpr (RELAY != 0) {
 #pragma unroll
-    for (int mi = 0; mi < (RELAY ? 8 : 1); ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) pr[mi][ni][0] = pr[mi][ni][1] = 0.0;
+    for (int t = 0; t < 10; ++t) pr[t][0] = pr[t][1] = pr2[t][0] = pr2[t][1] = 0.0;
   }
+  const int sr = tid >> 3, sc = (tid & 7) * 2;   // staging: thread = (row of the 32-row slab, 16-byte column slot)
   for (int sb = 0; sb < 4; ++sb) {
     const int c0 = sb * SB;
     if (tid == 0) spin_until_set(const_cast<int*>(sub) + sb, info);
     __syncthreads();                        // flag seen; previous step's staging buffers are free
-    for (int idx = tid; idx < SB * c0; idx += GEMM_THREADS) {
-      const int r = idx / c0, c = idx - r * c0;
-      sLr[r * PLD + c] = __ldcg(Lkk + (size_t)(c0 + r) * ld + c);
-    }
-    for (int idx = tid; idx < SB * SB; idx += GEMM_THREADS) {
-      const int r = idx >> 5, c = idx & 31;
-      sDi[r * DLD + c] = __ldcg(Wkk + (size_t)(c0 + r) * ld + c0 + c);
-    }
+    for (int c = sc; c < c0; c += 16)
+      *reinterpret_cast<double2*>(&sLr[sr * PLD + c]) =
+          __ldcg(reinterpret_cast<const double2*>(Lkk + (size_t)(c0 + sr) * ld + c));
+    for (int c = sc; c < SB; c += 16)
+      *reinterpret_cast<double2*>(&sDi[sr * DLD + c]) =
+          __ldcg(reinterpret_cast<const double2*>(Wkk + (size_t)(c0 + sr) * ld + c0 + c));
     __syncthreads();
     double xa[2][4][2];
 #pragma unroll
@@ -227,6 +276,7 @@ __device__ __forceinline__ void stepwise_solve(double* smem, const double* A, co
         for (int ni = 0; ni < 4; ++ni) dmma884(xo[mi][ni][0], xo[mi][ni][1], af[mi], bf[ni]);
     }
     __syncwarp();
+    if (gate && sb == 0) wait_flag(gate, info);
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -234,7 +284,7 @@ __device__ __forceinline__ void stepwise_solve(double* smem, const double* A, co
         const int r = r0 + mi * 8 + lr, c = c0 + ni * 8 + 2 * lk;
         const double2 v = make_double2(xo[mi][ni][0], xo[mi][ni][1]);
         *reinterpret_cast<double2*>(&sT[r * PLD + c]) = v;
-        *reinterpret_cast<double2*>(Ab + (size_t)r * ld + c) = v;
+        if (store_x) *reinterpret_cast<double2*>(Ab + (size_t)r * ld + c) = v;
       }
     if (xflags) {
       __syncthreads();
@@ -243,32 +293,15 @@ __device__ __forceinline__ void stepwise_solve(double* smem, const double* A, co
         atomicExch(xflags + sb, 1);
       }
     }
-    if (RELAY) {
+    if constexpr (RELAY != 0) {
       __syncthreads();                      // columns [c0, c0+32) of the tile are complete in sT
-#pragma unroll
-      for (int k = 0; k < SB; k += 4) {     // P += X_s X_s^T
-        double af[8], bf[4];
-#pragma unroll
-        for (int mi = 0; mi < 8; ++mi) af[mi] = sT[(wm * 64 + mi * 8 + lr) * PLD + c0 + k + lk];
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) bf[ni] = sT[(wn * 32 + ni * 8 + lr) * PLD + c0 + k + lk];
-#pragma unroll
-        for (int mi = 0; mi < (RELAY ? 8 : 1); ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) dmma884(pr[mi][ni][0], pr[mi][ni][1], af[mi], bf[ni]);
-      }
+      relay_accumulate(pr, map, sT, c0, lr, lk);
+      if constexpr (RELAY == 2) relay_accumulate(pr2, map2, sT, c0, lr, lk);
     }
   }
-  if (RELAY) {
-#pragma unroll
-    for (int mi = 0; mi < (RELAY ? 8 : 1); ++mi) {
-      const int r = wm * 64 + mi * 8 + lr;
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const int c = wn * 32 + ni * 8 + lk * 2;
-        *reinterpret_cast<double2*>(Pout + (size_t)r * PB + c) = make_double2(pr[mi][ni][0], pr[mi][ni][1]);
-      }
-    }
+  if constexpr (RELAY != 0) {
+    relay_store(pr, map, Pout, lr, lk);
+    if constexpr (RELAY == 2) relay_store(pr2, map2, Pout, lr, lk);
   }
   __syncthreads();                          // sT and the staging buffers may be overwritten
 }
@@ -283,9 +316,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
   double* sT = smem;  // [128][PLD] tile
   tl_start(p.tl, 2 * kb);
 
-  // CTA 0 owns the diagonal block; CTA c >= 1 owns row blocks kb + c, kb + c + (G-1), ...
-  const int stride = (blockIdx.x == 0) ? nb : (int)gridDim.x - 1;
-  for (int i = kb + (int)blockIdx.x; i < nb; i += stride) {
+  // CTA 0 owns the diagonal block; CTA c = 1 .. G-1 owns row blocks kb + c, kb + c + (G-1), ...; with relay2 the
+  // extra CTA G duplicates the solve of row block kb + 1 and forms the second half of the relay product
+  const int n_solve = (int)gridDim.x - 1 - p.relay2;
+  const bool second_relay = p.relay2 && (int)blockIdx.x == (int)gridDim.x - 1;
+  const int stride = (blockIdx.x == 0 || second_relay) ? nb : n_solve;
+  for (int i = second_relay ? kb + 1 : kb + (int)blockIdx.x; i < nb; i += stride) {
     const int m0 = i * BM;
     double acc[8][4][2];
 #pragma unroll
@@ -356,9 +392,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) panel_kernel(PanelArgs p) {
     {
       const bool relay = p.relay && blockIdx.x == 1 && i == kb + 1;
       const int* sub = p.flags + kb * NFLAG;
-      if (relay) stepwise_solve<true>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, p.relay + (size_t)((kb + 1) & 1) * PB * PB, p.info);
-      else stepwise_solve<false>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, nullptr, p.info);
-      if (p.done && tid == 0) {   // stepwise_solve ended with a barrier: cumulative fence, then publish
+      double* Pout = p.relay + (size_t)((kb + 1) & 1) * PB * PB;
+      if (second_relay) {
+        if (tid == 0) atomicExch(p.r2_loaded, 1);   // after the barrier above: every thread's part of the tile is in sT
+        stepwise_solve<1>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, Pout, p.info, 1, false);
+      } else if (relay && p.relay2) {
+        stepwise_solve<1>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, Pout, p.info, 0, true, p.r2_loaded);
+      }
+      else if (relay) stepwise_solve<2>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, Pout, p.info);
+      else stepwise_solve<0>(smem, p.A, p.W, ld, n0, sub, Ab, nullptr, nullptr, p.info);
+      if (p.done && !second_relay && tid == 0) {   // stepwise_solve ended with a barrier: cumulative fence, then publish
         __threadfence();
         atomicExch(p.done + kb * nb + i, 1);
         if (relay) atomicExch(p.relay_ready + kb + 1, 1);
@@ -471,7 +514,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) potrf_small_kernel(SmallArgs 
     potf2_factor_invert(smem, m0, p.info, dbg, Potf2Publish{Ab, Wb, ld, p.sub + c * 4}, false);
     return;
   }
-  stepwise_solve<false>(smem, p.A, p.W, ld, n0, p.sub + c * 4, Ab, (r == c + 1) ? p.xf + c * 4 : nullptr, nullptr, p.info);
+  stepwise_solve<0>(smem, p.A, p.W, ld, n0, p.sub + c * 4, Ab, (r == c + 1) ? p.xf + c * 4 : nullptr, nullptr, p.info);
   if (tid == 0) {   // stepwise_solve ended with a barrier: every store of the tile is ordered before this fence
     __threadfence();
     atomicExch(p.done + r * nbt + c, 1);
@@ -615,7 +658,15 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
         for (int i = c; i < nb; ++i) out.push_back(make_int4(T(i), T(c), T(applied[c]), T(upto)));
         return (double)(nb - c) * (upto - applied[c]);
       };
+      // Tail: once the panel chain is the bound (the rank-128 update of everything that is left takes less time
+      // than one panel), nothing is deferred any more - from step `tail` on the window covers every remaining
+      // column (W = infinity, no far launches); its first launch there catches the far columns up.
+      // Measured at N = 8192 (nb = 64, eager / graph ms): no tail 8.02 / 8.22, tail from 20: 7.87 / 7.99, 24: 7.71 / 7.84,
+      // 28: 7.63 / 7.73, 32: 7.56 / 7.74, 36: 7.66 / 7.88.
+      int tail = nb - 34;
+      if (const char* env = getenv("DISTBO_POTRF_TAIL")) tail = atoi(env);
       for (int kb = 0; kb < nb; ++kb) {
+        const int Wk = (tail >= 0 && kb >= tail) ? nb : W;
         p->pend_lo[kb] = applied[kb];          // the panel kernel applies [applied, kb) itself
         p->wait_next[kb] = last_next[kb];
         p->wait_window[kb] = last_window[kb];
@@ -634,7 +685,7 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
         }
         {
           std::vector<int4> wt;
-          for (int c = kb + 4; c < nb && c <= kb + W; ++c) {
+          for (int c = kb + 4; c < nb && c <= kb + Wk; ++c) {
             st.near_work += column_tiles(wt, c, kb + 1);
             applied[c] = kb + 1;
             st.window_wait_far = std::max(st.window_wait_far, last_far[c]);
@@ -647,7 +698,7 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
         if ((kb + 1) % G == 0) {
           // columns that no near launch of the next G steps reaches
           std::vector<int4> ft;
-          for (int c = kb + 1 + G + W; c < nb; ++c) {
+          for (int c = kb + 1 + G + Wk; c < nb; ++c) {
             if (applied[c] >= kb + 1) continue;
             st.far_work += column_tiles(ft, c, kb + 1);
             applied[c] = kb + 1;
@@ -743,11 +794,13 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
   p->lookahead = !(la && la[0] == '0');
   const char* rl = getenv("DISTBO_POTRF_RELAY");
   p->relay_on = !(rl && rl[0] == '0');
+  const char* rl2 = getenv("DISTBO_POTRF_RELAY2");
+  p->relay2_on = !(rl2 && rl2[0] == '0');
   {
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  if (cudaMalloc(&p->d_flags, (size_t)nb * NFLAG * sizeof(int)) != cudaSuccess ||
+  if (cudaMalloc(&p->d_flags, (size_t)nb * (NFLAG + 1) * sizeof(int)) != cudaSuccess ||
       cudaMalloc(&p->d_relay, (size_t)2 * PB * PB * sizeof(double)) != cudaSuccess) {
     cudaFree(p->d_tiles);
     if (p->d_flags) cudaFree(p->d_flags);
@@ -823,7 +876,7 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
   }
 
   if (!p->steps.empty() && p->lookahead) {
-    DB_CUDA(cudaMemsetAsync(p->d_flags, 0, (size_t)nb * NFLAG * sizeof(int), U));
+    DB_CUDA(cudaMemsetAsync(p->d_flags, 0, (size_t)nb * (NFLAG + 1) * sizeof(int), U));
     GemmArgs upd{};   // C -= L[i, k range) L[j, k range)^T, k range per tile
     upd.A = A; upd.B = A; upd.C = A; upd.Cin = A;
     upd.lda = upd.ldb = upd.ldc = upd.ldcin = n;
@@ -853,10 +906,12 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
       if (p->wait_window[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_window[p->wait_window[kb]], 0));
       if (p->wait_far[kb] >= 0) DB_CUDA(cudaStreamWaitEvent(P, p->ev_far[p->wait_far[kb]], 0));
       const int use_relay = (p->relay_on && kb >= 1 && g_prev >= 2 && p->pend_lo[kb] <= kb - 1) ? 1 : 0;
+      // second relay CTA: once the panel chain is the bound (every row block has its own CTA), launches serialised
+      const int relay2 = (p->relay_on && p->relay2_on && !p->chain && g_this >= 2 && g_this == nb - kb) ? 1 : 0;
       PanelArgs pa{A, W, n, kb, nb, p->pend_lo[kb], info, p->d_flags, p->relay_on ? p->d_relay : nullptr, use_relay,
-                   g_timeline, done, relay_ready};
+                   g_timeline, done, relay_ready, relay2, p->d_flags + nb * NFLAG + kb};
       g_prev = g_this;
-      panel_kernel<<<g_this, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
+      panel_kernel<<<g_this + relay2, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
       DB_CHECK_LAUNCH();
       const Plan::Step& st = p->steps[kb];
       if (st.next.cnt > 0 || st.window.cnt > 0 || st.far.cnt > 0) DB_CUDA(cudaEventRecord(p->ev_panel[kb], P));
@@ -903,7 +958,7 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
   }
 
   {
-    DB_CUDA(cudaMemsetAsync(p->d_flags, 0, (size_t)nb * NFLAG * sizeof(int), U));
+    DB_CUDA(cudaMemsetAsync(p->d_flags, 0, (size_t)nb * (NFLAG + 1) * sizeof(int), U));
     GemmArgs rest{};  // C -= P P^T on the tiles (i, j), j >= kb + 2
     rest.A = A; rest.B = A; rest.C = A; rest.Cin = A;
     rest.lda = rest.ldb = rest.ldc = rest.ldcin = n;
@@ -923,10 +978,11 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
       const int g_this = fork ? panel_ctas(nb, kb, p->sms, running_rest_tiles, kb - p->pend_lo[kb], running_share) : nb - kb;
       // the previous launch had a relay CTA (row block kb) whenever it had more than one CTA
       const int use_relay = (p->relay_on && kb >= 1 && g_prev >= 2 && p->pend_lo[kb] <= kb - 1) ? 1 : 0;
+      const int relay2 = (p->relay_on && p->relay2_on && g_this >= 2 && g_this == nb - kb) ? 1 : 0;
       PanelArgs pa{A, W, n, kb, nb, p->pend_lo[kb], info, p->d_flags, p->relay_on ? p->d_relay : nullptr, use_relay,
-                   g_timeline, nullptr, nullptr};
+                   g_timeline, nullptr, nullptr, relay2, p->d_flags + nb * NFLAG + kb};
       g_prev = g_this;
-      panel_kernel<<<g_this, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
+      panel_kernel<<<g_this + relay2, GEMM_THREADS, PANEL_SMEM, P>>>(pa);
       DB_CHECK_LAUNCH();
       const int q = p->rest_after[kb];
       if (q >= 0) {

@@ -64,7 +64,7 @@ __device__ __forceinline__ int chain_1x1_shfl(double (&a)[SB], int lane, double*
 // u = (r c1 - q c2) / det, v = (p c2 - q c1) / det, a[k] -= u C1[k] + v C2[k] for k >= j + 2.
 // sC[j] = column j as it was BEFORE the pair step (c1), sC[j+1] = column j+1 before the pair step (c2, i.e. not yet
 // updated by column j); the scaling pass forms l_j = c1 / sqrt(p), l_{j+1} = (c2 - (q/p) c1) / sqrt(r - q^2 / p).
-__device__ __forceinline__ int chain_2x2(double (&a)[SB], int lane, double* sC) {
+__device__ __forceinline__ int chain_2x2_bench(double (&a)[SB], int lane, double* sC) {
   int bad = 0;
 #pragma unroll
   for (int j = 0; j < SB; j += 2) {
@@ -106,7 +106,7 @@ __global__ void bench_kernel(const double* __restrict__ A, double* __restrict__ 
   else if (variant == 1) bad = factor_32(a, myr, lane);
   else if (variant == 2) bad = chain_1x1(a, lane, sC);
   else if (variant == 3) bad = chain_1x1_shfl(a, lane, sC);
-  else if (variant == 4) bad = chain_2x2(a, lane, sC);
+  else if (variant == 4) bad = chain_2x2_bench(a, lane, sC);
   else {
     double x = A[lane], y = A[lane + 32];
 #pragma unroll

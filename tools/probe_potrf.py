@@ -12,7 +12,7 @@ import torch
 from distbo_b200 import _lib, engine as eng
 
 out = {"env": {k: v for k, v in os.environ.items() if k.startswith("DISTBO_")}}
-for N in (8192, 4096, 3000):
+for N in [int(v) for v in os.environ.get("DISTBO_PROBE_SIZES", "8192,4096,3000").split(",")]:
     rs = np.random.RandomState(0)
     theta, y = rs.randn(N, 8), rs.randn(N)
     e = eng.GPEngine(8)
