@@ -442,7 +442,12 @@ class gp_regressor(object):
         elif self._use_graph and self._graph_warm >= 1:
             g = torch.cuda.CUDAGraph()
             try:
-                with torch.cuda.graph(g):
+                # an explicit capture stream ON THE ENGINE'S DEVICE: torch.cuda.graph's default capture stream is
+                # created once per process, on whichever device was current then - a capture for another device
+                # through it records nothing (and its replays would silently do nothing)
+                if getattr(self, "_capture_stream", None) is None or self._capture_stream.device != self.engine.dev:
+                    self._capture_stream = torch.cuda.Stream(device=self.engine.dev)
+                with torch.cuda.graph(g, stream=self._capture_stream):
                     self._epoch_body()
                 self._graph = g
                 g.replay()
