@@ -8,7 +8,7 @@ LIB := distbo_b200/libdistbo_b200.so
 
 all: $(LIB)
 
-%.o: %.cu distbo_b200/csrc/common.cuh distbo_b200/csrc/gemm_core.cuh distbo_b200/csrc/potf2.cuh include/distbo_b200.h
+%.o: %.cu distbo_b200/csrc/common.cuh distbo_b200/csrc/gemm_core.cuh distbo_b200/csrc/potf2.cuh distbo_b200/csrc/tma.cuh include/distbo_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(OBJ)

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "gemm_core.cuh"
+#include "tma.cuh"
 
 namespace db {
 
@@ -88,6 +89,7 @@ struct ScoreArgs {
   const double* V;
   const double* Kst;
   int n_pad, slices;
+  int tile_w;             // candidates per partial-sum tile: TN (DMMA path) or I8_TILE (tcgen05 path)
   const double* log_scale;
   const double* mean_param;
   long long c_begin, M, index_offset;
@@ -181,9 +183,9 @@ __global__ void __launch_bounds__(128) score_finish_kernel(ScoreArgs p) {
   long long idx = 0x7fffffffffffffffLL;
   if (c < p.M) {
     double sumsq = 0.0, dot = 0.0;
-    const int t64 = (n0 + tid) / TN, l64 = (n0 + tid) % TN;
+    const int t64 = (n0 + tid) / p.tile_w, l64 = (n0 + tid) % p.tile_w;
     for (int sl = 0; sl < p.slices; ++sl) {
-      const double* src = p.partial + (((size_t)t64 * p.slices + sl) * TN + l64) * 2;
+      const double* src = p.partial + (((size_t)t64 * p.slices + sl) * p.tile_w + l64) * 2;
       sumsq += src[0];
       dot += src[1];
     }
@@ -231,6 +233,339 @@ __global__ void merge_best_kernel(const double* __restrict__ bv, const long long
     }
   *best_val = v;
   *best_idx = i;
+}
+
+
+// =========================================================================================================
+// tcgen05 path: the same contraction A = K_* W^T on the 5th-generation tensor cores, exact in integers.
+//
+// fp64 has no tcgen05 kind, int8 has (kind::i8, s32 accumulators in tensor memory, 4x the DMMA rate per byte
+// of operand).  Both operands are cut into I8_NS = 8 signed base-128 digits of a 56-bit fixed-point number
+// (Ozaki splitting):   W[i,k]   = 2^(e_i - 55) sum_s d_s[i,k] 2^(49 - 7 s),   e_i = exponent of max_k |W[i,k]|
+//                      K_*[c,k] = 2^(f - 55)   sum_t q_t[c,k] 2^(49 - 7 t),   f   = exponent of scale max|kvec|
+// so that   A[c,i] = 2^(e_i + f - 61) sum_l 2^(49 - 7 l) acc_l[c,i],   acc_l = sum_{s+t=l} sum_k q_t[c,k] d_s[i,k].
+// Every acc_l is an exact int32 dot product (|digit| <= 64: |acc_l| <= 8 * n_pad * 2^12 < 2^31 up to
+// n_pad = 32768); the 36 digit pairs with l = s + t <= 7 are kept (the dropped ones are below 2^-52 of
+// max|W_i| max|K_*| per term, the digit representation itself is exact to 2^-56).  Per (128-candidate tile,
+// 64-row block of W) the eight level accumulators fill the SM's tensor memory (8 x 64 columns x 128 lanes);
+// they are folded into fp64 only once, after the whole k range: two exact int64 Horner sums, two conversions,
+// one fma.  A warp-specialised CTA per SM: one thread issues the TMA loads of the digit planes (64-byte
+// swizzle, 96 KB per stage, two stages), one thread issues the 72 MMAs per stage, four warps read the
+// accumulators back (tcgen05.ld) and carry sum A^2 and sum A V per candidate in registers.
+// =========================================================================================================
+constexpr int I8_NS = 8;          // digits per operand
+constexpr int I8_TILE = 128;      // candidates per tile = MMA M
+constexpr int I8_RB = 64;         // W rows per row block = MMA N
+constexpr int I8_KC = 64;         // k per stage (bytes per smem row; two K = 32 MMA steps)
+constexpr int I8_STAGES = 2;
+constexpr int I8_STAGE_A = I8_NS * I8_TILE * I8_KC;   // 65536
+constexpr int I8_STAGE_B = I8_NS * I8_RB * I8_KC;     // 32768
+constexpr int I8_STAGE = I8_STAGE_A + I8_STAGE_B;
+constexpr int I8_SMEM = I8_STAGES * I8_STAGE + 1024 /* alignment slack */ + 128 /* barriers, tmem slot */;
+constexpr int I8_THREADS = 192;   // warp 0: TMA, warp 1: MMA + tensor-memory owner, warps 2-5: read-back
+constexpr int I8_MAX_RB = 512;    // n_pad <= 32768
+constexpr int I8_MAX_SLICES = 64;
+constexpr int I8_FRAC = 55;       // fractional bits of the fixed-point operands
+
+struct I8Args {
+  int n_rb, ntiles, slices, tiles_in_flight;
+  const double* rowscale;   // [n_pad] 2^e_i
+  const double* kexp;       // [2]: 2^(55 - f), 2^(f - 61)
+  const double* V;
+  double* partial;          // [ntiles][slices][128][2]
+  unsigned short off[I8_MAX_SLICES + 1];   // row blocks of slice s: order[off[s] .. off[s+1])
+  unsigned short order[I8_MAX_RB];
+};
+
+// 56-bit fixed point -> 8 balanced base-128 digits, most significant first (d[0] in [-64, 64], others in [-64, 63])
+__device__ __forceinline__ void digits8(double x_scaled, int (&dg)[I8_NS]) {
+  long long v = __double2ll_rn(x_scaled);
+#pragma unroll
+  for (int s = I8_NS - 1; s > 0; --s) {
+    const int low = (int)((v + 64) & 127) - 64;
+    dg[s] = low;
+    v = (v - low) >> 7;
+  }
+  dg[0] = (int)v;
+}
+
+// 2^(55 - f) and 2^(f - 61) with f = exponent of scale * max_i |kvec_i| (K_* = scale * matern * kvec, matern <= 1)
+__global__ void __launch_bounds__(256) i8_kexp_kernel(const double* __restrict__ kvec, int N,
+                                                      const double* __restrict__ log_scale, double* kexp) {
+  __shared__ double red[256];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) m = fmax(m, fabs(kvec[i]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int f = 0;
+    const double bound = exp(*log_scale) * red[0];
+    if (bound > 0.0 && isfinite(bound)) frexp(bound, &f);
+    kexp[0] = ldexp(1.0, I8_FRAC - f);
+    kexp[1] = ldexp(1.0, f - 61);
+  }
+}
+
+// digit planes of W (once per fit): W8[s][i][k], rowscale[i] = 2^e_i.  One CTA per row; k > i is zero.
+__global__ void __launch_bounds__(256) i8_wsplit_kernel(const double* __restrict__ W, int n_pad,
+                                                        signed char* __restrict__ W8, double* __restrict__ rowscale) {
+  __shared__ double red[256];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const double* row = W + (size_t)i * n_pad;
+  double m = 0.0;
+  for (int k = tid; k <= i; k += 256) m = fmax(m, fabs(row[k]));
+  red[tid] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] = fmax(red[tid], red[tid + s]);
+    __syncthreads();
+  }
+  int e = 0;
+  if (red[0] > 0.0 && isfinite(red[0])) frexp(red[0], &e);
+  if (tid == 0) rowscale[i] = ldexp(1.0, e);
+  const double sc = ldexp(1.0, I8_FRAC - e);
+  const size_t plane = (size_t)n_pad * n_pad;
+  for (int k4 = tid * 4; k4 < n_pad; k4 += 1024) {
+    unsigned pk[I8_NS];
+#pragma unroll
+    for (int s = 0; s < I8_NS; ++s) pk[s] = 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k4 + u;
+      int dg[I8_NS];
+      digits8(k <= i ? row[k] * sc : 0.0, dg);
+#pragma unroll
+      for (int s = 0; s < I8_NS; ++s) pk[s] |= (unsigned)(dg[s] & 0xff) << (8 * u);
+    }
+#pragma unroll
+    for (int s = 0; s < I8_NS; ++s)
+      *reinterpret_cast<unsigned*>(W8 + s * plane + (size_t)i * n_pad + k4) = pk[s];
+  }
+}
+
+// digit planes of the K_* chunk: K8[s][c][i] (i contiguous), zero on pad rows / pad candidates.
+// CTA = KST_CAND candidates; a thread takes four consecutive observations at a time (32-bit stores per plane).
+template <int D>
+__global__ void __launch_bounds__(256, 2) i8_kst_kernel(const double* __restrict__ theta_s,
+                                                        const double* __restrict__ sqnorm, int N, int n_pad, int d,
+                                                        const double* __restrict__ log_bw,
+                                                        const double* __restrict__ kvec,
+                                                        const double* __restrict__ log_scale,
+                                                        const double* __restrict__ theta_c,
+                                                        const double* __restrict__ c_shift,
+                                                        const double* __restrict__ c_scale, long long c_begin,
+                                                        long long M, const double* __restrict__ kexp, int chunk_rows,
+                                                        signed char* __restrict__ K8) {
+  __shared__ double ys[KST_CAND][D];
+  __shared__ double ysq[KST_CAND];
+  const int tid = threadIdx.x;
+  const long long cl0 = (long long)blockIdx.x * KST_CAND;
+  if (tid < KST_CAND * D) {
+    const int q = tid / D, k = tid % D;
+    const long long c = c_begin + cl0 + q;
+    double v = 0.0;
+    if (k < d && c < M) {
+      v = theta_c[c * d + k];
+      if (c_shift) v = (v - c_shift[k]) / c_scale[k];
+      v = v / exp(log_bw[k]);
+    }
+    ys[q][k] = v;
+  }
+  __syncthreads();
+  if (tid < KST_CAND) {
+    double s = 0.0;
+    for (int k = 0; k < d; ++k) s += ys[tid][k] * ys[tid][k];
+    ysq[tid] = s;
+  }
+  __syncthreads();
+  const double scale = exp(*log_scale);
+  const double fx = kexp[0];
+  const size_t plane = (size_t)chunk_rows * n_pad;
+  for (int i4 = tid * 4; i4 < n_pad; i4 += 1024) {
+    double sqi[4], kv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sqi[u] = sqnorm[i4 + u];
+      kv[u] = (i4 + u < N) ? kvec[i4 + u] : 0.0;
+    }
+    double xi[D <= 8 ? 4 : 1][D <= 8 ? D : 1];
+    if (D <= 8) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < D; ++k) xi[D <= 8 ? u : 0][D <= 8 ? k : 0] = (k < d) ? theta_s[(size_t)(i4 + u) * d + k] : 0.0;
+    }
+#pragma unroll 1
+    for (int q = 0; q < KST_CAND; ++q) {
+      double dot[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double yk = ys[q][k];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (D <= 8) dot[u] += xi[D <= 8 ? u : 0][D <= 8 ? k : 0] * yk;
+          else if (k < d) dot[u] += theta_s[(size_t)(i4 + u) * d + k] * yk;
+        }
+      }
+      unsigned pk[I8_NS];
+#pragma unroll
+      for (int s = 0; s < I8_NS; ++s) pk[s] = 0u;
+      const bool cand_ok = c_begin + cl0 + q < M;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double d2 = -2.0 * dot[u] + sqi[u] + ysq[q];
+        double v = (scale * matern32_from_d2(d2)) * kv[u];
+        if (i4 + u >= N || !cand_ok) v = 0.0;
+        int dg[I8_NS];
+        digits8(v * fx, dg);
+#pragma unroll
+        for (int s = 0; s < I8_NS; ++s) pk[s] |= (unsigned)(dg[s] & 0xff) << (8 * u);
+      }
+#pragma unroll
+      for (int s = 0; s < I8_NS; ++s)
+        *reinterpret_cast<unsigned*>(K8 + s * plane + (size_t)(cl0 + q) * n_pad + i4) = pk[s];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(I8_THREADS, 1)
+    score_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapW,
+                    const __grid_constant__ I8Args p) {
+  extern __shared__ unsigned char smem_raw[];
+  const unsigned raw = tma::smem_u32(smem_raw);
+  const unsigned base = (raw + 1023u) & ~1023u;                 // stage buffers: 1024-byte aligned
+  const unsigned bars = base + I8_STAGES * I8_STAGE;            // full[2], empty[2], tmem_full, tmem_empty
+  const unsigned bar_full = bars, bar_empty = bars + 8 * I8_STAGES;
+  const unsigned bar_tfull = bars + 16 * I8_STAGES, bar_tempty = bar_tfull + 8;
+  const unsigned slot = bar_tempty + 8;
+  volatile unsigned* slot_ptr = reinterpret_cast<volatile unsigned*>(smem_raw + (slot - raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = blockIdx.x % p.slices, tl = blockIdx.x / p.slices;
+
+  if (warp == 0 && lane == 0) {
+    tma::prefetch_map(&mapK);
+    tma::prefetch_map(&mapW);
+#pragma unroll
+    for (int s = 0; s < I8_STAGES; ++s) {
+      tma::mbar_init(bar_full + 8 * s, 1);
+      tma::mbar_init(bar_empty + 8 * s, 1);
+    }
+    tma::mbar_init(bar_tfull, 1);
+    tma::mbar_init(bar_tempty, 4);
+    tma::fence_barrier_init();
+  }
+  if (warp == 1) tc5::alloc(slot, 512);
+  tc5::fence_before();
+  __syncthreads();
+  tc5::fence_after();
+  const unsigned tmem = *slot_ptr;
+  const int r_begin = p.off[slice], r_end = p.off[slice + 1];
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      unsigned phase = 0;
+      for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight)
+        for (int r = r_begin; r < r_end; ++r) {
+          const int rb = p.order[r];
+          for (int kc = 0; kc <= rb; ++kc) {
+            tma::mbar_wait_bounded(bar_empty + 8 * stage, phase ^ 1u);
+            tma::mbar_arrive_expect_tx(bar_full + 8 * stage, I8_STAGE);
+            const unsigned dst = base + stage * I8_STAGE;
+            tma::load_3d(dst, &mapK, kc * I8_KC, tile * I8_TILE, 0, bar_full + 8 * stage);
+            tma::load_3d(dst + I8_STAGE_A, &mapW, kc * I8_KC, rb * I8_RB, 0, bar_full + 8 * stage);
+            if (++stage == I8_STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr unsigned idesc = tc5::idesc_i8(I8_TILE, I8_RB);
+      int stage = 0;
+      unsigned phase = 0, tphase = 0;
+      for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight)
+        for (int r = r_begin; r < r_end; ++r) {
+          const int rb = p.order[r];
+          tma::mbar_wait_bounded(bar_tempty, tphase ^ 1u);      // the read-back of the previous row block is done
+          tc5::fence_after();
+          for (int kc = 0; kc <= rb; ++kc) {
+            tma::mbar_wait_bounded(bar_full + 8 * stage, phase);
+            tc5::fence_after();
+            const unsigned long long da = tc5::desc_k_sw64(base + stage * I8_STAGE);
+            const unsigned long long dbs = tc5::desc_k_sw64(base + stage * I8_STAGE + I8_STAGE_A);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+              for (int l = 0; l < I8_NS; ++l)
+#pragma unroll
+                for (int s = 0; s <= l; ++s) {
+                  const int t = l - s;  // digit t of K_* (A operand) x digit s of W (B operand) -> level l
+                  const unsigned long long ad = da + (unsigned long long)((t * I8_TILE * I8_KC + ks * 32) >> 4);
+                  const unsigned long long bd = dbs + (unsigned long long)((s * I8_RB * I8_KC + ks * 32) >> 4);
+                  const unsigned acc = (kc > 0 || ks > 0 || s > 0) ? 1u : 0u;
+                  tc5::mma_i8(tmem + l * I8_RB, ad, bd, idesc, acc);
+                }
+            tc5::commit(bar_empty + 8 * stage);                 // frees the stage once these MMAs have read it
+            if (++stage == I8_STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          tc5::commit(bar_tfull);                               // accumulators of this row block are complete
+          tphase ^= 1u;
+        }
+    }
+  } else {
+    const int q = warp & 3;                                     // tensor-memory lane quadrant of this warp
+    const int c = q * 32 + lane;                                // candidate within the tile
+    const unsigned tq = tmem + ((unsigned)(q * 32) << 16);
+    const double kx = p.kexp[1];
+    unsigned tphase = 0;
+    for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight) {
+      double s2 = 0.0, sv = 0.0;
+      for (int r = r_begin; r < r_end; ++r) {
+        const int rb = p.order[r];
+        tma::mbar_wait_bounded(bar_tfull, tphase);
+        tphase ^= 1u;
+        tc5::fence_after();
+#pragma unroll 1
+        for (int j0 = 0; j0 < I8_RB; j0 += 8) {
+          int a[I8_NS][8];
+#pragma unroll
+          for (int l = 0; l < I8_NS; ++l) tc5::ld_32x32b_x8(tq + l * I8_RB + j0, a[l]);
+          tc5::wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long hi = ((((long long)a[0][j] * 128 + a[1][j]) * 128 + a[2][j]) * 128) + a[3][j];
+            const long long lo = ((((long long)a[4][j] * 128 + a[5][j]) * 128 + a[6][j]) * 128) + a[7][j];
+            const int i = rb * I8_RB + j0 + j;
+            const double av = (__ldg(p.rowscale + i) * kx) * fma((double)hi, 268435456.0, (double)lo);
+            s2 = fma(av, av, s2);
+            sv = fma(av, __ldg(p.V + i), sv);
+          }
+        }
+        tc5::fence_before();
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(bar_tempty);
+      }
+      double* dst = p.partial + (((size_t)tile * p.slices + slice) * I8_TILE + c) * 2;
+      dst[0] = s2;
+      dst[1] = sv;
+    }
+  }
+  tc5::fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc5::dealloc(tmem, 512);
+  }
 }
 
 // Optional per-launch timing of score_kernel (bench.py's roofline figure): CUDA events recorded on
@@ -324,6 +659,7 @@ extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_p
     a.W = W; a.V = V; a.Kst = Kst; a.n_pad = n_pad;
     a.slices = (n_pad / BM < SCORE_SLICES) ? n_pad / BM : SCORE_SLICES;
     a.partial = Kst + (size_t)chunk * n_pad;
+    a.tile_w = TN;
     a.log_scale = log_scale; a.mean_param = mean_param;
     a.c_begin = c0; a.M = M; a.index_offset = index_offset;
     a.acq_kind = acq_kind; a.y_max = y_max; a.xi = xi; a.kappa = kappa;
@@ -335,6 +671,133 @@ extern "C" int distbo_score_f64(const double* W, const double* V, int N, int n_p
     score_kernel<<<2 * tiles * a.slices, GEMM_THREADS, TGEMM_SMEM_BYTES, st>>>(a);
     DB_CHECK_LAUNCH();
     if (timed) cudaEventRecord(t1, st);
+    score_finish_kernel<<<tiles, 128, 0, st>>>(a);
+    DB_CHECK_LAUNCH();
+    merge_best_kernel<<<1, 32, 0, st>>>(block_best_val, (const long long*)block_best_idx, tiles, first, best_val,
+                                        (long long*)best_idx);
+    DB_CHECK_LAUNCH();
+    first = 0;
+  }
+  return DISTBO_OK;
+}
+
+// ---- tcgen05 path, host side ---------------------------------------------------------------------------
+namespace db {
+
+// Row blocks (cost ~ k range + read-back) dealt to `slices` CTAs, longest first onto the least loaded slice.
+static void i8_partition(int n_rb, int slices, I8Args& a) {
+  std::vector<double> load(slices, 0.0);
+  std::vector<std::vector<unsigned short>> lists(slices);
+  for (int rb = n_rb - 1; rb >= 0; --rb) {
+    int best = 0;
+    for (int s = 1; s < slices; ++s)
+      if (load[s] < load[best]) best = s;
+    load[best] += (rb + 1) + 1.5;
+    lists[best].push_back((unsigned short)rb);
+  }
+  int o = 0;
+  for (int s = 0; s < slices; ++s) {
+    a.off[s] = (unsigned short)o;
+    for (unsigned short rb : lists[s]) a.order[o++] = rb;
+  }
+  a.off[slices] = (unsigned short)o;
+}
+
+static void i8_shape(int n_pad, int* slices, int* tiles_in_flight) {
+  const int sms = device_sm_count(), n_rb = n_pad / I8_RB;
+  int tf = 4;
+  int sl = sms / tf;
+  if (sl > I8_MAX_SLICES) sl = I8_MAX_SLICES;
+  if (sl > n_rb) sl = n_rb;
+  tf = sms / sl;
+  *slices = sl;
+  *tiles_in_flight = tf;
+}
+
+}  // namespace db
+
+extern "C" int64_t distbo_score_i8_workspace(int n_pad) {
+  const int64_t chunk = distbo_score_chunk();
+  // digit planes of the K_* chunk (8 bytes per element), per-slice partial sums, the two exponent factors
+  return chunk * n_pad + (chunk / I8_TILE) * I8_MAX_SLICES * I8_TILE * 2 + 2;
+}
+
+extern "C" int distbo_score_i8_prepare(const double* W, int n_pad, int8_t* W8, double* rowscale, void* stream) {
+  if (!W || !W8 || !rowscale || n_pad <= 0 || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB) return DISTBO_EARG;
+  i8_wsplit_kernel<<<n_pad, 256, 0, (cudaStream_t)stream>>>(W, n_pad, (signed char*)W8, rowscale);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
+extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, const double* V, int N, int n_pad,
+                                   const double* theta_s, const double* sqnorm, int d, const double* log_bw,
+                                   const double* kvec, const double* log_scale, const double* mean_param,
+                                   const double* theta_c, const double* cand_shift, const double* cand_scale,
+                                   int64_t M, int acq_kind, double y_max, double xi, double kappa, double* ws,
+                                   double* out_mean, double* out_std, double* out_acq, double* block_best_val,
+                                   int64_t* block_best_idx, double* best_val, int64_t* best_idx,
+                                   int64_t index_offset, void* stream) {
+  if (!W8 || !rowscale || !V || !theta_s || !sqnorm || !log_bw || !kvec || !log_scale || !mean_param || !theta_c ||
+      !ws || !block_best_val || !block_best_idx || !best_val || !best_idx)
+    return DISTBO_EARG;
+  if (N <= 0 || n_pad < N || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB || d <= 0 || d > SCORE_DMAX || M <= 0)
+    return DISTBO_EARG;
+  if (acq_kind < 0 || acq_kind > 2 || ((cand_shift == nullptr) != (cand_scale == nullptr))) return DISTBO_EARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = distbo_score_chunk();
+  static PerDeviceOnce once;
+  if (once.needed()) {
+    DB_CUDA(cudaFuncSetAttribute(score_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    once.mark();
+  }
+  signed char* K8 = reinterpret_cast<signed char*>(ws);
+  double* partial = ws + (size_t)chunk * n_pad;
+  double* kexp = partial + (size_t)(chunk / I8_TILE) * I8_MAX_SLICES * I8_TILE * 2;
+  CUtensorMap mapK, mapW;
+  if (!tma::encode_u8_planes(&mapK, K8, (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE) ||
+      !tma::encode_u8_planes(&mapW, W8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB))
+    return DISTBO_ECUDA;
+  I8Args ia;
+  ia.n_rb = n_pad / I8_RB;
+  i8_shape(n_pad, &ia.slices, &ia.tiles_in_flight);
+  i8_partition(ia.n_rb, ia.slices, ia);
+  ia.rowscale = rowscale; ia.kexp = kexp; ia.V = V; ia.partial = partial;
+  i8_kexp_kernel<<<1, 256, 0, st>>>(kvec, N, log_scale, kexp);
+  DB_CHECK_LAUNCH();
+  int first = 1;
+  for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+    const int64_t mc = (M - c0 < chunk) ? (M - c0) : chunk;
+    const int tiles = (int)((mc + I8_TILE - 1) / I8_TILE);
+    const int kgrid = tiles * I8_TILE / KST_CAND;
+    if (d <= 4)
+      i8_kst_kernel<4><<<kgrid, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale, theta_c,
+                                               cand_shift, cand_scale, (long long)c0, (long long)M, kexp, chunk, K8);
+    else if (d <= 8)
+      i8_kst_kernel<8><<<kgrid, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale, theta_c,
+                                               cand_shift, cand_scale, (long long)c0, (long long)M, kexp, chunk, K8);
+    else
+      i8_kst_kernel<SCORE_DMAX><<<kgrid, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale,
+                                                        theta_c, cand_shift, cand_scale, (long long)c0,
+                                                        (long long)M, kexp, chunk, K8);
+    DB_CHECK_LAUNCH();
+    ia.ntiles = tiles;
+    const int tf = ia.tiles_in_flight < tiles ? ia.tiles_in_flight : tiles;
+    I8Args launch = ia;
+    launch.tiles_in_flight = tf;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    const bool timed = g_timing && timing_pair(&t0, &t1);
+    if (timed) cudaEventRecord(t0, st);
+    score_i8_kernel<<<ia.slices * tf, I8_THREADS, I8_SMEM, st>>>(mapK, mapW, launch);
+    DB_CHECK_LAUNCH();
+    if (timed) cudaEventRecord(t1, st);
+    ScoreArgs a;
+    a.W = nullptr; a.V = V; a.Kst = nullptr; a.n_pad = n_pad;
+    a.slices = ia.slices; a.tile_w = I8_TILE; a.partial = partial;
+    a.log_scale = log_scale; a.mean_param = mean_param;
+    a.c_begin = c0; a.M = M; a.index_offset = index_offset;
+    a.acq_kind = acq_kind; a.y_max = y_max; a.xi = xi; a.kappa = kappa;
+    a.out_mean = out_mean; a.out_std = out_std; a.out_acq = out_acq;
+    a.block_best_val = block_best_val; a.block_best_idx = (long long*)block_best_idx;
     score_finish_kernel<<<tiles, 128, 0, st>>>(a);
     DB_CHECK_LAUNCH();
     merge_best_kernel<<<1, 32, 0, st>>>(block_best_val, (const long long*)block_best_idx, tiles, first, best_val,

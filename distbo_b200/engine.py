@@ -15,6 +15,7 @@ Layout in HBM (row-major, fp64 unless noted; n_pad = roundup(N, 128)):
 from __future__ import annotations
 
 import functools
+import os
 import math
 
 import numpy as np
@@ -217,6 +218,12 @@ class GPEngine:
         self.best_val = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.best_idx = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._score_ws = None
+        self._score_i8_ws = None
+        self._w8 = None                  # int8 digit planes of W + row exponents (tcgen05 scoring path)
+        self.W_version = 0               # bumped whenever self.W changes
+        self._w8_version = -1
+        self.score_i8_min_npad = int(os.environ.get("DISTBO_SCORE_I8_MIN", "128"))
+        self.use_score_i8 = os.environ.get("DISTBO_SCORE_I8", "0") == "1"
         self._emb_ws = {}
         self._emb_raw = None
         self.E = None
@@ -395,6 +402,7 @@ class GPEngine:
             _lib.check(self.lib.distbo_trtri_f64(self.plan, _lib.ptr(self.K), _lib.ptr(self.W), _lib.ptr(self.Tm), st),
                        "distbo_trtri_f64")
             self.W_valid = True
+            self.W_version += 1
         if need_kinv:
             _lib.check(self.lib.distbo_lauum_f64(self.plan, _lib.ptr(self.W), _lib.ptr(self.Tm), st),
                        "distbo_lauum_f64")
@@ -484,6 +492,8 @@ class GPEngine:
         if not torch.is_tensor(theta_c):
             theta_c = torch.from_numpy(np.ascontiguousarray(theta_c, dtype=np.float64)).to(self.dev)
         M = int(theta_c.shape[0])
+        if self.use_score_i8 and self.n_pad >= self.score_i8_min_npad:
+            return self._score_i8(theta_c, M, acq, y_max, xi, kappa, want_arrays, index_offset, kvec, scaler)
         chunk = self.lib.distbo_score_chunk()
         need = int(self.lib.distbo_score_workspace(self.n_pad))
         if self._score_ws is None or self._score_ws[0].numel() < need:
@@ -508,6 +518,43 @@ class GPEngine:
             _lib.ptr(kst), _lib.ptr(mean), _lib.ptr(std), _lib.ptr(acqv), _lib.ptr(bbv), _lib.ptr(bbi),
             _lib.ptr(self.best_val), _lib.ptr(self.best_idx), int(index_offset), _stream())
         _lib.check(rc, "distbo_score_f64")
+        return {"best_val": self.best_val, "best_idx": self.best_idx, "mean": mean, "std": std, "acq": acqv}
+
+    def _score_i8(self, theta_c, M, acq, y_max, xi, kappa, want_arrays, index_offset, kvec, scaler):
+        """The same operator on the tcgen05 tensor cores (int8 digit planes, exact integer accumulation in
+        tensor memory; include/distbo_b200.h).  W's digit planes are refreshed when W changed."""
+        n_pad = self.n_pad
+        if self._w8 is None or self._w8[0].shape[1] != n_pad:
+            self._w8 = (torch.empty(8, n_pad, n_pad, dtype=torch.int8, device=self.dev), self._f64(n_pad))
+            self._w8_version = -1
+        if self._w8_version != self.W_version:
+            _lib.check(self.lib.distbo_score_i8_prepare(_lib.ptr(self.W), n_pad, _lib.ptr(self._w8[0]),
+                                                        _lib.ptr(self._w8[1]), _stream()), "distbo_score_i8_prepare")
+            self._w8_version = self.W_version
+        chunk = self.lib.distbo_score_chunk()
+        need = int(self.lib.distbo_score_i8_workspace(n_pad))
+        if self._score_i8_ws is None or self._score_i8_ws[0].numel() < need:
+            self._score_i8_ws = (torch.empty(need, dtype=torch.float64, device=self.dev),
+                                 torch.empty(chunk // 128, dtype=torch.float64, device=self.dev),
+                                 torch.empty(chunk // 128, dtype=torch.int64, device=self.dev))
+        ws, bbv, bbi = self._score_i8_ws
+        if kvec is None:
+            kvec = self.kvec
+        mean = std = acqv = None
+        if want_arrays:
+            mean = torch.empty(M, dtype=torch.float64, device=self.dev)
+            std = torch.empty(M, dtype=torch.float64, device=self.dev)
+            acqv = torch.empty(M, dtype=torch.float64, device=self.dev)
+        p = self.params
+        rc = self.lib.distbo_score_i8_f64(
+            _lib.ptr(self._w8[0]), _lib.ptr(self._w8[1]), _lib.ptr(self.V), self.N, n_pad, _lib.ptr(self.theta_s),
+            _lib.ptr(self.sqnorm), self.d, _lib.ptr(p.view("log_bw")), _lib.ptr(kvec), _lib.ptr(p.view("log_scale")),
+            _lib.ptr(p.view("mean")), _lib.ptr(theta_c),
+            _lib.ptr(scaler[0]) if scaler is not None else None,
+            _lib.ptr(scaler[1]) if scaler is not None else None, M, ACQ[acq], float(y_max), float(xi), float(kappa),
+            _lib.ptr(ws), _lib.ptr(mean), _lib.ptr(std), _lib.ptr(acqv), _lib.ptr(bbv), _lib.ptr(bbi),
+            _lib.ptr(self.best_val), _lib.ptr(self.best_idx), int(index_offset), _stream())
+        _lib.check(rc, "distbo_score_i8_f64")
         return {"best_val": self.best_val, "best_idx": self.best_idx, "mean": mean, "std": std, "acq": acqv}
 
     # ------------------------------------------------------------------ one evaluation of loss + gradient

@@ -237,6 +237,26 @@ int distbo_score_f64(const double* W, const double* V, int N, int n_pad, const d
                      int64_t* block_best_idx, double* best_val, int64_t* best_idx,
                      int64_t index_offset, void* stream);
 
+/* ---- K4 on the 5th-generation tensor cores (tcgen05, int8 digits, exact integer accumulation) ------------
+ * Same operator, same results to fp64 rounding level, for the same reference code as distbo_score_f64
+ * (log_gaus_likelihood.py:199-217: tf.matrix_triangular_solve + reduce_sum(square)).  fp64 has no tcgen05
+ * kind; W = L^-1 and K_* are cut into 8 signed base-128 digits of a 56-bit fixed-point number each and the
+ * 36 digit-pair products that matter are exact int32 tcgen05.mma kind::i8 accumulations in tensor memory,
+ * folded into fp64 once per (candidate, row of W).
+ * distbo_score_i8_prepare: W [n_pad,n_pad] (lower triangle read) -> W8 [8][n_pad][n_pad] int8 digit planes,
+ *   rowscale [n_pad] = 2^exponent(max_k |W[i,k]|); once per fit.
+ * distbo_score_i8_f64: as distbo_score_f64 with (W8, rowscale) in place of W and `ws` a workspace of
+ *   distbo_score_i8_workspace(n_pad) doubles (digit planes of one K_* chunk + per-slice partial sums). */
+int64_t distbo_score_i8_workspace(int n_pad);
+int distbo_score_i8_prepare(const double* W, int n_pad, int8_t* W8, double* rowscale, void* stream);
+int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, const double* V, int N, int n_pad,
+                        const double* theta_s, const double* sqnorm, int d, const double* log_bw,
+                        const double* kvec, const double* log_scale, const double* mean_param,
+                        const double* theta_c, const double* cand_shift, const double* cand_scale, int64_t M,
+                        int acq_kind, double y_max, double xi, double kappa, double* ws, double* out_mean,
+                        double* out_std, double* out_acq, double* block_best_val, int64_t* block_best_idx,
+                        double* best_val, int64_t* best_idx, int64_t index_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
