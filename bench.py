@@ -43,6 +43,7 @@ M_DEFAULT = 1 << 20
 XI, KAPPA = 0.01, 2.58           # experiments/train_test.py:63-64
 FP64_FALLBACK_TFLOPS = 35.5      # cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peak.json)
 SCORE_KERNEL_DRAM_BYTES = 11.87e9  # dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch (ncu)
+SCORE_I8_KERNEL_DRAM_BYTES = None   # filled from the ncu --set full capture of score_i8_kernel (profiles/)
 
 
 # ----------------------------------------------------------------------------------- workload
@@ -278,6 +279,26 @@ def fp64_peak(torch, dev):
     return 2.0 * n ** 3 / best / 1e9
 
 
+def int8_peak(torch, dev):
+    """int8 tensor-core denominator: MEASURED_PEAKS.json carries no int8 figure, so the library int8 GEMM
+    (torch._int_mm -> cuBLASLt, s8 x s8 -> s32, 8192^3) is timed here, best of 5 after warm-up; None when the
+    library refuses the call."""
+    n = 8192
+    a = torch.randint(-64, 64, (n, n), dtype=torch.int8, device=dev)
+    b = torch.randint(-64, 64, (n, n), dtype=torch.int8, device=dev)
+    best = 1e30
+    for i in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch._int_mm(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / best / 1e9
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -418,15 +439,47 @@ def run_cuda(args):
     n_launch = max(int(kn.value), 1)
     cands_per_launch = (hi - lo) * K / n_launch
     avg_ms = kms.value / n_launch
-    achieved = flops_per_cand * cands_per_launch / (avg_ms / 1e3) / 1e12
-    roofline = {"kernel": "score_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": SCORE_KERNEL_DRAM_BYTES, "peak_source": peak_src,
-                "traffic_note": "dram read+write per launch from ncu --set full (profiles/r01_score_kernel_ncu_full.txt): "
-                                "algorithmic bytes are the K_* chunk (1.24 GB) + the lower triangle of W (0.27 GB); every K_* tile is "
-                                "re-read once per row block of W and 83 % of those re-reads hit L2 (it was 40.3 GB before the "
-                                "CTAs of one tile were made co-resident)",
-                "avg_launch_ms": avg_ms, "launches_timed": n_launch, "candidates_per_launch": cands_per_launch,
-                "share_of_step": kms.value / ms_local}
+    fp64_equiv = flops_per_cand * cands_per_launch / (avg_ms / 1e3) / 1e12
+    on_i8 = bool(eng.use_score_i8 and n_pad >= eng.score_i8_min_npad)
+    if on_i8:
+        # what the kernel executes: every fp64 multiply-add of A = K_* W^T (lower triangle of W, 64-row blocks)
+        # is 36 exact int8 digit-pair multiply-adds on the tcgen05 tensor cores
+        nrb = n_pad // 64
+        macs_per_cand = 36.0 * 64.0 * 64.0 * nrb * (nrb + 1) / 2.0
+        achieved = 2.0 * macs_per_cand * cands_per_launch / (avg_ms / 1e3) / 1e12
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        try:
+            i8_peak = int8_peak(torch, dev)
+            i8_src = "library int8 GEMM (torch._int_mm, cuBLASLt s8 x s8 -> s32, 8192^3) measured in this run"
+        except Exception as ex:  # noqa: BLE001
+            i8_peak = 2.0 * float(mp.get("bf16_tflops", 1590.0))
+            i8_src = ("2 x MEASURED_PEAKS bf16_tflops (burst) - int8 dense is twice bf16 dense on B200 and the library "
+                      "int8 GEMM was not available here (%s)" % type(ex).__name__)
+        roofline = {"kernel": "score_i8_kernel", "bound": "tensor", "achieved": achieved, "peak": i8_peak,
+                    "unit": "TOP/s", "frac": achieved / i8_peak, "traffic": SCORE_I8_KERNEL_DRAM_BYTES,
+                    "peak_source": i8_src,
+                    "what": "tcgen05.mma kind::i8 (s32 accumulators in tensor memory): 36 digit-pair products of the 8 x 8 "
+                            "int8 digit planes per fp64 multiply-add, lower triangle of W in 64-row blocks",
+                    "fp64_equivalent": {"achieved": fp64_equiv, "unit": "TFLOP/s", "dgemm_peak": peak,
+                                        "ratio_to_dgemm_peak": fp64_equiv / peak, "dgemm_peak_source": peak_src,
+                                        "what": "algorithmic fp64 flops (N^2 + 2N per candidate) per second of this kernel "
+                                                "against the FP64 DMMA peak it replaces; r01's DMMA kernel reached 0.947"},
+                    "traffic_note": "dram read+write per launch from ncu --set full (profiles/r02_score_i8_kernel_ncu_full.txt); "
+                                    "algorithmic bytes are the digit planes of the K_* chunk (1.24 GB) + of the lower "
+                                    "triangle of W (0.27 GB)",
+                    "avg_launch_ms": avg_ms, "launches_timed": n_launch, "candidates_per_launch": cands_per_launch,
+                    "share_of_step": kms.value / ms_local}
+    else:
+        achieved = fp64_equiv
+        roofline = {"kernel": "score_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": SCORE_KERNEL_DRAM_BYTES, "peak_source": peak_src,
+                    "traffic_note": "dram read+write per launch from ncu --set full (profiles/r01_score_kernel_ncu_full.txt): "
+                                    "algorithmic bytes are the K_* chunk (1.24 GB) + the lower triangle of W (0.27 GB); every K_* tile is "
+                                    "re-read once per row block of W and 83 % of those re-reads hit L2 (it was 40.3 GB before the "
+                                    "CTAs of one tile were made co-resident)",
+                    "avg_launch_ms": avg_ms, "launches_timed": n_launch, "candidates_per_launch": cands_per_launch,
+                    "share_of_step": kms.value / ms_local}
     fit_flops = float(n_pad) ** 3
     fit["fit_tflops"] = fit_flops / (fit["fit_ms"] / 1e3) / 1e12
     fit["fit_frac_of_fp64_peak"] = fit["fit_tflops"] / peak
@@ -526,6 +579,8 @@ def run_cuda(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": bench_config(M, args.lkh_var, world),
+            "score_path": ("tcgen05 kind::i8 on 8 x 8 int8 digit planes of the fp64 operands (exact s32 accumulation, "
+                           "folded to fp64; results equal the DMMA path to 1e-13)") if on_i8 else "FP64 DMMA",
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": M / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 16 * world,

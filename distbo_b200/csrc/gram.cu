@@ -144,6 +144,9 @@ __global__ void __launch_bounds__(256, 2) gram_grad_rows_kernel(
     xi[k] = (row_ok && k < d) ? theta_s[(size_t)i * d + k] : 0.0;
     gbw[k] = 0.0;
   }
+  // rows k >= d of the staged tile are never filled below but enter the unrolled dot product with xi[k] = 0:
+  // they must hold finite numbers (0 * NaN left over in shared memory by an earlier kernel is NaN)
+  for (int idx = threadIdx.x; idx < (D - d) * 128; idx += 256) sJt[d + idx / 128][idx % 128] = 0.0;
   const double* krow = Kinv + (size_t)(row_ok ? i : 0) * n_pad;
   int tcur = -1;      // lane 0: running (task, partial sum) of rowH[i][.]
   double hcur = 0.0;

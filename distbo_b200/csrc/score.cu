@@ -12,6 +12,7 @@
 //   score_finish   : adds a tile's slices in order, acquisition epilogue, per-tile (max value, lowest index);
 //   merge_kernel   : deterministic (max value, min index) merge into the running best.
 #include "../../include/distbo_b200.h"
+#include <stdlib.h>
 #include <vector>
 
 #include "gemm_core.cuh"
@@ -261,7 +262,7 @@ constexpr int I8_STAGES = 2;
 constexpr int I8_STAGE_A = I8_NS * I8_TILE * I8_KC;   // 65536
 constexpr int I8_STAGE_B = I8_NS * I8_RB * I8_KC;     // 32768
 constexpr int I8_STAGE = I8_STAGE_A + I8_STAGE_B;
-constexpr int I8_SMEM = I8_STAGES * I8_STAGE + 1024 /* alignment slack */ + 128 /* barriers, tmem slot */;
+constexpr int I8_SMEM = I8_STAGES * I8_STAGE + 1024 /* alignment slack */ + 128 /* 12 barriers, tmem slot */;
 constexpr int I8_THREADS = 192;   // warp 0: TMA, warp 1: MMA + tensor-memory owner, warps 2-5: read-back
 constexpr int I8_MAX_RB = 512;    // n_pad <= 32768
 constexpr int I8_MAX_SLICES = 64;
@@ -269,6 +270,7 @@ constexpr int I8_FRAC = 55;       // fractional bits of the fixed-point operands
 
 struct I8Args {
   int n_rb, ntiles, slices, tiles_in_flight;
+  int debug;                // measurement only: bit 0 = no MMAs, bit 1 = no TMA loads, bit 2 = no read-back
   const double* rowscale;   // [n_pad] 2^e_i
   const double* kexp;       // [2]: 2^(55 - f), 2^(f - 61)
   const double* V;
@@ -438,9 +440,12 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
   extern __shared__ unsigned char smem_raw[];
   const unsigned raw = tma::smem_u32(smem_raw);
   const unsigned base = (raw + 1023u) & ~1023u;                 // stage buffers: 1024-byte aligned
-  const unsigned bars = base + I8_STAGES * I8_STAGE;            // full[2], empty[2], tmem_full, tmem_empty
-  const unsigned bar_full = bars, bar_empty = bars + 8 * I8_STAGES;
-  const unsigned bar_tfull = bars + 16 * I8_STAGES, bar_tempty = bar_tfull + 8;
+  // A stage is handed over in three loads of 32 KB with a barrier each: the W planes (all needed by digit 0), the
+  // K_* planes 0-3 and the K_* planes 4-7 (waited for when digit 4 comes up, given back after digit 3 / digit 7).
+  // One 96 KB unit per stage could not cover the L2 latency with two stages (measured: 0.3 us stall per stage);
+  // sixteen 4-8 KB loads per stage halved the TMA throughput instead.
+  const unsigned bars = base + I8_STAGES * I8_STAGE;   // per stage: fullW, fullA0, fullA1, emptyA0, emptyRest
+  const unsigned bar_tfull = bars + 40 * I8_STAGES, bar_tempty = bar_tfull + 8;
   const unsigned slot = bar_tempty + 8;
   volatile unsigned* slot_ptr = reinterpret_cast<volatile unsigned*>(smem_raw + (slot - raw));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -450,10 +455,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
     tma::prefetch_map(&mapK);
     tma::prefetch_map(&mapW);
 #pragma unroll
-    for (int s = 0; s < I8_STAGES; ++s) {
-      tma::mbar_init(bar_full + 8 * s, 1);
-      tma::mbar_init(bar_empty + 8 * s, 1);
-    }
+    for (int s = 0; s < I8_STAGES * 5; ++s) tma::mbar_init(bars + 8 * s, 1);
     tma::mbar_init(bar_tfull, 1);
     tma::mbar_init(bar_tempty, 4);
     tma::fence_barrier_init();
@@ -473,11 +475,24 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
         for (int r = r_begin; r < r_end; ++r) {
           const int rb = p.order[r];
           for (int kc = 0; kc <= rb; ++kc) {
-            tma::mbar_wait_bounded(bar_empty + 8 * stage, phase ^ 1u);
-            tma::mbar_arrive_expect_tx(bar_full + 8 * stage, I8_STAGE);
-            const unsigned dst = base + stage * I8_STAGE;
-            tma::load_3d(dst, &mapK, kc * I8_KC, tile * I8_TILE, 0, bar_full + 8 * stage);
-            tma::load_3d(dst + I8_STAGE_A, &mapW, kc * I8_KC, rb * I8_RB, 0, bar_full + 8 * stage);
+            const unsigned dst = base + stage * I8_STAGE, sb = bars + 40 * stage;
+            tma::mbar_wait_bounded(sb + 24, phase ^ 1u);        // K_* planes 0-3 of this slot are free
+            if (p.debug & 2) {
+              tma::mbar_arrive(sb + 8);
+            } else {
+              tma::mbar_arrive_expect_tx(sb + 8, I8_STAGE_A / 2);
+              tma::load_3d(dst, &mapK, kc * I8_KC, tile * I8_TILE, 0, sb + 8);
+            }
+            tma::mbar_wait_bounded(sb + 32, phase ^ 1u);        // ... and the rest of it
+            if (p.debug & 2) {
+              tma::mbar_arrive(sb);
+              tma::mbar_arrive(sb + 16);
+            } else {
+              tma::mbar_arrive_expect_tx(sb, I8_STAGE_B);
+              tma::load_3d(dst + I8_STAGE_A, &mapW, kc * I8_KC, rb * I8_RB, 0, sb);
+              tma::mbar_arrive_expect_tx(sb + 16, I8_STAGE_A / 2);
+              tma::load_3d(dst + I8_STAGE_A / 2, &mapK, kc * I8_KC, tile * I8_TILE, I8_NS / 2, sb + 16);
+            }
             if (++stage == I8_STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -487,7 +502,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr unsigned idesc = tc5::idesc_i8(I8_TILE, I8_RB);
       int stage = 0;
       unsigned phase = 0, tphase = 0;
       for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight)
@@ -496,23 +510,47 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
           tma::mbar_wait_bounded(bar_tempty, tphase ^ 1u);      // the read-back of the previous row block is done
           tc5::fence_after();
           for (int kc = 0; kc <= rb; ++kc) {
-            tma::mbar_wait_bounded(bar_full + 8 * stage, phase);
+            const unsigned sb = bars + 40 * stage;
+            tma::mbar_wait_bounded(sb, phase);
+            tma::mbar_wait_bounded(sb + 8, phase);
             tc5::fence_after();
             const unsigned long long da = tc5::desc_k_sw64(base + stage * I8_STAGE);
             const unsigned long long dbs = tc5::desc_k_sw64(base + stage * I8_STAGE + I8_STAGE_A);
+            if (!(p.debug & 1)) {
+              // Digit t of K_* (A operand) meets digits s = 0 .. 7 - t of W at once: the W planes are contiguous
+              // in the stage (64 rows x 64 bytes each), so planes s0 .. s0 + n - 1 form ONE K-major B operand of
+              // N = 64 n rows, and because the level accumulators are contiguous in tensor memory too
+              // (level l at columns 64 l), its product lands on levels t + s0 .. t + s0 + n - 1 in one MMA.
+              // 12 wide MMAs (N = 256 / 192 / 128, one of 64) per k-step instead of 36 of N = 64, which were
+              // bound by re-reading the A tile from shared memory (measured 45 % of the int8 rate).
+              // k-step outermost: consecutive MMAs then write different accumulator columns (the same columns
+              // come up again 12 MMAs later); with the digit outermost the accumulate dependency serialised them.
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
+              for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-              for (int l = 0; l < I8_NS; ++l)
-#pragma unroll
-                for (int s = 0; s <= l; ++s) {
-                  const int t = l - s;  // digit t of K_* (A operand) x digit s of W (B operand) -> level l
+                for (int t = 0; t < I8_NS; ++t) {
+                  if (ks == 0 && t == I8_NS / 2) {
+                    tma::mbar_wait_bounded(sb + 16, phase);
+                    tc5::fence_after();
+                  }
                   const unsigned long long ad = da + (unsigned long long)((t * I8_TILE * I8_KC + ks * 32) >> 4);
-                  const unsigned long long bd = dbs + (unsigned long long)((s * I8_RB * I8_KC + ks * 32) >> 4);
-                  const unsigned acc = (kc > 0 || ks > 0 || s > 0) ? 1u : 0u;
-                  tc5::mma_i8(tmem + l * I8_RB, ad, bd, idesc, acc);
+                  const int planes = I8_NS - t;                       // W digits 0 .. planes - 1
+                  const int n0 = planes > 4 ? (planes == 5 ? 3 : 4) : planes;   // 8=4+4 7=4+3 6=4+2 5=3+2
+                  const unsigned acc = (kc > 0 || ks > 0 || t > 0) ? 1u : 0u;   // t = 0 covers all 512 columns
+                  tc5::mma_i8(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
+                              tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
+                  if (planes > n0)
+                    tc5::mma_i8(tmem + (t + n0) * I8_RB, ad,
+                                dbs + (unsigned long long)((n0 * I8_RB * I8_KC + ks * 32) >> 4),
+                                tc5::idesc_i8(I8_TILE, (planes - n0) * I8_RB), acc);
+                  if (ks == 1 && t == I8_NS / 2 - 1) tc5::commit(sb + 24);
                 }
-            tc5::commit(bar_empty + 8 * stage);                 // frees the stage once these MMAs have read it
+              tc5::commit(sb + 32);
+            } else {
+              tma::mbar_wait_bounded(sb + 16, phase);
+              tc5::commit(sb + 24);
+              tc5::commit(sb + 32);
+            }
             if (++stage == I8_STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -536,7 +574,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
         tphase ^= 1u;
         tc5::fence_after();
 #pragma unroll 1
-        for (int j0 = 0; j0 < I8_RB; j0 += 8) {
+        for (int j0 = 0; j0 < ((p.debug & 4) ? 0 : I8_RB); j0 += 8) {
           int a[I8_NS][8];
 #pragma unroll
           for (int l = 0; l < I8_NS; ++l) tc5::ld_32x32b_x8(tq + l * I8_RB + j0, a[l]);
@@ -754,13 +792,17 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
   double* partial = ws + (size_t)chunk * n_pad;
   double* kexp = partial + (size_t)(chunk / I8_TILE) * I8_MAX_SLICES * I8_TILE * 2;
   CUtensorMap mapK, mapW;
-  if (!tma::encode_u8_planes(&mapK, K8, (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE) ||
-      !tma::encode_u8_planes(&mapW, W8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB))
+  if (!tma::encode_u8_planes(&mapK, K8, (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE, I8_NS / 2) ||
+      !tma::encode_u8_planes(&mapW, W8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS))
     return DISTBO_ECUDA;
   I8Args ia;
   ia.n_rb = n_pad / I8_RB;
   i8_shape(n_pad, &ia.slices, &ia.tiles_in_flight);
   i8_partition(ia.n_rb, ia.slices, ia);
+  {
+    const char* dbg = getenv("DISTBO_I8_DEBUG");
+    ia.debug = dbg ? atoi(dbg) : 0;
+  }
   ia.rowscale = rowscale; ia.kexp = kexp; ia.V = V; ia.partial = partial;
   i8_kexp_kernel<<<1, 256, 0, st>>>(kvec, N, log_scale, kexp);
   DB_CHECK_LAUNCH();

@@ -113,15 +113,15 @@ inline bool encode_f64_rows(CUtensorMap* map, const double* base, uint64_t rows,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// int8 planes [planes][rows][cols] (cols contiguous); box = 64 bytes x box_rows x planes, 64-byte swizzle: the
+// int8 planes [planes][rows][cols] (cols contiguous); box = 64 bytes x box_rows x box_planes, 64-byte swizzle: the
 // layout tcgen05.mma reads as K-major SWIZZLE_64B operands, one plane after the other.
 inline bool encode_u8_planes(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t planes,
-                             uint32_t box_rows) {
+                             uint32_t box_rows, uint32_t box_planes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {cols, rows, planes};
   cuuint64_t strides[2] = {cols, cols * rows};
-  cuuint32_t box[3] = {64, box_rows, (cuuint32_t)planes};
+  cuuint32_t box[3] = {64, box_rows, box_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

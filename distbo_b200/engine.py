@@ -222,8 +222,11 @@ class GPEngine:
         self._w8 = None                  # int8 digit planes of W + row exponents (tcgen05 scoring path)
         self.W_version = 0               # bumped whenever self.W changes
         self._w8_version = -1
-        self.score_i8_min_npad = int(os.environ.get("DISTBO_SCORE_I8_MIN", "128"))
-        self.use_score_i8 = os.environ.get("DISTBO_SCORE_I8", "0") == "1"
+        # scoring path: tcgen05 int8 digit planes from n_pad = 512 (measured cross-over: 300 000 candidates take
+        # 0.99 / 1.87 ms at N = 120, 6.5 / 5.1 ms at N = 600, 308 / 134 ms per 151 552 at N = 8192, DMMA / tcgen05);
+        # DISTBO_SCORE_I8=0 keeps the FP64 DMMA kernel everywhere (A/B measurements)
+        self.score_i8_min_npad = int(os.environ.get("DISTBO_SCORE_I8_MIN", "512"))
+        self.use_score_i8 = os.environ.get("DISTBO_SCORE_I8", "1") == "1"
         self._emb_ws = {}
         self._emb_raw = None
         self.E = None
