@@ -448,7 +448,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
   const unsigned bar_tfull = bars + 40 * I8_STAGES, bar_tempty = bar_tfull + 8;
   const unsigned slot = bar_tempty + 8;
   volatile unsigned* slot_ptr = reinterpret_cast<volatile unsigned*>(smem_raw + (slot - raw));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler too
   const int slice = blockIdx.x % p.slices, tl = blockIdx.x / p.slices;
 
   if (warp == 0 && lane == 0) {
@@ -467,8 +468,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
   const unsigned tmem = *slot_ptr;
   const int r_begin = p.off[slice], r_end = p.off[slice + 1];
 
+  // Warps 0 and 1 run their loops with all 32 lanes and issue under elect.sync: in a `lane == 0` branch the
+  // compiler cannot prove the descriptors uniform and wraps every UTCIMMA / UTMALDG in a vote-and-broadcast
+  // loop (~20 instructions each), which made the single issuing thread the bottleneck of the pipeline.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       unsigned phase = 0;
       for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight)
@@ -477,22 +481,27 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
           for (int kc = 0; kc <= rb; ++kc) {
             const unsigned dst = base + stage * I8_STAGE, sb = bars + 40 * stage;
             tma::mbar_wait_bounded(sb + 24, phase ^ 1u);        // K_* planes 0-3 of this slot are free
-            if (p.debug & 2) {
-              tma::mbar_arrive(sb + 8);
-            } else {
-              tma::mbar_arrive_expect_tx(sb + 8, I8_STAGE_A / 2);
-              tma::load_3d(dst, &mapK, kc * I8_KC, tile * I8_TILE, 0, sb + 8);
+            if (tma::elect_one()) {
+              if (p.debug & 2) {
+                tma::mbar_arrive(sb + 8);
+              } else {
+                tma::mbar_arrive_expect_tx(sb + 8, I8_STAGE_A / 2);
+                tma::load_3d(dst, &mapK, kc * I8_KC, tile * I8_TILE, 0, sb + 8);
+              }
             }
             tma::mbar_wait_bounded(sb + 32, phase ^ 1u);        // ... and the rest of it
-            if (p.debug & 2) {
-              tma::mbar_arrive(sb);
-              tma::mbar_arrive(sb + 16);
-            } else {
-              tma::mbar_arrive_expect_tx(sb, I8_STAGE_B);
-              tma::load_3d(dst + I8_STAGE_A, &mapW, kc * I8_KC, rb * I8_RB, 0, sb);
-              tma::mbar_arrive_expect_tx(sb + 16, I8_STAGE_A / 2);
-              tma::load_3d(dst + I8_STAGE_A / 2, &mapK, kc * I8_KC, tile * I8_TILE, I8_NS / 2, sb + 16);
+            if (tma::elect_one()) {
+              if (p.debug & 2) {
+                tma::mbar_arrive(sb);
+                tma::mbar_arrive(sb + 16);
+              } else {
+                tma::mbar_arrive_expect_tx(sb, I8_STAGE_B);
+                tma::load_3d(dst + I8_STAGE_A, &mapW, kc * I8_KC, rb * I8_RB, 0, sb);
+                tma::mbar_arrive_expect_tx(sb + 16, I8_STAGE_A / 2);
+                tma::load_3d(dst + I8_STAGE_A / 2, &mapK, kc * I8_KC, tile * I8_TILE, I8_NS / 2, sb + 16);
+              }
             }
+            __syncwarp();
             if (++stage == I8_STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -501,7 +510,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0;
       unsigned phase = 0, tphase = 0;
       for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight)
@@ -516,47 +525,64 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
             tc5::fence_after();
             const unsigned long long da = tc5::desc_k_sw64(base + stage * I8_STAGE);
             const unsigned long long dbs = tc5::desc_k_sw64(base + stage * I8_STAGE + I8_STAGE_A);
+            // Digit t of K_* (A operand) meets digits s = 0 .. 7 - t of W at once: the W planes are contiguous in
+            // the stage (64 rows x 64 bytes each), so planes s0 .. s0 + n - 1 form ONE K-major B operand of N = 64 n
+            // rows, and because the level accumulators are contiguous in tensor memory too (level l at columns
+            // 64 l), its product lands on levels t + s0 .. t + s0 + n - 1 in one MMA: 12 wide MMAs (N = 256 / 192 /
+            // 128, one of 64) per k-step instead of 36 of N = 64, which were bound by re-reading the A tile from
+            // shared memory (measured 45 % of the int8 rate).  Digits 0-3 need two MMAs: the second one takes the A
+            // tile from the collector.  k-step outermost: consecutive MMAs write different accumulator columns (the
+            // same columns come up again 12 MMAs later); digit-outermost serialised on the accumulate dependency.
+            auto issue = [&](int ks, int t) {
+              const unsigned long long ad = da + (unsigned long long)((t * I8_TILE * I8_KC + ks * 32) >> 4);
+              const int planes = I8_NS - t;                                 // W digits 0 .. planes - 1
+              const int n0 = planes > 4 ? (planes == 5 ? 3 : 4) : planes;   // 8=4+4 7=4+3 6=4+2 5=3+2
+              const unsigned acc = (kc > 0 || ks > 0 || t > 0) ? 1u : 0u;   // t = 0 covers all 512 columns
+              if (planes > n0) {
+                tc5::mma_i8<1>(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
+                               tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
+                tc5::mma_i8<2>(tmem + (t + n0) * I8_RB, ad,
+                               dbs + (unsigned long long)((n0 * I8_RB * I8_KC + ks * 32) >> 4),
+                               tc5::idesc_i8(I8_TILE, (planes - n0) * I8_RB), acc);
+              } else {
+                tc5::mma_i8<0>(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
+                               tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
+              }
+            };
             if (!(p.debug & 1)) {
-              // Digit t of K_* (A operand) meets digits s = 0 .. 7 - t of W at once: the W planes are contiguous
-              // in the stage (64 rows x 64 bytes each), so planes s0 .. s0 + n - 1 form ONE K-major B operand of
-              // N = 64 n rows, and because the level accumulators are contiguous in tensor memory too
-              // (level l at columns 64 l), its product lands on levels t + s0 .. t + s0 + n - 1 in one MMA.
-              // 12 wide MMAs (N = 256 / 192 / 128, one of 64) per k-step instead of 36 of N = 64, which were
-              // bound by re-reading the A tile from shared memory (measured 45 % of the int8 rate).
-              // k-step outermost: consecutive MMAs then write different accumulator columns (the same columns
-              // come up again 12 MMAs later); with the digit outermost the accumulate dependency serialised them.
+              if (tma::elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks)
+                for (int t = 0; t < I8_NS / 2; ++t) issue(0, t);
+              }
+              __syncwarp();
+              tma::mbar_wait_bounded(sb + 16, phase);                       // K_* planes 4-7
+              tc5::fence_after();
+              if (tma::elect_one()) {
 #pragma unroll
-                for (int t = 0; t < I8_NS; ++t) {
-                  if (ks == 0 && t == I8_NS / 2) {
-                    tma::mbar_wait_bounded(sb + 16, phase);
-                    tc5::fence_after();
-                  }
-                  const unsigned long long ad = da + (unsigned long long)((t * I8_TILE * I8_KC + ks * 32) >> 4);
-                  const int planes = I8_NS - t;                       // W digits 0 .. planes - 1
-                  const int n0 = planes > 4 ? (planes == 5 ? 3 : 4) : planes;   // 8=4+4 7=4+3 6=4+2 5=3+2
-                  const unsigned acc = (kc > 0 || ks > 0 || t > 0) ? 1u : 0u;   // t = 0 covers all 512 columns
-                  tc5::mma_i8(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
-                              tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
-                  if (planes > n0)
-                    tc5::mma_i8(tmem + (t + n0) * I8_RB, ad,
-                                dbs + (unsigned long long)((n0 * I8_RB * I8_KC + ks * 32) >> 4),
-                                tc5::idesc_i8(I8_TILE, (planes - n0) * I8_RB), acc);
-                  if (ks == 1 && t == I8_NS / 2 - 1) tc5::commit(sb + 24);
-                }
-              tc5::commit(sb + 32);
+                for (int t = I8_NS / 2; t < I8_NS; ++t) issue(0, t);
+#pragma unroll
+                for (int t = 0; t < I8_NS / 2; ++t) issue(1, t);
+                tc5::commit(sb + 24);                                       // K_* planes 0-3 are free
+#pragma unroll
+                for (int t = I8_NS / 2; t < I8_NS; ++t) issue(1, t);
+                tc5::commit(sb + 32);                                       // ... and the rest of the stage
+              }
+              __syncwarp();
             } else {
               tma::mbar_wait_bounded(sb + 16, phase);
-              tc5::commit(sb + 24);
-              tc5::commit(sb + 32);
+              if (tma::elect_one()) {
+                tc5::commit(sb + 24);
+                tc5::commit(sb + 32);
+              }
+              __syncwarp();
             }
             if (++stage == I8_STAGES) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          tc5::commit(bar_tfull);                               // accumulators of this row block are complete
+          if (tma::elect_one()) tc5::commit(bar_tfull);         // accumulators of this row block are complete
+          __syncwarp();
           tphase ^= 1u;
         }
     }

@@ -77,6 +77,17 @@ __device__ __forceinline__ void mbar_wait_bounded(unsigned bar, unsigned parity)
     }
   }
 }
+// One lane of the (converged) warp: the form the compiler recognises as "exactly one thread", so that the
+// operands of the TMA / tcgen05 instructions issued under it stay in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred = 0;
+  asm volatile(
+      "{\n .reg .pred px;\n elect.sync _|px, 0xffffffff;\n selp.u32 %0, 1, 0, px;\n}\n"
+      : "=r"(pred)
+      :
+      : "memory");
+  return pred != 0;
+}
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
 }
@@ -147,14 +158,33 @@ __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::aft
 __device__ __forceinline__ void commit(unsigned bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, signed 8-bit operands, 32-bit integer accumulators; K = 32 per instruction
+// D[tmem] (+)= A[smem] * B[smem]^T, signed 8-bit operands, 32-bit integer accumulators; K = 32 per instruction.
+// COLLECT: 0 = plain; 1 = keep the A tile in the tensor core's collector buffer (collector::a::fill);
+//          2 = take A from the collector, last use (collector::a::lastuse) - the A tile is not re-read from
+//          shared memory (SASS: UTCIMMA gdesc.A_KEEP / .A_REUSE).
+template <int COLLECT>
 __device__ __forceinline__ void mma_i8(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
                                        unsigned idesc, unsigned accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-      " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
+  if (COLLECT == 1)
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(
+            d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+  else if (COLLECT == 2)
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(
+            d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+  else
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
 }
 // 32 lanes x 8 consecutive 32-bit columns: thread t of the warp gets lane (taddr.lane + t), columns taddr.col .. +7
 __device__ __forceinline__ void ld_32x32b_x8(unsigned taddr, int (&v)[8]) {
