@@ -275,20 +275,29 @@ struct I8Args {
   const double* kexp;       // [2]: 2^(55 - f), 2^(f - 61)
   const double* V;
   double* partial;          // [ntiles][slices][128][2]
+  unsigned* meet;           // [slices][waves][row blocks of the slice] arrival counters, zero on entry (or null)
+  int meet_stride, meet_waves;   // counters per wave, waves per launch
   unsigned short off[I8_MAX_SLICES + 1];   // row blocks of slice s: order[off[s] .. off[s+1])
   unsigned short order[I8_MAX_RB];
 };
 
-// 56-bit fixed point -> 8 balanced base-128 digits, most significant first (d[0] in [-64, 64], others in [-64, 63])
+// 56-bit fixed point -> 8 balanced base-128 digits, most significant first (d[0] in [-64, 64], others in [-64, 63]).
+// The integer is split once into two balanced 28-bit halves; the digits then come from 32-bit arithmetic.
 __device__ __forceinline__ void digits8(double x_scaled, int (&dg)[I8_NS]) {
-  long long v = __double2ll_rn(x_scaled);
+  const long long v = __double2ll_rn(x_scaled);
+  int lo = (int)((unsigned)(v + (1ll << 27)) & 0x0fffffffu) - (1 << 27);   // v = hi 2^28 + lo, lo in [-2^27, 2^27)
+  int hi = (int)((v - lo) >> 28);
 #pragma unroll
-  for (int s = I8_NS - 1; s > 0; --s) {
-    const int low = (int)((v + 64) & 127) - 64;
-    dg[s] = low;
-    v = (v - low) >> 7;
+  for (int s = 3; s > 0; --s) {
+    const int dl = ((lo + 64) & 127) - 64;
+    dg[4 + s] = dl;
+    lo = (lo - dl) >> 7;
+    const int dh = ((hi + 64) & 127) - 64;
+    dg[s] = dh;
+    hi = (hi - dh) >> 7;
   }
-  dg[0] = (int)v;
+  dg[4] = lo;   // in [-64, 64]
+  dg[0] = hi;
 }
 
 // 2^(55 - f) and 2^(f - 61) with f = exponent of scale * max_i |kvec_i| (K_* = scale * matern * kvec, matern <= 1)
@@ -450,7 +459,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
   volatile unsigned* slot_ptr = reinterpret_cast<volatile unsigned*>(smem_raw + (slot - raw));
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler too
-  const int slice = blockIdx.x % p.slices, tl = blockIdx.x / p.slices;
+  // the CTAs that walk the same row blocks of W (one per tile in flight) are neighbours in the grid
+  const int slice = blockIdx.x / p.tiles_in_flight, tl = blockIdx.x % p.tiles_in_flight;
 
   if (warp == 0 && lane == 0) {
     tma::prefetch_map(&mapK);
@@ -475,9 +485,23 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
     {
       int stage = 0;
       unsigned phase = 0;
-      for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight)
+      int wave = 0;
+      for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight, ++wave)
         for (int r = r_begin; r < r_end; ++r) {
           const int rb = p.order[r];
+          // Soft rendezvous of the CTAs that stream the same row block of W for different candidate tiles: they
+          // start it within a few microseconds of each other, so that one of them pulls the digit planes from HBM
+          // and the others hit L2 (without it they drift apart and W was read 3.6 times per wave: 35.7 GB of
+          // DRAM reads per launch).  Performance only - the wait is short and bounded, never a dependency.
+          if (p.meet && lane == 0) {
+            unsigned* ctr = p.meet + ((size_t)slice * p.meet_waves + wave) * p.meet_stride + (r - r_begin);
+            const int left = p.ntiles - wave * p.tiles_in_flight;
+            const unsigned want = left < p.tiles_in_flight ? left : p.tiles_in_flight;
+            atomicAdd(ctr, 1u);
+            const unsigned long long t0 = globaltimer_ns();
+            while (*(volatile unsigned*)ctr < want && globaltimer_ns() - t0 < 30000ull) __nanosleep(200);
+          }
+          __syncwarp();
           for (int kc = 0; kc <= rb; ++kc) {
             const unsigned dst = base + stage * I8_STAGE, sb = bars + 40 * stage;
             tma::mbar_wait_bounded(sb + 24, phase ^ 1u);        // K_* planes 0-3 of this slot are free
@@ -780,10 +804,17 @@ static void i8_shape(int n_pad, int* slices, int* tiles_in_flight) {
 
 }  // namespace db
 
+static int64_t i8_meet_words(int n_pad) {
+  // slices * waves * row blocks per slice <= (slices * waves) * n_rb; slices * tiles in flight <= SMs
+  return (int64_t)(distbo_score_chunk() / I8_TILE) * (n_pad / I8_RB) + 2;
+}
+
 extern "C" int64_t distbo_score_i8_workspace(int n_pad) {
   const int64_t chunk = distbo_score_chunk();
   // digit planes of the K_* chunk (8 bytes per element), per-slice partial sums, the two exponent factors
-  return chunk * n_pad + (chunk / I8_TILE) * I8_MAX_SLICES * I8_TILE * 2 + 2;
+  // + arrival counters of the row-block rendezvous (one per slice, wave and row block of the slice)
+  // (the digit planes are double buffered: chunk i + 1 is generated while chunk i is contracted)
+  return 2 * chunk * n_pad + (chunk / I8_TILE) * I8_MAX_SLICES * I8_TILE * 2 + 2 + i8_meet_words(n_pad) / 2 + 1;
 }
 
 extern "C" int distbo_score_i8_prepare(const double* W, int n_pad, int8_t* W8, double* rowscale, void* stream) {
@@ -814,11 +845,12 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
     DB_CUDA(cudaFuncSetAttribute(score_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
     once.mark();
   }
-  signed char* K8 = reinterpret_cast<signed char*>(ws);
-  double* partial = ws + (size_t)chunk * n_pad;
+  signed char* K8[2] = {reinterpret_cast<signed char*>(ws), reinterpret_cast<signed char*>(ws + (size_t)chunk * n_pad)};
+  double* partial = ws + 2 * (size_t)chunk * n_pad;
   double* kexp = partial + (size_t)(chunk / I8_TILE) * I8_MAX_SLICES * I8_TILE * 2;
-  CUtensorMap mapK, mapW;
-  if (!tma::encode_u8_planes(&mapK, K8, (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE, I8_NS / 2) ||
+  CUtensorMap mapK[2], mapW;
+  if (!tma::encode_u8_planes(&mapK[0], K8[0], (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE, I8_NS / 2) ||
+      !tma::encode_u8_planes(&mapK[1], K8[1], (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE, I8_NS / 2) ||
       !tma::encode_u8_planes(&mapW, W8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS))
     return DISTBO_ECUDA;
   I8Args ia;
@@ -830,34 +862,82 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
     ia.debug = dbg ? atoi(dbg) : 0;
   }
   ia.rowscale = rowscale; ia.kexp = kexp; ia.V = V; ia.partial = partial;
+  unsigned* meet = reinterpret_cast<unsigned*>(kexp + 2);
+  int max_rb = 0;
+  for (int sl = 0; sl < ia.slices; ++sl) max_rb = max_rb > ia.off[sl + 1] - ia.off[sl] ? max_rb : ia.off[sl + 1] - ia.off[sl];
+  ia.meet_stride = max_rb;
+  ia.meet = getenv("DISTBO_I8_NOMEET") ? nullptr : meet;
   i8_kexp_kernel<<<1, 256, 0, st>>>(kvec, N, log_scale, kexp);
   DB_CHECK_LAUNCH();
-  int first = 1;
-  for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+  // The digit planes of chunk i + 1 (fp64 ALU work: Matern + digit extraction) are generated on a side stream
+  // while chunk i is contracted on the tensor cores: the contraction kernel is enqueued first and takes one CTA
+  // per SM, the generator's CTAs fill the registers that are left.  Stream and events live for this call only
+  // (re-entrant; destruction is deferred by the runtime until the work has drained).
+  const int64_t nchunks = (M + chunk - 1) / chunk;
+  // (measured: 9 % faster at N = 600 .. 1230, 3 % slower at N = 8192 where the step is power-capped and the
+  // generator takes clock from the tensor kernel - so only below n_pad = 4096)
+  const bool overlap = nchunks > 1 && n_pad < 4096 && !getenv("DISTBO_I8_NOOVERLAP");
+  cudaStream_t s2 = st;
+  cudaEvent_t evK[2] = {nullptr, nullptr}, evS[2] = {nullptr, nullptr}, ev0 = nullptr;
+  if (overlap) {
+    DB_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      DB_CUDA(cudaEventCreateWithFlags(&evK[b], cudaEventDisableTiming));
+      DB_CUDA(cudaEventCreateWithFlags(&evS[b], cudaEventDisableTiming));
+    }
+    DB_CUDA(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+    DB_CUDA(cudaEventRecord(ev0, st));
+    DB_CUDA(cudaStreamWaitEvent(s2, ev0, 0));
+  }
+  auto gen_planes = [&](int64_t ci) -> int {
+    const int64_t c0 = ci * chunk;
     const int64_t mc = (M - c0 < chunk) ? (M - c0) : chunk;
     const int tiles = (int)((mc + I8_TILE - 1) / I8_TILE);
     const int kgrid = tiles * I8_TILE / KST_CAND;
+    signed char* dstK = K8[ci & 1];
+    if (overlap && ci >= 2) DB_CUDA(cudaStreamWaitEvent(s2, evS[ci & 1], 0));   // chunk ci - 2 has left this buffer
     if (d <= 4)
-      i8_kst_kernel<4><<<kgrid, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale, theta_c,
-                                               cand_shift, cand_scale, (long long)c0, (long long)M, kexp, chunk, K8);
+      i8_kst_kernel<4><<<kgrid, 256, 0, s2>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale, theta_c,
+                                               cand_shift, cand_scale, (long long)c0, (long long)M, kexp, chunk, dstK);
     else if (d <= 8)
-      i8_kst_kernel<8><<<kgrid, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale, theta_c,
-                                               cand_shift, cand_scale, (long long)c0, (long long)M, kexp, chunk, K8);
+      i8_kst_kernel<8><<<kgrid, 256, 0, s2>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale, theta_c,
+                                               cand_shift, cand_scale, (long long)c0, (long long)M, kexp, chunk, dstK);
     else
-      i8_kst_kernel<SCORE_DMAX><<<kgrid, 256, 0, st>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale,
+      i8_kst_kernel<SCORE_DMAX><<<kgrid, 256, 0, s2>>>(theta_s, sqnorm, N, n_pad, d, log_bw, kvec, log_scale,
                                                         theta_c, cand_shift, cand_scale, (long long)c0,
-                                                        (long long)M, kexp, chunk, K8);
+                                                        (long long)M, kexp, chunk, dstK);
     DB_CHECK_LAUNCH();
+    if (overlap) DB_CUDA(cudaEventRecord(evK[ci & 1], s2));
+    return DISTBO_OK;
+  };
+  {
+    const int rc0 = gen_planes(0);
+    if (rc0 != DISTBO_OK) return rc0;
+  }
+  int first = 1;
+  for (int64_t ci = 0; ci < nchunks; ++ci) {
+    const int64_t c0 = ci * chunk;
+    const int64_t mc = (M - c0 < chunk) ? (M - c0) : chunk;
+    const int tiles = (int)((mc + I8_TILE - 1) / I8_TILE);
+    if (overlap) DB_CUDA(cudaStreamWaitEvent(st, evK[ci & 1], 0));
     ia.ntiles = tiles;
     const int tf = ia.tiles_in_flight < tiles ? ia.tiles_in_flight : tiles;
     I8Args launch = ia;
     launch.tiles_in_flight = tf;
+    launch.meet_waves = (tiles + tf - 1) / tf;
+    if (launch.meet)
+      DB_CUDA(cudaMemsetAsync(meet, 0, sizeof(unsigned) * (size_t)ia.slices * launch.meet_waves * max_rb, st));
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     const bool timed = g_timing && timing_pair(&t0, &t1);
     if (timed) cudaEventRecord(t0, st);
-    score_i8_kernel<<<ia.slices * tf, I8_THREADS, I8_SMEM, st>>>(mapK, mapW, launch);
+    score_i8_kernel<<<ia.slices * tf, I8_THREADS, I8_SMEM, st>>>(mapK[ci & 1], mapW, launch);
     DB_CHECK_LAUNCH();
     if (timed) cudaEventRecord(t1, st);
+    if (overlap) DB_CUDA(cudaEventRecord(evS[ci & 1], st));
+    if (ci + 1 < nchunks) {                      // enqueued AFTER the contraction: its CTAs are placed first
+      const int rcn = gen_planes(ci + 1);
+      if (rcn != DISTBO_OK) return rcn;
+    }
     ScoreArgs a;
     a.W = nullptr; a.V = V; a.Kst = nullptr; a.n_pad = n_pad;
     a.slices = ia.slices; a.tile_w = I8_TILE; a.partial = partial;
@@ -872,6 +952,14 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
                                         (long long*)best_idx);
     DB_CHECK_LAUNCH();
     first = 0;
+  }
+  if (overlap) {
+    for (int b = 0; b < 2; ++b) {
+      cudaEventDestroy(evK[b]);
+      cudaEventDestroy(evS[b]);
+    }
+    cudaEventDestroy(ev0);
+    cudaStreamDestroy(s2);
   }
   return DISTBO_OK;
 }
