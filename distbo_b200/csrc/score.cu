@@ -275,6 +275,10 @@ struct I8Args {
   const double* kexp;       // [2]: 2^(55 - f), 2^(f - 61)
   const double* V;
   double* partial;          // [ntiles][slices][128][2]
+  const int4* items;        // MODE 1: (a_row, b_row, first k-chunk, end k-chunk) per work item
+  const int* item_off;      // MODE 1: items of CTA b = items[item_off[b] .. item_off[b + 1])
+  double* C;                // MODE 1: output matrix
+  int ldc;
   unsigned* meet;           // [slices][waves][row blocks of the slice] arrival counters, zero on entry (or null)
   int meet_stride, meet_waves;   // counters per wave, waves per launch
   unsigned short off[I8_MAX_SLICES + 1];   // row blocks of slice s: order[off[s] .. off[s+1])
@@ -443,6 +447,31 @@ __global__ void __launch_bounds__(256, 2) i8_kst_kernel(const double* __restrict
   }
 }
 
+// Work items of one CTA: (first row of the A tile, first row of the B block, k-chunk range).
+//   MODE 0 (scoring): derived from (slice, tile wave): A = K_* planes of the candidate tile, B = W planes of row
+//                     block rb, k-chunks 0 .. rb (W is lower triangular); the read-back reduces over the rows of W.
+//   MODE 1 (LAUUM)  : explicit list p.items[p.item_off[cta] .. p.item_off[cta + 1]): A and B are both planes of
+//                     T = W^T (row i of T = column i of W), C[i,j] = sum_k T[i,k] T[j,k] is stored as fp64.
+template <int MODE, class F>
+__device__ __forceinline__ void i8_for_items(const I8Args& p, int slice, int tl, F&& f) {
+  if (MODE == 0) {
+    const int r_begin = p.off[slice], r_end = p.off[slice + 1];
+    int wave = 0;
+    for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight, ++wave)
+      for (int r = r_begin; r < r_end; ++r) {
+        const int rb = p.order[r];
+        f(tile * I8_TILE, rb * I8_RB, 0, rb + 1, tile, wave, r - r_begin, r == r_end - 1);
+      }
+  } else {
+    const int i0 = p.item_off[blockIdx.x], i1 = p.item_off[blockIdx.x + 1];
+    for (int it = i0; it < i1; ++it) {
+      const int4 w = __ldg(p.items + it);
+      f(w.x, w.y, w.z, w.w, 0, 0, 0, false);
+    }
+  }
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(I8_THREADS, 1)
     score_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapW,
                     const __grid_constant__ I8Args p) {
@@ -460,7 +489,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler too
   // the CTAs that walk the same row blocks of W (one per tile in flight) are neighbours in the grid
-  const int slice = blockIdx.x / p.tiles_in_flight, tl = blockIdx.x % p.tiles_in_flight;
+  const int slice = MODE == 0 ? blockIdx.x / p.tiles_in_flight : 0;
+  const int tl = MODE == 0 ? blockIdx.x % p.tiles_in_flight : 0;
 
   if (warp == 0 && lane == 0) {
     tma::prefetch_map(&mapK);
@@ -476,183 +506,246 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
   __syncthreads();
   tc5::fence_after();
   const unsigned tmem = *slot_ptr;
-  const int r_begin = p.off[slice], r_end = p.off[slice + 1];
 
   // Warps 0 and 1 run their loops with all 32 lanes and issue under elect.sync: in a `lane == 0` branch the
   // compiler cannot prove the descriptors uniform and wraps every UTCIMMA / UTMALDG in a vote-and-broadcast
   // loop (~20 instructions each), which made the single issuing thread the bottleneck of the pipeline.
   if (warp == 0) {
-    {
-      int stage = 0;
-      unsigned phase = 0;
-      int wave = 0;
-      for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight, ++wave)
-        for (int r = r_begin; r < r_end; ++r) {
-          const int rb = p.order[r];
-          // Soft rendezvous of the CTAs that stream the same row block of W for different candidate tiles: they
-          // start it within a few microseconds of each other, so that one of them pulls the digit planes from HBM
-          // and the others hit L2 (without it they drift apart and W was read 3.6 times per wave: 35.7 GB of
-          // DRAM reads per launch).  Performance only - the wait is short and bounded, never a dependency.
-          if (p.meet && lane == 0) {
-            unsigned* ctr = p.meet + ((size_t)slice * p.meet_waves + wave) * p.meet_stride + (r - r_begin);
-            const int left = p.ntiles - wave * p.tiles_in_flight;
-            const unsigned want = left < p.tiles_in_flight ? left : p.tiles_in_flight;
-            atomicAdd(ctr, 1u);
-            const unsigned long long t0 = globaltimer_ns();
-            while (*(volatile unsigned*)ctr < want && globaltimer_ns() - t0 < 30000ull) __nanosleep(200);
-          }
-          __syncwarp();
-          for (int kc = 0; kc <= rb; ++kc) {
-            const unsigned dst = base + stage * I8_STAGE, sb = bars + 40 * stage;
-            tma::mbar_wait_bounded(sb + 24, phase ^ 1u);        // K_* planes 0-3 of this slot are free
-            if (tma::elect_one()) {
-              if (p.debug & 2) {
-                tma::mbar_arrive(sb + 8);
-              } else {
-                tma::mbar_arrive_expect_tx(sb + 8, I8_STAGE_A / 2);
-                tma::load_3d(dst, &mapK, kc * I8_KC, tile * I8_TILE, 0, sb + 8);
-              }
-            }
-            tma::mbar_wait_bounded(sb + 32, phase ^ 1u);        // ... and the rest of it
-            if (tma::elect_one()) {
-              if (p.debug & 2) {
-                tma::mbar_arrive(sb);
-                tma::mbar_arrive(sb + 16);
-              } else {
-                tma::mbar_arrive_expect_tx(sb, I8_STAGE_B);
-                tma::load_3d(dst + I8_STAGE_A, &mapW, kc * I8_KC, rb * I8_RB, 0, sb);
-                tma::mbar_arrive_expect_tx(sb + 16, I8_STAGE_A / 2);
-                tma::load_3d(dst + I8_STAGE_A / 2, &mapK, kc * I8_KC, tile * I8_TILE, I8_NS / 2, sb + 16);
-              }
-            }
-            __syncwarp();
-            if (++stage == I8_STAGES) {
-              stage = 0;
-              phase ^= 1u;
-            }
+    int stage = 0;
+    unsigned phase = 0;
+    i8_for_items<MODE>(p, slice, tl, [&](int a_row, int b_row, int kb, int ke, int tile, int wave, int ri, bool) {
+      // Soft rendezvous of the CTAs that stream the same row block of W for different candidate tiles: they
+      // start it within a few microseconds of each other, so that one of them pulls the digit planes from HBM
+      // and the others hit L2 (without it they drift apart and W was read 3.6 times per wave: 35.7 GB of
+      // DRAM reads per launch).  Performance only - the wait is short and bounded, never a dependency.
+      if (MODE == 0 && p.meet && lane == 0) {
+        unsigned* ctr = p.meet + ((size_t)slice * p.meet_waves + wave) * p.meet_stride + ri;
+        const int left = p.ntiles - wave * p.tiles_in_flight;
+        const unsigned want = left < p.tiles_in_flight ? left : p.tiles_in_flight;
+        atomicAdd(ctr, 1u);
+        const unsigned long long t0 = globaltimer_ns();
+        while (*(volatile unsigned*)ctr < want && globaltimer_ns() - t0 < 30000ull) __nanosleep(200);
+      }
+      __syncwarp();
+      for (int kc = kb; kc < ke; ++kc) {
+        const unsigned dst = base + stage * I8_STAGE, sb = bars + 40 * stage;
+        tma::mbar_wait_bounded(sb + 24, phase ^ 1u);            // A planes 0-3 of this slot are free
+        if (tma::elect_one()) {
+          if (p.debug & 2) {
+            tma::mbar_arrive(sb + 8);
+          } else {
+            tma::mbar_arrive_expect_tx(sb + 8, I8_STAGE_A / 2);
+            tma::load_3d(dst, &mapK, kc * I8_KC, a_row, 0, sb + 8);
           }
         }
-    }
+        tma::mbar_wait_bounded(sb + 32, phase ^ 1u);            // ... and the rest of it
+        if (tma::elect_one()) {
+          if (p.debug & 2) {
+            tma::mbar_arrive(sb);
+            tma::mbar_arrive(sb + 16);
+          } else {
+            tma::mbar_arrive_expect_tx(sb, I8_STAGE_B);
+            tma::load_3d(dst + I8_STAGE_A, &mapW, kc * I8_KC, b_row, 0, sb);
+            tma::mbar_arrive_expect_tx(sb + 16, I8_STAGE_A / 2);
+            tma::load_3d(dst + I8_STAGE_A / 2, &mapK, kc * I8_KC, a_row, I8_NS / 2, sb + 16);
+          }
+        }
+        __syncwarp();
+        if (++stage == I8_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    });
   } else if (warp == 1) {
-    {
-      int stage = 0;
-      unsigned phase = 0, tphase = 0;
-      for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight)
-        for (int r = r_begin; r < r_end; ++r) {
-          const int rb = p.order[r];
-          tma::mbar_wait_bounded(bar_tempty, tphase ^ 1u);      // the read-back of the previous row block is done
-          tc5::fence_after();
-          for (int kc = 0; kc <= rb; ++kc) {
-            const unsigned sb = bars + 40 * stage;
-            tma::mbar_wait_bounded(sb, phase);
-            tma::mbar_wait_bounded(sb + 8, phase);
-            tc5::fence_after();
-            const unsigned long long da = tc5::desc_k_sw64(base + stage * I8_STAGE);
-            const unsigned long long dbs = tc5::desc_k_sw64(base + stage * I8_STAGE + I8_STAGE_A);
-            // Digit t of K_* (A operand) meets digits s = 0 .. 7 - t of W at once: the W planes are contiguous in
-            // the stage (64 rows x 64 bytes each), so planes s0 .. s0 + n - 1 form ONE K-major B operand of N = 64 n
-            // rows, and because the level accumulators are contiguous in tensor memory too (level l at columns
-            // 64 l), its product lands on levels t + s0 .. t + s0 + n - 1 in one MMA: 12 wide MMAs (N = 256 / 192 /
-            // 128, one of 64) per k-step instead of 36 of N = 64, which were bound by re-reading the A tile from
-            // shared memory (measured 45 % of the int8 rate).  Digits 0-3 need two MMAs: the second one takes the A
-            // tile from the collector.  k-step outermost: consecutive MMAs write different accumulator columns (the
-            // same columns come up again 12 MMAs later); digit-outermost serialised on the accumulate dependency.
-            auto issue = [&](int ks, int t) {
-              const unsigned long long ad = da + (unsigned long long)((t * I8_TILE * I8_KC + ks * 32) >> 4);
-              const int planes = I8_NS - t;                                 // W digits 0 .. planes - 1
-              const int n0 = planes > 4 ? (planes == 5 ? 3 : 4) : planes;   // 8=4+4 7=4+3 6=4+2 5=3+2
-              const unsigned acc = (kc > 0 || ks > 0 || t > 0) ? 1u : 0u;   // t = 0 covers all 512 columns
-              if (planes > n0) {
-                tc5::mma_i8<1>(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
-                               tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
-                tc5::mma_i8<2>(tmem + (t + n0) * I8_RB, ad,
-                               dbs + (unsigned long long)((n0 * I8_RB * I8_KC + ks * 32) >> 4),
-                               tc5::idesc_i8(I8_TILE, (planes - n0) * I8_RB), acc);
-              } else {
-                tc5::mma_i8<0>(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
-                               tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
-              }
-            };
-            if (!(p.debug & 1)) {
-              if (tma::elect_one()) {
-#pragma unroll
-                for (int t = 0; t < I8_NS / 2; ++t) issue(0, t);
-              }
-              __syncwarp();
-              tma::mbar_wait_bounded(sb + 16, phase);                       // K_* planes 4-7
-              tc5::fence_after();
-              if (tma::elect_one()) {
-#pragma unroll
-                for (int t = I8_NS / 2; t < I8_NS; ++t) issue(0, t);
-#pragma unroll
-                for (int t = 0; t < I8_NS / 2; ++t) issue(1, t);
-                tc5::commit(sb + 24);                                       // K_* planes 0-3 are free
-#pragma unroll
-                for (int t = I8_NS / 2; t < I8_NS; ++t) issue(1, t);
-                tc5::commit(sb + 32);                                       // ... and the rest of the stage
-              }
-              __syncwarp();
-            } else {
-              tma::mbar_wait_bounded(sb + 16, phase);
-              if (tma::elect_one()) {
-                tc5::commit(sb + 24);
-                tc5::commit(sb + 32);
-              }
-              __syncwarp();
-            }
-            if (++stage == I8_STAGES) {
-              stage = 0;
-              phase ^= 1u;
-            }
+    int stage = 0;
+    unsigned phase = 0, tphase = 0;
+    i8_for_items<MODE>(p, slice, tl, [&](int, int, int kb, int ke, int, int, int, bool) {
+      tma::mbar_wait_bounded(bar_tempty, tphase ^ 1u);          // the read-back of the previous item is done
+      tc5::fence_after();
+      for (int kc = kb; kc < ke; ++kc) {
+        const unsigned sb = bars + 40 * stage;
+        tma::mbar_wait_bounded(sb, phase);
+        tma::mbar_wait_bounded(sb + 8, phase);
+        tc5::fence_after();
+        const unsigned long long da = tc5::desc_k_sw64(base + stage * I8_STAGE);
+        const unsigned long long dbs = tc5::desc_k_sw64(base + stage * I8_STAGE + I8_STAGE_A);
+        // Digit t of the A operand meets digits s = 0 .. 7 - t of the B operand at once: the B planes are
+        // contiguous in the stage (64 rows x 64 bytes each), so planes s0 .. s0 + n - 1 form ONE K-major B operand
+        // of N = 64 n rows, and because the level accumulators are contiguous in tensor memory too (level l at
+        // columns 64 l), its product lands on levels t + s0 .. t + s0 + n - 1 in one MMA: 12 wide MMAs (N = 256 /
+        // 192 / 128, one of 64) per k-step instead of 36 of N = 64, which were bound by re-reading the A tile from
+        // shared memory (measured 45 % of the int8 rate).  Digits 0-3 need two MMAs: the second one takes the A
+        // tile from the collector.  k-step outermost: consecutive MMAs write different accumulator columns (the
+        // same columns come up again 12 MMAs later); digit-outermost serialised on the accumulate dependency.
+        auto issue = [&](int ks, int t) {
+          const unsigned long long ad = da + (unsigned long long)((t * I8_TILE * I8_KC + ks * 32) >> 4);
+          const int planes = I8_NS - t;                                 // B digits 0 .. planes - 1
+          const int n0 = planes > 4 ? (planes == 5 ? 3 : 4) : planes;   // 8=4+4 7=4+3 6=4+2 5=3+2
+          const unsigned acc = (kc > kb || ks > 0 || t > 0) ? 1u : 0u;  // t = 0 covers all 512 columns
+          if (planes > n0) {
+            tc5::mma_i8<1>(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
+                           tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
+            tc5::mma_i8<2>(tmem + (t + n0) * I8_RB, ad,
+                           dbs + (unsigned long long)((n0 * I8_RB * I8_KC + ks * 32) >> 4),
+                           tc5::idesc_i8(I8_TILE, (planes - n0) * I8_RB), acc);
+          } else {
+            tc5::mma_i8<0>(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
+                           tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
           }
-          if (tma::elect_one()) tc5::commit(bar_tfull);         // accumulators of this row block are complete
+        };
+        if (!(p.debug & 1)) {
+          if (tma::elect_one()) {
+#pragma unroll
+            for (int t = 0; t < I8_NS / 2; ++t) issue(0, t);
+          }
           __syncwarp();
-          tphase ^= 1u;
+          tma::mbar_wait_bounded(sb + 16, phase);                       // A planes 4-7
+          tc5::fence_after();
+          if (tma::elect_one()) {
+#pragma unroll
+            for (int t = I8_NS / 2; t < I8_NS; ++t) issue(0, t);
+#pragma unroll
+            for (int t = 0; t < I8_NS / 2; ++t) issue(1, t);
+            tc5::commit(sb + 24);                                       // A planes 0-3 are free
+#pragma unroll
+            for (int t = I8_NS / 2; t < I8_NS; ++t) issue(1, t);
+            tc5::commit(sb + 32);                                       // ... and the rest of the stage
+          }
+          __syncwarp();
+        } else {
+          tma::mbar_wait_bounded(sb + 16, phase);
+          if (tma::elect_one()) {
+            tc5::commit(sb + 24);
+            tc5::commit(sb + 32);
+          }
+          __syncwarp();
         }
-    }
+        if (++stage == I8_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (tma::elect_one()) tc5::commit(bar_tfull);             // accumulators of this item are complete
+      __syncwarp();
+      tphase ^= 1u;
+    });
   } else {
     const int q = warp & 3;                                     // tensor-memory lane quadrant of this warp
-    const int c = q * 32 + lane;                                // candidate within the tile
+    const int c = q * 32 + lane;                                // row within the A tile
     const unsigned tq = tmem + ((unsigned)(q * 32) << 16);
-    const double kx = p.kexp[1];
+    const double kx = MODE == 0 ? p.kexp[1] : 4.336808689942017736e-19;   // 2^(f - 61) / 2^-61
     unsigned tphase = 0;
-    for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight) {
-      double s2 = 0.0, sv = 0.0;
-      for (int r = r_begin; r < r_end; ++r) {
-        const int rb = p.order[r];
-        tma::mbar_wait_bounded(bar_tfull, tphase);
-        tphase ^= 1u;
-        tc5::fence_after();
+    double s2 = 0.0, sv = 0.0;
+    i8_for_items<MODE>(p, slice, tl, [&](int a_row, int b_row, int, int, int tile, int, int, bool last) {
+      tma::mbar_wait_bounded(bar_tfull, tphase);
+      tphase ^= 1u;
+      tc5::fence_after();
+      const double rsa = MODE == 1 ? __ldg(p.rowscale + a_row + c) * kx : kx;
+      double* crow = MODE == 1 ? p.C + (size_t)(a_row + c) * p.ldc + b_row : nullptr;
 #pragma unroll 1
-        for (int j0 = 0; j0 < ((p.debug & 4) ? 0 : I8_RB); j0 += 8) {
-          int a[I8_NS][8];
+      for (int j0 = 0; j0 < ((p.debug & 4) ? 0 : I8_RB); j0 += 8) {
+        int a[I8_NS][8];
 #pragma unroll
-          for (int l = 0; l < I8_NS; ++l) tc5::ld_32x32b_x8(tq + l * I8_RB + j0, a[l]);
-          tc5::wait_ld();
+        for (int l = 0; l < I8_NS; ++l) tc5::ld_32x32b_x8(tq + l * I8_RB + j0, a[l]);
+        tc5::wait_ld();
+        double out[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const long long hi = ((((long long)a[0][j] * 128 + a[1][j]) * 128 + a[2][j]) * 128) + a[3][j];
-            const long long lo = ((((long long)a[4][j] * 128 + a[5][j]) * 128 + a[6][j]) * 128) + a[7][j];
-            const int i = rb * I8_RB + j0 + j;
-            const double av = (__ldg(p.rowscale + i) * kx) * fma((double)hi, 268435456.0, (double)lo);
+        for (int j = 0; j < 8; ++j) {
+          const long long hi = ((((long long)a[0][j] * 128 + a[1][j]) * 128 + a[2][j]) * 128) + a[3][j];
+          const long long lo = ((((long long)a[4][j] * 128 + a[5][j]) * 128 + a[6][j]) * 128) + a[7][j];
+          const int i = b_row + j0 + j;
+          const double av = (__ldg(p.rowscale + i) * rsa) * fma((double)hi, 268435456.0, (double)lo);
+          if (MODE == 0) {
             s2 = fma(av, av, s2);
             sv = fma(av, __ldg(p.V + i), sv);
+          } else {
+            out[j] = av;
           }
         }
-        tc5::fence_before();
-        __syncwarp();
-        if (lane == 0) tma::mbar_arrive(bar_tempty);
+        if (MODE == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2)
+            *reinterpret_cast<double2*>(crow + j0 + j) = make_double2(out[j], out[j + 1]);
+        }
       }
-      double* dst = p.partial + (((size_t)tile * p.slices + slice) * I8_TILE + c) * 2;
-      dst[0] = s2;
-      dst[1] = sv;
-    }
+      tc5::fence_before();
+      __syncwarp();
+      if (lane == 0) tma::mbar_arrive(bar_tempty);
+      if (MODE == 0 && last) {
+        double* dst = p.partial + (((size_t)tile * p.slices + slice) * I8_TILE + c) * 2;
+        dst[0] = s2;
+        dst[1] = sv;
+        s2 = sv = 0.0;
+      }
+    });
   }
   tc5::fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc5::dealloc(tmem, 512);
+  }
+}
+
+// digit planes of T = W^T with one exponent per row of T (= column of W): T8[s][i][k] = digit s of W[k][i] (k >= i)
+// colmax pass: CTA = 64 columns x 512 rows of the lower triangle (4 row lanes per column), merged with an integer
+// atomicMax on the bit pattern (non-negative doubles order like integers); colmax must be zero on entry
+__global__ void __launch_bounds__(256) i8_colmax_kernel(const double* __restrict__ W, int n_pad,
+                                                        unsigned long long* __restrict__ colmax) {
+  const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int k0 = blockIdx.y * 512, k1 = min(n_pad, k0 + 512);
+  if (k1 <= blockIdx.x * 64) return;                            // chunk entirely above the diagonal
+  double m = 0.0;
+  for (int k = max(k0, i) + (threadIdx.x >> 6); k < k1; k += 4) m = fmax(m, fabs(W[(size_t)k * n_pad + i]));
+  if (m > 0.0) atomicMax(colmax + i, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void __launch_bounds__(256) i8_colscale_kernel(double* __restrict__ colscale, int n_pad) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_pad) return;
+  const double m = colscale[i];   // the column maximum (bit pattern written by atomicMax)
+  int e = 0;
+  if (m > 0.0 && isfinite(m)) frexp(m, &e);
+  colscale[i] = ldexp(1.0, e);
+}
+
+// CTA = 64 x 64 tile (k block, i block) of the lower triangle of W, transposed through shared memory
+__global__ void __launch_bounds__(256) i8_wtsplit_kernel(const double* __restrict__ W, int n_pad,
+                                                         const double* __restrict__ colscale,
+                                                         signed char* __restrict__ T8) {
+  __shared__ __align__(16) unsigned char sm[I8_NS][64][64];   // [plane][i][k]
+  // lower-triangular tile index -> (kb, ib), ib <= kb
+  int kb = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((kb + 1) * (kb + 2) / 2 <= (int)blockIdx.x) ++kb;
+  while (kb * (kb + 1) / 2 > (int)blockIdx.x) --kb;
+  const int ib = blockIdx.x - kb * (kb + 1) / 2;
+  const int tid = threadIdx.x;
+  const int il = tid & 63;
+  const int i = ib * 64 + il;
+  const double sc = ldexp(1.0, I8_FRAC) / colscale[i];          // colscale is a power of two: exact
+  // (colscale was turned into 2^exponent by i8_colscale_kernel)
+  for (int kq = tid >> 6; kq < 16; kq += 4) {                   // four consecutive k per thread
+    unsigned pk[I8_NS];
+#pragma unroll
+    for (int s = 0; s < I8_NS; ++s) pk[s] = 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = kb * 64 + kq * 4 + u;
+      int dg[I8_NS];
+      digits8(k >= i ? W[(size_t)k * n_pad + i] * sc : 0.0, dg);
+#pragma unroll
+      for (int s = 0; s < I8_NS; ++s) pk[s] |= (unsigned)(dg[s] & 0xff) << (8 * u);
+    }
+#pragma unroll
+    for (int s = 0; s < I8_NS; ++s) *reinterpret_cast<unsigned*>(&sm[s][il][kq * 4]) = pk[s];
+  }
+  __syncthreads();
+  const size_t plane = (size_t)n_pad * n_pad;
+  for (int v = tid; v < I8_NS * 64 * 4; v += 256) {             // 16-byte pieces: [plane][i][4 pieces]
+    const int s = v >> 8, r = (v >> 2) & 63, q = v & 3;
+    *reinterpret_cast<uint4*>(T8 + s * plane + (size_t)(ib * 64 + r) * n_pad + kb * 64 + q * 16) =
+        *reinterpret_cast<const uint4*>(&sm[s][r][q * 16]);
   }
 }
 
@@ -842,7 +935,7 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
   const int chunk = distbo_score_chunk();
   static PerDeviceOnce once;
   if (once.needed()) {
-    DB_CUDA(cudaFuncSetAttribute(score_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    DB_CUDA(cudaFuncSetAttribute(score_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
     once.mark();
   }
   signed char* K8[2] = {reinterpret_cast<signed char*>(ws), reinterpret_cast<signed char*>(ws + (size_t)chunk * n_pad)};
@@ -862,6 +955,7 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
     ia.debug = dbg ? atoi(dbg) : 0;
   }
   ia.rowscale = rowscale; ia.kexp = kexp; ia.V = V; ia.partial = partial;
+  ia.items = nullptr; ia.item_off = nullptr; ia.C = nullptr; ia.ldc = 0;
   unsigned* meet = reinterpret_cast<unsigned*>(kexp + 2);
   int max_rb = 0;
   for (int sl = 0; sl < ia.slices; ++sl) max_rb = max_rb > ia.off[sl + 1] - ia.off[sl] ? max_rb : ia.off[sl + 1] - ia.off[sl];
@@ -930,7 +1024,7 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     const bool timed = g_timing && timing_pair(&t0, &t1);
     if (timed) cudaEventRecord(t0, st);
-    score_i8_kernel<<<ia.slices * tf, I8_THREADS, I8_SMEM, st>>>(mapK[ci & 1], mapW, launch);
+    score_i8_kernel<0><<<ia.slices * tf, I8_THREADS, I8_SMEM, st>>>(mapK[ci & 1], mapW, launch);
     DB_CHECK_LAUNCH();
     if (timed) cudaEventRecord(t1, st);
     if (overlap) DB_CUDA(cudaEventRecord(evS[ci & 1], st));
@@ -961,5 +1055,100 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
     cudaEventDestroy(ev0);
     cudaStreamDestroy(s2);
   }
+  return DISTBO_OK;
+}
+
+// ---- LAUUM on the tcgen05 tensor cores: Kinv = W^T W = T T^T with T = W^T in int8 digit planes ---------------
+namespace db {
+static int lauum_i8_items(int n_pad, std::vector<int4>* items, std::vector<int>* off) {
+  const int sms = device_sm_count();
+  const int nb = n_pad / I8_TILE, nk = n_pad / I8_KC;
+  struct It { int4 w; double cost; };
+  std::vector<It> all;
+  for (int ib = 0; ib < nb; ++ib)
+    for (int jb = 0; jb <= 2 * ib + 1; ++jb)
+      all.push_back({make_int4(ib * I8_TILE, jb * I8_RB, 2 * ib, nk), (double)(nk - 2 * ib) + 2.0});
+  // longest first onto the least loaded CTA (items are generated with decreasing k range already)
+  std::vector<double> load(sms, 0.0);
+  std::vector<std::vector<int4>> lists(sms);
+  for (const It& it : all) {
+    int best = 0;
+    for (int c = 1; c < sms; ++c)
+      if (load[c] < load[best]) best = c;
+    load[best] += it.cost;
+    lists[best].push_back(it.w);
+  }
+  if (items) {
+    items->clear();
+    off->assign(sms + 1, 0);
+    for (int c = 0; c < sms; ++c) {
+      (*off)[c] = (int)items->size();
+      items->insert(items->end(), lists[c].begin(), lists[c].end());
+    }
+    (*off)[sms] = (int)items->size();
+  }
+  return (int)all.size();
+}
+}  // namespace db
+
+extern "C" int64_t distbo_lauum_i8_sched_words(int n_pad) {
+  if (n_pad <= 0 || n_pad % 128) return 0;
+  return (int64_t)lauum_i8_items(n_pad, nullptr, nullptr) * 4 + device_sm_count() + 1 + 3;
+}
+
+extern "C" int distbo_lauum_i8_plan(int n_pad, int32_t* sched) {
+  if (!sched || n_pad <= 0 || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB) return DISTBO_EARG;
+  std::vector<int4> items;
+  std::vector<int> off;
+  lauum_i8_items(n_pad, &items, &off);
+  // layout: [sms + 1 offsets, padded to a multiple of 4 words][items]
+  const size_t off_words = (off.size() + 3) / 4 * 4;
+  DB_CUDA(cudaMemcpy(sched, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+  DB_CUDA(cudaMemcpy(sched + off_words, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  return DISTBO_OK;
+}
+
+extern "C" int64_t distbo_lauum_i8_workspace(int n_pad) {
+  return (int64_t)n_pad * n_pad + n_pad;   // doubles: 8 digit planes of W^T (8 bytes per element) + column exponents
+}
+
+extern "C" int distbo_lauum_i8_f64(const double* W, int n_pad, const int32_t* sched, double* ws, double* Kinv,
+                                   void* stream) {
+  if (!W || !sched || !ws || !Kinv || n_pad <= 0 || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB) return DISTBO_EARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  static PerDeviceOnce once;
+  if (once.needed()) {
+    DB_CUDA(cudaFuncSetAttribute(score_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    once.mark();
+  }
+  signed char* T8 = reinterpret_cast<signed char*>(ws);
+  double* colscale = ws + (size_t)n_pad * n_pad;
+  DB_CUDA(cudaMemsetAsync(colscale, 0, sizeof(double) * n_pad, st));
+  i8_colmax_kernel<<<dim3(n_pad / 64, (n_pad + 511) / 512), 256, 0, st>>>(W, n_pad,
+                                                                         reinterpret_cast<unsigned long long*>(colscale));
+  DB_CHECK_LAUNCH();
+  i8_colscale_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(colscale, n_pad);
+  DB_CHECK_LAUNCH();
+  const int nb64 = n_pad / 64;
+  i8_wtsplit_kernel<<<nb64 * (nb64 + 1) / 2, 256, 0, st>>>(W, n_pad, colscale, T8);
+  DB_CHECK_LAUNCH();
+  CUtensorMap mapA, mapB;
+  if (!tma::encode_u8_planes(&mapA, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS / 2) ||
+      !tma::encode_u8_planes(&mapB, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS))
+    return DISTBO_ECUDA;
+  const int sms = device_sm_count();
+  I8Args a;
+  a.n_rb = n_pad / I8_RB; a.ntiles = 0; a.slices = 1; a.tiles_in_flight = 1;
+  {
+    const char* dbg = getenv("DISTBO_I8_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
+  a.rowscale = colscale; a.kexp = nullptr; a.V = nullptr; a.partial = nullptr;
+  a.item_off = reinterpret_cast<const int*>(sched);
+  a.items = reinterpret_cast<const int4*>(sched + (sms + 1 + 3) / 4 * 4);
+  a.C = Kinv; a.ldc = n_pad;
+  a.meet = nullptr; a.meet_stride = 0; a.meet_waves = 0;
+  score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mapA, mapB, a);
+  DB_CHECK_LAUNCH();
   return DISTBO_OK;
 }

@@ -227,6 +227,10 @@ class GPEngine:
         # DISTBO_SCORE_I8=0 keeps the FP64 DMMA kernel everywhere (A/B measurements)
         self.score_i8_min_npad = int(os.environ.get("DISTBO_SCORE_I8_MIN", "512"))
         self.use_score_i8 = os.environ.get("DISTBO_SCORE_I8", "1") == "1"
+        # K^-1 = W^T W (LAUUM) on the same tcgen05 digit-plane kernel from n_pad = 2048; DISTBO_LAUUM_I8=0 = DMMA
+        self.use_lauum_i8 = os.environ.get("DISTBO_LAUUM_I8", "1") == "1"
+        self.lauum_i8_min_npad = int(os.environ.get("DISTBO_LAUUM_I8_MIN", "2048"))
+        self._lauum_i8 = None
         self._emb_ws = {}
         self._emb_raw = None
         self.E = None
@@ -267,6 +271,12 @@ class GPEngine:
                 self._plan.destroy()
             self._plan = FitPlan(n_pad)
             self.plan = self._plan.handle
+            self._lauum_i8 = None
+            if self.use_lauum_i8 and n_pad >= self.lauum_i8_min_npad:
+                sched = torch.zeros(int(self.lib.distbo_lauum_i8_sched_words(n_pad)), dtype=torch.int32,
+                                    device=self.dev)
+                _lib.check(self.lib.distbo_lauum_i8_plan(n_pad, _lib.ptr(sched)), "distbo_lauum_i8_plan")
+                self._lauum_i8 = (sched, self._f64(int(self.lib.distbo_lauum_i8_workspace(n_pad))))
         self.N = N
         self.theta = torch.from_numpy(theta).to(self.dev)
         self.y = torch.from_numpy(y).to(self.dev)
@@ -406,7 +416,11 @@ class GPEngine:
                        "distbo_trtri_f64")
             self.W_valid = True
             self.W_version += 1
-        if need_kinv:
+        if need_kinv and self._lauum_i8 is not None:
+            _lib.check(self.lib.distbo_lauum_i8_f64(_lib.ptr(self.W), self.n_pad, _lib.ptr(self._lauum_i8[0]),
+                                                    _lib.ptr(self._lauum_i8[1]), _lib.ptr(self.Tm), st),
+                       "distbo_lauum_i8_f64")
+        elif need_kinv:
             _lib.check(self.lib.distbo_lauum_f64(self.plan, _lib.ptr(self.W), _lib.ptr(self.Tm), st),
                        "distbo_lauum_f64")
 

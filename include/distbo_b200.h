@@ -257,6 +257,17 @@ int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, const double* 
                         double* out_std, double* out_acq, double* block_best_val, int64_t* block_best_idx,
                         double* best_val, int64_t* best_idx, int64_t index_offset, void* stream);
 
+/* ---- LAUUM on the tcgen05 tensor cores: Kinv = W^T W (lower 128-tiles), the same digit-plane contraction with
+ * T = W^T split per column of W; replaces distbo_lauum_f64 from n_pad = 2048 (autodiff through tf.cholesky /
+ * tf.matrix_triangular_solve in the reference, log_gaus_likelihood.py:119-125).
+ * distbo_lauum_i8_plan fills `sched` (distbo_lauum_i8_sched_words(n_pad) int32, device) with the static work
+ * lists of the persistent CTAs - once per n_pad, synchronous, outside any capture.
+ * distbo_lauum_i8_f64: ws = distbo_lauum_i8_workspace(n_pad) doubles; capture-safe. */
+int64_t distbo_lauum_i8_sched_words(int n_pad);
+int distbo_lauum_i8_plan(int n_pad, int32_t* sched);
+int64_t distbo_lauum_i8_workspace(int n_pad);
+int distbo_lauum_i8_f64(const double* W, int n_pad, const int32_t* sched, double* ws, double* Kinv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
