@@ -59,6 +59,13 @@ SIGNATURES = {
     "distbo_score_timing_read": (_i, [C.POINTER(_d), C.POINTER(_i64)]),
     "distbo_score_f64": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _d, _d,
                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "distbo_trtri_levels": (_i, [_vp]),
+    "distbo_trtri_range_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "distbo_trtri_i8_first_level": (_i, [_i, _i]),
+    "distbo_trtri_i8_sched_words": (_i64, [_i, _i]),
+    "distbo_trtri_i8_plan": (_i, [_i, _i, _vp]),
+    "distbo_trtri_i8_workspace": (_i64, [_i]),
+    "distbo_trtri_i8_f64": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "distbo_lauum_i8_sched_words": (_i64, [_i]),
     "distbo_lauum_i8_plan": (_i, [_i, _vp]),
     "distbo_lauum_i8_workspace": (_i64, [_i]),

@@ -23,10 +23,6 @@ namespace db {
 struct Range {
   int off, cnt;
 };
-struct TriNode {
-  int o, n1, n2;
-};
-
 struct Plan {
   int n = 0, nb = 0;
   int4* d_tiles = nullptr;
@@ -561,16 +557,6 @@ static int panel_ctas(int nb, int kb, int sms, int rest_tiles_prev, int depth, i
   return rows;
 }
 
-static int build_tri(int o, int cnt, std::vector<std::vector<TriNode>>& levels) {
-  if (cnt == 1) return 0;
-  int n1 = cnt / 2, n2 = cnt - n1;
-  int l1 = build_tri(o, n1, levels), l2 = build_tri(o + n1, n2, levels);
-  int lvl = std::max(l1, l2) + 1;
-  if ((int)levels.size() <= lvl) levels.resize(lvl + 1);
-  levels[lvl].push_back({o, n1, n2});
-  return lvl;
-}
-
 static bool longer_k(const int4& a, const int4& b) { return (a.w - a.z) > (b.w - b.z); }
 
 }  // namespace db
@@ -1010,14 +996,25 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
   return DISTBO_EARG;  // unreachable: the fused panel path above is the only one
 }
 
-extern "C" int distbo_trtri_f64(void* plan, const double* L, double* W, double* T, void* stream) {
-  if (!plan || !L || !W || !T) return DISTBO_EARG;
+// Levels [level_begin, level_end) of the triangular inverse: level 0 = the 128-row diagonal blocks, level h >= 1 = the
+// merges at height h of the halving tree (two DMMA tile-GEMM launches each).  distbo_trtri_f64 = all of them.
+extern "C" int distbo_trtri_levels(void* plan) {
+  if (!plan) return DISTBO_EARG;
+  return (int)((Plan*)plan)->tri1.size() + 1;
+}
+
+extern "C" int distbo_trtri_range_f64(void* plan, const double* L, double* W, double* T, int level_begin,
+                                      int level_end, void* stream) {
+  if (!plan || !L || !W || !T || level_begin < 0) return DISTBO_EARG;
   Plan* p = (Plan*)plan;
   cudaStream_t st = (cudaStream_t)stream;
   const int n = p->n;
-  diag_inverse_kernel<<<p->nb, POTF2_THREADS, POTF2_SMEM, st>>>(L, W, n);
-  DB_CHECK_LAUNCH();
-  for (size_t l = 0; l < p->tri1.size(); ++l) {
+  if (level_begin == 0 && level_end > 0) {
+    diag_inverse_kernel<<<p->nb, POTF2_THREADS, POTF2_SMEM, st>>>(L, W, n);
+    DB_CHECK_LAUNCH();
+  }
+  for (int h = std::max(level_begin, 1); h < level_end && h <= (int)p->tri1.size(); ++h) {
+    const size_t l = (size_t)h - 1;
     GemmArgs g1{};  // T = L21 * W11
     g1.A = L; g1.B = W; g1.C = T; g1.Cin = T;
     g1.lda = g1.ldb = g1.ldc = g1.ldcin = n;
@@ -1032,6 +1029,11 @@ extern "C" int distbo_trtri_f64(void* plan, const double* L, double* W, double* 
     DB_CUDA((launch_gemm_tiles<KMAJOR, XMAJOR>(g2, p->tri2[l].cnt, st)));
   }
   return DISTBO_OK;
+}
+
+extern "C" int distbo_trtri_f64(void* plan, const double* L, double* W, double* T, void* stream) {
+  if (!plan) return DISTBO_EARG;
+  return distbo_trtri_range_f64(plan, L, W, T, 0, (int)((Plan*)plan)->tri1.size() + 1, stream);
 }
 
 extern "C" int distbo_lauum_f64(void* plan, const double* W, double* Kinv, void* stream) {

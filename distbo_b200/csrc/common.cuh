@@ -25,7 +25,25 @@ extern long long g_db_launches;
     if (e__ != cudaSuccess) return DISTBO_ECUDA;                           \
   } while (0)
 
+#include <algorithm>
+#include <vector>
+
 namespace db {
+
+// Recursive-halving tree of the triangular inverse over nb diagonal blocks of 128 rows: levels[h] = the nodes
+// (first block, blocks in the top part, blocks in the bottom part) merged at height h (chol.cu, score.cu).
+struct TriNode {
+  int o, n1, n2;
+};
+inline int build_tri(int o, int cnt, std::vector<std::vector<TriNode>>& levels) {
+  if (cnt == 1) return 0;
+  int n1 = cnt / 2, n2 = cnt - n1;
+  int l1 = build_tri(o, n1, levels), l2 = build_tri(o + n1, n2, levels);
+  int lvl = std::max(l1, l2) + 1;
+  if ((int)levels.size() <= lvl) levels.resize(lvl + 1);
+  levels[lvl].push_back({o, n1, n2});
+  return lvl;
+}
 
 // cudaFuncSetAttribute opt-ins and SM counts are per DEVICE: one-shot guards keyed by the current device ordinal
 // (a process may drive several GPUs).  Thread safe: racing first calls repeat a harmless attribute write.

@@ -13,6 +13,11 @@
 //   merge_kernel   : deterministic (max value, min index) merge into the running best.
 #include "../../include/distbo_b200.h"
 #include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "gemm_core.cuh"
@@ -277,8 +282,10 @@ struct I8Args {
   double* partial;          // [ntiles][slices][128][2]
   const int4* items;        // MODE 1: (a_row, b_row, first k-chunk, end k-chunk) per work item
   const int* item_off;      // MODE 1: items of CTA b = items[item_off[b] .. item_off[b + 1])
-  double* C;                // MODE 1: output matrix
+  double* C;                // MODE 1: output matrix, C = alpha * A B^T
   int ldc;
+  const double* rowscale_a; // MODE 1: 2^exponent per row of the A operand (rowscale: per row of the B operand)
+  double alpha;
   unsigned* meet;           // [slices][waves][row blocks of the slice] arrival counters, zero on entry (or null)
   int meet_stride, meet_waves;   // counters per wave, waves per launch
   unsigned short off[I8_MAX_SLICES + 1];   // row blocks of slice s: order[off[s] .. off[s+1])
@@ -325,14 +332,25 @@ __global__ void __launch_bounds__(256) i8_kexp_kernel(const double* __restrict__
   }
 }
 
-// digit planes of W (once per fit): W8[s][i][k], rowscale[i] = 2^e_i.  One CTA per row; k > i is zero.
+// digit planes of a lower-triangular matrix split per ROW: W8[s][i][k], rowscale[i] = 2^e_i.  One CTA per row.
+// rr == null: the whole row (k <= i is data, k > i zero) - W = L^-1 once per fit.  Otherwise only the rows with a
+// non-empty column range rr[i] = [k0, k1) are written, over that range (k > i zero): the bottom-right blocks W22
+// of one level of the triangular inverse.
 __global__ void __launch_bounds__(256) i8_wsplit_kernel(const double* __restrict__ W, int n_pad,
-                                                        signed char* __restrict__ W8, double* __restrict__ rowscale) {
+                                                        signed char* __restrict__ W8, double* __restrict__ rowscale,
+                                                        const int2* __restrict__ rr) {
   __shared__ double red[256];
   const int i = blockIdx.x, tid = threadIdx.x;
+  int k0 = 0, k1 = n_pad;
+  if (rr) {
+    const int2 r = rr[i];
+    k0 = r.x;
+    k1 = r.y;
+    if (k1 <= k0) return;
+  }
   const double* row = W + (size_t)i * n_pad;
   double m = 0.0;
-  for (int k = tid; k <= i; k += 256) m = fmax(m, fabs(row[k]));
+  for (int k = k0 + tid; k <= i; k += 256) m = fmax(m, fabs(row[k]));
   red[tid] = m;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
@@ -344,7 +362,7 @@ __global__ void __launch_bounds__(256) i8_wsplit_kernel(const double* __restrict
   if (tid == 0) rowscale[i] = ldexp(1.0, e);
   const double sc = ldexp(1.0, I8_FRAC - e);
   const size_t plane = (size_t)n_pad * n_pad;
-  for (int k4 = tid * 4; k4 < n_pad; k4 += 1024) {
+  for (int k4 = k0 + tid * 4; k4 < k1; k4 += 1024) {
     unsigned pk[I8_NS];
 #pragma unroll
     for (int s = 0; s < I8_NS; ++s) pk[s] = 0u;
@@ -641,7 +659,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
       tma::mbar_wait_bounded(bar_tfull, tphase);
       tphase ^= 1u;
       tc5::fence_after();
-      const double rsa = MODE == 1 ? __ldg(p.rowscale + a_row + c) * kx : kx;
+      const double rsa = MODE == 1 ? __ldg(p.rowscale_a + a_row + c) * (kx * p.alpha) : kx;
       double* crow = MODE == 1 ? p.C + (size_t)(a_row + c) * p.ldc + b_row : nullptr;
 #pragma unroll 1
       for (int j0 = 0; j0 < ((p.debug & 4) ? 0 : I8_RB); j0 += 8) {
@@ -689,15 +707,27 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
 }
 
 // digit planes of T = W^T with one exponent per row of T (= column of W): T8[s][i][k] = digit s of W[k][i] (k >= i)
-// colmax pass: CTA = 64 columns x 512 rows of the lower triangle (4 row lanes per column), merged with an integer
-// atomicMax on the bit pattern (non-negative doubles order like integers); colmax must be zero on entry
+// Row range of column j of the matrix that is split per COLUMN:
+//   cr == null : [j, n_pad)            the lower triangle of W (LAUUM)
+//   mode 0     : [j, cr[j].x)          the top-left blocks W11 of one level of the triangular inverse
+//   mode 1     : [cr[j].x, cr[j].y)    the off-diagonal blocks T = L21 W11 of that level
+// (cr[j] = (0, 0) on the columns that take no part).
+__device__ __forceinline__ int2 i8_col_range(const int2* __restrict__ cr, int mode, int j, int n_pad) {
+  if (!cr) return make_int2(j, n_pad);
+  const int2 r = cr[j];
+  return mode == 0 ? make_int2(j, r.x) : r;
+}
+
+// colmax pass: CTA = 64 columns x 512 rows (4 row lanes per column), merged with an integer atomicMax on the bit
+// pattern (non-negative doubles order like integers); colmax must be zero on entry
 __global__ void __launch_bounds__(256) i8_colmax_kernel(const double* __restrict__ W, int n_pad,
-                                                        unsigned long long* __restrict__ colmax) {
+                                                        unsigned long long* __restrict__ colmax,
+                                                        const int2* __restrict__ cr, int mode) {
   const int i = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int k0 = blockIdx.y * 512, k1 = min(n_pad, k0 + 512);
-  if (k1 <= blockIdx.x * 64) return;                            // chunk entirely above the diagonal
+  const int2 rg = i8_col_range(cr, mode, i, n_pad);
+  const int k0 = max((int)blockIdx.y * 512, rg.x), k1 = min(min(n_pad, (int)blockIdx.y * 512 + 512), rg.y);
   double m = 0.0;
-  for (int k = max(k0, i) + (threadIdx.x >> 6); k < k1; k += 4) m = fmax(m, fabs(W[(size_t)k * n_pad + i]));
+  for (int k = k0 + (threadIdx.x >> 6); k < k1; k += 4) m = fmax(m, fabs(W[(size_t)k * n_pad + i]));
   if (m > 0.0) atomicMax(colmax + i, (unsigned long long)__double_as_longlong(m));
 }
 
@@ -710,21 +740,30 @@ __global__ void __launch_bounds__(256) i8_colscale_kernel(double* __restrict__ c
   colscale[i] = ldexp(1.0, e);
 }
 
-// CTA = 64 x 64 tile (k block, i block) of the lower triangle of W, transposed through shared memory
+// CTA = 64 x 64 tile (k block, i block), transposed through shared memory.  cr == null: the lower-triangular tiles
+// are enumerated in blockIdx.x; otherwise the grid is (k blocks, i blocks) and tiles outside the column ranges exit.
 __global__ void __launch_bounds__(256) i8_wtsplit_kernel(const double* __restrict__ W, int n_pad,
                                                          const double* __restrict__ colscale,
-                                                         signed char* __restrict__ T8) {
+                                                         signed char* __restrict__ T8, const int2* __restrict__ cr,
+                                                         int mode) {
   __shared__ __align__(16) unsigned char sm[I8_NS][64][64];   // [plane][i][k]
-  // lower-triangular tile index -> (kb, ib), ib <= kb
-  int kb = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
-  while ((kb + 1) * (kb + 2) / 2 <= (int)blockIdx.x) ++kb;
-  while (kb * (kb + 1) / 2 > (int)blockIdx.x) --kb;
-  const int ib = blockIdx.x - kb * (kb + 1) / 2;
+  int kb, ib;
+  if (!cr) {
+    kb = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+    while ((kb + 1) * (kb + 2) / 2 <= (int)blockIdx.x) ++kb;
+    while (kb * (kb + 1) / 2 > (int)blockIdx.x) --kb;
+    ib = blockIdx.x - kb * (kb + 1) / 2;
+  } else {
+    kb = blockIdx.x;
+    ib = blockIdx.y;
+    const int2 r0 = i8_col_range(cr, mode, ib * 64, n_pad);   // the 64 columns of a tile share their block
+    if (kb * 64 + 64 <= r0.x || kb * 64 >= r0.y) return;
+  }
   const int tid = threadIdx.x;
   const int il = tid & 63;
   const int i = ib * 64 + il;
+  const int2 rg = i8_col_range(cr, mode, i, n_pad);
   const double sc = ldexp(1.0, I8_FRAC) / colscale[i];          // colscale is a power of two: exact
-  // (colscale was turned into 2^exponent by i8_colscale_kernel)
   for (int kq = tid >> 6; kq < 16; kq += 4) {                   // four consecutive k per thread
     unsigned pk[I8_NS];
 #pragma unroll
@@ -733,7 +772,7 @@ __global__ void __launch_bounds__(256) i8_wtsplit_kernel(const double* __restric
     for (int u = 0; u < 4; ++u) {
       const int k = kb * 64 + kq * 4 + u;
       int dg[I8_NS];
-      digits8(k >= i ? W[(size_t)k * n_pad + i] * sc : 0.0, dg);
+      digits8((k >= rg.x && k < rg.y) ? W[(size_t)k * n_pad + i] * sc : 0.0, dg);
 #pragma unroll
       for (int s = 0; s < I8_NS; ++s) pk[s] |= (unsigned)(dg[s] & 0xff) << (8 * u);
     }
@@ -912,7 +951,7 @@ extern "C" int64_t distbo_score_i8_workspace(int n_pad) {
 
 extern "C" int distbo_score_i8_prepare(const double* W, int n_pad, int8_t* W8, double* rowscale, void* stream) {
   if (!W || !W8 || !rowscale || n_pad <= 0 || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB) return DISTBO_EARG;
-  i8_wsplit_kernel<<<n_pad, 256, 0, (cudaStream_t)stream>>>(W, n_pad, (signed char*)W8, rowscale);
+  i8_wsplit_kernel<<<n_pad, 256, 0, (cudaStream_t)stream>>>(W, n_pad, (signed char*)W8, rowscale, nullptr);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
 }
@@ -955,7 +994,7 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
     ia.debug = dbg ? atoi(dbg) : 0;
   }
   ia.rowscale = rowscale; ia.kexp = kexp; ia.V = V; ia.partial = partial;
-  ia.items = nullptr; ia.item_off = nullptr; ia.C = nullptr; ia.ldc = 0;
+  ia.items = nullptr; ia.item_off = nullptr; ia.C = nullptr; ia.ldc = 0; ia.rowscale_a = nullptr; ia.alpha = 1.0;
   unsigned* meet = reinterpret_cast<unsigned*>(kexp + 2);
   int max_rb = 0;
   for (int sl = 0; sl < ia.slices; ++sl) max_rb = max_rb > ia.off[sl + 1] - ia.off[sl] ? max_rb : ia.off[sl + 1] - ia.off[sl];
@@ -1124,13 +1163,13 @@ extern "C" int distbo_lauum_i8_f64(const double* W, int n_pad, const int32_t* sc
   signed char* T8 = reinterpret_cast<signed char*>(ws);
   double* colscale = ws + (size_t)n_pad * n_pad;
   DB_CUDA(cudaMemsetAsync(colscale, 0, sizeof(double) * n_pad, st));
-  i8_colmax_kernel<<<dim3(n_pad / 64, (n_pad + 511) / 512), 256, 0, st>>>(W, n_pad,
-                                                                         reinterpret_cast<unsigned long long*>(colscale));
+  i8_colmax_kernel<<<dim3(n_pad / 64, (n_pad + 511) / 512), 256, 0, st>>>(
+      W, n_pad, reinterpret_cast<unsigned long long*>(colscale), nullptr, 0);
   DB_CHECK_LAUNCH();
   i8_colscale_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(colscale, n_pad);
   DB_CHECK_LAUNCH();
   const int nb64 = n_pad / 64;
-  i8_wtsplit_kernel<<<nb64 * (nb64 + 1) / 2, 256, 0, st>>>(W, n_pad, colscale, T8);
+  i8_wtsplit_kernel<<<nb64 * (nb64 + 1) / 2, 256, 0, st>>>(W, n_pad, colscale, T8, nullptr, 0);
   DB_CHECK_LAUNCH();
   CUtensorMap mapA, mapB;
   if (!tma::encode_u8_planes(&mapA, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS / 2) ||
@@ -1146,9 +1185,230 @@ extern "C" int distbo_lauum_i8_f64(const double* W, int n_pad, const int32_t* sc
   a.rowscale = colscale; a.kexp = nullptr; a.V = nullptr; a.partial = nullptr;
   a.item_off = reinterpret_cast<const int*>(sched);
   a.items = reinterpret_cast<const int4*>(sched + (sms + 1 + 3) / 4 * 4);
-  a.C = Kinv; a.ldc = n_pad;
+  a.C = Kinv; a.ldc = n_pad; a.rowscale_a = colscale; a.alpha = 1.0;
   a.meet = nullptr; a.meet_stride = 0; a.meet_waves = 0;
   score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mapA, mapB, a);
   DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}
+
+// ---- Top levels of the triangular inverse on the tcgen05 tensor cores ------------------------------------------
+// Level h of the halving tree merges pairs of inverted diagonal blocks:  W21 = -W22 (L21 W11).  Both products run
+// on the digit-plane kernel: T = L21 W11 from the row planes of L and the column planes of W11, then W21 = -W22 T
+// from the row planes of W22 and the column planes of T.  Only the levels whose blocks have at least `min_rows`
+// rows take this route (the GEMMs of the small levels are launch-bound; they stay on the DMMA tile GEMM).
+namespace db {
+
+struct TriI8Level {
+  std::vector<int2> cr, rr;            // per column / per row ranges (see i8_col_range, i8_wsplit_kernel)
+  std::vector<int4> items[2];          // work items of the two products, per CTA
+  std::vector<int> off[2];
+};
+
+static void tri_i8_deal(const std::vector<int4>& all, int sms, std::vector<int4>* items, std::vector<int>* off) {
+  std::vector<int4> sorted(all);
+  std::stable_sort(sorted.begin(), sorted.end(),
+                   [](const int4& a, const int4& b) { return (a.w - a.z) > (b.w - b.z); });
+  std::vector<double> load(sms, 0.0);
+  std::vector<std::vector<int4>> lists(sms);
+  for (const int4& it : sorted) {
+    int best = 0;
+    for (int c = 1; c < sms; ++c)
+      if (load[c] < load[best]) best = c;
+    load[best] += (double)(it.w - it.z) + 2.0;
+    lists[best].push_back(it);
+  }
+  items->clear();
+  off->assign(sms + 1, 0);
+  for (int c = 0; c < sms; ++c) {
+    (*off)[c] = (int)items->size();
+    items->insert(items->end(), lists[c].begin(), lists[c].end());
+  }
+  (*off)[sms] = (int)items->size();
+}
+
+static int tri_i8_levels_build(int n_pad, int min_rows, std::vector<TriI8Level>* out);
+
+// cached per (SM count, n_pad, min_rows): the lists are rebuilt on the host only once (a training loop that is not
+// replayed as a CUDA graph enqueues the inverse every epoch)
+static int tri_i8_levels(int n_pad, int min_rows, std::vector<TriI8Level>* out) {
+  if (!out) return tri_i8_levels_build(n_pad, min_rows, nullptr);
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int>, std::pair<int, std::vector<TriI8Level>>> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_tuple(device_sm_count(), n_pad, min_rows);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    std::vector<TriI8Level> lv;
+    const int first = tri_i8_levels_build(n_pad, min_rows, &lv);
+    it = cache.emplace(key, std::make_pair(first, std::move(lv))).first;
+  }
+  *out = it->second.second;
+  return it->second.first;
+}
+
+// returns the first height that takes the int8 route (levels.size() when none does) and fills `out`
+static int tri_i8_levels_build(int n_pad, int min_rows, std::vector<TriI8Level>* out) {
+  const int nb = n_pad / 128, sms = device_sm_count();
+  std::vector<std::vector<TriNode>> levels;
+  build_tri(0, nb, levels);
+  int first = (int)levels.size();
+  for (int h = 1; h < (int)levels.size(); ++h) {
+    int small = 1 << 30;
+    for (const TriNode& nd : levels[h]) small = std::min(small, std::min(nd.n1, nd.n2) * 128);
+    if (small >= min_rows) {
+      first = h;
+      break;
+    }
+  }
+  if (first < 1) first = 1;
+  if (out) {
+    out->clear();
+    for (int h = first; h < (int)levels.size(); ++h) {
+      TriI8Level lv;
+      lv.cr.assign(n_pad, make_int2(0, 0));
+      lv.rr.assign(n_pad, make_int2(0, 0));
+      std::vector<int4> g1, g2;
+      for (const TriNode& nd : levels[h]) {
+        const int o = nd.o * 128, mid = (nd.o + nd.n1) * 128, end = (nd.o + nd.n1 + nd.n2) * 128;
+        for (int j = o; j < mid; ++j) lv.cr[j] = make_int2(mid, end);
+        for (int i = mid; i < end; ++i) lv.rr[i] = make_int2(mid, end);
+        for (int a = mid; a < end; a += I8_TILE)
+          for (int b = o; b < mid; b += I8_RB) {
+            g1.push_back(make_int4(a, b, b / I8_KC, mid / I8_KC));                 // T = L21 W11 : k in [b, mid)
+            g2.push_back(make_int4(a, b, mid / I8_KC, (a + I8_TILE) / I8_KC));     // W21 = -W22 T: k in [mid, a+128)
+          }
+      }
+      tri_i8_deal(g1, sms, &lv.items[0], &lv.off[0]);
+      tri_i8_deal(g2, sms, &lv.items[1], &lv.off[1]);
+      out->push_back(std::move(lv));
+    }
+  }
+  return first;
+}
+
+static size_t pad4(size_t w) { return (w + 3) / 4 * 4; }
+
+}  // namespace db
+
+extern "C" int distbo_trtri_i8_first_level(int n_pad, int min_rows) {
+  if (n_pad <= 0 || n_pad % 128 || min_rows < 128) return DISTBO_EARG;
+  return tri_i8_levels(n_pad, min_rows, nullptr);
+}
+
+extern "C" int64_t distbo_trtri_i8_sched_words(int n_pad, int min_rows) {
+  if (n_pad <= 0 || n_pad % 128 || min_rows < 128) return 0;
+  std::vector<TriI8Level> lv;
+  tri_i8_levels(n_pad, min_rows, &lv);
+  size_t w = 4;
+  for (const TriI8Level& l : lv)
+    w += 4 * (size_t)n_pad + pad4(l.off[0].size()) + 4 * l.items[0].size() + pad4(l.off[1].size()) + 4 * l.items[1].size();
+  return (int64_t)w;
+}
+
+extern "C" int distbo_trtri_i8_plan(int n_pad, int min_rows, int32_t* sched) {
+  if (!sched || n_pad <= 0 || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB || min_rows < 128) return DISTBO_EARG;
+  std::vector<TriI8Level> lv;
+  tri_i8_levels(n_pad, min_rows, &lv);
+  std::vector<int32_t> host;
+  auto put = [&](const void* src, size_t words, size_t padded) {
+    const size_t at = host.size();
+    host.resize(at + padded, 0);
+    memcpy(host.data() + at, src, words * sizeof(int32_t));
+  };
+  for (const TriI8Level& l : lv) {
+    put(l.cr.data(), 2 * (size_t)n_pad, 2 * (size_t)n_pad);
+    put(l.rr.data(), 2 * (size_t)n_pad, 2 * (size_t)n_pad);
+    for (int g = 0; g < 2; ++g) {
+      put(l.off[g].data(), l.off[g].size(), pad4(l.off[g].size()));
+      put(l.items[g].data(), 4 * l.items[g].size(), 4 * l.items[g].size());
+    }
+  }
+  if (!host.empty()) DB_CUDA(cudaMemcpy(sched, host.data(), host.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return DISTBO_OK;
+}
+
+extern "C" int64_t distbo_trtri_i8_workspace(int n_pad) {
+  // doubles: four sets of digit planes (rows of L, columns of W11, rows of W22, columns of T) + their exponents
+  return 4 * (int64_t)n_pad * n_pad + 4 * (int64_t)n_pad;
+}
+
+extern "C" int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_pad, int min_rows,
+                                   const int32_t* sched, double* ws, void* stream) {
+  if (!L || !W || !T || !sched || !ws || n_pad <= 0 || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB || min_rows < 128)
+    return DISTBO_EARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  static PerDeviceOnce once;
+  if (once.needed()) {
+    DB_CUDA(cudaFuncSetAttribute(score_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    once.mark();
+  }
+  std::vector<TriI8Level> lv;
+  tri_i8_levels(n_pad, min_rows, &lv);
+  if (lv.empty()) return DISTBO_OK;
+  const size_t nn = (size_t)n_pad * n_pad;
+  signed char* L8 = reinterpret_cast<signed char*>(ws);
+  signed char* C8 = reinterpret_cast<signed char*>(ws + nn);        // columns of W11
+  signed char* R8 = reinterpret_cast<signed char*>(ws + 2 * nn);    // rows of W22
+  signed char* T8 = reinterpret_cast<signed char*>(ws + 3 * nn);    // columns of T
+  double* rsL = ws + 4 * nn;
+  double* csW = rsL + n_pad;
+  double* rsW = csW + n_pad;
+  double* csT = rsW + n_pad;
+  CUtensorMap mL, mC, mR, mT;
+  if (!tma::encode_u8_planes(&mL, L8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS / 2) ||
+      !tma::encode_u8_planes(&mC, C8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS) ||
+      !tma::encode_u8_planes(&mR, R8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS / 2) ||
+      !tma::encode_u8_planes(&mT, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS))
+    return DISTBO_ECUDA;
+  const int sms = device_sm_count();
+  const dim3 cgrid(n_pad / 64, (n_pad + 511) / 512), tgrid(n_pad / 64, n_pad / 64);
+  // rows of L, once (k <= i)
+  i8_wsplit_kernel<<<n_pad, 256, 0, st>>>(L, n_pad, L8, rsL, nullptr);
+  DB_CHECK_LAUNCH();
+  const int32_t* cur = sched;
+  for (const TriI8Level& l : lv) {
+    const int2* cr = reinterpret_cast<const int2*>(cur);
+    const int2* rr = reinterpret_cast<const int2*>(cur + 2 * (size_t)n_pad);
+    cur += 4 * (size_t)n_pad;
+    const int* off1 = cur;
+    cur += pad4(l.off[0].size());
+    const int4* it1 = reinterpret_cast<const int4*>(cur);
+    cur += 4 * l.items[0].size();
+    const int* off2 = cur;
+    cur += pad4(l.off[1].size());
+    const int4* it2 = reinterpret_cast<const int4*>(cur);
+    cur += 4 * l.items[1].size();
+
+    I8Args a;
+    a.n_rb = n_pad / I8_RB; a.ntiles = 0; a.slices = 1; a.tiles_in_flight = 1; a.debug = 0;
+    a.kexp = nullptr; a.V = nullptr; a.partial = nullptr;
+    a.meet = nullptr; a.meet_stride = 0; a.meet_waves = 0;
+    a.ldc = n_pad;
+    // columns of W11, then T = L21 W11
+    DB_CUDA(cudaMemsetAsync(csW, 0, sizeof(double) * n_pad, st));
+    i8_colmax_kernel<<<cgrid, 256, 0, st>>>(W, n_pad, reinterpret_cast<unsigned long long*>(csW), cr, 0);
+    DB_CHECK_LAUNCH();
+    i8_colscale_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(csW, n_pad);
+    DB_CHECK_LAUNCH();
+    i8_wtsplit_kernel<<<tgrid, 256, 0, st>>>(W, n_pad, csW, C8, cr, 0);
+    DB_CHECK_LAUNCH();
+    a.item_off = off1; a.items = it1; a.C = T; a.alpha = 1.0; a.rowscale_a = rsL; a.rowscale = csW;
+    score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mL, mC, a);
+    DB_CHECK_LAUNCH();
+    // rows of W22, columns of T, then W21 = -W22 T
+    i8_wsplit_kernel<<<n_pad, 256, 0, st>>>(W, n_pad, R8, rsW, rr);
+    DB_CHECK_LAUNCH();
+    DB_CUDA(cudaMemsetAsync(csT, 0, sizeof(double) * n_pad, st));
+    i8_colmax_kernel<<<cgrid, 256, 0, st>>>(T, n_pad, reinterpret_cast<unsigned long long*>(csT), cr, 1);
+    DB_CHECK_LAUNCH();
+    i8_colscale_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(csT, n_pad);
+    DB_CHECK_LAUNCH();
+    i8_wtsplit_kernel<<<tgrid, 256, 0, st>>>(T, n_pad, csT, T8, cr, 1);
+    DB_CHECK_LAUNCH();
+    a.item_off = off2; a.items = it2; a.C = W; a.alpha = -1.0; a.rowscale_a = rsW; a.rowscale = csT;
+    score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mR, mT, a);
+    DB_CHECK_LAUNCH();
+  }
   return DISTBO_OK;
 }

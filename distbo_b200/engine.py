@@ -231,6 +231,10 @@ class GPEngine:
         self.use_lauum_i8 = os.environ.get("DISTBO_LAUUM_I8", "1") == "1"
         self.lauum_i8_min_npad = int(os.environ.get("DISTBO_LAUUM_I8_MIN", "2048"))
         self._lauum_i8 = None
+        # the top levels of W = L^-1 (blocks of at least DISTBO_TRTRI_I8_MIN rows) on the same kernel
+        self.use_trtri_i8 = os.environ.get("DISTBO_TRTRI_I8", "1") == "1"
+        self.trtri_i8_min_rows = int(os.environ.get("DISTBO_TRTRI_I8_MIN", "1024"))
+        self._trtri_i8 = None
         self._emb_ws = {}
         self._emb_raw = None
         self.E = None
@@ -271,6 +275,15 @@ class GPEngine:
                 self._plan.destroy()
             self._plan = FitPlan(n_pad)
             self.plan = self._plan.handle
+            self._trtri_i8 = None
+            if self.use_trtri_i8 and n_pad >= 2 * self.trtri_i8_min_rows:
+                mr = self.trtri_i8_min_rows
+                first = int(self.lib.distbo_trtri_i8_first_level(n_pad, mr))
+                if 1 <= first < int(self.lib.distbo_trtri_levels(self.plan)):
+                    sched = torch.zeros(int(self.lib.distbo_trtri_i8_sched_words(n_pad, mr)), dtype=torch.int32,
+                                        device=self.dev)
+                    _lib.check(self.lib.distbo_trtri_i8_plan(n_pad, mr, _lib.ptr(sched)), "distbo_trtri_i8_plan")
+                    self._trtri_i8 = (first, sched, self._f64(int(self.lib.distbo_trtri_i8_workspace(n_pad))))
             self._lauum_i8 = None
             if self.use_lauum_i8 and n_pad >= self.lauum_i8_min_npad:
                 sched = torch.zeros(int(self.lib.distbo_lauum_i8_sched_words(n_pad)), dtype=torch.int32,
@@ -411,9 +424,17 @@ class GPEngine:
         st = _stream()
         _lib.check(self.lib.distbo_potrf_f64(self.plan, _lib.ptr(self.K), _lib.ptr(self.W), _lib.ptr(self.info), st),
                    "distbo_potrf_f64")
-        if need_inverse or need_kinv:
+        if (need_inverse or need_kinv) and self._trtri_i8 is not None:
+            first, sched, ws = self._trtri_i8
+            _lib.check(self.lib.distbo_trtri_range_f64(self.plan, _lib.ptr(self.K), _lib.ptr(self.W), _lib.ptr(self.Tm),
+                                                       0, first, st), "distbo_trtri_range_f64")
+            _lib.check(self.lib.distbo_trtri_i8_f64(_lib.ptr(self.K), _lib.ptr(self.W), _lib.ptr(self.Tm), self.n_pad,
+                                                    self.trtri_i8_min_rows, _lib.ptr(sched), _lib.ptr(ws), st),
+                       "distbo_trtri_i8_f64")
+        elif need_inverse or need_kinv:
             _lib.check(self.lib.distbo_trtri_f64(self.plan, _lib.ptr(self.K), _lib.ptr(self.W), _lib.ptr(self.Tm), st),
                        "distbo_trtri_f64")
+        if need_inverse or need_kinv:
             self.W_valid = True
             self.W_version += 1
         if need_kinv and self._lauum_i8 is not None:

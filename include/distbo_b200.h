@@ -268,6 +268,24 @@ int distbo_lauum_i8_plan(int n_pad, int32_t* sched);
 int64_t distbo_lauum_i8_workspace(int n_pad);
 int distbo_lauum_i8_f64(const double* W, int n_pad, const int32_t* sched, double* ws, double* Kinv, void* stream);
 
+/* ---- Triangular inverse W = L^-1 by levels.  distbo_trtri_levels: number of levels of the halving tree over the
+ * 128-row diagonal blocks (level 0 = the diagonal blocks themselves).  distbo_trtri_range_f64 runs levels
+ * [level_begin, level_end) on the FP64 DMMA tile GEMM (distbo_trtri_f64 = all of them).
+ * The levels whose blocks have at least `min_rows` rows can run on the tcgen05 digit-plane kernel instead:
+ * distbo_trtri_i8_first_level = the first such level; distbo_trtri_i8_plan fills `sched`
+ * (distbo_trtri_i8_sched_words int32, device; once per n_pad, synchronous); distbo_trtri_i8_f64 runs those levels
+ * (ws: distbo_trtri_i8_workspace(n_pad) doubles; T: the n_pad x n_pad scratch distbo_trtri_f64 uses; capture-safe).
+ * Replaces tf.matrix_triangular_solve of log_gaus_likelihood.py:183-184,211-214. */
+int distbo_trtri_levels(void* plan);
+int distbo_trtri_range_f64(void* plan, const double* L, double* W, double* T, int level_begin, int level_end,
+                           void* stream);
+int distbo_trtri_i8_first_level(int n_pad, int min_rows);
+int64_t distbo_trtri_i8_sched_words(int n_pad, int min_rows);
+int distbo_trtri_i8_plan(int n_pad, int min_rows, int32_t* sched);
+int64_t distbo_trtri_i8_workspace(int n_pad);
+int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_pad, int min_rows, const int32_t* sched,
+                        double* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
