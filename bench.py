@@ -43,7 +43,7 @@ M_DEFAULT = 1 << 20
 XI, KAPPA = 0.01, 2.58           # experiments/train_test.py:63-64
 FP64_FALLBACK_TFLOPS = 35.5      # cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peak.json)
 SCORE_KERNEL_DRAM_BYTES = 11.87e9  # dram__bytes_read.sum + dram__bytes_write.sum of one score_kernel launch (ncu)
-SCORE_I8_KERNEL_DRAM_BYTES = None   # filled from the ncu --set full capture of score_i8_kernel (profiles/)
+SCORE_I8_KERNEL_DRAM_BYTES = 20.29e9   # dram__bytes_read.sum + dram__bytes_write.sum of one score_i8_kernel launch (ncu, profiles/r02_score_i8_kernel_ncu_full.txt)
 
 
 # ----------------------------------------------------------------------------------- workload

@@ -569,7 +569,7 @@ class gp_regressor(object):
                 self._KE_all = torch.zeros(*shape, dtype=torch.float64, device=e.dev)
             out.append(self._KE_all)
         e.W_valid = True
-        e.W_version += 1                 # the broadcast overwrites W: digit planes of the tcgen05 path are stale
+        e.W_version = getattr(e, "W_version", 0) + 1   # the broadcast overwrites W: the digit planes of the tcgen05 path are stale
         return out
 
     def _compute_posterior_state(self):

@@ -70,6 +70,15 @@ def test_sass_is_sm100a_with_fp64_tensor_ops():
     assert len(bodies) == 8            # column tiles 1..4 x row tiles 1..2
     for b in bodies:
         assert "UBLKCP" in b and "SYNCS" in b and "HMMA.1688.F32.TF32" in b
+    # tcgen05 digit-plane contraction (scoring, LAUUM, top levels of TRTRI): TMA tensor loads (UTMALDG), int8 MMAs
+    # with accumulators in tensor memory (UTCIMMA, the second MMA of a digit re-using the A tile from the
+    # collector), tensor-memory read-back (LDTM), no legacy tensor instruction
+    bodies = [b for b in per_fn if "15score_i8_kernel" in b.split("\n", 1)[0]]
+    assert len(bodies) == 2            # <0> scoring epilogue, <1> store epilogue
+    for b in bodies:
+        assert b.count("UTCIMMA") == 24 and "A_KEEP" in b and "A_REUSE" in b
+        assert b.count("UTMALDG.3D") == 3 and "LDTM" in b and "UTCBAR" in b
+        assert "HMMA" not in b and "DMMA" not in b and "IMMA." not in b
 
 
 def test_no_cpu_fallback():
