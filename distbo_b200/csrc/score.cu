@@ -473,13 +473,17 @@ __global__ void __launch_bounds__(256, 2) i8_kst_kernel(const double* __restrict
 template <int MODE, class F>
 __device__ __forceinline__ void i8_for_items(const I8Args& p, int slice, int tl, F&& f) {
   if (MODE == 0) {
-    const int r_begin = p.off[slice], r_end = p.off[slice + 1];
+    // The row-block lists of the slices are only balanced to ~5 % (whole row blocks, longest first): a CTA takes
+    // slice (slice + wave) mod slices in wave `wave`, so over a launch every CTA walks every list once.
     int wave = 0;
-    for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight, ++wave)
+    for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight, ++wave) {
+      const int sl = (slice + wave) % p.slices;
+      const int r_begin = p.off[sl], r_end = p.off[sl + 1];
       for (int r = r_begin; r < r_end; ++r) {
         const int rb = p.order[r];
-        f(tile * I8_TILE, rb * I8_RB, 0, rb + 1, tile, wave, r - r_begin, r == r_end - 1);
+        f(tile * I8_TILE, rb * I8_RB, 0, rb + 1, tile, wave, (sl << 16) | (r - r_begin), r == r_end - 1);
       }
+    }
   } else {
     const int i0 = p.item_off[blockIdx.x], i1 = p.item_off[blockIdx.x + 1];
     for (int it = i0; it < i1; ++it) {
@@ -537,7 +541,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
       // and the others hit L2 (without it they drift apart and W was read 3.6 times per wave: 35.7 GB of
       // DRAM reads per launch).  Performance only - the wait is short and bounded, never a dependency.
       if (MODE == 0 && p.meet && lane == 0) {
-        unsigned* ctr = p.meet + ((size_t)slice * p.meet_waves + wave) * p.meet_stride + ri;
+        unsigned* ctr = p.meet + ((size_t)(ri >> 16) * p.meet_waves + wave) * p.meet_stride + (ri & 0xffff);
         const int left = p.ntiles - wave * p.tiles_in_flight;
         const unsigned want = left < p.tiles_in_flight ? left : p.tiles_in_flight;
         atomicAdd(ctr, 1u);
@@ -655,7 +659,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
     const double kx = MODE == 0 ? p.kexp[1] : 4.336808689942017736e-19;   // 2^(f - 61) / 2^-61
     unsigned tphase = 0;
     double s2 = 0.0, sv = 0.0;
-    i8_for_items<MODE>(p, slice, tl, [&](int a_row, int b_row, int, int, int tile, int, int, bool last) {
+    i8_for_items<MODE>(p, slice, tl, [&](int a_row, int b_row, int, int, int tile, int, int ri, bool last) {
       tma::mbar_wait_bounded(bar_tfull, tphase);
       tphase ^= 1u;
       tc5::fence_after();
@@ -691,7 +695,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
       __syncwarp();
       if (lane == 0) tma::mbar_arrive(bar_tempty);
       if (MODE == 0 && last) {
-        double* dst = p.partial + (((size_t)tile * p.slices + slice) * I8_TILE + c) * 2;
+        double* dst = p.partial + (((size_t)tile * p.slices + (ri >> 16)) * I8_TILE + c) * 2;
         dst[0] = s2;
         dst[1] = sv;
         s2 = sv = 0.0;
@@ -923,15 +927,42 @@ static void i8_partition(int n_rb, int slices, I8Args& a) {
   a.off[slices] = (unsigned short)o;
 }
 
+// Slices x tiles in flight <= SMs.  Large N: 4 tiles in flight (their K_* planes, 8 MB each at N = 8192, stay in L2)
+// and SMs / 4 slices.  With few row blocks the slice count is chosen for balance instead: every candidate count
+// s <= min(SMs / 4, row blocks) that keeps the planes of the tiles in flight within L2 is scored by (mean load / max load of the longest-first deal) x (SMs used / SMs).
 static void i8_shape(int n_pad, int* slices, int* tiles_in_flight) {
   const int sms = device_sm_count(), n_rb = n_pad / I8_RB;
-  int tf = 4;
-  int sl = sms / tf;
-  if (sl > I8_MAX_SLICES) sl = I8_MAX_SLICES;
-  if (sl > n_rb) sl = n_rb;
-  tf = sms / sl;
-  *slices = sl;
-  *tiles_in_flight = tf;
+  int smax = sms / 4;
+  if (smax > I8_MAX_SLICES) smax = I8_MAX_SLICES;
+  if (smax > n_rb) smax = n_rb;
+  // the K_* planes of the tiles in flight must stay in L2: tiles in flight * 128 * n_pad * 8 bytes <= 40 MB
+  int tf_max = (int)(40.0e6 / (1024.0 * n_pad));
+  if (tf_max < 4) tf_max = 4;
+  int smin = (sms + tf_max - 1) / tf_max;
+  if (smin > smax) smin = smax;
+  if (smin < 1) smin = 1;
+  int best_s = smax;
+  double best_score = -1.0;
+  for (int sl = smax; sl >= smin; --sl) {
+    std::vector<double> load(sl, 0.0);
+    double total = 0.0;
+    for (int rb = n_rb - 1; rb >= 0; --rb) {
+      int b = 0;
+      for (int q = 1; q < sl; ++q)
+        if (load[q] < load[b]) b = q;
+      load[b] += (rb + 1) + 1.5;
+      total += (rb + 1) + 1.5;
+    }
+    double mx = 0.0;
+    for (double v : load) mx = mx > v ? mx : v;
+    const double score = (total / sl / mx) * ((double)(sl * (sms / sl)) / sms);
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best_s = sl;
+    }
+  }
+  *slices = best_s;
+  *tiles_in_flight = sms / best_s;
 }
 
 }  // namespace db
