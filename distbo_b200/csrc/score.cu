@@ -11,17 +11,16 @@
 //                    column sums of A^2 and A*V - A is never written; per-slice partial sums out;
 //   score_finish   : adds a tile's slices in order, acquisition epilogue, per-tile (max value, lowest index);
 //   merge_kernel   : deterministic (max value, min index) merge into the running best.
+// From n_pad = 512 the contraction runs on the tcgen05 tensor cores instead (distbo_score_i8_f64): i8_kst_kernel
+// writes the int8 digit planes of K_*, score_i8_kernel<0> (digit_planes.cuh) contracts them with the planes of W in
+// tensor memory and carries the same two sums; finish and merge are shared.
 #include "../../include/distbo_b200.h"
 #include <stdlib.h>
-#include <string.h>
-#include <algorithm>
-#include <map>
-#include <mutex>
-#include <tuple>
+
 #include <vector>
 
 #include "gemm_core.cuh"
-#include "tma.cuh"
+#include "digit_planes.cuh"
 
 namespace db {
 
@@ -242,75 +241,7 @@ __global__ void merge_best_kernel(const double* __restrict__ bv, const long long
 }
 
 
-// =========================================================================================================
-// tcgen05 path: the same contraction A = K_* W^T on the 5th-generation tensor cores, exact in integers.
-//
-// fp64 has no tcgen05 kind, int8 has (kind::i8, s32 accumulators in tensor memory, 4x the DMMA rate per byte
-// of operand).  Both operands are cut into I8_NS = 8 signed base-128 digits of a 56-bit fixed-point number
-// (Ozaki splitting):   W[i,k]   = 2^(e_i - 55) sum_s d_s[i,k] 2^(49 - 7 s),   e_i = exponent of max_k |W[i,k]|
-//                      K_*[c,k] = 2^(f - 55)   sum_t q_t[c,k] 2^(49 - 7 t),   f   = exponent of scale max|kvec|
-// so that   A[c,i] = 2^(e_i + f - 61) sum_l 2^(49 - 7 l) acc_l[c,i],   acc_l = sum_{s+t=l} sum_k q_t[c,k] d_s[i,k].
-// Every acc_l is an exact int32 dot product (|digit| <= 64: |acc_l| <= 8 * n_pad * 2^12 < 2^31 up to
-// n_pad = 32768); the 36 digit pairs with l = s + t <= 7 are kept (the dropped ones are below 2^-52 of
-// max|W_i| max|K_*| per term, the digit representation itself is exact to 2^-56).  Per (128-candidate tile,
-// 64-row block of W) the eight level accumulators fill the SM's tensor memory (8 x 64 columns x 128 lanes);
-// they are folded into fp64 only once, after the whole k range: two exact int64 Horner sums, two conversions,
-// one fma.  A warp-specialised CTA per SM: one thread issues the TMA loads of the digit planes (64-byte
-// swizzle, 96 KB per stage, two stages), one thread issues the 72 MMAs per stage, four warps read the
-// accumulators back (tcgen05.ld) and carry sum A^2 and sum A V per candidate in registers.
-// =========================================================================================================
-constexpr int I8_NS = 8;          // digits per operand
-constexpr int I8_TILE = 128;      // candidates per tile = MMA M
-constexpr int I8_RB = 64;         // W rows per row block = MMA N
-constexpr int I8_KC = 64;         // k per stage (bytes per smem row; two K = 32 MMA steps)
-constexpr int I8_STAGES = 2;
-constexpr int I8_STAGE_A = I8_NS * I8_TILE * I8_KC;   // 65536
-constexpr int I8_STAGE_B = I8_NS * I8_RB * I8_KC;     // 32768
-constexpr int I8_STAGE = I8_STAGE_A + I8_STAGE_B;
-constexpr int I8_SMEM = I8_STAGES * I8_STAGE + 1024 /* alignment slack */ + 128 /* 12 barriers, tmem slot */;
-constexpr int I8_THREADS = 192;   // warp 0: TMA, warp 1: MMA + tensor-memory owner, warps 2-5: read-back
-constexpr int I8_MAX_RB = 512;    // n_pad <= 32768
-constexpr int I8_MAX_SLICES = 64;
-constexpr int I8_FRAC = 55;       // fractional bits of the fixed-point operands
-
-struct I8Args {
-  int n_rb, ntiles, slices, tiles_in_flight;
-  int debug;                // measurement only: bit 0 = no MMAs, bit 1 = no TMA loads, bit 2 = no read-back
-  const double* rowscale;   // [n_pad] 2^e_i
-  const double* kexp;       // [2]: 2^(55 - f), 2^(f - 61)
-  const double* V;
-  double* partial;          // [ntiles][slices][128][2]
-  const int4* items;        // MODE 1: (a_row, b_row, first k-chunk, end k-chunk) per work item
-  const int* item_off;      // MODE 1: items of CTA b = items[item_off[b] .. item_off[b + 1])
-  double* C;                // MODE 1: output matrix, C = alpha * A B^T
-  int ldc;
-  const double* rowscale_a; // MODE 1: 2^exponent per row of the A operand (rowscale: per row of the B operand)
-  double alpha;
-  unsigned* meet;           // [slices][waves][row blocks of the slice] arrival counters, zero on entry (or null)
-  int meet_stride, meet_waves;   // counters per wave, waves per launch
-  unsigned short off[I8_MAX_SLICES + 1];   // row blocks of slice s: order[off[s] .. off[s+1])
-  unsigned short order[I8_MAX_RB];
-};
-
-// 56-bit fixed point -> 8 balanced base-128 digits, most significant first (d[0] in [-64, 64], others in [-64, 63]).
-// The integer is split once into two balanced 28-bit halves; the digits then come from 32-bit arithmetic.
-__device__ __forceinline__ void digits8(double x_scaled, int (&dg)[I8_NS]) {
-  const long long v = __double2ll_rn(x_scaled);
-  int lo = (int)((unsigned)(v + (1ll << 27)) & 0x0fffffffu) - (1 << 27);   // v = hi 2^28 + lo, lo in [-2^27, 2^27)
-  int hi = (int)((v - lo) >> 28);
-#pragma unroll
-  for (int s = 3; s > 0; --s) {
-    const int dl = ((lo + 64) & 127) - 64;
-    dg[4 + s] = dl;
-    lo = (lo - dl) >> 7;
-    const int dh = ((hi + 64) & 127) - 64;
-    dg[s] = dh;
-    hi = (hi - dh) >> 7;
-  }
-  dg[4] = lo;   // in [-64, 64]
-  dg[0] = hi;
-}
-
+// digit-plane kernels of the scoring path only (the shared machinery is in digit_planes.cuh)
 // 2^(55 - f) and 2^(f - 61) with f = exponent of scale * max_i |kvec_i| (K_* = scale * matern * kvec, matern <= 1)
 __global__ void __launch_bounds__(256) i8_kexp_kernel(const double* __restrict__ kvec, int N,
                                                       const double* __restrict__ log_scale, double* kexp) {
@@ -329,54 +260,6 @@ __global__ void __launch_bounds__(256) i8_kexp_kernel(const double* __restrict__
     if (bound > 0.0 && isfinite(bound)) frexp(bound, &f);
     kexp[0] = ldexp(1.0, I8_FRAC - f);
     kexp[1] = ldexp(1.0, f - 61);
-  }
-}
-
-// digit planes of a lower-triangular matrix split per ROW: W8[s][i][k], rowscale[i] = 2^e_i.  One CTA per row.
-// rr == null: the whole row (k <= i is data, k > i zero) - W = L^-1 once per fit.  Otherwise only the rows with a
-// non-empty column range rr[i] = [k0, k1) are written, over that range (k > i zero): the bottom-right blocks W22
-// of one level of the triangular inverse.
-__global__ void __launch_bounds__(256) i8_wsplit_kernel(const double* __restrict__ W, int n_pad,
-                                                        signed char* __restrict__ W8, double* __restrict__ rowscale,
-                                                        const int2* __restrict__ rr) {
-  __shared__ double red[256];
-  const int i = blockIdx.x, tid = threadIdx.x;
-  int k0 = 0, k1 = n_pad;
-  if (rr) {
-    const int2 r = rr[i];
-    k0 = r.x;
-    k1 = r.y;
-    if (k1 <= k0) return;
-  }
-  const double* row = W + (size_t)i * n_pad;
-  double m = 0.0;
-  for (int k = k0 + tid; k <= i; k += 256) m = fmax(m, fabs(row[k]));
-  red[tid] = m;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (tid < s) red[tid] = fmax(red[tid], red[tid + s]);
-    __syncthreads();
-  }
-  int e = 0;
-  if (red[0] > 0.0 && isfinite(red[0])) frexp(red[0], &e);
-  if (tid == 0) rowscale[i] = ldexp(1.0, e);
-  const double sc = ldexp(1.0, I8_FRAC - e);
-  const size_t plane = (size_t)n_pad * n_pad;
-  for (int k4 = k0 + tid * 4; k4 < k1; k4 += 1024) {
-    unsigned pk[I8_NS];
-#pragma unroll
-    for (int s = 0; s < I8_NS; ++s) pk[s] = 0u;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int k = k4 + u;
-      int dg[I8_NS];
-      digits8(k <= i ? row[k] * sc : 0.0, dg);
-#pragma unroll
-      for (int s = 0; s < I8_NS; ++s) pk[s] |= (unsigned)(dg[s] & 0xff) << (8 * u);
-    }
-#pragma unroll
-    for (int s = 0; s < I8_NS; ++s)
-      *reinterpret_cast<unsigned*>(W8 + s * plane + (size_t)i * n_pad + k4) = pk[s];
   }
 }
 
@@ -462,333 +345,6 @@ __global__ void __launch_bounds__(256, 2) i8_kst_kernel(const double* __restrict
       for (int s = 0; s < I8_NS; ++s)
         *reinterpret_cast<unsigned*>(K8 + s * plane + (size_t)(cl0 + q) * n_pad + i4) = pk[s];
     }
-  }
-}
-
-// Work items of one CTA: (first row of the A tile, first row of the B block, k-chunk range).
-//   MODE 0 (scoring): derived from (slice, tile wave): A = K_* planes of the candidate tile, B = W planes of row
-//                     block rb, k-chunks 0 .. rb (W is lower triangular); the read-back reduces over the rows of W.
-//   MODE 1 (LAUUM)  : explicit list p.items[p.item_off[cta] .. p.item_off[cta + 1]): A and B are both planes of
-//                     T = W^T (row i of T = column i of W), C[i,j] = sum_k T[i,k] T[j,k] is stored as fp64.
-template <int MODE, class F>
-__device__ __forceinline__ void i8_for_items(const I8Args& p, int slice, int tl, F&& f) {
-  if (MODE == 0) {
-    // The row-block lists of the slices are only balanced to ~5 % (whole row blocks, longest first): a CTA takes
-    // slice (slice + wave) mod slices in wave `wave`, so over a launch every CTA walks every list once.
-    int wave = 0;
-    for (int tile = tl; tile < p.ntiles; tile += p.tiles_in_flight, ++wave) {
-      const int sl = (slice + wave) % p.slices;
-      const int r_begin = p.off[sl], r_end = p.off[sl + 1];
-      for (int r = r_begin; r < r_end; ++r) {
-        const int rb = p.order[r];
-        f(tile * I8_TILE, rb * I8_RB, 0, rb + 1, tile, wave, (sl << 16) | (r - r_begin), r == r_end - 1);
-      }
-    }
-  } else {
-    const int i0 = p.item_off[blockIdx.x], i1 = p.item_off[blockIdx.x + 1];
-    for (int it = i0; it < i1; ++it) {
-      const int4 w = __ldg(p.items + it);
-      f(w.x, w.y, w.z, w.w, 0, 0, 0, false);
-    }
-  }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(I8_THREADS, 1)
-    score_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapW,
-                    const __grid_constant__ I8Args p) {
-  extern __shared__ unsigned char smem_raw[];
-  const unsigned raw = tma::smem_u32(smem_raw);
-  const unsigned base = (raw + 1023u) & ~1023u;                 // stage buffers: 1024-byte aligned
-  // A stage is handed over in three loads of 32 KB with a barrier each: the W planes (all needed by digit 0), the
-  // K_* planes 0-3 and the K_* planes 4-7 (waited for when digit 4 comes up, given back after digit 3 / digit 7).
-  // One 96 KB unit per stage could not cover the L2 latency with two stages (measured: 0.3 us stall per stage);
-  // sixteen 4-8 KB loads per stage halved the TMA throughput instead.
-  const unsigned bars = base + I8_STAGES * I8_STAGE;   // per stage: fullW, fullA0, fullA1, emptyA0, emptyRest
-  const unsigned bar_tfull = bars + 40 * I8_STAGES, bar_tempty = bar_tfull + 8;
-  const unsigned slot = bar_tempty + 8;
-  volatile unsigned* slot_ptr = reinterpret_cast<volatile unsigned*>(smem_raw + (slot - raw));
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler too
-  // the CTAs that walk the same row blocks of W (one per tile in flight) are neighbours in the grid
-  const int slice = MODE == 0 ? blockIdx.x / p.tiles_in_flight : 0;
-  const int tl = MODE == 0 ? blockIdx.x % p.tiles_in_flight : 0;
-
-  if (warp == 0 && lane == 0) {
-    tma::prefetch_map(&mapK);
-    tma::prefetch_map(&mapW);
-#pragma unroll
-    for (int s = 0; s < I8_STAGES * 5; ++s) tma::mbar_init(bars + 8 * s, 1);
-    tma::mbar_init(bar_tfull, 1);
-    tma::mbar_init(bar_tempty, 4);
-    tma::fence_barrier_init();
-  }
-  if (warp == 1) tc5::alloc(slot, 512);
-  tc5::fence_before();
-  __syncthreads();
-  tc5::fence_after();
-  const unsigned tmem = *slot_ptr;
-
-  // Warps 0 and 1 run their loops with all 32 lanes and issue under elect.sync: in a `lane == 0` branch the
-  // compiler cannot prove the descriptors uniform and wraps every UTCIMMA / UTMALDG in a vote-and-broadcast
-  // loop (~20 instructions each), which made the single issuing thread the bottleneck of the pipeline.
-  if (warp == 0) {
-    int stage = 0;
-    unsigned phase = 0;
-    i8_for_items<MODE>(p, slice, tl, [&](int a_row, int b_row, int kb, int ke, int tile, int wave, int ri, bool) {
-      // Soft rendezvous of the CTAs that stream the same row block of W for different candidate tiles: they
-      // start it within a few microseconds of each other, so that one of them pulls the digit planes from HBM
-      // and the others hit L2 (without it they drift apart and W was read 3.6 times per wave: 35.7 GB of
-      // DRAM reads per launch).  Performance only - the wait is short and bounded, never a dependency.
-      if (MODE == 0 && p.meet && lane == 0) {
-        unsigned* ctr = p.meet + ((size_t)(ri >> 16) * p.meet_waves + wave) * p.meet_stride + (ri & 0xffff);
-        const int left = p.ntiles - wave * p.tiles_in_flight;
-        const unsigned want = left < p.tiles_in_flight ? left : p.tiles_in_flight;
-        atomicAdd(ctr, 1u);
-        const unsigned long long t0 = globaltimer_ns();
-        while (*(volatile unsigned*)ctr < want && globaltimer_ns() - t0 < 30000ull) __nanosleep(200);
-      }
-      __syncwarp();
-      for (int kc = kb; kc < ke; ++kc) {
-        const unsigned dst = base + stage * I8_STAGE, sb = bars + 40 * stage;
-        tma::mbar_wait_bounded(sb + 24, phase ^ 1u);            // A planes 0-3 of this slot are free
-        if (tma::elect_one()) {
-          if (p.debug & 2) {
-            tma::mbar_arrive(sb + 8);
-          } else {
-            tma::mbar_arrive_expect_tx(sb + 8, I8_STAGE_A / 2);
-            tma::load_3d(dst, &mapK, kc * I8_KC, a_row, 0, sb + 8);
-          }
-        }
-        tma::mbar_wait_bounded(sb + 32, phase ^ 1u);            // ... and the rest of it
-        if (tma::elect_one()) {
-          if (p.debug & 2) {
-            tma::mbar_arrive(sb);
-            tma::mbar_arrive(sb + 16);
-          } else {
-            tma::mbar_arrive_expect_tx(sb, I8_STAGE_B);
-            tma::load_3d(dst + I8_STAGE_A, &mapW, kc * I8_KC, b_row, 0, sb);
-            tma::mbar_arrive_expect_tx(sb + 16, I8_STAGE_A / 2);
-            tma::load_3d(dst + I8_STAGE_A / 2, &mapK, kc * I8_KC, a_row, I8_NS / 2, sb + 16);
-          }
-        }
-        __syncwarp();
-        if (++stage == I8_STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-    });
-  } else if (warp == 1) {
-    int stage = 0;
-    unsigned phase = 0, tphase = 0;
-    i8_for_items<MODE>(p, slice, tl, [&](int, int, int kb, int ke, int, int, int, bool) {
-      tma::mbar_wait_bounded(bar_tempty, tphase ^ 1u);          // the read-back of the previous item is done
-      tc5::fence_after();
-      for (int kc = kb; kc < ke; ++kc) {
-        const unsigned sb = bars + 40 * stage;
-        tma::mbar_wait_bounded(sb, phase);
-        tma::mbar_wait_bounded(sb + 8, phase);
-        tc5::fence_after();
-        const unsigned long long da = tc5::desc_k_sw64(base + stage * I8_STAGE);
-        const unsigned long long dbs = tc5::desc_k_sw64(base + stage * I8_STAGE + I8_STAGE_A);
-        // Digit t of the A operand meets digits s = 0 .. 7 - t of the B operand at once: the B planes are
-        // contiguous in the stage (64 rows x 64 bytes each), so planes s0 .. s0 + n - 1 form ONE K-major B operand
-        // of N = 64 n rows, and because the level accumulators are contiguous in tensor memory too (level l at
-        // columns 64 l), its product lands on levels t + s0 .. t + s0 + n - 1 in one MMA: 12 wide MMAs (N = 256 /
-        // 192 / 128, one of 64) per k-step instead of 36 of N = 64, which were bound by re-reading the A tile from
-        // shared memory (measured 45 % of the int8 rate).  Digits 0-3 need two MMAs: the second one takes the A
-        // tile from the collector.  k-step outermost: consecutive MMAs write different accumulator columns (the
-        // same columns come up again 12 MMAs later); digit-outermost serialised on the accumulate dependency.
-        auto issue = [&](int ks, int t) {
-          const unsigned long long ad = da + (unsigned long long)((t * I8_TILE * I8_KC + ks * 32) >> 4);
-          const int planes = I8_NS - t;                                 // B digits 0 .. planes - 1
-          const int n0 = planes > 4 ? (planes == 5 ? 3 : 4) : planes;   // 8=4+4 7=4+3 6=4+2 5=3+2
-          const unsigned acc = (kc > kb || ks > 0 || t > 0) ? 1u : 0u;  // t = 0 covers all 512 columns
-          if (planes > n0) {
-            tc5::mma_i8<1>(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
-                           tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
-            tc5::mma_i8<2>(tmem + (t + n0) * I8_RB, ad,
-                           dbs + (unsigned long long)((n0 * I8_RB * I8_KC + ks * 32) >> 4),
-                           tc5::idesc_i8(I8_TILE, (planes - n0) * I8_RB), acc);
-          } else {
-            tc5::mma_i8<0>(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
-                           tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
-          }
-        };
-        if (!(p.debug & 1)) {
-          if (tma::elect_one()) {
-#pragma unroll
-            for (int t = 0; t < I8_NS / 2; ++t) issue(0, t);
-          }
-          __syncwarp();
-          tma::mbar_wait_bounded(sb + 16, phase);                       // A planes 4-7
-          tc5::fence_after();
-          if (tma::elect_one()) {
-#pragma unroll
-            for (int t = I8_NS / 2; t < I8_NS; ++t) issue(0, t);
-#pragma unroll
-            for (int t = 0; t < I8_NS / 2; ++t) issue(1, t);
-            tc5::commit(sb + 24);                                       // A planes 0-3 are free
-#pragma unroll
-            for (int t = I8_NS / 2; t < I8_NS; ++t) issue(1, t);
-            tc5::commit(sb + 32);                                       // ... and the rest of the stage
-          }
-          __syncwarp();
-        } else {
-          tma::mbar_wait_bounded(sb + 16, phase);
-          if (tma::elect_one()) {
-            tc5::commit(sb + 24);
-            tc5::commit(sb + 32);
-          }
-          __syncwarp();
-        }
-        if (++stage == I8_STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-      if (tma::elect_one()) tc5::commit(bar_tfull);             // accumulators of this item are complete
-      __syncwarp();
-      tphase ^= 1u;
-    });
-  } else {
-    const int q = warp & 3;                                     // tensor-memory lane quadrant of this warp
-    const int c = q * 32 + lane;                                // row within the A tile
-    const unsigned tq = tmem + ((unsigned)(q * 32) << 16);
-    const double kx = MODE == 0 ? p.kexp[1] : 4.336808689942017736e-19;   // 2^(f - 61) / 2^-61
-    unsigned tphase = 0;
-    double s2 = 0.0, sv = 0.0;
-    i8_for_items<MODE>(p, slice, tl, [&](int a_row, int b_row, int, int, int tile, int, int ri, bool last) {
-      tma::mbar_wait_bounded(bar_tfull, tphase);
-      tphase ^= 1u;
-      tc5::fence_after();
-      const double rsa = MODE == 1 ? __ldg(p.rowscale_a + a_row + c) * (kx * p.alpha) : kx;
-      double* crow = MODE == 1 ? p.C + (size_t)(a_row + c) * p.ldc + b_row : nullptr;
-#pragma unroll 1
-      for (int j0 = 0; j0 < ((p.debug & 4) ? 0 : I8_RB); j0 += 8) {
-        int a[I8_NS][8];
-#pragma unroll
-        for (int l = 0; l < I8_NS; ++l) tc5::ld_32x32b_x8(tq + l * I8_RB + j0, a[l]);
-        tc5::wait_ld();
-        double out[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const long long hi = ((((long long)a[0][j] * 128 + a[1][j]) * 128 + a[2][j]) * 128) + a[3][j];
-          const long long lo = ((((long long)a[4][j] * 128 + a[5][j]) * 128 + a[6][j]) * 128) + a[7][j];
-          const int i = b_row + j0 + j;
-          const double av = (__ldg(p.rowscale + i) * rsa) * fma((double)hi, 268435456.0, (double)lo);
-          if (MODE == 0) {
-            s2 = fma(av, av, s2);
-            sv = fma(av, __ldg(p.V + i), sv);
-          } else {
-            out[j] = av;
-          }
-        }
-        if (MODE == 1) {
-#pragma unroll
-          for (int j = 0; j < 8; j += 2)
-            *reinterpret_cast<double2*>(crow + j0 + j) = make_double2(out[j], out[j + 1]);
-        }
-      }
-      tc5::fence_before();
-      __syncwarp();
-      if (lane == 0) tma::mbar_arrive(bar_tempty);
-      if (MODE == 0 && last) {
-        double* dst = p.partial + (((size_t)tile * p.slices + (ri >> 16)) * I8_TILE + c) * 2;
-        dst[0] = s2;
-        dst[1] = sv;
-        s2 = sv = 0.0;
-      }
-    });
-  }
-  tc5::fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc5::dealloc(tmem, 512);
-  }
-}
-
-// digit planes of T = W^T with one exponent per row of T (= column of W): T8[s][i][k] = digit s of W[k][i] (k >= i)
-// Row range of column j of the matrix that is split per COLUMN:
-//   cr == null : [j, n_pad)            the lower triangle of W (LAUUM)
-//   mode 0     : [j, cr[j].x)          the top-left blocks W11 of one level of the triangular inverse
-//   mode 1     : [cr[j].x, cr[j].y)    the off-diagonal blocks T = L21 W11 of that level
-// (cr[j] = (0, 0) on the columns that take no part).
-__device__ __forceinline__ int2 i8_col_range(const int2* __restrict__ cr, int mode, int j, int n_pad) {
-  if (!cr) return make_int2(j, n_pad);
-  const int2 r = cr[j];
-  return mode == 0 ? make_int2(j, r.x) : r;
-}
-
-// colmax pass: CTA = 64 columns x 512 rows (4 row lanes per column), merged with an integer atomicMax on the bit
-// pattern (non-negative doubles order like integers); colmax must be zero on entry
-__global__ void __launch_bounds__(256) i8_colmax_kernel(const double* __restrict__ W, int n_pad,
-                                                        unsigned long long* __restrict__ colmax,
-                                                        const int2* __restrict__ cr, int mode) {
-  const int i = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int2 rg = i8_col_range(cr, mode, i, n_pad);
-  const int k0 = max((int)blockIdx.y * 512, rg.x), k1 = min(min(n_pad, (int)blockIdx.y * 512 + 512), rg.y);
-  double m = 0.0;
-  for (int k = k0 + (threadIdx.x >> 6); k < k1; k += 4) m = fmax(m, fabs(W[(size_t)k * n_pad + i]));
-  if (m > 0.0) atomicMax(colmax + i, (unsigned long long)__double_as_longlong(m));
-}
-
-__global__ void __launch_bounds__(256) i8_colscale_kernel(double* __restrict__ colscale, int n_pad) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= n_pad) return;
-  const double m = colscale[i];   // the column maximum (bit pattern written by atomicMax)
-  int e = 0;
-  if (m > 0.0 && isfinite(m)) frexp(m, &e);
-  colscale[i] = ldexp(1.0, e);
-}
-
-// CTA = 64 x 64 tile (k block, i block), transposed through shared memory.  cr == null: the lower-triangular tiles
-// are enumerated in blockIdx.x; otherwise the grid is (k blocks, i blocks) and tiles outside the column ranges exit.
-__global__ void __launch_bounds__(256) i8_wtsplit_kernel(const double* __restrict__ W, int n_pad,
-                                                         const double* __restrict__ colscale,
-                                                         signed char* __restrict__ T8, const int2* __restrict__ cr,
-                                                         int mode) {
-  __shared__ __align__(16) unsigned char sm[I8_NS][64][64];   // [plane][i][k]
-  int kb, ib;
-  if (!cr) {
-    kb = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
-    while ((kb + 1) * (kb + 2) / 2 <= (int)blockIdx.x) ++kb;
-    while (kb * (kb + 1) / 2 > (int)blockIdx.x) --kb;
-    ib = blockIdx.x - kb * (kb + 1) / 2;
-  } else {
-    kb = blockIdx.x;
-    ib = blockIdx.y;
-    const int2 r0 = i8_col_range(cr, mode, ib * 64, n_pad);   // the 64 columns of a tile share their block
-    if (kb * 64 + 64 <= r0.x || kb * 64 >= r0.y) return;
-  }
-  const int tid = threadIdx.x;
-  const int il = tid & 63;
-  const int i = ib * 64 + il;
-  const int2 rg = i8_col_range(cr, mode, i, n_pad);
-  const double sc = ldexp(1.0, I8_FRAC) / colscale[i];          // colscale is a power of two: exact
-  for (int kq = tid >> 6; kq < 16; kq += 4) {                   // four consecutive k per thread
-    unsigned pk[I8_NS];
-#pragma unroll
-    for (int s = 0; s < I8_NS; ++s) pk[s] = 0u;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int k = kb * 64 + kq * 4 + u;
-      int dg[I8_NS];
-      digits8((k >= rg.x && k < rg.y) ? W[(size_t)k * n_pad + i] * sc : 0.0, dg);
-#pragma unroll
-      for (int s = 0; s < I8_NS; ++s) pk[s] |= (unsigned)(dg[s] & 0xff) << (8 * u);
-    }
-#pragma unroll
-    for (int s = 0; s < I8_NS; ++s) *reinterpret_cast<unsigned*>(&sm[s][il][kq * 4]) = pk[s];
-  }
-  __syncthreads();
-  const size_t plane = (size_t)n_pad * n_pad;
-  for (int v = tid; v < I8_NS * 64 * 4; v += 256) {             // 16-byte pieces: [plane][i][4 pieces]
-    const int s = v >> 8, r = (v >> 2) & 63, q = v & 3;
-    *reinterpret_cast<uint4*>(T8 + s * plane + (size_t)(ib * 64 + r) * n_pad + kb * 64 + q * 16) =
-        *reinterpret_cast<const uint4*>(&sm[s][r][q * 16]);
   }
 }
 
@@ -1124,322 +680,6 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
     }
     cudaEventDestroy(ev0);
     cudaStreamDestroy(s2);
-  }
-  return DISTBO_OK;
-}
-
-// ---- LAUUM on the tcgen05 tensor cores: Kinv = W^T W = T T^T with T = W^T in int8 digit planes ---------------
-namespace db {
-static int lauum_i8_items(int n_pad, std::vector<int4>* items, std::vector<int>* off) {
-  const int sms = device_sm_count();
-  const int nb = n_pad / I8_TILE, nk = n_pad / I8_KC;
-  struct It { int4 w; double cost; };
-  std::vector<It> all;
-  for (int ib = 0; ib < nb; ++ib)
-    for (int jb = 0; jb <= 2 * ib + 1; ++jb)
-      all.push_back({make_int4(ib * I8_TILE, jb * I8_RB, 2 * ib, nk), (double)(nk - 2 * ib) + 2.0});
-  // longest first onto the least loaded CTA (items are generated with decreasing k range already)
-  std::vector<double> load(sms, 0.0);
-  std::vector<std::vector<int4>> lists(sms);
-  for (const It& it : all) {
-    int best = 0;
-    for (int c = 1; c < sms; ++c)
-      if (load[c] < load[best]) best = c;
-    load[best] += it.cost;
-    lists[best].push_back(it.w);
-  }
-  if (items) {
-    items->clear();
-    off->assign(sms + 1, 0);
-    for (int c = 0; c < sms; ++c) {
-      (*off)[c] = (int)items->size();
-      items->insert(items->end(), lists[c].begin(), lists[c].end());
-    }
-    (*off)[sms] = (int)items->size();
-  }
-  return (int)all.size();
-}
-}  // namespace db
-
-extern "C" int64_t distbo_lauum_i8_sched_words(int n_pad) {
-  if (n_pad <= 0 || n_pad % 128) return 0;
-  return (int64_t)lauum_i8_items(n_pad, nullptr, nullptr) * 4 + device_sm_count() + 1 + 3;
-}
-
-extern "C" int distbo_lauum_i8_plan(int n_pad, int32_t* sched) {
-  if (!sched || n_pad <= 0 || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB) return DISTBO_EARG;
-  std::vector<int4> items;
-  std::vector<int> off;
-  lauum_i8_items(n_pad, &items, &off);
-  // layout: [sms + 1 offsets, padded to a multiple of 4 words][items]
-  const size_t off_words = (off.size() + 3) / 4 * 4;
-  DB_CUDA(cudaMemcpy(sched, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
-  DB_CUDA(cudaMemcpy(sched + off_words, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice));
-  return DISTBO_OK;
-}
-
-extern "C" int64_t distbo_lauum_i8_workspace(int n_pad) {
-  return (int64_t)n_pad * n_pad + n_pad;   // doubles: 8 digit planes of W^T (8 bytes per element) + column exponents
-}
-
-extern "C" int distbo_lauum_i8_f64(const double* W, int n_pad, const int32_t* sched, double* ws, double* Kinv,
-                                   void* stream) {
-  if (!W || !sched || !ws || !Kinv || n_pad <= 0 || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB) return DISTBO_EARG;
-  cudaStream_t st = (cudaStream_t)stream;
-  static PerDeviceOnce once;
-  if (once.needed()) {
-    DB_CUDA(cudaFuncSetAttribute(score_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-    once.mark();
-  }
-  signed char* T8 = reinterpret_cast<signed char*>(ws);
-  double* colscale = ws + (size_t)n_pad * n_pad;
-  DB_CUDA(cudaMemsetAsync(colscale, 0, sizeof(double) * n_pad, st));
-  i8_colmax_kernel<<<dim3(n_pad / 64, (n_pad + 511) / 512), 256, 0, st>>>(
-      W, n_pad, reinterpret_cast<unsigned long long*>(colscale), nullptr, 0);
-  DB_CHECK_LAUNCH();
-  i8_colscale_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(colscale, n_pad);
-  DB_CHECK_LAUNCH();
-  const int nb64 = n_pad / 64;
-  i8_wtsplit_kernel<<<nb64 * (nb64 + 1) / 2, 256, 0, st>>>(W, n_pad, colscale, T8, nullptr, 0);
-  DB_CHECK_LAUNCH();
-  CUtensorMap mapA, mapB;
-  if (!tma::encode_u8_planes(&mapA, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS / 2) ||
-      !tma::encode_u8_planes(&mapB, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS))
-    return DISTBO_ECUDA;
-  const int sms = device_sm_count();
-  I8Args a;
-  a.n_rb = n_pad / I8_RB; a.ntiles = 0; a.slices = 1; a.tiles_in_flight = 1;
-  {
-    const char* dbg = getenv("DISTBO_I8_DEBUG");
-    a.debug = dbg ? atoi(dbg) : 0;
-  }
-  a.rowscale = colscale; a.kexp = nullptr; a.V = nullptr; a.partial = nullptr;
-  a.item_off = reinterpret_cast<const int*>(sched);
-  a.items = reinterpret_cast<const int4*>(sched + (sms + 1 + 3) / 4 * 4);
-  a.C = Kinv; a.ldc = n_pad; a.rowscale_a = colscale; a.alpha = 1.0;
-  a.meet = nullptr; a.meet_stride = 0; a.meet_waves = 0;
-  score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mapA, mapB, a);
-  DB_CHECK_LAUNCH();
-  return DISTBO_OK;
-}
-
-// ---- Top levels of the triangular inverse on the tcgen05 tensor cores ------------------------------------------
-// Level h of the halving tree merges pairs of inverted diagonal blocks:  W21 = -W22 (L21 W11).  Both products run
-// on the digit-plane kernel: T = L21 W11 from the row planes of L and the column planes of W11, then W21 = -W22 T
-// from the row planes of W22 and the column planes of T.  Only the levels whose blocks have at least `min_rows`
-// rows take this route (the GEMMs of the small levels are launch-bound; they stay on the DMMA tile GEMM).
-namespace db {
-
-struct TriI8Level {
-  std::vector<int2> cr, rr;            // per column / per row ranges (see i8_col_range, i8_wsplit_kernel)
-  std::vector<int4> items[2];          // work items of the two products, per CTA
-  std::vector<int> off[2];
-};
-
-static void tri_i8_deal(const std::vector<int4>& all, int sms, std::vector<int4>* items, std::vector<int>* off) {
-  std::vector<int4> sorted(all);
-  std::stable_sort(sorted.begin(), sorted.end(),
-                   [](const int4& a, const int4& b) { return (a.w - a.z) > (b.w - b.z); });
-  std::vector<double> load(sms, 0.0);
-  std::vector<std::vector<int4>> lists(sms);
-  for (const int4& it : sorted) {
-    int best = 0;
-    for (int c = 1; c < sms; ++c)
-      if (load[c] < load[best]) best = c;
-    load[best] += (double)(it.w - it.z) + 2.0;
-    lists[best].push_back(it);
-  }
-  items->clear();
-  off->assign(sms + 1, 0);
-  for (int c = 0; c < sms; ++c) {
-    (*off)[c] = (int)items->size();
-    items->insert(items->end(), lists[c].begin(), lists[c].end());
-  }
-  (*off)[sms] = (int)items->size();
-}
-
-static int tri_i8_levels_build(int n_pad, int min_rows, std::vector<TriI8Level>* out);
-
-// cached per (SM count, n_pad, min_rows): the lists are rebuilt on the host only once (a training loop that is not
-// replayed as a CUDA graph enqueues the inverse every epoch)
-static int tri_i8_levels(int n_pad, int min_rows, std::vector<TriI8Level>* out) {
-  if (!out) return tri_i8_levels_build(n_pad, min_rows, nullptr);
-  static std::mutex mu;
-  static std::map<std::tuple<int, int, int>, std::pair<int, std::vector<TriI8Level>>> cache;
-  std::lock_guard<std::mutex> lock(mu);
-  const auto key = std::make_tuple(device_sm_count(), n_pad, min_rows);
-  auto it = cache.find(key);
-  if (it == cache.end()) {
-    std::vector<TriI8Level> lv;
-    const int first = tri_i8_levels_build(n_pad, min_rows, &lv);
-    it = cache.emplace(key, std::make_pair(first, std::move(lv))).first;
-  }
-  *out = it->second.second;
-  return it->second.first;
-}
-
-// returns the first height that takes the int8 route (levels.size() when none does) and fills `out`
-static int tri_i8_levels_build(int n_pad, int min_rows, std::vector<TriI8Level>* out) {
-  const int nb = n_pad / 128, sms = device_sm_count();
-  std::vector<std::vector<TriNode>> levels;
-  build_tri(0, nb, levels);
-  int first = (int)levels.size();
-  for (int h = 1; h < (int)levels.size(); ++h) {
-    int small = 1 << 30;
-    for (const TriNode& nd : levels[h]) small = std::min(small, std::min(nd.n1, nd.n2) * 128);
-    if (small >= min_rows) {
-      first = h;
-      break;
-    }
-  }
-  if (first < 1) first = 1;
-  if (out) {
-    out->clear();
-    for (int h = first; h < (int)levels.size(); ++h) {
-      TriI8Level lv;
-      lv.cr.assign(n_pad, make_int2(0, 0));
-      lv.rr.assign(n_pad, make_int2(0, 0));
-      std::vector<int4> g1, g2;
-      for (const TriNode& nd : levels[h]) {
-        const int o = nd.o * 128, mid = (nd.o + nd.n1) * 128, end = (nd.o + nd.n1 + nd.n2) * 128;
-        for (int j = o; j < mid; ++j) lv.cr[j] = make_int2(mid, end);
-        for (int i = mid; i < end; ++i) lv.rr[i] = make_int2(mid, end);
-        for (int a = mid; a < end; a += I8_TILE)
-          for (int b = o; b < mid; b += I8_RB) {
-            g1.push_back(make_int4(a, b, b / I8_KC, mid / I8_KC));                 // T = L21 W11 : k in [b, mid)
-            g2.push_back(make_int4(a, b, mid / I8_KC, (a + I8_TILE) / I8_KC));     // W21 = -W22 T: k in [mid, a+128)
-          }
-      }
-      tri_i8_deal(g1, sms, &lv.items[0], &lv.off[0]);
-      tri_i8_deal(g2, sms, &lv.items[1], &lv.off[1]);
-      out->push_back(std::move(lv));
-    }
-  }
-  return first;
-}
-
-static size_t pad4(size_t w) { return (w + 3) / 4 * 4; }
-
-}  // namespace db
-
-extern "C" int distbo_trtri_i8_first_level(int n_pad, int min_rows) {
-  if (n_pad <= 0 || n_pad % 128 || min_rows < 128) return DISTBO_EARG;
-  return tri_i8_levels(n_pad, min_rows, nullptr);
-}
-
-extern "C" int64_t distbo_trtri_i8_sched_words(int n_pad, int min_rows) {
-  if (n_pad <= 0 || n_pad % 128 || min_rows < 128) return 0;
-  std::vector<TriI8Level> lv;
-  tri_i8_levels(n_pad, min_rows, &lv);
-  size_t w = 4;
-  for (const TriI8Level& l : lv)
-    w += 4 * (size_t)n_pad + pad4(l.off[0].size()) + 4 * l.items[0].size() + pad4(l.off[1].size()) + 4 * l.items[1].size();
-  return (int64_t)w;
-}
-
-extern "C" int distbo_trtri_i8_plan(int n_pad, int min_rows, int32_t* sched) {
-  if (!sched || n_pad <= 0 || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB || min_rows < 128) return DISTBO_EARG;
-  std::vector<TriI8Level> lv;
-  tri_i8_levels(n_pad, min_rows, &lv);
-  std::vector<int32_t> host;
-  auto put = [&](const void* src, size_t words, size_t padded) {
-    const size_t at = host.size();
-    host.resize(at + padded, 0);
-    memcpy(host.data() + at, src, words * sizeof(int32_t));
-  };
-  for (const TriI8Level& l : lv) {
-    put(l.cr.data(), 2 * (size_t)n_pad, 2 * (size_t)n_pad);
-    put(l.rr.data(), 2 * (size_t)n_pad, 2 * (size_t)n_pad);
-    for (int g = 0; g < 2; ++g) {
-      put(l.off[g].data(), l.off[g].size(), pad4(l.off[g].size()));
-      put(l.items[g].data(), 4 * l.items[g].size(), 4 * l.items[g].size());
-    }
-  }
-  if (!host.empty()) DB_CUDA(cudaMemcpy(sched, host.data(), host.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  return DISTBO_OK;
-}
-
-extern "C" int64_t distbo_trtri_i8_workspace(int n_pad) {
-  // doubles: four sets of digit planes (rows of L, columns of W11, rows of W22, columns of T) + their exponents
-  return 4 * (int64_t)n_pad * n_pad + 4 * (int64_t)n_pad;
-}
-
-extern "C" int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_pad, int min_rows,
-                                   const int32_t* sched, double* ws, void* stream) {
-  if (!L || !W || !T || !sched || !ws || n_pad <= 0 || n_pad % 128 || n_pad / I8_RB > I8_MAX_RB || min_rows < 128)
-    return DISTBO_EARG;
-  cudaStream_t st = (cudaStream_t)stream;
-  static PerDeviceOnce once;
-  if (once.needed()) {
-    DB_CUDA(cudaFuncSetAttribute(score_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-    once.mark();
-  }
-  std::vector<TriI8Level> lv;
-  tri_i8_levels(n_pad, min_rows, &lv);
-  if (lv.empty()) return DISTBO_OK;
-  const size_t nn = (size_t)n_pad * n_pad;
-  signed char* L8 = reinterpret_cast<signed char*>(ws);
-  signed char* C8 = reinterpret_cast<signed char*>(ws + nn);        // columns of W11
-  signed char* R8 = reinterpret_cast<signed char*>(ws + 2 * nn);    // rows of W22
-  signed char* T8 = reinterpret_cast<signed char*>(ws + 3 * nn);    // columns of T
-  double* rsL = ws + 4 * nn;
-  double* csW = rsL + n_pad;
-  double* rsW = csW + n_pad;
-  double* csT = rsW + n_pad;
-  CUtensorMap mL, mC, mR, mT;
-  if (!tma::encode_u8_planes(&mL, L8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS / 2) ||
-      !tma::encode_u8_planes(&mC, C8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS) ||
-      !tma::encode_u8_planes(&mR, R8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS / 2) ||
-      !tma::encode_u8_planes(&mT, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS))
-    return DISTBO_ECUDA;
-  const int sms = device_sm_count();
-  const dim3 cgrid(n_pad / 64, (n_pad + 511) / 512), tgrid(n_pad / 64, n_pad / 64);
-  // rows of L, once (k <= i)
-  i8_wsplit_kernel<<<n_pad, 256, 0, st>>>(L, n_pad, L8, rsL, nullptr);
-  DB_CHECK_LAUNCH();
-  const int32_t* cur = sched;
-  for (const TriI8Level& l : lv) {
-    const int2* cr = reinterpret_cast<const int2*>(cur);
-    const int2* rr = reinterpret_cast<const int2*>(cur + 2 * (size_t)n_pad);
-    cur += 4 * (size_t)n_pad;
-    const int* off1 = cur;
-    cur += pad4(l.off[0].size());
-    const int4* it1 = reinterpret_cast<const int4*>(cur);
-    cur += 4 * l.items[0].size();
-    const int* off2 = cur;
-    cur += pad4(l.off[1].size());
-    const int4* it2 = reinterpret_cast<const int4*>(cur);
-    cur += 4 * l.items[1].size();
-
-    I8Args a;
-    a.n_rb = n_pad / I8_RB; a.ntiles = 0; a.slices = 1; a.tiles_in_flight = 1; a.debug = 0;
-    a.kexp = nullptr; a.V = nullptr; a.partial = nullptr;
-    a.meet = nullptr; a.meet_stride = 0; a.meet_waves = 0;
-    a.ldc = n_pad;
-    // columns of W11, then T = L21 W11
-    DB_CUDA(cudaMemsetAsync(csW, 0, sizeof(double) * n_pad, st));
-    i8_colmax_kernel<<<cgrid, 256, 0, st>>>(W, n_pad, reinterpret_cast<unsigned long long*>(csW), cr, 0);
-    DB_CHECK_LAUNCH();
-    i8_colscale_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(csW, n_pad);
-    DB_CHECK_LAUNCH();
-    i8_wtsplit_kernel<<<tgrid, 256, 0, st>>>(W, n_pad, csW, C8, cr, 0);
-    DB_CHECK_LAUNCH();
-    a.item_off = off1; a.items = it1; a.C = T; a.alpha = 1.0; a.rowscale_a = rsL; a.rowscale = csW;
-    score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mL, mC, a);
-    DB_CHECK_LAUNCH();
-    // rows of W22, columns of T, then W21 = -W22 T
-    i8_wsplit_kernel<<<n_pad, 256, 0, st>>>(W, n_pad, R8, rsW, rr);
-    DB_CHECK_LAUNCH();
-    DB_CUDA(cudaMemsetAsync(csT, 0, sizeof(double) * n_pad, st));
-    i8_colmax_kernel<<<cgrid, 256, 0, st>>>(T, n_pad, reinterpret_cast<unsigned long long*>(csT), cr, 1);
-    DB_CHECK_LAUNCH();
-    i8_colscale_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(csT, n_pad);
-    DB_CHECK_LAUNCH();
-    i8_wtsplit_kernel<<<tgrid, 256, 0, st>>>(T, n_pad, csT, T8, cr, 1);
-    DB_CHECK_LAUNCH();
-    a.item_off = off2; a.items = it2; a.C = W; a.alpha = -1.0; a.rowscale_a = rsW; a.rowscale = csT;
-    score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mR, mT, a);
-    DB_CHECK_LAUNCH();
   }
   return DISTBO_OK;
 }
