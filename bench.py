@@ -443,9 +443,12 @@ def run_cuda(args):
     on_i8 = bool(eng.use_score_i8 and n_pad >= eng.score_i8_min_npad)
     if on_i8:
         # what the kernel executes: every fp64 multiply-add of A = K_* W^T (lower triangle of W, 64-row blocks)
-        # is 36 exact int8 digit-pair multiply-adds on the tcgen05 tensor cores
+        # is 28 exact int8 digit-pair multiply-adds on the tcgen05 tensor cores (7 base-256 digits per operand,
+        # pairs s + t <= 6; distbo_b200.engine.I8_DIGITS)
+        from distbo_b200.engine import I8_DIGITS
+        pairs = I8_DIGITS * (I8_DIGITS + 1) // 2
         nrb = n_pad // 64
-        macs_per_cand = 36.0 * 64.0 * 64.0 * nrb * (nrb + 1) / 2.0
+        macs_per_cand = float(pairs) * 64.0 * 64.0 * nrb * (nrb + 1) / 2.0
         achieved = 2.0 * macs_per_cand * cands_per_launch / (avg_ms / 1e3) / 1e12
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
             os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -459,8 +462,9 @@ def run_cuda(args):
         roofline = {"kernel": "score_i8_kernel", "bound": "tensor", "achieved": achieved, "peak": i8_peak,
                     "unit": "TOP/s", "frac": achieved / i8_peak, "traffic": SCORE_I8_KERNEL_DRAM_BYTES,
                     "peak_source": i8_src,
-                    "what": "tcgen05.mma kind::i8 (s32 accumulators in tensor memory): 36 digit-pair products of the 8 x 8 "
-                            "int8 digit planes per fp64 multiply-add, lower triangle of W in 64-row blocks",
+                    "what": "tcgen05.mma kind::i8 (s32 accumulators in tensor memory): %d digit-pair products of the %d x %d "
+                            "int8 digit planes per fp64 multiply-add, lower triangle of W in 64-row blocks" % (
+                                pairs, I8_DIGITS, I8_DIGITS),
                     "fp64_equivalent": {"achieved": fp64_equiv, "unit": "TFLOP/s", "dgemm_peak": peak,
                                         "ratio_to_dgemm_peak": fp64_equiv / peak, "dgemm_peak_source": peak_src,
                                         "what": "algorithmic fp64 flops (N^2 + 2N per candidate) per second of this kernel "
@@ -579,8 +583,8 @@ def run_cuda(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": bench_config(M, args.lkh_var, world),
-            "score_path": ("tcgen05 kind::i8 on 8 x 8 int8 digit planes of the fp64 operands (exact s32 accumulation, "
-                           "folded to fp64; results equal the DMMA path to 1e-13)") if on_i8 else "FP64 DMMA",
+            "score_path": ("tcgen05 kind::i8 on 7 x 7 int8 digit planes of the fp64 operands (exact s32 accumulation, "
+                           "folded to fp64; results equal the DMMA path to 1e-12)") if on_i8 else "FP64 DMMA",
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": M / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 16 * world,

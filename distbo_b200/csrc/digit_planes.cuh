@@ -16,38 +16,41 @@ namespace db {
 // tcgen05 path: the same contraction A = K_* W^T on the 5th-generation tensor cores, exact in integers.
 //
 // fp64 has no tcgen05 kind, int8 has (kind::i8, s32 accumulators in tensor memory, 4x the DMMA rate per byte
-// of operand).  Both operands are cut into I8_NS = 8 signed base-128 digits of a 56-bit fixed-point number
-// (Ozaki splitting):   W[i,k]   = 2^(e_i - 55) sum_s d_s[i,k] 2^(49 - 7 s),   e_i = exponent of max_k |W[i,k]|
-//                      K_*[c,k] = 2^(f - 55)   sum_t q_t[c,k] 2^(49 - 7 t),   f   = exponent of scale max|kvec|
-// so that   A[c,i] = 2^(e_i + f - 61) sum_l 2^(49 - 7 l) acc_l[c,i],   acc_l = sum_{s+t=l} sum_k q_t[c,k] d_s[i,k].
-// Every acc_l is an exact int32 dot product (|digit| <= 64: |acc_l| <= 8 * n_pad * 2^12 < 2^31 up to
-// n_pad = 32768); the 36 digit pairs with l = s + t <= 7 are kept (the dropped ones are below 2^-52 of
-// max|W_i| max|K_*| per term, the digit representation itself is exact to 2^-56).  Per (128-candidate tile,
-// 64-row block of W) the eight level accumulators fill the SM's tensor memory (8 x 64 columns x 128 lanes);
+// of operand).  Both operands are cut into I8_NS = 7 signed base-256 digits of a 55-bit fixed-point number
+// (Ozaki splitting):   W[i,k]   = 2^(e_i - 54) sum_s d_s[i,k] 2^(48 - 8 s),   e_i = exponent of max_k |W[i,k]|
+//                      K_*[c,k] = 2^(f - 54)   sum_t q_t[c,k] 2^(48 - 8 t),   f   = exponent of scale max|kvec|
+// so that   A[c,i] = 2^(e_i + f - 60) sum_l 2^(48 - 8 l) acc_l[c,i],   acc_l = sum_{s+t=l} sum_k q_t[c,k] d_s[i,k].
+// Every acc_l is an exact int32 dot product (|digit| <= 128: |acc_l| <= 7 * n_pad * 2^14 < 2^31 up to
+// n_pad = 16384); the 28 digit pairs with l = s + t <= 6 are kept (the dropped ones are below 2^-52 of
+// max|W_i| max|K_*| per term, the digit representation itself is exact to 2^-55).  (Round 2 started with 8 digits
+// of 7 bits = 36 pairs; 7 digits of 8 bits carry the same 55-56 bits in 28 pairs - 22 % fewer MMAs and 12.5 % fewer
+// bytes for the same error.)  Per (128-candidate tile, 64-row block of W) the seven level accumulators take
+// 448 of the SM's 512 tensor-memory columns (7 x 64 columns x 128 lanes);
 // they are folded into fp64 only once, after the whole k range: two exact int64 Horner sums, two conversions,
 // one fma.  A warp-specialised CTA per SM: one thread issues the TMA loads of the digit planes (64-byte
-// swizzle, 96 KB per stage, two stages), one thread issues the 72 MMAs per stage, four warps read the
+// swizzle, 84 KB per stage, two stages), one thread issues the 20 MMAs per stage, four warps read the
 // accumulators back (tcgen05.ld) and carry sum A^2 and sum A V per candidate in registers.
 // =========================================================================================================
-constexpr int I8_NS = 8;          // digits per operand
+constexpr int I8_NS = 7;          // digits per operand (base 256, balanced)
+constexpr int I8_A_LO = 4;        // A planes of the first load / waited for at once; the rest when digit 4 comes up
 constexpr int I8_TILE = 128;      // candidates per tile = MMA M
 constexpr int I8_RB = 64;         // W rows per row block = MMA N
 constexpr int I8_KC = 64;         // k per stage (bytes per smem row; two K = 32 MMA steps)
 constexpr int I8_STAGES = 2;
-constexpr int I8_STAGE_A = I8_NS * I8_TILE * I8_KC;   // 65536
-constexpr int I8_STAGE_B = I8_NS * I8_RB * I8_KC;     // 32768
+constexpr int I8_STAGE_A = I8_NS * I8_TILE * I8_KC;   // 57344
+constexpr int I8_STAGE_B = I8_NS * I8_RB * I8_KC;     // 28672
 constexpr int I8_STAGE = I8_STAGE_A + I8_STAGE_B;
 constexpr int I8_SMEM = I8_STAGES * I8_STAGE + 1024 /* alignment slack */ + 128 /* 12 barriers, tmem slot */;
 constexpr int I8_THREADS = 192;   // warp 0: TMA, warp 1: MMA + tensor-memory owner, warps 2-5: read-back
-constexpr int I8_MAX_RB = 512;    // n_pad <= 32768
+constexpr int I8_MAX_RB = 256;    // n_pad <= 16384: 7 pairs * n_pad * 2^14 must stay below 2^31
 constexpr int I8_MAX_SLICES = 64;
-constexpr int I8_FRAC = 55;       // fractional bits of the fixed-point operands
+constexpr int I8_FRAC = 54;       // fractional bits of the fixed-point operands (|x| < 1 -> |integer| < 2^54)
 
 struct I8Args {
   int n_rb, ntiles, slices, tiles_in_flight;
   int debug;                // measurement only: bit 0 = no MMAs, bit 1 = no TMA loads, bit 2 = no read-back
   const double* rowscale;   // [n_pad] 2^e_i
-  const double* kexp;       // [2]: 2^(55 - f), 2^(f - 61)
+  const double* kexp;       // [2]: 2^(54 - f), 2^(f - 60)
   const double* V;
   double* partial;          // [ntiles][slices][128][2]
   const int4* items;        // MODE 1: (a_row, b_row, first k-chunk, end k-chunk) per work item
@@ -62,22 +65,25 @@ struct I8Args {
   unsigned short order[I8_MAX_RB];
 };
 
-// 56-bit fixed point -> 8 balanced base-128 digits, most significant first (d[0] in [-64, 64], others in [-64, 63]).
-// The integer is split once into two balanced 28-bit halves; the digits then come from 32-bit arithmetic.
+// 55-bit fixed point -> 7 balanced base-256 digits, most significant first: d[1..6] in [-128, 127], d[0] in
+// [-65, 65].  The low three digits come from the low 24 bits (carry into the rest), all in 32-bit arithmetic.
 __device__ __forceinline__ void digits8(double x_scaled, int (&dg)[I8_NS]) {
-  const long long v = __double2ll_rn(x_scaled);
-  int lo = (int)((unsigned)(v + (1ll << 27)) & 0x0fffffffu) - (1 << 27);   // v = hi 2^28 + lo, lo in [-2^27, 2^27)
-  int hi = (int)((v - lo) >> 28);
+  const long long v = __double2ll_rn(x_scaled);          // |v| <= 2^54
+  int lo = (int)((unsigned)v & 0x00ffffffu);             // v = (v >> 24) 2^24 + lo, 0 <= lo < 2^24
+  int hi = (int)(v >> 24);                               // floor; |hi| <= 2^30
+#pragma unroll
+  for (int s = 6; s > 3; --s) {
+    const int d = ((lo + 128) & 255) - 128;
+    dg[s] = d;
+    lo = (lo - d) >> 8;
+  }
+  hi += lo;                                              // carry of the low group: 0 or 1
 #pragma unroll
   for (int s = 3; s > 0; --s) {
-    const int dl = ((lo + 64) & 127) - 64;
-    dg[4 + s] = dl;
-    lo = (lo - dl) >> 7;
-    const int dh = ((hi + 64) & 127) - 64;
-    dg[s] = dh;
-    hi = (hi - dh) >> 7;
+    const int d = ((hi + 128) & 255) - 128;
+    dg[s] = d;
+    hi = (hi - d) >> 8;
   }
-  dg[4] = lo;   // in [-64, 64]
   dg[0] = hi;
 }
 
@@ -159,8 +165,8 @@ __device__ __forceinline__ void i8_for_items(const I8Args& p, int slice, int tl,
 
 template <int MODE>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-    score_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapW,
-                    const __grid_constant__ I8Args p) {
+    score_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapKhi,
+                    const __grid_constant__ CUtensorMap mapW, const __grid_constant__ I8Args p) {
   extern __shared__ unsigned char smem_raw[];
   const unsigned raw = tma::smem_u32(smem_raw);
   const unsigned base = (raw + 1023u) & ~1023u;                 // stage buffers: 1024-byte aligned
@@ -180,6 +186,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
 
   if (warp == 0 && lane == 0) {
     tma::prefetch_map(&mapK);
+    tma::prefetch_map(&mapKhi);
     tma::prefetch_map(&mapW);
 #pragma unroll
     for (int s = 0; s < I8_STAGES * 5; ++s) tma::mbar_init(bars + 8 * s, 1);
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
           if (p.debug & 2) {
             tma::mbar_arrive(sb + 8);
           } else {
-            tma::mbar_arrive_expect_tx(sb + 8, I8_STAGE_A / 2);
+            tma::mbar_arrive_expect_tx(sb + 8, I8_A_LO * I8_TILE * I8_KC);
             tma::load_3d(dst, &mapK, kc * I8_KC, a_row, 0, sb + 8);
           }
         }
@@ -232,8 +239,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
           } else {
             tma::mbar_arrive_expect_tx(sb, I8_STAGE_B);
             tma::load_3d(dst + I8_STAGE_A, &mapW, kc * I8_KC, b_row, 0, sb);
-            tma::mbar_arrive_expect_tx(sb + 16, I8_STAGE_A / 2);
-            tma::load_3d(dst + I8_STAGE_A / 2, &mapK, kc * I8_KC, a_row, I8_NS / 2, sb + 16);
+            tma::mbar_arrive_expect_tx(sb + 16, (I8_NS - I8_A_LO) * I8_TILE * I8_KC);
+            tma::load_3d(dst + I8_A_LO * I8_TILE * I8_KC, &mapKhi, kc * I8_KC, a_row, I8_A_LO, sb + 16);
           }
         }
         __syncwarp();
@@ -259,16 +266,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
         // Digit t of the A operand meets digits s = 0 .. 7 - t of the B operand at once: the B planes are
         // contiguous in the stage (64 rows x 64 bytes each), so planes s0 .. s0 + n - 1 form ONE K-major B operand
         // of N = 64 n rows, and because the level accumulators are contiguous in tensor memory too (level l at
-        // columns 64 l), its product lands on levels t + s0 .. t + s0 + n - 1 in one MMA: 12 wide MMAs (N = 256 /
-        // 192 / 128, one of 64) per k-step instead of 36 of N = 64, which were bound by re-reading the A tile from
-        // shared memory (measured 45 % of the int8 rate).  Digits 0-3 need two MMAs: the second one takes the A
+        // columns 64 l), its product lands on levels t + s0 .. t + s0 + n - 1 in one MMA: 10 wide MMAs (N = 256 /
+        // 192 / 128, one of 64) per k-step instead of 28 of N = 64, which were bound by re-reading the A tile from
+        // shared memory (measured 45 % of the int8 rate).  Digits 0-2 need two MMAs: the second one takes the A
         // tile from the collector.  k-step outermost: consecutive MMAs write different accumulator columns (the
-        // same columns come up again 12 MMAs later); digit-outermost serialised on the accumulate dependency.
+        // same columns come up again 10 MMAs later); digit-outermost serialised on the accumulate dependency.
         auto issue = [&](int ks, int t) {
           const unsigned long long ad = da + (unsigned long long)((t * I8_TILE * I8_KC + ks * 32) >> 4);
           const int planes = I8_NS - t;                                 // B digits 0 .. planes - 1
-          const int n0 = planes > 4 ? (planes == 5 ? 3 : 4) : planes;   // 8=4+4 7=4+3 6=4+2 5=3+2
-          const unsigned acc = (kc > kb || ks > 0 || t > 0) ? 1u : 0u;  // t = 0 covers all 512 columns
+          const int n0 = planes > 4 ? (planes == 5 ? 3 : 4) : planes;   // 7=4+3 6=4+2 5=3+2
+          const unsigned acc = (kc > kb || ks > 0 || t > 0) ? 1u : 0u;  // t = 0 covers all 448 columns
           if (planes > n0) {
             tc5::mma_i8<1>(tmem + t * I8_RB, ad, dbs + (unsigned long long)((ks * 32) >> 4),
                            tc5::idesc_i8(I8_TILE, n0 * I8_RB), acc);
@@ -283,19 +290,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
         if (!(p.debug & 1)) {
           if (tma::elect_one()) {
 #pragma unroll
-            for (int t = 0; t < I8_NS / 2; ++t) issue(0, t);
+            for (int t = 0; t < I8_A_LO; ++t) issue(0, t);
           }
           __syncwarp();
           tma::mbar_wait_bounded(sb + 16, phase);                       // A planes 4-7
           tc5::fence_after();
           if (tma::elect_one()) {
 #pragma unroll
-            for (int t = I8_NS / 2; t < I8_NS; ++t) issue(0, t);
+            for (int t = I8_A_LO; t < I8_NS; ++t) issue(0, t);
 #pragma unroll
-            for (int t = 0; t < I8_NS / 2; ++t) issue(1, t);
+            for (int t = 0; t < I8_A_LO; ++t) issue(1, t);
             tc5::commit(sb + 24);                                       // A planes 0-3 are free
 #pragma unroll
-            for (int t = I8_NS / 2; t < I8_NS; ++t) issue(1, t);
+            for (int t = I8_A_LO; t < I8_NS; ++t) issue(1, t);
             tc5::commit(sb + 32);                                       // ... and the rest of the stage
           }
           __syncwarp();
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
     const int q = warp & 3;                                     // tensor-memory lane quadrant of this warp
     const int c = q * 32 + lane;                                // row within the A tile
     const unsigned tq = tmem + ((unsigned)(q * 32) << 16);
-    const double kx = MODE == 0 ? p.kexp[1] : 4.336808689942017736e-19;   // 2^(f - 61) / 2^-61
+    const double kx = MODE == 0 ? p.kexp[1] : 8.673617379884035472e-19;   // 2^(f - 60) / 2^-60
     unsigned tphase = 0;
     double s2 = 0.0, sv = 0.0;
     i8_for_items<MODE>(p, slice, tl, [&](int a_row, int b_row, int, int, int tile, int, int ri, bool last) {
@@ -338,10 +345,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
         double out[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const long long hi = ((((long long)a[0][j] * 128 + a[1][j]) * 128 + a[2][j]) * 128) + a[3][j];
-          const long long lo = ((((long long)a[4][j] * 128 + a[5][j]) * 128 + a[6][j]) * 128) + a[7][j];
+          // sum_l acc_l 2^(48 - 8 l) = hi 2^32 + lo; |hi| < 2^47 converts exactly, |lo| < 2^55 to 2^-53 of itself
+          const long long hi = (((long long)a[0][j] * 256 + a[1][j]) * 256) + a[2][j];
+          const long long lo = ((((long long)a[3][j] * 256 + a[4][j]) * 256 + a[5][j]) * 256) + a[6][j];
           const int i = b_row + j0 + j;
-          const double av = (__ldg(p.rowscale + i) * rsa) * fma((double)hi, 268435456.0, (double)lo);
+          const double av = (__ldg(p.rowscale + i) * rsa) * fma((double)hi, 4294967296.0, (double)lo);
           if (MODE == 0) {
             s2 = fma(av, av, s2);
             sv = fma(av, __ldg(p.V + i), sv);

@@ -90,8 +90,9 @@ extern "C" int distbo_lauum_i8_f64(const double* W, int n_pad, const int32_t* sc
   const int nb64 = n_pad / 64;
   i8_wtsplit_kernel<<<nb64 * (nb64 + 1) / 2, 256, 0, st>>>(W, n_pad, colscale, T8, nullptr, 0);
   DB_CHECK_LAUNCH();
-  CUtensorMap mapA, mapB;
-  if (!tma::encode_u8_planes(&mapA, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS / 2) ||
+  CUtensorMap mapA, mapAhi, mapB;
+  if (!tma::encode_u8_planes(&mapA, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_A_LO) ||
+      !tma::encode_u8_planes(&mapAhi, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS - I8_A_LO) ||
       !tma::encode_u8_planes(&mapB, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS))
     return DISTBO_ECUDA;
   const int sms = device_sm_count();
@@ -106,7 +107,7 @@ extern "C" int distbo_lauum_i8_f64(const double* W, int n_pad, const int32_t* sc
   a.items = reinterpret_cast<const int4*>(sched + (sms + 1 + 3) / 4 * 4);
   a.C = Kinv; a.ldc = n_pad; a.rowscale_a = colscale; a.alpha = 1.0;
   a.meet = nullptr; a.meet_stride = 0; a.meet_waves = 0;
-  score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mapA, mapB, a);
+  score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mapA, mapAhi, mapB, a);
   DB_CHECK_LAUNCH();
   return DISTBO_OK;
 }
@@ -277,10 +278,12 @@ extern "C" int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_
   double* csW = rsL + n_pad;
   double* rsW = csW + n_pad;
   double* csT = rsW + n_pad;
-  CUtensorMap mL, mC, mR, mT;
-  if (!tma::encode_u8_planes(&mL, L8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS / 2) ||
+  CUtensorMap mL, mLhi, mC, mR, mRhi, mT;
+  if (!tma::encode_u8_planes(&mL, L8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_A_LO) ||
+      !tma::encode_u8_planes(&mLhi, L8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS - I8_A_LO) ||
       !tma::encode_u8_planes(&mC, C8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS) ||
-      !tma::encode_u8_planes(&mR, R8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS / 2) ||
+      !tma::encode_u8_planes(&mR, R8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_A_LO) ||
+      !tma::encode_u8_planes(&mRhi, R8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE, I8_NS - I8_A_LO) ||
       !tma::encode_u8_planes(&mT, T8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS))
     return DISTBO_ECUDA;
   const int sms = device_sm_count();
@@ -316,7 +319,7 @@ extern "C" int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_
     i8_wtsplit_kernel<<<tgrid, 256, 0, st>>>(W, n_pad, csW, C8, cr, 0);
     DB_CHECK_LAUNCH();
     a.item_off = off1; a.items = it1; a.C = T; a.alpha = 1.0; a.rowscale_a = rsL; a.rowscale = csW;
-    score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mL, mC, a);
+    score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mL, mLhi, mC, a);
     DB_CHECK_LAUNCH();
     // rows of W22, columns of T, then W21 = -W22 T
     i8_wsplit_kernel<<<n_pad, 256, 0, st>>>(W, n_pad, R8, rsW, rr);
@@ -329,7 +332,7 @@ extern "C" int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_
     i8_wtsplit_kernel<<<tgrid, 256, 0, st>>>(T, n_pad, csT, T8, cr, 1);
     DB_CHECK_LAUNCH();
     a.item_off = off2; a.items = it2; a.C = W; a.alpha = -1.0; a.rowscale_a = rsW; a.rowscale = csT;
-    score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mR, mT, a);
+    score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mR, mRhi, mT, a);
     DB_CHECK_LAUNCH();
   }
   return DISTBO_OK;

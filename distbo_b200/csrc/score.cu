@@ -242,7 +242,7 @@ __global__ void merge_best_kernel(const double* __restrict__ bv, const long long
 
 
 // digit-plane kernels of the scoring path only (the shared machinery is in digit_planes.cuh)
-// 2^(55 - f) and 2^(f - 61) with f = exponent of scale * max_i |kvec_i| (K_* = scale * matern * kvec, matern <= 1)
+// 2^(54 - f) and 2^(f - 60) with f = exponent of scale * max_i |kvec_i| (K_* = scale * matern * kvec, matern <= 1)
 __global__ void __launch_bounds__(256) i8_kexp_kernel(const double* __restrict__ kvec, int N,
                                                       const double* __restrict__ log_scale, double* kexp) {
   __shared__ double red[256];
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) i8_kexp_kernel(const double* __restrict__
     const double bound = exp(*log_scale) * red[0];
     if (bound > 0.0 && isfinite(bound)) frexp(bound, &f);
     kexp[0] = ldexp(1.0, I8_FRAC - f);
-    kexp[1] = ldexp(1.0, f - 61);
+    kexp[1] = ldexp(1.0, f - 60);
   }
 }
 
@@ -567,9 +567,11 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
   signed char* K8[2] = {reinterpret_cast<signed char*>(ws), reinterpret_cast<signed char*>(ws + (size_t)chunk * n_pad)};
   double* partial = ws + 2 * (size_t)chunk * n_pad;
   double* kexp = partial + (size_t)(chunk / I8_TILE) * I8_MAX_SLICES * I8_TILE * 2;
-  CUtensorMap mapK[2], mapW;
-  if (!tma::encode_u8_planes(&mapK[0], K8[0], (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE, I8_NS / 2) ||
-      !tma::encode_u8_planes(&mapK[1], K8[1], (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE, I8_NS / 2) ||
+  CUtensorMap mapK[2], mapKhi[2], mapW;
+  if (!tma::encode_u8_planes(&mapK[0], K8[0], (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE, I8_A_LO) ||
+      !tma::encode_u8_planes(&mapK[1], K8[1], (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE, I8_A_LO) ||
+      !tma::encode_u8_planes(&mapKhi[0], K8[0], (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE, I8_NS - I8_A_LO) ||
+      !tma::encode_u8_planes(&mapKhi[1], K8[1], (uint64_t)n_pad, (uint64_t)chunk, I8_NS, I8_TILE, I8_NS - I8_A_LO) ||
       !tma::encode_u8_planes(&mapW, W8, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB, I8_NS))
     return DISTBO_ECUDA;
   I8Args ia;
@@ -650,7 +652,7 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     const bool timed = g_timing && timing_pair(&t0, &t1);
     if (timed) cudaEventRecord(t0, st);
-    score_i8_kernel<0><<<ia.slices * tf, I8_THREADS, I8_SMEM, st>>>(mapK[ci & 1], mapW, launch);
+    score_i8_kernel<0><<<ia.slices * tf, I8_THREADS, I8_SMEM, st>>>(mapK[ci & 1], mapKhi[ci & 1], mapW, launch);
     DB_CHECK_LAUNCH();
     if (timed) cudaEventRecord(t1, st);
     if (overlap) DB_CUDA(cudaEventRecord(evS[ci & 1], st));

@@ -29,6 +29,8 @@ CTRL_CUR_MIN, CTRL_COUNTDOWN, CTRL_STOP, CTRL_EPOCHS, CTRL_LAST_LOSS, CTRL_FIRST
 CTRL_THRESHOLD, CTRL_PATIENCE, CTRL_SLOTS = 7, 8, 16
 ACQ = {"ei": 0, "ucb": 1, "lcb": 2}
 D_MAX = 16         # gram.cu DMAX / score.cu SCORE_DMAX
+I8_DIGITS = 7      # digit_planes.cuh I8_NS: int8 planes per fp64 operand of the tcgen05 contractions
+I8_MAX_NPAD = 16384  # ... whose s32 accumulators are exact up to this size (larger problems stay on FP64 DMMA)
 
 
 def round_up(n, m):
@@ -276,7 +278,7 @@ class GPEngine:
             self._plan = FitPlan(n_pad)
             self.plan = self._plan.handle
             self._trtri_i8 = None
-            if self.use_trtri_i8 and n_pad >= 2 * self.trtri_i8_min_rows:
+            if self.use_trtri_i8 and 2 * self.trtri_i8_min_rows <= n_pad <= I8_MAX_NPAD:
                 mr = self.trtri_i8_min_rows
                 first = int(self.lib.distbo_trtri_i8_first_level(n_pad, mr))
                 if 1 <= first < int(self.lib.distbo_trtri_levels(self.plan)):
@@ -285,7 +287,7 @@ class GPEngine:
                     _lib.check(self.lib.distbo_trtri_i8_plan(n_pad, mr, _lib.ptr(sched)), "distbo_trtri_i8_plan")
                     self._trtri_i8 = (first, sched, self._f64(int(self.lib.distbo_trtri_i8_workspace(n_pad))))
             self._lauum_i8 = None
-            if self.use_lauum_i8 and n_pad >= self.lauum_i8_min_npad:
+            if self.use_lauum_i8 and self.lauum_i8_min_npad <= n_pad <= I8_MAX_NPAD:
                 sched = torch.zeros(int(self.lib.distbo_lauum_i8_sched_words(n_pad)), dtype=torch.int32,
                                     device=self.dev)
                 _lib.check(self.lib.distbo_lauum_i8_plan(n_pad, _lib.ptr(sched)), "distbo_lauum_i8_plan")
@@ -530,7 +532,7 @@ class GPEngine:
         if not torch.is_tensor(theta_c):
             theta_c = torch.from_numpy(np.ascontiguousarray(theta_c, dtype=np.float64)).to(self.dev)
         M = int(theta_c.shape[0])
-        if self.use_score_i8 and self.n_pad >= self.score_i8_min_npad:
+        if self.use_score_i8 and self.score_i8_min_npad <= self.n_pad <= I8_MAX_NPAD:
             return self._score_i8(theta_c, M, acq, y_max, xi, kappa, want_arrays, index_offset, kvec, scaler)
         chunk = self.lib.distbo_score_chunk()
         need = int(self.lib.distbo_score_workspace(self.n_pad))
@@ -563,7 +565,7 @@ class GPEngine:
         tensor memory; include/distbo_b200.h).  W's digit planes are refreshed when W changed."""
         n_pad = self.n_pad
         if self._w8 is None or self._w8[0].shape[1] != n_pad:
-            self._w8 = (torch.empty(8, n_pad, n_pad, dtype=torch.int8, device=self.dev), self._f64(n_pad))
+            self._w8 = (torch.empty(I8_DIGITS, n_pad, n_pad, dtype=torch.int8, device=self.dev), self._f64(n_pad))
             self._w8_version = -1
         if self._w8_version != self.W_version:
             _lib.check(self.lib.distbo_score_i8_prepare(_lib.ptr(self.W), n_pad, _lib.ptr(self._w8[0]),

@@ -240,10 +240,10 @@ int distbo_score_f64(const double* W, const double* V, int N, int n_pad, const d
 /* ---- K4 on the 5th-generation tensor cores (tcgen05, int8 digits, exact integer accumulation) ------------
  * Same operator, same results to fp64 rounding level, for the same reference code as distbo_score_f64
  * (log_gaus_likelihood.py:199-217: tf.matrix_triangular_solve + reduce_sum(square)).  fp64 has no tcgen05
- * kind; W = L^-1 and K_* are cut into 8 signed base-128 digits of a 56-bit fixed-point number each and the
- * 36 digit-pair products that matter are exact int32 tcgen05.mma kind::i8 accumulations in tensor memory,
+ * kind; W = L^-1 and K_* are cut into 7 signed base-256 digits of a 55-bit fixed-point number each and the
+ * 28 digit-pair products that matter are exact int32 tcgen05.mma kind::i8 accumulations in tensor memory,
  * folded into fp64 once per (candidate, row of W).
- * distbo_score_i8_prepare: W [n_pad,n_pad] (lower triangle read) -> W8 [8][n_pad][n_pad] int8 digit planes,
+ * distbo_score_i8_prepare: W [n_pad,n_pad] (lower triangle read) -> W8 [7][n_pad][n_pad] int8 digit planes,
  *   rowscale [n_pad] = 2^exponent(max_k |W[i,k]|); once per fit.
  * distbo_score_i8_f64: as distbo_score_f64 with (W8, rowscale) in place of W and `ws` a workspace of
  *   distbo_score_i8_workspace(n_pad) doubles (digit planes of one K_* chunk + per-slice partial sums). */

@@ -76,7 +76,7 @@ def test_sass_is_sm100a_with_fp64_tensor_ops():
     bodies = [b for b in per_fn if "15score_i8_kernel" in b.split("\n", 1)[0]]
     assert len(bodies) == 2            # <0> scoring epilogue, <1> store epilogue
     for b in bodies:
-        assert b.count("UTCIMMA") == 24 and "A_KEEP" in b and "A_REUSE" in b
+        assert b.count("UTCIMMA") == 20 and "A_KEEP" in b and "A_REUSE" in b
         assert b.count("UTMALDG.3D") == 3 and "LDTM" in b and "UTCBAR" in b
         assert "HMMA" not in b and "DMMA" not in b and "IMMA." not in b
 

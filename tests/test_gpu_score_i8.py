@@ -94,8 +94,8 @@ def test_i8_pad_rows_zero_kvec_and_scaler(cuda_engine_mod):
 
 
 def test_i8_digit_planes_reconstruct_w(cuda_engine_mod):
-    """The digit planes are an exact 56-bit fixed-point image of W: sum_s d_s 2^(49-7s) 2^(e_i-55) equals W to
-    2^-56 of the row maximum; digits stay in [-64, 64]."""
+    """The digit planes are an exact 55-bit fixed-point image of W: sum_s d_s 2^(48-8s) 2^(e_i-54) equals W to
+    2^-55 of the row maximum; digits stay in [-128, 127], the leading one in [-65, 65]."""
     eng = cuda_engine_mod
     e, theta, y, kv, rs = fitted_engine(eng, 300, 3, 1e-4, seed=9)
     e.use_score_i8, e.score_i8_min_npad = True, 128
@@ -103,15 +103,16 @@ def test_i8_digit_planes_reconstruct_w(cuda_engine_mod):
     torch.cuda.synchronize()
     W8, rowscale = e._w8
     n = e.n_pad
+    assert W8.shape[0] == 7
     W = np.tril(e.W.cpu().numpy()[:n, :n])
     dg = W8.cpu().numpy().astype(np.int64)
-    assert dg.min() >= -64 and dg.max() <= 64
-    fixed = sum(dg[s] * (1 << (49 - 7 * s)) for s in range(8))
+    assert dg.min() >= -128 and dg.max() <= 127 and np.abs(dg[0]).max() <= 65
+    fixed = sum(dg[s] * (1 << (48 - 8 * s)) for s in range(7))
     rs_ = rowscale.cpu().numpy()
-    back = fixed.astype(np.float64) * (rs_[:, None] * 2.0 ** -55)
+    back = fixed.astype(np.float64) * (rs_[:, None] * 2.0 ** -54)
     rowmax = np.abs(W).max(axis=1)
     assert np.all(rs_ >= rowmax) and np.all(rs_ <= 2.0 * np.maximum(rowmax, 1e-300) + (rowmax == 0))
-    assert np.max(np.abs(back - W) / rs_[:, None]) <= 2.0 ** -56
+    assert np.max(np.abs(back - W) / rs_[:, None]) <= 2.0 ** -55
 
 
 def test_i8_refreshes_after_refit(cuda_engine_mod):
