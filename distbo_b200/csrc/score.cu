@@ -598,7 +598,9 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
   const int64_t nchunks = (M + chunk - 1) / chunk;
   // (measured: 9 % faster at N = 600 .. 1230, 3 % slower at N = 8192 where the step is power-capped and the
   // generator takes clock from the tensor kernel - so only below n_pad = 4096)
-  const bool overlap = nchunks > 1 && n_pad < 4096 && !getenv("DISTBO_I8_NOOVERLAP");
+  int overlap_below = 4096;
+  if (const char* ev = getenv("DISTBO_I8_OVERLAP_BELOW")) overlap_below = atoi(ev);
+  const bool overlap = nchunks > 1 && n_pad < overlap_below && !getenv("DISTBO_I8_NOOVERLAP");
   cudaStream_t s2 = st;
   cudaEvent_t evK[2] = {nullptr, nullptr}, evS[2] = {nullptr, nullptr}, ev0 = nullptr;
   if (overlap) {
