@@ -16,6 +16,7 @@
 #include "../../include/distbo_b200.h"
 #include "gemm_core.cuh"
 #include "potf2.cuh"
+#include "digit_planes.cuh"
 
 namespace db {
 
@@ -51,6 +52,9 @@ struct Plan {
   // (column kb+3 is left to the next step's "next" launch, which catches it up with k = 256).
   struct Step {
     Range next{0, 0}, window{0, 0}, far{0, 0};
+    // the far launch on the tcgen05 digit-plane kernel (far_i8): word offset of its work lists in d_far_sched, and
+    // the column panel of L it multiplies (rows >= far_row0, columns [far_k0, far_k1))
+    int far_i8_off = -1, far_row0 = 0, far_k0 = 0, far_k1 = 0;
     int next_wait_window = -1, next_wait_far = -1;   // earlier launches (step index) on the same tiles
     int window_wait_far = -1;
     double near_work = 0.0, far_work = 0.0;          // tiles x panels
@@ -79,6 +83,17 @@ struct Plan {
   bool relay2_on = true;     // DISTBO_POTRF_RELAY2=0: the relay product stays on one CTA (A/B measurements)
   bool small_ok = false;     // the whole-matrix cooperative kernel can be used (n_pad <= 2048, all CTAs resident)
   int* d_small_flags = nullptr;   // done [nb*nb] | sub [nb*4] | xf [nb*4]
+  // Far updates on the tcgen05 digit-plane kernel (DISTBO_POTRF_FAR_I8, default on with the far schedule): the
+  // rank-512 updates of the columns far behind the window are C -= P P^T with P the last four column panels of L;
+  // P is cut into int8 digit planes (i8_panel_split_kernel) and the product runs on far_ctas persistent CTAs with
+  // a read-modify-write epilogue, at ~2.5x the DMMA rate and on a fixed share of the SMs (the panel and the near
+  // updates keep the others).
+  bool far_i8 = false;
+  int far_ctas = 64;
+  int32_t* d_far_sched = nullptr;     // per far step: [far_ctas + 1 offsets, padded to 4][items]
+  signed char* d_far_planes = nullptr;   // [I8_NS][n][n] (only the panel columns of the current far step are live)
+  double* d_far_rowscale = nullptr;   // [n]
+  CUtensorMap far_map_a, far_map_ahi, far_map_b;
 };
 
 // ------------------------------------------------------------------ fused panel kernel
@@ -588,6 +603,7 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
   p->nb = n_pad / 128;
   const int nb = p->nb;
   std::vector<int4> tiles;
+  std::vector<int32_t> far_sched;   // work lists of the far updates on the digit-plane kernel
   auto T = [](int i) { return i * 128; };
   {
     // number of double-depth steps (env DISTBO_POTRF_DOUBLE).  Measured on B200 at N = 8192 (profiles/
@@ -635,6 +651,11 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
     if (const char* env = getenv("DISTBO_POTRF_FAR")) W = atoi(env);
     if (const char* env = getenv("DISTBO_POTRF_FARG")) G = atoi(env);
     if (W >= 2 && G >= 2 && nb >= 3 * G + W) {
+      {
+        const char* env = getenv("DISTBO_POTRF_FAR_I8");
+        p->far_i8 = !(env && atoi(env) == 0) && n_pad / I8_RB <= I8_MAX_RB;
+        if (const char* c = getenv("DISTBO_POTRF_FAR_I8_CTAS")) p->far_ctas = std::max(8, std::min(148, atoi(c)));
+      }
       std::vector<int> applied(nb, 0), last_next(nb, -1), last_window(nb, -1), last_far(nb, -1);
       p->steps.assign(nb, Plan::Step());
       p->wait_next.assign(nb, -1);
@@ -692,6 +713,43 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
           }
           st.far = Range{(int)tiles.size(), (int)ft.size()};
           tiles.insert(tiles.end(), ft.begin(), ft.end());
+          if (p->far_i8 && !ft.empty()) {
+            // the same tiles as work items of the digit-plane kernel: (128-row tile, 64-row block, k-chunks of 64)
+            std::vector<int4> items;
+            int row0 = 1 << 30, k0 = 1 << 30, k1 = 0;
+            for (const int4& t : ft) {
+              items.push_back(make_int4(t.x, t.y, t.z / I8_KC, t.w / I8_KC));
+              items.push_back(make_int4(t.x, t.y + I8_RB, t.z / I8_KC, t.w / I8_KC));
+              row0 = std::min(row0, t.y);
+              k0 = std::min(k0, t.z);
+              k1 = std::max(k1, t.w);
+            }
+            std::stable_sort(items.begin(), items.end(),
+                             [](const int4& a, const int4& b) { return (a.w - a.z) > (b.w - b.z); });
+            std::vector<double> load(p->far_ctas, 0.0);
+            std::vector<std::vector<int4>> lists(p->far_ctas);
+            for (const int4& it : items) {
+              int best = 0;
+              for (int c = 1; c < p->far_ctas; ++c)
+                if (load[c] < load[best]) best = c;
+              load[best] += (double)(it.w - it.z) + 3.0;
+              lists[best].push_back(it);
+            }
+            st.far_i8_off = (int)far_sched.size();
+            st.far_row0 = row0; st.far_k0 = k0; st.far_k1 = k1;
+            const size_t offw = ((size_t)p->far_ctas + 1 + 3) / 4 * 4;
+            far_sched.resize(far_sched.size() + offw, 0);
+            int run = 0;
+            for (int c = 0; c < p->far_ctas; ++c) {
+              far_sched[st.far_i8_off + c] = run;
+              run += (int)lists[c].size();
+            }
+            far_sched[st.far_i8_off + p->far_ctas] = run;
+            for (int c = 0; c < p->far_ctas; ++c)
+              for (const int4& it : lists[c]) {
+                far_sched.push_back(it.x); far_sched.push_back(it.y); far_sched.push_back(it.z); far_sched.push_back(it.w);
+              }
+          }
         }
       }
     }
@@ -729,6 +787,29 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
     cudaFree(p->d_tiles);
     delete p;
     return DISTBO_ECUDA;
+  }
+  if (p->far_i8 && !far_sched.empty()) {
+    const size_t planes = (size_t)I8_NS * n_pad * n_pad;
+    bool ok = cudaMalloc(&p->d_far_sched, far_sched.size() * sizeof(int32_t)) == cudaSuccess &&
+              cudaMemcpy(p->d_far_sched, far_sched.data(), far_sched.size() * sizeof(int32_t),
+                         cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc(&p->d_far_planes, planes) == cudaSuccess &&
+              cudaMalloc(&p->d_far_rowscale, (size_t)n_pad * sizeof(double)) == cudaSuccess &&
+              cudaMemset(p->d_far_planes, 0, planes) == cudaSuccess &&
+              tma::encode_u8_planes(&p->far_map_a, p->d_far_planes, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_TILE,
+                                    I8_A_LO) &&
+              tma::encode_u8_planes(&p->far_map_ahi, p->d_far_planes, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS,
+                                    I8_TILE, I8_NS - I8_A_LO) &&
+              tma::encode_u8_planes(&p->far_map_b, p->d_far_planes, (uint64_t)n_pad, (uint64_t)n_pad, I8_NS, I8_RB,
+                                    I8_NS) &&
+              cudaFuncSetAttribute(score_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) ==
+                  cudaSuccess;
+    if (!ok) {   // not fatal: the far updates stay on the DMMA tile GEMM
+      cudaGetLastError();
+      p->far_i8 = false;
+    }
+  } else {
+    p->far_i8 = false;
   }
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -837,6 +918,9 @@ extern "C" int distbo_plan_destroy(void* plan) {
   if (p->d_flags) cudaFree(p->d_flags);
   if (p->d_relay) cudaFree(p->d_relay);
   if (p->d_small_flags) cudaFree(p->d_small_flags);
+  if (p->d_far_sched) cudaFree(p->d_far_sched);
+  if (p->d_far_planes) cudaFree(p->d_far_planes);
+  if (p->d_far_rowscale) cudaFree(p->d_far_rowscale);
   delete p;
   return DISTBO_OK;
 }
@@ -919,7 +1003,27 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
         DB_CUDA(cudaEventRecord(p->ev_window[kb], Nw));
       }
       running = st.near_work;
-      if (st.far.cnt > 0) {
+      static const bool skip_far = getenv("DISTBO_POTRF_SKIPFAR") != nullptr;   // timing experiment only (wrong L)
+      if (st.far.cnt > 0 && skip_far) {
+        DB_CUDA(cudaStreamWaitEvent(F, p->ev_panel[kb], 0));
+        DB_CUDA(cudaEventRecord(p->ev_far[kb], F));
+      } else if (st.far.cnt > 0 && p->far_i8 && st.far_i8_off >= 0) {
+        DB_CUDA(cudaStreamWaitEvent(F, p->ev_panel[kb], 0));
+        i8_panel_split_kernel<<<n - st.far_row0, 128, 0, F>>>(A, n, st.far_row0, st.far_k0, st.far_k1, p->d_far_planes,
+                                                            p->d_far_rowscale);
+        DB_CHECK_LAUNCH();
+        I8Args fa;
+        fa.n_rb = n / I8_RB; fa.ntiles = 0; fa.slices = 1; fa.tiles_in_flight = 1; fa.debug = 0;
+        fa.rowscale = p->d_far_rowscale; fa.rowscale_a = p->d_far_rowscale; fa.kexp = nullptr; fa.V = nullptr;
+        fa.partial = nullptr; fa.meet = nullptr; fa.meet_stride = 0; fa.meet_waves = 0;
+        fa.item_off = p->d_far_sched + st.far_i8_off;
+        fa.items = reinterpret_cast<const int4*>(p->d_far_sched + st.far_i8_off + ((size_t)p->far_ctas + 1 + 3) / 4 * 4);
+        fa.C = A; fa.ldc = n; fa.alpha = -1.0; fa.beta = 1;
+        score_i8_kernel<1><<<p->far_ctas, I8_THREADS, I8_SMEM, F>>>(p->far_map_a, p->far_map_ahi, p->far_map_b, fa);
+        DB_CHECK_LAUNCH();
+        DB_CUDA(cudaEventRecord(p->ev_far[kb], F));
+        far_share = st.far_work / 4.0;
+      } else if (st.far.cnt > 0) {
         DB_CUDA(cudaStreamWaitEvent(F, p->ev_panel[kb], 0));
         upd.tiles = p->d_tiles + st.far.off;
         upd.tl_id = 2 * nb + kb;          // far launches have their own timeline rows (buffer: 3 nb rows)

@@ -59,6 +59,7 @@ struct I8Args {
   int ldc;
   const double* rowscale_a; // MODE 1: 2^exponent per row of the A operand (rowscale: per row of the B operand)
   double alpha;
+  int beta;                 // MODE 1: 0 = C is overwritten, 1 = C += alpha * A B^T (read-modify-write of the tile)
   unsigned* meet;           // [slices][waves][row blocks of the slice] arrival counters, zero on entry (or null)
   int meet_stride, meet_waves;   // counters per wave, waves per launch
   unsigned short off[I8_MAX_SLICES + 1];   // row blocks of slice s: order[off[s] .. off[s+1])
@@ -358,6 +359,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
           }
         }
         if (MODE == 1) {
+          if (p.beta) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const double2 c = *reinterpret_cast<const double2*>(crow + j0 + j);
+              out[j] += c.x;
+              out[j + 1] += c.y;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 8; j += 2)
             *reinterpret_cast<double2*>(crow + j0 + j) = make_double2(out[j], out[j + 1]);
@@ -383,6 +392,44 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
 }
 
 // digit planes of T = W^T with one exponent per row of T (= column of W): T8[s][i][k] = digit s of W[k][i] (k >= i)
+// digit planes of a column panel of L: rows [row0, n_pad), columns [k0, k1) (all below the diagonal), one exponent
+// per row over that column range; one CTA per row.  Feeds the rank-(k1 - k0) trailing updates of the Cholesky.
+static __global__ void __launch_bounds__(128) i8_panel_split_kernel(const double* __restrict__ L, int n_pad, int row0,
+                                                                    int k0, int k1, signed char* __restrict__ P8,
+                                                                    double* __restrict__ rowscale) {
+  __shared__ double red[128];
+  const int i = row0 + blockIdx.x, tid = threadIdx.x;
+  const double* row = L + (size_t)i * n_pad;
+  double m = 0.0;
+  for (int k = k0 + tid; k < k1; k += 128) m = fmax(m, fabs(row[k]));
+  red[tid] = m;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (tid < s) red[tid] = fmax(red[tid], red[tid + s]);
+    __syncthreads();
+  }
+  int e = 0;
+  if (red[0] > 0.0 && isfinite(red[0])) frexp(red[0], &e);
+  if (tid == 0) rowscale[i] = ldexp(1.0, e);
+  const double sc = ldexp(1.0, I8_FRAC - e);
+  const size_t plane = (size_t)n_pad * n_pad;
+  for (int k4 = k0 + tid * 4; k4 < k1; k4 += 512) {
+    unsigned pk[I8_NS];
+#pragma unroll
+    for (int s = 0; s < I8_NS; ++s) pk[s] = 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int dg[I8_NS];
+      digits8(row[k4 + u] * sc, dg);
+#pragma unroll
+      for (int s = 0; s < I8_NS; ++s) pk[s] |= (unsigned)(dg[s] & 0xff) << (8 * u);
+    }
+#pragma unroll
+    for (int s = 0; s < I8_NS; ++s)
+      *reinterpret_cast<unsigned*>(P8 + s * plane + (size_t)i * n_pad + k4) = pk[s];
+  }
+}
+
 // Row range of column j of the matrix that is split per COLUMN:
 //   cr == null : [j, n_pad)            the lower triangle of W (LAUUM)
 //   mode 0     : [j, cr[j].x)          the top-left blocks W11 of one level of the triangular inverse

@@ -105,7 +105,7 @@ extern "C" int distbo_lauum_i8_f64(const double* W, int n_pad, const int32_t* sc
   a.rowscale = colscale; a.kexp = nullptr; a.V = nullptr; a.partial = nullptr;
   a.item_off = reinterpret_cast<const int*>(sched);
   a.items = reinterpret_cast<const int4*>(sched + (sms + 1 + 3) / 4 * 4);
-  a.C = Kinv; a.ldc = n_pad; a.rowscale_a = colscale; a.alpha = 1.0;
+  a.C = Kinv; a.ldc = n_pad; a.rowscale_a = colscale; a.alpha = 1.0; a.beta = 0;
   a.meet = nullptr; a.meet_stride = 0; a.meet_waves = 0;
   score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mapA, mapAhi, mapB, a);
   DB_CHECK_LAUNCH();
@@ -309,7 +309,7 @@ extern "C" int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_
     a.n_rb = n_pad / I8_RB; a.ntiles = 0; a.slices = 1; a.tiles_in_flight = 1; a.debug = 0;
     a.kexp = nullptr; a.V = nullptr; a.partial = nullptr;
     a.meet = nullptr; a.meet_stride = 0; a.meet_waves = 0;
-    a.ldc = n_pad;
+    a.ldc = n_pad; a.beta = 0;
     // columns of W11, then T = L21 W11
     DB_CUDA(cudaMemsetAsync(csW, 0, sizeof(double) * n_pad, st));
     i8_colmax_kernel<<<cgrid, 256, 0, st>>>(W, n_pad, reinterpret_cast<unsigned long long*>(csW), cr, 0);

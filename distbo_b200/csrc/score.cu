@@ -583,7 +583,7 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
     ia.debug = dbg ? atoi(dbg) : 0;
   }
   ia.rowscale = rowscale; ia.kexp = kexp; ia.V = V; ia.partial = partial;
-  ia.items = nullptr; ia.item_off = nullptr; ia.C = nullptr; ia.ldc = 0; ia.rowscale_a = nullptr; ia.alpha = 1.0;
+  ia.items = nullptr; ia.item_off = nullptr; ia.C = nullptr; ia.ldc = 0; ia.rowscale_a = nullptr; ia.alpha = 1.0; ia.beta = 0;
   unsigned* meet = reinterpret_cast<unsigned*>(kexp + 2);
   int max_rb = 0;
   for (int sl = 0; sl < ia.slices; ++sl) max_rb = max_rb > ia.off[sl + 1] - ia.off[sl] ? max_rb : ia.off[sl + 1] - ia.off[sl];
