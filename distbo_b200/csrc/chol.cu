@@ -1022,7 +1022,8 @@ extern "C" int distbo_potrf_f64(void* plan, double* A, double* W, int32_t* info,
         score_i8_kernel<1><<<p->far_ctas, I8_THREADS, I8_SMEM, F>>>(p->far_map_a, p->far_map_ahi, p->far_map_b, fa);
         DB_CHECK_LAUNCH();
         DB_CUDA(cudaEventRecord(p->ev_far[kb], F));
-        far_share = st.far_work / 4.0;
+        static const double far_div = getenv("DISTBO_POTRF_FAR_I8_DIV") ? atof(getenv("DISTBO_POTRF_FAR_I8_DIV")) : 8.0;
+        far_share = st.far_work / far_div;
       } else if (st.far.cnt > 0) {
         DB_CUDA(cudaStreamWaitEvent(F, p->ev_panel[kb], 0));
         upd.tiles = p->d_tiles + st.far.off;
