@@ -647,7 +647,11 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
     // with W = 6, G = 4 (W = 4..8 within 1 %, W = 12 or G = 2 slower); N <= 4096 is faster with the uniform
     // schedule, whose panel chain is the bound there.  Default: on from 56 column blocks (N >= 7168);
     // DISTBO_POTRF_FAR=0 switches it off.
-    int W = nb >= 56 ? 6 : 0, G = 4;
+    // With the far updates on the tcgen05 digit-plane kernel (below) the schedule already pays from 40 column blocks
+    // (N = 5120: 2.86 -> 2.70 ms, 6144: 4.24 -> 3.71 ms; at 4096 the uniform schedule stays faster: 1.91 vs 2.18 ms).
+    const bool far_i8_wanted = !(getenv("DISTBO_POTRF_FAR_I8") && atoi(getenv("DISTBO_POTRF_FAR_I8")) == 0) &&
+                               n_pad / I8_RB <= I8_MAX_RB;
+    int W = nb >= (far_i8_wanted ? 40 : 56) ? 6 : 0, G = 4;
     if (const char* env = getenv("DISTBO_POTRF_FAR")) W = atoi(env);
     if (const char* env = getenv("DISTBO_POTRF_FARG")) G = atoi(env);
     if (W >= 2 && G >= 2 && nb >= 3 * G + W) {
