@@ -603,6 +603,19 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
   const bool overlap = nchunks > 1 && n_pad < overlap_below && !getenv("DISTBO_I8_NOOVERLAP");
   cudaStream_t s2 = st;
   cudaEvent_t evK[2] = {nullptr, nullptr}, evS[2] = {nullptr, nullptr}, ev0 = nullptr;
+  struct SideGuard {   // releases the side stream and its events on every way out (the runtime defers the
+    cudaStream_t* s;   // destruction until the enqueued work has drained)
+    cudaStream_t main;
+    cudaEvent_t *k, *sv, *e0;
+    ~SideGuard() {
+      for (int b = 0; b < 2; ++b) {
+        if (k[b]) cudaEventDestroy(k[b]);
+        if (sv[b]) cudaEventDestroy(sv[b]);
+      }
+      if (*e0) cudaEventDestroy(*e0);
+      if (*s != main) cudaStreamDestroy(*s);
+    }
+  } side_guard{&s2, st, evK, evS, &ev0};
   if (overlap) {
     DB_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
     for (int b = 0; b < 2; ++b) {
@@ -676,14 +689,6 @@ extern "C" int distbo_score_i8_f64(const int8_t* W8, const double* rowscale, con
                                         (long long*)best_idx);
     DB_CHECK_LAUNCH();
     first = 0;
-  }
-  if (overlap) {
-    for (int b = 0; b < 2; ++b) {
-      cudaEventDestroy(evK[b]);
-      cudaEventDestroy(evS[b]);
-    }
-    cudaEventDestroy(ev0);
-    cudaStreamDestroy(s2);
   }
   return DISTBO_OK;
 }
