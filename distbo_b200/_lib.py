@@ -31,6 +31,7 @@ SIGNATURES = {
     "distbo_embed_f32_on_tensor_cores": (_i, [_i, _i, _i, _i, _i, _i]),
     "distbo_embed_workspace": (_i64, [_i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "distbo_py_shuffle_i64": (_i, [_vp, _vp, _vp, _i64]),
+    "distbo_gather_rows": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "distbo_task_gram_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "distbo_scale_theta_f64": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "distbo_gram_f64": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _d, _vp, _vp]),

@@ -57,3 +57,38 @@ extern "C" int distbo_py_shuffle_i64(uint32_t* mt_state, int32_t* mt_index, int6
   }
   return DISTBO_OK;
 }
+
+
+// Mini-batch gather on the device: dst[r, :] = src[idx[r], :] for rows of `row_bytes` bytes (a multiple of 8; 16-byte
+// pieces when the pitch allows).  Replaces torch.index_select in the captured training step (train/gp_utils.py:28-104
+// draws the rows on the host; the copy of the selected rows is the device part).
+namespace {
+template <typename V>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const V* __restrict__ src, const int64_t* __restrict__ idx,
+                                                          int64_t n_rows, int pieces, V* __restrict__ dst) {
+  const int64_t total = n_rows * pieces;
+  for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (int64_t)gridDim.x * 256) {
+    const int64_t r = g / pieces;
+    const int c = (int)(g - r * pieces);
+    dst[r * pieces + c] = src[idx[r] * pieces + c];
+  }
+}
+}  // namespace
+
+extern "C" int distbo_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, int64_t n_rows, void* dst,
+                                  void* stream) {
+  if (!src || !idx || !dst || row_bytes <= 0 || row_bytes % 8 || n_rows < 0) return DISTBO_EARG;
+  if (n_rows == 0) return DISTBO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool v16 = row_bytes % 16 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0;
+  const int pieces = (int)(row_bytes / (v16 ? 16 : 8));
+  int64_t blocks = (n_rows * pieces + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (v16)
+    gather_rows_kernel<uint4><<<(int)blocks, 256, 0, st>>>((const uint4*)src, idx, n_rows, pieces, (uint4*)dst);
+  else
+    gather_rows_kernel<unsigned long long><<<(int)blocks, 256, 0, st>>>((const unsigned long long*)src, idx, n_rows,
+                                                                         pieces, (unsigned long long*)dst);
+  DB_CHECK_LAUNCH();
+  return DISTBO_OK;
+}

@@ -425,8 +425,12 @@ class gp_regressor(object):
         elif sampler.constant:
             e.loss_and_grad(self._full[0], self._full[1], self._full[2], size_ratio=self._ratio)
         else:
-            torch.index_select(self._full[0], 0, self._gather_dev, out=self._bX)
-            torch.index_select(self._full[1], 0, self._gather_dev, out=self._bY)
+            L = _eng._lib
+            for src, dst in ((self._full[0], self._bX), (self._full[1], self._bY)):
+                assert src.is_contiguous() and dst.is_contiguous() and src.shape[1] == dst.shape[1]
+                L.check(e.lib.distbo_gather_rows(L.ptr(src), src.shape[1] * src.element_size(),
+                                                 L.ptr(self._gather_dev), int(self._gather_dev.numel()),
+                                                 L.ptr(dst), _eng._stream()), "distbo_gather_rows")
             e.loss_and_grad(self._bX, self._bY, self._batch_off, size_ratio=self._ratio)
         ctrl = self._ctrl
         e.adam_step(self._lr, clip_norm=self._clip, lr_t_dev=self._lrt_dev,

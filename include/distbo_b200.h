@@ -286,6 +286,10 @@ int64_t distbo_trtri_i8_workspace(int n_pad);
 int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_pad, int min_rows, const int32_t* sched,
                         double* ws, void* stream);
 
+/* Mini-batch gather: dst[r, :] = src[idx[r], :], rows of row_bytes bytes (multiple of 8), idx int64 on the device.
+ * The device part of loop_batches (train/gp_utils.py:28-104); capture-safe. */
+int distbo_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, int64_t n_rows, void* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

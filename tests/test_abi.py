@@ -74,7 +74,7 @@ def test_sass_is_sm100a_with_fp64_tensor_ops():
     # with accumulators in tensor memory (UTCIMMA, the second MMA of a digit re-using the A tile from the
     # collector), tensor-memory read-back (LDTM), no legacy tensor instruction
     bodies = [b for b in per_fn if "15score_i8_kernel" in b.split("\n", 1)[0]]
-    assert len(bodies) == 2            # <0> scoring epilogue, <1> store epilogue
+    assert len(bodies) == 3            # <0> scoring epilogue (score.cu), <1> store epilogue (inverse_i8.cu, chol.cu)
     for b in bodies:
         assert b.count("UTCIMMA") == 20 and "A_KEEP" in b and "A_REUSE" in b
         assert b.count("UTMALDG.3D") == 3 and "LDTM" in b and "UTCBAR" in b
