@@ -266,7 +266,10 @@ __global__ void __launch_bounds__(256) i8_kexp_kernel(const double* __restrict__
 // digit planes of the K_* chunk: K8[s][c][i] (i contiguous), zero on pad rows / pad candidates.
 // CTA = KST_CAND candidates; a thread takes four consecutive observations at a time (32-bit stores per plane).
 template <int D>
-__global__ void __launch_bounds__(256, 2) i8_kst_kernel(const double* __restrict__ theta_s,
+#ifndef KST_MINB
+#define KST_MINB 2
+#endif
+__global__ void __launch_bounds__(256, KST_MINB) i8_kst_kernel(const double* __restrict__ theta_s,
                                                         const double* __restrict__ sqnorm, int N, int n_pad, int d,
                                                         const double* __restrict__ log_bw,
                                                         const double* __restrict__ kvec,
@@ -315,7 +318,11 @@ __global__ void __launch_bounds__(256, 2) i8_kst_kernel(const double* __restrict
 #pragma unroll
         for (int k = 0; k < D; ++k) xi[D <= 8 ? u : 0][D <= 8 ? k : 0] = (k < d) ? theta_s[(size_t)(i4 + u) * d + k] : 0.0;
     }
-#pragma unroll 1
+#ifndef KST_UNROLL
+#define KST_UNROLL 2
+#endif
+    constexpr int kst_unroll = KST_UNROLL;
+#pragma unroll kst_unroll
     for (int q = 0; q < KST_CAND; ++q) {
       double dot[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
