@@ -334,23 +334,22 @@ __global__ void __launch_bounds__(256, KST_MINB) i8_kst_kernel(const double* __r
           else if (k < d) dot[u] += theta_s[(size_t)(i4 + u) * d + k] * yk;
         }
       }
-      unsigned pk[I8_NS];
-#pragma unroll
-      for (int s = 0; s < I8_NS; ++s) pk[s] = 0u;
       const bool cand_ok = c_begin + cl0 + q < M;
+      int dg[4][I8_NS];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const double d2 = -2.0 * dot[u] + sqi[u] + ysq[q];
         double v = (scale * matern32_from_d2(d2)) * kv[u];
         if (i4 + u >= N || !cand_ok) v = 0.0;
-        int dg[I8_NS];
-        digits8(v * fx, dg);
-#pragma unroll
-        for (int s = 0; s < I8_NS; ++s) pk[s] |= (unsigned)(dg[s] & 0xff) << (8 * u);
+        digits8(v * fx, dg[u]);
       }
+      // the low bytes of the four observations' digits, one byte-permute tree per plane
 #pragma unroll
-      for (int s = 0; s < I8_NS; ++s)
-        *reinterpret_cast<unsigned*>(K8 + s * plane + (size_t)(cl0 + q) * n_pad + i4) = pk[s];
+      for (int s = 0; s < I8_NS; ++s) {
+        const unsigned lo = __byte_perm((unsigned)dg[0][s], (unsigned)dg[1][s], 0x0040);
+        const unsigned hi = __byte_perm((unsigned)dg[2][s], (unsigned)dg[3][s], 0x0040);
+        *reinterpret_cast<unsigned*>(K8 + s * plane + (size_t)(cl0 + q) * n_pad + i4) = __byte_perm(lo, hi, 0x5410);
+      }
     }
   }
 }
