@@ -288,9 +288,32 @@ extern "C" int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_
     return DISTBO_ECUDA;
   const int sms = device_sm_count();
   const dim3 cgrid(n_pad / 64, (n_pad + 511) / 512), tgrid(n_pad / 64, n_pad / 64);
+  // The row splits (of L once, of the W22 blocks per level) do not depend on the product that runs before them on the
+  // main stream: they go to a side stream and are joined where their planes are first read (fork / join by events,
+  // capture-safe; stream and events live for this call, their destruction is deferred by the runtime).
+  struct Side {
+    cudaStream_t s = nullptr;
+    std::vector<cudaEvent_t> ev;
+    ~Side() {
+      for (cudaEvent_t e : ev) cudaEventDestroy(e);
+      if (s) cudaStreamDestroy(s);
+    }
+    cudaEvent_t event() {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) ev.push_back(e);
+      return e;
+    }
+  } side;
+  DB_CUDA(cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking));
+  cudaEvent_t ev_fork = side.event(), ev_l = side.event();
+  if (!ev_fork || !ev_l) return DISTBO_ECUDA;
+  DB_CUDA(cudaEventRecord(ev_fork, st));
+  DB_CUDA(cudaStreamWaitEvent(side.s, ev_fork, 0));
   // rows of L, once (k <= i)
-  i8_wsplit_kernel<<<n_pad, 256, 0, st>>>(L, n_pad, L8, rsL, nullptr);
+  i8_wsplit_kernel<<<n_pad, 256, 0, side.s>>>(L, n_pad, L8, rsL, nullptr);
   DB_CHECK_LAUNCH();
+  DB_CUDA(cudaEventRecord(ev_l, side.s));
+  bool l_joined = false;
   const int32_t* cur = sched;
   for (const TriI8Level& l : lv) {
     const int2* cr = reinterpret_cast<const int2*>(cur);
@@ -318,12 +341,23 @@ extern "C" int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_
     DB_CHECK_LAUNCH();
     i8_wtsplit_kernel<<<tgrid, 256, 0, st>>>(W, n_pad, csW, C8, cr, 0);
     DB_CHECK_LAUNCH();
+    // rows of W22 on the side stream, next to the first product (W of the previous level is complete: the side
+    // stream waits for the point the main stream has reached, i.e. behind the previous level's second product)
+    cudaEvent_t ev_lvl = side.event(), ev_r = side.event();
+    if (!ev_lvl || !ev_r) return DISTBO_ECUDA;
+    DB_CUDA(cudaEventRecord(ev_lvl, st));
+    DB_CUDA(cudaStreamWaitEvent(side.s, ev_lvl, 0));
+    i8_wsplit_kernel<<<n_pad, 256, 0, side.s>>>(W, n_pad, R8, rsW, rr);
+    DB_CHECK_LAUNCH();
+    DB_CUDA(cudaEventRecord(ev_r, side.s));
+    if (!l_joined) {
+      DB_CUDA(cudaStreamWaitEvent(st, ev_l, 0));
+      l_joined = true;
+    }
     a.item_off = off1; a.items = it1; a.C = T; a.alpha = 1.0; a.rowscale_a = rsL; a.rowscale = csW;
     score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mL, mLhi, mC, a);
     DB_CHECK_LAUNCH();
-    // rows of W22, columns of T, then W21 = -W22 T
-    i8_wsplit_kernel<<<n_pad, 256, 0, st>>>(W, n_pad, R8, rsW, rr);
-    DB_CHECK_LAUNCH();
+    // columns of T, then W21 = -W22 T
     DB_CUDA(cudaMemsetAsync(csT, 0, sizeof(double) * n_pad, st));
     i8_colmax_kernel<<<cgrid, 256, 0, st>>>(T, n_pad, reinterpret_cast<unsigned long long*>(csT), cr, 1);
     DB_CHECK_LAUNCH();
@@ -331,6 +365,7 @@ extern "C" int distbo_trtri_i8_f64(const double* L, double* W, double* T, int n_
     DB_CHECK_LAUNCH();
     i8_wtsplit_kernel<<<tgrid, 256, 0, st>>>(T, n_pad, csT, T8, cr, 1);
     DB_CHECK_LAUNCH();
+    DB_CUDA(cudaStreamWaitEvent(st, ev_r, 0));
     a.item_off = off2; a.items = it2; a.C = W; a.alpha = -1.0; a.rowscale_a = rsW; a.rowscale = csT;
     score_i8_kernel<1><<<sms, I8_THREADS, I8_SMEM, st>>>(mR, mRhi, mT, a);
     DB_CHECK_LAUNCH();
