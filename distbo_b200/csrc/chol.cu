@@ -651,7 +651,8 @@ extern "C" int distbo_plan_create(int n_pad, void** plan_out) {
     // (N = 5120: 2.86 -> 2.70 ms, 6144: 4.24 -> 3.71 ms; at 4096 the uniform schedule stays faster: 1.91 vs 2.18 ms).
     const bool far_i8_wanted = !(getenv("DISTBO_POTRF_FAR_I8") && atoi(getenv("DISTBO_POTRF_FAR_I8")) == 0) &&
                                n_pad / I8_RB <= I8_MAX_RB;
-    int W = nb >= (far_i8_wanted ? 40 : 56) ? 6 : 0, G = 4;
+    // (window of 5 instead of 6 column blocks once the far updates are cheap: 6.35 -> 6.20 ms at N = 8192)
+    int W = nb >= (far_i8_wanted ? 40 : 56) ? (far_i8_wanted ? 5 : 6) : 0, G = 4;
     if (const char* env = getenv("DISTBO_POTRF_FAR")) W = atoi(env);
     if (const char* env = getenv("DISTBO_POTRF_FARG")) G = atoi(env);
     if (W >= 2 && G >= 2 && nb >= 3 * G + W) {
