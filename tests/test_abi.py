@@ -110,3 +110,26 @@ def test_dimension_limits_are_reported():
         NetSpec(7, 1, 20, 10, 20, 17, y_mode=1)
     with pytest.raises(ValueError):
         NetSpec(7, 1, 20, 10, y_mode=5)
+
+
+def test_digit_plane_planning_entry_points_are_pure_host():
+    """Work-list sizes and level selection of the tcgen05 inverse products need no device (the plan functions that
+    upload them do): sizes grow with n_pad, the int8 route of the triangular inverse starts where the halving tree's
+    blocks reach min_rows, bad arguments are refused."""
+    from distbo_b200 import _lib
+    lib = _lib.load()
+    assert lib.distbo_trtri_i8_first_level(8192, 1024) == 4      # heights 1..3 merge 128/256/512-row blocks
+    assert lib.distbo_trtri_i8_first_level(8192, 128) == 1
+    assert lib.distbo_trtri_i8_first_level(2560, 1024) == 5      # 20 blocks: 10 + 10 is the first split >= 1024 rows
+    assert lib.distbo_trtri_i8_first_level(1000, 1024) == -1     # not a multiple of 128
+    w1, w2 = lib.distbo_trtri_i8_sched_words(4096, 1024), lib.distbo_trtri_i8_sched_words(8192, 1024)
+    assert 0 < w1 < w2
+    assert lib.distbo_trtri_i8_sched_words(8192, 64) == 0
+    l1, l2 = lib.distbo_lauum_i8_sched_words(2048), lib.distbo_lauum_i8_sched_words(8192)
+    assert 0 < l1 < l2 and lib.distbo_lauum_i8_sched_words(100) == 0
+    # items of LAUUM: sum_ib 2 (ib + 1) (128-row tile, 64-row block) pairs, 4 words each, + offsets
+    nb = 8192 // 128
+    assert l2 >= 4 * sum(2 * (ib + 1) for ib in range(nb))
+    assert lib.distbo_lauum_i8_workspace(1024) == 1024 * 1024 + 1024
+    assert lib.distbo_trtri_i8_workspace(1024) == 4 * 1024 * 1024 + 4 * 1024
+    assert lib.distbo_score_i8_workspace(1024) > 2 * lib.distbo_score_chunk() * 1024
