@@ -364,7 +364,13 @@ def run_cuda(args):
     barrier()
     hand = gp.refresh_posterior()
     refresh_ms, bcast_ms, bcast_bytes = hand["refresh_ms"], hand["bcast_ms"], hand["bytes"]
-    refresh_ms, bcast_ms = max_over_ranks(refresh_ms), max_over_ranks(bcast_ms)
+    # refresh_ms: the fitting rank's (the others skip the computation).  bcast_ms as each rank sees it runs from "my
+    # part of the computation is enqueued" to "the last tensor has arrived", so on a receiving rank it contains the
+    # wait for the fitting rank's computation: the collective itself is the FITTING rank's figure (the minimum), the
+    # whole hand-off the maximum over ranks of the sum.
+    total_ms = max_over_ranks(refresh_ms + bcast_ms)
+    refresh_ms = max_over_ranks(refresh_ms)
+    bcast_ms = -max_over_ranks(-bcast_ms)
     eng = gp.engine
 
     # ---------------- scoring, candidates resident in HBM
@@ -590,7 +596,8 @@ def run_cuda(args):
                     "h2d_bytes_per_step": bi, "d2h_bytes_per_step": 16 * world,
                     "api": "UtilityFunction.argmax(x_tries_host, gp, y_max) -> gp_regressor.acquire"},
             "gpu_launches": launches, "clocks": clk,
-            "handoff": {"refresh_ms": refresh_ms, "broadcast_ms": bcast_ms, "broadcast_bytes": bcast_bytes,
+            "handoff": {"refresh_ms": refresh_ms, "broadcast_ms": bcast_ms, "total_ms": total_ms,
+                        "broadcast_bytes": bcast_bytes,
                         "api": "gp_regressor.refresh_posterior() = what the first acquire / predict_y after "
                                "maximise_likhd performs on every rank",
                         "what": "fitting rank: embed 65 full sample sets + task Gram + K + POTRF + TRTRI + V; then "
