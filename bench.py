@@ -354,6 +354,59 @@ def run_cuda(args):
         fit_ms = e0.elapsed_time(e1) / kf
         fit = {"fit_ms": fit_ms, "fit_epochs_timed": kf, "fit_mode": "cuda_graph_replay" if gp._graph is not None else "eager",
                "nll": loss, "lkh_var_init": args.lkh_var}
+        # stage breakdown of the fit (eager library calls on the same matrices, CUDA events, mean of 5 after 2
+        # warm-ups; the stages of a graph replay run back to back with the same kernels)
+        eg = gp.engine
+
+        def timed(fn, prep=None, reps=5):
+            tot = 0.0
+            for i in range(reps + 2):
+                if prep is not None:
+                    prep()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    tot += a.elapsed_time(b)
+            return tot / reps
+
+        st = _lib.C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        KEc = eg.KE
+
+        def do_potrf():
+            _lib.check(lib.distbo_potrf_f64(eg.plan, _lib.ptr(eg.K), _lib.ptr(eg.W), _lib.ptr(eg.info), st), "potrf")
+
+        def do_trtri():
+            if eg._trtri_i8 is not None:
+                first, sched, ws = eg._trtri_i8
+                _lib.check(lib.distbo_trtri_range_f64(eg.plan, _lib.ptr(eg.K), _lib.ptr(eg.W), _lib.ptr(eg.Tm), 0, first, st),
+                           "trtri_range")
+                _lib.check(lib.distbo_trtri_i8_f64(_lib.ptr(eg.K), _lib.ptr(eg.W), _lib.ptr(eg.Tm), eg.n_pad,
+                                                   eg.trtri_i8_min_rows, _lib.ptr(sched), _lib.ptr(ws), st), "trtri_i8")
+            else:
+                _lib.check(lib.distbo_trtri_f64(eg.plan, _lib.ptr(eg.K), _lib.ptr(eg.W), _lib.ptr(eg.Tm), st), "trtri")
+
+        def do_lauum():
+            if eg._lauum_i8 is not None:
+                _lib.check(lib.distbo_lauum_i8_f64(_lib.ptr(eg.W), eg.n_pad, _lib.ptr(eg._lauum_i8[0]),
+                                                   _lib.ptr(eg._lauum_i8[1]), _lib.ptr(eg.Tm), st), "lauum_i8")
+            else:
+                _lib.check(lib.distbo_lauum_f64(eg.plan, _lib.ptr(eg.W), _lib.ptr(eg.Tm), st), "lauum")
+
+        n3 = float(eg.n_pad) ** 3 / 3.0
+        t_gram = timed(lambda: eg.build_gram(KEc))
+        t_potrf = timed(do_potrf, prep=lambda: eg.build_gram(KEc))
+        t_trtri = timed(do_trtri)
+        t_lauum = timed(do_lauum)
+        fit["fit_stages_ms"] = {"gram": t_gram, "potrf": t_potrf, "trtri": t_trtri, "lauum": t_lauum,
+                                "rest": fit_ms - (t_gram + t_potrf + t_trtri + t_lauum),
+                                "potrf_tflops_fp64_equiv": n3 / t_potrf / 1e9, "trtri_tflops_fp64_equiv": n3 / t_trtri / 1e9,
+                                "lauum_tflops_fp64_equiv": n3 / t_lauum / 1e9,
+                                "paths": {"potrf_far_updates": "tcgen05 int8 digit planes" if eg.n_pad >= 5120 else "FP64 DMMA",
+                                          "trtri_top_levels": "tcgen05 int8 digit planes" if eg._trtri_i8 is not None else "FP64 DMMA",
+                                          "lauum": "tcgen05 int8 digit planes" if eg._lauum_i8 is not None else "FP64 DMMA"}}
     barrier()
 
     # ---------------- fit -> score hand-off, performed by the product API itself (gp_regressor.refresh_posterior =
